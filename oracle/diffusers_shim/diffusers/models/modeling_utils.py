@@ -1,0 +1,12 @@
+"""ModelMixin stand-in: nn.Module with .dtype/.device (oracle shim, test infrastructure)."""
+import torch
+
+
+class ModelMixin(torch.nn.Module):
+    @property
+    def dtype(self):
+        return next(self.parameters()).dtype
+
+    @property
+    def device(self):
+        return next(self.parameters()).device

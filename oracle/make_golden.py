@@ -1,0 +1,79 @@
+"""TEST INFRASTRUCTURE ONLY (oracle) — generate tests/golden/*.pt from the REFERENCE modules.
+
+Run in the build container (needs /root/reference; cannot run on the GPU box):
+
+    python -m oracle.make_golden
+
+Imports the reference's own ``src/models/unet.py`` UNCHANGED through ``oracle/diffusers_shim``,
+loads the deterministic synthetic state dict (``rcdms_b200.synthetic``), runs fp32 CPU forwards
+and saves small input/output/intermediate tensors.  The committed fixtures pin
+``oracle/unet_ref.py`` (and through it the CUDA path) to the reference implementation.
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = os.environ.get("RCDMS_REFERENCE", "/root/reference")
+
+
+def load_reference_unet(cfg):
+    sys.path.insert(0, os.path.join(ROOT, "oracle", "diffusers_shim"))
+    sys.path.insert(0, REF)
+    sys.path.insert(0, ROOT)
+    from src.models.unet import UNet3DConditionModel  # the reference's class, unmodified
+    init = {k: (list(v) if isinstance(v, tuple) else v) for k, v in cfg.items()}
+    return UNet3DConditionModel.from_config(init)
+
+
+def golden_inputs(cfg, b, f, h, w, L, seed):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn((b, cfg["in_channels"], f, h, w), generator=g)
+    ctx = torch.randn((b * f, L, cfg["cross_attention_dim"]), generator=g)
+    return x, ctx
+
+
+def main():
+    from rcdms_b200.synthetic import synthetic_state_dict
+    from rcdms_b200.unet_spec import full_config, tiny_config
+    out_dir = os.path.join(ROOT, "tests", "golden")
+    os.makedirs(out_dir, exist_ok=True)
+    torch.manual_seed(0)
+    cases = [
+        # name, cfg, (b, f, h, w, L), timestep, taps kept
+        ("tiny_8x8", tiny_config(), (2, 5, 8, 8, 7), 981),
+        ("tiny_16x16", tiny_config(), (2, 5, 16, 16, 85), 501),
+        ("full_8x8", full_config(), (2, 5, 8, 8, 85), 981),
+    ]
+    for name, cfg, (b, f, h, w, L), t in cases:
+        model = load_reference_unet(cfg).eval()
+        sd = synthetic_state_dict(cfg, seed=0)
+        model.load_state_dict(sd, strict=True)
+        x, ctx = golden_inputs(cfg, b, f, h, w, L, seed=1234)
+        taps = {}
+        hooks = []
+        for mod_name in ("conv_in", "down_blocks.0.resnets.0", "down_blocks.0.attentions.0",
+                         "down_blocks.0.motion_modules.0", "down_blocks.0.downsamplers.0", "mid_block",
+                         "up_blocks.0.upsamplers.0", "up_blocks.3.motion_modules.2"):
+            mod = model.get_submodule(mod_name)
+
+            def hook(m, i, o, key=mod_name):
+                o = o[0] if isinstance(o, tuple) else (o.sample if hasattr(o, "sample") else o)
+                taps[key] = o.detach().clone()
+            hooks.append(mod.register_forward_hook(hook))
+        with torch.no_grad():
+            y = model(x, torch.tensor(t), encoder_hidden_states=ctx, return_dict=False)[0]
+        for hk in hooks:
+            hk.remove()
+        keep = {k: v[:1, :8, :, :4, :4].contiguous() for k, v in taps.items()}  # small corner of each tap
+        torch.save(dict(shape=(b, f, h, w, L), timestep=t, input_seed=1234, weight_seed=0,
+                        out=y.contiguous(), taps=keep), os.path.join(out_dir, f"unet_{name}.pt"))
+        print(name, tuple(y.shape), float(y.abs().mean()), float(y.abs().max()))
+        del model, sd
+
+
+if __name__ == "__main__":
+    main()

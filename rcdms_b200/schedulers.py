@@ -1,0 +1,107 @@
+"""Host-side DDIM scheduler with the surface ``RCDMsPipeline`` uses from
+``diffusers.DDIMScheduler`` (0.24.0): ``set_timesteps``, ``timesteps``, ``scale_model_input``,
+``step(...).prev_sample``, ``init_noise_sigma``, ``order``, ``config``/``_internal_dict``
+(reference call sites: ``src/pipelines/RCDMs_pipeline.py:84-109,347,455-456,478,483,497``;
+constructed at ``stage2_batchtest_rcdms_model.py:247`` from ``configs/testing.yaml:18-21``).
+
+The schedule tables (betas, alpha-bar, timestep indices) are host integers/fp32 — they are
+what must be bit-identical to the reference.  The per-step arithmetic on latents normally
+runs in the fused CUDA kernel (``rcdm_ddim_cfg_step``); ``step`` here is the same formula on
+torch tensors for API completeness (CPU tensors, callbacks, non-fused use).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Optional
+
+import numpy as np
+import torch
+
+
+class FrozenConfig(dict):
+    """dict with attribute access (the pipeline reads ``scheduler.config.steps_offset``)."""
+
+    def __getattr__(self, k):
+        try:
+            return self[k]
+        except KeyError as e:
+            raise AttributeError(k) from e
+
+
+@dataclass
+class DDIMStepOutput:
+    prev_sample: torch.Tensor
+    pred_original_sample: Optional[torch.Tensor] = None
+
+
+class DDIMScheduler:
+    order = 1
+
+    def __init__(self, num_train_timesteps: int = 1000, beta_start: float = 0.0001, beta_end: float = 0.02,
+                 beta_schedule: str = "linear", trained_betas=None, clip_sample: bool = True,
+                 set_alpha_to_one: bool = True, steps_offset: int = 0, prediction_type: str = "epsilon",
+                 timestep_spacing: str = "leading"):
+        if trained_betas is not None:
+            betas = torch.tensor(trained_betas, dtype=torch.float32)
+        elif beta_schedule == "linear":
+            betas = torch.linspace(beta_start, beta_end, num_train_timesteps, dtype=torch.float32)
+        elif beta_schedule == "scaled_linear":
+            betas = torch.linspace(beta_start ** 0.5, beta_end ** 0.5, num_train_timesteps, dtype=torch.float32) ** 2
+        else:
+            raise NotImplementedError(f"{beta_schedule} is not implemented for {self.__class__}")
+        if prediction_type != "epsilon":
+            raise NotImplementedError("only epsilon prediction is on the RCDMs stage-2 path")
+        if timestep_spacing != "leading":
+            raise NotImplementedError("only 'leading' timestep spacing is on the RCDMs stage-2 path")
+        self.betas = betas
+        self.alphas = 1.0 - betas
+        self.alphas_cumprod = torch.cumprod(self.alphas, dim=0)
+        self.final_alpha_cumprod = torch.tensor(1.0) if set_alpha_to_one else self.alphas_cumprod[0]
+        self.init_noise_sigma = 1.0
+        self._internal_dict = FrozenConfig(
+            num_train_timesteps=num_train_timesteps, beta_start=beta_start, beta_end=beta_end,
+            beta_schedule=beta_schedule, trained_betas=trained_betas, clip_sample=clip_sample,
+            set_alpha_to_one=set_alpha_to_one, steps_offset=steps_offset, prediction_type=prediction_type,
+            timestep_spacing=timestep_spacing)
+        self.num_inference_steps: Optional[int] = None
+        self.timesteps = torch.arange(num_train_timesteps - 1, -1, -1, dtype=torch.int64)
+
+    @property
+    def config(self) -> FrozenConfig:
+        return self._internal_dict
+
+    def scale_model_input(self, sample: torch.Tensor, timestep=None) -> torch.Tensor:
+        return sample
+
+    def set_timesteps(self, num_inference_steps: int, device=None) -> None:
+        n_train = self.config.num_train_timesteps
+        if num_inference_steps > n_train:
+            raise ValueError(f"`num_inference_steps`: {num_inference_steps} cannot be larger than {n_train}")
+        self.num_inference_steps = num_inference_steps
+        ratio = n_train // num_inference_steps
+        ts = np.flip(np.arange(num_inference_steps, dtype=np.int64) * ratio).copy() + self.config.steps_offset
+        self.timesteps = torch.from_numpy(ts).to(device)
+
+    def step_coefficients(self, timestep: int):
+        """(alpha_bar_t, alpha_bar_prev) as fp32 python floats for one step — what the fused
+        CUDA step consumes.  Index arithmetic identical to diffusers' ``step``."""
+        if self.num_inference_steps is None:
+            raise ValueError("Number of inference steps is 'None', you need to run 'set_timesteps' first")
+        prev = int(timestep) - self.config.num_train_timesteps // self.num_inference_steps
+        a_t = self.alphas_cumprod[int(timestep)]
+        a_prev = self.alphas_cumprod[prev] if prev >= 0 else self.final_alpha_cumprod
+        return float(a_t), float(a_prev)
+
+    def step(self, model_output: torch.Tensor, timestep, sample: torch.Tensor, eta: float = 0.0,
+             use_clipped_model_output: bool = False, generator=None, variance_noise=None,
+             return_dict: bool = True):
+        if eta != 0.0:
+            raise NotImplementedError("eta > 0 (stochastic DDIM) is not on the RCDMs path (eta=0.0 default)")
+        a_t, a_prev = self.step_coefficients(timestep)
+        x0 = (sample - (1.0 - a_t) ** 0.5 * model_output) / a_t ** 0.5
+        if self.config.clip_sample:
+            x0 = x0.clamp(-1.0, 1.0)
+        prev_sample = a_prev ** 0.5 * x0 + (1.0 - a_prev) ** 0.5 * model_output
+        if not return_dict:
+            return (prev_sample,)
+        return DDIMStepOutput(prev_sample=prev_sample, pred_original_sample=x0)

@@ -1,0 +1,87 @@
+"""Deterministic synthetic weights and PororoSV-shaped inputs.
+
+No pretrained weights, datasets or checkpoints exist offline, so tests and ``bench.py`` run
+on synthetic tensors that depend only on (entry name, shape, seed): the reference modules
+in the build container (golden generation) and this package on the GPU box therefore see
+bit-identical fp32 values without sharing a 5 GB file.
+"""
+from __future__ import annotations
+
+import math
+import zlib
+from typing import Dict, Iterable, Tuple
+
+import torch
+
+from .unet_spec import BUFFER_SUFFIX, state_dict_spec
+
+
+def _gen(name: str, seed: int) -> torch.Generator:
+    g = torch.Generator(device="cpu")
+    g.manual_seed((zlib.crc32(name.encode()) ^ (seed * 0x9E3779B1)) & 0x7FFFFFFF)
+    return g
+
+
+def positional_encoding(max_len: int, d_model: int) -> torch.Tensor:
+    """``PositionalEncoding.pe`` buffer, ``src/models/motion_module.py:256-262``."""
+    position = torch.arange(max_len).unsqueeze(1)
+    div_term = torch.exp(torch.arange(0, d_model, 2) * (-math.log(10000.0) / d_model))
+    pe = torch.zeros(1, max_len, d_model)
+    pe[0, :, 0::2] = torch.sin(position * div_term)
+    pe[0, :, 1::2] = torch.cos(position * div_term)
+    return pe
+
+
+def synthetic_tensor(name: str, shape: Tuple[int, ...], seed: int = 0) -> torch.Tensor:
+    """fp32 CPU tensor for one state-dict entry.
+
+    Linear/conv weights and all biases: U(-1/sqrt(fan_in), 1/sqrt(fan_in)) (PyTorch's default
+    scale, so activations stay O(1) through the 100+ layers); norm scales 1 + 0.2 U(-1,1) and
+    norm shifts 0.2 U(-1,1) so affine parameters are exercised; ``pe`` from its closed form.
+    The zero-initialised temporal ``proj_out`` (``motion_module.py:84-85``) is deliberately
+    NOT zero here, otherwise the 20 motion modules would be identities and untested.
+    """
+    if name.endswith(BUFFER_SUFFIX):
+        return positional_encoding(shape[1], shape[2])
+    g = _gen(name, seed)
+    u = torch.rand(shape, generator=g, dtype=torch.float32) * 2 - 1
+    is_norm = any(k in name for k in (".norm", "norms.", "ff_norm", "prior_norm", "conv_norm_out"))
+    if is_norm:
+        return 1 + 0.2 * u if name.endswith("weight") else 0.2 * u
+    if name.endswith("weight"):
+        fan_in = 1
+        for s in shape[1:]:
+            fan_in *= s
+    else:  # bias: fan-in of the matching weight is unknown here; a fixed small scale is enough
+        fan_in = 256
+    return u / math.sqrt(fan_in)
+
+
+def synthetic_state_dict(cfg: Dict, seed: int = 0, dtype=torch.float32, device="cpu",
+                         names: Iterable[str] = None) -> Dict[str, torch.Tensor]:
+    out = {}
+    want = set(names) if names is not None else None
+    for name, shape in state_dict_spec(cfg):
+        if want is not None and name not in want:
+            continue
+        out[name] = synthetic_tensor(name, shape, seed).to(device=device, dtype=dtype)
+    return out
+
+
+def synthetic_clip_inputs(clip_index: int, h: int, w: int, ctx_len: int = 85, ctx_dim: int = 768,
+                          frames: int = 5, seed: int = 42) -> Dict[str, torch.Tensor]:
+    """Per-clip inputs of the denoise loop (fp32, CPU), generator seed ``seed + clip_index``
+    (42 = the reference's ``--seed_number`` default, ``stage2_batchtest_rcdms_model.py:426``).
+
+    latents ~ N(0,1) (1,4,f,h,w); masked_latents = 0.18215 N(0,1) (stand-in for the VAE posterior
+    sample, ``RCDMs_pipeline.py:429-431``); mask = [1,0,0,0,0] per frame ('continue' mode,
+    ``stage2_batchtest_rcdms_model.py:286-288``); ctx ~ N(0,1) (2f, L, ctx_dim).
+    """
+    g = torch.Generator(device="cpu")
+    g.manual_seed(seed + clip_index)
+    latents = torch.randn((1, 4, frames, h, w), generator=g)
+    masked_latents = 0.18215 * torch.randn((1, 4, frames, h, w), generator=g)
+    mask = torch.zeros((1, 1, frames, h, w))
+    mask[:, :, 0] = 1.0
+    ctx = torch.randn((2 * frames, ctx_len, ctx_dim), generator=g)
+    return dict(latents=latents, masked_latents=masked_latents, mask=mask, ctx=ctx)
