@@ -1,0 +1,156 @@
+/* librcdm_b200 — C ABI of the B200-native RCDMs stage-2 denoise hot path.
+ *
+ * The reference (muzishen/RCDMs) is pure Python and has no native boundary; these entry points are what a
+ * maintainer binds (ctypes) behind the reference's own module API:
+ *
+ *   rcdm_unet_*          replaces  UNet3DConditionModel            src/models/unet.py:37-508
+ *                                  (construction :40-251, load_state_dict via stage2_batchtest_rcdms_model.py:243,
+ *                                   forward :322-462 and everything below it: unet_blocks.py, resnet.py,
+ *                                   attention.py, motion_module.py)
+ *   rcdm_ddim_cfg_step   replaces  CFG combine + DDIMScheduler.step + next-input concat
+ *                                  src/pipelines/RCDMs_pipeline.py:482-497
+ *   rcdm_denoise_loop    replaces  the whole loop            src/pipelines/RCDMs_pipeline.py:476-503
+ *   rcdm_{gemm,conv3x3,groupnorm,layernorm,flash_attn,temporal_attn}
+ *                        per-kernel entry points (the finest operator slot the reference defines is the
+ *                        xformers attention hook, src/models/attention.py:153-156,244-251; rcdm_flash_attn sits
+ *                        exactly there) so every kernel can be parity-tested and profiled alone.
+ *
+ * Conventions: plain pointers and sizes only; every function returns 0 on success and a non-zero status on
+ * failure (message via rcdm_last_error()); no C++ exception crosses the ABI.  All pointers named *_dev are
+ * device pointers owned by the caller (torch tensors) and must stay alive for the call; work is enqueued on the
+ * caller's CUDA stream (pass torch.cuda.current_stream().cuda_stream) without host synchronisation, so calls
+ * can be captured into a CUDA graph.  One handle per (process, device); handles are not thread-safe.
+ * There is NO CPU fallback: without a CUDA device every compute entry point fails.
+ */
+#ifndef RCDM_H_
+#define RCDM_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define RCDM_API __attribute__((visibility("default")))
+#else
+#define RCDM_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RCDM_DT_F32 0
+#define RCDM_DT_F16 1
+#define RCDM_DT_BF16 2
+
+#define RCDM_MAX_BLOCKS 4
+
+/* UNet3DConditionModel configuration: the subset of src/models/unet.py:40-92 the stage-2 path exercises. */
+typedef struct rcdm_unet_config {
+  int in_channels;                          /* 9  (unet.py:477) */
+  int out_channels;                         /* 4 */
+  int num_blocks;                           /* len(block_out_channels) = 4 */
+  int block_out_channels[RCDM_MAX_BLOCKS];  /* 320, 640, 1280, 1280 */
+  int down_has_attn[RCDM_MAX_BLOCKS];       /* CrossAttnDownBlock3D -> 1, DownBlock3D -> 0 */
+  int up_has_attn[RCDM_MAX_BLOCKS];         /* UpBlock3D -> 0, CrossAttnUpBlock3D -> 1 */
+  int layers_per_block;                     /* 2 */
+  int attention_heads;                      /* 8 ("attention_head_dim" is used as the head COUNT, unet_blocks.py:345) */
+  int cross_attention_dim;                  /* 768 */
+  int norm_num_groups;                      /* 32 */
+  float norm_eps;                           /* 1e-5 */
+  int flip_sin_to_cos;                      /* 1 */
+  float freq_shift;                         /* 0 */
+  int use_motion_module;                    /* 1 */
+  int motion_down[RCDM_MAX_BLOCKS];         /* motion module after every resnet of down block i */
+  int motion_up[RCDM_MAX_BLOCKS];
+  int motion_mid;                           /* 0 */
+  int motion_heads;                         /* 8 */
+  int motion_attn_blocks;                   /* 2 ("Temporal_Self","Temporal_Self") */
+  int motion_max_len;                       /* 5 */
+  int compute_dtype;                        /* RCDM_DT_F16 or RCDM_DT_BF16 */
+} rcdm_unet_config;
+
+typedef struct rcdm_unet rcdm_unet;
+
+/* ---- library ---- */
+RCDM_API const char* rcdm_version(void);
+RCDM_API const char* rcdm_last_error(void);            /* thread-local message of the last failing call */
+RCDM_API int rcdm_device_count(void);                  /* number of visible CUDA devices (0 => nothing can run) */
+RCDM_API uint64_t rcdm_kernel_launches(void);          /* kernels launched by this library since load (bench evidence) */
+
+/* ---- model life cycle (host only until the first weight arrives) ---- */
+RCDM_API int rcdm_unet_create(const rcdm_unet_config* cfg, rcdm_unet** out);
+RCDM_API void rcdm_unet_destroy(rcdm_unet* h);
+/* state-dict surface: the reference's names and shapes (1 286 entries at the shipped config) */
+RCDM_API int rcdm_unet_num_weights(const rcdm_unet* h);
+RCDM_API int rcdm_unet_weight_info(const rcdm_unet* h, int index, char* name_buf, int name_buf_len, int64_t* dims /*[4]*/,
+                          int* ndim);
+/* copy + repack one state-dict entry (contiguous, reference layout, dtype RCDM_DT_*) into the kernel layout */
+RCDM_API int rcdm_unet_load_weight(rcdm_unet* h, const char* name, const void* data_dev, int dtype, const int64_t* dims,
+                          int ndim, void* stream);
+RCDM_API int rcdm_unet_weights_missing(const rcdm_unet* h); /* entries not loaded yet (0 => ready) */
+
+/* ---- forward: sample (b, in_ch, f, h, w) NCFHW, ctx (b*f, L, cross_dim), out (b, out_ch, f, h, w) ---- */
+/* (re)plan for a problem size: allocates the activation workspace and encodes all TMA descriptors */
+RCDM_API int rcdm_unet_prepare(rcdm_unet* h, int batch, int frames, int height, int width, int ctx_len);
+RCDM_API size_t rcdm_unet_workspace_bytes(const rcdm_unet* h);
+/* timestep: read from device int64 *timestep_dev when non-null (the reference passes a 0-dim cuda int64 tensor,
+ * RCDMs_pipeline.py:480,488), else timestep_host. */
+RCDM_API int rcdm_unet_forward(rcdm_unet* h, const void* sample_dev, int sample_dtype, const int64_t* timestep_dev,
+                      double timestep_host, const void* ctx_dev, int ctx_dtype, void* out_dev, int out_dtype,
+                      void* stream);
+/* debug: copy an internal activation recorded during the last forward ("conv_in", "down_blocks.0.resnets.0", ...)
+ * as fp32 channels-last tokens [rows, C]; returns rows*C written (<= capacity), negative on error. */
+RCDM_API int64_t rcdm_unet_read_tap(rcdm_unet* h, const char* name, float* out_dev, int64_t capacity, int* rows, int* channels,
+                           void* stream);
+RCDM_API int rcdm_unet_enable_taps(rcdm_unet* h, int enable); /* keep tapped activations alive (costs memory) */
+
+/* ---- fused CFG + DDIM step (+ next 9-channel UNet input).  All tensors NCFHW.  eta = 0. ----
+ * eps (2B|B, 4, f, h, w); latents_f32 (B,4,f,h,w) fp32 master copy updated in place; latents_out optional copy in
+ * latents_dtype; next_input (2B|B, 9, f, h, w) optional; mask (B,1,f,h,w); masked_latents (B,4,f,h,w). */
+RCDM_API int rcdm_ddim_cfg_step(const void* eps_dev, int eps_dtype, float* latents_f32_dev, void* latents_out_dev,
+                       int latents_dtype, void* next_input_dev, int next_dtype, const void* mask_dev, int mask_dtype,
+                       const void* masked_latents_dev, int masked_dtype, int clips, int frames, int height, int width,
+                       int do_cfg, float guidance_scale, float alpha_bar_t, float alpha_bar_prev, void* stream);
+
+/* ---- whole denoise loop for `clips` clips batched on this GPU (RCDMs_pipeline.py:476-503) ----
+ * latents (clips,4,f,h,w), mask (clips,1,f,h,w), masked_latents (clips,4,f,h,w), ctx (clips*2*f | clips*f, L, D)
+ * ordered [uncond clips..., cond clips...] like torch.cat([x]*2).  timesteps/alpha tables are host arrays of
+ * length num_steps (alpha_bar_prev = 1.0 for the final step).  The step (UNet + CFG + DDIM) is captured once into
+ * a CUDA graph and replayed num_steps times when use_graph != 0.  Result in latents_out (latents_dtype). */
+RCDM_API int rcdm_denoise_loop(rcdm_unet* h, const void* latents_dev, int latents_dtype, const void* mask_dev, int mask_dtype,
+                      const void* masked_latents_dev, int masked_dtype, const void* ctx_dev, int ctx_dtype,
+                      int clips, int frames, int height, int width, int ctx_len, const int64_t* timesteps_host,
+                      const float* alpha_bar_t_host, const float* alpha_bar_prev_host, int num_steps,
+                      float guidance_scale, int use_graph, void* latents_out_dev, void* stream);
+
+/* ---- single kernels (16-bit storage dtype RCDM_DT_F16/BF16, fp32 accumulation) ---- */
+/* out[M,N] = A[M,K] W[N,K]^T (+bias fp32[N]) (+residual[M,N]); geglu: W/bias rows packed by rcdm_pack_geglu */
+RCDM_API int rcdm_gemm(int dtype, const void* a_dev, const void* w_dev, const float* bias_dev, const void* residual_dev,
+              void* out_dev, int M, int N, int K, int geglu, int tile_n /*0 = auto*/, int simple, void* stream);
+RCDM_API int rcdm_pack_geglu(int dtype, const void* w_dev, const float* bias_dev, void* w_out_dev, float* bias_out_dev, int N,
+                    int K, void* stream);
+/* 3x3 conv, pad 1, stride 1|2, channels-last x [n,h,w,cin], w_packed [cout, 9*cin] (tap-major) */
+RCDM_API int rcdm_conv3x3(int dtype, const void* x_dev, const void* w_packed_dev, const float* bias_dev,
+                 const void* residual_dev, void* out_dev, int n, int h, int w, int cin, int cout, int stride,
+                 int simple, void* stream);
+RCDM_API int rcdm_pack_conv3x3(int dtype, const void* w_dev /*[cout,cin,3,3] same dtype*/, void* w_out_dev, int cout, int cin,
+                      void* stream);
+/* GroupNorm(+SiLU) over rows_per_stat rows x (C/groups) channels of tokens [rows, C]; scratch >= rcdm_groupnorm_scratch_bytes */
+RCDM_API size_t rcdm_groupnorm_scratch_bytes(int rows, int rows_per_stat, int groups);
+RCDM_API int rcdm_groupnorm(int dtype, const void* x_dev, const float* gamma_dev, const float* beta_dev, void* out_dev,
+                   int rows, int channels, int groups, int rows_per_stat, float eps, int silu, void* scratch_dev,
+                   void* stream);
+RCDM_API int rcdm_layernorm(int dtype, const void* x_dev, const float* gamma_dev, const float* beta_dev, void* out_dev,
+                   int rows, int channels, float eps, const float* pe_dev, int rows_per_frame, int frames,
+                   void* stream);
+/* softmax(q k^T / sqrt(d)) v; q [batch*S_q, ldq], k/v [batch*S_kv, ldkv], head h at columns [h*d, h*d+d) */
+RCDM_API int rcdm_flash_attn(int dtype, const void* q_dev, int ldq, const void* k_dev, const void* v_dev, int ldkv,
+                    void* out_dev, int ldo, int batch, int heads, int S_q, int S_kv, int d, int simple, void* stream);
+/* attention over the frame axis: qkv [(b f hw), 3C] -> out [(b f hw), C] */
+RCDM_API int rcdm_temporal_attn(int dtype, const void* qkv_dev, void* out_dev, int batch, int frames, int hw, int heads, int d,
+                       void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RCDM_H_ */

@@ -1,0 +1,561 @@
+// extern "C" surface of librcdm_b200.so (declared in include/rcdm.h).  No C++ exception crosses this boundary.
+#include <cmath>
+#include <cstring>
+#include <mutex>
+
+#include "elementwise.cuh"
+#include "internal.h"
+
+using namespace rcdm;
+
+#define API_BEGIN try {
+#define API_END                                             \
+  }                                                         \
+  catch (const std::exception& e) { return set_err(e.what()); } \
+  catch (...) { return set_err("unknown C++ exception"); }
+
+#define CUDA_OK(expr)                                                                          \
+  do {                                                                                         \
+    cudaError_t _e = (expr);                                                                   \
+    if (_e != cudaSuccess) return set_err(std::string(#expr) + ": " + cudaGetErrorString(_e)); \
+  } while (0)
+
+static int check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_err(std::string(what) + ": " + cudaGetErrorString(e));
+  return 0;
+}
+
+static int ensure_device_ready() {
+  static std::once_flag once;
+  static std::string err;
+  static bool ok = false;
+  std::call_once(once, [&]() {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+      (void)cudaGetLastError();
+      err = "no CUDA device: librcdm_b200 has no CPU fallback";
+      return;
+    }
+    ok = gemm_setup_attributes(&err) && attn_setup_attributes(&err);
+  });
+  return ok ? 0 : set_err(err);
+}
+
+static inline int grid_for(size_t total, int block, int cap = 148 * 16) {
+  size_t g = (total + block - 1) / block;
+  return (int)(g < (size_t)cap ? (g ? g : 1) : cap);
+}
+static bool dt16(int dt) { return dt == RCDM_DT_F16 || dt == RCDM_DT_BF16; }
+
+static __global__ void tap_to_f32_kernel(const void* src, int dt, float* dst, size_t n) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    dst[i] = load_any(src, dt, i);
+}
+static void tap_to_f32(const void* src, int dt, float* dst, size_t n, cudaStream_t st) {
+  tap_to_f32_kernel<<<grid_for(n, 256), 256, 0, st>>>(src, dt, dst, n);
+}
+
+extern "C" {
+
+const char* rcdm_version(void) { return "rcdm_b200 0.1 (sm_100a; tcgen05/TMA)"; }
+const char* rcdm_last_error(void) { return g_err.c_str(); }
+int rcdm_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    (void)cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+uint64_t rcdm_kernel_launches(void) { return g_launches.load(); }
+
+int rcdm_unet_create(const rcdm_unet_config* cfg, rcdm_unet** out) {
+  API_BEGIN
+  return unet_create(cfg, out);
+  API_END
+}
+void rcdm_unet_destroy(rcdm_unet* h) {
+  try {
+    unet_destroy(h);
+  } catch (...) {
+  }
+}
+int rcdm_unet_num_weights(const rcdm_unet* h) { return h ? (int)h->slots.size() : -1; }
+int rcdm_unet_weight_info(const rcdm_unet* h, int index, char* name_buf, int name_buf_len, int64_t* dims, int* ndim) {
+  API_BEGIN
+  if (!h || index < 0 || index >= (int)h->slots.size()) return set_err("weight index out of range");
+  const Slot& s = h->slots[index];
+  if (name_buf && name_buf_len > 0) {
+    strncpy(name_buf, s.name.c_str(), name_buf_len - 1);
+    name_buf[name_buf_len - 1] = 0;
+  }
+  if (dims)
+    for (int i = 0; i < 4; ++i) dims[i] = s.dims[i];
+  if (ndim) *ndim = s.ndim;
+  return 0;
+  API_END
+}
+int rcdm_unet_load_weight(rcdm_unet* h, const char* name, const void* data_dev, int dtype, const int64_t* dims,
+                          int ndim, void* stream) {
+  API_BEGIN
+  return unet_load_weight(h, name, data_dev, dtype, dims, ndim, stream);
+  API_END
+}
+int rcdm_unet_weights_missing(const rcdm_unet* h) {
+  if (!h) return -1;
+  int n = 0;
+  for (auto& s : h->slots) n += s.loaded ? 0 : 1;
+  return n;
+}
+int rcdm_unet_prepare(rcdm_unet* h, int batch, int frames, int height, int width, int ctx_len) {
+  API_BEGIN
+  return unet_prepare(h, batch, frames, height, width, ctx_len);
+  API_END
+}
+size_t rcdm_unet_workspace_bytes(const rcdm_unet* h) { return h ? h->ws_bytes : 0; }
+int rcdm_unet_enable_taps(rcdm_unet* h, int enable) {
+  if (!h) return set_err("null handle");
+  if (h->taps_enabled != (enable != 0)) {
+    h->taps_enabled = enable != 0;
+    h->planned = false;  // force a re-plan
+  }
+  return 0;
+}
+
+int rcdm_unet_forward(rcdm_unet* h, const void* sample_dev, int sample_dtype, const int64_t* timestep_dev,
+                      double timestep_host, const void* ctx_dev, int ctx_dtype, void* out_dev, int out_dtype,
+                      void* stream) {
+  API_BEGIN
+  if (!h || !sample_dev || !ctx_dev || !out_dev) return set_err("null argument");
+  if (!h->planned) return set_err("rcdm_unet_forward: call rcdm_unet_prepare first");
+  const int missing = rcdm_unet_weights_missing(h);
+  if (missing) return set_err("rcdm_unet_forward: " + std::to_string(missing) + " state-dict entries not loaded");
+  h->cur_sample = sample_dev;
+  h->cur_sample_dt = sample_dtype;
+  h->cur_t_dev = timestep_dev;
+  h->cur_t_host = (float)timestep_host;
+  h->cur_ctx = ctx_dev;
+  h->cur_ctx_dt = ctx_dtype;
+  h->cur_out = out_dev;
+  h->cur_out_dt = out_dtype;
+  return unet_run(h, true, true, reinterpret_cast<cudaStream_t>(stream));
+  API_END
+}
+
+int64_t rcdm_unet_read_tap(rcdm_unet* h, const char* name, float* out_dev, int64_t capacity, int* rows, int* channels,
+                           void* stream) {
+  try {
+    if (!h || !name) return -(int64_t)set_err("null argument");
+    auto it = h->taps.find(name);
+    if (it == h->taps.end()) return -(int64_t)set_err(std::string("no such tap: ") + name);
+    const TapInfo& t = it->second;
+    if (rows) *rows = t.rows;
+    if (channels) *channels = t.C;
+    const int64_t n = (int64_t)t.rows * t.C;
+    if (!out_dev) return n;
+    if (n > capacity) return -(int64_t)set_err("tap buffer too small");
+    tap_to_f32(h->ws + t.off, h->dt, out_dev, (size_t)n, reinterpret_cast<cudaStream_t>(stream));
+    return n;
+  } catch (...) {
+    return -(int64_t)set_err("exception in rcdm_unet_read_tap");
+  }
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------
+// DDIM step + denoise loop
+// ------------------------------------------------------------------------------------------
+static void ddim_coefs(float abar_t, float abar_prev, float* c) {
+  // fp32 arithmetic like the reference's 0-dim fp32 tensors (scheduling_ddim.step)
+  c[0] = sqrtf(abar_t);
+  c[1] = sqrtf(1.0f - abar_t);
+  c[2] = sqrtf(abar_prev);
+  c[3] = sqrtf(1.0f - abar_prev);
+}
+
+static __global__ void set_timestep_kernel(const int64_t* table, const int* step_idx, int64_t* t_cur) {
+  *t_cur = table[*step_idx];
+}
+
+extern "C" {
+
+int rcdm_ddim_cfg_step(const void* eps_dev, int eps_dtype, float* latents_f32_dev, void* latents_out_dev,
+                       int latents_dtype, void* next_input_dev, int next_dtype, const void* mask_dev, int mask_dtype,
+                       const void* masked_latents_dev, int masked_dtype, int clips, int frames, int height, int width,
+                       int do_cfg, float guidance_scale, float alpha_bar_t, float alpha_bar_prev, void* stream) {
+  API_BEGIN
+  if (!eps_dev || !latents_f32_dev) return set_err("null argument");
+  if (next_input_dev && (!mask_dev || !masked_latents_dev)) return set_err("next_input needs mask and masked_latents");
+  if (ensure_device_ready()) return 1;
+  DdimArgs a;
+  memset(&a, 0, sizeof a);
+  a.eps = eps_dev;
+  a.eps_dt = eps_dtype;
+  a.latents = latents_f32_dev;
+  a.latents_out = latents_out_dev;
+  a.latents_out_dt = latents_dtype;
+  a.next_in = next_input_dev;
+  a.next_dt = next_dtype;
+  a.mask = mask_dev;
+  a.mask_dt = mask_dtype;
+  a.masked = masked_latents_dev;
+  a.masked_dt = masked_dtype;
+  a.B = clips;
+  a.FHW = frames * height * width;
+  a.cfg = do_cfg;
+  a.guidance = guidance_scale;
+  ddim_coefs(alpha_bar_t, alpha_bar_prev, a.c);
+  a.round_dt = latents_dtype;
+  const size_t n = (size_t)clips * 4 * a.FHW;
+  ddim_cfg_step_kernel<<<grid_for(n, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(a);
+  g_launches++;
+  return check_launch("ddim_cfg_step");
+  API_END
+}
+
+int rcdm_denoise_loop(rcdm_unet* h, const void* latents_dev, int latents_dtype, const void* mask_dev, int mask_dtype,
+                      const void* masked_latents_dev, int masked_dtype, const void* ctx_dev, int ctx_dtype,
+                      int clips, int frames, int height, int width, int ctx_len, const int64_t* timesteps_host,
+                      const float* alpha_bar_t_host, const float* alpha_bar_prev_host, int num_steps,
+                      float guidance_scale, int use_graph, void* latents_out_dev, void* stream) {
+  API_BEGIN
+  if (!h || !latents_dev || !mask_dev || !masked_latents_dev || !ctx_dev || !latents_out_dev || !timesteps_host ||
+      !alpha_bar_t_host || !alpha_bar_prev_host)
+    return set_err("null argument");
+  if (num_steps < 1 || clips < 1) return set_err("bad num_steps / clips");
+  const int cfg = guidance_scale > 1.0f ? 1 : 0;  // RCDMs_pipeline.py:416
+  const int B = cfg ? 2 * clips : clips;
+  if (unet_prepare(h, B, frames, height, width, ctx_len)) return 1;
+  const int missing = rcdm_unet_weights_missing(h);
+  if (missing) return set_err("rcdm_denoise_loop: " + std::to_string(missing) + " state-dict entries not loaded");
+  cudaStream_t caller = reinterpret_cast<cudaStream_t>(stream);
+  if (!h->loop_stream) {
+    CUDA_OK(cudaStreamCreateWithFlags(&h->loop_stream, cudaStreamNonBlocking));
+    CUDA_OK(cudaEventCreateWithFlags(&h->ev_in, cudaEventDisableTiming));
+    CUDA_OK(cudaEventCreateWithFlags(&h->ev_out, cudaEventDisableTiming));
+  }
+  cudaStream_t st = h->loop_stream;
+  // ---- loop buffers
+  const size_t FHW = (size_t)frames * height * width;
+  auto al = [](size_t v) { return (v + 255) & ~size_t(255); };
+  const size_t o_lat = 0, o_next = o_lat + al(clips * 4 * FHW * 4), o_eps = o_next + al(B * 9 * FHW * 2),
+               o_tab = o_eps + al(B * 4 * FHW * 2), o_ts = o_tab + al((size_t)num_steps * 16),
+               o_idx = o_ts + al((size_t)num_steps * 8), o_tcur = o_idx + 256, total = o_tcur + 256;
+  if (h->loop_buf_bytes < total) {
+    if (h->loop_buf) CUDA_OK(cudaFree(h->loop_buf));
+    h->loop_buf = nullptr;
+    CUDA_OK(cudaMalloc(&h->loop_buf, total));
+    h->loop_buf_bytes = total;
+    if (h->graph_exec) {
+      cudaGraphExecDestroy(h->graph_exec);
+      h->graph_exec = nullptr;
+    }
+  }
+  float* lat32 = reinterpret_cast<float*>(h->loop_buf + o_lat);
+  void* next_in = h->loop_buf + o_next;
+  void* eps = h->loop_buf + o_eps;
+  float4* table = reinterpret_cast<float4*>(h->loop_buf + o_tab);
+  int64_t* ts = reinterpret_cast<int64_t*>(h->loop_buf + o_ts);
+  int* step_idx = reinterpret_cast<int*>(h->loop_buf + o_idx);
+  int64_t* t_cur = reinterpret_cast<int64_t*>(h->loop_buf + o_tcur);
+
+  CUDA_OK(cudaEventRecord(h->ev_in, caller));
+  CUDA_OK(cudaStreamWaitEvent(st, h->ev_in, 0));
+  std::vector<float4> tab(num_steps);
+  for (int i = 0; i < num_steps; ++i) {
+    float c[4];
+    ddim_coefs(alpha_bar_t_host[i], alpha_bar_prev_host[i], c);
+    tab[i] = make_float4(c[0], c[1], c[2], c[3]);
+  }
+  CUDA_OK(cudaMemcpyAsync(table, tab.data(), (size_t)num_steps * 16, cudaMemcpyHostToDevice, st));
+  CUDA_OK(cudaMemcpyAsync(ts, timesteps_host, (size_t)num_steps * 8, cudaMemcpyHostToDevice, st));
+  CUDA_OK(cudaMemsetAsync(step_idx, 0, 4, st));
+  CUDA_OK(cudaMemsetAsync(eps, 0, (size_t)B * 4 * FHW * 2, st));
+  CUDA_OK(cudaStreamSynchronize(st));  // `tab` is a host temporary
+  // ---- initial state: latents -> fp32 master, first 9-channel input (identity "step": x0 = x, x_prev = x)
+  DdimArgs a;
+  memset(&a, 0, sizeof a);
+  a.eps = eps;
+  a.eps_dt = h->dt;
+  a.latents = lat32;
+  a.latents_out = latents_out_dev;
+  a.latents_out_dt = latents_dtype;
+  a.next_in = next_in;
+  a.next_dt = h->dt;
+  a.mask = mask_dev;
+  a.mask_dt = mask_dtype;
+  a.masked = masked_latents_dev;
+  a.masked_dt = masked_dtype;
+  a.B = clips;
+  a.FHW = (int)FHW;
+  a.cfg = cfg;
+  a.guidance = guidance_scale;
+  a.round_dt = latents_dtype;
+  const size_t n = (size_t)clips * 4 * FHW;
+  {
+    DdimArgs init = a;
+    init.c[0] = 1.f;
+    init.c[1] = 0.f;
+    init.c[2] = 1.f;
+    init.c[3] = 0.f;
+    tap_to_f32_kernel<<<grid_for(n, 256), 256, 0, st>>>(latents_dev, latents_dtype, lat32, n);
+    ddim_cfg_step_kernel<<<grid_for(n, 256), 256, 0, st>>>(init);
+    g_launches += 2;
+  }
+  // ---- step-invariant part: context cast + cross-attention K/V of all 16 spatial transformers
+  h->cur_sample = next_in;
+  h->cur_sample_dt = h->dt;
+  h->cur_t_dev = t_cur;
+  h->cur_t_host = 0.f;
+  h->cur_ctx = ctx_dev;
+  h->cur_ctx_dt = ctx_dtype;
+  h->cur_out = eps;
+  h->cur_out_dt = h->dt;
+  if (unet_run(h, true, false, st)) return 1;
+  // ---- one step = [t <- timesteps[i]] [UNet] [CFG + DDIM + next input] [i++]
+  a.table = table;
+  a.step_idx = step_idx;
+  auto enqueue_step = [&]() -> int {
+    set_timestep_kernel<<<1, 1, 0, st>>>(ts, step_idx, t_cur);
+    if (unet_run(h, false, true, st)) return 1;
+    ddim_cfg_step_kernel<<<grid_for(n, 256), 256, 0, st>>>(a);
+    advance_step_kernel<<<1, 1, 0, st>>>(step_idx);
+    g_launches += 3;
+    return 0;
+  };
+  if (use_graph) {
+    char key[256];
+    snprintf(key, sizeof key, "%d/%d/%d/%d/%d/%d/%p/%p/%p/%d/%d/%d/%g/%p", clips, frames, height, width, ctx_len, cfg,
+             mask_dev, masked_latents_dev, latents_out_dev, mask_dtype, masked_dtype, latents_dtype,
+             (double)guidance_scale, (void*)h->loop_buf);
+    if (!h->graph_exec || h->graph_key != key) {
+      if (h->graph_exec) {
+        cudaGraphExecDestroy(h->graph_exec);
+        h->graph_exec = nullptr;
+      }
+      const uint64_t before = g_launches.load();
+      CUDA_OK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+      const int rc = enqueue_step();
+      cudaGraph_t graph = nullptr;
+      cudaError_t e = cudaStreamEndCapture(st, &graph);
+      g_launches.store(before);  // captured launches are counted per replay below
+      if (rc) return 1;
+      if (e != cudaSuccess) return set_err(std::string("cudaStreamEndCapture: ") + cudaGetErrorString(e));
+      e = cudaGraphInstantiate(&h->graph_exec, graph, 0);
+      cudaGraphDestroy(graph);
+      if (e != cudaSuccess) return set_err(std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e));
+      h->graph_key = key;
+    }
+    const uint64_t per_step = (uint64_t)h->step_ops.size() + 3;  // lower bound: >= 1 kernel per recorded op
+    for (int i = 0; i < num_steps; ++i) CUDA_OK(cudaGraphLaunch(h->graph_exec, st));
+    g_launches += per_step * num_steps;
+  } else {
+    for (int i = 0; i < num_steps; ++i)
+      if (enqueue_step()) return 1;
+  }
+  CUDA_OK(cudaEventRecord(h->ev_out, st));
+  CUDA_OK(cudaStreamWaitEvent(caller, h->ev_out, 0));
+  return check_launch("denoise_loop");
+  API_END
+}
+
+// ------------------------------------------------------------------------------------------
+// single-kernel entry points
+// ------------------------------------------------------------------------------------------
+int rcdm_gemm(int dtype, const void* a_dev, const void* w_dev, const float* bias_dev, const void* residual_dev,
+              void* out_dev, int M, int N, int K, int geglu, int tile_n, int simple, void* stream) {
+  API_BEGIN
+  if (!dt16(dtype)) return set_err("rcdm_gemm: dtype must be f16/bf16");
+  if (ensure_device_ready()) return 1;
+  GemmDesc d;
+  memset(&d, 0, sizeof d);
+  d.dt = dtype;
+  d.M = M;
+  d.N = N;
+  d.nseg = 1;
+  d.seg[0] = ASeg{SEG_PLAIN, a_dev, K, K, 0, 0, 0};
+  d.w = w_dev;
+  d.Ktot = K;
+  d.w_rows = N;
+  d.out = out_dev;
+  d.ldo = geglu ? N / 2 : N;
+  d.bias = bias_dev;
+  d.res = residual_dev;
+  d.ldr = N;
+  d.geglu = geglu;
+  d.force_bn = geglu ? 0 : tile_n;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (simple) {
+    gemm_simple_launch(d, st);
+  } else {
+    GemmLaunch l;
+    std::string e;
+    if (!gemm_prepare(d, &l, &e)) return set_err(e);
+    gemm_launch(l, st);
+  }
+  g_launches++;
+  return check_launch("rcdm_gemm");
+  API_END
+}
+
+int rcdm_pack_geglu(int dtype, const void* w_dev, const float* bias_dev, void* w_out_dev, float* bias_out_dev, int N,
+                    int K, void* stream) {
+  API_BEGIN
+  if (!dt16(dtype)) return set_err("dtype must be f16/bf16");
+  if (N % GEGLU_BN) return set_err("GEGLU pack: N must be a multiple of 128");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (dtype == DT_F16)
+    pack_weight_kernel<__half><<<grid_for((size_t)N * K, 256), 256, 0, st>>>(
+        w_dev, dtype, reinterpret_cast<__half*>(w_out_dev), N, K, K, 0, 0, 0, 0, GEGLU_BN);
+  else
+    pack_weight_kernel<__nv_bfloat16><<<grid_for((size_t)N * K, 256), 256, 0, st>>>(
+        w_dev, dtype, reinterpret_cast<__nv_bfloat16*>(w_out_dev), N, K, K, 0, 0, 0, 0, GEGLU_BN);
+  if (bias_dev && bias_out_dev)
+    pack_vec_kernel<<<(N + 255) / 256, 256, 0, st>>>(bias_dev, DT_F32, bias_out_dev, N, 0, GEGLU_BN, 0);
+  g_launches += 2;
+  return check_launch("rcdm_pack_geglu");
+  API_END
+}
+
+int rcdm_pack_conv3x3(int dtype, const void* w_dev, void* w_out_dev, int cout, int cin, void* stream) {
+  API_BEGIN
+  if (!dt16(dtype)) return set_err("dtype must be f16/bf16");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const size_t total = (size_t)cout * cin * 9;
+  if (dtype == DT_F16)
+    pack_weight_kernel<__half><<<grid_for(total, 256), 256, 0, st>>>(w_dev, dtype, reinterpret_cast<__half*>(w_out_dev),
+                                                                     cout, 9 * cin, 9 * cin, 0, 0, 1, cin, 0);
+  else
+    pack_weight_kernel<__nv_bfloat16><<<grid_for(total, 256), 256, 0, st>>>(
+        w_dev, dtype, reinterpret_cast<__nv_bfloat16*>(w_out_dev), cout, 9 * cin, 9 * cin, 0, 0, 1, cin, 0);
+  g_launches++;
+  return check_launch("rcdm_pack_conv3x3");
+  API_END
+}
+
+int rcdm_conv3x3(int dtype, const void* x_dev, const void* w_packed_dev, const float* bias_dev,
+                 const void* residual_dev, void* out_dev, int n, int h, int w, int cin, int cout, int stride,
+                 int simple, void* stream) {
+  API_BEGIN
+  if (!dt16(dtype)) return set_err("rcdm_conv3x3: dtype must be f16/bf16");
+  if (stride != 1 && stride != 2) return set_err("stride must be 1 or 2");
+  if (ensure_device_ready()) return 1;
+  const int Ho = h / stride, Wo = w / stride;
+  GemmDesc d;
+  memset(&d, 0, sizeof d);
+  d.dt = dtype;
+  d.M = n * Ho * Wo;
+  d.N = cout;
+  d.nseg = 1;
+  d.seg[0] = ASeg{stride == 2 ? SEG_CONV3S2 : SEG_CONV3, x_dev, cin, cin, h, w, n};
+  d.w = w_packed_dev;
+  d.Ktot = 9 * cin;
+  d.w_rows = cout;
+  d.Ho = Ho;
+  d.Wo = Wo;
+  d.NI = n;
+  d.out = out_dev;
+  d.ldo = cout;
+  d.bias = bias_dev;
+  d.res = residual_dev;
+  d.ldr = cout;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (simple) {
+    gemm_simple_launch(d, st);
+  } else {
+    GemmLaunch l;
+    std::string e;
+    if (!gemm_prepare(d, &l, &e)) return set_err(e);
+    gemm_launch(l, st);
+  }
+  g_launches++;
+  return check_launch("rcdm_conv3x3");
+  API_END
+}
+
+size_t rcdm_groupnorm_scratch_bytes(int rows, int rows_per_stat, int groups) {
+  if (rows_per_stat <= 0) return 0;
+  return gn_scratch_bytes(rows / rows_per_stat, groups);
+}
+
+int rcdm_groupnorm(int dtype, const void* x_dev, const float* gamma_dev, const float* beta_dev, void* out_dev,
+                   int rows, int channels, int groups, int rows_per_stat, float eps, int silu, void* scratch_dev,
+                   void* stream) {
+  API_BEGIN
+  if (!dt16(dtype)) return set_err("rcdm_groupnorm: dtype must be f16/bf16");
+  if (channels % 8 || channels % groups || rows % rows_per_stat) return set_err("rcdm_groupnorm: bad shape");
+  if (rows / rows_per_stat > 16384) return set_err("rcdm_groupnorm: too many statistic batches");
+  if (ensure_device_ready()) return 1;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  CUDA_OK(cudaMemsetAsync(scratch_dev, 0, 65536, st));
+  GnLaunch l;
+  gn_configure(&l, dtype, x_dev, channels, nullptr, 0, rows, rows_per_stat, groups, eps, gamma_dev, beta_dev, out_dev,
+               silu, scratch_dev);
+  gn_run(l, st);
+  return check_launch("rcdm_groupnorm");
+  API_END
+}
+
+int rcdm_layernorm(int dtype, const void* x_dev, const float* gamma_dev, const float* beta_dev, void* out_dev,
+                   int rows, int channels, float eps, const float* pe_dev, int rows_per_frame, int frames,
+                   void* stream) {
+  API_BEGIN
+  if (!dt16(dtype)) return set_err("rcdm_layernorm: dtype must be f16/bf16");
+  if (ensure_device_ready()) return 1;
+  if (!ln_run(dtype, x_dev, out_dev, gamma_dev, beta_dev, rows, channels, eps, pe_dev, rows_per_frame > 0 ? rows_per_frame : 1,
+              frames > 0 ? frames : 1, reinterpret_cast<cudaStream_t>(stream)))
+    return set_err("rcdm_layernorm: unsupported channel count");
+  return check_launch("rcdm_layernorm");
+  API_END
+}
+
+int rcdm_flash_attn(int dtype, const void* q_dev, int ldq, const void* k_dev, const void* v_dev, int ldkv,
+                    void* out_dev, int ldo, int batch, int heads, int S_q, int S_kv, int d, int simple, void* stream) {
+  API_BEGIN
+  if (!dt16(dtype)) return set_err("rcdm_flash_attn: dtype must be f16/bf16");
+  if (ensure_device_ready()) return 1;
+  AttnDesc a;
+  memset(&a, 0, sizeof a);
+  a.dt = dtype;
+  a.q = q_dev;
+  a.ldq = ldq;
+  a.k = k_dev;
+  a.v = v_dev;
+  a.ldkv = ldkv;
+  a.S_q = S_q;
+  a.S_kv = S_kv;
+  a.heads = heads;
+  a.d = d;
+  a.batch = batch;
+  a.out = out_dev;
+  a.ldo = ldo;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (simple) {
+    if (d > 160) return set_err("head dim > 160");
+    attn_simple_launch(a, st);
+  } else {
+    AttnLaunch l;
+    std::string e;
+    if (!attn_prepare(a, &l, &e)) return set_err(e);
+    attn_launch(l, st);
+  }
+  g_launches++;
+  return check_launch("rcdm_flash_attn");
+  API_END
+}
+
+int rcdm_temporal_attn(int dtype, const void* qkv_dev, void* out_dev, int batch, int frames, int hw, int heads, int d,
+                       void* stream) {
+  API_BEGIN
+  if (!dt16(dtype)) return set_err("rcdm_temporal_attn: dtype must be f16/bf16");
+  if (frames < 1 || frames > 5 || d % 8) return set_err("rcdm_temporal_attn: frames must be 1..5 and d % 8 == 0");
+  if (ensure_device_ready()) return 1;
+  temporal_attn_launch(dtype, qkv_dev, out_dev, batch, frames, hw, heads, d, reinterpret_cast<cudaStream_t>(stream));
+  g_launches++;
+  return check_launch("rcdm_temporal_attn");
+  API_END
+}
+
+}  // extern "C"

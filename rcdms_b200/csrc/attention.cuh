@@ -1,0 +1,296 @@
+// Attention kernels for sm_100a.
+//
+// flash_attn_kernel: softmax(scale * Q K^T) V without materialising the scores (the reference writes an
+// (80, 4096, 4096) score tensor per 64x64 layer: attention.py:170-199).  One CTA = 128 queries of one
+// (image, head).  Both GEMMs run on tcgen05 with accumulators in TMEM:
+//     S = Q K_j^T   (128 x 128 fp32, TMEM cols [0,128))      O += P_j V_j   (128 x DPAD fp32, TMEM cols [128, ...))
+// Q/K/V head slices are fetched straight out of the fused projection output [rows, ld] by 5-D TMA maps
+// (8 elems, row, 16-byte chunk, head, image) into the no-swizzle "interleaved" UMMA layout
+// [chunk][row][8 elems]; out-of-range chunks / rows are zero-filled by TMA, which pads head_dim 40 -> 48 and
+// ragged KV lengths (context L = 85 / 91) for free.  V is consumed as an MN-major B operand, so no transpose.
+// Warps 0-3: online softmax (thread <-> query row), P written to smem as the A operand of the second GEMM.
+// Warp 4 (one lane): TMA producer + MMA issuer.
+//
+// temporal_attn_kernel: the motion modules' attention over the f = 5 frames at each spatial location
+// (motion_module.py:294-354): a 5x5 problem per (location, head) -> CUDA cores, one thread per (location, head),
+// q/k/v read once directly from the (b f hw)-ordered token matrix (no "(b f) d c -> (b d) f c" copies).
+#pragma once
+#include "common.cuh"
+
+namespace rcdm {
+
+struct AttnParams {
+  int S_q, S_kv;  // rows per image for queries / keys
+  int heads, d;   // head dim (multiple of 8)
+  int batch;      // images
+  void* out;      // [batch * S_q, ldo]; head h -> columns [h*d, h*d + d)
+  int ldo;
+  float scale_log2;  // d^-0.5 * log2(e)
+};
+
+struct AttnMaps {
+  CUtensorMap q, k, v;
+};
+
+template <int DPAD> struct AttnCfg {
+  static constexpr int NCH = DPAD / 8;               // 16-byte chunks per head row
+  static constexpr int TILE_BYTES = NCH * 128 * 16;  // one 128-row operand tile
+  static constexpr int KV_STAGES = DPAD <= 80 ? 2 : 1;
+  static constexpr int P_BYTES = 16 * 128 * 16;
+  static constexpr int TMEM_COLS = (128 + DPAD) <= 256 ? 256 : 512;
+  static constexpr int SMEM_BYTES = TILE_BYTES * (1 + 2 * KV_STAGES) + P_BYTES + 1024 + 256;
+};
+
+template <typename T, int DPAD>
+__global__ void __launch_bounds__(160)
+flash_attn_kernel(const __grid_constant__ AttnMaps maps, const AttnParams p) {
+  using Cfg = AttnCfg<DPAD>;
+  constexpr int KV = Cfg::KV_STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + Cfg::TILE_BYTES;
+  uint8_t* sV = sK + KV * Cfg::TILE_BYTES;
+  uint8_t* sP = sV + KV * Cfg::TILE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + Cfg::P_BYTES);
+  uint64_t* q_full = bars;
+  uint64_t* kv_full = bars + 1;        // [KV]
+  uint64_t* kv_empty = bars + 1 + KV;  // [KV]
+  uint64_t* s_full = bars + 1 + 2 * KV;
+  uint64_t* p_full = s_full + 1;
+  uint64_t* o_done = s_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_full + 3);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q_tile = blockIdx.x, head = blockIdx.y, img = blockIdx.z;
+  const int n_kv = (p.S_kv + 127) / 128;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      mbar_init(q_full, 1);
+      for (int i = 0; i < KV; ++i) {
+        mbar_init(&kv_full[i], 1);
+        mbar_init(&kv_empty[i], 1);
+      }
+      mbar_init(s_full, 1);
+      mbar_init(p_full, 128);
+      mbar_init(o_done, 1);
+      fence_mbar_init();
+      tma_prefetch_desc(&maps.q);
+      tma_prefetch_desc(&maps.k);
+      tma_prefetch_desc(&maps.v);
+    }
+    __syncwarp();
+    tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_S = tmem_base, tmem_O = tmem_base + 128;
+
+  if (warp == 4) {
+    if (elect_one()) {
+      constexpr uint32_t idesc_qk = umma_idesc_f16(DT<T>::umma_fmt, 128, 128, 0, 0);
+      constexpr uint32_t idesc_pv = umma_idesc_f16(DT<T>::umma_fmt, 128, DPAD, 0, 1);  // B (=V) is MN-major
+      mbar_expect_tx(q_full, Cfg::TILE_BYTES);
+      tma_load_5d(sQ, &maps.q, q_full, 0, q_tile * 128, 0, head, img);
+      const uint32_t q_addr = smem_u32(sQ), p_addr = smem_u32(sP);
+      for (int j = 0; j < n_kv; ++j) {
+        // ---- producer: keep the K/V ring full
+        const int t_first = (j == 0) ? 0 : j + KV - 1, t_last = j + KV - 1;
+        for (int t = t_first; t <= t_last; ++t) {
+          if (t >= n_kv) break;
+          const int s = t % KV;
+          if (t >= KV) mbar_wait(&kv_empty[s], ((t / KV) - 1) & 1);
+          mbar_expect_tx(&kv_full[s], 2 * Cfg::TILE_BYTES);
+          tma_load_5d(sK + s * Cfg::TILE_BYTES, &maps.k, &kv_full[s], 0, t * 128, 0, head, img);
+          tma_load_5d(sV + s * Cfg::TILE_BYTES, &maps.v, &kv_full[s], 0, t * 128, 0, head, img);
+        }
+        const int s = j % KV;
+        if (j == 0) mbar_wait(q_full, 0);
+        mbar_wait(&kv_full[s], (j / KV) & 1);
+        tc_fence_after();
+        // ---- S = Q K^T : A, B K-major interleaved; +2 chunks (= 4096 B) per K=16 step
+        const uint32_t k_addr = smem_u32(sK + s * Cfg::TILE_BYTES);
+#pragma unroll
+        for (int ks = 0; ks < DPAD / 16; ++ks) {
+          const uint64_t ad = umma_smem_desc(q_addr + ks * 4096, 2048, 128, UMMA_SWIZZLE_NONE);
+          const uint64_t bd = umma_smem_desc(k_addr + ks * 4096, 2048, 128, UMMA_SWIZZLE_NONE);
+          umma_f16_ss(tmem_S, ad, bd, idesc_qk, ks != 0);
+        }
+        umma_commit(s_full);
+        // ---- O += P V : A = P K-major interleaved, B = V MN-major interleaved (+16 kv rows = 256 B per step)
+        mbar_wait(p_full, j & 1);
+        tc_fence_after();
+        const uint32_t v_addr = smem_u32(sV + s * Cfg::TILE_BYTES);
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {
+          const uint64_t ad = umma_smem_desc(p_addr + ks * 4096, 2048, 128, UMMA_SWIZZLE_NONE);
+          const uint64_t bd = umma_smem_desc(v_addr + ks * 256, 128, 2048, UMMA_SWIZZLE_NONE);
+          umma_f16_ss(tmem_O, ad, bd, idesc_pv, (j | ks) != 0);
+        }
+        umma_commit(&kv_empty[s]);
+        if (j == n_kv - 1) umma_commit(o_done);
+      }
+    }
+  } else {
+    // =================================== softmax warps ===================================
+    const int row = warp * 32 + lane;
+    const uint32_t lane_sel = uint32_t(warp * 32) << 16;
+    float m_run = -INFINITY, l_run = 0.f;
+    for (int j = 0; j < n_kv; ++j) {
+      mbar_wait(s_full, j & 1);
+      tc_fence_after();
+      const int kv_valid = min(128, p.S_kv - j * 128);
+      float mx = -INFINITY;
+#pragma unroll 1
+      for (int c = 0; c < 128; c += 32) {
+        uint32_t r[32];
+        tmem_ld32(tmem_S + lane_sel + c, r);
+        tmem_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (c + i < kv_valid) mx = fmaxf(mx, __uint_as_float(r[i]));
+      }
+      const float m_new = fmaxf(m_run, mx * p.scale_log2);
+      const float alpha = exp2f(m_run - m_new);  // m_run = -inf on the first tile -> 0
+      float rowsum = 0.f;
+#pragma unroll 1
+      for (int c = 0; c < 128; c += 16) {
+        uint32_t r[16];
+        tmem_ld16(tmem_S + lane_sel + c, r);
+        tmem_wait_ld();
+        float pv[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float e = exp2f(__uint_as_float(r[i]) * p.scale_log2 - m_new);
+          pv[i] = (c + i < kv_valid) ? e : 0.f;
+          rowsum += pv[i];
+        }
+        // P tile, K-major interleaved: [chunk = kv/8][row][8 elems]
+        *reinterpret_cast<uint4*>(sP + (c / 8) * 2048 + row * 16) = pack8<T>(pv);
+        *reinterpret_cast<uint4*>(sP + (c / 8 + 1) * 2048 + row * 16) = pack8<T>(pv + 8);
+      }
+      l_run = l_run * alpha + rowsum;
+      m_run = m_new;
+      if (j > 0 && __any_sync(0xffffffffu, alpha != 1.0f)) {
+#pragma unroll 1
+        for (int c = 0; c < DPAD; c += 16) {
+          uint32_t r[16];
+          tmem_ld16(tmem_O + lane_sel + c, r);
+          tmem_wait_ld();
+#pragma unroll
+          for (int i = 0; i < 16; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
+          tmem_st16(tmem_O + lane_sel + c, r);
+        }
+        tmem_wait_st();
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(p_full);
+    }
+    // ---- normalise and store
+    mbar_wait(o_done, 0);
+    tc_fence_after();
+    const float inv_l = 1.0f / l_run;
+    const int qrow = q_tile * 128 + row;
+    T* out = reinterpret_cast<T*>(p.out) + ((size_t)img * p.S_q + qrow) * p.ldo + head * p.d;
+#pragma unroll 1
+    for (int c = 0; c < DPAD; c += 16) {
+      uint32_t r[16];
+      tmem_ld16(tmem_O + lane_sel + c, r);
+      tmem_wait_ld();
+      if (qrow < p.S_q) {
+        float v[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]) * inv_l;
+        if (c < p.d) *reinterpret_cast<uint4*>(out + c) = pack8<T>(v);
+        if (c + 8 < p.d) *reinterpret_cast<uint4*>(out + c + 8) = pack8<T>(v + 8);
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// temporal attention: qkv [rows, 3C] with rows ordered (b, f, hw); out [rows, C]
+// one thread per (b, hw, head); F <= 8 frames
+// ------------------------------------------------------------------------------------------
+template <typename T, int F>
+__global__ void temporal_attn_kernel(const T* __restrict__ qkv, T* __restrict__ out, int batch, int hw, int heads,
+                                     int d, float scale) {
+  const int C = heads * d;
+  const size_t total = (size_t)batch * hw * heads;
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int h = (int)(idx % heads);
+  const size_t loc = idx / heads;
+  const int pix = (int)(loc % hw);
+  const int b = (int)(loc / hw);
+  const size_t row0 = (size_t)b * F * hw + pix;  // frame f -> row0 + f*hw
+  const int ld = 3 * C;
+  float s[F][F];
+#pragma unroll
+  for (int i = 0; i < F; ++i)
+#pragma unroll
+    for (int j = 0; j < F; ++j) s[i][j] = 0.f;
+  for (int c = 0; c < d; c += 8) {
+    float qf[F][8], kf[F][8];
+#pragma unroll
+    for (int f = 0; f < F; ++f) {
+      const T* base = qkv + (row0 + (size_t)f * hw) * ld + h * d + c;
+      unpack8<T>(__ldg(reinterpret_cast<const uint4*>(base)), qf[f]);
+      unpack8<T>(__ldg(reinterpret_cast<const uint4*>(base + C)), kf[f]);
+    }
+#pragma unroll
+    for (int i = 0; i < F; ++i)
+#pragma unroll
+      for (int j = 0; j < F; ++j)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) s[i][j] += qf[i][e] * kf[j][e];
+  }
+#pragma unroll
+  for (int i = 0; i < F; ++i) {
+    float mx = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < F; ++j) {
+      s[i][j] *= scale;
+      mx = fmaxf(mx, s[i][j]);
+    }
+    float sum = 0.f;
+#pragma unroll
+    for (int j = 0; j < F; ++j) {
+      s[i][j] = __expf(s[i][j] - mx);
+      sum += s[i][j];
+    }
+    const float inv = 1.0f / sum;
+#pragma unroll
+    for (int j = 0; j < F; ++j) s[i][j] *= inv;
+  }
+  for (int c = 0; c < d; c += 8) {
+    float vf[F][8];
+#pragma unroll
+    for (int f = 0; f < F; ++f)
+      unpack8<T>(__ldg(reinterpret_cast<const uint4*>(qkv + (row0 + (size_t)f * hw) * ld + 2 * C + h * d + c)), vf[f]);
+#pragma unroll
+    for (int i = 0; i < F; ++i) {
+      float o[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        float acc = 0.f;
+#pragma unroll
+        for (int j = 0; j < F; ++j) acc += s[i][j] * vf[j][e];
+        o[e] = acc;
+      }
+      *reinterpret_cast<uint4*>(out + (row0 + (size_t)i * hw) * C + h * d + c) = pack8<T>(o);
+    }
+  }
+}
+
+}  // namespace rcdm

@@ -1,0 +1,156 @@
+// Host side of the attention kernels: 5-D TMA maps over the fused projection outputs, launch, and a
+// CUDA-core debug kernel with identical semantics (RCDM_SIMPLE=1 only).
+#include "launch.h"
+
+namespace rcdm {
+
+static int pick_dpad(int d) {
+  if (d <= 16) return 16;
+  if (d <= 32) return 32;
+  if (d <= 48) return 48;
+  if (d <= 80) return 80;
+  if (d <= 160) return 160;
+  return -1;
+}
+
+// (8 elems, rows-per-image, 16-byte chunks of the head, heads, images); box (8, 128, dpad/8, 1, 1)
+static bool head_map(CUtensorMap* m, const void* base, int ld, int S, int heads, int d, int batch, int dpad,
+                     std::string* err) {
+  uint64_t dims[5] = {8, (uint64_t)S, (uint64_t)d / 8, (uint64_t)heads, (uint64_t)batch};
+  uint64_t str[4] = {(uint64_t)ld * 2, 16, (uint64_t)d * 2, (uint64_t)S * ld * 2};
+  uint32_t box[5] = {8, 128, (uint32_t)dpad / 8, 1, 1};
+  return encode_tmap(m, base, 5, dims, str, box, false, err);
+}
+
+bool attn_prepare(const AttnDesc& d, AttnLaunch* l, std::string* err) {
+  const int dpad = pick_dpad(d.d);
+  if (dpad < 0 || d.d % 8 != 0) {
+    if (err) *err = "attn_prepare: unsupported head dim";
+    return false;
+  }
+  memset(&l->maps, 0, sizeof l->maps);
+  l->dpad = dpad;
+  l->dt = d.dt;
+  if (!head_map(&l->maps.q, d.q, d.ldq, d.S_q, d.heads, d.d, d.batch, dpad, err)) return false;
+  if (!head_map(&l->maps.k, d.k, d.ldkv, d.S_kv, d.heads, d.d, d.batch, dpad, err)) return false;
+  if (!head_map(&l->maps.v, d.v, d.ldkv, d.S_kv, d.heads, d.d, d.batch, dpad, err)) return false;
+  l->p.S_q = d.S_q;
+  l->p.S_kv = d.S_kv;
+  l->p.heads = d.heads;
+  l->p.d = d.d;
+  l->p.batch = d.batch;
+  l->p.out = d.out;
+  l->p.ldo = d.ldo;
+  l->p.scale_log2 = (float)(1.4426950408889634 / sqrt((double)d.d));
+  l->grid = dim3((d.S_q + 127) / 128, d.heads, d.batch);
+  return true;
+}
+
+template <typename T, int DPAD> static void launch_one(const AttnLaunch& l, cudaStream_t s) {
+  flash_attn_kernel<T, DPAD><<<l.grid, 160, AttnCfg<DPAD>::SMEM_BYTES, s>>>(l.maps, l.p);
+}
+template <typename T> static void launch_dt(const AttnLaunch& l, cudaStream_t s) {
+  switch (l.dpad) {
+    case 16: launch_one<T, 16>(l, s); break;
+    case 32: launch_one<T, 32>(l, s); break;
+    case 48: launch_one<T, 48>(l, s); break;
+    case 80: launch_one<T, 80>(l, s); break;
+    default: launch_one<T, 160>(l, s); break;
+  }
+}
+void attn_launch(const AttnLaunch& l, cudaStream_t s) {
+  if (l.dt == DT_F16) launch_dt<__half>(l, s);
+  else launch_dt<__nv_bfloat16>(l, s);
+}
+
+template <typename T, int DPAD> static cudaError_t set_attr() {
+  return cudaFuncSetAttribute(flash_attn_kernel<T, DPAD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              AttnCfg<DPAD>::SMEM_BYTES);
+}
+template <typename T> static cudaError_t set_attr_dt() {
+  cudaError_t e = set_attr<T, 16>();
+  if (e == cudaSuccess) e = set_attr<T, 32>();
+  if (e == cudaSuccess) e = set_attr<T, 48>();
+  if (e == cudaSuccess) e = set_attr<T, 80>();
+  if (e == cudaSuccess) e = set_attr<T, 160>();
+  return e;
+}
+bool attn_setup_attributes(std::string* err) {
+  cudaError_t e = set_attr_dt<__half>();
+  if (e == cudaSuccess) e = set_attr_dt<__nv_bfloat16>();
+  if (e != cudaSuccess) {
+    if (err) *err = std::string("cudaFuncSetAttribute(attn): ") + cudaGetErrorString(e);
+    return false;
+  }
+  return true;
+}
+
+// ---- debug kernel: one thread per (image, head, query row) --------------------------------------------
+template <typename T>
+__global__ void attn_simple_kernel(const AttnDesc a) {
+  const size_t total = (size_t)a.batch * a.heads * a.S_q;
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int i = (int)(idx % a.S_q);
+  const int h = (int)((idx / a.S_q) % a.heads);
+  const int b = (int)(idx / ((size_t)a.S_q * a.heads));
+  const T* q = reinterpret_cast<const T*>(a.q) + ((size_t)b * a.S_q + i) * a.ldq + h * a.d;
+  const T* kb = reinterpret_cast<const T*>(a.k) + (size_t)b * a.S_kv * a.ldkv + h * a.d;
+  const T* vb = reinterpret_cast<const T*>(a.v) + (size_t)b * a.S_kv * a.ldkv + h * a.d;
+  const float scale = rsqrtf((float)a.d);
+  float mx = -INFINITY;
+  for (int j = 0; j < a.S_kv; ++j) {
+    float s = 0.f;
+    for (int c = 0; c < a.d; ++c) s += DT<T>::to_f(q[c]) * DT<T>::to_f(kb[(size_t)j * a.ldkv + c]);
+    mx = fmaxf(mx, s * scale);
+  }
+  float o[160];
+  for (int c = 0; c < a.d; ++c) o[c] = 0.f;
+  float l = 0.f;
+  for (int j = 0; j < a.S_kv; ++j) {
+    float s = 0.f;
+    for (int c = 0; c < a.d; ++c) s += DT<T>::to_f(q[c]) * DT<T>::to_f(kb[(size_t)j * a.ldkv + c]);
+    const float pr = __expf(s * scale - mx);
+    l += pr;
+    for (int c = 0; c < a.d; ++c) o[c] += pr * DT<T>::to_f(vb[(size_t)j * a.ldkv + c]);
+  }
+  T* out = reinterpret_cast<T*>(a.out) + ((size_t)b * a.S_q + i) * a.ldo + h * a.d;
+  for (int c = 0; c < a.d; ++c) out[c] = DT<T>::from_f(o[c] / l);
+}
+
+void attn_simple_launch(const AttnDesc& d, cudaStream_t s) {
+  const size_t total = (size_t)d.batch * d.heads * d.S_q;
+  const int blocks = (int)((total + 127) / 128);
+  if (d.dt == DT_F16) attn_simple_kernel<__half><<<blocks, 128, 0, s>>>(d);
+  else attn_simple_kernel<__nv_bfloat16><<<blocks, 128, 0, s>>>(d);
+}
+
+void temporal_attn_launch(int dt, const void* qkv, void* out, int batch, int frames, int hw, int heads, int d,
+                          cudaStream_t s) {
+  const size_t total = (size_t)batch * hw * heads;
+  const int blocks = (int)((total + 127) / 128);
+  const float scale = 1.0f / sqrtf((float)d);
+#define RCDM_TA(T, F)                                                                                              \
+  temporal_attn_kernel<T, F><<<blocks, 128, 0, s>>>(reinterpret_cast<const T*>(qkv), reinterpret_cast<T*>(out), \
+                                                     batch, hw, heads, d, scale)
+  if (dt == DT_F16) {
+    switch (frames) {
+      case 1: RCDM_TA(__half, 1); break;
+      case 2: RCDM_TA(__half, 2); break;
+      case 3: RCDM_TA(__half, 3); break;
+      case 4: RCDM_TA(__half, 4); break;
+      default: RCDM_TA(__half, 5); break;
+    }
+  } else {
+    switch (frames) {
+      case 1: RCDM_TA(__nv_bfloat16, 1); break;
+      case 2: RCDM_TA(__nv_bfloat16, 2); break;
+      case 3: RCDM_TA(__nv_bfloat16, 3); break;
+      case 4: RCDM_TA(__nv_bfloat16, 4); break;
+      default: RCDM_TA(__nv_bfloat16, 5); break;
+    }
+  }
+#undef RCDM_TA
+}
+
+}  // namespace rcdm

@@ -1,0 +1,250 @@
+// Small HBM-bound kernels around the tensor-core path: boundary layout conversion (NCFHW <-> channels-last
+// tokens), conv_in im2col (9 input channels), nearest 2x upsample, the timestep-embedding MLP, the fused
+// CFG + DDIM step, and the weight (re)packing kernels.
+#pragma once
+#include "common.cuh"
+
+namespace rcdm {
+
+__device__ __forceinline__ float load_any(const void* p, int dt, size_t i) {
+  if (dt == DT_F32) return reinterpret_cast<const float*>(p)[i];
+  if (dt == DT_F16) return __half2float(reinterpret_cast<const __half*>(p)[i]);
+  return __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p)[i]);
+}
+__device__ __forceinline__ void store_any(void* p, int dt, size_t i, float v) {
+  if (dt == DT_F32) reinterpret_cast<float*>(p)[i] = v;
+  else if (dt == DT_F16) reinterpret_cast<__half*>(p)[i] = __float2half_rn(v);
+  else reinterpret_cast<__nv_bfloat16*>(p)[i] = __float2bfloat16_rn(v);
+}
+
+// conv_in (unet.py:403; InflatedConv3d resnet.py:10-18): sample (b, Cin, f, h, w) in any dtype ->
+// im2col matrix A[(b f y x), Kpad] with k = (ky*3 + kx)*Cin + c (zero for padding taps and k >= 9*Cin).
+// The sample is first rounded to the compute dtype, as `.to(dtype=latents_dtype)` does (RCDMs_pipeline.py:486).
+template <typename T>
+__global__ void im2col_in_kernel(const void* __restrict__ x, int x_dt, T* __restrict__ A, int B, int Cin, int F, int H,
+                                 int W, int Kpad) {
+  const size_t total = (size_t)B * F * H * W * Kpad;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (size_t)gridDim.x * blockDim.x) {
+    const int k = (int)(idx % Kpad);
+    size_t m = idx / Kpad;
+    const int xx = (int)(m % W);
+    m /= W;
+    const int yy = (int)(m % H);
+    m /= H;
+    const int f = (int)(m % F);
+    const int b = (int)(m / F);
+    float v = 0.f;
+    if (k < 9 * Cin) {
+      const int tap = k / Cin, c = k % Cin;
+      const int sy = yy + tap / 3 - 1, sx = xx + tap % 3 - 1;
+      if (sy >= 0 && sy < H && sx >= 0 && sx < W)
+        v = load_any(x, x_dt, ((((size_t)b * Cin + c) * F + f) * H + sy) * W + sx);
+    }
+    A[idx] = DT<T>::from_f(v);
+  }
+}
+
+// tokens [(b f y x), C] -> (b, C, f, h, w) in the caller's dtype (conv_out result, unet.py:457-460)
+template <typename T>
+__global__ void tokens_to_ncfhw_kernel(const T* __restrict__ tok, void* __restrict__ out, int out_dt, int B, int C,
+                                       int F, int HW) {
+  const size_t total = (size_t)B * C * F * HW;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (size_t)gridDim.x * blockDim.x) {
+    const int pix = (int)(idx % HW);
+    size_t r = idx / HW;
+    const int f = (int)(r % F);
+    r /= F;
+    const int c = (int)(r % C);
+    const int b = (int)(r / C);
+    store_any(out, out_dt, idx, DT<T>::to_f(tok[(((size_t)b * F + f) * HW + pix) * C + c]));
+  }
+}
+
+// nearest-neighbour 2x spatial upsample on channels-last images (Upsample3D, resnet.py:65)
+template <typename T>
+__global__ void upsample2x_kernel(const T* __restrict__ x, T* __restrict__ y, int N, int H, int W, int C) {
+  const int vecs = C / 8;
+  const size_t total = (size_t)N * 2 * H * 2 * W * vecs;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (size_t)gridDim.x * blockDim.x) {
+    const int v = (int)(idx % vecs);
+    size_t r = idx / vecs;
+    const int ox = (int)(r % (2 * W));
+    r /= 2 * W;
+    const int oy = (int)(r % (2 * H));
+    const int n = (int)(r / (2 * H));
+    const uint4 val = __ldg(reinterpret_cast<const uint4*>(x + (((size_t)n * H + oy / 2) * W + ox / 2) * C + v * 8));
+    *reinterpret_cast<uint4*>(y + idx * 8) = val;
+  }
+}
+
+// ---- timestep embedding (unet.py:367-389 + resnet.py:190-191), all in fp32 from 16-bit weights ----------
+// step 1: sinusoid (flip_sin_to_cos, freq_shift 0) -> rounded to T (".to(dtype)") -> linear_1 -> SiLU
+// one warp per output feature.  t comes from device memory (int64) when t_dev != nullptr.
+template <typename T>
+__global__ void temb_linear1_kernel(const int64_t* t_dev, float t_host, const T* __restrict__ w,
+                                    const float* __restrict__ bias, float* __restrict__ out, int c0, int n_out,
+                                    int flip_sin_to_cos, float freq_shift) {
+  const int o = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (o >= n_out) return;
+  const float t = t_dev ? (float)(*t_dev) : t_host;
+  const int half = c0 / 2;
+  float acc = 0.f;
+  for (int i = lane; i < c0; i += 32) {
+    // column i of the embedding: [cos | sin] when flipped, [sin | cos] otherwise
+    const int fi = i % half;
+    const bool is_sin = flip_sin_to_cos ? (i >= half) : (i < half);
+    const float freq = expf(-logf(10000.0f) * (float)fi / ((float)half - freq_shift));
+    const float arg = t * freq;
+    float e = is_sin ? sinf(arg) : cosf(arg);
+    e = DT<T>::to_f(DT<T>::from_f(e));
+    acc += e * DT<T>::to_f(w[(size_t)o * c0 + i]);
+  }
+#pragma unroll
+  for (int s = 16; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
+  if (lane == 0) out[o] = silu_f(acc + bias[o]);
+}
+
+// generic fp32-activation GEMV: out[o] = act_out(dot(x, w[o,:]) + bias[o]); one warp per output
+template <typename T>
+__global__ void gemv_kernel(const float* __restrict__ x, const T* __restrict__ w, const float* __restrict__ bias,
+                            const float* __restrict__ bias2, float* __restrict__ out, int n_in, int n_out,
+                            int silu_out) {
+  const int o = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (o >= n_out) return;
+  float acc = 0.f;
+  for (int i = lane * 8; i < n_in; i += 256) {
+    float f[8];
+    unpack8<T>(__ldg(reinterpret_cast<const uint4*>(w + (size_t)o * n_in + i)), f);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc += f[e] * x[i + e];
+  }
+#pragma unroll
+  for (int s = 16; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
+  if (lane == 0) {
+    acc += bias[o];
+    if (bias2) acc += bias2[o];
+    out[o] = silu_out ? silu_f(acc) : acc;
+  }
+}
+
+// ---- fused classifier-free guidance + DDIM step + next UNet input (RCDMs_pipeline.py:482-497) ------------
+// eps:      (2B, 4, f, h, w)   [uncond clips | cond clips]   (B, ...) when !cfg
+// latents:  (B, 4, f, h, w)  updated in place (fp32 master copy + optional user-dtype copy)
+// next_in:  (2B, 9, f, h, w)   [latents | mask | masked_latents] for both CFG halves (compute dtype T)
+// coef: {sqrt(abar_t), sqrt(1-abar_t), sqrt(abar_prev), sqrt(1-abar_prev)} read from a device table at *step_idx
+// when table != nullptr (graph replay), else passed by value.
+struct DdimArgs {
+  const void* eps;
+  int eps_dt;
+  float* latents;        // fp32 master [B,4,f,h,w]
+  void* latents_out;     // optional copy in user dtype
+  int latents_out_dt;
+  void* next_in;         // (2B or B, 9, f, h, w) in next_dt, may be nullptr
+  int next_dt;
+  const void* mask;      // (B,1,f,h,w) any dtype
+  int mask_dt;
+  const void* masked;    // (B,4,f,h,w)
+  int masked_dt;
+  int B, FHW;            // clips, f*h*w
+  int cfg;
+  float guidance;
+  float c[4];
+  const float4* table;   // [steps] or nullptr
+  const int* step_idx;   // device counter (read)
+  int round_dt;          // dtype the reference would hold latents in (rounding point), DT_*
+};
+
+__device__ __forceinline__ float round_to(float v, int dt) {
+  if (dt == DT_F16) return __half2float(__float2half_rn(v));
+  if (dt == DT_BF16) return __bfloat162float(__float2bfloat16_rn(v));
+  return v;
+}
+
+static __global__ void ddim_cfg_step_kernel(const DdimArgs a) {
+  const size_t n = (size_t)a.B * 4 * a.FHW;
+  float4 co = make_float4(a.c[0], a.c[1], a.c[2], a.c[3]);
+  if (a.table) co = a.table[*a.step_idx];
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (size_t)gridDim.x * blockDim.x) {
+    const int pix = (int)(idx % a.FHW);
+    const int ch = (int)((idx / a.FHW) % 4);
+    const int b = (int)(idx / ((size_t)4 * a.FHW));
+    float e;
+    if (a.cfg) {
+      const float eu = load_any(a.eps, a.eps_dt, idx);
+      const float ec = load_any(a.eps, a.eps_dt, idx + n);
+      e = round_to(eu + a.guidance * (ec - eu), a.round_dt);
+    } else {
+      e = load_any(a.eps, a.eps_dt, idx);
+    }
+    const float x = a.latents[idx];
+    const float x0 = (x - co.y * e) / co.x;
+    const float xn = round_to(co.z * x0 + co.w * e, a.round_dt);
+    a.latents[idx] = xn;
+    if (a.latents_out) store_any(a.latents_out, a.latents_out_dt, idx, xn);
+    if (a.next_in) {
+      const int reps = a.cfg ? 2 : 1;
+      for (int r = 0; r < reps; ++r) {
+        const size_t ob = ((size_t)(r * a.B + b) * 9) * a.FHW;
+        store_any(a.next_in, a.next_dt, ob + (size_t)ch * a.FHW + pix, xn);
+        store_any(a.next_in, a.next_dt, ob + (size_t)(5 + ch) * a.FHW + pix,
+                  load_any(a.masked, a.masked_dt, idx));
+        if (ch == 0)
+          store_any(a.next_in, a.next_dt, ob + (size_t)4 * a.FHW + pix,
+                    load_any(a.mask, a.mask_dt, (size_t)b * a.FHW + pix));
+      }
+    }
+  }
+}
+
+static __global__ void advance_step_kernel(int* step_idx) { *step_idx += 1; }
+
+// ---- weight packing ------------------------------------------------------------------------------------
+// dst[(row_map(n)) * ldd + col_off + k'] for src viewed as [N, K] (K = Cin*taps for convs)
+// kind 0: matrix [N,K] row-major;  kind 1: conv3x3 [N, Cin, 3, 3] -> k' = tap*Cin + c
+// geglu_bn > 0: GEGLU row interleave for tile width geglu_bn (rows [0,N/2) = h, [N/2,N) = gate)
+__device__ __forceinline__ int geglu_row(int r, int N, int bn) {
+  const int half = N / 2, hb = bn / 2;
+  const int gate = r >= half;
+  const int j = gate ? r - half : r;
+  return (j / hb) * bn + (gate ? hb : 0) + (j % hb);
+}
+
+template <typename T>
+__global__ void pack_weight_kernel(const void* __restrict__ src, int src_dt, T* __restrict__ dst, int N, int K, int ldd,
+                                   int col_off, int row_off, int kind, int Cin, int geglu_bn) {
+  const size_t total = (size_t)N * K;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (size_t)gridDim.x * blockDim.x) {
+    const int n = (int)(idx / K);
+    const int k = (int)(idx % K);
+    int kk = k;
+    if (kind == 1) {  // src k = c*9 + tap
+      const int c = k / 9, tap = k % 9;
+      kk = tap * Cin + c;
+    }
+    const int row = (geglu_bn > 0 ? geglu_row(n, N, geglu_bn) : n) + row_off;
+    dst[(size_t)row * ldd + col_off + kk] = DT<T>::from_f(load_any(src, src_dt, idx));
+  }
+}
+
+static __global__ void pack_vec_kernel(const void* __restrict__ src, int src_dt, float* __restrict__ dst, int N, int off,
+                                int geglu_bn, int accumulate) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  const int row = (geglu_bn > 0 ? geglu_row(i, N, geglu_bn) : i) + off;
+  const float v = load_any(src, src_dt, i);
+  dst[row] = accumulate ? dst[row] + v : v;
+}
+
+template <typename T>
+__global__ void cast_rows_kernel(const void* __restrict__ src, int src_dt, T* __restrict__ dst, size_t n) {
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (size_t)gridDim.x * blockDim.x)
+    dst[idx] = DT<T>::from_f(load_any(src, src_dt, idx));
+}
+
+}  // namespace rcdm

@@ -1,0 +1,289 @@
+// Host side of the tcgen05 GEMM / implicit-GEMM conv: tensor-map construction, tile selection, launch.
+// Also holds the CUDA-core "simple" kernel with identical semantics, used only for bisecting parity
+// failures (RCDM_SIMPLE=1); it is never the benchmarked path.
+#include <cudaTypedefs.h>
+
+#include <mutex>
+
+#include "launch.h"
+
+namespace rcdm {
+
+// ------------------------------------------------------------------------------------------
+// tensor maps
+// ------------------------------------------------------------------------------------------
+static PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn(std::string* err) {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  static std::once_flag once;
+  static std::string once_err;
+  std::call_once(once, [&]() {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPointByVersion("cuTensorMapEncodeTiled", &p, 12000, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !p) {
+      once_err = std::string("cuTensorMapEncodeTiled unavailable: ") + cudaGetErrorString(e);
+      (void)cudaGetLastError();
+      return;
+    }
+    fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+  });
+  if (!fn && err) *err = once_err;
+  return fn;
+}
+
+bool encode_tmap(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                 const uint32_t* box, bool swizzle128, std::string* err) {
+  auto fn = get_encode_fn(err);
+  if (!fn) return false;
+  cuuint64_t gdim[5], gstr[4];
+  cuuint32_t bdim[5], estr[5];
+  for (int i = 0; i < rank; ++i) {
+    gdim[i] = dims[i];
+    bdim[i] = box[i];
+    estr[i] = 1;
+    if (i < rank - 1) gstr[i] = strides_bytes[i];
+  }
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0) {
+    if (err) *err = "TMA base address not 16-byte aligned";
+    return false;
+  }
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_UINT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bdim, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    if (err) {
+      char buf[256];
+      snprintf(buf, sizeof buf, "cuTensorMapEncodeTiled failed (CUresult %d): rank %d dims [%llu %llu %llu %llu %llu] box [%u %u %u %u %u]",
+               (int)r, rank, (unsigned long long)gdim[0], (unsigned long long)(rank > 1 ? gdim[1] : 0),
+               (unsigned long long)(rank > 2 ? gdim[2] : 0), (unsigned long long)(rank > 3 ? gdim[3] : 0),
+               (unsigned long long)(rank > 4 ? gdim[4] : 0), bdim[0], rank > 1 ? bdim[1] : 0, rank > 2 ? bdim[2] : 0,
+               rank > 3 ? bdim[3] : 0, rank > 4 ? bdim[4] : 0);
+      *err = buf;
+    }
+    return false;
+  }
+  return true;
+}
+
+// ------------------------------------------------------------------------------------------
+// GEMM prepare / launch
+// ------------------------------------------------------------------------------------------
+static bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
+
+static int pick_bn(const GemmDesc& d) {
+  if (d.force_bn) return d.force_bn;
+  if (d.geglu) return GEGLU_BN;
+  if (d.N % 160 == 0) return 160;
+  if (d.N <= 64) return 64;
+  return 128;
+}
+
+bool gemm_prepare(const GemmDesc& d, GemmLaunch* l, std::string* err) {
+  auto fail = [&](const std::string& m) {
+    if (err) *err = "gemm_prepare: " + m;
+    return false;
+  };
+  GemmParams& p = l->p;
+  memset(&p, 0, sizeof p);
+  memset(&l->maps, 0, sizeof l->maps);
+  const int bn = pick_bn(d);
+  l->bn = bn;
+  l->dt = d.dt;
+  p.M = d.M;
+  p.N = d.N;
+  p.nseg = d.nseg;
+  p.out = d.out;
+  p.ldo = d.ldo;
+  p.bias = d.bias;
+  p.res = d.res;
+  p.ldr = d.ldr;
+  p.geglu = d.geglu;
+  p.tw = 1;
+  p.th = 1;
+  p.tn = 128;
+  p.tiles_x = 1;
+  p.tiles_y = 1;
+  if (d.geglu && (d.N % bn != 0)) return fail("GEGLU needs N % BN == 0");
+  if (d.Ktot % 8 != 0) return fail("K must be a multiple of 8");
+  bool has_conv = false;
+  int nmap = 0, kb = 0, kcols = 0;
+  for (int s = 0; s < d.nseg; ++s) {
+    const ASeg& a = d.seg[s];
+    p.seg[s].mode = a.mode;
+    p.seg[s].tmap = nmap;
+    p.seg[s].cblocks = (a.C + 63) / 64;
+    if (d.nseg > 1 && a.C % 64 != 0) return fail("multi-segment K must be 64-aligned");
+    if (a.mode == SEG_PLAIN) {
+      if (nmap + 1 > 4) return fail("too many tensor maps");
+      uint64_t dims[2] = {(uint64_t)a.C, (uint64_t)d.M};
+      uint64_t str[1] = {(uint64_t)a.ld * 2};
+      uint32_t box[2] = {64, 128};
+      if (!encode_tmap(&l->maps.a[nmap], a.ptr, 2, dims, str, box, true, err)) return false;
+      nmap += 1;
+      kb += p.seg[s].cblocks;
+      kcols += a.C;
+    } else {
+      if (a.C % 64 != 0) return fail("conv channels must be a multiple of 64");
+      has_conv = true;
+      if (a.mode == SEG_CONV3) {
+        if (nmap + 1 > 4) return fail("too many tensor maps");
+        if (a.H != d.Ho || a.W != d.Wo) return fail("conv3 s1: input/output grid mismatch");
+        nmap += 1;  // encoded below once the tile geometry is known
+      } else {
+        if (nmap + 4 > 4) return fail("too many tensor maps");
+        if (a.H != 2 * d.Ho || a.W != 2 * d.Wo) return fail("conv3 s2: input must be 2x the output grid");
+        nmap += 4;
+      }
+      kb += 9 * p.seg[s].cblocks;
+      kcols += 9 * a.C;
+    }
+  }
+  if (kcols != d.Ktot) return fail("segment K does not add up to the weight K");
+  p.num_kb = kb;
+  if (has_conv) {
+    if (!is_pow2(d.Ho) || !is_pow2(d.Wo)) return fail("conv path needs power-of-two spatial dims");
+    if (d.M != d.NI * d.Ho * d.Wo) return fail("conv M mismatch");
+    p.tw = d.Wo < 128 ? d.Wo : 128;
+    p.th = d.Ho < 128 / p.tw ? d.Ho : 128 / p.tw;
+    p.tn = 128 / (p.tw * p.th);
+    p.tiles_x = d.Wo / p.tw;
+    p.tiles_y = d.Ho / p.th;
+    for (int s = 0; s < d.nseg; ++s) {
+      const ASeg& a = d.seg[s];
+      const int mi = p.seg[s].tmap;
+      uint32_t box[4] = {64, (uint32_t)p.tw, (uint32_t)p.th, (uint32_t)p.tn};
+      if (a.mode == SEG_CONV3) {
+        uint64_t dims[4] = {(uint64_t)a.C, (uint64_t)a.W, (uint64_t)a.H, (uint64_t)a.NI};
+        uint64_t str[3] = {(uint64_t)a.C * 2, (uint64_t)a.W * a.C * 2, (uint64_t)a.H * a.W * a.C * 2};
+        if (!encode_tmap(&l->maps.a[mi], a.ptr, 4, dims, str, box, true, err)) return false;
+      } else if (a.mode == SEG_CONV3S2) {
+        for (int py = 0; py < 2; ++py)
+          for (int px = 0; px < 2; ++px) {
+            const char* base = reinterpret_cast<const char*>(a.ptr) + ((size_t)py * a.W + px) * a.C * 2;
+            uint64_t dims[4] = {(uint64_t)a.C, (uint64_t)a.W / 2, (uint64_t)a.H / 2, (uint64_t)a.NI};
+            uint64_t str[3] = {(uint64_t)2 * a.C * 2, (uint64_t)2 * a.W * a.C * 2, (uint64_t)a.H * a.W * a.C * 2};
+            if (!encode_tmap(&l->maps.a[mi + py * 2 + px], base, 4, dims, str, box, true, err)) return false;
+          }
+      }
+    }
+  }
+  {
+    uint64_t dims[2] = {(uint64_t)d.Ktot, (uint64_t)d.w_rows};
+    uint64_t str[1] = {(uint64_t)d.Ktot * 2};
+    uint32_t box[2] = {64, (uint32_t)bn};
+    if (!encode_tmap(&l->maps.b, d.w, 2, dims, str, box, true, err)) return false;
+  }
+  const int m_tiles = has_conv ? ((d.NI + p.tn - 1) / p.tn) * p.tiles_y * p.tiles_x : (d.M + 127) / 128;
+  l->grid = dim3((d.N + bn - 1) / bn, m_tiles, 1);
+  return true;
+}
+
+template <typename T, int BN> static void launch_one(const GemmLaunch& l, cudaStream_t s) {
+  gemm_tcgen05_kernel<T, BN><<<l.grid, 192, GemmCfg<BN>::SMEM_BYTES, s>>>(l.maps, l.p);
+}
+
+void gemm_launch(const GemmLaunch& l, cudaStream_t s) {
+  if (l.dt == DT_F16) {
+    if (l.bn == 64) launch_one<__half, 64>(l, s);
+    else if (l.bn == 128) launch_one<__half, 128>(l, s);
+    else launch_one<__half, 160>(l, s);
+  } else {
+    if (l.bn == 64) launch_one<__nv_bfloat16, 64>(l, s);
+    else if (l.bn == 128) launch_one<__nv_bfloat16, 128>(l, s);
+    else launch_one<__nv_bfloat16, 160>(l, s);
+  }
+}
+
+template <typename T, int BN> static cudaError_t set_attr() {
+  return cudaFuncSetAttribute(gemm_tcgen05_kernel<T, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              GemmCfg<BN>::SMEM_BYTES);
+}
+
+bool gemm_setup_attributes(std::string* err) {
+  cudaError_t e = cudaSuccess;
+  if (e == cudaSuccess) e = set_attr<__half, 64>();
+  if (e == cudaSuccess) e = set_attr<__half, 128>();
+  if (e == cudaSuccess) e = set_attr<__half, 160>();
+  if (e == cudaSuccess) e = set_attr<__nv_bfloat16, 64>();
+  if (e == cudaSuccess) e = set_attr<__nv_bfloat16, 128>();
+  if (e == cudaSuccess) e = set_attr<__nv_bfloat16, 160>();
+  if (e != cudaSuccess) {
+    if (err) *err = std::string("cudaFuncSetAttribute(gemm): ") + cudaGetErrorString(e);
+    return false;
+  }
+  return true;
+}
+
+// ------------------------------------------------------------------------------------------
+// CUDA-core debug kernel: one thread per output element, same segment / epilogue semantics
+// ------------------------------------------------------------------------------------------
+struct SimpleArgs {
+  GemmDesc d;
+  int bn;
+};
+
+template <typename T>
+__device__ float simple_dot(const GemmDesc& d, int m, int wrow) {
+  const T* w = reinterpret_cast<const T*>(d.w) + (size_t)wrow * d.Ktot;
+  float acc = 0.f;
+  int koff = 0;
+  for (int s = 0; s < d.nseg; ++s) {
+    const ASeg& a = d.seg[s];
+    const T* ap = reinterpret_cast<const T*>(a.ptr);
+    if (a.mode == SEG_PLAIN) {
+      for (int k = 0; k < a.C; ++k) acc += DT<T>::to_f(ap[(size_t)m * a.ld + k]) * DT<T>::to_f(w[koff + k]);
+      koff += a.C;
+    } else {
+      const int x = m % d.Wo, y = (m / d.Wo) % d.Ho, n = m / (d.Wo * d.Ho);
+      const int st = a.mode == SEG_CONV3S2 ? 2 : 1;
+      for (int tap = 0; tap < 9; ++tap) {
+        const int sy = y * st + tap / 3 - 1, sx = x * st + tap % 3 - 1;
+        if (sy >= 0 && sy < a.H && sx >= 0 && sx < a.W) {
+          const T* src = ap + (((size_t)n * a.H + sy) * a.W + sx) * a.C;
+          for (int c = 0; c < a.C; ++c) acc += DT<T>::to_f(src[c]) * DT<T>::to_f(w[koff + tap * a.C + c]);
+        }
+      }
+      koff += 9 * a.C;
+    }
+  }
+  return acc;
+}
+
+template <typename T>
+__global__ void gemm_simple_kernel(const SimpleArgs sa) {
+  const GemmDesc& d = sa.d;
+  const int nout = d.geglu ? d.N / 2 : d.N;
+  const size_t total = (size_t)d.M * nout;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (size_t)gridDim.x * blockDim.x) {
+    const int m = (int)(idx / nout), j = (int)(idx % nout);
+    float v;
+    if (d.geglu) {
+      const int hb = sa.bn / 2;
+      const int rh = (j / hb) * sa.bn + (j % hb), rg = rh + hb;
+      float hv = simple_dot<T>(d, m, rh), gv = simple_dot<T>(d, m, rg);
+      if (d.bias) {
+        hv += d.bias[rh];
+        gv += d.bias[rg];
+      }
+      v = hv * gelu_erf_f(gv);
+    } else {
+      v = simple_dot<T>(d, m, j);
+      if (d.bias) v += d.bias[j];
+      if (d.res) v += DT<T>::to_f(reinterpret_cast<const T*>(d.res)[(size_t)m * d.ldr + j]);
+    }
+    reinterpret_cast<T*>(d.out)[(size_t)m * d.ldo + j] = DT<T>::from_f(v);
+  }
+}
+
+void gemm_simple_launch(const GemmDesc& d, cudaStream_t s) {
+  SimpleArgs sa;
+  sa.d = d;
+  sa.bn = pick_bn(d);
+  const size_t total = (size_t)d.M * (d.geglu ? d.N / 2 : d.N);
+  const int blocks = (int)((total + 255) / 256 < 65535 * 16 ? (total + 255) / 256 : 65535 * 16);
+  if (d.dt == DT_F16) gemm_simple_kernel<__half><<<blocks, 256, 0, s>>>(sa);
+  else gemm_simple_kernel<__nv_bfloat16><<<blocks, 256, 0, s>>>(sa);
+}
+
+}  // namespace rcdm

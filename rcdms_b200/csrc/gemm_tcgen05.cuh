@@ -1,0 +1,267 @@
+// tcgen05 GEMM / implicit-GEMM convolution for sm_100a.
+//
+//   D[M, N] = sum over K-segments of A_seg[M, K_seg] * W[N, K_total]^T   (+ epilogue)
+//
+// One CTA computes a 128 x BN output tile.  Warp roles (192 threads):
+//   warp 0     TMA producer  (one elected lane)  : HBM -> 128B-swizzled smem ring
+//   warp 1     MMA issuer    (one elected lane)  : tcgen05.mma, accumulator in TMEM; owns TMEM alloc
+//   warps 2-5  epilogue      (thread <-> row)    : tcgen05.ld -> bias/residual/GEGLU -> global
+// Two CTAs are co-resident per SM (<= 113 KB smem, <= 256 TMEM columns each) so one CTA's epilogue
+// overlaps the other's main loop.
+//
+// The K loop runs over up to three "segments", each reading A through its own TMA tensor map(s):
+//   SEG_PLAIN    A is a row-major [M, K] matrix             (Linear, conv1x1, im2col'ed conv_in)
+//   SEG_CONV3    A is an NHWC activation; 3x3, stride 1, pad 1: for each tap the SAME 4-D tensor map is
+//                read at spatial offset (kx-1, ky-1); TMA out-of-bounds zero fill implements the padding,
+//                so no im2col buffer ever exists ("im2col-free" implicit GEMM)
+//   SEG_CONV3S2  3x3, stride 2, pad 1: four parity-subsampled 4-D maps (y%2, x%2), tap -> (map, offset)
+// Segments accumulate into the same TMEM tile, which is how conv2 + the 1x1 shortcut of a resblock (whose input
+// is the un-materialised concat [h | skip]) become a single launch.
+#pragma once
+#include "common.cuh"
+
+namespace rcdm {
+
+enum : int { SEG_PLAIN = 0, SEG_CONV3 = 1, SEG_CONV3S2 = 2 };
+
+struct GemmSeg {
+  int mode;     // SEG_*
+  int tmap;     // index of the first A tensor map of this segment
+  int cblocks;  // 64-wide K blocks (per tap for conv segments)
+};
+
+struct GemmParams {
+  int M, N;       // rows, accumulator columns (for GEGLU: 2x the output width)
+  int num_kb;     // total number of 64-wide K blocks over all segments
+  int nseg;
+  GemmSeg seg[3];
+  // conv tile geometry: a 128-row M tile is a (tn images) x (th rows) x (tw cols) box of the OUTPUT grid
+  int tw, th, tn, tiles_x, tiles_y;
+  // epilogue
+  void* out;
+  int ldo;
+  const float* bias;  // [N] (GEGLU: packed like the weight rows) or nullptr
+  const void* res;    // residual [M, ldr] or nullptr (may alias out)
+  int ldr;
+  int geglu;          // 1: out[m, j] = (acc[j] + b[j]) * gelu(acc[BN/2 + j] + b[BN/2 + j]) per tile
+};
+
+struct GemmMaps {
+  CUtensorMap a[4];
+  CUtensorMap b;
+};
+
+template <int BN> struct GemmCfg {
+  static constexpr int BM = 128, BK = 64;
+  static constexpr int STAGES = (BN <= 64) ? 4 : 3;
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int TMEM_COLS = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+template <typename T, int BN>
+__global__ void __launch_bounds__(192, 2)
+gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
+  using Cfg = GemmCfg<BN>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + STAGES * Cfg::A_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + STAGES;
+  uint64_t* tmem_full_bar = bars + 2 * STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int n_tile = blockIdx.x;
+  const int m_tile = blockIdx.y;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&maps.b);
+    tma_prefetch_desc(&maps.a[0]);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int i = 0; i < STAGES; ++i) {
+        mbar_init(&full_bar[i], 1);
+        mbar_init(&empty_bar[i], 1);
+      }
+      mbar_init(tmem_full_bar, 1);
+      fence_mbar_init();
+    }
+    __syncwarp();
+    tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // =================================== TMA producer ===================================
+    if (elect_one()) {
+      // decode the conv tile origin (only used by conv segments)
+      int t = m_tile;
+      const int tx = t % p.tiles_x;
+      t /= p.tiles_x;
+      const int ty = t % p.tiles_y;
+      const int tb = t / p.tiles_y;
+      const int x0 = tx * p.tw, y0 = ty * p.th, n0 = tb * p.tn;
+      int stage = 0;
+      uint32_t phase = 0;
+      int kb = 0;
+      for (int s = 0; s < p.nseg; ++s) {
+        const GemmSeg sg = p.seg[s];
+        const int ntap = (sg.mode == SEG_PLAIN) ? 1 : 9;
+        for (int tap = 0; tap < ntap; ++tap) {
+          int mi = sg.tmap, dx = 0, dy = 0;
+          if (sg.mode == SEG_CONV3) {
+            dy = tap / 3 - 1;
+            dx = tap % 3 - 1;
+          } else if (sg.mode == SEG_CONV3S2) {
+            const int ky = tap / 3, kx = tap % 3;
+            const int py = (ky + 1) & 1, px = (kx + 1) & 1;  // parity of (2y + ky - 1)
+            dy = (ky == 0) ? -1 : 0;
+            dx = (kx == 0) ? -1 : 0;
+            mi = sg.tmap + py * 2 + px;
+          }
+          for (int c = 0; c < sg.cblocks; ++c, ++kb) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+            void* sa = smem_a + stage * Cfg::A_BYTES;
+            void* sb = smem_b + stage * Cfg::B_BYTES;
+            if (sg.mode == SEG_PLAIN)
+              tma_load_2d(sa, &maps.a[mi], &full_bar[stage], c * 64, m_tile * 128);
+            else
+              tma_load_4d(sa, &maps.a[mi], &full_bar[stage], c * 64, x0 + dx, y0 + dy, n0);
+            tma_load_2d(sb, &maps.b, &full_bar[stage], kb * 64, n_tile * BN);
+            if (++stage == STAGES) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =================================== MMA issuer ===================================
+    if (elect_one()) {
+      constexpr uint32_t idesc = umma_idesc_f16(DT<T>::umma_fmt, 128, BN, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = 0; kb < p.num_kb; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(smem_a + stage * Cfg::A_BYTES);
+        const uint32_t b_addr = smem_u32(smem_b + stage * Cfg::B_BYTES);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          // K-major, 128B swizzle: rows at 128 B, 8-row groups at 1024 B; +32 B per 16-element K step
+          const uint64_t ad = umma_smem_desc(a_addr + k * 32, 16, 1024, UMMA_SWIZZLE_128B);
+          const uint64_t bd = umma_smem_desc(b_addr + k * 32, 16, 1024, UMMA_SWIZZLE_128B);
+          umma_f16_ss(tmem_base, ad, bd, idesc, (kb | k) != 0);
+        }
+        umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs have read it
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+      umma_commit(tmem_full_bar);
+    }
+  } else {
+    // =================================== epilogue ===================================
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const int row = q * 32 + lane;
+    const int m = m_tile * 128 + row;
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+    const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16);
+    T* out = reinterpret_cast<T*>(p.out);
+    const T* res = reinterpret_cast<const T*>(p.res);
+    const bool row_ok = m < p.M;
+    if (!p.geglu) {
+      const bool vec_ok = (p.N % 8 == 0) && (p.ldo % 8 == 0);
+#pragma unroll 1
+      for (int c = 0; c < BN; c += 16) {
+        const int n = n_tile * BN + c;
+        if (n >= p.N) break;  // warp-uniform
+        uint32_t r[16];
+        tmem_ld16(taddr + c, r);
+        tmem_wait_ld();
+        if (!row_ok) continue;
+        float v[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+        if (p.bias) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            if (n + i < p.N) v[i] += __ldg(p.bias + n + i);
+        }
+        if (vec_ok) {
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            if (n + h * 8 < p.N) {
+              if (res) {
+                float rr[8];
+                unpack8<T>(*reinterpret_cast<const uint4*>(res + (size_t)m * p.ldr + n + h * 8), rr);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[h * 8 + i] += rr[i];
+              }
+              *reinterpret_cast<uint4*>(out + (size_t)m * p.ldo + n + h * 8) = pack8<T>(v + h * 8);
+            }
+          }
+        } else {
+          for (int i = 0; i < 16; ++i) {
+            if (n + i < p.N) {
+              float x = v[i];
+              if (res) x += DT<T>::to_f(res[(size_t)m * p.ldr + n + i]);
+              out[(size_t)m * p.ldo + n + i] = DT<T>::from_f(x);
+            }
+          }
+        }
+      }
+    } else {
+      // accumulator columns [0, BN/2) hold h, [BN/2, BN) the gate of output columns n_tile*BN/2 + [0, BN/2)
+      constexpr int HB = BN / 2;
+      const int nout = p.N / 2;
+#pragma unroll 1
+      for (int c = 0; c < HB; c += 16) {
+        const int j = n_tile * HB + c;
+        if (j >= nout) break;
+        uint32_t rh[16], rg[16];
+        tmem_ld16(taddr + c, rh);
+        tmem_ld16(taddr + HB + c, rg);
+        tmem_wait_ld();
+        if (!row_ok) continue;
+        float v[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          float hv = __uint_as_float(rh[i]), gv = __uint_as_float(rg[i]);
+          if (p.bias) {
+            hv += __ldg(p.bias + n_tile * BN + c + i);
+            gv += __ldg(p.bias + n_tile * BN + HB + c + i);
+          }
+          v[i] = hv * gelu_erf_f(gv);
+        }
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+          if (j + h * 8 < nout)
+            *reinterpret_cast<uint4*>(out + (size_t)m * p.ldo + j + h * 8) = pack8<T>(v + h * 8);
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+  }
+}
+
+}  // namespace rcdm

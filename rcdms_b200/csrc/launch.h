@@ -1,0 +1,80 @@
+// Host-side launch descriptors shared by the translation units of librcdm_b200.so.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+
+#include "attention.cuh"
+#include "gemm_tcgen05.cuh"
+
+namespace rcdm {
+
+// ---- TMA tensor-map encoding (driver entry point resolved at run time; no link-time libcuda dependency) ----
+// dims/box innermost-first; strides_bytes has rank-1 entries (dimension 0 is contiguous). 16-bit elements.
+bool encode_tmap(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                 const uint32_t* box, bool swizzle128, std::string* err);
+
+// ---- GEMM / implicit-GEMM conv -------------------------------------------------------------------------
+struct ASeg {
+  int mode;         // SEG_PLAIN / SEG_CONV3 / SEG_CONV3S2
+  const void* ptr;  // plain: [M, ld]; conv: NHWC activation [NI, H, W, C]
+  int C;            // K of this segment per tap
+  int ld;           // plain: row pitch in elements
+  int H, W, NI;     // conv: INPUT spatial dims and image count
+};
+struct GemmDesc {
+  int dt;  // DT_F16 / DT_BF16
+  int M, N;
+  int nseg;
+  ASeg seg[3];
+  const void* w;  // [w_rows, Ktot] row-major, K order = segments in sequence (conv: tap-major, channel-minor)
+  int Ktot, w_rows;
+  int Ho, Wo, NI;  // conv OUTPUT grid (M = NI*Ho*Wo); ignored for plain-only GEMMs
+  void* out;
+  int ldo;
+  const float* bias;
+  const void* res;
+  int ldr;
+  int geglu;
+  int force_bn;  // 0 = heuristic
+};
+struct GemmLaunch {
+  GemmMaps maps;
+  GemmParams p;
+  dim3 grid;
+  int bn, dt;
+};
+bool gemm_prepare(const GemmDesc& d, GemmLaunch* l, std::string* err);
+void gemm_launch(const GemmLaunch& l, cudaStream_t s);
+void gemm_simple_launch(const GemmDesc& d, cudaStream_t s);  // CUDA-core debug path (same semantics)
+bool gemm_setup_attributes(std::string* err);                // opt-in dynamic smem; call once per process/device
+constexpr int GEGLU_BN = 128;
+
+// ---- attention ---------------------------------------------------------------------------------------
+struct AttnDesc {
+  int dt;
+  const void* q;  // q[(img*S_q + i)*ldq + h*d + c]
+  int ldq;
+  const void* k;
+  const void* v;  // k/v[(img*S_kv + j)*ldkv + h*d + c]
+  int ldkv;
+  int S_q, S_kv, heads, d, batch;
+  void* out;
+  int ldo;
+};
+struct AttnLaunch {
+  AttnMaps maps;
+  AttnParams p;
+  dim3 grid;
+  int dpad, dt;
+};
+bool attn_prepare(const AttnDesc& d, AttnLaunch* l, std::string* err);
+void attn_launch(const AttnLaunch& l, cudaStream_t s);
+void attn_simple_launch(const AttnDesc& d, cudaStream_t s);
+bool attn_setup_attributes(std::string* err);
+void temporal_attn_launch(int dt, const void* qkv, void* out, int batch, int frames, int hw, int heads, int d,
+                          cudaStream_t s);
+
+}  // namespace rcdm

@@ -1,0 +1,94 @@
+// Host launchers for the normalisation kernels (shared by the UNet plan and the single-kernel C entry points).
+#include "internal.h"
+
+namespace rcdm {
+
+size_t gn_scratch_bytes(int nstat, int groups) {
+  // partial [nstat][<=1024 chunks][groups] float2 is bounded by chunks*nstat <= 1024 + nstat
+  return 65536 + (size_t)(1024 + 2 * (size_t)nstat) * groups * 8 + (size_t)nstat * groups * 8 + 2048;
+}
+
+void gn_configure(GnLaunch* l, int dt, const void* x0, int C0, const void* x1, int C1, int rows, int rows_per_stat,
+                  int groups, float eps, const float* gamma, const float* beta, void* out, int silu, void* scratch) {
+  GnArgs& a = l->a;
+  memset(&a, 0, sizeof a);
+  const int C = C0 + C1;
+  a.x0 = x0;
+  a.x1 = x1;
+  a.C0 = C0;
+  a.C1 = C1;
+  a.groups = groups;
+  a.rows_per_stat = rows_per_stat;
+  a.nstat = rows / rows_per_stat;
+  a.eps = eps;
+  a.gamma = gamma;
+  a.beta = beta;
+  a.out = out;
+  a.silu = silu;
+  int target = 592 / a.nstat;
+  if (target < 1) target = 1;
+  if (target > 1024) target = 1024;
+  int chunks = 1;
+  for (int c = target; c >= 1; --c)
+    if (rows_per_stat % c == 0) {
+      chunks = c;
+      break;
+    }
+  a.rows_per_cta = rows_per_stat / chunks;
+  // fixed layout: [counters | stats | partial] so the (always-zero-at-rest) counters never alias partial sums
+  unsigned char* s = reinterpret_cast<unsigned char*>(scratch);
+  a.counters = reinterpret_cast<unsigned*>(s);
+  size_t off = 65536;  // counters region is fixed-size (<= 16384 statistic batches) for every caller
+  a.stats = reinterpret_cast<float2*>(s + off);
+  off += ((size_t)a.nstat * groups * 8 + 1023) & ~size_t(1023);
+  a.partial = reinterpret_cast<float2*>(s + off);
+  const int vecs = C / 8;
+  int k = 256 / vecs;
+  if (k > a.rows_per_cta) k = a.rows_per_cta;
+  if (k < 1) k = 1;
+  while (vecs * k < groups) ++k;  // the group reduction needs >= groups threads
+  l->threads = vecs * k;
+  l->smem = (size_t)k * 2 * C * 4;
+  l->grid = dim3(chunks, a.nstat);
+  l->total_vecs = (size_t)rows * vecs;
+  size_t g = (l->total_vecs + 255) / 256;
+  l->agrid = (int)(g < 148 * 8 ? (g ? g : 1) : 148 * 8);
+  l->dt = dt;
+}
+
+void gn_run(const GnLaunch& l, cudaStream_t s) {
+  if (l.dt == DT_F16) {
+    gn_stats_kernel<__half><<<l.grid, l.threads, l.smem, s>>>(l.a);
+    gn_apply_kernel<__half><<<l.agrid, 256, 0, s>>>(l.a, l.total_vecs);
+  } else {
+    gn_stats_kernel<__nv_bfloat16><<<l.grid, l.threads, l.smem, s>>>(l.a);
+    gn_apply_kernel<__nv_bfloat16><<<l.agrid, 256, 0, s>>>(l.a, l.total_vecs);
+  }
+  g_launches += 2;
+}
+
+bool ln_run(int dt, const void* x, void* o, const float* gp, const float* bp, int nrows, int C, float eps,
+            const float* pep, int rows_per_frame, int frames, cudaStream_t s) {
+  const int maxv = (C / 8 + 31) / 32;
+  if (maxv > 5 || C % 8) return false;
+  const int blocks = (nrows + 7) / 8;
+#define RCDM_LN(T, V)                                                                                           \
+  layernorm_kernel<T, V><<<blocks, 256, 0, s>>>(reinterpret_cast<const T*>(x), reinterpret_cast<T*>(o), gp, bp, \
+                                                nrows, C, eps, pep, rows_per_frame, frames)
+  if (dt == DT_F16) {
+    if (maxv <= 1) RCDM_LN(__half, 1);
+    else if (maxv == 2) RCDM_LN(__half, 2);
+    else if (maxv == 3) RCDM_LN(__half, 3);
+    else RCDM_LN(__half, 5);
+  } else {
+    if (maxv <= 1) RCDM_LN(__nv_bfloat16, 1);
+    else if (maxv == 2) RCDM_LN(__nv_bfloat16, 2);
+    else if (maxv == 3) RCDM_LN(__nv_bfloat16, 3);
+    else RCDM_LN(__nv_bfloat16, 5);
+  }
+#undef RCDM_LN
+  g_launches++;
+  return true;
+}
+
+}  // namespace rcdm

@@ -1,0 +1,190 @@
+// HBM-bound normalisation passes on channels-last token matrices [rows, C] (16-bit storage, fp32 math).
+//   * GroupNorm statistics (deterministic two-level reduction; the last CTA of each statistic batch finalises)
+//   * GroupNorm apply (+SiLU), reading a virtual channel-concat of two sources (skip connections)
+//   * LayerNorm (+ temporal sinusoidal positional encoding)
+// Reference semantics: F.group_norm on the 5-D tensor (resnet.py:185,197; unet.py:455 -> statistics span all frames)
+// or per frame (attention.py:328; motion_module.py:162), nn.LayerNorm eps 1e-5 (attention.py:412,429,435;
+// motion_module.py:226,232) followed by `x + pe[:, :f]` (motion_module.py:264-267).
+#pragma once
+#include "common.cuh"
+
+namespace rcdm {
+
+struct GnArgs {
+  const void* x0;   // [rows, C0]
+  const void* x1;   // [rows, C1] or nullptr : channels [C0, C0+C1)
+  int C0, C1;
+  int groups;       // 32
+  int rows_per_stat;   // rows sharing one set of statistics (f*h*w for 5-D GN, h*w for per-frame GN)
+  int nstat;           // number of statistic batches = rows / rows_per_stat
+  int rows_per_cta;    // rows handled by one stats CTA (divides rows_per_stat)
+  float eps;
+  float2* partial;     // [nstat][chunks][groups] (sum, sumsq)
+  unsigned* counters;  // [nstat], zero before first use; left zero by the kernel
+  float2* stats;       // [nstat][groups] (mean, rstd)
+  const float* gamma;  // [C]
+  const float* beta;   // [C]
+  void* out;           // [rows, C]
+  int silu;
+};
+
+// grid (chunks, nstat); block = vecs * k threads, vecs = C/8; thread owns 8 fixed channels.
+template <typename T>
+__global__ void gn_stats_kernel(const GnArgs a) {
+  extern __shared__ float sm[];  // [k][2*C] per-(row lane, channel) sum / sumsq  (fixed-order => deterministic)
+  const int C = a.C0 + a.C1;
+  const int vecs = C / 8;
+  const int k = blockDim.x / vecs;
+  const int v = threadIdx.x % vecs;
+  const int rl = threadIdx.x / vecs;
+  const int chunk = blockIdx.x, sb = blockIdx.y;
+  const int chunks = gridDim.x;
+  if (rl < k) {
+    float s[8], ss[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s[i] = ss[i] = 0.f;
+    const int c = v * 8;
+    const T* src = reinterpret_cast<const T*>(c < a.C0 ? a.x0 : a.x1);
+    const int ld = c < a.C0 ? a.C0 : a.C1;
+    const int cc = c < a.C0 ? c : c - a.C0;
+    const size_t row0 = (size_t)sb * a.rows_per_stat + (size_t)chunk * a.rows_per_cta;
+    for (int r = rl; r < a.rows_per_cta; r += k) {
+      float f[8];
+      unpack8<T>(__ldg(reinterpret_cast<const uint4*>(src + (row0 + r) * ld + cc)), f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        s[i] += f[i];
+        ss[i] += f[i] * f[i];
+      }
+    }
+    float* dst = sm + (size_t)rl * 2 * C;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      dst[c + i] = s[i];
+      dst[C + c + i] = ss[i];
+    }
+  }
+  __syncthreads();
+  const int cpg = C / a.groups;
+  if (threadIdx.x < a.groups) {
+    float gs = 0.f, gss = 0.f;
+    for (int l = 0; l < k; ++l) {
+      const float* src = sm + (size_t)l * 2 * C + threadIdx.x * cpg;
+      for (int i = 0; i < cpg; ++i) {
+        gs += src[i];
+        gss += src[C + i];
+      }
+    }
+    a.partial[((size_t)sb * chunks + chunk) * a.groups + threadIdx.x] = make_float2(gs, gss);
+  }
+  // last CTA of this statistic batch reduces the partials in a fixed order (deterministic)
+  __shared__ unsigned is_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned prev = atomicAdd(&a.counters[sb], 1u);
+    is_last = (prev == (unsigned)chunks - 1);
+  }
+  __syncthreads();
+  if (is_last) {
+    __threadfence();
+    if (threadIdx.x < a.groups) {
+      double gs = 0.0, gss = 0.0;
+      for (int ch = 0; ch < chunks; ++ch) {
+        float2 pz = __ldcg(&a.partial[((size_t)sb * chunks + ch) * a.groups + threadIdx.x]);
+        gs += pz.x;
+        gss += pz.y;
+      }
+      const double n = (double)a.rows_per_stat * cpg;
+      const double mean = gs / n;
+      double var = gss / n - mean * mean;
+      if (var < 0) var = 0;
+      a.stats[(size_t)sb * a.groups + threadIdx.x] = make_float2((float)mean, (float)(1.0 / sqrt(var + (double)a.eps)));
+    }
+    if (threadIdx.x == 0) a.counters[sb] = 0;
+  }
+}
+
+// one thread per 8-channel vector of one row; grid-stride over rows*vecs
+template <typename T>
+__global__ void gn_apply_kernel(const GnArgs a, size_t total_vecs) {
+  const int C = a.C0 + a.C1;
+  const int vecs = C / 8;
+  const int cpg = C / a.groups;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total_vecs;
+       idx += (size_t)gridDim.x * blockDim.x) {
+    const size_t row = idx / vecs;
+    const int c = (int)(idx % vecs) * 8;
+    const int sb = (int)(row / a.rows_per_stat);
+    const T* src = reinterpret_cast<const T*>(c < a.C0 ? a.x0 : a.x1);
+    const int ld = c < a.C0 ? a.C0 : a.C1;
+    const int cc = c < a.C0 ? c : c - a.C0;
+    float f[8];
+    unpack8<T>(__ldg(reinterpret_cast<const uint4*>(src + row * ld + cc)), f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float2 st = __ldg(&a.stats[(size_t)sb * a.groups + (c + i) / cpg]);
+      float y = (f[i] - st.x) * st.y * __ldg(a.gamma + c + i) + __ldg(a.beta + c + i);
+      f[i] = a.silu ? silu_f(y) : y;
+    }
+    *reinterpret_cast<uint4*>(reinterpret_cast<T*>(a.out) + row * C + c) = pack8<T>(f);
+  }
+}
+
+// LayerNorm over the last dim; one warp per row; C multiple of 8, C <= 32*8*MAXV.
+// pe (optional): fp32 [frames, C]; frame of a row = (row / rows_per_frame) % frames.
+template <typename T, int MAXV>
+__global__ void layernorm_kernel(const T* __restrict__ x, T* __restrict__ out, const float* __restrict__ gamma,
+                                 const float* __restrict__ beta, int rows, int C, float eps,
+                                 const float* __restrict__ pe, int rows_per_frame, int frames) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= rows) return;
+  const int vecs = C / 8;
+  float f[MAXV][8];
+  float sum = 0.f;
+#pragma unroll
+  for (int j = 0; j < MAXV; ++j) {
+    const int v = lane + j * 32;
+    if (v < vecs) {
+      unpack8<T>(__ldg(reinterpret_cast<const uint4*>(x + (size_t)warp * C + v * 8)), f[j]);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) sum += f[j][i];
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  const float mean = sum / C;
+  float var = 0.f;
+#pragma unroll
+  for (int j = 0; j < MAXV; ++j) {
+    const int v = lane + j * 32;
+    if (v < vecs) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float d = f[j][i] - mean;
+        var += d * d;
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) var += __shfl_xor_sync(0xffffffffu, var, o);
+  const float rstd = rsqrtf(var / C + eps);
+  const float* pe_row = pe ? pe + (size_t)((warp / rows_per_frame) % frames) * C : nullptr;
+#pragma unroll
+  for (int j = 0; j < MAXV; ++j) {
+    const int v = lane + j * 32;
+    if (v < vecs) {
+      float y[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int c = v * 8 + i;
+        y[i] = (f[j][i] - mean) * rstd * __ldg(gamma + c) + __ldg(beta + c);
+        if (pe_row) y[i] += __ldg(pe_row + c);
+      }
+      *reinterpret_cast<uint4*>(out + (size_t)warp * C + v * 8) = pack8<T>(y);
+    }
+  }
+}
+
+}  // namespace rcdm

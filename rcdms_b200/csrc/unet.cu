@@ -1,0 +1,1074 @@
+// UNet3DConditionModel on sm_100a: model construction (state-dict surface), weight repacking, execution plan
+// (activation arena + every TMA descriptor resolved once per problem size) and the forward pass.
+// Reference: src/models/unet.py:37-462, unet_blocks.py, resnet.py, attention.py, motion_module.py.
+//
+// Layout: every activation is a channels-last token matrix [(b f y x), C] in the compute dtype, so conv,
+// Linear and attention share one layout and none of the reference's einops rearranges exists here.
+#include <atomic>
+#include <cmath>
+#include <cstring>
+
+#include "elementwise.cuh"
+#include "internal.h"
+
+namespace rcdm {
+
+thread_local std::string g_err;
+std::atomic<uint64_t> g_launches{0};
+
+int set_err(const std::string& m) {
+  g_err = m;
+  return 1;
+}
+
+#define CUDA_OK(expr)                                                                  \
+  do {                                                                                 \
+    cudaError_t _e = (expr);                                                           \
+    if (_e != cudaSuccess) return set_err(std::string(#expr) + ": " + cudaGetErrorString(_e)); \
+  } while (0)
+
+static inline int grid_for(size_t total, int block, int cap = 148 * 16) {
+  size_t g = (total + block - 1) / block;
+  return (int)(g < (size_t)cap ? (g ? g : 1) : cap);
+}
+
+// ==========================================================================================
+// model construction
+// ==========================================================================================
+struct Builder {
+  rcdm_unet_impl* h;
+  size_t top = 0;
+  size_t take(size_t bytes) {
+    size_t o = top;
+    top += (bytes + 255) & ~size_t(255);
+    return o;
+  }
+  Mat mat(int rows, int cols) {
+    Mat m;
+    m.rows = rows;
+    m.cols = cols;
+    m.off = take((size_t)rows * cols * 2);
+    return m;
+  }
+  Vec vec(int n) {
+    Vec v;
+    v.n = n;
+    v.off = take((size_t)n * 4);
+    return v;
+  }
+  void slot(const std::string& name, std::initializer_list<int64_t> dims, int kind, size_t dst, int ldd = 0,
+            int col_off = 0, int row_off = 0, int geglu_bn = 0, int cin = 0) {
+    Slot s;
+    s.name = name;
+    s.ndim = (int)dims.size();
+    int i = 0;
+    for (auto d : dims) s.dims[i++] = d;
+    s.kind = kind;
+    s.dst = dst;
+    s.ldd = ldd;
+    s.col_off = col_off;
+    s.row_off = row_off;
+    s.geglu_bn = geglu_bn;
+    s.cin = cin;
+    h->slot_index[name] = (int)h->slots.size();
+    h->slots.push_back(s);
+  }
+  Vec vslot(const std::string& name, int n) {
+    Vec v = vec(n);
+    slot(name, {n}, SLOT_VEC, v.off);
+    return v;
+  }
+  Mat lin(const std::string& name, int n, int k) {  // nn.Linear weight [n, k]
+    Mat m = mat(n, k);
+    slot(name, {n, k}, SLOT_MAT, m.off, k);
+    return m;
+  }
+
+  void resnet(const std::string& p, int cin, int cout, ResW& r) {
+    const int temb = h->temb_dim;
+    r.cin = cin;
+    r.cout = cout;
+    r.shortcut = cin != cout;
+    r.n1g = vslot(p + ".norm1.weight", cin);
+    r.n1b = vslot(p + ".norm1.bias", cin);
+    r.c1 = mat(cout, 9 * cin);
+    slot(p + ".conv1.weight", {cout, cin, 3, 3}, SLOT_CONV3, r.c1.off, 9 * cin, 0, 0, 0, cin);
+    r.temb_row = h->temb_rows;
+    h->temb_rows += cout;
+    // conv1.bias / time_emb_proj.{weight,bias} land in the concatenated per-step tables (filled in finish())
+    slot(p + ".conv1.bias", {cout}, SLOT_VEC, 0, 0, 0, r.temb_row);
+    slot(p + ".time_emb_proj.weight", {cout, temb}, SLOT_MAT, 0, temb, 0, r.temb_row);
+    slot(p + ".time_emb_proj.bias", {cout}, SLOT_VEC, 0, 0, 0, r.temb_row);
+    r.n2g = vslot(p + ".norm2.weight", cout);
+    r.n2b = vslot(p + ".norm2.bias", cout);
+    const int k2 = 9 * cout + (r.shortcut ? cin : 0);
+    r.c2 = mat(cout, k2);
+    slot(p + ".conv2.weight", {cout, cout, 3, 3}, SLOT_CONV3, r.c2.off, k2, 0, 0, 0, cout);
+    r.c2b = vslot(p + ".conv2.bias", cout);
+    r.c2beff = vec(cout);
+    if (r.shortcut) {
+      slot(p + ".conv_shortcut.weight", {cout, cin, 1, 1}, SLOT_MAT, r.c2.off, k2, 9 * cout);
+      r.scb = vslot(p + ".conv_shortcut.bias", cout);
+    }
+  }
+  void attn(const std::string& p, int C, int kvdim, bool cross, AttW& a) {
+    if (!cross) {
+      a.qkv = mat(3 * C, C);
+      slot(p + ".to_q.weight", {C, C}, SLOT_MAT, a.qkv.off, C, 0, 0);
+      slot(p + ".to_k.weight", {C, C}, SLOT_MAT, a.qkv.off, C, 0, C);
+      slot(p + ".to_v.weight", {C, C}, SLOT_MAT, a.qkv.off, C, 0, 2 * C);
+    } else {
+      a.q = lin(p + ".to_q.weight", C, C);
+      a.kv = mat(2 * C, kvdim);
+      slot(p + ".to_k.weight", {C, kvdim}, SLOT_MAT, a.kv.off, kvdim, 0, 0);
+      slot(p + ".to_v.weight", {C, kvdim}, SLOT_MAT, a.kv.off, kvdim, 0, C);
+    }
+    a.out = lin(p + ".to_out.0.weight", C, C);
+    a.outb = vslot(p + ".to_out.0.bias", C);
+  }
+  void ff(const std::string& p, int C, Mat& ff1, Vec& ff1b, Mat& ff2, Vec& ff2b) {
+    ff1 = mat(8 * C, C);
+    slot(p + ".net.0.proj.weight", {8 * C, C}, SLOT_MAT, ff1.off, C, 0, 0, GEGLU_BN);
+    ff1b = vec(8 * C);
+    slot(p + ".net.0.proj.bias", {8 * C}, SLOT_VEC, ff1b.off, 0, 0, 0, GEGLU_BN);
+    ff2 = lin(p + ".net.2.weight", C, 4 * C);
+    ff2b = vslot(p + ".net.2.bias", C);
+  }
+  void transformer(const std::string& p, int C, TfW& t) {
+    const std::string b = p + ".transformer_blocks.0";
+    t.C = C;
+    t.ng = vslot(p + ".norm.weight", C);
+    t.nb = vslot(p + ".norm.bias", C);
+    t.pi = mat(C, C);
+    slot(p + ".proj_in.weight", {C, C, 1, 1}, SLOT_MAT, t.pi.off, C);
+    t.pib = vslot(p + ".proj_in.bias", C);
+    attn(b + ".attn1", C, C, false, t.a1);
+    t.ln1g = vslot(b + ".norm1.weight", C);
+    t.ln1b = vslot(b + ".norm1.bias", C);
+    attn(b + ".attn2", C, h->cfg.cross_attention_dim, true, t.a2);
+    t.ln2g = vslot(b + ".norm2.weight", C);
+    t.ln2b = vslot(b + ".norm2.bias", C);
+    ff(b + ".ff", C, t.ff1, t.ff1b, t.ff2, t.ff2b);
+    t.ln3g = vslot(b + ".norm3.weight", C);
+    t.ln3b = vslot(b + ".norm3.bias", C);
+    t.po = mat(C, C);
+    slot(p + ".proj_out.weight", {C, C, 1, 1}, SLOT_MAT, t.po.off, C);
+    t.pob = vslot(p + ".proj_out.bias", C);
+  }
+  void motion(const std::string& p0, int C, MoW& m) {
+    const std::string p = p0 + ".temporal_transformer";
+    const std::string b = p + ".transformer_blocks.0";
+    const int na = h->cfg.motion_attn_blocks, ml = h->cfg.motion_max_len;
+    m.C = C;
+    m.ng = vslot(p + ".norm.weight", C);
+    m.nb = vslot(p + ".norm.bias", C);
+    slot(p + ".prior_norm.weight", {C}, SLOT_IGNORE, 0);  // stage-1 only (motion_module.py:150-153)
+    slot(p + ".prior_norm.bias", {C}, SLOT_IGNORE, 0);
+    m.pi = lin(p + ".proj_in.weight", C, C);
+    m.pib = vslot(p + ".proj_in.bias", C);
+    for (int i = 0; i < na; ++i) {
+      const std::string a = b + ".attention_blocks." + std::to_string(i);
+      attn(a, C, C, false, m.att[i]);
+      m.pe[i] = vec(ml * C);
+      slot(a + ".pos_encoder.pe", {1, ml, C}, SLOT_VEC, m.pe[i].off);
+    }
+    for (int i = 0; i < na; ++i) {
+      m.lng[i] = vslot(b + ".norms." + std::to_string(i) + ".weight", C);
+      m.lnb[i] = vslot(b + ".norms." + std::to_string(i) + ".bias", C);
+    }
+    ff(b + ".ff", C, m.ff1, m.ff1b, m.ff2, m.ff2b);
+    m.ffng = vslot(b + ".ff_norm.weight", C);
+    m.ffnb = vslot(b + ".ff_norm.bias", C);
+    m.po = lin(p + ".proj_out.weight", C, C);
+    m.pob = vslot(p + ".proj_out.bias", C);
+  }
+};
+
+static int build_model(rcdm_unet_impl* h) {
+  const rcdm_unet_config& c = h->cfg;
+  if (c.num_blocks < 1 || c.num_blocks > RCDM_MAX_BLOCKS) return set_err("num_blocks out of range");
+  if (c.compute_dtype != RCDM_DT_F16 && c.compute_dtype != RCDM_DT_BF16)
+    return set_err("compute_dtype must be RCDM_DT_F16 or RCDM_DT_BF16 (no fp32 tensor-core path)");
+  if (c.motion_attn_blocks > 4) return set_err("at most 4 temporal attention blocks");
+  if (c.motion_max_len > 5) return set_err("temporal_position_encoding_max_len > 5 is not supported");
+  for (int i = 0; i < c.num_blocks; ++i) {
+    const int C = c.block_out_channels[i];
+    if (C % 64 != 0 || C % c.norm_num_groups != 0 || C % (8 * c.attention_heads) != 0)
+      return set_err("block_out_channels must be multiples of 64, of norm_num_groups and of 8*heads");
+  }
+  if (c.cross_attention_dim % 8 != 0) return set_err("cross_attention_dim must be a multiple of 8");
+  h->dt = c.compute_dtype;
+  Builder b{h};
+  const int c0 = c.block_out_channels[0];
+  h->temb_dim = 4 * c0;
+  h->temb_rows = 0;
+  h->conv_in_kpad = (9 * c.in_channels + 7) / 8 * 8;
+  h->conv_in_w = b.mat(c0, h->conv_in_kpad);
+  b.slot("conv_in.weight", {c0, c.in_channels, 3, 3}, SLOT_CONV3, h->conv_in_w.off, h->conv_in_kpad, 0, 0, 0,
+         c.in_channels);
+  h->conv_in_b = b.vslot("conv_in.bias", c0);
+  h->l1w = b.lin("time_embedding.linear_1.weight", h->temb_dim, c0);
+  h->l1b = b.vslot("time_embedding.linear_1.bias", h->temb_dim);
+  h->l2w = b.lin("time_embedding.linear_2.weight", h->temb_dim, h->temb_dim);
+  h->l2b = b.vslot("time_embedding.linear_2.bias", h->temb_dim);
+
+  h->down.resize(c.num_blocks);
+  int out_c = c0;
+  for (int i = 0; i < c.num_blocks; ++i) {
+    const int in_c = out_c;
+    out_c = c.block_out_channels[i];
+    BlockW& blk = h->down[i];
+    blk.C = out_c;
+    blk.layers.resize(c.layers_per_block);
+    const std::string p = "down_blocks." + std::to_string(i);
+    if (c.down_has_attn[i])
+      for (int j = 0; j < c.layers_per_block; ++j) {
+        blk.layers[j].has_tf = true;
+        b.transformer(p + ".attentions." + std::to_string(j), out_c, blk.layers[j].tf);
+      }
+    for (int j = 0; j < c.layers_per_block; ++j)
+      b.resnet(p + ".resnets." + std::to_string(j), j == 0 ? in_c : out_c, out_c, blk.layers[j].res);
+    if (c.use_motion_module && c.motion_down[i])
+      for (int j = 0; j < c.layers_per_block; ++j) {
+        blk.layers[j].has_mo = true;
+        b.motion(p + ".motion_modules." + std::to_string(j), out_c, blk.layers[j].mo);
+      }
+    blk.sampler = i != c.num_blocks - 1;
+    if (blk.sampler) {
+      blk.sw = b.mat(out_c, 9 * out_c);
+      b.slot(p + ".downsamplers.0.conv.weight", {out_c, out_c, 3, 3}, SLOT_CONV3, blk.sw.off, 9 * out_c, 0, 0, 0, out_c);
+      blk.sb = b.vslot(p + ".downsamplers.0.conv.bias", out_c);
+    }
+  }
+  h->up.resize(c.num_blocks);
+  out_c = c.block_out_channels[c.num_blocks - 1];
+  for (int i = 0; i < c.num_blocks; ++i) {
+    const int prev = out_c;
+    out_c = c.block_out_channels[c.num_blocks - 1 - i];
+    const int in_idx = c.num_blocks - 1 - (i + 1 < c.num_blocks ? i + 1 : c.num_blocks - 1);
+    const int in_c = c.block_out_channels[in_idx];
+    BlockW& blk = h->up[i];
+    blk.C = out_c;
+    const int nl = c.layers_per_block + 1;
+    blk.layers.resize(nl);
+    const std::string p = "up_blocks." + std::to_string(i);
+    if (c.up_has_attn[i])
+      for (int j = 0; j < nl; ++j) {
+        blk.layers[j].has_tf = true;
+        b.transformer(p + ".attentions." + std::to_string(j), out_c, blk.layers[j].tf);
+      }
+    for (int j = 0; j < nl; ++j) {
+      const int skip = (j == nl - 1) ? in_c : out_c;
+      const int rin = (j == 0) ? prev : out_c;
+      b.resnet(p + ".resnets." + std::to_string(j), rin + skip, out_c, blk.layers[j].res);
+    }
+    if (c.use_motion_module && c.motion_up[i])
+      for (int j = 0; j < nl; ++j) {
+        blk.layers[j].has_mo = true;
+        b.motion(p + ".motion_modules." + std::to_string(j), out_c, blk.layers[j].mo);
+      }
+    blk.sampler = i != c.num_blocks - 1;
+    if (blk.sampler) {
+      blk.sw = b.mat(out_c, 9 * out_c);
+      b.slot(p + ".upsamplers.0.conv.weight", {out_c, out_c, 3, 3}, SLOT_CONV3, blk.sw.off, 9 * out_c, 0, 0, 0, out_c);
+      blk.sb = b.vslot(p + ".upsamplers.0.conv.bias", out_c);
+    }
+  }
+  const int mc = c.block_out_channels[c.num_blocks - 1];
+  b.transformer("mid_block.attentions.0", mc, h->mid_tf);
+  b.resnet("mid_block.resnets.0", mc, mc, h->mid_r0);
+  b.resnet("mid_block.resnets.1", mc, mc, h->mid_r1);
+  h->mid_has_mo = c.use_motion_module && c.motion_mid;
+  if (h->mid_has_mo) b.motion("mid_block.motion_modules.0", mc, h->mid_mo);
+  h->cno_g = b.vslot("conv_norm_out.weight", c0);
+  h->cno_b = b.vslot("conv_norm_out.bias", c0);
+  h->conv_out_w = b.mat(c.out_channels, 9 * c0);
+  b.slot("conv_out.weight", {c.out_channels, c0, 3, 3}, SLOT_CONV3, h->conv_out_w.off, 9 * c0, 0, 0, 0, c0);
+  h->conv_out_b = b.vslot("conv_out.bias", c.out_channels);
+
+  // concatenated per-step time-embedding tables (all resnets at once)
+  h->temb_all = b.mat(h->temb_rows, h->temb_dim);
+  h->c1b_all = b.vec(h->temb_rows);
+  h->tb_all = b.vec(h->temb_rows);
+  h->temb_static_b = b.vec(h->temb_rows);
+  h->bias_eff_all = b.vec(h->temb_rows);
+  for (auto& s : h->slots) {
+    const std::string& n = s.name;
+    auto ends = [&](const char* suf) {
+      const size_t l = strlen(suf);
+      return n.size() >= l && n.compare(n.size() - l, l, suf) == 0;
+    };
+    if (ends(".time_emb_proj.weight")) s.dst = h->temb_all.off;
+    else if (ends(".time_emb_proj.bias")) s.dst = h->tb_all.off + (size_t)s.row_off * 4, s.row_off = 0;
+    else if (ends(".conv1.bias")) s.dst = h->c1b_all.off + (size_t)s.row_off * 4, s.row_off = 0;
+  }
+  h->arena_bytes = b.top;
+  return 0;
+}
+
+// ==========================================================================================
+// weights
+// ==========================================================================================
+template <typename T>
+static void pack_dispatch(rcdm_unet_impl* h, const Slot& s, const void* src, int src_dt, cudaStream_t st) {
+  if (s.kind == SLOT_VEC) {
+    int n = 1;
+    for (int i = 0; i < s.ndim; ++i) n *= (int)s.dims[i];
+    pack_vec_kernel<<<(n + 255) / 256, 256, 0, st>>>(src, src_dt, reinterpret_cast<float*>(h->arena + s.dst), n,
+                                                     s.row_off, s.geglu_bn, 0);
+  } else {
+    const int N = (int)s.dims[0];
+    int K = 1;
+    for (int i = 1; i < s.ndim; ++i) K *= (int)s.dims[i];
+    const bool conv3 = s.kind == SLOT_CONV3;
+    pack_weight_kernel<T><<<grid_for((size_t)N * K, 256), 256, 0, st>>>(
+        src, src_dt, reinterpret_cast<T*>(h->arena + s.dst), N, K, s.ldd, s.col_off, s.row_off, conv3 ? 1 : 0, s.cin,
+        s.geglu_bn);
+  }
+  g_launches++;
+}
+
+__global__ void add_vec_kernel(const float* a, const float* b, float* o, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) o[i] = a[i] + (b ? b[i] : 0.f);
+}
+
+static void finalize_res(rcdm_unet_impl* h, const ResW& r, cudaStream_t st) {
+  auto f = [&](const Vec& v) { return reinterpret_cast<float*>(h->arena + v.off); };
+  add_vec_kernel<<<(r.cout + 255) / 256, 256, 0, st>>>(f(r.c2b), r.shortcut ? f(r.scb) : nullptr, f(r.c2beff), r.cout);
+}
+
+static void finalize_weights(rcdm_unet_impl* h, cudaStream_t st) {
+  auto f = [&](const Vec& v) { return reinterpret_cast<float*>(h->arena + v.off); };
+  for (auto& blk : h->down)
+    for (auto& l : blk.layers) finalize_res(h, l.res, st);
+  for (auto& blk : h->up)
+    for (auto& l : blk.layers) finalize_res(h, l.res, st);
+  finalize_res(h, h->mid_r0, st);
+  finalize_res(h, h->mid_r1, st);
+  add_vec_kernel<<<(h->temb_rows + 255) / 256, 256, 0, st>>>(f(h->c1b_all), f(h->tb_all), f(h->temb_static_b),
+                                                             h->temb_rows);
+  h->dirty = false;
+}
+
+// ==========================================================================================
+// plan
+// ==========================================================================================
+struct Act {
+  size_t off = 0;
+  int C = 0, H = 0, W = 0;
+};
+
+struct Planner {
+  rcdm_unet_impl* h;
+  bool dry;
+  std::vector<Op>* ops;
+  std::map<size_t, size_t> free_list;
+  size_t top = 0, peak = 0;
+  std::string err;
+  bool failed = false;
+  size_t gn_scratch = 0;  // persistent scratch for GroupNorm (counters stay zero between launches)
+
+  size_t alloc(size_t bytes) {
+    bytes = (bytes + 1023) & ~size_t(1023);
+    for (auto it = free_list.begin(); it != free_list.end(); ++it) {
+      if (it->second >= bytes) {
+        const size_t off = it->first, sz = it->second;
+        free_list.erase(it);
+        if (sz > bytes) free_list[off + bytes] = sz - bytes;
+        return off;
+      }
+    }
+    const size_t off = top;
+    top += bytes;
+    if (top > peak) peak = top;
+    return off;
+  }
+  void release(size_t off, size_t bytes) {
+    bytes = (bytes + 1023) & ~size_t(1023);
+    auto it = free_list.emplace(off, bytes).first;
+    auto nx = std::next(it);
+    if (nx != free_list.end() && it->first + it->second == nx->first) {
+      it->second += nx->second;
+      free_list.erase(nx);
+    }
+    if (it != free_list.begin()) {
+      auto pv = std::prev(it);
+      if (pv->first + pv->second == it->first) {
+        pv->second += it->second;
+        free_list.erase(it);
+        it = pv;
+      }
+    }
+    if (it->first + it->second == top) {
+      top = it->first;
+      free_list.erase(it);
+    }
+  }
+  int rows(const Act& a) const { return h->B * h->F * a.H * a.W; }
+  size_t abytes(const Act& a) const { return (size_t)rows(a) * a.C * 2; }
+  Act new_act(int C, int H, int W) {
+    Act a;
+    a.C = C;
+    a.H = H;
+    a.W = W;
+    a.off = alloc(abytes(a));
+    return a;
+  }
+  void free_act(const Act& a) { release(a.off, abytes(a)); }
+  void* p(size_t off) const { return h->ws + off; }
+  const void* wm(const Mat& m) const { return h->arena + m.off; }
+  const float* wv(const Vec& v) const { return reinterpret_cast<const float*>(h->arena + v.off); }
+  void fail(const std::string& m) {
+    if (!failed) err = m;
+    failed = true;
+  }
+  void push(Op op) {
+    if (!dry) ops->push_back(std::move(op));
+  }
+
+  // ---------------- op emitters ----------------
+  void gemm(GemmDesc d) {
+    if (dry || failed) return;
+    d.dt = h->dt;
+    if (h->simple) {
+      push([d](cudaStream_t s) {
+        gemm_simple_launch(d, s);
+        g_launches++;
+      });
+      return;
+    }
+    GemmLaunch l;
+    std::string e;
+    if (!gemm_prepare(d, &l, &e)) return fail(e);
+    push([l](cudaStream_t s) {
+      gemm_launch(l, s);
+      g_launches++;
+    });
+  }
+  // plain GEMM: out[M,N] = A[M,K] W^T (+bias)(+res)
+  void linear(size_t a_off, int M, int K, const Mat& w, const Vec* bias, size_t out_off, int ldo, const size_t* res_off,
+              int geglu = 0) {
+    GemmDesc d;
+    memset(&d, 0, sizeof d);
+    d.M = M;
+    d.N = w.rows;
+    d.nseg = 1;
+    d.seg[0] = ASeg{SEG_PLAIN, p(a_off), K, K, 0, 0, 0};
+    d.w = wm(w);
+    d.Ktot = w.cols;
+    d.w_rows = w.rows;
+    d.out = p(out_off);
+    d.ldo = ldo;
+    d.bias = bias ? wv(*bias) : nullptr;
+    d.res = res_off ? p(*res_off) : nullptr;
+    d.ldr = ldo;
+    d.geglu = geglu;
+    if (K != w.cols) return fail("linear: K mismatch");
+    gemm(d);
+  }
+  void groupnorm(const Act& x0, const Act* x1, const Vec& g, const Vec& b, float eps, bool per_frame, bool silu,
+                 size_t out_off) {
+    if (dry || failed) return;
+    const int hw = x0.H * x0.W;
+    GnLaunch l;
+    gn_configure(&l, h->dt, p(x0.off), x0.C, x1 ? p(x1->off) : nullptr, x1 ? x1->C : 0, rows(x0),
+                 per_frame ? hw : h->F * hw, h->cfg.norm_num_groups, eps, wv(g), wv(b), p(out_off), silu ? 1 : 0,
+                 p(gn_scratch));
+    push([l](cudaStream_t s) { gn_run(l, s); });
+  }
+  void layernorm(size_t x_off, size_t out_off, int nrows, int C, const Vec& g, const Vec& b, const Vec* pe,
+                 int rows_per_frame) {
+    if (dry || failed) return;
+    const void* x = p(x_off);
+    void* o = p(out_off);
+    const float* gp = wv(g);
+    const float* bp = wv(b);
+    const float* pep = pe ? wv(*pe) : nullptr;
+    const int frames = h->F, dt = h->dt;
+    if ((C / 8 + 31) / 32 > 5) return fail("layernorm: C too large");
+    push([=](cudaStream_t s) { ln_run(dt, x, o, gp, bp, nrows, C, 1e-5f, pep, rows_per_frame, frames, s); });
+  }
+  void attention(AttnDesc d) {
+    if (dry || failed) return;
+    d.dt = h->dt;
+    if (h->simple) {
+      push([d](cudaStream_t s) {
+        attn_simple_launch(d, s);
+        g_launches++;
+      });
+      return;
+    }
+    AttnLaunch l;
+    std::string e;
+    if (!attn_prepare(d, &l, &e)) return fail(e);
+    push([l](cudaStream_t s) {
+      attn_launch(l, s);
+      g_launches++;
+    });
+  }
+  void tap(const std::string& name, const Act& a) {
+    if (!h->taps_enabled) return;
+    const size_t bytes = abytes(a);
+    const size_t off = alloc(bytes);  // never released
+    if (dry) return;
+    h->taps[name] = TapInfo{off, rows(a), a.C};
+    void* dst = p(off);
+    const void* src = p(a.off);
+    push([=](cudaStream_t s) { cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, s); });
+  }
+
+  // ---------------- modules ----------------
+  // ResnetBlock3D.forward (resnet.py:182-212); in1 = skip tensor concatenated on the channel dim (unet_blocks.py:644,754)
+  Act resnet(const Act& in0, const Act* in1, const ResW& r) {
+    const int cin = in0.C + (in1 ? in1->C : 0);
+    if (cin != r.cin) fail("resnet: channel mismatch");
+    if (!r.shortcut && in1) fail("resnet: concat input without shortcut");
+    const int NI = h->B * h->F, M = rows(in0);
+    Act n = new_act(cin, in0.H, in0.W);
+    groupnorm(in0, in1, r.n1g, r.n1b, h->cfg.norm_eps, false, true, n.off);
+    Act h1 = new_act(r.cout, in0.H, in0.W);
+    {
+      GemmDesc d;
+      memset(&d, 0, sizeof d);
+      d.M = M;
+      d.N = r.cout;
+      d.nseg = 1;
+      d.seg[0] = ASeg{SEG_CONV3, p(n.off), cin, cin, in0.H, in0.W, NI};
+      d.w = wm(r.c1);
+      d.Ktot = r.c1.cols;
+      d.w_rows = r.cout;
+      d.Ho = in0.H;
+      d.Wo = in0.W;
+      d.NI = NI;
+      d.out = p(h1.off);
+      d.ldo = r.cout;
+      d.bias = wv(h->bias_eff_all) + r.temb_row;  // conv1.bias + time_emb_proj(silu(emb)) for this step
+      gemm(d);
+    }
+    free_act(n);
+    Act n2 = new_act(r.cout, in0.H, in0.W);
+    groupnorm(h1, nullptr, r.n2g, r.n2b, h->cfg.norm_eps, false, true, n2.off);
+    free_act(h1);
+    Act out = new_act(r.cout, in0.H, in0.W);
+    {
+      GemmDesc d;
+      memset(&d, 0, sizeof d);
+      d.M = M;
+      d.N = r.cout;
+      d.nseg = 1;
+      d.seg[0] = ASeg{SEG_CONV3, p(n2.off), r.cout, r.cout, in0.H, in0.W, NI};
+      if (r.shortcut) {  // 1x1 shortcut over the (virtual) concat accumulates into the same tile
+        d.seg[d.nseg++] = ASeg{SEG_PLAIN, p(in0.off), in0.C, in0.C, 0, 0, 0};
+        if (in1) d.seg[d.nseg++] = ASeg{SEG_PLAIN, p(in1->off), in1->C, in1->C, 0, 0, 0};
+      } else {
+        d.res = p(in0.off);
+        d.ldr = in0.C;
+      }
+      d.w = wm(r.c2);
+      d.Ktot = r.c2.cols;
+      d.w_rows = r.cout;
+      d.Ho = in0.H;
+      d.Wo = in0.W;
+      d.NI = NI;
+      d.out = p(out.off);
+      d.ldo = r.cout;
+      d.bias = wv(r.c2beff);
+      gemm(d);
+    }
+    free_act(n2);
+    return out;
+  }
+
+  // Transformer3DModel + BasicTransformerBlock (attention.py:318-365, 479-526); x updated in place
+  void transformer(const Act& x, const TfW& t, size_t kv_off) {
+    const int C = t.C, M = rows(x), HW = x.H * x.W, NI = h->B * h->F;
+    const int heads = h->cfg.attention_heads, d = C / heads;
+    Act n = new_act(C, x.H, x.W);
+    groupnorm(x, nullptr, t.ng, t.nb, 1e-6f, true, false, n.off);
+    Act y = new_act(C, x.H, x.W);
+    linear(n.off, M, C, t.pi, &t.pib, y.off, C, nullptr);
+    free_act(n);
+    Act tmp = new_act(C, x.H, x.W);
+    // self-attention
+    layernorm(y.off, tmp.off, M, C, t.ln1g, t.ln1b, nullptr, 1);
+    Act qkv = new_act(3 * C, x.H, x.W);
+    linear(tmp.off, M, C, t.a1.qkv, nullptr, qkv.off, 3 * C, nullptr);
+    {
+      AttnDesc a;
+      memset(&a, 0, sizeof a);
+      a.q = p(qkv.off);
+      a.ldq = 3 * C;
+      a.k = reinterpret_cast<const char*>(p(qkv.off)) + (size_t)C * 2;
+      a.v = reinterpret_cast<const char*>(p(qkv.off)) + (size_t)2 * C * 2;
+      a.ldkv = 3 * C;
+      a.S_q = HW;
+      a.S_kv = HW;
+      a.heads = heads;
+      a.d = d;
+      a.batch = NI;
+      a.out = p(tmp.off);
+      a.ldo = C;
+      attention(a);
+    }
+    free_act(qkv);
+    linear(tmp.off, M, C, t.a1.out, &t.a1.outb, y.off, C, &y.off);
+    // cross-attention to the fused context
+    layernorm(y.off, tmp.off, M, C, t.ln2g, t.ln2b, nullptr, 1);
+    Act q = new_act(C, x.H, x.W);
+    linear(tmp.off, M, C, t.a2.q, nullptr, q.off, C, nullptr);
+    {
+      AttnDesc a;
+      memset(&a, 0, sizeof a);
+      a.q = p(q.off);
+      a.ldq = C;
+      a.k = p(kv_off);
+      a.v = reinterpret_cast<const char*>(p(kv_off)) + (size_t)C * 2;
+      a.ldkv = 2 * C;
+      a.S_q = HW;
+      a.S_kv = h->L;
+      a.heads = heads;
+      a.d = d;
+      a.batch = NI;
+      a.out = p(tmp.off);
+      a.ldo = C;
+      attention(a);
+    }
+    free_act(q);
+    linear(tmp.off, M, C, t.a2.out, &t.a2.outb, y.off, C, &y.off);
+    // GEGLU feed-forward
+    layernorm(y.off, tmp.off, M, C, t.ln3g, t.ln3b, nullptr, 1);
+    Act g = new_act(4 * C, x.H, x.W);
+    linear(tmp.off, M, C, t.ff1, &t.ff1b, g.off, 4 * C, nullptr, 1);
+    linear(g.off, M, 4 * C, t.ff2, &t.ff2b, y.off, C, &y.off);
+    free_act(g);
+    free_act(tmp);
+    linear(y.off, M, C, t.po, &t.pob, x.off, C, &x.off);
+    free_act(y);
+  }
+
+  // VanillaTemporalModule (motion_module.py:87-93,147-182,234-246,294-354); x updated in place
+  void motion(const Act& x, const MoW& m) {
+    const int C = m.C, M = rows(x), HW = x.H * x.W;
+    const int heads = h->cfg.motion_heads, d = C / heads;
+    Act n = new_act(C, x.H, x.W);
+    groupnorm(x, nullptr, m.ng, m.nb, 1e-6f, true, false, n.off);
+    Act y = new_act(C, x.H, x.W);
+    linear(n.off, M, C, m.pi, &m.pib, y.off, C, nullptr);
+    free_act(n);
+    Act tmp = new_act(C, x.H, x.W);
+    for (int i = 0; i < h->cfg.motion_attn_blocks; ++i) {
+      layernorm(y.off, tmp.off, M, C, m.lng[i], m.lnb[i], &m.pe[i], HW);
+      Act qkv = new_act(3 * C, x.H, x.W);
+      linear(tmp.off, M, C, m.att[i].qkv, nullptr, qkv.off, 3 * C, nullptr);
+      if (!dry && !failed) {
+        const void* qp = p(qkv.off);
+        void* op = p(tmp.off);
+        const int dt = h->dt, B = h->B, F = h->F;
+        push([=](cudaStream_t s) {
+          temporal_attn_launch(dt, qp, op, B, F, HW, heads, d, s);
+          g_launches++;
+        });
+      }
+      free_act(qkv);
+      linear(tmp.off, M, C, m.att[i].out, &m.att[i].outb, y.off, C, &y.off);
+    }
+    layernorm(y.off, tmp.off, M, C, m.ffng, m.ffnb, nullptr, 1);
+    Act g = new_act(4 * C, x.H, x.W);
+    linear(tmp.off, M, C, m.ff1, &m.ff1b, g.off, 4 * C, nullptr, 1);
+    linear(g.off, M, 4 * C, m.ff2, &m.ff2b, y.off, C, &y.off);
+    free_act(g);
+    free_act(tmp);
+    linear(y.off, M, C, m.po, &m.pob, x.off, C, &x.off);
+    free_act(y);
+  }
+
+  Act conv_sampler(const Act& x, const Mat& w, const Vec& b, int stride, int Ho, int Wo) {
+    Act out = new_act(w.rows, Ho, Wo);
+    GemmDesc d;
+    memset(&d, 0, sizeof d);
+    d.M = rows(out);
+    d.N = w.rows;
+    d.nseg = 1;
+    d.seg[0] = ASeg{stride == 2 ? SEG_CONV3S2 : SEG_CONV3, p(x.off), x.C, x.C, x.H, x.W, h->B * h->F};
+    d.w = wm(w);
+    d.Ktot = w.cols;
+    d.w_rows = w.rows;
+    d.Ho = Ho;
+    d.Wo = Wo;
+    d.NI = h->B * h->F;
+    d.out = p(out.off);
+    d.ldo = w.rows;
+    d.bias = wv(b);
+    gemm(d);
+    return out;
+  }
+};
+
+// walk the network once; records ops (unless dry) and returns the peak arena size
+static int plan_network(rcdm_unet_impl* h, bool dry, size_t* peak) {
+  const rcdm_unet_config& c = h->cfg;
+  Planner P{h, dry, nullptr};
+  const int NI = h->B * h->F;
+  // ---- persistent regions
+  const size_t gn_bytes = gn_scratch_bytes(NI, c.norm_num_groups);
+  P.gn_scratch = P.alloc(gn_bytes);
+  const int c0 = c.block_out_channels[0];
+  const size_t e1 = P.alloc((size_t)h->temb_dim * 4), e2 = P.alloc((size_t)h->temb_dim * 4);
+  const size_t ctx16 = P.alloc((size_t)NI * h->L * c.cross_attention_dim * 2);
+  // ---- ctx ops
+  P.ops = &h->ctx_ops;
+  if (!dry) {
+    void* dst = P.p(ctx16);
+    const size_t n = (size_t)NI * h->L * c.cross_attention_dim;
+    const int dt = h->dt;
+    void* gscr = P.p(P.gn_scratch);
+    P.push([=](cudaStream_t s) {
+      cudaMemsetAsync(gscr, 0, gn_bytes, s);
+      if (dt == DT_F16)
+        cast_rows_kernel<__half><<<grid_for(n, 256), 256, 0, s>>>(h->cur_ctx, h->cur_ctx_dt,
+                                                                  reinterpret_cast<__half*>(dst), n);
+      else
+        cast_rows_kernel<__nv_bfloat16><<<grid_for(n, 256), 256, 0, s>>>(h->cur_ctx, h->cur_ctx_dt,
+                                                                         reinterpret_cast<__nv_bfloat16*>(dst), n);
+      g_launches++;
+    });
+  }
+  // cross-attention K/V of every spatial transformer: step-invariant, computed by ctx_ops BEFORE any step op runs,
+  // so these buffers are persistent and must be carved out before any temporary is allocated.
+  std::map<const TfW*, size_t> kv_of;
+  {
+    std::vector<const TfW*> tfs;
+    for (auto& blk : h->down)
+      for (auto& l : blk.layers)
+        if (l.has_tf) tfs.push_back(&l.tf);
+    tfs.push_back(&h->mid_tf);
+    for (auto& blk : h->up)
+      for (auto& l : blk.layers)
+        if (l.has_tf) tfs.push_back(&l.tf);
+    for (const TfW* t : tfs) {
+      const size_t off = P.alloc((size_t)NI * h->L * 2 * t->C * 2);
+      kv_of[t] = off;
+      P.linear(ctx16, NI * h->L, c.cross_attention_dim, t->a2.kv, nullptr, off, 2 * t->C, nullptr);
+    }
+  }
+  auto plan_kv = [&](const TfW& t) { return kv_of.at(&t); };
+
+  // ---- step ops
+  P.ops = &h->step_ops;
+  if (!dry) {
+    float* e1p = reinterpret_cast<float*>(P.p(e1));
+    float* e2p = reinterpret_cast<float*>(P.p(e2));
+    const int dt = h->dt, td = h->temb_dim, tr = h->temb_rows;
+    const void* l1w = P.wm(h->l1w);
+    const void* l2w = P.wm(h->l2w);
+    const void* tw = P.wm(h->temb_all);
+    const float* l1b = P.wv(h->l1b);
+    const float* l2b = P.wv(h->l2b);
+    const float* sb = P.wv(h->temb_static_b);
+    float* beff = const_cast<float*>(P.wv(h->bias_eff_all));
+    const int flip = c.flip_sin_to_cos;
+    const float fs = c.freq_shift;
+    P.push([=](cudaStream_t s) {
+      // unet.py:367-389 + every resnet's time_emb_proj (resnet.py:190-191) in three launches
+      if (dt == DT_F16) {
+        temb_linear1_kernel<__half><<<(td * 32 + 255) / 256, 256, 0, s>>>(h->cur_t_dev, h->cur_t_host,
+                                                                          reinterpret_cast<const __half*>(l1w), l1b, e1p,
+                                                                          c0, td, flip, fs);
+        gemv_kernel<__half><<<(td * 32 + 255) / 256, 256, 0, s>>>(e1p, reinterpret_cast<const __half*>(l2w), l2b,
+                                                                  nullptr, e2p, td, td, 1);
+        gemv_kernel<__half><<<(tr * 32 + 255) / 256, 256, 0, s>>>(e2p, reinterpret_cast<const __half*>(tw), sb, nullptr,
+                                                                  beff, td, tr, 0);
+      } else {
+        temb_linear1_kernel<__nv_bfloat16><<<(td * 32 + 255) / 256, 256, 0, s>>>(
+            h->cur_t_dev, h->cur_t_host, reinterpret_cast<const __nv_bfloat16*>(l1w), l1b, e1p, c0, td, flip, fs);
+        gemv_kernel<__nv_bfloat16><<<(td * 32 + 255) / 256, 256, 0, s>>>(
+            e1p, reinterpret_cast<const __nv_bfloat16*>(l2w), l2b, nullptr, e2p, td, td, 1);
+        gemv_kernel<__nv_bfloat16><<<(tr * 32 + 255) / 256, 256, 0, s>>>(
+            e2p, reinterpret_cast<const __nv_bfloat16*>(tw), sb, nullptr, beff, td, tr, 0);
+      }
+      g_launches += 3;
+    });
+  }
+  // conv_in via im2col (9 input channels) + tensor-core GEMM
+  Act x = P.new_act(c0, h->H, h->W);
+  {
+    const int M = P.rows(x), kpad = h->conv_in_kpad;
+    const size_t a_off = P.alloc((size_t)M * kpad * 2);
+    if (!dry) {
+      void* A = P.p(a_off);
+      const int dt = h->dt, B = h->B, Cin = c.in_channels, F = h->F, H = h->H, W = h->W;
+      P.push([=](cudaStream_t s) {
+        const size_t total = (size_t)M * kpad;
+        if (dt == DT_F16)
+          im2col_in_kernel<__half><<<grid_for(total, 256), 256, 0, s>>>(h->cur_sample, h->cur_sample_dt,
+                                                                        reinterpret_cast<__half*>(A), B, Cin, F, H, W,
+                                                                        kpad);
+        else
+          im2col_in_kernel<__nv_bfloat16><<<grid_for(total, 256), 256, 0, s>>>(
+              h->cur_sample, h->cur_sample_dt, reinterpret_cast<__nv_bfloat16*>(A), B, Cin, F, H, W, kpad);
+        g_launches++;
+      });
+    }
+    P.linear(a_off, M, kpad, h->conv_in_w, &h->conv_in_b, x.off, c0, nullptr);
+    P.release(a_off, (size_t)M * kpad * 2);
+  }
+  P.tap("conv_in", x);
+  std::vector<Act> skips{x};
+  auto in_skips = [&](const Act& a) {
+    for (auto& s : skips)
+      if (s.off == a.off) return true;
+    return false;
+  };
+  for (int i = 0; i < c.num_blocks; ++i) {
+    BlockW& blk = h->down[i];
+    const std::string bp = "down_blocks." + std::to_string(i);
+    for (size_t j = 0; j < blk.layers.size(); ++j) {
+      LayerW& l = blk.layers[j];
+      Act r = P.resnet(x, nullptr, l.res);
+      if (!in_skips(x)) P.free_act(x);
+      x = r;
+      P.tap(bp + ".resnets." + std::to_string(j), x);
+      if (l.has_tf) {
+        P.transformer(x, l.tf, plan_kv(l.tf));
+        P.tap(bp + ".attentions." + std::to_string(j), x);
+      }
+      if (l.has_mo) {
+        P.motion(x, l.mo);
+        P.tap(bp + ".motion_modules." + std::to_string(j), x);
+      }
+      skips.push_back(x);
+    }
+    if (blk.sampler) {
+      if (x.H % 2 || x.W % 2) {
+        P.fail("downsample needs even spatial dims");
+        break;
+      }
+      x = P.conv_sampler(x, blk.sw, blk.sb, 2, x.H / 2, x.W / 2);
+      P.tap(bp + ".downsamplers.0", x);
+      skips.push_back(x);
+    }
+  }
+  {  // mid block (unet_blocks.py:272-280)
+    Act r0 = P.resnet(x, nullptr, h->mid_r0);
+    P.transformer(r0, h->mid_tf, plan_kv(h->mid_tf));
+    if (h->mid_has_mo) P.motion(r0, h->mid_mo);
+    Act r1 = P.resnet(r0, nullptr, h->mid_r1);
+    P.free_act(r0);
+    x = r1;  // previous x is the last skip: still owned by `skips`
+    P.tap("mid_block", x);
+  }
+  for (int i = 0; i < c.num_blocks && !P.failed; ++i) {
+    BlockW& blk = h->up[i];
+    const std::string bp = "up_blocks." + std::to_string(i);
+    for (size_t j = 0; j < blk.layers.size(); ++j) {
+      LayerW& l = blk.layers[j];
+      if (skips.empty()) {
+        P.fail("skip stack underflow");
+        break;
+      }
+      Act sk = skips.back();
+      skips.pop_back();
+      if (sk.H != x.H || sk.W != x.W) {
+        P.fail("skip / hidden spatial mismatch");
+        break;
+      }
+      Act r = P.resnet(x, &sk, l.res);
+      P.free_act(x);
+      P.free_act(sk);
+      x = r;
+      P.tap(bp + ".resnets." + std::to_string(j), x);
+      if (l.has_tf) {
+        P.transformer(x, l.tf, plan_kv(l.tf));
+        P.tap(bp + ".attentions." + std::to_string(j), x);
+      }
+      if (l.has_mo) {
+        P.motion(x, l.mo);
+        P.tap(bp + ".motion_modules." + std::to_string(j), x);
+      }
+    }
+    if (blk.sampler) {  // Upsample3D: nearest 2x then conv3x3 (resnet.py:46-80)
+      Act u = P.new_act(x.C, 2 * x.H, 2 * x.W);
+      if (!dry) {
+        const void* src = P.p(x.off);
+        void* dst = P.p(u.off);
+        const int dt = h->dt, N = NI, H = x.H, W = x.W, C = x.C;
+        P.push([=](cudaStream_t s) {
+          const size_t total = (size_t)N * 4 * H * W * (C / 8);
+          if (dt == DT_F16)
+            upsample2x_kernel<__half><<<grid_for(total, 256), 256, 0, s>>>(reinterpret_cast<const __half*>(src),
+                                                                            reinterpret_cast<__half*>(dst), N, H, W, C);
+          else
+            upsample2x_kernel<__nv_bfloat16><<<grid_for(total, 256), 256, 0, s>>>(
+                reinterpret_cast<const __nv_bfloat16*>(src), reinterpret_cast<__nv_bfloat16*>(dst), N, H, W, C);
+          g_launches++;
+        });
+      }
+      P.free_act(x);
+      x = P.conv_sampler(u, blk.sw, blk.sb, 1, u.H, u.W);
+      P.free_act(u);
+      P.tap(bp + ".upsamplers.0", x);
+    }
+  }
+  if (!P.failed) {  // conv_norm_out -> SiLU -> conv_out (unet.py:455-457), then back to NCFHW
+    Act n = P.new_act(x.C, x.H, x.W);
+    P.groupnorm(x, nullptr, h->cno_g, h->cno_b, c.norm_eps, false, true, n.off);
+    P.free_act(x);
+    Act o = P.new_act(8, x.H, x.W);  // only out_channels (<= 8) columns are written
+    if (c.out_channels > 8) P.fail("out_channels > 8 unsupported");
+    {
+      GemmDesc d;
+      memset(&d, 0, sizeof d);
+      d.M = P.rows(n);
+      d.N = c.out_channels;
+      d.nseg = 1;
+      d.seg[0] = ASeg{SEG_CONV3, P.p(n.off), n.C, n.C, n.H, n.W, NI};
+      d.w = P.wm(h->conv_out_w);
+      d.Ktot = h->conv_out_w.cols;
+      d.w_rows = c.out_channels;
+      d.Ho = n.H;
+      d.Wo = n.W;
+      d.NI = NI;
+      d.out = P.p(o.off);
+      d.ldo = c.out_channels;
+      d.bias = P.wv(h->conv_out_b);
+      P.gemm(d);
+    }
+    P.free_act(n);
+    if (!dry) {
+      const void* tok = P.p(o.off);
+      const int dt = h->dt, B = h->B, C = c.out_channels, F = h->F, HW = h->H * h->W;
+      P.push([=](cudaStream_t s) {
+        const size_t total = (size_t)B * C * F * HW;
+        if (dt == DT_F16)
+          tokens_to_ncfhw_kernel<__half><<<grid_for(total, 256), 256, 0, s>>>(reinterpret_cast<const __half*>(tok),
+                                                                              h->cur_out, h->cur_out_dt, B, C, F, HW);
+        else
+          tokens_to_ncfhw_kernel<__nv_bfloat16><<<grid_for(total, 256), 256, 0, s>>>(
+              reinterpret_cast<const __nv_bfloat16*>(tok), h->cur_out, h->cur_out_dt, B, C, F, HW);
+        g_launches++;
+      });
+    }
+    P.free_act(o);
+  }
+  if (P.failed) return set_err("plan: " + P.err);
+  *peak = P.peak;
+  return 0;
+}
+
+int unet_create(const rcdm_unet_config* cfg, rcdm_unet** out) {
+  if (!cfg || !out) return set_err("null argument");
+  rcdm_unet* h = new rcdm_unet();
+  h->cfg = *cfg;
+  const char* env = getenv("RCDM_SIMPLE");
+  h->simple = env && env[0] == '1';
+  if (build_model(h)) {
+    delete h;
+    return 1;
+  }
+  *out = h;
+  return 0;
+}
+
+static void release_plan(rcdm_unet_impl* h) {
+  h->ctx_ops.clear();
+  h->step_ops.clear();
+  h->taps.clear();
+  if (h->graph_exec) {
+    cudaGraphExecDestroy(h->graph_exec);
+    h->graph_exec = nullptr;
+  }
+  h->graph_key.clear();
+  if (h->ws) {
+    cudaFree(h->ws);
+    h->ws = nullptr;
+  }
+  h->planned = false;
+}
+
+void unet_destroy(rcdm_unet* h) {
+  if (!h) return;
+  release_plan(h);
+  if (h->arena) cudaFree(h->arena);
+  if (h->loop_buf) cudaFree(h->loop_buf);
+  if (h->loop_stream) cudaStreamDestroy(h->loop_stream);
+  if (h->ev_in) cudaEventDestroy(h->ev_in);
+  if (h->ev_out) cudaEventDestroy(h->ev_out);
+  delete h;
+}
+
+static int ensure_arena(rcdm_unet_impl* h) {
+  if (h->arena) return 0;
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+    (void)cudaGetLastError();
+    return set_err("no CUDA device: librcdm_b200 has no CPU fallback");
+  }
+  CUDA_OK(cudaMalloc(&h->arena, h->arena_bytes));
+  CUDA_OK(cudaMemset(h->arena, 0, h->arena_bytes));
+  std::string e;
+  if (!gemm_setup_attributes(&e) || !attn_setup_attributes(&e)) return set_err(e);
+  return 0;
+}
+
+int unet_load_weight(rcdm_unet* h, const char* name, const void* data, int dtype, const int64_t* dims, int ndim,
+                     void* stream) {
+  if (!h || !name || !data) return set_err("null argument");
+  auto it = h->slot_index.find(name);
+  if (it == h->slot_index.end()) return set_err(std::string("unexpected key in state_dict: ") + name);
+  Slot& s = h->slots[it->second];
+  if (ndim != s.ndim) return set_err(std::string("size mismatch for ") + name);
+  for (int i = 0; i < ndim; ++i)
+    if (dims[i] != s.dims[i]) return set_err(std::string("size mismatch for ") + name);
+  if (dtype < 0 || dtype > 2) return set_err("bad dtype");
+  if (s.kind == SLOT_IGNORE) {
+    s.loaded = true;
+    return 0;
+  }
+  if (ensure_arena(h)) return 1;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (h->dt == DT_F16) pack_dispatch<__half>(h, s, data, dtype, st);
+  else pack_dispatch<__nv_bfloat16>(h, s, data, dtype, st);
+  CUDA_OK(cudaGetLastError());
+  s.loaded = true;
+  h->dirty = true;
+  return 0;
+}
+
+int unet_prepare(rcdm_unet* h, int batch, int frames, int height, int width, int ctx_len) {
+  if (!h) return set_err("null handle");
+  if (batch < 1 || frames < 1 || frames > 5 || height < 1 || width < 1 || ctx_len < 1)
+    return set_err("prepare: bad problem size (frames must be 1..5)");
+  if (h->planned && h->B == batch && h->F == frames && h->H == height && h->W == width && h->L == ctx_len) return 0;
+  if (ensure_arena(h)) return 1;
+  release_plan(h);
+  h->B = batch;
+  h->F = frames;
+  h->H = height;
+  h->W = width;
+  h->L = ctx_len;
+  size_t peak = 0;
+  if (plan_network(h, true, &peak)) return 1;
+  h->ws_bytes = peak + 4096;
+  CUDA_OK(cudaMalloc(&h->ws, h->ws_bytes));
+  CUDA_OK(cudaMemset(h->ws, 0, h->ws_bytes));
+  if (plan_network(h, false, &peak)) {
+    release_plan(h);
+    return 1;
+  }
+  h->planned = true;
+  return 0;
+}
+
+int unet_run(rcdm_unet* h, bool run_ctx, bool run_step, cudaStream_t st) {
+  if (h->dirty) finalize_weights(h, st);
+  if (run_ctx)
+    for (auto& op : h->ctx_ops) op(st);
+  if (run_step)
+    for (auto& op : h->step_ops) op(st);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_err(std::string("kernel launch failed: ") + cudaGetErrorString(e));
+  return 0;
+}
+
+}  // namespace rcdm

@@ -1,0 +1,138 @@
+"""Thin torch-tensor wrappers over the single-kernel C entry points (``rcdm_gemm``, ``rcdm_conv3x3``,
+``rcdm_groupnorm``, ``rcdm_layernorm``, ``rcdm_flash_attn``, ``rcdm_temporal_attn``, ``rcdm_ddim_cfg_step``).
+
+They exist so each kernel can be parity-tested and profiled in isolation; the UNet forward does not go
+through Python per op.  All tensors must be CUDA, contiguous, float16 or bfloat16 unless stated.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from . import _lib
+
+
+def _dt(t: torch.Tensor) -> int:
+    if not t.is_cuda:
+        raise RuntimeError("rcdms_b200.ops: CUDA tensors only (no CPU fallback)")
+    if not t.is_contiguous():
+        raise ValueError("rcdms_b200.ops: contiguous tensors only")
+    return _lib.torch_dtype_id(t.dtype)
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def linear(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None,
+           residual: Optional[torch.Tensor] = None, tile_n: int = 0, simple: bool = False) -> torch.Tensor:
+    """out[M,N] = a[M,K] @ w[N,K]^T (+ bias fp32[N]) (+ residual[M,N])."""
+    M, K = a.shape
+    N = w.shape[0]
+    out = torch.empty((M, N), dtype=a.dtype, device=a.device)
+    _lib.check(_lib.lib().rcdm_gemm(_dt(a), a.data_ptr(), w.data_ptr(), _ptr(bias), _ptr(residual), out.data_ptr(),
+                                    M, N, K, 0, tile_n, int(simple), _lib.current_stream_ptr()))
+    return out
+
+
+def geglu_linear(a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, simple: bool = False) -> torch.Tensor:
+    """diffusers GEGLU: h, g = (a @ w^T + b).chunk(2); h * gelu(g).  w [2J, K] in the reference layout."""
+    M, K = a.shape
+    N = w.shape[0]
+    L = _lib.lib()
+    wp = torch.empty_like(w)
+    bp = torch.empty((N,), dtype=torch.float32, device=a.device)
+    b32 = bias.float().contiguous()
+    s = _lib.current_stream_ptr()
+    _lib.check(L.rcdm_pack_geglu(_dt(w), w.data_ptr(), b32.data_ptr(), wp.data_ptr(), bp.data_ptr(), N, K, s))
+    out = torch.empty((M, N // 2), dtype=a.dtype, device=a.device)
+    _lib.check(L.rcdm_gemm(_dt(a), a.data_ptr(), wp.data_ptr(), bp.data_ptr(), None, out.data_ptr(), M, N, K, 1, 0,
+                           int(simple), s))
+    return out
+
+
+def conv3x3(x_nhwc: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = None,
+            residual: Optional[torch.Tensor] = None, stride: int = 1, simple: bool = False) -> torch.Tensor:
+    """3x3 / pad 1 conv on channels-last x [n,h,w,cin]; weight in the reference layout [cout,cin,3,3]."""
+    n, h, w, cin = x_nhwc.shape
+    cout = weight.shape[0]
+    L = _lib.lib()
+    s = _lib.current_stream_ptr()
+    wp = torch.empty((cout, 9 * cin), dtype=x_nhwc.dtype, device=x_nhwc.device)
+    wsrc = weight.to(x_nhwc.dtype).contiguous()
+    _lib.check(L.rcdm_pack_conv3x3(_dt(wsrc), wsrc.data_ptr(), wp.data_ptr(), cout, cin, s))
+    out = torch.empty((n, h // stride, w // stride, cout), dtype=x_nhwc.dtype, device=x_nhwc.device)
+    _lib.check(L.rcdm_conv3x3(_dt(x_nhwc), x_nhwc.data_ptr(), wp.data_ptr(), _ptr(bias), _ptr(residual),
+                              out.data_ptr(), n, h, w, cin, cout, stride, int(simple), s))
+    return out
+
+
+def group_norm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, groups: int, rows_per_stat: int,
+               eps: float, silu: bool) -> torch.Tensor:
+    """x [rows, C] tokens; statistics over blocks of rows_per_stat rows x (C/groups) channels."""
+    rows, C = x.shape
+    L = _lib.lib()
+    scratch = torch.zeros((L.rcdm_groupnorm_scratch_bytes(rows, rows_per_stat, groups),), dtype=torch.uint8,
+                          device=x.device)
+    out = torch.empty_like(x)
+    _lib.check(L.rcdm_groupnorm(_dt(x), x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), out.data_ptr(), rows, C,
+                                groups, rows_per_stat, eps, int(silu), scratch.data_ptr(),
+                                _lib.current_stream_ptr()))
+    return out
+
+
+def layer_norm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float = 1e-5,
+               pe: Optional[torch.Tensor] = None, rows_per_frame: int = 1, frames: int = 1) -> torch.Tensor:
+    rows, C = x.shape
+    out = torch.empty_like(x)
+    _lib.check(_lib.lib().rcdm_layernorm(_dt(x), x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), out.data_ptr(), rows,
+                                         C, eps, _ptr(pe), rows_per_frame, frames, _lib.current_stream_ptr()))
+    return out
+
+
+def flash_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, simple: bool = False) -> torch.Tensor:
+    """q [batch, S_q, heads*d], k/v [batch, S_kv, heads*d] (separate contiguous tensors) -> [batch, S_q, heads*d]."""
+    b, sq, c = q.shape
+    skv = k.shape[1]
+    d = c // heads
+    if k.shape != v.shape:
+        raise ValueError("k and v must have the same shape")
+    out = torch.empty_like(q)
+    # k and v are separate allocations: interleave into one [b*S_kv, 2c] buffer as the fused projection would
+    kv = torch.cat([k, v], dim=-1).contiguous()
+    _lib.check(_lib.lib().rcdm_flash_attn(_dt(q), q.data_ptr(), c, kv.data_ptr(), kv.data_ptr() + c * q.element_size(),
+                                          2 * c, out.data_ptr(), c, b, heads, sq, skv, d, int(simple),
+                                          _lib.current_stream_ptr()))
+    return out
+
+
+def temporal_attention(qkv: torch.Tensor, batch: int, frames: int, hw: int, heads: int) -> torch.Tensor:
+    """qkv [(b f hw), 3C] -> [(b f hw), C]: attention over the frame axis at every (b, hw, head)."""
+    rows, c3 = qkv.shape
+    C = c3 // 3
+    out = torch.empty((rows, C), dtype=qkv.dtype, device=qkv.device)
+    _lib.check(_lib.lib().rcdm_temporal_attn(_dt(qkv), qkv.data_ptr(), out.data_ptr(), batch, frames, hw, heads,
+                                             C // heads, _lib.current_stream_ptr()))
+    return out
+
+
+def ddim_cfg_step(eps: torch.Tensor, latents_f32: torch.Tensor, alpha_bar_t: float, alpha_bar_prev: float,
+                  guidance_scale: float, do_cfg: bool, latents_dtype: torch.dtype,
+                  mask: Optional[torch.Tensor] = None, masked_latents: Optional[torch.Tensor] = None,
+                  next_dtype: Optional[torch.dtype] = None):
+    """Fused CFG + DDIM step; returns (latents in latents_dtype, next 9-channel UNet input or None).
+    latents_f32 (clips,4,f,h,w) is updated in place."""
+    clips, _, f, h, w = latents_f32.shape
+    lat_out = torch.empty(latents_f32.shape, dtype=latents_dtype, device=eps.device)
+    nxt = None
+    if mask is not None:
+        nb = 2 * clips if do_cfg else clips
+        nxt = torch.empty((nb, 9, f, h, w), dtype=next_dtype or eps.dtype, device=eps.device)
+    _lib.check(_lib.lib().rcdm_ddim_cfg_step(
+        eps.data_ptr(), _dt(eps), latents_f32.data_ptr(), lat_out.data_ptr(), _lib.torch_dtype_id(latents_dtype),
+        _ptr(nxt), _lib.torch_dtype_id(nxt.dtype) if nxt is not None else 0, _ptr(mask),
+        _dt(mask) if mask is not None else 0, _ptr(masked_latents),
+        _dt(masked_latents) if masked_latents is not None else 0, clips, f, h, w, int(do_cfg), float(guidance_scale),
+        float(alpha_bar_t), float(alpha_bar_prev), _lib.current_stream_ptr()))
+    return lat_out, nxt

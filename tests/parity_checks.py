@@ -1,0 +1,214 @@
+"""Parity checks of each CUDA kernel (through the C ABI) against an fp32 torch reference fed the SAME
+16-bit-rounded inputs and weights (then only accumulation order and one output rounding
+differ, so fp16 can meet rtol 1e-3 per op; bf16's output rounding alone is 2^-8, so it gets rtol 1.6e-2).
+
+Every check returns a dict(name, err, tol, ok, ...); ``tests/test_ops_gpu.py`` asserts on them and
+``scripts/gpu_report.py`` prints them all without stopping at the first failure.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+import torch.nn.functional as F
+
+from rcdms_b200 import ops
+
+# tolerances: |ours - ref| <= atol + rtol * |ref|, with atol scaled by the reference's RMS
+TOL = {torch.float16: (1e-3, 1e-3), torch.bfloat16: (1.6e-2, 8e-3)}
+
+
+def _result(name, out, ref, dtype, extra=None, rtol_mul=1.0):
+    out = out.float()
+    ref = ref.float()
+    rtol, atol_rel = TOL[dtype]
+    rtol *= rtol_mul
+    scale = ref.pow(2).mean().sqrt().item() + 1e-12
+    atol = atol_rel * rtol_mul * scale
+    diff = (out - ref).abs()
+    bad = diff > (atol + rtol * ref.abs())
+    finite = bool(torch.isfinite(out).all())
+    r = dict(name=name, dtype=str(dtype).replace("torch.", ""), max_abs=diff.max().item(), ref_rms=scale,
+             rel=diff.max().item() / scale, frac_bad=bad.float().mean().item(), ok=finite and not bool(bad.any()))
+    if extra:
+        r.update(extra)
+    return r
+
+
+def _rand(shape, dtype, gen, scale=1.0):
+    return (torch.randn(shape, generator=gen, device="cuda") * scale).to(dtype)
+
+
+def _gen(seed):
+    g = torch.Generator(device="cuda")
+    g.manual_seed(seed)
+    return g
+
+
+def check_linear(M, N, K, dtype, bias=True, residual=False, tile_n=0, simple=False, seed=0):
+    g = _gen(seed)
+    a = _rand((M, K), dtype, g)
+    w = _rand((N, K), dtype, g, 1.0 / math.sqrt(K))
+    b = torch.randn((N,), generator=g, device="cuda") if bias else None
+    r = _rand((M, N), dtype, g) if residual else None
+    out = ops.linear(a, w, b, r, tile_n=tile_n, simple=simple)
+    ref = a.float() @ w.float().t()
+    if bias:
+        ref = ref + b
+    if residual:
+        ref = ref + r.float()
+    return _result(f"linear M{M} N{N} K{K} bn{tile_n} b{int(bias)} r{int(residual)} s{int(simple)}", out, ref, dtype)
+
+
+def check_geglu(M, C, dtype, simple=False, seed=1):
+    g = _gen(seed)
+    a = _rand((M, C), dtype, g)
+    w = _rand((8 * C, C), dtype, g, 1.0 / math.sqrt(C))
+    b = torch.randn((8 * C,), generator=g, device="cuda") * 0.5
+    out = ops.geglu_linear(a, w, b, simple=simple)
+    hg = a.float() @ w.float().t() + b
+    h, gate = hg.chunk(2, dim=-1)
+    ref = h * F.gelu(gate)
+    return _result(f"geglu M{M} C{C} s{int(simple)}", out, ref, dtype, rtol_mul=2.0)
+
+
+def check_conv3x3(n, h, w, cin, cout, stride, dtype, residual=False, simple=False, seed=2):
+    g = _gen(seed)
+    x = _rand((n, h, w, cin), dtype, g)
+    wt = _rand((cout, cin, 3, 3), dtype, g, 1.0 / math.sqrt(9 * cin))
+    b = torch.randn((cout,), generator=g, device="cuda")
+    r = _rand((n, h // stride, w // stride, cout), dtype, g) if residual else None
+    out = ops.conv3x3(x, wt, b, r, stride=stride, simple=simple)
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), wt.float(), b, stride=stride, padding=1).permute(0, 2, 3, 1)
+    if residual:
+        ref = ref + r.float()
+    return _result(f"conv3x3 n{n} {h}x{w} {cin}->{cout} s{stride} r{int(residual)} simple{int(simple)}", out, ref,
+                   dtype)
+
+
+def check_groupnorm(nstat, rows_per_stat, C, dtype, silu=True, eps=1e-5, seed=3):
+    g = _gen(seed)
+    x = _rand((nstat * rows_per_stat, C), dtype, g) * 2 + 0.5
+    gamma = 1 + 0.2 * torch.randn((C,), generator=g, device="cuda")
+    beta = 0.2 * torch.randn((C,), generator=g, device="cuda")
+    out = ops.group_norm(x, gamma, beta, 32, rows_per_stat, eps, silu)
+    xr = x.float().reshape(nstat, rows_per_stat, C).permute(0, 2, 1)  # (N, C, L)
+    ref = F.group_norm(xr, 32, gamma, beta, eps)
+    if silu:
+        ref = F.silu(ref)
+    ref = ref.permute(0, 2, 1).reshape(nstat * rows_per_stat, C)
+    return _result(f"groupnorm nstat{nstat} rows{rows_per_stat} C{C} silu{int(silu)}", out, ref, dtype, rtol_mul=2.0)
+
+
+def check_layernorm(rows, C, dtype, pe=False, seed=4):
+    g = _gen(seed)
+    x = _rand((rows, C), dtype, g) * 1.5 + 0.3
+    gamma = 1 + 0.2 * torch.randn((C,), generator=g, device="cuda")
+    beta = 0.2 * torch.randn((C,), generator=g, device="cuda")
+    frames, rpf = 5, max(1, rows // 10)
+    pet = torch.randn((frames, C), generator=g, device="cuda") if pe else None
+    out = ops.layer_norm(x, gamma, beta, 1e-5, pet, rpf, frames)
+    ref = F.layer_norm(x.float(), (C,), gamma, beta, 1e-5)
+    if pe:
+        fr = (torch.arange(rows, device="cuda") // rpf) % frames
+        ref = ref + pet[fr]
+    return _result(f"layernorm rows{rows} C{C} pe{int(pe)}", out, ref, dtype, rtol_mul=2.0)
+
+
+def check_flash(batch, heads, sq, skv, d, dtype, simple=False, seed=5, qscale=1.0):
+    g = _gen(seed)
+    q = _rand((batch, sq, heads * d), dtype, g, qscale)
+    k = _rand((batch, skv, heads * d), dtype, g)
+    v = _rand((batch, skv, heads * d), dtype, g)
+    out = ops.flash_attention(q, k, v, heads, simple=simple)
+
+    def split(t, s):
+        return t.float().reshape(batch, s, heads, d).permute(0, 2, 1, 3)
+    ref = F.scaled_dot_product_attention(split(q, sq), split(k, skv), split(v, skv))
+    ref = ref.permute(0, 2, 1, 3).reshape(batch, sq, heads * d)
+    return _result(f"flash b{batch} h{heads} Sq{sq} Skv{skv} d{d} simple{int(simple)} qs{qscale}", out, ref, dtype,
+                   rtol_mul=3.0)
+
+
+def check_temporal(batch, frames, hw, heads, d, dtype, seed=6):
+    g = _gen(seed)
+    C = heads * d
+    qkv = _rand((batch * frames * hw, 3 * C), dtype, g)
+    out = ops.temporal_attention(qkv, batch, frames, hw, heads)
+    t = qkv.float().reshape(batch, frames, hw, 3, heads, d)
+    q, k, v = (t[:, :, :, i].permute(0, 2, 3, 1, 4) for i in range(3))  # (b, hw, heads, f, d)
+    ref = F.scaled_dot_product_attention(q, k, v)  # attention over f
+    ref = ref.permute(0, 3, 1, 2, 4).reshape(batch * frames * hw, C)
+    return _result(f"temporal b{batch} f{frames} hw{hw} h{heads} d{d}", out, ref, dtype, rtol_mul=3.0)
+
+
+def check_ddim(clips, f, h, w, dtype, cfg=True, seed=7):
+    from oracle.loop_ref import make_scheduler
+    g = _gen(seed)
+    nb = 2 * clips if cfg else clips
+    eps = _rand((nb, 4, f, h, w), dtype, g)
+    lat = _rand((clips, 4, f, h, w), dtype, g)
+    mask = (torch.rand((clips, 1, f, h, w), generator=g, device="cuda") > 0.5).to(dtype)
+    ml = _rand((clips, 4, f, h, w), dtype, g, 0.18)
+    sched = make_scheduler()
+    sched.set_timesteps(50)
+    t = 501
+    a_t = float(sched.alphas_cumprod[t])
+    a_prev = float(sched.alphas_cumprod[t - 20])
+    lat32 = lat.float().clone()
+    out, nxt = ops.ddim_cfg_step(eps, lat32, a_t, a_prev, 2.0, cfg, dtype, mask, ml, dtype)
+    e = eps.float()
+    if cfg:
+        eu, ec = e.chunk(2)
+        e = eu + 2.0 * (ec - eu)
+    ref = sched.step(e.cpu(), t, lat.float().cpu(), eta=0.0).prev_sample.cuda()
+    r = _result(f"ddim clips{clips} {f}x{h}x{w} cfg{int(cfg)}", out, ref, dtype, rtol_mul=2.0)
+    lat2 = torch.cat([out] * 2) if cfg else out
+    ref_next = torch.cat([lat2, torch.cat([mask] * (2 if cfg else 1)), torch.cat([ml] * (2 if cfg else 1))], dim=1)
+    r["next_exact"] = bool(torch.equal(nxt, ref_next))
+    r["master_matches"] = bool(torch.equal(lat32.to(dtype), out))
+    r["ok"] = r["ok"] and r["next_exact"] and r["master_matches"]
+    return r
+
+
+def all_op_checks(dtypes=(torch.float16, torch.bfloat16), quick=False):
+    """Yield thunks so a failing (or crashing) check does not hide the others."""
+    for dt in dtypes:
+        for (M, N, K) in [(256, 160, 64), (640, 320, 320), (1000, 128, 96), (130, 64, 128), (4096, 960, 320),
+                          (2560, 1280, 1280), (10, 256, 256), (850, 640, 768)]:
+            yield lambda M=M, N=N, K=K, dt=dt: check_linear(M, N, K, dt, bias=True, residual=(N % 2 == 0 and M > 200))
+        for bn in (64, 128, 160):
+            yield lambda bn=bn, dt=dt: check_linear(512, 320, 256, dt, tile_n=bn)
+        yield lambda dt=dt: check_linear(384, 192, 320, dt, bias=False)
+        yield lambda dt=dt: check_linear(40960, 320, 1280, dt, residual=True)
+        yield lambda dt=dt: check_linear(300, 320, 64, dt, simple=True)
+        for (M, C) in [(256, 64), (1024, 320), (100, 128)]:
+            yield lambda M=M, C=C, dt=dt: check_geglu(M, C, dt)
+        yield lambda dt=dt: check_geglu(128, 64, dt, simple=True)
+        for (n, h, w, cin, cout, s) in [(10, 8, 8, 64, 64, 1), (2, 64, 64, 128, 160, 1), (10, 4, 4, 128, 64, 1),
+                                        (10, 2, 2, 64, 128, 1), (10, 1, 1, 256, 256, 1), (3, 16, 16, 320, 640, 1),
+                                        (10, 32, 32, 64, 4, 1), (10, 8, 8, 64, 128, 2), (2, 64, 64, 64, 64, 2),
+                                        (10, 2, 2, 128, 128, 2), (5, 16, 16, 192, 320, 2)]:
+            yield lambda a=(n, h, w, cin, cout, s), dt=dt: check_conv3x3(*a, dt, residual=(a[4] % 8 == 0))
+        yield lambda dt=dt: check_conv3x3(4, 8, 8, 64, 64, 1, dt, simple=True)
+        yield lambda dt=dt: check_conv3x3(4, 8, 8, 64, 64, 2, dt, simple=True)
+        for (ns, rps, C, silu) in [(2, 5 * 64, 320, True), (10, 64, 64, False), (2, 5 * 4096, 320, True),
+                                   (10, 1, 256, True), (2, 5 * 256, 960, True), (10, 1024, 640, False),
+                                   (2, 20, 2560, True)]:
+            yield lambda a=(ns, rps, C), silu=silu, dt=dt: check_groupnorm(*a, dt, silu=silu,
+                                                                           eps=1e-5 if silu else 1e-6)
+        for (rows, C, pe) in [(640, 320, False), (640, 320, True), (100, 64, True), (2560, 1280, True),
+                              (1000, 640, False), (77, 256, False)]:
+            yield lambda a=(rows, C, pe), dt=dt: check_layernorm(a[0], a[1], dt, pe=a[2])
+        for (b, hds, sq, skv, d) in [(4, 8, 256, 256, 40), (3, 8, 64, 85, 40), (2, 8, 1024, 1024, 80),
+                                     (2, 8, 256, 256, 160), (10, 8, 64, 64, 8), (10, 8, 16, 7, 16),
+                                     (10, 8, 4, 4, 32), (10, 8, 1, 1, 32), (2, 2, 4096, 4096, 40),
+                                     (2, 8, 1024, 91, 80), (2, 4, 300, 200, 40)]:
+            yield lambda a=(b, hds, sq, skv, d), dt=dt: check_flash(*a, dt)
+        yield lambda dt=dt: check_flash(2, 4, 512, 512, 40, dt, qscale=8.0)
+        yield lambda dt=dt: check_flash(2, 8, 64, 85, 40, dt, simple=True)
+        for (b, f, hw, hds, d) in [(2, 5, 64, 8, 40), (2, 5, 16, 8, 8), (2, 5, 4096, 8, 40), (2, 5, 1, 8, 32),
+                                   (2, 5, 256, 8, 160), (1, 3, 10, 8, 80)]:
+            yield lambda a=(b, f, hw, hds, d), dt=dt: check_temporal(*a, dt)
+        yield lambda dt=dt: check_ddim(1, 5, 64, 64, dt, cfg=True)
+        yield lambda dt=dt: check_ddim(3, 5, 8, 8, dt, cfg=False)

@@ -1,0 +1,84 @@
+"""Whole-UNet parity on the GPU: CUDA path (through the drop-in module -> C ABI) vs
+(a) the fp32 oracle fed the same rounded weights/inputs, (b) the REFERENCE golden vectors in tests/golden/.
+
+Tolerance: north_star's rtol 1e-3/atol 1e-4 is below the reference's own fp16-vs-fp32 noise for
+a whole forward, so the bar is the noise floor: max|ours - ref_fp32| <= max(3 * max|ref_half - ref_fp32|, 5e-3) and
+mean|ours - ref_fp32| <= 2 * mean|ref_half - ref_fp32| + 1e-4, where ref_half is the oracle run in eager half on
+the same GPU."""
+import os
+
+import pytest
+import torch
+
+import unet_checks as uc
+from rcdms_b200.unet_spec import full_config, tiny_config
+
+pytestmark = pytest.mark.gpu
+
+
+def _assert_close(res):
+    s, fl = res["stats"], res["floor"]
+    assert s["finite"], s
+    assert s["max_abs"] <= max(3 * fl["max_abs"], 5e-3), (s, fl)
+    assert s["mean_abs"] <= 2 * fl["mean_abs"] + 1e-4, (s, fl)
+
+
+@pytest.mark.parametrize("shape,t,dtype", [((2, 5, 8, 8, 7), 981, torch.float16),
+                                            ((2, 5, 16, 16, 85), 501, torch.float16),
+                                            ((2, 5, 16, 16, 85), 501, torch.bfloat16),
+                                            ((4, 5, 32, 32, 91), 21, torch.float16)])
+def test_tiny_unet_matches_oracle(shape, t, dtype):
+    _assert_close(uc.run_case(tiny_config(), shape, t, dtype))
+
+
+def test_simple_and_tensorcore_paths_agree():
+    a = uc.run_case(tiny_config(), (2, 5, 8, 8, 7), 981, torch.float16, simple=True)
+    b = uc.run_case(tiny_config(), (2, 5, 8, 8, 7), 981, torch.float16, simple=False)
+    _assert_close(a)
+    _assert_close(b)
+    assert (a["y"].float() - b["y"].float()).abs().max().item() <= max(3 * a["floor"]["max_abs"], 5e-3)
+
+
+@pytest.mark.parametrize("name,cfg_fn", [("tiny_8x8", tiny_config), ("tiny_16x16", tiny_config),
+                                         ("full_8x8", full_config)])
+def test_matches_reference_golden(name, cfg_fn):
+    """tests/golden/unet_*.pt = outputs of the reference's own UNet3DConditionModel (fp32 CPU)."""
+    cfg = cfg_fn()
+    gold = torch.load(os.path.join(uc.GOLDEN, f"unet_{name}.pt"))
+    res = uc.run_case(cfg, tuple(gold["shape"]), gold["timestep"], torch.float16, seed=gold["input_seed"])
+    _assert_close(res)
+    # golden is fp32 weights/inputs; ours saw fp16-rounded ones: bound by the same noise floor
+    d = (res["y"].float().cpu() - gold["out"]).abs()
+    fl = res["floor"]
+    assert d.max().item() <= max(4 * fl["max_abs"], 8e-3), (d.max().item(), fl)
+    assert d.mean().item() <= 3 * fl["mean_abs"] + 2e-4, (d.mean().item(), fl)
+
+
+def test_forward_contract():
+    """Boundary behaviour of unet.py:322-463: new tensor, inputs untouched, tuple when return_dict=False,
+    python-number and 0-dim cuda int64 timesteps agree, state_dict round trip."""
+    cfg = tiny_config()
+    m = uc.build_model(cfg, torch.float16)
+    x, ctx = uc.golden_inputs(cfg, 2, 5, 8, 8, 7, 1)
+    x, ctx = x.cuda().half(), ctx.cuda().half()
+    x0, c0 = x.clone(), ctx.clone()
+    y1 = m(x, 981, encoder_hidden_states=ctx, return_dict=False)
+    assert isinstance(y1, tuple) and y1[0].shape == (2, 4, 5, 8, 8) and y1[0].dtype == torch.float16
+    y2 = m(x, torch.tensor(981, device="cuda"), encoder_hidden_states=ctx)
+    assert torch.is_tensor(y2) and torch.equal(y1[0], y2)
+    assert torch.equal(x, x0) and torch.equal(ctx, c0)
+    y3 = m(x.float(), 981.0, encoder_hidden_states=ctx.float(), return_dict=False)[0]
+    assert y3.dtype == torch.float32 and torch.allclose(y3, y2.float(), atol=2e-3)
+    sd = m.state_dict()
+    assert len(sd) == len(m._spec)
+    with pytest.raises(ValueError):
+        m(x[:, :4], 981, encoder_hidden_states=ctx)
+    with pytest.raises(ValueError):
+        m(x, 981, encoder_hidden_states=ctx[:3])
+    # weights changed in place -> re-bound on the next forward
+    with torch.no_grad():
+        m.conv_out.bias.add_(1.0)
+    y4 = m(x, 981, encoder_hidden_states=ctx)
+    assert torch.allclose(y4.float(), y2.float() + 1.0, atol=5e-3)
+    with pytest.raises(TypeError):
+        uc.build_model(cfg, torch.float32)(x.float(), 981, encoder_hidden_states=ctx.float())
