@@ -1,0 +1,329 @@
+#!/usr/bin/env python
+"""Benchmark of the RCDMs stage-2 denoise hot path on B200 (contract: see the task statement / DESIGN.md §5).
+
+    python bench.py --gpus 1 --steps 3 --warmup 3                 # this repo's CUDA path
+    python bench.py --impl reference --gpus 1 --steps 2 --warmup 1 # the reference algorithm on the host CPU cores
+    torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N   # one rank per GPU, clips sharded (weak scaling)
+
+A "step" is one pass of the hot path over one batch: the full denoise of `--clips` 5-frame clips per GPU
+(BASELINE.json configs[1]: PororoSV 512x512 -> 64x64 latents, 50 DDIM steps, fp16, CFG guidance 2.0, L = 85)
+from prepared latents / mask / masked-image latents / fused context to the final latents, by
+`rcdm_denoise_loop` (CUDA-graph replay of UNet + CFG + DDIM).  metric = story-frames/sec = 5 * clips * N / t.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FLOP_PER_FORWARD_64 = 11.044e12  # algorithmic FLOPs of one UNet forward, 512^2, 1 clip, CFG, L=85
+METRIC = "story-frames/sec @50 DDIM steps, 512x512x5-frame clip"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--clips", type=int, default=1, help="clips per GPU (batched into one UNet call)")
+    ap.add_argument("--ddim-steps", type=int, default=50)
+    ap.add_argument("--latent", type=int, default=64, help="latent height = width (64 <=> 512x512 frames)")
+    ap.add_argument("--ctx-len", type=int, default=85)
+    ap.add_argument("--dtype", default="fp16", choices=["fp16", "bf16"])
+    ap.add_argument("--guidance", type=float, default=2.0)
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-profile", action="store_true")
+    ap.add_argument("--cpu-budget-s", type=float, default=150.0)
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(tflops=d.get("bf16_tflops_sustained", 1400.0), tflops_burst=d.get("bf16_tflops", 1590.0),
+                    hbm=d.get("hbm_gbs", 6650.0), source="measured (MEASURED_PEAKS.json)")
+    return dict(tflops=1400.0, tflops_burst=1590.0, hbm=6650.0, source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.rows, self.proc, self.idx = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:  # noqa: BLE001
+                pass
+        return dict(sm_mhz=statistics.median(sm) if sm else None, sm_max_mhz=max(mx) if mx else None,
+                    reasons=sorted(reasons), samples=len(sm))
+
+
+# ----------------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle port of the reference algorithm on the host cores
+# ----------------------------------------------------------------------------------------------------------
+def cpu_reference_step_seconds(latent, ctx_len, ddim_steps, guidance, n_steps, n_warm, budget_s):
+    """Times `n_steps` DDIM steps (UNet forward at `latent`^2 + CFG + scheduler step) of ONE clip with the
+    oracle restatement of the reference (fp32, all host threads).  Returns (mean seconds per DDIM step, info)."""
+    import torch
+    from oracle.loop_ref import make_scheduler
+    from oracle.unet_ref import unet_forward
+    from rcdms_b200.synthetic import synthetic_clip_inputs, synthetic_state_dict
+    from rcdms_b200.unet_spec import full_config
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cfg = full_config()
+    sd = synthetic_state_dict(cfg, seed=0)
+    inp = synthetic_clip_inputs(0, latent, latent, ctx_len)
+    sched = make_scheduler()
+    sched.set_timesteps(ddim_steps)
+    lat, mask, ml, ctx = inp["latents"], inp["mask"], inp["masked_latents"], inp["ctx"]
+    mask2, ml2 = torch.cat([mask] * 2), torch.cat([ml] * 2)
+    times = []
+    t_start = time.time()
+    with torch.no_grad():
+        for i, t in enumerate(sched.timesteps[: n_warm + n_steps]):
+            t0 = time.time()
+            x = torch.cat([torch.cat([lat] * 2), mask2, ml2], dim=1)
+            eps = unet_forward(sd, cfg, x, t, ctx)
+            eu, ec = eps.chunk(2)
+            lat = sched.step(eu + guidance * (ec - eu), t, lat, eta=0.0).prev_sample
+            dt = time.time() - t0
+            if i >= n_warm:
+                times.append(dt)
+            if time.time() - t_start > budget_s and times:
+                break
+    return sum(times) / len(times), dict(cores=cores, threads=torch.get_num_threads(), executed=len(times))
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    t_step, info = cpu_reference_step_seconds(a.latent, a.ctx_len, a.ddim_steps, a.guidance, a.steps,
+                                              min(a.warmup, 1), budget_s=240.0)
+    clip_s = t_step * a.ddim_steps
+    value = 5.0 / clip_s
+    sample = (f"{info['executed']} of {a.ddim_steps} DDIM steps (UNet fp32 forward at {a.latent}x{a.latent} latents + CFG "
+              f"+ DDIM step) of one clip, extrapolated x{a.ddim_steps}")
+    line = dict(metric=METRIC, value=value, unit="frames/s", n_gpus=a.gpus, steps=a.steps, warmup=a.warmup,
+                ms_per_step=clip_s * 1e3, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
+                data="synthetic", impl="reference",
+                config=dict(workload=workload_name(a), clips_per_gpu=1, ddim_steps=a.ddim_steps, latent=a.latent,
+                            ctx_len=a.ctx_len, guidance=a.guidance,
+                            note="reference algorithm = oracle port of src/models/unet.py + diffusers DDIM on host CPU; "
+                                 "the Python reference itself cannot travel to the GPU box"),
+                cpu_baseline=dict(value=value, unit="frames/s", cores=info["cores"], kind="port", sample=sample),
+                e2e=dict(value=value, unit="frames/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
+    print(json.dumps(line), flush=True)
+
+
+def workload_name(a):
+    px = a.latent * 8
+    return (f"stage2 PororoSV {px}x{px}, {a.ddim_steps} DDIM steps, {a.dtype}, batch={a.clips} clip(s)/GPU, "
+            f"CFG {a.guidance}, L={a.ctx_len}")
+
+
+# ----------------------------------------------------------------------------------------------------------
+# our arm
+# ----------------------------------------------------------------------------------------------------------
+def run_ours(a):
+    import torch
+    import torch.distributed as dist
+    from rcdms_b200 import _lib
+    from rcdms_b200.models import UNet3DConditionModel
+    from rcdms_b200.pipelines.RCDMs_pipeline import RCDMsPipeline
+    from rcdms_b200.schedulers import DDIMScheduler
+    from rcdms_b200.synthetic import synthetic_clip_inputs, synthetic_state_dict
+    from rcdms_b200.unet_spec import RCDMS_SCHEDULER_KWARGS, full_config
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    dtype = torch.float16 if a.dtype == "fp16" else torch.bfloat16
+    L = _lib.lib()  # fails loudly if the CUDA library is missing
+
+    cfg = full_config()
+    unet = UNet3DConditionModel.from_config(cfg)
+    unet.load_state_dict(synthetic_state_dict(cfg, seed=0), strict=True)
+    unet = unet.to(device=dev, dtype=dtype)
+
+    class _VaeCfg:  # the pipeline only needs vae_scale_factor = 8 here; VAE/CLIP stay outside the hot path
+        block_out_channels = (128, 256, 512, 512)
+
+    class _Vae:
+        config = _VaeCfg()
+    pipe = RCDMsPipeline(vae=_Vae(), text_encoder=None, tokenizer=None, unet=unet, local_module=None,
+                         global_module=None, scheduler=DDIMScheduler(**RCDMS_SCHEDULER_KWARGS))
+    pipe.use_cuda_graph = not a.no_graph
+
+    # per-clip synthetic inputs, clip index = global (rank-independent results); pinned host copies for e2e
+    clip_ids = [rank * a.clips + i for i in range(a.clips)]
+    ins = [synthetic_clip_inputs(k, a.latent, a.latent, a.ctx_len) for k in clip_ids]
+    host = dict(
+        latents=torch.cat([i["latents"] for i in ins]).to(dtype).pin_memory(),
+        masked=torch.cat([i["masked_latents"] for i in ins]).to(dtype).pin_memory(),
+        mask=torch.cat([i["mask"] for i in ins]).to(dtype).pin_memory(),
+        # ctx rows ordered (b f) with b = [uncond clips..., cond clips...]
+        ctx=torch.cat([i["ctx"][:5] for i in ins] + [i["ctx"][5:] for i in ins]).to(dtype).pin_memory())
+    devt = {k: v.to(dev) for k, v in host.items()}
+    out_host = torch.empty_like(host["latents"]).pin_memory()
+
+    def denoise_resident():
+        return pipe.denoise(devt["latents"], torch.cat([devt["mask"]] * 2), torch.cat([devt["masked"]] * 2), devt["ctx"],
+                            a.ddim_steps, a.guidance)
+
+    def denoise_e2e():
+        d = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
+        lat = pipe.denoise(d["latents"], torch.cat([d["mask"]] * 2), torch.cat([d["masked"]] * 2), d["ctx"],
+                           a.ddim_steps, a.guidance)
+        out_host.copy_(lat, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return lat
+
+    def gather(lat):
+        if world > 1:  # the path's only collective: final latents of every shard
+            buf = torch.empty((world,) + tuple(lat.shape), dtype=lat.dtype, device=dev)
+            dist.all_gather_into_tensor(buf, lat.contiguous())
+            return buf
+        return lat
+
+    def timed(fn, k):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(k):
+            gather(fn())
+        e1.record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item()
+
+    for _ in range(max(a.warmup, 3)):
+        gather(denoise_resident())
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = L.rcdm_kernel_launches()
+    ms_total = timed(denoise_resident, a.steps)
+    launches = L.rcdm_kernel_launches() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    gather(denoise_e2e())
+    ms_e2e = timed(denoise_e2e, a.steps)
+
+    ms_per_step = ms_total / a.steps
+    frames = 5 * a.clips * world
+    value = frames / (ms_per_step / 1e3)
+    e2e_value = frames / (ms_e2e / a.steps / 1e3)
+    flop_step = FLOP_PER_FORWARD_64 * (a.latent / 64.0) ** 2 * a.clips * a.ddim_steps  # per GPU per "step" (approx. off 64^2)
+    pk = peaks()
+
+    roofline = None
+    if not a.no_profile and rank == 0:
+        # dominant kernel = gemm_tcgen05_kernel (Linear / conv1x1 / implicit-GEMM conv3x3): per-launch CUDA-event timing
+        x = torch.cat([torch.cat([devt["latents"]] * 2), torch.cat([devt["mask"]] * 2), torch.cat([devt["masked"]] * 2)], 1)
+        prof = unet.profile(x, 501.0, devt["ctx"], reps=3)
+        agg = {}
+        for p in prof:
+            g = agg.setdefault(p["kind"], dict(ms=0.0, flops=0.0, bytes=0.0, n=0))
+            g["ms"] += p["ms"]
+            g["flops"] += p["flops"]
+            g["bytes"] += p["bytes"]
+            g["n"] += 1
+        tot_ms = sum(g["ms"] for g in agg.values())
+        mm = [agg[k] for k in ("gemm", "gemm_geglu", "conv3x3") if k in agg]
+        mm_ms, mm_fl, mm_n = sum(g["ms"] for g in mm), sum(g["flops"] for g in mm), sum(g["n"] for g in mm)
+        achieved = mm_fl / (mm_ms / 1e3) / 1e12
+        roofline = dict(bound="tensor", kernel="gemm_tcgen05_kernel", achieved=achieved, peak=pk["tflops"], unit="TFLOP/s",
+                        frac=achieved / pk["tflops"], traffic=None, peak_source=pk["source"] + ", sustained bf16",
+                        launches_per_forward=mm_n, share_of_forward=mm_ms / tot_ms,
+                        flops_per_launch_avg=mm_fl / mm_n, ms_per_launch_avg=mm_ms / mm_n,
+                        by_kind={k: dict(ms=round(v["ms"], 4), n=v["n"],
+                                         tflops=round(v["flops"] / max(v["ms"], 1e-9) / 1e9, 1),
+                                         gbs=round(v["bytes"] / max(v["ms"], 1e-9) / 1e6, 1)) for k, v in agg.items()},
+                        forward_ms_sum_of_ops=tot_ms)
+
+    cpu_baseline = None
+    if not a.no_cpu_baseline and rank == 0 and world == 1:
+        t_step, info = cpu_reference_step_seconds(a.latent, a.ctx_len, a.ddim_steps, a.guidance, 1, 0, a.cpu_budget_s)
+        cpu_baseline = dict(value=5.0 / (t_step * a.ddim_steps), unit="frames/s", cores=info["cores"], kind="port",
+                            sample=f"1 of {a.ddim_steps} DDIM steps (UNet fp32 forward at {a.latent}x{a.latent} latents + "
+                                   f"CFG + DDIM) of one clip, {t_step:.1f} s, extrapolated x{a.ddim_steps}")
+
+    if rank == 0:
+        h2d = sum(v.numel() * v.element_size() for v in host.values())
+        d2h = out_host.numel() * out_host.element_size()
+        line = dict(metric=METRIC, value=value, unit="frames/s", n_gpus=world, steps=a.steps, warmup=max(a.warmup, 3),
+                    ms_per_step=ms_per_step, higher_is_better=True, scaling="weak", vs_baseline=None,
+                    dtype="f16" if a.dtype == "fp16" else "bf16", data="synthetic",
+                    config=dict(workload=workload_name(a), clips_per_gpu=a.clips, ddim_steps=a.ddim_steps,
+                                latent=a.latent, ctx_len=a.ctx_len, guidance=a.guidance, cuda_graph=not a.no_graph,
+                                parallelism=f"clip-sharded x{world}, one all_gather of final latents",
+                                l2="not flushed: per-step working set (2.55 GB fp16 weights + activations) >> 126 MB L2",
+                                ms_per_ddim_step=ms_per_step / a.ddim_steps,
+                                achieved_tflops_per_gpu=flop_step / (ms_per_step / 1e3) / 1e12,
+                                frac_of_sustained_bf16_peak=flop_step / (ms_per_step / 1e3) / 1e12 / pk["tflops"]),
+                    e2e=dict(value=e2e_value, unit="frames/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
+                             ms_per_step=ms_e2e / a.steps, api="RCDMsPipeline.denoise (host pinned tensors in, host latents out)"),
+                    gpu_launches=int(launches), clocks=clocks, roofline=roofline, cpu_baseline=cpu_baseline)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)
+
+
+if __name__ == "__main__":
+    main()

@@ -143,6 +143,55 @@ int rcdm_unet_forward(rcdm_unet* h, const void* sample_dev, int sample_dtype, co
   API_END
 }
 
+int rcdm_unet_profile(rcdm_unet* h, const void* sample_dev, int sample_dtype, double timestep_host,
+                      const void* ctx_dev, int ctx_dtype, void* out_dev, int out_dtype, int reps, int max_ops,
+                      float* ms_host, double* flops_host, double* bytes_host, char* kinds_host, int* n_ops,
+                      void* stream) {
+  API_BEGIN
+  if (!h || !sample_dev || !ctx_dev || !out_dev || !n_ops) return set_err("null argument");
+  if (!h->planned) return set_err("rcdm_unet_profile: call rcdm_unet_prepare first");
+  if (rcdm_unet_weights_missing(h)) return set_err("rcdm_unet_profile: weights not loaded");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  h->cur_sample = sample_dev;
+  h->cur_sample_dt = sample_dtype;
+  h->cur_t_dev = nullptr;
+  h->cur_t_host = (float)timestep_host;
+  h->cur_ctx = ctx_dev;
+  h->cur_ctx_dt = ctx_dtype;
+  h->cur_out = out_dev;
+  h->cur_out_dt = out_dtype;
+  if (unet_run(h, true, true, st)) return 1;  // warm-up (also finalises weights, computes the context K/V)
+  const int n = (int)h->step_ops.size();
+  *n_ops = n;
+  if (n > max_ops) return set_err("rcdm_unet_profile: max_ops too small");
+  std::vector<cudaEvent_t> ev(n + 1);
+  for (auto& e : ev) CUDA_OK(cudaEventCreate(&e));
+  std::vector<double> acc(n, 0.0);
+  if (reps < 1) reps = 1;
+  for (int r = 0; r < reps; ++r) {
+    CUDA_OK(cudaEventRecord(ev[0], st));
+    for (int i = 0; i < n; ++i) {
+      h->step_ops[i](st);
+      CUDA_OK(cudaEventRecord(ev[i + 1], st));
+    }
+    CUDA_OK(cudaStreamSynchronize(st));
+    for (int i = 0; i < n; ++i) {
+      float ms = 0.f;
+      CUDA_OK(cudaEventElapsedTime(&ms, ev[i], ev[i + 1]));
+      acc[i] += ms;
+    }
+  }
+  for (auto& e : ev) cudaEventDestroy(e);
+  for (int i = 0; i < n; ++i) {
+    if (ms_host) ms_host[i] = (float)(acc[i] / reps);
+    if (flops_host) flops_host[i] = h->step_meta[i].flops;
+    if (bytes_host) bytes_host[i] = h->step_meta[i].bytes;
+    if (kinds_host) memcpy(kinds_host + (size_t)i * 16, h->step_meta[i].kind, 16);
+  }
+  return check_launch("rcdm_unet_profile");
+  API_END
+}
+
 int64_t rcdm_unet_read_tap(rcdm_unet* h, const char* name, float* out_dev, int64_t capacity, int* rows, int* channels,
                            void* stream) {
   try {

@@ -77,6 +77,12 @@ struct BlockW {
 
 using Op = std::function<void(cudaStream_t)>;
 
+struct OpMeta {  // one entry per recorded step op (for rcdm_unet_profile)
+  char kind[16];
+  double flops;  // algorithmic FLOPs (2*MAC, no padding)
+  double bytes;  // algorithmic HBM bytes (inputs + outputs once)
+};
+
 struct TapInfo {
   size_t off;
   int rows, C;
@@ -105,6 +111,7 @@ struct rcdm_unet_impl {
   unsigned char* ws = nullptr;
   size_t ws_bytes = 0;
   std::vector<Op> ctx_ops, step_ops;
+  std::vector<OpMeta> step_meta;
   bool taps_enabled = false;
   std::map<std::string, TapInfo> taps;
   int simple = 0;

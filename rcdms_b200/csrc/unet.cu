@@ -423,19 +423,41 @@ struct Planner {
     if (!failed) err = m;
     failed = true;
   }
-  void push(Op op) {
-    if (!dry) ops->push_back(std::move(op));
+  void push(Op op, const char* kind = "misc", double flops = 0.0, double bytes = 0.0) {
+    if (dry) return;
+    ops->push_back(std::move(op));
+    if (ops == &h->step_ops) {
+      OpMeta m;
+      memset(&m, 0, sizeof m);
+      strncpy(m.kind, kind, sizeof(m.kind) - 1);
+      m.flops = flops;
+      m.bytes = bytes;
+      h->step_meta.push_back(m);
+    }
   }
 
   // ---------------- op emitters ----------------
   void gemm(GemmDesc d) {
     if (dry || failed) return;
     d.dt = h->dt;
+    // algorithmic FLOPs: 2*M*N*K with K = sum of segment channels (x9 for 3x3 taps), no padding
+    double k_alg = 0;
+    bool conv = false;
+    for (int i = 0; i < d.nseg; ++i) {
+      k_alg += d.seg[i].mode == SEG_PLAIN ? d.seg[i].C : 9.0 * d.seg[i].C;
+      conv |= d.seg[i].mode != SEG_PLAIN;
+    }
+    if (d.seg[0].mode == SEG_PLAIN && d.nseg == 1 && d.seg[0].C == h->conv_in_kpad && d.w == wm(h->conv_in_w))
+      k_alg = 9.0 * h->cfg.in_channels;
+    const double flops = 2.0 * d.M * d.N * k_alg;
+    const double bytes = 2.0 * ((double)d.M * k_alg / (conv ? 9.0 : 1.0) + (double)d.N * k_alg +
+                                (double)d.M * (d.geglu ? d.N / 2 : d.N));
+    const char* kind = conv ? "conv3x3" : (d.geglu ? "gemm_geglu" : "gemm");
     if (h->simple) {
       push([d](cudaStream_t s) {
         gemm_simple_launch(d, s);
         g_launches++;
-      });
+      }, kind, flops, bytes);
       return;
     }
     GemmLaunch l;
@@ -444,7 +466,7 @@ struct Planner {
     push([l](cudaStream_t s) {
       gemm_launch(l, s);
       g_launches++;
-    });
+    }, kind, flops, bytes);
   }
   // plain GEMM: out[M,N] = A[M,K] W^T (+bias)(+res)
   void linear(size_t a_off, int M, int K, const Mat& w, const Vec* bias, size_t out_off, int ldo, const size_t* res_off,
@@ -475,7 +497,7 @@ struct Planner {
     gn_configure(&l, h->dt, p(x0.off), x0.C, x1 ? p(x1->off) : nullptr, x1 ? x1->C : 0, rows(x0),
                  per_frame ? hw : h->F * hw, h->cfg.norm_num_groups, eps, wv(g), wv(b), p(out_off), silu ? 1 : 0,
                  p(gn_scratch));
-    push([l](cudaStream_t s) { gn_run(l, s); });
+    push([l](cudaStream_t s) { gn_run(l, s); }, "groupnorm", 0.0, 3.0 * rows(x0) * (x0.C + (x1 ? x1->C : 0)) * 2.0);
   }
   void layernorm(size_t x_off, size_t out_off, int nrows, int C, const Vec& g, const Vec& b, const Vec* pe,
                  int rows_per_frame) {
@@ -487,16 +509,20 @@ struct Planner {
     const float* pep = pe ? wv(*pe) : nullptr;
     const int frames = h->F, dt = h->dt;
     if ((C / 8 + 31) / 32 > 5) return fail("layernorm: C too large");
-    push([=](cudaStream_t s) { ln_run(dt, x, o, gp, bp, nrows, C, 1e-5f, pep, rows_per_frame, frames, s); });
+    push([=](cudaStream_t s) { ln_run(dt, x, o, gp, bp, nrows, C, 1e-5f, pep, rows_per_frame, frames, s); }, "layernorm",
+         0.0, 2.0 * nrows * C * 2.0);
   }
   void attention(AttnDesc d) {
     if (dry || failed) return;
     d.dt = h->dt;
+    const double flops = 4.0 * d.batch * d.heads * (double)d.S_q * d.S_kv * d.d;
+    const double bytes = 2.0 * d.batch * d.heads * d.d * (2.0 * d.S_q + 2.0 * d.S_kv);
+    const char* kind = d.S_q == d.S_kv ? "attn_self" : "attn_cross";
     if (h->simple) {
       push([d](cudaStream_t s) {
         attn_simple_launch(d, s);
         g_launches++;
-      });
+      }, kind, flops, bytes);
       return;
     }
     AttnLaunch l;
@@ -505,7 +531,7 @@ struct Planner {
     push([l](cudaStream_t s) {
       attn_launch(l, s);
       g_launches++;
-    });
+    }, kind, flops, bytes);
   }
   void tap(const std::string& name, const Act& a) {
     if (!h->taps_enabled) return;
@@ -668,7 +694,7 @@ struct Planner {
         push([=](cudaStream_t s) {
           temporal_attn_launch(dt, qp, op, B, F, HW, heads, d, s);
           g_launches++;
-        });
+        }, "attn_temporal", 4.0 * B * HW * heads * (double)F * F * d, 2.0 * M * 4.0 * C);
       }
       free_act(qkv);
       linear(tmp.off, M, C, m.att[i].out, &m.att[i].outb, y.off, C, &y.off);
@@ -973,6 +999,7 @@ int unet_create(const rcdm_unet_config* cfg, rcdm_unet** out) {
 static void release_plan(rcdm_unet_impl* h) {
   h->ctx_ops.clear();
   h->step_ops.clear();
+  h->step_meta.clear();
   h->taps.clear();
   if (h->graph_exec) {
     cudaGraphExecDestroy(h->graph_exec);

@@ -266,6 +266,30 @@ class UNet3DConditionModel(nn.Module):
             return (out,)
         return out  # the reference returns the bare tensor here too (unet.py:462-463)
 
+    # ---- measurement -----------------------------------------------------------------------------------
+    @torch.no_grad()
+    def profile(self, sample: torch.Tensor, timestep: float, encoder_hidden_states: torch.Tensor, reps: int = 3):
+        """Per-op CUDA-event timing of one forward (``rcdm_unet_profile``): list of dicts
+        {kind, ms, flops, bytes} in launch order."""
+        b, c, f, h, w = sample.shape
+        ctx = encoder_hidden_states.contiguous()
+        sample = sample.contiguous()
+        self._ensure_bound()
+        self._prepare(b, f, h, w, ctx.shape[1])
+        out = torch.empty((b, self.config.out_channels, f, h, w), dtype=sample.dtype, device=sample.device)
+        C = _lib.C
+        cap = 4096
+        ms, fl, by = (C.c_float * cap)(), (C.c_double * cap)(), (C.c_double * cap)()
+        kinds = C.create_string_buffer(16 * cap)
+        n = C.c_int()
+        _lib.check(_lib.lib().rcdm_unet_profile(
+            self._handle, sample.data_ptr(), _lib.torch_dtype_id(sample.dtype), float(timestep), ctx.data_ptr(),
+            _lib.torch_dtype_id(ctx.dtype), out.data_ptr(), _lib.torch_dtype_id(out.dtype), reps, cap, ms, fl, by,
+            kinds, C.byref(n), _lib.current_stream_ptr()))
+        raw = kinds.raw
+        return [dict(kind=raw[16 * i:16 * i + 16].split(b"\0")[0].decode(), ms=ms[i], flops=fl[i], bytes=by[i])
+                for i in range(n.value)]
+
     # ---- debugging aid ----------------------------------------------------------------------------------
     def enable_taps(self, enable: bool = True) -> None:
         self._ensure_bound()
