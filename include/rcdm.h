@@ -104,8 +104,8 @@ RCDM_API int rcdm_unet_forward(rcdm_unet* h, const void* sample_dev, int sample_
  * padding) and algorithmic bytes.  Host output arrays of length max_ops (kinds: 16 bytes each). */
 RCDM_API int rcdm_unet_profile(rcdm_unet* h, const void* sample_dev, int sample_dtype, double timestep_host,
                       const void* ctx_dev, int ctx_dtype, void* out_dev, int out_dtype, int reps, int max_ops,
-                      float* ms_host, double* flops_host, double* bytes_host, char* kinds_host, int* n_ops,
-                      void* stream);
+                      float* ms_host, double* flops_host, double* bytes_host, char* kinds_host,
+                      int* dims_host /*[3*max_ops]: M,N,K of GEMM-like ops*/, int* n_ops, void* stream);
 /* debug: copy an internal activation recorded during the last forward ("conv_in", "down_blocks.0.resnets.0", ...)
  * as fp32 channels-last tokens [rows, C]; returns rows*C written (<= capacity), negative on error. */
 RCDM_API int64_t rcdm_unet_read_tap(rcdm_unet* h, const char* name, float* out_dev, int64_t capacity, int* rows, int* channels,

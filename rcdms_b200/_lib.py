@@ -48,7 +48,7 @@ SIGNATURES = {
     "rcdm_unet_workspace_bytes": (C.c_size_t, [_P]),
     "rcdm_unet_forward": (_I, [_P, _P, _I, _P, _D, _P, _I, _P, _I, _P]),
     "rcdm_unet_profile": (_I, [_P, _P, _I, _D, _P, _I, _P, _I, _I, _I, C.POINTER(_F), C.POINTER(_D), C.POINTER(_D),
-                               C.c_char_p, C.POINTER(_I), _P]),
+                               C.c_char_p, C.POINTER(_I), C.POINTER(_I), _P]),
     "rcdm_unet_read_tap": (_I64, [_P, C.c_char_p, _P, _I64, C.POINTER(_I), C.POINTER(_I), _P]),
     "rcdm_unet_enable_taps": (_I, [_P, _I]),
     "rcdm_ddim_cfg_step": (_I, [_P, _I, _P, _P, _I, _P, _I, _P, _I, _P, _I, _I, _I, _I, _I, _I, _F, _F, _F, _P]),

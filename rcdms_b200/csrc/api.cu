@@ -145,8 +145,8 @@ int rcdm_unet_forward(rcdm_unet* h, const void* sample_dev, int sample_dtype, co
 
 int rcdm_unet_profile(rcdm_unet* h, const void* sample_dev, int sample_dtype, double timestep_host,
                       const void* ctx_dev, int ctx_dtype, void* out_dev, int out_dtype, int reps, int max_ops,
-                      float* ms_host, double* flops_host, double* bytes_host, char* kinds_host, int* n_ops,
-                      void* stream) {
+                      float* ms_host, double* flops_host, double* bytes_host, char* kinds_host, int* dims_host,
+                      int* n_ops, void* stream) {
   API_BEGIN
   if (!h || !sample_dev || !ctx_dev || !out_dev || !n_ops) return set_err("null argument");
   if (!h->planned) return set_err("rcdm_unet_profile: call rcdm_unet_prepare first");
@@ -187,6 +187,11 @@ int rcdm_unet_profile(rcdm_unet* h, const void* sample_dev, int sample_dtype, do
     if (flops_host) flops_host[i] = h->step_meta[i].flops;
     if (bytes_host) bytes_host[i] = h->step_meta[i].bytes;
     if (kinds_host) memcpy(kinds_host + (size_t)i * 16, h->step_meta[i].kind, 16);
+    if (dims_host) {
+      dims_host[3 * i] = h->step_meta[i].m;
+      dims_host[3 * i + 1] = h->step_meta[i].n;
+      dims_host[3 * i + 2] = h->step_meta[i].k;
+    }
   }
   return check_launch("rcdm_unet_profile");
   API_END

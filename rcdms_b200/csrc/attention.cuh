@@ -42,7 +42,7 @@ template <int DPAD> struct AttnCfg {
 };
 
 template <typename T, int DPAD>
-__global__ void __launch_bounds__(160)
+__global__ void __launch_bounds__(160, AttnCfg<DPAD>::SMEM_BYTES <= 113 * 1024 ? 2 : 1)
 flash_attn_kernel(const __grid_constant__ AttnMaps maps, const AttnParams p) {
   using Cfg = AttnCfg<DPAD>;
   constexpr int KV = Cfg::KV_STAGES;
@@ -136,55 +136,106 @@ flash_attn_kernel(const __grid_constant__ AttnMaps maps, const AttnParams p) {
     }
   } else {
     // =================================== softmax warps ===================================
+    // One thread per query row.  Lazy online softmax: the first KV tile fixes the reference maximum m_run with a
+    // separate max pass; every later tile is ONE pass that exponentiates against m_run while tracking the tile
+    // maximum, and only if some row's tile maximum exceeds m_run by more than 2^8 (P would approach the 16-bit
+    // range) does the warp fall back to re-exponentiating the tile and rescaling O in TMEM.
     const int row = warp * 32 + lane;
     const uint32_t lane_sel = uint32_t(warp * 32) << 16;
+    const float sc = p.scale_log2;
     float m_run = -INFINITY, l_run = 0.f;
+    uint8_t* sP_row = sP + row * 16;
+
+    // exponentiate one 128-column S row against `mref`, write P, return the row sum; tracks the raw max in `mx`
+    auto exp_pass = [&](float mref, int kv_valid, float& mx) -> float {
+      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+      float x0 = -INFINITY, x1 = -INFINITY, x2 = -INFINITY, x3 = -INFINITY;
+      const bool full = kv_valid >= 128;
+#pragma unroll 1
+      for (int c = 0; c < 128; c += 64) {
+        uint32_t r[64];
+        tmem_ld32(tmem_S + lane_sel + c, r);
+        tmem_ld32(tmem_S + lane_sel + c + 32, r + 32);
+        tmem_wait_ld();
+        if (!full) {
+#pragma unroll
+          for (int i = 0; i < 64; ++i)
+            if (c + i >= kv_valid) r[i] = 0xff800000u;  // -inf: exp2 -> 0, ignored by max
+        }
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+          float pv[8];
+#pragma unroll
+          for (int i = 0; i < 8; i += 4) {
+            const float a0 = __uint_as_float(r[g * 8 + i]), a1 = __uint_as_float(r[g * 8 + i + 1]);
+            const float a2 = __uint_as_float(r[g * 8 + i + 2]), a3 = __uint_as_float(r[g * 8 + i + 3]);
+            x0 = fmaxf(x0, a0);
+            x1 = fmaxf(x1, a1);
+            x2 = fmaxf(x2, a2);
+            x3 = fmaxf(x3, a3);
+            pv[i] = exp2f(fmaf(a0, sc, -mref));
+            pv[i + 1] = exp2f(fmaf(a1, sc, -mref));
+            pv[i + 2] = exp2f(fmaf(a2, sc, -mref));
+            pv[i + 3] = exp2f(fmaf(a3, sc, -mref));
+            s0 += pv[i];
+            s1 += pv[i + 1];
+            s2 += pv[i + 2];
+            s3 += pv[i + 3];
+          }
+          // P tile, K-major interleaved: [chunk = kv/8][row][8 elems]
+          *reinterpret_cast<uint4*>(sP_row + (c / 8 + g) * 2048) = pack8<T>(pv);
+        }
+      }
+      mx = fmaxf(fmaxf(x0, x1), fmaxf(x2, x3));
+      return (s0 + s1) + (s2 + s3);
+    };
+
     for (int j = 0; j < n_kv; ++j) {
       mbar_wait(s_full, j & 1);
       tc_fence_after();
       const int kv_valid = min(128, p.S_kv - j * 128);
-      float mx = -INFINITY;
+      if (j == 0) {
+        float x0 = -INFINITY, x1 = -INFINITY;
 #pragma unroll 1
-      for (int c = 0; c < 128; c += 32) {
-        uint32_t r[32];
-        tmem_ld32(tmem_S + lane_sel + c, r);
-        tmem_wait_ld();
-#pragma unroll
-        for (int i = 0; i < 32; ++i)
-          if (c + i < kv_valid) mx = fmaxf(mx, __uint_as_float(r[i]));
-      }
-      const float m_new = fmaxf(m_run, mx * p.scale_log2);
-      const float alpha = exp2f(m_run - m_new);  // m_run = -inf on the first tile -> 0
-      float rowsum = 0.f;
-#pragma unroll 1
-      for (int c = 0; c < 128; c += 16) {
-        uint32_t r[16];
-        tmem_ld16(tmem_S + lane_sel + c, r);
-        tmem_wait_ld();
-        float pv[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const float e = exp2f(__uint_as_float(r[i]) * p.scale_log2 - m_new);
-          pv[i] = (c + i < kv_valid) ? e : 0.f;
-          rowsum += pv[i];
-        }
-        // P tile, K-major interleaved: [chunk = kv/8][row][8 elems]
-        *reinterpret_cast<uint4*>(sP + (c / 8) * 2048 + row * 16) = pack8<T>(pv);
-        *reinterpret_cast<uint4*>(sP + (c / 8 + 1) * 2048 + row * 16) = pack8<T>(pv + 8);
-      }
-      l_run = l_run * alpha + rowsum;
-      m_run = m_new;
-      if (j > 0 && __any_sync(0xffffffffu, alpha != 1.0f)) {
-#pragma unroll 1
-        for (int c = 0; c < DPAD; c += 16) {
-          uint32_t r[16];
-          tmem_ld16(tmem_O + lane_sel + c, r);
+        for (int c = 0; c < 128; c += 64) {
+          uint32_t r[64];
+          tmem_ld32(tmem_S + lane_sel + c, r);
+          tmem_ld32(tmem_S + lane_sel + c + 32, r + 32);
           tmem_wait_ld();
 #pragma unroll
-          for (int i = 0; i < 16; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
-          tmem_st16(tmem_O + lane_sel + c, r);
+          for (int i = 0; i < 64; i += 2) {
+            if (c + i < kv_valid) x0 = fmaxf(x0, __uint_as_float(r[i]));
+            if (c + i + 1 < kv_valid) x1 = fmaxf(x1, __uint_as_float(r[i + 1]));
+          }
         }
-        tmem_wait_st();
+        m_run = fmaxf(x0, x1) * sc;
+        float mx;
+        l_run = exp_pass(m_run, kv_valid, mx);
+      } else {
+        float mx;
+        const float sum = exp_pass(m_run, kv_valid, mx);
+        const float m_tile = mx * sc;
+        if (__any_sync(0xffffffffu, m_tile > m_run + 8.0f)) {
+          // rare: re-reference this tile (and everything accumulated so far) to the new maximum
+          const float m_new = fmaxf(m_run, m_tile);
+          const float alpha = exp2f(m_run - m_new);
+          float dummy;
+          const float sum2 = exp_pass(m_new, kv_valid, dummy);
+#pragma unroll 1
+          for (int c = 0; c < DPAD; c += 16) {
+            uint32_t r[16];
+            tmem_ld16(tmem_O + lane_sel + c, r);
+            tmem_wait_ld();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
+            tmem_st16(tmem_O + lane_sel + c, r);
+          }
+          tmem_wait_st();
+          l_run = l_run * alpha + sum2;
+          m_run = m_new;
+        } else {
+          l_run += sum;
+        }
       }
       fence_proxy_async_smem();
       tc_fence_before();

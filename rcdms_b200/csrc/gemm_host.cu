@@ -70,6 +70,17 @@ bool encode_tmap(CUtensorMap* out, const void* base, int rank, const uint64_t* d
 // ------------------------------------------------------------------------------------------
 static bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
 
+static int num_sms() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
+        n <= 0)
+      n = 148;
+  }
+  return n;
+}
+
 static int pick_bn(const GemmDesc& d) {
   if (d.force_bn) return d.force_bn;
   if (d.geglu) return GEGLU_BN;
@@ -174,7 +185,11 @@ bool gemm_prepare(const GemmDesc& d, GemmLaunch* l, std::string* err) {
     if (!encode_tmap(&l->maps.b, d.w, 2, dims, str, box, true, err)) return false;
   }
   const int m_tiles = has_conv ? ((d.NI + p.tn - 1) / p.tn) * p.tiles_y * p.tiles_x : (d.M + 127) / 128;
-  l->grid = dim3((d.N + bn - 1) / bn, m_tiles, 1);
+  p.num_m_tiles = m_tiles;
+  p.num_n_tiles = (d.N + bn - 1) / bn;
+  const int tiles = p.num_m_tiles * p.num_n_tiles;
+  const int sms = num_sms();
+  l->grid = dim3(tiles < sms ? tiles : sms, 1, 1);
   return true;
 }
 

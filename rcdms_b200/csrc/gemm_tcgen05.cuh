@@ -2,12 +2,14 @@
 //
 //   D[M, N] = sum over K-segments of A_seg[M, K_seg] * W[N, K_total]^T   (+ epilogue)
 //
-// One CTA computes a 128 x BN output tile.  Warp roles (192 threads):
-//   warp 0     TMA producer  (one elected lane)  : HBM -> 128B-swizzled smem ring
-//   warp 1     MMA issuer    (one elected lane)  : tcgen05.mma, accumulator in TMEM; owns TMEM alloc
-//   warps 2-5  epilogue      (thread <-> row)    : tcgen05.ld -> bias/residual/GEGLU -> global
-// Two CTAs are co-resident per SM (<= 113 KB smem, <= 256 TMEM columns each) so one CTA's epilogue
-// overlaps the other's main loop.
+// Persistent kernel, one CTA per SM, looping over 128 x BN output tiles.  Warp roles (192 threads):
+//   warp 0     TMA producer  (one elected lane)  : HBM/L2 -> 128B-swizzled smem ring (5-6 stages), runs ahead
+//                                                  across tile boundaries
+//   warp 1     MMA issuer    (one elected lane)  : tcgen05.mma into one of TWO TMEM accumulators; owns TMEM alloc
+//   warps 2-5  epilogue                          : residual prefetch (coalesced, before the accumulator is ready)
+//                                                  -> tcgen05.ld (+bias / GEGLU) -> 16-bit smem staging slab
+//                                                  -> 16-byte lane-contiguous global stores (+residual)
+// so the main loop of tile i+1 overlaps the epilogue of tile i.
 //
 // The K loop runs over up to three "segments", each reading A through its own TMA tensor map(s):
 //   SEG_PLAIN    A is a row-major [M, K] matrix             (Linear, conv1x1, im2col'ed conv_in)
@@ -37,6 +39,7 @@ struct GemmParams {
   GemmSeg seg[3];
   // conv tile geometry: a 128-row M tile is a (tn images) x (th rows) x (tw cols) box of the OUTPUT grid
   int tw, th, tn, tiles_x, tiles_y;
+  int num_m_tiles, num_n_tiles;  // persistent tile loop: tile = m_tile * num_n_tiles + n_tile
   // epilogue
   void* out;
   int ldo;
@@ -53,16 +56,23 @@ struct GemmMaps {
 
 template <int BN> struct GemmCfg {
   static constexpr int BM = 128, BK = 64;
-  static constexpr int STAGES = (BN <= 64) ? 4 : 3;
+  static constexpr int STAGES = (BN <= 64) ? 6 : 5;
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int TMEM_COLS = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int OUT_PITCH = BN * 2 + 16;  // +16 B keeps 16-byte row-strided smem stores conflict-free
+  static constexpr int STAGING_BYTES = BM * OUT_PITCH;
+  static constexpr int ACC_STRIDE = BN <= 64 ? 64 : BN <= 128 ? 128 : 256;  // TMEM columns between the 2 accumulators
+  static constexpr int TMEM_COLS = 2 * ACC_STRIDE;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB per-CTA shared memory limit");
 };
 
+// Persistent, warp-specialised: grid = min(#tiles, #SMs), one CTA per SM.  Tiles are visited round-robin
+// (n fastest, so CTAs running concurrently share A rows in L2).  The TMA producer runs ahead across tile
+// boundaries; two TMEM accumulators let the MMA warp start tile i+1 while the epilogue warps drain tile i.
 template <typename T, int BN>
-__global__ void __launch_bounds__(192, 2)
+__global__ void __launch_bounds__(192, 1)
 gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
   using Cfg = GemmCfg<BN>;
   constexpr int STAGES = Cfg::STAGES;
@@ -70,16 +80,17 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + STAGES * Cfg::A_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint8_t* staging = smem + STAGES * Cfg::STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + Cfg::STAGING_BYTES);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + STAGES;
-  uint64_t* tmem_full_bar = bars + 2 * STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
+  uint64_t* tmem_full_bar = bars + 2 * STAGES;       // [2]
+  uint64_t* tmem_empty_bar = bars + 2 * STAGES + 2;  // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int n_tile = blockIdx.x;
-  const int m_tile = blockIdx.y;
+  const int num_tiles = p.num_m_tiles * p.num_n_tiles;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&maps.b);
@@ -91,7 +102,10 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
         mbar_init(&full_bar[i], 1);
         mbar_init(&empty_bar[i], 1);
       }
-      mbar_init(tmem_full_bar, 1);
+      for (int i = 0; i < 2; ++i) {
+        mbar_init(&tmem_full_bar[i], 1);
+        mbar_init(&tmem_empty_bar[i], 128);
+      }
       fence_mbar_init();
     }
     __syncwarp();
@@ -105,44 +119,46 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
   if (warp == 0) {
     // =================================== TMA producer ===================================
     if (elect_one()) {
-      // decode the conv tile origin (only used by conv segments)
-      int t = m_tile;
-      const int tx = t % p.tiles_x;
-      t /= p.tiles_x;
-      const int ty = t % p.tiles_y;
-      const int tb = t / p.tiles_y;
-      const int x0 = tx * p.tw, y0 = ty * p.th, n0 = tb * p.tn;
       int stage = 0;
       uint32_t phase = 0;
-      int kb = 0;
-      for (int s = 0; s < p.nseg; ++s) {
-        const GemmSeg sg = p.seg[s];
-        const int ntap = (sg.mode == SEG_PLAIN) ? 1 : 9;
-        for (int tap = 0; tap < ntap; ++tap) {
-          int mi = sg.tmap, dx = 0, dy = 0;
-          if (sg.mode == SEG_CONV3) {
-            dy = tap / 3 - 1;
-            dx = tap % 3 - 1;
-          } else if (sg.mode == SEG_CONV3S2) {
-            const int ky = tap / 3, kx = tap % 3;
-            const int py = (ky + 1) & 1, px = (kx + 1) & 1;  // parity of (2y + ky - 1)
-            dy = (ky == 0) ? -1 : 0;
-            dx = (kx == 0) ? -1 : 0;
-            mi = sg.tmap + py * 2 + px;
-          }
-          for (int c = 0; c < sg.cblocks; ++c, ++kb) {
-            mbar_wait(&empty_bar[stage], phase ^ 1);
-            mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
-            void* sa = smem_a + stage * Cfg::A_BYTES;
-            void* sb = smem_b + stage * Cfg::B_BYTES;
-            if (sg.mode == SEG_PLAIN)
-              tma_load_2d(sa, &maps.a[mi], &full_bar[stage], c * 64, m_tile * 128);
-            else
-              tma_load_4d(sa, &maps.a[mi], &full_bar[stage], c * 64, x0 + dx, y0 + dy, n0);
-            tma_load_2d(sb, &maps.b, &full_bar[stage], kb * 64, n_tile * BN);
-            if (++stage == STAGES) {
-              stage = 0;
-              phase ^= 1;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int n_tile = tile % p.num_n_tiles, m_tile = tile / p.num_n_tiles;
+        int t = m_tile;  // conv tile origin (only used by conv segments)
+        const int tx = t % p.tiles_x;
+        t /= p.tiles_x;
+        const int ty = t % p.tiles_y;
+        const int tb = t / p.tiles_y;
+        const int x0 = tx * p.tw, y0 = ty * p.th, n0 = tb * p.tn;
+        int kb = 0;
+        for (int s = 0; s < p.nseg; ++s) {
+          const GemmSeg sg = p.seg[s];
+          const int ntap = (sg.mode == SEG_PLAIN) ? 1 : 9;
+          for (int tap = 0; tap < ntap; ++tap) {
+            int mi = sg.tmap, dx = 0, dy = 0;
+            if (sg.mode == SEG_CONV3) {
+              dy = tap / 3 - 1;
+              dx = tap % 3 - 1;
+            } else if (sg.mode == SEG_CONV3S2) {
+              const int ky = tap / 3, kx = tap % 3;
+              const int py = (ky + 1) & 1, px = (kx + 1) & 1;  // parity of (2y + ky - 1)
+              dy = (ky == 0) ? -1 : 0;
+              dx = (kx == 0) ? -1 : 0;
+              mi = sg.tmap + py * 2 + px;
+            }
+            for (int c = 0; c < sg.cblocks; ++c, ++kb) {
+              mbar_wait(&empty_bar[stage], phase ^ 1);
+              mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+              void* sa = smem_a + stage * Cfg::A_BYTES;
+              void* sb = smem_b + stage * Cfg::B_BYTES;
+              if (sg.mode == SEG_PLAIN)
+                tma_load_2d(sa, &maps.a[mi], &full_bar[stage], c * 64, m_tile * 128);
+              else
+                tma_load_4d(sa, &maps.a[mi], &full_bar[stage], c * 64, x0 + dx, y0 + dy, n0);
+              tma_load_2d(sb, &maps.b, &full_bar[stage], kb * 64, n_tile * BN);
+              if (++stage == STAGES) {
+                stage = 0;
+                phase ^= 1;
+              }
             }
           }
         }
@@ -154,108 +170,160 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
       constexpr uint32_t idesc = umma_idesc_f16(DT<T>::umma_fmt, 128, BN, 0, 0);
       int stage = 0;
       uint32_t phase = 0;
-      for (int kb = 0; kb < p.num_kb; ++kb) {
-        mbar_wait(&full_bar[stage], phase);
+      int it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);  // epilogue has drained this accumulator
         tc_fence_after();
-        const uint32_t a_addr = smem_u32(smem_a + stage * Cfg::A_BYTES);
-        const uint32_t b_addr = smem_u32(smem_b + stage * Cfg::B_BYTES);
+        const uint32_t d_tmem = tmem_base + acc * Cfg::ACC_STRIDE;
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem_a + stage * Cfg::A_BYTES);
+          const uint32_t b_addr = smem_u32(smem_b + stage * Cfg::B_BYTES);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          // K-major, 128B swizzle: rows at 128 B, 8-row groups at 1024 B; +32 B per 16-element K step
-          const uint64_t ad = umma_smem_desc(a_addr + k * 32, 16, 1024, UMMA_SWIZZLE_128B);
-          const uint64_t bd = umma_smem_desc(b_addr + k * 32, 16, 1024, UMMA_SWIZZLE_128B);
-          umma_f16_ss(tmem_base, ad, bd, idesc, (kb | k) != 0);
+          for (int k = 0; k < 4; ++k) {
+            // K-major, 128B swizzle: rows at 128 B, 8-row groups at 1024 B; +32 B per 16-element K step
+            const uint64_t ad = umma_smem_desc(a_addr + k * 32, 16, 1024, UMMA_SWIZZLE_128B);
+            const uint64_t bd = umma_smem_desc(b_addr + k * 32, 16, 1024, UMMA_SWIZZLE_128B);
+            umma_f16_ss(d_tmem, ad, bd, idesc, (kb | k) != 0);
+          }
+          umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs have read it
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
         }
-        umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs have read it
-        if (++stage == STAGES) {
-          stage = 0;
-          phase ^= 1;
-        }
+        umma_commit(&tmem_full_bar[acc]);
       }
-      umma_commit(tmem_full_bar);
     }
   } else {
     // =================================== epilogue ===================================
     const int q = warp & 3;  // TMEM lane quarter this warp may access
-    const int row = q * 32 + lane;
-    const int m = m_tile * 128 + row;
-    mbar_wait(tmem_full_bar, 0);
-    tc_fence_after();
-    const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16);
     T* out = reinterpret_cast<T*>(p.out);
     const T* res = reinterpret_cast<const T*>(p.res);
-    const bool row_ok = m < p.M;
-    if (!p.geglu) {
-      const bool vec_ok = (p.N % 8 == 0) && (p.ldo % 8 == 0);
-#pragma unroll 1
-      for (int c = 0; c < BN; c += 16) {
-        const int n = n_tile * BN + c;
-        if (n >= p.N) break;  // warp-uniform
-        uint32_t r[16];
-        tmem_ld16(taddr + c, r);
-        tmem_wait_ld();
-        if (!row_ok) continue;
-        float v[16];
+    const bool vec_ok = (p.N % 8 == 0) && (p.ldo % 8 == 0) && (!p.res || p.ldr % 8 == 0);
+    constexpr int PITCH = Cfg::OUT_PITCH;
+    uint8_t* stage_out = staging + (size_t)q * 32 * PITCH;  // this warp's private 32-row slab
+    const int out_w = p.geglu ? BN / 2 : BN;                // output columns produced per tile
+    const int n_total = p.geglu ? p.N / 2 : p.N;
+    constexpr int NCHUNK = BN / 8;                          // 16-byte chunks per staged row (max)
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int n_tile = tile % p.num_n_tiles, m_tile = tile / p.num_n_tiles;
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      const uint32_t taddr = tmem_base + acc * Cfg::ACC_STRIDE + (uint32_t(q * 32) << 16);
+      const int n_base = n_tile * out_w;
+      const int m_warp = m_tile * 128 + q * 32;
+      if (vec_ok) {
+        int cpr = (n_total - n_base) / 8;  // valid 16-byte chunks per row in this tile
+        if (cpr > out_w / 8) cpr = out_w / 8;
+        const int total = 32 * cpr;
+        // ---- residual prefetch: coalesced, issued BEFORE waiting for the accumulator (hidden by the main loop)
+        uint4 rv[NCHUNK];
+        if (res) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-        if (p.bias) {
-#pragma unroll
-          for (int i = 0; i < 16; ++i)
-            if (n + i < p.N) v[i] += __ldg(p.bias + n + i);
+          for (int u = 0; u < NCHUNK; ++u) {
+            const int id = u * 32 + lane;
+            const int rr = id / cpr, cc = id - rr * cpr;
+            if (id < total && m_warp + rr < p.M)
+              rv[u] = *reinterpret_cast<const uint4*>(res + (size_t)(m_warp + rr) * p.ldr + n_base + cc * 8);
+          }
         }
-        if (vec_ok) {
+        mbar_wait(&tmem_full_bar[acc], acc_phase);
+        tc_fence_after();
+        // ---- phase 1: TMEM -> registers (+bias, GEGLU) -> 16-bit staging slab (thread <-> row)
+        if (!p.geglu) {
+#pragma unroll 1
+          for (int c = 0; c < BN; c += 32) {
+            if (n_base + c >= n_total) break;  // warp-uniform
+            uint32_t r[32];
+            tmem_ld32(taddr + c, r);
+            tmem_wait_ld();
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            if (n + h * 8 < p.N) {
-              if (res) {
-                float rr[8];
-                unpack8<T>(*reinterpret_cast<const uint4*>(res + (size_t)m * p.ldr + n + h * 8), rr);
+            for (int g = 0; g < 4; ++g) {
+              float v[8];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) v[h * 8 + i] += rr[i];
+              for (int i = 0; i < 8; ++i) {
+                v[i] = __uint_as_float(r[g * 8 + i]);
+                if (p.bias && n_base + c + g * 8 + i < n_total) v[i] += __ldg(p.bias + n_base + c + g * 8 + i);
               }
-              *reinterpret_cast<uint4*>(out + (size_t)m * p.ldo + n + h * 8) = pack8<T>(v + h * 8);
+              if (c + g * 8 < BN) *reinterpret_cast<uint4*>(stage_out + lane * PITCH + (c + g * 8) * 2) = pack8<T>(v);
             }
           }
         } else {
-          for (int i = 0; i < 16; ++i) {
-            if (n + i < p.N) {
-              float x = v[i];
-              if (res) x += DT<T>::to_f(res[(size_t)m * p.ldr + n + i]);
-              out[(size_t)m * p.ldo + n + i] = DT<T>::from_f(x);
+          constexpr int HB = BN / 2;
+#pragma unroll 1
+          for (int c = 0; c < HB; c += 16) {
+            uint32_t rh[16], rg[16];
+            tmem_ld16(taddr + c, rh);
+            tmem_ld16(taddr + HB + c, rg);
+            tmem_wait_ld();
+            float v[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              float hv = __uint_as_float(rh[i]), gv = __uint_as_float(rg[i]);
+              if (p.bias) {
+                hv += __ldg(p.bias + n_tile * BN + c + i);
+                gv += __ldg(p.bias + n_tile * BN + HB + c + i);
+              }
+              v[i] = hv * gelu_erf_f(gv);
+            }
+            *reinterpret_cast<uint4*>(stage_out + lane * PITCH + c * 2) = pack8<T>(v);
+            *reinterpret_cast<uint4*>(stage_out + lane * PITCH + c * 2 + 16) = pack8<T>(v + 8);
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(&tmem_empty_bar[acc]);  // accumulator drained: the MMA warp may start the tile after next
+        __syncwarp();
+        // ---- phase 2: staging slab -> global, 16-byte lane-contiguous (+ prefetched residual)
+#pragma unroll
+        for (int u = 0; u < NCHUNK; ++u) {
+          const int id = u * 32 + lane;
+          const int rr = id / cpr, cc = id - rr * cpr;
+          if (id < total && m_warp + rr < p.M) {
+            uint4 sv = *reinterpret_cast<const uint4*>(stage_out + rr * PITCH + cc * 16);
+            if (res) {
+              float a[8], b[8];
+              unpack8<T>(sv, a);
+              unpack8<T>(rv[u], b);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) a[i] += b[i];
+              sv = pack8<T>(a);
+            }
+            *reinterpret_cast<uint4*>(out + (size_t)(m_warp + rr) * p.ldo + n_base + cc * 8) = sv;
+          }
+        }
+        __syncwarp();  // the slab is rewritten by the next tile's phase 1
+      } else {
+        // ---- scalar fallback (conv_out: N = 4): thread <-> row, direct stores
+        const int m = m_warp + lane;
+        mbar_wait(&tmem_full_bar[acc], acc_phase);
+        tc_fence_after();
+#pragma unroll 1
+        for (int c = 0; c < BN; c += 16) {
+          const int n = n_tile * BN + c;
+          if (n >= p.N) break;  // warp-uniform
+          uint32_t r[16];
+          tmem_ld16(taddr + c, r);
+          tmem_wait_ld();
+          if (m < p.M) {
+            for (int i = 0; i < 16; ++i) {
+              if (n + i < p.N) {
+                float x = __uint_as_float(r[i]);
+                if (p.bias) x += __ldg(p.bias + n + i);
+                if (res) x += DT<T>::to_f(res[(size_t)m * p.ldr + n + i]);
+                out[(size_t)m * p.ldo + n + i] = DT<T>::from_f(x);
+              }
             }
           }
         }
-      }
-    } else {
-      // accumulator columns [0, BN/2) hold h, [BN/2, BN) the gate of output columns n_tile*BN/2 + [0, BN/2)
-      constexpr int HB = BN / 2;
-      const int nout = p.N / 2;
-#pragma unroll 1
-      for (int c = 0; c < HB; c += 16) {
-        const int j = n_tile * HB + c;
-        if (j >= nout) break;
-        uint32_t rh[16], rg[16];
-        tmem_ld16(taddr + c, rh);
-        tmem_ld16(taddr + HB + c, rg);
-        tmem_wait_ld();
-        if (!row_ok) continue;
-        float v[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          float hv = __uint_as_float(rh[i]), gv = __uint_as_float(rg[i]);
-          if (p.bias) {
-            hv += __ldg(p.bias + n_tile * BN + c + i);
-            gv += __ldg(p.bias + n_tile * BN + HB + c + i);
-          }
-          v[i] = hv * gelu_erf_f(gv);
-        }
-#pragma unroll
-        for (int h = 0; h < 2; ++h)
-          if (j + h * 8 < nout)
-            *reinterpret_cast<uint4*>(out + (size_t)m * p.ldo + j + h * 8) = pack8<T>(v + h * 8);
+        tc_fence_before();
+        mbar_arrive(&tmem_empty_bar[acc]);
       }
     }
-    tc_fence_before();
   }
   __syncthreads();
   if (warp == 1) {

@@ -81,6 +81,7 @@ struct OpMeta {  // one entry per recorded step op (for rcdm_unet_profile)
   char kind[16];
   double flops;  // algorithmic FLOPs (2*MAC, no padding)
   double bytes;  // algorithmic HBM bytes (inputs + outputs once)
+  int m, n, k;   // GEMM-like ops: problem shape (0 otherwise)
 };
 
 struct TapInfo {

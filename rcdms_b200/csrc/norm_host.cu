@@ -71,20 +71,23 @@ bool ln_run(int dt, const void* x, void* o, const float* gp, const float* bp, in
             const float* pep, int rows_per_frame, int frames, cudaStream_t s) {
   const int maxv = (C / 8 + 31) / 32;
   if (maxv > 5 || C % 8) return false;
-  const int blocks = (nrows + 7) / 8;
-#define RCDM_LN(T, V)                                                                                           \
-  layernorm_kernel<T, V><<<blocks, 256, 0, s>>>(reinterpret_cast<const T*>(x), reinterpret_cast<T*>(o), gp, bp, \
-                                                nrows, C, eps, pep, rows_per_frame, frames)
+  // rows per warp: keep ~8 16-byte loads in flight per lane
+  const int rpw = maxv <= 1 ? 8 : maxv == 2 ? 4 : 2;
+  const int warps = (nrows + rpw - 1) / rpw;
+  const int blocks = (warps + 7) / 8;
+#define RCDM_LN(T, V, R)                                                                                           \
+  layernorm_kernel<T, V, R><<<blocks, 256, 0, s>>>(reinterpret_cast<const T*>(x), reinterpret_cast<T*>(o), gp, bp, \
+                                                   nrows, C, eps, pep, rows_per_frame, frames)
   if (dt == DT_F16) {
-    if (maxv <= 1) RCDM_LN(__half, 1);
-    else if (maxv == 2) RCDM_LN(__half, 2);
-    else if (maxv == 3) RCDM_LN(__half, 3);
-    else RCDM_LN(__half, 5);
+    if (maxv <= 1) RCDM_LN(__half, 1, 8);
+    else if (maxv == 2) RCDM_LN(__half, 2, 4);
+    else if (maxv == 3) RCDM_LN(__half, 3, 2);
+    else RCDM_LN(__half, 5, 2);
   } else {
-    if (maxv <= 1) RCDM_LN(__nv_bfloat16, 1);
-    else if (maxv == 2) RCDM_LN(__nv_bfloat16, 2);
-    else if (maxv == 3) RCDM_LN(__nv_bfloat16, 3);
-    else RCDM_LN(__nv_bfloat16, 5);
+    if (maxv <= 1) RCDM_LN(__nv_bfloat16, 1, 8);
+    else if (maxv == 2) RCDM_LN(__nv_bfloat16, 2, 4);
+    else if (maxv == 3) RCDM_LN(__nv_bfloat16, 3, 2);
+    else RCDM_LN(__nv_bfloat16, 5, 2);
   }
 #undef RCDM_LN
   g_launches++;

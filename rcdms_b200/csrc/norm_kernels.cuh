@@ -48,7 +48,23 @@ __global__ void gn_stats_kernel(const GnArgs a) {
     const int ld = c < a.C0 ? a.C0 : a.C1;
     const int cc = c < a.C0 ? c : c - a.C0;
     const size_t row0 = (size_t)sb * a.rows_per_stat + (size_t)chunk * a.rows_per_cta;
-    for (int r = rl; r < a.rows_per_cta; r += k) {
+    int r = rl;
+    for (; r + 3 * k < a.rows_per_cta; r += 4 * k) {  // 4 independent 16-byte loads in flight per thread
+      uint4 raw[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) raw[u] = __ldg(reinterpret_cast<const uint4*>(src + (row0 + r + u * k) * ld + cc));
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        float f[8];
+        unpack8<T>(raw[u], f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          s[i] += f[i];
+          ss[i] += f[i] * f[i];
+        }
+      }
+    }
+    for (; r < a.rows_per_cta; r += k) {
       float f[8];
       unpack8<T>(__ldg(reinterpret_cast<const uint4*>(src + (row0 + r) * ld + cc)), f);
 #pragma unroll
@@ -105,84 +121,134 @@ __global__ void gn_stats_kernel(const GnArgs a) {
   }
 }
 
-// one thread per 8-channel vector of one row; grid-stride over rows*vecs
+// one thread per 8-channel vector of one row; grid-stride over rows*vecs, 4 vectors in flight per thread
 template <typename T>
-__global__ void gn_apply_kernel(const GnArgs a, size_t total_vecs) {
+__global__ void __launch_bounds__(256)
+gn_apply_kernel(const GnArgs a, size_t total_vecs) {
   const int C = a.C0 + a.C1;
   const int vecs = C / 8;
   const int cpg = C / a.groups;
-  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total_vecs;
-       idx += (size_t)gridDim.x * blockDim.x) {
-    const size_t row = idx / vecs;
-    const int c = (int)(idx % vecs) * 8;
-    const int sb = (int)(row / a.rows_per_stat);
-    const T* src = reinterpret_cast<const T*>(c < a.C0 ? a.x0 : a.x1);
-    const int ld = c < a.C0 ? a.C0 : a.C1;
-    const int cc = c < a.C0 ? c : c - a.C0;
-    float f[8];
-    unpack8<T>(__ldg(reinterpret_cast<const uint4*>(src + row * ld + cc)), f);
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t base = (size_t)blockIdx.x * blockDim.x + threadIdx.x; base < total_vecs; base += 4 * stride) {
+    uint4 raw[4];
+    size_t row[4];
+    int c[4];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const float2 st = __ldg(&a.stats[(size_t)sb * a.groups + (c + i) / cpg]);
-      float y = (f[i] - st.x) * st.y * __ldg(a.gamma + c + i) + __ldg(a.beta + c + i);
-      f[i] = a.silu ? silu_f(y) : y;
+    for (int u = 0; u < 4; ++u) {
+      const size_t idx = base + u * stride;
+      if (idx < total_vecs) {
+        row[u] = idx / vecs;
+        c[u] = (int)(idx - row[u] * vecs) * 8;
+        const T* src = reinterpret_cast<const T*>(c[u] < a.C0 ? a.x0 : a.x1);
+        const int ld = c[u] < a.C0 ? a.C0 : a.C1;
+        const int cc = c[u] < a.C0 ? c[u] : c[u] - a.C0;
+        raw[u] = __ldg(reinterpret_cast<const uint4*>(src + row[u] * ld + cc));
+      }
     }
-    *reinterpret_cast<uint4*>(reinterpret_cast<T*>(a.out) + row * C + c) = pack8<T>(f);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const size_t idx = base + u * stride;
+      if (idx >= total_vecs) break;
+      const int sb = (int)(row[u] / a.rows_per_stat);
+      float f[8];
+      unpack8<T>(raw[u], f);
+      const float4 g0 = __ldg(reinterpret_cast<const float4*>(a.gamma + c[u]));
+      const float4 g1 = __ldg(reinterpret_cast<const float4*>(a.gamma + c[u] + 4));
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(a.beta + c[u]));
+      const float4 b1 = __ldg(reinterpret_cast<const float4*>(a.beta + c[u] + 4));
+      const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+      const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+      const float2* st_base = a.stats + (size_t)sb * a.groups;
+      const int g_lo = c[u] / cpg, g_hi = (c[u] + 7) / cpg;
+      const float2 st_lo = __ldg(st_base + g_lo);
+      const float2 st_hi = __ldg(st_base + g_hi);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int g = (c[u] + i) / cpg;
+        const float2 st = (g == g_lo) ? st_lo : ((g == g_hi) ? st_hi : __ldg(st_base + g));
+        const float y = (f[i] - st.x) * st.y * gg[i] + bb[i];
+        f[i] = a.silu ? silu_f(y) : y;
+      }
+      *reinterpret_cast<uint4*>(reinterpret_cast<T*>(a.out) + row[u] * C + c[u]) = pack8<T>(f);
+    }
   }
 }
 
-// LayerNorm over the last dim; one warp per row; C multiple of 8, C <= 32*8*MAXV.
+// LayerNorm over the last dim; one warp per ROWS consecutive rows (all loads issued before any reduction so each
+// lane keeps ROWS*MAXV 16-byte requests in flight); C multiple of 8, C <= 32*8*MAXV.
 // pe (optional): fp32 [frames, C]; frame of a row = (row / rows_per_frame) % frames.
-template <typename T, int MAXV>
-__global__ void layernorm_kernel(const T* __restrict__ x, T* __restrict__ out, const float* __restrict__ gamma,
-                                 const float* __restrict__ beta, int rows, int C, float eps,
-                                 const float* __restrict__ pe, int rows_per_frame, int frames) {
+template <typename T, int MAXV, int ROWS>
+__global__ void __launch_bounds__(256)
+layernorm_kernel(const T* __restrict__ x, T* __restrict__ out, const float* __restrict__ gamma,
+                 const float* __restrict__ beta, int rows, int C, float eps, const float* __restrict__ pe,
+                 int rows_per_frame, int frames) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
-  if (warp >= rows) return;
+  const int row0 = warp * ROWS;
+  if (row0 >= rows) return;
   const int vecs = C / 8;
-  float f[MAXV][8];
-  float sum = 0.f;
+  uint4 raw[ROWS][MAXV];
 #pragma unroll
-  for (int j = 0; j < MAXV; ++j) {
-    const int v = lane + j * 32;
-    if (v < vecs) {
-      unpack8<T>(__ldg(reinterpret_cast<const uint4*>(x + (size_t)warp * C + v * 8)), f[j]);
+  for (int r = 0; r < ROWS; ++r)
+#pragma unroll
+    for (int j = 0; j < MAXV; ++j) {
+      const int v = lane + j * 32;
+      if (v < vecs && row0 + r < rows)
+        raw[r][j] = __ldg(reinterpret_cast<const uint4*>(x + (size_t)(row0 + r) * C + v * 8));
+      else
+        raw[r][j] = make_uint4(0, 0, 0, 0);
+    }
+#pragma unroll
+  for (int r = 0; r < ROWS; ++r) {
+    if (row0 + r >= rows) break;  // warp-uniform
+    float f[MAXV][8];
+    float sum = 0.f;
+#pragma unroll
+    for (int j = 0; j < MAXV; ++j) {
+      unpack8<T>(raw[r][j], f[j]);
 #pragma unroll
       for (int i = 0; i < 8; ++i) sum += f[j][i];
     }
-  }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-  const float mean = sum / C;
-  float var = 0.f;
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float mean = sum / C;
+    float var = 0.f;
 #pragma unroll
-  for (int j = 0; j < MAXV; ++j) {
-    const int v = lane + j * 32;
-    if (v < vecs) {
+    for (int j = 0; j < MAXV; ++j) {
+      if (lane + j * 32 < vecs) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float d = f[j][i] - mean;
-        var += d * d;
+        for (int i = 0; i < 8; ++i) {
+          const float d = f[j][i] - mean;
+          var += d * d;
+        }
       }
     }
-  }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) var += __shfl_xor_sync(0xffffffffu, var, o);
-  const float rstd = rsqrtf(var / C + eps);
-  const float* pe_row = pe ? pe + (size_t)((warp / rows_per_frame) % frames) * C : nullptr;
+    for (int o = 16; o > 0; o >>= 1) var += __shfl_xor_sync(0xffffffffu, var, o);
+    const float rstd = rsqrtf(var / C + eps);
+    const int row = row0 + r;
+    const float* pe_row = pe ? pe + (size_t)((row / rows_per_frame) % frames) * C : nullptr;
 #pragma unroll
-  for (int j = 0; j < MAXV; ++j) {
-    const int v = lane + j * 32;
-    if (v < vecs) {
-      float y[8];
+    for (int j = 0; j < MAXV; ++j) {
+      const int v = lane + j * 32;
+      if (v < vecs) {
+        const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + v * 8));
+        const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + v * 8 + 4));
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + v * 8));
+        const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta + v * 8 + 4));
+        const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+        const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+        float y[8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int c = v * 8 + i;
-        y[i] = (f[j][i] - mean) * rstd * __ldg(gamma + c) + __ldg(beta + c);
-        if (pe_row) y[i] += __ldg(pe_row + c);
+        for (int i = 0; i < 8; ++i) y[i] = (f[j][i] - mean) * rstd * gg[i] + bb[i];
+        if (pe_row) {
+          const float4 p0 = __ldg(reinterpret_cast<const float4*>(pe_row + v * 8));
+          const float4 p1 = __ldg(reinterpret_cast<const float4*>(pe_row + v * 8 + 4));
+          y[0] += p0.x; y[1] += p0.y; y[2] += p0.z; y[3] += p0.w;
+          y[4] += p1.x; y[5] += p1.y; y[6] += p1.z; y[7] += p1.w;
+        }
+        *reinterpret_cast<uint4*>(out + (size_t)row * C + v * 8) = pack8<T>(y);
       }
-      *reinterpret_cast<uint4*>(out + (size_t)warp * C + v * 8) = pack8<T>(y);
     }
   }
 }

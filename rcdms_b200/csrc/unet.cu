@@ -423,7 +423,7 @@ struct Planner {
     if (!failed) err = m;
     failed = true;
   }
-  void push(Op op, const char* kind = "misc", double flops = 0.0, double bytes = 0.0) {
+  void push(Op op, const char* kind = "misc", double flops = 0.0, double bytes = 0.0, int pm = 0, int pn = 0, int pk = 0) {
     if (dry) return;
     ops->push_back(std::move(op));
     if (ops == &h->step_ops) {
@@ -432,6 +432,9 @@ struct Planner {
       strncpy(m.kind, kind, sizeof(m.kind) - 1);
       m.flops = flops;
       m.bytes = bytes;
+      m.m = pm;
+      m.n = pn;
+      m.k = pk;
       h->step_meta.push_back(m);
     }
   }
@@ -457,7 +460,7 @@ struct Planner {
       push([d](cudaStream_t s) {
         gemm_simple_launch(d, s);
         g_launches++;
-      }, kind, flops, bytes);
+      }, kind, flops, bytes, d.M, d.N, (int)k_alg);
       return;
     }
     GemmLaunch l;
@@ -466,7 +469,7 @@ struct Planner {
     push([l](cudaStream_t s) {
       gemm_launch(l, s);
       g_launches++;
-    }, kind, flops, bytes);
+    }, kind, flops, bytes, d.M, d.N, (int)k_alg);
   }
   // plain GEMM: out[M,N] = A[M,K] W^T (+bias)(+res)
   void linear(size_t a_off, int M, int K, const Mat& w, const Vec* bias, size_t out_off, int ldo, const size_t* res_off,
@@ -531,7 +534,7 @@ struct Planner {
     push([l](cudaStream_t s) {
       attn_launch(l, s);
       g_launches++;
-    }, kind, flops, bytes);
+    }, kind, flops, bytes, d.S_q, d.S_kv, d.d);
   }
   void tap(const std::string& name, const Act& a) {
     if (!h->taps_enabled) return;

@@ -281,13 +281,15 @@ class UNet3DConditionModel(nn.Module):
         cap = 4096
         ms, fl, by = (C.c_float * cap)(), (C.c_double * cap)(), (C.c_double * cap)()
         kinds = C.create_string_buffer(16 * cap)
+        dims = (C.c_int * (3 * cap))()
         n = C.c_int()
         _lib.check(_lib.lib().rcdm_unet_profile(
             self._handle, sample.data_ptr(), _lib.torch_dtype_id(sample.dtype), float(timestep), ctx.data_ptr(),
             _lib.torch_dtype_id(ctx.dtype), out.data_ptr(), _lib.torch_dtype_id(out.dtype), reps, cap, ms, fl, by,
-            kinds, C.byref(n), _lib.current_stream_ptr()))
+            kinds, dims, C.byref(n), _lib.current_stream_ptr()))
         raw = kinds.raw
-        return [dict(kind=raw[16 * i:16 * i + 16].split(b"\0")[0].decode(), ms=ms[i], flops=fl[i], bytes=by[i])
+        return [dict(kind=raw[16 * i:16 * i + 16].split(b"\0")[0].decode(), ms=ms[i], flops=fl[i], bytes=by[i],
+                     shape=(dims[3 * i], dims[3 * i + 1], dims[3 * i + 2]))
                 for i in range(n.value)]
 
     # ---- debugging aid ----------------------------------------------------------------------------------
