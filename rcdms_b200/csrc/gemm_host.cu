@@ -194,7 +194,7 @@ bool gemm_prepare(const GemmDesc& d, GemmLaunch* l, std::string* err) {
 }
 
 template <typename T, int BN> static void launch_one(const GemmLaunch& l, cudaStream_t s) {
-  gemm_tcgen05_kernel<T, BN><<<l.grid, 192, GemmCfg<BN>::SMEM_BYTES, s>>>(l.maps, l.p);
+  gemm_tcgen05_kernel<T, BN><<<l.grid, 320, GemmCfg<BN>::SMEM_BYTES, s>>>(l.maps, l.p);
 }
 
 void gemm_launch(const GemmLaunch& l, cudaStream_t s) {

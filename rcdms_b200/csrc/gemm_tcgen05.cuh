@@ -6,7 +6,7 @@
 //   warp 0     TMA producer  (one elected lane)  : HBM/L2 -> 128B-swizzled smem ring (5-6 stages), runs ahead
 //                                                  across tile boundaries
 //   warp 1     MMA issuer    (one elected lane)  : tcgen05.mma into one of TWO TMEM accumulators; owns TMEM alloc
-//   warps 2-5  epilogue                          : residual prefetch (coalesced, before the accumulator is ready)
+//   warps 2-9  epilogue (8 warps)                : residual prefetch (coalesced, before the accumulator is ready)
 //                                                  -> tcgen05.ld (+bias / GEGLU) -> 16-bit smem staging slab
 //                                                  -> 16-byte lane-contiguous global stores (+residual)
 // so the main loop of tile i+1 overlaps the epilogue of tile i.
@@ -60,8 +60,9 @@ template <int BN> struct GemmCfg {
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int OUT_PITCH = BN * 2 + 16;  // +16 B keeps 16-byte row-strided smem stores conflict-free
-  static constexpr int STAGING_BYTES = BM * OUT_PITCH;
+  // 8 epilogue warps, each with a private slab: 32 rows x (BN/2 cols * 2 B + 16 B pad)
+  static constexpr int SLAB_BYTES = 32 * (BN + 16);
+  static constexpr int STAGING_BYTES = 8 * SLAB_BYTES;
   static constexpr int ACC_STRIDE = BN <= 64 ? 64 : BN <= 128 ? 128 : 256;  // TMEM columns between the 2 accumulators
   static constexpr int TMEM_COLS = 2 * ACC_STRIDE;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
@@ -72,7 +73,7 @@ template <int BN> struct GemmCfg {
 // (n fastest, so CTAs running concurrently share A rows in L2).  The TMA producer runs ahead across tile
 // boundaries; two TMEM accumulators let the MMA warp start tile i+1 while the epilogue warps drain tile i.
 template <typename T, int BN>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(320, 1)
 gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
   using Cfg = GemmCfg<BN>;
   constexpr int STAGES = Cfg::STAGES;
@@ -104,7 +105,7 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
       }
       for (int i = 0; i < 2; ++i) {
         mbar_init(&tmem_full_bar[i], 1);
-        mbar_init(&tmem_empty_bar[i], 128);
+        mbar_init(&tmem_empty_bar[i], 256);
       }
       fence_mbar_init();
     }
@@ -199,123 +200,147 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
       }
     }
   } else {
-    // =================================== epilogue ===================================
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    // =================================== epilogue (8 warps) ===================================
+    // warp -> (q, hs): q = TMEM lane quarter (rows q*32..+31), hs = which half of the tile's output columns.
+    // phase 1 (thread <-> row):  TMEM -> registers, + bias (smem broadcast), GEGLU -> 16-bit private slab
+    // phase 2 (lane <-> fixed 16-byte column chunk, RPI rows per pass): slab (+ prefetched residual, packed
+    //          half2 add == fp32 add + one rounding) -> coalesced global stores
+    const int q = warp & 3;
+    const int hs = (warp - 2) >> 2;
     T* out = reinterpret_cast<T*>(p.out);
     const T* res = reinterpret_cast<const T*>(p.res);
     const bool vec_ok = (p.N % 8 == 0) && (p.ldo % 8 == 0) && (!p.res || p.ldr % 8 == 0);
-    constexpr int PITCH = Cfg::OUT_PITCH;
-    uint8_t* stage_out = staging + (size_t)q * 32 * PITCH;  // this warp's private 32-row slab
-    const int out_w = p.geglu ? BN / 2 : BN;                // output columns produced per tile
+    constexpr int OUT_W = BN;            // accumulator columns per tile
+    constexpr int HALF = BN / 2;         // accumulator columns per warp (plain) ...
+    constexpr int W_COLS = HALF;         // max output columns per warp (GEGLU uses HALF / 2)
+    constexpr int PITCH = W_COLS * 2 + 16;
+    uint8_t* slab = staging + (size_t)(warp - 2) * Cfg::SLAB_BYTES;
     const int n_total = p.geglu ? p.N / 2 : p.N;
-    constexpr int NCHUNK = BN / 8;                          // 16-byte chunks per staged row (max)
+    const int wcols = p.geglu ? HALF / 2 : HALF;   // output columns this warp produces per tile
+    const int CH = wcols / 8;                      // 16-byte chunks per slab row
+    const int RPI = 32 / CH;                       // rows per phase-2 pass
+    const int l_row = lane / CH, l_chunk = lane - l_row * CH;
+    const bool l_active = l_row < RPI;
+    constexpr int MAX_PASS = (BN == 160) ? 11 : 8;
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int n_tile = tile % p.num_n_tiles, m_tile = tile / p.num_n_tiles;
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       const uint32_t taddr = tmem_base + acc * Cfg::ACC_STRIDE + (uint32_t(q * 32) << 16);
-      const int n_base = n_tile * out_w;
       const int m_warp = m_tile * 128 + q * 32;
       if (vec_ok) {
-        int cpr = (n_total - n_base) / 8;  // valid 16-byte chunks per row in this tile
-        if (cpr > out_w / 8) cpr = out_w / 8;
-        const int total = 32 * cpr;
-        // ---- residual prefetch: coalesced, issued BEFORE waiting for the accumulator (hidden by the main loop)
-        uint4 rv[NCHUNK];
+        const int n_warp = n_tile * (p.geglu ? HALF : OUT_W) + hs * wcols;  // first output column of this warp
+        const bool chunk_ok = l_active && (n_warp + l_chunk * 8 < n_total);
+        // ---- residual prefetch (coalesced; issued before the accumulator is ready => hidden by the main loop)
+        uint4 rv[MAX_PASS];
         if (res) {
 #pragma unroll
-          for (int u = 0; u < NCHUNK; ++u) {
-            const int id = u * 32 + lane;
-            const int rr = id / cpr, cc = id - rr * cpr;
-            if (id < total && m_warp + rr < p.M)
-              rv[u] = *reinterpret_cast<const uint4*>(res + (size_t)(m_warp + rr) * p.ldr + n_base + cc * 8);
+          for (int u = 0; u < MAX_PASS; ++u) {
+            const int rr = u * RPI + l_row;
+            if (chunk_ok && rr < 32 && m_warp + rr < p.M)
+              rv[u] = *reinterpret_cast<const uint4*>(res + (size_t)(m_warp + rr) * p.ldr + n_warp + l_chunk * 8);
           }
         }
         mbar_wait(&tmem_full_bar[acc], acc_phase);
         tc_fence_after();
-        // ---- phase 1: TMEM -> registers (+bias, GEGLU) -> 16-bit staging slab (thread <-> row)
+        // ---- phase 1
         if (!p.geglu) {
 #pragma unroll 1
-          for (int c = 0; c < BN; c += 32) {
-            if (n_base + c >= n_total) break;  // warp-uniform
-            uint32_t r[32];
-            tmem_ld32(taddr + c, r);
-            tmem_wait_ld();
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              float v[8];
-#pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                v[i] = __uint_as_float(r[g * 8 + i]);
-                if (p.bias && n_base + c + g * 8 + i < n_total) v[i] += __ldg(p.bias + n_base + c + g * 8 + i);
-              }
-              if (c + g * 8 < BN) *reinterpret_cast<uint4*>(stage_out + lane * PITCH + (c + g * 8) * 2) = pack8<T>(v);
-            }
-          }
-        } else {
-          constexpr int HB = BN / 2;
-#pragma unroll 1
-          for (int c = 0; c < HB; c += 16) {
-            uint32_t rh[16], rg[16];
-            tmem_ld16(taddr + c, rh);
-            tmem_ld16(taddr + HB + c, rg);
+          for (int c = 0; c < HALF; c += 16) {
+            uint32_t r[16];
+            tmem_ld16(taddr + hs * HALF + c, r);
             tmem_wait_ld();
             float v[16];
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              float hv = __uint_as_float(rh[i]), gv = __uint_as_float(rg[i]);
-              if (p.bias) {
-                hv += __ldg(p.bias + n_tile * BN + c + i);
-                gv += __ldg(p.bias + n_tile * BN + HB + c + i);
+            for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+            if (p.bias) {  // warp-uniform addresses: broadcast 16-byte loads served by L1
+#pragma unroll
+              for (int g = 0; g < 4; ++g) {
+                const int n = n_warp + c + g * 4;
+                if (n + 4 <= n_total) {
+                  const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+                  v[g * 4] += b4.x;
+                  v[g * 4 + 1] += b4.y;
+                  v[g * 4 + 2] += b4.z;
+                  v[g * 4 + 3] += b4.w;
+                }
               }
-              v[i] = hv * gelu_erf_f(gv);
             }
-            *reinterpret_cast<uint4*>(stage_out + lane * PITCH + c * 2) = pack8<T>(v);
-            *reinterpret_cast<uint4*>(stage_out + lane * PITCH + c * 2 + 16) = pack8<T>(v + 8);
+            *reinterpret_cast<uint4*>(slab + lane * PITCH + c * 2) = pack8<T>(v);
+            *reinterpret_cast<uint4*>(slab + lane * PITCH + c * 2 + 16) = pack8<T>(v + 8);
+          }
+        } else {
+#pragma unroll 1
+          for (int c = 0; c < HALF / 2; c += 16) {
+            uint32_t rh[16], rg[16];
+            tmem_ld16(taddr + hs * (HALF / 2) + c, rh);
+            tmem_ld16(taddr + HALF + hs * (HALF / 2) + c, rg);
+            tmem_wait_ld();
+            float v[16], bh[16], bg[16];
+            if (p.bias) {  // packed GEGLU bias: tile-local [h (HALF) | gate (HALF)]
+              const float* bp = p.bias + n_tile * BN + hs * wcols + c;
+#pragma unroll
+              for (int g = 0; g < 4; ++g) {
+                const float4 h4 = __ldg(reinterpret_cast<const float4*>(bp + g * 4));
+                const float4 g4 = __ldg(reinterpret_cast<const float4*>(bp + HALF + g * 4));
+                bh[g * 4] = h4.x; bh[g * 4 + 1] = h4.y; bh[g * 4 + 2] = h4.z; bh[g * 4 + 3] = h4.w;
+                bg[g * 4] = g4.x; bg[g * 4 + 1] = g4.y; bg[g * 4 + 2] = g4.z; bg[g * 4 + 3] = g4.w;
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) bh[i] = bg[i] = 0.f;
+            }
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              v[i] = (__uint_as_float(rh[i]) + bh[i]) * gelu_erf_f(__uint_as_float(rg[i]) + bg[i]);
+            *reinterpret_cast<uint4*>(slab + lane * PITCH + c * 2) = pack8<T>(v);
+            *reinterpret_cast<uint4*>(slab + lane * PITCH + c * 2 + 16) = pack8<T>(v + 8);
           }
         }
         tc_fence_before();
-        mbar_arrive(&tmem_empty_bar[acc]);  // accumulator drained: the MMA warp may start the tile after next
+        mbar_arrive(&tmem_empty_bar[acc]);  // accumulator drained: the MMA warp may reuse it
         __syncwarp();
-        // ---- phase 2: staging slab -> global, 16-byte lane-contiguous (+ prefetched residual)
+        // ---- phase 2
+        if (chunk_ok) {
 #pragma unroll
-        for (int u = 0; u < NCHUNK; ++u) {
-          const int id = u * 32 + lane;
-          const int rr = id / cpr, cc = id - rr * cpr;
-          if (id < total && m_warp + rr < p.M) {
-            uint4 sv = *reinterpret_cast<const uint4*>(stage_out + rr * PITCH + cc * 16);
-            if (res) {
-              float a[8], b[8];
-              unpack8<T>(sv, a);
-              unpack8<T>(rv[u], b);
+          for (int u = 0; u < MAX_PASS; ++u) {
+            const int rr = u * RPI + l_row;
+            if (rr < 32 && m_warp + rr < p.M) {
+              uint4 sv = *reinterpret_cast<const uint4*>(slab + rr * PITCH + l_chunk * 16);
+              if (res) {
+                using T2 = typename DT<T>::T2;
+                T2* a2 = reinterpret_cast<T2*>(&sv);
+                const T2* b2 = reinterpret_cast<const T2*>(&rv[u]);
 #pragma unroll
-              for (int i = 0; i < 8; ++i) a[i] += b[i];
-              sv = pack8<T>(a);
+                for (int i = 0; i < 4; ++i) a2[i] = __hadd2(a2[i], b2[i]);
+              }
+              *reinterpret_cast<uint4*>(out + (size_t)(m_warp + rr) * p.ldo + n_warp + l_chunk * 8) = sv;
             }
-            *reinterpret_cast<uint4*>(out + (size_t)(m_warp + rr) * p.ldo + n_base + cc * 8) = sv;
           }
         }
-        __syncwarp();  // the slab is rewritten by the next tile's phase 1
+        __syncwarp();  // the slab is rewritten for the next tile
       } else {
-        // ---- scalar fallback (conv_out: N = 4): thread <-> row, direct stores
+        // ---- scalar fallback (conv_out: N = 4): thread <-> row, direct stores; only the hs == 0 warps work
         const int m = m_warp + lane;
         mbar_wait(&tmem_full_bar[acc], acc_phase);
         tc_fence_after();
+        if (hs == 0) {
 #pragma unroll 1
-        for (int c = 0; c < BN; c += 16) {
-          const int n = n_tile * BN + c;
-          if (n >= p.N) break;  // warp-uniform
-          uint32_t r[16];
-          tmem_ld16(taddr + c, r);
-          tmem_wait_ld();
-          if (m < p.M) {
-            for (int i = 0; i < 16; ++i) {
-              if (n + i < p.N) {
-                float x = __uint_as_float(r[i]);
-                if (p.bias) x += __ldg(p.bias + n + i);
-                if (res) x += DT<T>::to_f(res[(size_t)m * p.ldr + n + i]);
-                out[(size_t)m * p.ldo + n + i] = DT<T>::from_f(x);
+          for (int c = 0; c < BN; c += 16) {
+            const int n = n_tile * BN + c;
+            if (n >= p.N) break;  // warp-uniform
+            uint32_t r[16];
+            tmem_ld16(taddr + c, r);
+            tmem_wait_ld();
+            if (m < p.M) {
+              for (int i = 0; i < 16; ++i) {
+                if (n + i < p.N) {
+                  float x = __uint_as_float(r[i]);
+                  if (p.bias) x += __ldg(p.bias + n + i);
+                  if (res) x += DT<T>::to_f(res[(size_t)m * p.ldr + n + i]);
+                  out[(size_t)m * p.ldo + n + i] = DT<T>::from_f(x);
+                }
               }
             }
           }

@@ -59,10 +59,10 @@ void gn_configure(GnLaunch* l, int dt, const void* x0, int C0, const void* x1, i
 void gn_run(const GnLaunch& l, cudaStream_t s) {
   if (l.dt == DT_F16) {
     gn_stats_kernel<__half><<<l.grid, l.threads, l.smem, s>>>(l.a);
-    gn_apply_kernel<__half><<<l.agrid, 256, 0, s>>>(l.a, l.total_vecs);
+    gn_apply_kernel<__half><<<l.grid, l.threads, 0, s>>>(l.a);
   } else {
     gn_stats_kernel<__nv_bfloat16><<<l.grid, l.threads, l.smem, s>>>(l.a);
-    gn_apply_kernel<__nv_bfloat16><<<l.agrid, 256, 0, s>>>(l.a, l.total_vecs);
+    gn_apply_kernel<__nv_bfloat16><<<l.grid, l.threads, 0, s>>>(l.a);
   }
   g_launches += 2;
 }
