@@ -15,6 +15,8 @@
 // (motion_module.py:294-354): a 5x5 problem per (location, head) -> CUDA cores, one thread per (location, head),
 // q/k/v read once directly from the (b f hw)-ordered token matrix (no "(b f) d c -> (b d) f c" copies).
 #pragma once
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace rcdm {
@@ -145,84 +147,95 @@ flash_attn_kernel(const __grid_constant__ AttnMaps maps, const AttnParams p) {
     const float sc = p.scale_log2;
     float m_run = -INFINITY, l_run = 0.f;
     uint8_t* sP_row = sP + row * 16;
+    // Row sums for free: when the head dim leaves a spare padded column (d = 40 in a 48-wide tile), column d of
+    // every V row is set to 1 so that the P V MMA accumulates sum_j P_ij (of the ROUNDED probabilities) in TMEM.
+    const bool mma_sum = p.d < DPAD;
+    using T2 = typename DT<T>::T2;
 
-    // exponentiate one 128-column S row against `mref`, write P, return the row sum; tracks the raw max in `mx`
-    auto exp_pass = [&](float mref, int kv_valid, float& mx) -> float {
+    // exponentiate one 128-column S row against `mref`, write P; returns the row sum (0 when MS) and, in `pmax`,
+    // the largest probability written (as float)
+    auto exp_pass = [&](auto ms_tag, float mref, int kv_valid, float& pmax) -> float {
+      constexpr bool MS = decltype(ms_tag)::value;
       float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-      float x0 = -INFINITY, x1 = -INFINITY, x2 = -INFINITY, x3 = -INFINITY;
+      T2 mx2 = DT<T>::from_f2(0.f, 0.f);
       const bool full = kv_valid >= 128;
+      // software pipeline over four 32-column chunks: the TMEM load of chunk k+1 is in flight while chunk k is
+      // exponentiated (tcgen05.wait::ld only before the data is consumed)
+      uint32_t rbuf[2][32];
+      tmem_ld32(tmem_S + lane_sel, rbuf[0]);
+      tmem_wait_ld();
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        uint32_t* r = rbuf[k & 1];
+        if (k < 3) tmem_ld32(tmem_S + lane_sel + (k + 1) * 32, rbuf[(k + 1) & 1]);
+        const int c = k * 32;
+        if (!full) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (c + i >= kv_valid) r[i] = 0xff800000u;  // -inf: exp2 -> 0
+        }
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          float pv[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) pv[i] = exp2f(fmaf(__uint_as_float(r[g * 8 + i]), sc, -mref));
+          if constexpr (!MS) {
+            s0 += pv[0] + pv[4];
+            s1 += pv[1] + pv[5];
+            s2 += pv[2] + pv[6];
+            s3 += pv[3] + pv[7];
+          }
+          uint4 pk = pack8<T>(pv);
+          const T2* p2 = reinterpret_cast<const T2*>(&pk);
+          mx2 = __hmax2(mx2, __hmax2(__hmax2(p2[0], p2[1]), __hmax2(p2[2], p2[3])));
+          // P tile, K-major interleaved: [chunk = kv/8][row][8 elems]
+          *reinterpret_cast<uint4*>(sP_row + (c / 8 + g) * 2048) = pk;
+        }
+        if (k < 3) tmem_wait_ld();
+      }
+      const float2 mxf = DT<T>::to_f2(mx2);
+      pmax = fmaxf(mxf.x, mxf.y);
+      return (s0 + s1) + (s2 + s3);
+    };
+    auto row_max = [&](int kv_valid) -> float {
+      float x0 = -INFINITY, x1 = -INFINITY;
 #pragma unroll 1
       for (int c = 0; c < 128; c += 64) {
         uint32_t r[64];
         tmem_ld32(tmem_S + lane_sel + c, r);
         tmem_ld32(tmem_S + lane_sel + c + 32, r + 32);
         tmem_wait_ld();
-        if (!full) {
 #pragma unroll
-          for (int i = 0; i < 64; ++i)
-            if (c + i >= kv_valid) r[i] = 0xff800000u;  // -inf: exp2 -> 0, ignored by max
-        }
-#pragma unroll
-        for (int g = 0; g < 8; ++g) {
-          float pv[8];
-#pragma unroll
-          for (int i = 0; i < 8; i += 4) {
-            const float a0 = __uint_as_float(r[g * 8 + i]), a1 = __uint_as_float(r[g * 8 + i + 1]);
-            const float a2 = __uint_as_float(r[g * 8 + i + 2]), a3 = __uint_as_float(r[g * 8 + i + 3]);
-            x0 = fmaxf(x0, a0);
-            x1 = fmaxf(x1, a1);
-            x2 = fmaxf(x2, a2);
-            x3 = fmaxf(x3, a3);
-            pv[i] = exp2f(fmaf(a0, sc, -mref));
-            pv[i + 1] = exp2f(fmaf(a1, sc, -mref));
-            pv[i + 2] = exp2f(fmaf(a2, sc, -mref));
-            pv[i + 3] = exp2f(fmaf(a3, sc, -mref));
-            s0 += pv[i];
-            s1 += pv[i + 1];
-            s2 += pv[i + 2];
-            s3 += pv[i + 3];
-          }
-          // P tile, K-major interleaved: [chunk = kv/8][row][8 elems]
-          *reinterpret_cast<uint4*>(sP_row + (c / 8 + g) * 2048) = pack8<T>(pv);
+        for (int i = 0; i < 64; i += 2) {
+          if (c + i < kv_valid) x0 = fmaxf(x0, __uint_as_float(r[i]));
+          if (c + i + 1 < kv_valid) x1 = fmaxf(x1, __uint_as_float(r[i + 1]));
         }
       }
-      mx = fmaxf(fmaxf(x0, x1), fmaxf(x2, x3));
-      return (s0 + s1) + (s2 + s3);
+      return fmaxf(x0, x1);
+    };
+    auto run_pass = [&](float mref, int kv_valid, float& pmax) -> float {
+      return mma_sum ? exp_pass(std::true_type{}, mref, kv_valid, pmax) : exp_pass(std::false_type{}, mref, kv_valid, pmax);
     };
 
     for (int j = 0; j < n_kv; ++j) {
       mbar_wait(s_full, j & 1);
       tc_fence_after();
       const int kv_valid = min(128, p.S_kv - j * 128);
+      if (mma_sum)  // V tile j has landed (same barrier as K): set its "ones" column for this thread's kv row
+        *reinterpret_cast<T*>(sV + (j % KV) * Cfg::TILE_BYTES + (p.d / 8) * 2048 + row * 16) = DT<T>::from_f(1.0f);
+      float pmax;
       if (j == 0) {
-        float x0 = -INFINITY, x1 = -INFINITY;
-#pragma unroll 1
-        for (int c = 0; c < 128; c += 64) {
-          uint32_t r[64];
-          tmem_ld32(tmem_S + lane_sel + c, r);
-          tmem_ld32(tmem_S + lane_sel + c + 32, r + 32);
-          tmem_wait_ld();
-#pragma unroll
-          for (int i = 0; i < 64; i += 2) {
-            if (c + i < kv_valid) x0 = fmaxf(x0, __uint_as_float(r[i]));
-            if (c + i + 1 < kv_valid) x1 = fmaxf(x1, __uint_as_float(r[i + 1]));
-          }
-        }
-        m_run = fmaxf(x0, x1) * sc;
-        float mx;
-        l_run = exp_pass(m_run, kv_valid, mx);
+        m_run = row_max(kv_valid) * sc;
+        l_run = run_pass(m_run, kv_valid, pmax);
       } else {
-        float mx;
-        const float sum = exp_pass(m_run, kv_valid, mx);
-        const float m_tile = mx * sc;
-        if (__any_sync(0xffffffffu, m_tile > m_run + 8.0f)) {
-          // rare: re-reference this tile (and everything accumulated so far) to the new maximum
-          const float m_new = fmaxf(m_run, m_tile);
+        const float sum = run_pass(m_run, kv_valid, pmax);
+        if (__any_sync(0xffffffffu, pmax > 256.0f)) {
+          // rare: some probability left the comfortable 16-bit range -> re-reference to the new maximum
+          const float m_new = fmaxf(m_run, row_max(kv_valid) * sc);
           const float alpha = exp2f(m_run - m_new);
-          float dummy;
-          const float sum2 = exp_pass(m_new, kv_valid, dummy);
+          const float sum2 = run_pass(m_new, kv_valid, pmax);
 #pragma unroll 1
-          for (int c = 0; c < DPAD; c += 16) {
+          for (int c = 0; c < DPAD; c += 16) {  // rescales the row-sum column as well
             uint32_t r[16];
             tmem_ld16(tmem_O + lane_sel + c, r);
             tmem_wait_ld();
@@ -244,6 +257,12 @@ flash_attn_kernel(const __grid_constant__ AttnMaps maps, const AttnParams p) {
     // ---- normalise and store
     mbar_wait(o_done, 0);
     tc_fence_after();
+    if (mma_sum) {
+      uint32_t r[16];
+      tmem_ld16(tmem_O + lane_sel + (p.d & ~15), r);
+      tmem_wait_ld();
+      l_run = __uint_as_float(r[p.d & 15]);
+    }
     const float inv_l = 1.0f / l_run;
     const int qrow = q_tile * 128 + row;
     T* out = reinterpret_cast<T*>(p.out) + ((size_t)img * p.S_q + qrow) * p.ldo + head * p.d;

@@ -58,7 +58,21 @@ template <typename T> __device__ __forceinline__ uint4 pack8(const float* f) {
 }
 
 __device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
-__device__ __forceinline__ float gelu_erf_f(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+// erf-GELU (diffusers GEGLU uses F.gelu's exact/erf form).  erf via Abramowitz-Stegun 7.1.26
+// (|error| <= 1.5e-7, far below 16-bit output rounding): 1 RCP + 1 EX2 + ~10 FMA instead of libdevice erff.
+__device__ __forceinline__ float erf_as(float x) {
+  const float ax = fabsf(x);
+  const float t = __fdividef(1.0f, fmaf(0.3275911f, ax, 1.0f));
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  poly *= t;
+  const float e = exp2f(-1.4426950408889634f * ax * ax);
+  const float r = fmaf(-poly, e, 1.0f);
+  return copysignf(r, x);
+}
+__device__ __forceinline__ float gelu_erf_f(float x) { return 0.5f * x * (1.0f + erf_as(x * 0.70710678118654752f)); }
 
 // ------------------------------------------------------------------------------------------
 // shared-memory address / elect

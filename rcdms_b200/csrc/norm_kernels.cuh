@@ -104,12 +104,28 @@ __global__ void gn_stats_kernel(const GnArgs a) {
   __syncthreads();
   if (is_last) {
     __threadfence();
-    if (threadIdx.x < a.groups) {
+    // all threads participate: thread (part, g) sums chunks part, part+P, ... of group g (independent loads in
+    // flight), then thread g folds the P partial sums in a fixed order -> deterministic
+    double* red = reinterpret_cast<double*>(sm);  // [P][groups][2]; the per-channel sums are dead by now
+    const int P = blockDim.x / a.groups;
+    const int part = threadIdx.x / a.groups, g = threadIdx.x % a.groups;
+    __syncthreads();
+    if (part < P) {
       double gs = 0.0, gss = 0.0;
-      for (int ch = 0; ch < chunks; ++ch) {
-        float2 pz = __ldcg(&a.partial[((size_t)sb * chunks + ch) * a.groups + threadIdx.x]);
+      for (int ch = part; ch < chunks; ch += P) {
+        const float2 pz = __ldcg(&a.partial[((size_t)sb * chunks + ch) * a.groups + g]);
         gs += pz.x;
         gss += pz.y;
+      }
+      red[(part * a.groups + g) * 2] = gs;
+      red[(part * a.groups + g) * 2 + 1] = gss;
+    }
+    __syncthreads();
+    if (threadIdx.x < a.groups) {
+      double gs = 0.0, gss = 0.0;
+      for (int pp = 0; pp < P; ++pp) {
+        gs += red[(pp * a.groups + threadIdx.x) * 2];
+        gss += red[(pp * a.groups + threadIdx.x) * 2 + 1];
       }
       const double n = (double)a.rows_per_stat * cpg;
       const double mean = gs / n;

@@ -41,7 +41,30 @@ def gemm_case(M, N, K, bias, res, bn=0):
     print(f"gemm M{M} N{N} K{K} bias{int(bias)} res{int(res)} bn{bn}: {us:8.1f} us  {2 * M * N * K / us / 1e6:7.1f} TF/s", flush=True)
 
 
+def flash_case(b, h, sq, skv, d):
+    q = torch.randn((b, sq, h * d), device="cuda").to(dt)
+    kv = torch.randn((b, skv, 2 * h * d), device="cuda").to(dt)
+    out = torch.empty_like(q)
+    L = _lib.lib()
+    s = _lib.current_stream_ptr()
+    c = h * d
+
+    def run():
+        _lib.check(L.rcdm_flash_attn(1, q.data_ptr(), c, kv.data_ptr(), kv.data_ptr() + c * 2, 2 * c, out.data_ptr(), c,
+                                     b, h, sq, skv, d, 0, s))
+    us = timeit(run)
+    print(f"flash b{b} h{h} Sq{sq} Skv{skv} d{d}: {us:8.1f} us  {4 * b * h * sq * skv * d / us / 1e6:7.1f} TF/s "
+          f"({us * 1.965e3 * 148 / (b * h * ((sq + 127) // 128) * ((skv + 127) // 128)):.0f} cyc/tile/SM)", flush=True)
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "flash":
+        flash_case(10, 8, 4096, 4096, 40)
+        flash_case(10, 8, 1024, 1024, 80)
+        flash_case(10, 8, 256, 256, 160)
+        flash_case(10, 8, 4096, 85, 40)
+        flash_case(10, 8, 1024, 85, 80)
+        sys.exit(0)
     for bias, res in ((0, 0), (1, 0), (1, 1)):
         gemm_case(40960, 320, 320, bias, res)
     gemm_case(40960, 320, 320, 1, 1, bn=128)
