@@ -43,6 +43,10 @@ def _digest() -> str:
 
 
 def build(force: bool = False, verbose: bool = True) -> str:
+    global NVCC_FLAGS
+    extra = os.environ.get("RCDM_EXTRA_NVCC_FLAGS", "").split()
+    if extra:
+        NVCC_FLAGS = [f for f in NVCC_FLAGS if f not in extra] + extra
     os.makedirs(OUT_DIR, exist_ok=True)
     stamp = os.path.join(OUT_DIR, "build.sha256")
     dig = _digest()

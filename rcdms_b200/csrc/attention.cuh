@@ -3,7 +3,7 @@
 // flash_attn_kernel: softmax(scale * Q K^T) V without materialising the scores (the reference writes an
 // (80, 4096, 4096) score tensor per 64x64 layer: attention.py:170-199).  One CTA = 128 queries of one
 // (image, head).  Both GEMMs run on tcgen05 with accumulators in TMEM:
-//     S = Q K_j^T   (128 x 128 fp32, TMEM cols [0,128))      O += P_j V_j   (128 x DPAD fp32, TMEM cols [128, ...))
+//     S_j = Q K_j^T (128 x 64 fp32, two TMEM buffers)        O += P_j V_j   (128 x DPAD fp32, TMEM cols [128, ...))
 // Q/K/V head slices are fetched straight out of the fused projection output [rows, ld] by 5-D TMA maps
 // (8 elems, row, 16-byte chunk, head, image) into the no-swizzle "interleaved" UMMA layout
 // [chunk][row][8 elems]; out-of-range chunks / rows are zero-filled by TMA, which pads head_dim 40 -> 48 and
@@ -16,6 +16,12 @@
 // q/k/v read once directly from the (b f hw)-ordered token matrix (no "(b f) d c -> (b d) f c" copies).
 #pragma once
 #include <type_traits>
+
+// Compile-time experiment switch for bottleneck analysis (never set in a product build):
+//   1 = no exp2 (FFMA result used), 2 = no TMEM loads of S, 3 = no P stores to smem, 4 = no P V MMAs
+#ifndef RCDM_ATTN_EXPERIMENT
+#define RCDM_ATTN_EXPERIMENT 0
+#endif
 
 #include "common.cuh"
 
@@ -35,37 +41,44 @@ struct AttnMaps {
 };
 
 template <int DPAD> struct AttnCfg {
-  static constexpr int NCH = DPAD / 8;               // 16-byte chunks per head row
-  static constexpr int TILE_BYTES = NCH * 128 * 16;  // one 128-row operand tile
-  static constexpr int KV_STAGES = DPAD <= 80 ? 2 : 1;
-  static constexpr int P_BYTES = 16 * 128 * 16;
-  static constexpr int TMEM_COLS = (128 + DPAD) <= 256 ? 256 : 512;
-  static constexpr int SMEM_BYTES = TILE_BYTES * (1 + 2 * KV_STAGES) + P_BYTES + 1024 + 256;
+  static constexpr int BLOCK_M = 128, BLOCK_N = 64;
+  static constexpr int NCH = DPAD / 8;                   // 16-byte chunks per head row
+  static constexpr int Q_BYTES = NCH * BLOCK_M * 16;     // Q tile
+  static constexpr int KV_BYTES = NCH * BLOCK_N * 16;    // one K (or V) tile
+  static constexpr int KV_STAGES = DPAD <= 48 ? 3 : 2;
+  static constexpr int P_BYTES = (BLOCK_N / 8) * BLOCK_M * 16;  // one P buffer (two are kept)
+  static constexpr int TMEM_COLS = (2 * BLOCK_N + DPAD) <= 256 ? 256 : 512;
+  static constexpr int SMEM_BYTES = Q_BYTES + 2 * KV_STAGES * KV_BYTES + 2 * P_BYTES + 1024 + 256;
 };
 
+// Software pipeline (per CTA): S and P are double-buffered, so the tensor core computes S_{j+1} = Q K_{j+1}^T while
+// the softmax warps exponentiate S_j, and O += P_j V_j runs while they work on S_{j+1}; the softmax warps never
+// wait for an MMA in steady state.  TMEM: S0 | S1 (64 cols each) | O (DPAD cols).
 template <typename T, int DPAD>
 __global__ void __launch_bounds__(160, AttnCfg<DPAD>::SMEM_BYTES <= 113 * 1024 ? 2 : 1)
 flash_attn_kernel(const __grid_constant__ AttnMaps maps, const AttnParams p) {
   using Cfg = AttnCfg<DPAD>;
   constexpr int KV = Cfg::KV_STAGES;
+  constexpr int BN = Cfg::BLOCK_N;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;
-  uint8_t* sK = sQ + Cfg::TILE_BYTES;
-  uint8_t* sV = sK + KV * Cfg::TILE_BYTES;
-  uint8_t* sP = sV + KV * Cfg::TILE_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + Cfg::P_BYTES);
+  uint8_t* sK = sQ + Cfg::Q_BYTES;
+  uint8_t* sV = sK + KV * Cfg::KV_BYTES;
+  uint8_t* sP = sV + KV * Cfg::KV_BYTES;  // [2][P_BYTES]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * Cfg::P_BYTES);
   uint64_t* q_full = bars;
   uint64_t* kv_full = bars + 1;        // [KV]
   uint64_t* kv_empty = bars + 1 + KV;  // [KV]
-  uint64_t* s_full = bars + 1 + 2 * KV;
-  uint64_t* p_full = s_full + 1;
-  uint64_t* o_done = s_full + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_full + 3);
+  uint64_t* s_full = bars + 1 + 2 * KV;  // [2]
+  uint64_t* p_full = s_full + 2;         // [2]
+  uint64_t* pv_done = s_full + 4;
+  uint64_t* o_done = s_full + 5;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_full + 6);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q_tile = blockIdx.x, head = blockIdx.y, img = blockIdx.z;
-  const int n_kv = (p.S_kv + 127) / 128;
+  const int n_kv = (p.S_kv + BN - 1) / BN;
 
   if (warp == 4) {
     if (lane == 0) {
@@ -74,8 +87,11 @@ flash_attn_kernel(const __grid_constant__ AttnMaps maps, const AttnParams p) {
         mbar_init(&kv_full[i], 1);
         mbar_init(&kv_empty[i], 1);
       }
-      mbar_init(s_full, 1);
-      mbar_init(p_full, 128);
+      for (int i = 0; i < 2; ++i) {
+        mbar_init(&s_full[i], 1);
+        mbar_init(&p_full[i], 128);
+      }
+      mbar_init(pv_done, 1);
       mbar_init(o_done, 1);
       fence_mbar_init();
       tma_prefetch_desc(&maps.q);
@@ -89,85 +105,97 @@ flash_attn_kernel(const __grid_constant__ AttnMaps maps, const AttnParams p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_S = tmem_base, tmem_O = tmem_base + 128;
+  const uint32_t tmem_O = tmem_base + 2 * BN;
 
   if (warp == 4) {
     if (elect_one()) {
-      constexpr uint32_t idesc_qk = umma_idesc_f16(DT<T>::umma_fmt, 128, 128, 0, 0);
+      constexpr uint32_t idesc_qk = umma_idesc_f16(DT<T>::umma_fmt, 128, BN, 0, 0);
       constexpr uint32_t idesc_pv = umma_idesc_f16(DT<T>::umma_fmt, 128, DPAD, 0, 1);  // B (=V) is MN-major
-      mbar_expect_tx(q_full, Cfg::TILE_BYTES);
-      tma_load_5d(sQ, &maps.q, q_full, 0, q_tile * 128, 0, head, img);
-      const uint32_t q_addr = smem_u32(sQ), p_addr = smem_u32(sP);
-      for (int j = 0; j < n_kv; ++j) {
-        // ---- producer: keep the K/V ring full
-        const int t_first = (j == 0) ? 0 : j + KV - 1, t_last = j + KV - 1;
-        for (int t = t_first; t <= t_last; ++t) {
-          if (t >= n_kv) break;
-          const int s = t % KV;
-          if (t >= KV) mbar_wait(&kv_empty[s], ((t / KV) - 1) & 1);
-          mbar_expect_tx(&kv_full[s], 2 * Cfg::TILE_BYTES);
-          tma_load_5d(sK + s * Cfg::TILE_BYTES, &maps.k, &kv_full[s], 0, t * 128, 0, head, img);
-          tma_load_5d(sV + s * Cfg::TILE_BYTES, &maps.v, &kv_full[s], 0, t * 128, 0, head, img);
-        }
-        const int s = j % KV;
-        if (j == 0) mbar_wait(q_full, 0);
-        mbar_wait(&kv_full[s], (j / KV) & 1);
+      const uint32_t q_addr = smem_u32(sQ);
+      auto load_kv = [&](int t) {
+        const int s = t % KV;
+        mbar_expect_tx(&kv_full[s], 2 * Cfg::KV_BYTES);
+        tma_load_5d(sK + s * Cfg::KV_BYTES, &maps.k, &kv_full[s], 0, t * BN, 0, head, img);
+        tma_load_5d(sV + s * Cfg::KV_BYTES, &maps.v, &kv_full[s], 0, t * BN, 0, head, img);
+      };
+      // S_t = Q K_t^T : A, B K-major interleaved [chunk][row][8]; one K=16 step = 2 chunks
+      auto mma_qk = [&](int t) {
+        const int s = t % KV;
+        mbar_wait(&kv_full[s], (t / KV) & 1);
         tc_fence_after();
-        // ---- S = Q K^T : A, B K-major interleaved; +2 chunks (= 4096 B) per K=16 step
-        const uint32_t k_addr = smem_u32(sK + s * Cfg::TILE_BYTES);
+        const uint32_t k_addr = smem_u32(sK + s * Cfg::KV_BYTES);
 #pragma unroll
         for (int ks = 0; ks < DPAD / 16; ++ks) {
-          const uint64_t ad = umma_smem_desc(q_addr + ks * 4096, 2048, 128, UMMA_SWIZZLE_NONE);
-          const uint64_t bd = umma_smem_desc(k_addr + ks * 4096, 2048, 128, UMMA_SWIZZLE_NONE);
-          umma_f16_ss(tmem_S, ad, bd, idesc_qk, ks != 0);
+          const uint64_t ad = umma_smem_desc(q_addr + ks * 2 * (128 * 16), 128 * 16, 128, UMMA_SWIZZLE_NONE);
+          const uint64_t bd = umma_smem_desc(k_addr + ks * 2 * (BN * 16), BN * 16, 128, UMMA_SWIZZLE_NONE);
+          umma_f16_ss(tmem_base + (t & 1) * BN, ad, bd, idesc_qk, ks != 0);
         }
-        umma_commit(s_full);
-        // ---- O += P V : A = P K-major interleaved, B = V MN-major interleaved (+16 kv rows = 256 B per step)
-        mbar_wait(p_full, j & 1);
+        umma_commit(&s_full[t & 1]);
+      };
+      mbar_expect_tx(q_full, Cfg::Q_BYTES);
+      tma_load_5d(sQ, &maps.q, q_full, 0, q_tile * 128, 0, head, img);
+      for (int t = 0; t < KV && t < n_kv; ++t) load_kv(t);
+      mbar_wait(q_full, 0);
+      mma_qk(0);
+      for (int j = 0; j < n_kv; ++j) {
+        if (j + 1 < n_kv) mma_qk(j + 1);  // overlaps the softmax of tile j
+        // ---- O += P_j V_j : A = P K-major interleaved, B = V MN-major interleaved (16 kv rows = 256 B per step)
+        mbar_wait(&p_full[j & 1], (j >> 1) & 1);
         tc_fence_after();
-        const uint32_t v_addr = smem_u32(sV + s * Cfg::TILE_BYTES);
+        const int s = j % KV;
+        const uint32_t p_addr = smem_u32(sP + (j & 1) * Cfg::P_BYTES);
+        const uint32_t v_addr = smem_u32(sV + s * Cfg::KV_BYTES);
 #pragma unroll
-        for (int ks = 0; ks < 8; ++ks) {
+        for (int ks = 0; ks < (RCDM_ATTN_EXPERIMENT == 4 ? 1 : BN / 16); ++ks) {
           const uint64_t ad = umma_smem_desc(p_addr + ks * 4096, 2048, 128, UMMA_SWIZZLE_NONE);
-          const uint64_t bd = umma_smem_desc(v_addr + ks * 256, 128, 2048, UMMA_SWIZZLE_NONE);
+          const uint64_t bd = umma_smem_desc(v_addr + ks * 256, 128, BN * 16, UMMA_SWIZZLE_NONE);
           umma_f16_ss(tmem_O, ad, bd, idesc_pv, (j | ks) != 0);
         }
         umma_commit(&kv_empty[s]);
+        umma_commit(pv_done);
         if (j == n_kv - 1) umma_commit(o_done);
+        if (j + KV < n_kv) {  // refill the stage just consumed
+          mbar_wait(&kv_empty[s], (j / KV) & 1);
+          load_kv(j + KV);
+        }
       }
     }
   } else {
     // =================================== softmax warps ===================================
     // One thread per query row.  Lazy online softmax: the first KV tile fixes the reference maximum m_run with a
-    // separate max pass; every later tile is ONE pass that exponentiates against m_run while tracking the tile
-    // maximum, and only if some row's tile maximum exceeds m_run by more than 2^8 (P would approach the 16-bit
-    // range) does the warp fall back to re-exponentiating the tile and rescaling O in TMEM.
+    // separate max pass; every later tile is ONE pass that exponentiates against m_run while tracking the largest
+    // probability, and only if some probability exceeds 2^8 does the warp re-reference the tile and rescale O.
     const int row = warp * 32 + lane;
     const uint32_t lane_sel = uint32_t(warp * 32) << 16;
     const float sc = p.scale_log2;
     float m_run = -INFINITY, l_run = 0.f;
-    uint8_t* sP_row = sP + row * 16;
     // Row sums for free: when the head dim leaves a spare padded column (d = 40 in a 48-wide tile), column d of
     // every V row is set to 1 so that the P V MMA accumulates sum_j P_ij (of the ROUNDED probabilities) in TMEM.
     const bool mma_sum = p.d < DPAD;
     using T2 = typename DT<T>::T2;
 
-    // exponentiate one 128-column S row against `mref`, write P; returns the row sum (0 when MS) and, in `pmax`,
-    // the largest probability written (as float)
-    auto exp_pass = [&](auto ms_tag, float mref, int kv_valid, float& pmax) -> float {
+    // exponentiate one 64-column S row against `mref`, write P; returns the row sum (0 when MS) and, in `pmax`,
+    // the largest probability written
+    auto exp_pass = [&](auto ms_tag, uint32_t tS, uint8_t* sP_row, float mref, int kv_valid, float& pmax) -> float {
       constexpr bool MS = decltype(ms_tag)::value;
       float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
       T2 mx2 = DT<T>::from_f2(0.f, 0.f);
-      const bool full = kv_valid >= 128;
-      // software pipeline over four 32-column chunks: the TMEM load of chunk k+1 is in flight while chunk k is
-      // exponentiated (tcgen05.wait::ld only before the data is consumed)
+      const bool full = kv_valid >= BN;
+      // two 32-column chunks; the TMEM load of chunk 1 is in flight while chunk 0 is exponentiated
       uint32_t rbuf[2][32];
-      tmem_ld32(tmem_S + lane_sel, rbuf[0]);
-      tmem_wait_ld();
+#if RCDM_ATTN_EXPERIMENT == 2
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        uint32_t* r = rbuf[k & 1];
-        if (k < 3) tmem_ld32(tmem_S + lane_sel + (k + 1) * 32, rbuf[(k + 1) & 1]);
+      for (int i = 0; i < 32; ++i) rbuf[0][i] = rbuf[1][i] = __float_as_uint(0.01f * (float)(i + lane));
+#else
+      tmem_ld32(tS + lane_sel, rbuf[0]);
+      tmem_wait_ld();
+#endif
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        uint32_t* r = rbuf[k];
+#if RCDM_ATTN_EXPERIMENT != 2
+        if (k == 0) tmem_ld32(tS + lane_sel + 32, rbuf[1]);
+#endif
         const int c = k * 32;
         if (!full) {
 #pragma unroll
@@ -178,7 +206,13 @@ flash_attn_kernel(const __grid_constant__ AttnMaps maps, const AttnParams p) {
         for (int g = 0; g < 4; ++g) {
           float pv[8];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) pv[i] = exp2f(fmaf(__uint_as_float(r[g * 8 + i]), sc, -mref));
+          for (int i = 0; i < 8; ++i) {
+#if RCDM_ATTN_EXPERIMENT == 1
+            pv[i] = fmaf(__uint_as_float(r[g * 8 + i]), sc, -mref);
+#else
+            pv[i] = exp2f(fmaf(__uint_as_float(r[g * 8 + i]), sc, -mref));
+#endif
+          }
           if constexpr (!MS) {
             s0 += pv[0] + pv[4];
             s1 += pv[1] + pv[5];
@@ -189,53 +223,59 @@ flash_attn_kernel(const __grid_constant__ AttnMaps maps, const AttnParams p) {
           const T2* p2 = reinterpret_cast<const T2*>(&pk);
           mx2 = __hmax2(mx2, __hmax2(__hmax2(p2[0], p2[1]), __hmax2(p2[2], p2[3])));
           // P tile, K-major interleaved: [chunk = kv/8][row][8 elems]
+#if RCDM_ATTN_EXPERIMENT != 3
           *reinterpret_cast<uint4*>(sP_row + (c / 8 + g) * 2048) = pk;
+#endif
         }
-        if (k < 3) tmem_wait_ld();
+#if RCDM_ATTN_EXPERIMENT != 2
+        if (k == 0) tmem_wait_ld();
+#endif
       }
       const float2 mxf = DT<T>::to_f2(mx2);
       pmax = fmaxf(mxf.x, mxf.y);
       return (s0 + s1) + (s2 + s3);
     };
-    auto row_max = [&](int kv_valid) -> float {
+    auto row_max = [&](uint32_t tS, int kv_valid) -> float {
       float x0 = -INFINITY, x1 = -INFINITY;
-#pragma unroll 1
-      for (int c = 0; c < 128; c += 64) {
-        uint32_t r[64];
-        tmem_ld32(tmem_S + lane_sel + c, r);
-        tmem_ld32(tmem_S + lane_sel + c + 32, r + 32);
-        tmem_wait_ld();
+      uint32_t r[64];
+      tmem_ld32(tS + lane_sel, r);
+      tmem_ld32(tS + lane_sel + 32, r + 32);
+      tmem_wait_ld();
 #pragma unroll
-        for (int i = 0; i < 64; i += 2) {
-          if (c + i < kv_valid) x0 = fmaxf(x0, __uint_as_float(r[i]));
-          if (c + i + 1 < kv_valid) x1 = fmaxf(x1, __uint_as_float(r[i + 1]));
-        }
+      for (int i = 0; i < 64; i += 2) {
+        if (i < kv_valid) x0 = fmaxf(x0, __uint_as_float(r[i]));
+        if (i + 1 < kv_valid) x1 = fmaxf(x1, __uint_as_float(r[i + 1]));
       }
       return fmaxf(x0, x1);
     };
-    auto run_pass = [&](float mref, int kv_valid, float& pmax) -> float {
-      return mma_sum ? exp_pass(std::true_type{}, mref, kv_valid, pmax) : exp_pass(std::false_type{}, mref, kv_valid, pmax);
+    auto run_pass = [&](uint32_t tS, uint8_t* sP_row, float mref, int kv_valid, float& pmax) -> float {
+      return mma_sum ? exp_pass(std::true_type{}, tS, sP_row, mref, kv_valid, pmax)
+                     : exp_pass(std::false_type{}, tS, sP_row, mref, kv_valid, pmax);
     };
 
     for (int j = 0; j < n_kv; ++j) {
-      mbar_wait(s_full, j & 1);
+      mbar_wait(&s_full[j & 1], (j >> 1) & 1);
       tc_fence_after();
-      const int kv_valid = min(128, p.S_kv - j * 128);
-      if (mma_sum)  // V tile j has landed (same barrier as K): set its "ones" column for this thread's kv row
-        *reinterpret_cast<T*>(sV + (j % KV) * Cfg::TILE_BYTES + (p.d / 8) * 2048 + row * 16) = DT<T>::from_f(1.0f);
+      const uint32_t tS = tmem_base + (j & 1) * BN;
+      uint8_t* sP_row = sP + (j & 1) * Cfg::P_BYTES + row * 16;
+      const int kv_valid = min(BN, p.S_kv - j * BN);
+      if (mma_sum && row < BN)  // V tile j has landed (same barrier as K_j): set its "ones" column
+        *reinterpret_cast<T*>(sV + (j % KV) * Cfg::KV_BYTES + (p.d / 8) * (BN * 16) + row * 16) = DT<T>::from_f(1.0f);
       float pmax;
       if (j == 0) {
-        m_run = row_max(kv_valid) * sc;
-        l_run = run_pass(m_run, kv_valid, pmax);
+        m_run = row_max(tS, kv_valid) * sc;
+        l_run = run_pass(tS, sP_row, m_run, kv_valid, pmax);
       } else {
-        const float sum = run_pass(m_run, kv_valid, pmax);
+        const float sum = run_pass(tS, sP_row, m_run, kv_valid, pmax);
         if (__any_sync(0xffffffffu, pmax > 256.0f)) {
           // rare: some probability left the comfortable 16-bit range -> re-reference to the new maximum
-          const float m_new = fmaxf(m_run, row_max(kv_valid) * sc);
+          const float m_new = fmaxf(m_run, row_max(tS, kv_valid) * sc);
           const float alpha = exp2f(m_run - m_new);
-          const float sum2 = run_pass(m_new, kv_valid, pmax);
+          const float sum2 = run_pass(tS, sP_row, m_new, kv_valid, pmax);
+          mbar_wait(pv_done, (j - 1) & 1);  // O (incl. the row-sum column) must be quiescent: P_{j-1} V_{j-1} done
+          tc_fence_after();
 #pragma unroll 1
-          for (int c = 0; c < DPAD; c += 16) {  // rescales the row-sum column as well
+          for (int c = 0; c < DPAD; c += 16) {
             uint32_t r[16];
             tmem_ld16(tmem_O + lane_sel + c, r);
             tmem_wait_ld();
@@ -252,7 +292,7 @@ flash_attn_kernel(const __grid_constant__ AttnMaps maps, const AttnParams p) {
       }
       fence_proxy_async_smem();
       tc_fence_before();
-      mbar_arrive(p_full);
+      mbar_arrive(&p_full[j & 1]);
     }
     // ---- normalise and store
     mbar_wait(o_done, 0);

@@ -13,12 +13,12 @@ static int pick_dpad(int d) {
   return -1;
 }
 
-// (8 elems, rows-per-image, 16-byte chunks of the head, heads, images); box (8, 128, dpad/8, 1, 1)
+// (8 elems, rows-per-image, 16-byte chunks of the head, heads, images); box (8, 128 | 64, dpad/8, 1, 1)
 static bool head_map(CUtensorMap* m, const void* base, int ld, int S, int heads, int d, int batch, int dpad,
-                     std::string* err) {
+                     int box_rows, std::string* err) {
   uint64_t dims[5] = {8, (uint64_t)S, (uint64_t)d / 8, (uint64_t)heads, (uint64_t)batch};
   uint64_t str[4] = {(uint64_t)ld * 2, 16, (uint64_t)d * 2, (uint64_t)S * ld * 2};
-  uint32_t box[5] = {8, 128, (uint32_t)dpad / 8, 1, 1};
+  uint32_t box[5] = {8, (uint32_t)box_rows, (uint32_t)dpad / 8, 1, 1};
   return encode_tmap(m, base, 5, dims, str, box, false, err);
 }
 
@@ -31,9 +31,9 @@ bool attn_prepare(const AttnDesc& d, AttnLaunch* l, std::string* err) {
   memset(&l->maps, 0, sizeof l->maps);
   l->dpad = dpad;
   l->dt = d.dt;
-  if (!head_map(&l->maps.q, d.q, d.ldq, d.S_q, d.heads, d.d, d.batch, dpad, err)) return false;
-  if (!head_map(&l->maps.k, d.k, d.ldkv, d.S_kv, d.heads, d.d, d.batch, dpad, err)) return false;
-  if (!head_map(&l->maps.v, d.v, d.ldkv, d.S_kv, d.heads, d.d, d.batch, dpad, err)) return false;
+  if (!head_map(&l->maps.q, d.q, d.ldq, d.S_q, d.heads, d.d, d.batch, dpad, 128, err)) return false;
+  if (!head_map(&l->maps.k, d.k, d.ldkv, d.S_kv, d.heads, d.d, d.batch, dpad, 64, err)) return false;
+  if (!head_map(&l->maps.v, d.v, d.ldkv, d.S_kv, d.heads, d.d, d.batch, dpad, 64, err)) return false;
   l->p.S_q = d.S_q;
   l->p.S_kv = d.S_kv;
   l->p.heads = d.heads;

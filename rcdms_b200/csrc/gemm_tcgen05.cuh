@@ -65,7 +65,9 @@ template <int BN> struct GemmCfg {
   static constexpr int STAGING_BYTES = 8 * SLAB_BYTES;
   static constexpr int ACC_STRIDE = BN <= 64 ? 64 : BN <= 128 ? 128 : 256;  // TMEM columns between the 2 accumulators
   static constexpr int TMEM_COLS = 2 * ACC_STRIDE;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int BIAS_BYTES = 2 * BN * 4;  // two buffers (tile parity) of BN fp32 bias values
+  static constexpr int SMEM_BYTES =
+      STAGES * STAGE_BYTES + STAGING_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + BIAS_BYTES;
   static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB per-CTA shared memory limit");
 };
 
@@ -88,6 +90,7 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
   uint64_t* tmem_full_bar = bars + 2 * STAGES;       // [2]
   uint64_t* tmem_empty_bar = bars + 2 * STAGES + 2;  // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  float* bias_sm = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);  // [2][BN]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -244,6 +247,23 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
         }
         mbar_wait(&tmem_full_bar[acc], acc_phase);
         tc_fence_after();
+        // ---- bias slice of this warp's column half -> smem[tile parity].  The four warps sharing `hs` write
+        // identical values (benign); filling AFTER the wait makes the parity double-buffer race-free (tile i+2
+        // cannot become ready before every thread finished phase 1 of tile i).
+        float* bsm = bias_sm + (it & 1) * BN + hs * HALF;
+        if (p.bias) {
+          if (!p.geglu) {
+            for (int i = lane; i < HALF; i += 32) bsm[i] = (n_warp + i < n_total) ? __ldg(p.bias + n_warp + i) : 0.f;
+          } else {  // packed GEGLU bias: tile-local [h (HALF) | gate (HALF)]; h/gate columns hs*wcols..+wcols
+            for (int i = lane; i < wcols; i += 32) {
+              bsm[i] = __ldg(p.bias + n_tile * BN + hs * wcols + i);
+              bsm[wcols + i] = __ldg(p.bias + n_tile * BN + HALF + hs * wcols + i);
+            }
+          }
+        } else {
+          for (int i = lane; i < HALF; i += 32) bsm[i] = 0.f;
+        }
+        __syncwarp();
         // ---- phase 1
         if (!p.geglu) {
 #pragma unroll 1
@@ -253,19 +273,12 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
             tmem_wait_ld();
             float v[16];
 #pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-            if (p.bias) {  // warp-uniform addresses: broadcast 16-byte loads served by L1
-#pragma unroll
-              for (int g = 0; g < 4; ++g) {
-                const int n = n_warp + c + g * 4;
-                if (n + 4 <= n_total) {
-                  const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
-                  v[g * 4] += b4.x;
-                  v[g * 4 + 1] += b4.y;
-                  v[g * 4 + 2] += b4.z;
-                  v[g * 4 + 3] += b4.w;
-                }
-              }
+            for (int g = 0; g < 4; ++g) {
+              const float4 b4 = *reinterpret_cast<const float4*>(bsm + c + g * 4);  // smem broadcast
+              v[g * 4] = __uint_as_float(r[g * 4]) + b4.x;
+              v[g * 4 + 1] = __uint_as_float(r[g * 4 + 1]) + b4.y;
+              v[g * 4 + 2] = __uint_as_float(r[g * 4 + 2]) + b4.z;
+              v[g * 4 + 3] = __uint_as_float(r[g * 4 + 3]) + b4.w;
             }
             *reinterpret_cast<uint4*>(slab + lane * PITCH + c * 2) = pack8<T>(v);
             *reinterpret_cast<uint4*>(slab + lane * PITCH + c * 2 + 16) = pack8<T>(v + 8);
@@ -277,23 +290,10 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
             tmem_ld16(taddr + hs * (HALF / 2) + c, rh);
             tmem_ld16(taddr + HALF + hs * (HALF / 2) + c, rg);
             tmem_wait_ld();
-            float v[16], bh[16], bg[16];
-            if (p.bias) {  // packed GEGLU bias: tile-local [h (HALF) | gate (HALF)]
-              const float* bp = p.bias + n_tile * BN + hs * wcols + c;
-#pragma unroll
-              for (int g = 0; g < 4; ++g) {
-                const float4 h4 = __ldg(reinterpret_cast<const float4*>(bp + g * 4));
-                const float4 g4 = __ldg(reinterpret_cast<const float4*>(bp + HALF + g * 4));
-                bh[g * 4] = h4.x; bh[g * 4 + 1] = h4.y; bh[g * 4 + 2] = h4.z; bh[g * 4 + 3] = h4.w;
-                bg[g * 4] = g4.x; bg[g * 4 + 1] = g4.y; bg[g * 4 + 2] = g4.z; bg[g * 4 + 3] = g4.w;
-              }
-            } else {
-#pragma unroll
-              for (int i = 0; i < 16; ++i) bh[i] = bg[i] = 0.f;
-            }
+            float v[16];
 #pragma unroll
             for (int i = 0; i < 16; ++i)
-              v[i] = (__uint_as_float(rh[i]) + bh[i]) * gelu_erf_f(__uint_as_float(rg[i]) + bg[i]);
+              v[i] = (__uint_as_float(rh[i]) + bsm[c + i]) * gelu_erf_f(__uint_as_float(rg[i]) + bsm[wcols + c + i]);
             *reinterpret_cast<uint4*>(slab + lane * PITCH + c * 2) = pack8<T>(v);
             *reinterpret_cast<uint4*>(slab + lane * PITCH + c * 2 + 16) = pack8<T>(v + 8);
           }

@@ -21,6 +21,12 @@ def _dt(t: torch.Tensor) -> int:
     return _lib.torch_dtype_id(t.dtype)
 
 
+def _dt16(t: torch.Tensor) -> int:
+    if t.dtype not in (torch.float16, torch.bfloat16):
+        raise TypeError(f"rcdms_b200.ops: tensor-core kernels take float16/bfloat16 storage, got {t.dtype}")
+    return _dt(t)
+
+
 def _ptr(t: Optional[torch.Tensor]):
     return None if t is None else t.data_ptr()
 
@@ -31,7 +37,7 @@ def linear(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None
     M, K = a.shape
     N = w.shape[0]
     out = torch.empty((M, N), dtype=a.dtype, device=a.device)
-    _lib.check(_lib.lib().rcdm_gemm(_dt(a), a.data_ptr(), w.data_ptr(), _ptr(bias), _ptr(residual), out.data_ptr(),
+    _lib.check(_lib.lib().rcdm_gemm(_dt16(a), a.data_ptr(), w.data_ptr(), _ptr(bias), _ptr(residual), out.data_ptr(),
                                     M, N, K, 0, tile_n, int(simple), _lib.current_stream_ptr()))
     return out
 
