@@ -37,7 +37,7 @@ static int ensure_device_ready() {
       err = "no CUDA device: librcdm_b200 has no CPU fallback";
       return;
     }
-    ok = gemm_setup_attributes(&err) && attn_setup_attributes(&err);
+    ok = gemm_setup_attributes(&err) && attn_setup_attributes(&err) && gn_setup_attributes(&err);
   });
   return ok ? 0 : set_err(err);
 }
@@ -222,8 +222,9 @@ int64_t rcdm_unet_read_tap(rcdm_unet* h, const char* name, float* out_dev, int64
 // DDIM step + denoise loop
 // ------------------------------------------------------------------------------------------
 static void ddim_coefs(float abar_t, float abar_prev, float* c) {
-  // fp32 arithmetic like the reference's 0-dim fp32 tensors (scheduling_ddim.step)
-  c[0] = sqrtf(abar_t);
+  // fp32 arithmetic like the reference's 0-dim fp32 tensors (scheduling_ddim.step); c[0] is the reciprocal torch
+  // forms when a tensor is divided by a CPU scalar (host IEEE division: this file's device code is --use_fast_math)
+  c[0] = 1.0f / sqrtf(abar_t);
   c[1] = sqrtf(1.0f - abar_t);
   c[2] = sqrtf(abar_prev);
   c[3] = sqrtf(1.0f - abar_prev);

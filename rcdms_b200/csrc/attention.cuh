@@ -106,6 +106,7 @@ flash_attn_kernel(const __grid_constant__ AttnMaps maps, const AttnParams p) {
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_O = tmem_base + 2 * BN;
+  pdl_sync();
 
   if (warp == 4) {
     if (elect_one()) {
@@ -338,6 +339,7 @@ __global__ void temporal_attn_kernel(const T* __restrict__ qkv, T* __restrict__ 
   const int C = heads * d;
   const size_t total = (size_t)batch * hw * heads;
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  pdl_sync();
   if (idx >= total) return;
   const int h = (int)(idx % heads);
   const size_t loc = idx / heads;

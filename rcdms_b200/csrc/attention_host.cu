@@ -47,7 +47,7 @@ bool attn_prepare(const AttnDesc& d, AttnLaunch* l, std::string* err) {
 }
 
 template <typename T, int DPAD> static void launch_one(const AttnLaunch& l, cudaStream_t s) {
-  flash_attn_kernel<T, DPAD><<<l.grid, 160, AttnCfg<DPAD>::SMEM_BYTES, s>>>(l.maps, l.p);
+  launch_k(flash_attn_kernel<T, DPAD>, l.grid, dim3(160), AttnCfg<DPAD>::SMEM_BYTES, s, l.maps, l.p);
 }
 template <typename T> static void launch_dt(const AttnLaunch& l, cudaStream_t s) {
   switch (l.dpad) {
@@ -76,7 +76,8 @@ template <typename T> static cudaError_t set_attr_dt() {
   return e;
 }
 bool attn_setup_attributes(std::string* err) {
-  cudaError_t e = set_attr_dt<__half>();
+  cudaError_t e = pdl_upload_mode(pdl_mode() == 2);
+  if (e == cudaSuccess) e = set_attr_dt<__half>();
   if (e == cudaSuccess) e = set_attr_dt<__nv_bfloat16>();
   if (e != cudaSuccess) {
     if (err) *err = std::string("cudaFuncSetAttribute(attn): ") + cudaGetErrorString(e);
@@ -131,8 +132,8 @@ void temporal_attn_launch(int dt, const void* qkv, void* out, int batch, int fra
   const int blocks = (int)((total + 127) / 128);
   const float scale = 1.0f / sqrtf((float)d);
 #define RCDM_TA(T, F)                                                                                              \
-  temporal_attn_kernel<T, F><<<blocks, 128, 0, s>>>(reinterpret_cast<const T*>(qkv), reinterpret_cast<T*>(out), \
-                                                     batch, hw, heads, d, scale)
+  launch_k(temporal_attn_kernel<T, F>, dim3(blocks), dim3(128), 0, s, reinterpret_cast<const T*>(qkv),         \
+           reinterpret_cast<T*>(out), batch, hw, heads, d, scale)
   if (dt == DT_F16) {
     switch (frames) {
       case 1: RCDM_TA(__half, 1); break;

@@ -90,6 +90,29 @@ __device__ __forceinline__ bool elect_one() {
 }
 
 // ------------------------------------------------------------------------------------------
+// Programmatic dependent launch (PDL).  Every kernel of the denoise step is launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization (launch.h: launch_k), so its CTAs may become resident
+// while the previous kernel of the stream is still draining: barrier init, TMEM allocation and tensor-map
+// prefetch then overlap the predecessor's tail.  pdl_wait() blocks until the predecessor grid has completed and
+// its memory is visible; it must precede the first global-memory access.  pdl_trigger() lets the successor start
+// its own prologue.  Both are no-ops for a kernel launched without the attribute.
+// ------------------------------------------------------------------------------------------
+// c_pdl_early (per translation unit, uploaded by pdl_upload_mode): 1 = trigger the successor before waiting.
+static __constant__ int c_pdl_early;
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_sync() {
+  if (c_pdl_early) {
+    pdl_trigger();
+    pdl_wait();
+  } else {
+    pdl_wait();
+    pdl_trigger();
+  }
+}
+static inline cudaError_t pdl_upload_mode(int early) { return cudaMemcpyToSymbol(c_pdl_early, &early, sizeof(int)); }
+
+// ------------------------------------------------------------------------------------------
 // mbarrier
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {

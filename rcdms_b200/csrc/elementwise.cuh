@@ -136,7 +136,7 @@ __global__ void gemv_kernel(const float* __restrict__ x, const T* __restrict__ w
 // eps:      (2B, 4, f, h, w)   [uncond clips | cond clips]   (B, ...) when !cfg
 // latents:  (B, 4, f, h, w)  updated in place (fp32 master copy + optional user-dtype copy)
 // next_in:  (2B, 9, f, h, w)   [latents | mask | masked_latents] for both CFG halves (compute dtype T)
-// coef: {sqrt(abar_t), sqrt(1-abar_t), sqrt(abar_prev), sqrt(1-abar_prev)} read from a device table at *step_idx
+// coef: {1/sqrt(abar_t), sqrt(1-abar_t), sqrt(abar_prev), sqrt(1-abar_prev)} read from a device table at *step_idx
 // when table != nullptr (graph replay), else passed by value.
 struct DdimArgs {
   const void* eps;
@@ -165,10 +165,18 @@ __device__ __forceinline__ float round_to(float v, int dt) {
   return v;
 }
 
+// Arithmetic mirrors the reference op by op: torch evaluates every elementwise op on 16-bit tensors in fp32 and
+// rounds the result to the tensor dtype, scalars (python floats / 0-dim fp32 CPU tensors) stay fp32, and a division
+// by a CPU scalar is a multiplication by its fp32 reciprocal.  So, with r() = round to the latents dtype:
+//   CFG  (RCDMs_pipeline.py:493-494):  e = r(eu + r(g * r(ec - eu)))
+//   DDIM (diffusers scheduling_ddim.step, eta = 0, epsilon prediction, no clipping):
+//        x0 = r(r(x - r(c1 * e)) * c0inv) ;  x_prev = r(r(c2 * x0) + r(c3 * e))
+// __fmul_rn / __fadd_rn keep nvcc from contracting across the reference's rounding points (fp32 latents too).
 static __global__ void ddim_cfg_step_kernel(const DdimArgs a) {
   const size_t n = (size_t)a.B * 4 * a.FHW;
   float4 co = make_float4(a.c[0], a.c[1], a.c[2], a.c[3]);
   if (a.table) co = a.table[*a.step_idx];
+  const int rd = a.round_dt;
   for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (size_t)gridDim.x * blockDim.x) {
     const int pix = (int)(idx % a.FHW);
     const int ch = (int)((idx / a.FHW) % 4);
@@ -177,13 +185,15 @@ static __global__ void ddim_cfg_step_kernel(const DdimArgs a) {
     if (a.cfg) {
       const float eu = load_any(a.eps, a.eps_dt, idx);
       const float ec = load_any(a.eps, a.eps_dt, idx + n);
-      e = round_to(eu + a.guidance * (ec - eu), a.round_dt);
+      const float d = round_to(__fadd_rn(ec, -eu), rd);
+      e = round_to(__fadd_rn(eu, round_to(__fmul_rn(a.guidance, d), rd)), rd);
     } else {
       e = load_any(a.eps, a.eps_dt, idx);
     }
     const float x = a.latents[idx];
-    const float x0 = (x - co.y * e) / co.x;
-    const float xn = round_to(co.z * x0 + co.w * e, a.round_dt);
+    const float t2 = round_to(__fadd_rn(x, -round_to(__fmul_rn(co.y, e), rd)), rd);
+    const float x0 = round_to(__fmul_rn(t2, co.x), rd);
+    const float xn = round_to(__fadd_rn(round_to(__fmul_rn(co.z, x0), rd), round_to(__fmul_rn(co.w, e), rd)), rd);
     a.latents[idx] = xn;
     if (a.latents_out) store_any(a.latents_out, a.latents_out_dt, idx, xn);
     if (a.next_in) {

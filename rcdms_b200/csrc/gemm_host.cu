@@ -68,9 +68,18 @@ bool encode_tmap(CUtensorMap* out, const void* base, int rank, const uint64_t* d
 // ------------------------------------------------------------------------------------------
 // GEMM prepare / launch
 // ------------------------------------------------------------------------------------------
+int pdl_mode() {
+  static const int mode = [] {
+    const char* e = getenv("RCDM_PDL");
+    return e ? atoi(e) : 0;
+  }();
+  return mode;
+}
+bool pdl_enabled() { return pdl_mode() > 0; }
+
 static bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
 
-static int num_sms() {
+int num_sms() {
   static int n = 0;
   if (!n) {
     int dev = 0;
@@ -194,7 +203,7 @@ bool gemm_prepare(const GemmDesc& d, GemmLaunch* l, std::string* err) {
 }
 
 template <typename T, int BN> static void launch_one(const GemmLaunch& l, cudaStream_t s) {
-  gemm_tcgen05_kernel<T, BN><<<l.grid, 320, GemmCfg<BN>::SMEM_BYTES, s>>>(l.maps, l.p);
+  launch_k(gemm_tcgen05_kernel<T, BN>, l.grid, dim3(320), GemmCfg<BN>::SMEM_BYTES, s, l.maps, l.p);
 }
 
 void gemm_launch(const GemmLaunch& l, cudaStream_t s) {
@@ -215,7 +224,7 @@ template <typename T, int BN> static cudaError_t set_attr() {
 }
 
 bool gemm_setup_attributes(std::string* err) {
-  cudaError_t e = cudaSuccess;
+  cudaError_t e = pdl_upload_mode(pdl_mode() == 2);
   if (e == cudaSuccess) e = set_attr<__half, 64>();
   if (e == cudaSuccess) e = set_attr<__half, 128>();
   if (e == cudaSuccess) e = set_attr<__half, 160>();

@@ -119,6 +119,7 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_sync();  // everything above overlapped the previous kernel's tail; global memory is touched only below
 
   if (warp == 0) {
     // =================================== TMA producer ===================================

@@ -26,7 +26,13 @@ struct GnLaunch {
   size_t smem;
   size_t total_vecs;
   int agrid, dt;
+  // fused single-launch path (gn_fused_kernel); fused == 0 -> the two-kernel path above
+  int fused, cps, cache_rows, fthreads, fgrid, fk;
+  size_t fsmem;
+  int rows_per_cta_2k;  // rows_per_cta of the two-kernel path (a.rows_per_cta is the fused value when fused)
 };
+int num_sms();
+bool gn_setup_attributes(std::string* err);
 size_t gn_scratch_bytes(int nstat, int groups);
 // scratch must be zero-initialised once (the kernels leave the counters zero)
 void gn_configure(GnLaunch* l, int dt, const void* x0, int C0, const void* x1, int C1, int rows, int rows_per_stat,

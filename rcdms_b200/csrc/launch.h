@@ -5,11 +5,30 @@
 #include <stdint.h>
 
 #include <string>
+#include <utility>
 
 #include "attention.cuh"
 #include "gemm_tcgen05.cuh"
 
 namespace rcdm {
+
+// ---- kernel launch with programmatic stream serialization (PDL); RCDM_PDL=0 in the environment disables it ----
+bool pdl_enabled();  // RCDM_PDL = 0 (off, default: measured slower inside CUDA graphs) | 1 (wait, then trigger) | 2 (trigger, then wait)
+int pdl_mode();
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
+}
 
 // ---- TMA tensor-map encoding (driver entry point resolved at run time; no link-time libcuda dependency) ----
 // dims/box innermost-first; strides_bytes has rank-1 entries (dimension 0 is contiguous). 16-bit elements.

@@ -54,15 +54,66 @@ void gn_configure(GnLaunch* l, int dt, const void* x0, int C0, const void* x1, i
   size_t g = (l->total_vecs + 255) / 256;
   l->agrid = (int)(g < 148 * 8 ? (g ? g : 1) : 148 * 8);
   l->dt = dt;
+  l->rows_per_cta_2k = a.rows_per_cta;
+  // ---- fused single-launch path
+  static const bool fused_on = [] {
+    const char* e = getenv("RCDM_GN_FUSED");
+    return !(e && e[0] == '0');
+  }();
+  l->fused = 0;
+  if (fused_on && vecs <= 512 && a.nstat <= 8192 && groups <= 64) {
+    const int sms = num_sms();
+    int kf = 512 / vecs;
+    if (kf < 1) kf = 1;
+    int cps = sms / a.nstat;
+    if (cps < 1) cps = 1;
+    if (cps > rows_per_stat) cps = rows_per_stat;
+    const int rpc = (rows_per_stat + cps - 1) / cps;
+    cps = (rows_per_stat + rpc - 1) / rpc;  // drop CTAs that would own no rows
+    if (kf > rpc) kf = rpc;
+    const size_t scratch_b = (size_t)kf * 2 * C * 4;
+    const size_t budget = 232448 - 1024 - scratch_b;
+    size_t cache_rows = budget / ((size_t)C * 2);
+    if (cache_rows > (size_t)rpc) cache_rows = rpc;
+    l->fused = 1;
+    l->cps = cps;
+    l->cache_rows = (int)cache_rows;
+    l->fthreads = (vecs * kf + 31) / 32 * 32;
+    l->fk = kf;
+    l->fgrid = a.nstat * cps;
+    l->fsmem = scratch_b + cache_rows * (size_t)C * 2;
+    a.rows_per_cta = rpc;
+  }
+}
+
+bool gn_setup_attributes(std::string* err) {
+  cudaError_t e = pdl_upload_mode(pdl_mode() == 2);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(gn_fused_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 1024);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(gn_fused_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 1024);
+  if (e != cudaSuccess) {
+    if (err) *err = std::string("cudaFuncSetAttribute(gn_fused): ") + cudaGetErrorString(e);
+    return false;
+  }
+  return true;
 }
 
 void gn_run(const GnLaunch& l, cudaStream_t s) {
+  if (l.fused) {
+    if (l.dt == DT_F16)
+      launch_k(gn_fused_kernel<__half>, dim3(l.fgrid), dim3(l.fthreads), l.fsmem, s, l.a, l.cps, l.cache_rows, l.fk);
+    else
+      launch_k(gn_fused_kernel<__nv_bfloat16>, dim3(l.fgrid), dim3(l.fthreads), l.fsmem, s, l.a, l.cps, l.cache_rows, l.fk);
+    g_launches += 1;
+    return;
+  }
   if (l.dt == DT_F16) {
-    gn_stats_kernel<__half><<<l.grid, l.threads, l.smem, s>>>(l.a);
-    gn_apply_kernel<__half><<<l.grid, l.threads, 0, s>>>(l.a);
+    launch_k(gn_stats_kernel<__half>, l.grid, dim3(l.threads), l.smem, s, l.a);
+    launch_k(gn_apply_kernel<__half>, l.grid, dim3(l.threads), 0, s, l.a);
   } else {
-    gn_stats_kernel<__nv_bfloat16><<<l.grid, l.threads, l.smem, s>>>(l.a);
-    gn_apply_kernel<__nv_bfloat16><<<l.grid, l.threads, 0, s>>>(l.a);
+    launch_k(gn_stats_kernel<__nv_bfloat16>, l.grid, dim3(l.threads), l.smem, s, l.a);
+    launch_k(gn_apply_kernel<__nv_bfloat16>, l.grid, dim3(l.threads), 0, s, l.a);
   }
   g_launches += 2;
 }
@@ -76,8 +127,8 @@ bool ln_run(int dt, const void* x, void* o, const float* gp, const float* bp, in
   const int warps = (nrows + rpw - 1) / rpw;
   const int blocks = (warps + 7) / 8;
 #define RCDM_LN(T, V, R)                                                                                           \
-  layernorm_kernel<T, V, R><<<blocks, 256, 0, s>>>(reinterpret_cast<const T*>(x), reinterpret_cast<T*>(o), gp, bp, \
-                                                   nrows, C, eps, pep, rows_per_frame, frames)
+  launch_k(layernorm_kernel<T, V, R>, dim3(blocks), dim3(256), 0, s, reinterpret_cast<const T*>(x),                \
+           reinterpret_cast<T*>(o), gp, bp, nrows, C, eps, pep, rows_per_frame, frames)
   if (dt == DT_F16) {
     if (maxv <= 1) RCDM_LN(__half, 1, 8);
     else if (maxv == 2) RCDM_LN(__half, 2, 4);

@@ -39,6 +39,7 @@ __global__ void gn_stats_kernel(const GnArgs a) {
   const int rl = threadIdx.x / vecs;
   const int chunk = blockIdx.x, sb = blockIdx.y;
   const int chunks = gridDim.x;
+  pdl_sync();
   if (rl < k) {
     float s[8], ss[8];
 #pragma unroll
@@ -147,6 +148,7 @@ __global__ void gn_apply_kernel(const GnArgs a) {
   const int k = blockDim.x / vecs;
   const int v = threadIdx.x % vecs;
   const int rl = threadIdx.x / vecs;
+  pdl_sync();
   if (rl >= k) return;
   const int chunk = blockIdx.x, sb = blockIdx.y;
   const int c = v * 8;
@@ -185,6 +187,188 @@ __global__ void gn_apply_kernel(const GnArgs a) {
   for (; r < a.rows_per_cta; r += k) emit(__ldg(reinterpret_cast<const uint4*>(src + (row0 + r) * ld + cc)), row0 + r);
 }
 
+// ------------------------------------------------------------------------------------------
+// Fused GroupNorm (+SiLU): statistics AND normalisation in ONE launch and (when the tensor fits) ONE HBM/L2 read.
+// grid = nstat * cps CTAs (<= #SMs whenever cps > 1, so the CTAs of a statistic batch are co-resident and may
+// synchronise through global memory); CTA (sb, part) owns `rows_per_cta` consecutive rows of statistic batch sb:
+//   phase 1  stream the rows (16-byte loads, 4 in flight per thread), keep the first `cache_rows` of them in shared
+//            memory, accumulate per-thread per-channel sum / sum of squares; fixed-order block reduction to per-group
+//            partials -> global `partial[sb][part][group]`
+//   barrier  (cps > 1) arrive counter + spin, then every CTA folds the cps partials of its batch in a fixed order
+//            (double precision) -> mean / rstd.  Deterministic: no floating-point atomics anywhere.
+//   phase 2  normalise (+SiLU) from shared memory (rows beyond the cache are re-read) -> out
+// counters: [0, 8192) arrive, [8192, 16384) depart; both are left zero.
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(512, 1) gn_fused_kernel(const GnArgs a, const int cps, const int cache_rows, const int k) {
+  extern __shared__ __align__(16) uint8_t gsm[];
+  __shared__ float2 gstat[64];
+  const int C = a.C0 + a.C1;
+  const int vecs = C / 8;
+  // blockDim.x == vecs * k rounded up to a whole number of warps; threads with rl >= k only help in the reductions
+  float* red = reinterpret_cast<float*>(gsm);                                // [k][2][C]
+  uint4* cache = reinterpret_cast<uint4*>(gsm + (size_t)k * 2 * C * 4);      // [cache_rows][vecs]
+  const int v = threadIdx.x % vecs, rl = threadIdx.x / vecs;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  const int sb = blockIdx.x / cps, part = blockIdx.x - sb * cps;
+  const int r_first = min(part * a.rows_per_cta, a.rows_per_stat);
+  const int nrows = min(a.rows_per_cta, a.rows_per_stat - r_first);
+  const int c = v * 8;
+  const int cpg = C / a.groups;
+  const T* src = reinterpret_cast<const T*>(c < a.C0 ? a.x0 : a.x1);
+  const int ld = c < a.C0 ? a.C0 : a.C1;
+  const int cc = c < a.C0 ? c : c - a.C0;
+  const size_t row0 = (size_t)sb * a.rows_per_stat + r_first;
+  pdl_sync();
+  // ---------------- phase 1
+  if (rl < k) {
+    float s[8], ss[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s[i] = ss[i] = 0.f;
+    auto acc = [&](const uint4& raw) {
+      float f[8];
+      unpack8<T>(raw, f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        s[i] += f[i];
+        ss[i] = fmaf(f[i], f[i], ss[i]);
+      }
+    };
+    int r = rl;
+    for (; r + 3 * k < nrows; r += 4 * k) {
+      uint4 raw[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) raw[u] = __ldg(reinterpret_cast<const uint4*>(src + (row0 + r + u * k) * ld + cc));
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (r + u * k < cache_rows) cache[(size_t)(r + u * k) * vecs + v] = raw[u];
+        acc(raw[u]);
+      }
+    }
+    for (; r < nrows; r += k) {
+      const uint4 raw = __ldg(reinterpret_cast<const uint4*>(src + (row0 + r) * ld + cc));
+      if (r < cache_rows) cache[(size_t)r * vecs + v] = raw;
+      acc(raw);
+    }
+    float* d0 = red + (size_t)(rl * 2) * C + c;
+    float* d1 = d0 + C;
+    *reinterpret_cast<float4*>(d0) = make_float4(s[0], s[1], s[2], s[3]);
+    *reinterpret_cast<float4*>(d0 + 4) = make_float4(s[4], s[5], s[6], s[7]);
+    *reinterpret_cast<float4*>(d1) = make_float4(ss[0], ss[1], ss[2], ss[3]);
+    *reinterpret_cast<float4*>(d1 + 4) = make_float4(ss[4], ss[5], ss[6], ss[7]);
+  }
+  __syncthreads();
+  const double n_inv = 1.0 / ((double)a.rows_per_stat * cpg);
+  for (int g = warp; g < a.groups; g += nw) {  // one warp per group, fixed reduction tree
+    float gs = 0.f, gss = 0.f;
+    const int items = cpg * k;
+    for (int it = lane; it < items; it += 32) {
+      const int l = it / cpg, ch = g * cpg + (it - l * cpg);
+      gs += red[(size_t)(l * 2) * C + ch];
+      gss += red[(size_t)(l * 2 + 1) * C + ch];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      gs += __shfl_xor_sync(0xffffffffu, gs, o);
+      gss += __shfl_xor_sync(0xffffffffu, gss, o);
+    }
+    if (lane == 0) {
+      if (cps == 1) {
+        const double mean = (double)gs * n_inv;
+        double var = (double)gss * n_inv - mean * mean;
+        if (var < 0) var = 0;
+        gstat[g] = make_float2((float)mean, (float)(1.0 / sqrt(var + (double)a.eps)));
+      } else {
+        a.partial[((size_t)sb * cps + part) * a.groups + g] = make_float2(gs, gss);
+      }
+    }
+  }
+  if (cps > 1) {
+    // ---------------- barrier among the cps CTAs of this statistic batch
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      atomicAdd(&a.counters[sb], 1u);
+      unsigned spins = 0;
+      while (true) {
+        unsigned seen;
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(a.counters + sb) : "memory");
+        if (seen >= (unsigned)cps) break;
+        if (++spins > (1u << 26)) {
+          printf("rcdm: gn_fused barrier timed out (block %d)\n", blockIdx.x);
+          __trap();
+        }
+      }
+    }
+    __syncthreads();
+    for (int g = warp; g < a.groups; g += nw) {
+      double gs = 0.0, gss = 0.0;
+      for (int pp = lane; pp < cps; pp += 32) {
+        const float2 z = __ldcg(&a.partial[((size_t)sb * cps + pp) * a.groups + g]);
+        gs += z.x;
+        gss += z.y;
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        gs += __shfl_xor_sync(0xffffffffu, gs, o);
+        gss += __shfl_xor_sync(0xffffffffu, gss, o);
+      }
+      if (lane == 0) {
+        const double mean = gs * n_inv;
+        double var = gss * n_inv - mean * mean;
+        if (var < 0) var = 0;
+        gstat[g] = make_float2((float)mean, (float)(1.0 / sqrt(var + (double)a.eps)));
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {  // the last CTA to leave re-arms the barrier for the next launch
+      const unsigned d = atomicAdd(&a.counters[8192 + sb], 1u);
+      if (d == (unsigned)cps - 1) {
+        a.counters[sb] = 0;
+        a.counters[8192 + sb] = 0;
+      }
+    }
+  } else {
+    __syncthreads();
+  }
+  // ---------------- phase 2
+  if (rl >= k) return;
+  float sc[8], sh[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float2 st = gstat[(c + i) / cpg];
+    const float g = __ldg(a.gamma + c + i);
+    sc[i] = st.y * g;
+    sh[i] = __ldg(a.beta + c + i) - st.x * st.y * g;
+  }
+  T* dst = reinterpret_cast<T*>(a.out);
+  auto emit = [&](const uint4& raw, size_t row) {
+    float f[8];
+    unpack8<T>(raw, f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float y = fmaf(f[i], sc[i], sh[i]);
+      f[i] = a.silu ? silu_f(y) : y;
+    }
+    *reinterpret_cast<uint4*>(dst + row * C + c) = pack8<T>(f);
+  };
+  int r = rl;
+  for (; r + 3 * k < nrows; r += 4 * k) {
+    uint4 raw[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int rr = r + u * k;
+      raw[u] = rr < cache_rows ? cache[(size_t)rr * vecs + v]
+                               : __ldg(reinterpret_cast<const uint4*>(src + (row0 + rr) * ld + cc));
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) emit(raw[u], row0 + r + u * k);
+  }
+  for (; r < nrows; r += k)
+    emit(r < cache_rows ? cache[(size_t)r * vecs + v] : __ldg(reinterpret_cast<const uint4*>(src + (row0 + r) * ld + cc)),
+         row0 + r);
+}
+
 // LayerNorm over the last dim; one warp per ROWS consecutive rows (all loads issued before any reduction so each
 // lane keeps ROWS*MAXV 16-byte requests in flight); C multiple of 8, C <= 32*8*MAXV.
 // pe (optional): fp32 [frames, C]; frame of a row = (row / rows_per_frame) % frames.
@@ -196,6 +380,7 @@ layernorm_kernel(const T* __restrict__ x, T* __restrict__ out, const float* __re
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   const int row0 = warp * ROWS;
+  pdl_sync();
   if (row0 >= rows) return;
   const int vecs = C / 8;
   uint4 raw[ROWS][MAXV];

@@ -1037,7 +1037,7 @@ static int ensure_arena(rcdm_unet_impl* h) {
   CUDA_OK(cudaMalloc(&h->arena, h->arena_bytes));
   CUDA_OK(cudaMemset(h->arena, 0, h->arena_bytes));
   std::string e;
-  if (!gemm_setup_attributes(&e) || !attn_setup_attributes(&e)) return set_err(e);
+  if (!gemm_setup_attributes(&e) || !attn_setup_attributes(&e) || !gn_setup_attributes(&e)) return set_err(e);
   return 0;
 }
 

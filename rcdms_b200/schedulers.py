@@ -97,11 +97,19 @@ class DDIMScheduler:
              return_dict: bool = True):
         if eta != 0.0:
             raise NotImplementedError("eta > 0 (stochastic DDIM) is not on the RCDMs path (eta=0.0 default)")
-        a_t, a_prev = self.step_coefficients(timestep)
-        x0 = (sample - (1.0 - a_t) ** 0.5 * model_output) / a_t ** 0.5
+        if self.num_inference_steps is None:
+            raise ValueError("Number of inference steps is 'None', you need to run 'set_timesteps' first")
+        # 0-dim fp32 CPU tensors exactly like diffusers 0.24 (scheduling_ddim.step): the arithmetic on 16-bit latents is
+        # then op-for-op what the reference executes (the fused CUDA step mirrors the same rounding points).
+        prev = int(timestep) - self.config.num_train_timesteps // self.num_inference_steps
+        alpha_prod_t = self.alphas_cumprod[int(timestep)]
+        alpha_prod_t_prev = self.alphas_cumprod[prev] if prev >= 0 else self.final_alpha_cumprod
+        beta_prod_t = 1 - alpha_prod_t
+        x0 = (sample - beta_prod_t ** 0.5 * model_output) / alpha_prod_t ** 0.5
         if self.config.clip_sample:
             x0 = x0.clamp(-1.0, 1.0)
-        prev_sample = a_prev ** 0.5 * x0 + (1.0 - a_prev) ** 0.5 * model_output
+        pred_sample_direction = (1 - alpha_prod_t_prev) ** 0.5 * model_output
+        prev_sample = alpha_prod_t_prev ** 0.5 * x0 + pred_sample_direction
         if not return_dict:
             return (prev_sample,)
         return DDIMStepOutput(prev_sample=prev_sample, pred_original_sample=x0)

@@ -160,12 +160,23 @@ def check_ddim(clips, f, h, w, dtype, cfg=True, seed=7):
     a_prev = float(sched.alphas_cumprod[t - 20])
     lat32 = lat.float().clone()
     out, nxt = ops.ddim_cfg_step(eps, lat32, a_t, a_prev, 2.0, cfg, dtype, mask, ml, dtype)
+    # (a) bit-exact against the reference's own arithmetic: torch ops on `dtype` tensors with fp32 0-dim scalars
+    #     (RCDMs_pipeline.py:493-497 + diffusers DDIMScheduler.step as restated in rcdms_b200.schedulers)
+    e16 = eps
+    if cfg:
+        eu, ec = eps.chunk(2)
+        e16 = eu + 2.0 * (ec - eu)
+    ref16 = sched.step(e16, t, lat, eta=0.0).prev_sample
+    exact = bool(torch.equal(out, ref16))
+    # (b) close to the fp32 oracle (per-op 16-bit rounding of the reference included => looser tolerance)
     e = eps.float()
     if cfg:
         eu, ec = e.chunk(2)
         e = eu + 2.0 * (ec - eu)
     ref = sched.step(e.cpu(), t, lat.float().cpu(), eta=0.0).prev_sample.cuda()
-    r = _result(f"ddim clips{clips} {f}x{h}x{w} cfg{int(cfg)}", out, ref, dtype, rtol_mul=2.0)
+    r = _result(f"ddim clips{clips} {f}x{h}x{w} cfg{int(cfg)}", out, ref, dtype, rtol_mul=8.0)
+    r["bit_exact_vs_reference_arithmetic"] = exact
+    r["ok"] = r["ok"] and exact
     lat2 = torch.cat([out] * 2) if cfg else out
     ref_next = torch.cat([lat2, torch.cat([mask] * (2 if cfg else 1)), torch.cat([ml] * (2 if cfg else 1))], dim=1)
     r["next_exact"] = bool(torch.equal(nxt, ref_next))
@@ -197,7 +208,8 @@ def all_op_checks(dtypes=(torch.float16, torch.bfloat16), quick=False):
         yield lambda dt=dt: check_conv3x3(4, 8, 8, 64, 64, 2, dt, simple=True)
         for (ns, rps, C, silu) in [(2, 5 * 64, 320, True), (10, 64, 64, False), (2, 5 * 4096, 320, True),
                                    (10, 1, 256, True), (2, 5 * 256, 960, True), (10, 1024, 640, False),
-                                   (2, 20, 2560, True)]:
+                                   (2, 20, 2560, True), (2, 5 * 4096, 960, True), (3, 1000, 192, False),
+                                   (16, 4096, 320, False), (160, 64, 1280, True), (1, 7, 64, True)]:
             yield lambda a=(ns, rps, C), silu=silu, dt=dt: check_groupnorm(*a, dt, silu=silu,
                                                                            eps=1e-5 if silu else 1e-6)
         for (rows, C, pe) in [(640, 320, False), (640, 320, True), (100, 64, True), (2560, 1280, True),

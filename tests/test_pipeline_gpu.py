@@ -49,8 +49,10 @@ def test_native_loop_matches_python_loop_and_oracle(clips, steps):
     assert torch.equal(nat, nog), "graph and eager launches must agree bitwise"
     pipe.use_native_loop = False
     py = pipe.denoise(lat, torch.cat([mask] * 2), torch.cat([ml] * 2), ctx, steps, 2.0)
-    # same UNet kernels, scheduler arithmetic in torch half ops (per-op rounding) vs fused fp32: small drift
-    assert (nat.float() - py.float()).abs().max().item() < 2e-2
+    # same UNet kernels; the fused CFG + DDIM kernel mirrors torch's per-op fp16 rounding (elementwise.cuh), so the
+    # native loop and the reference-shaped python loop must agree bit for bit
+    d_py = (nat.float() - py.float()).abs().max().item()
+    assert torch.equal(nat, py), f"native loop vs python loop: max abs diff {d_py}"
     sd = {k: v.half().float().cuda() for k, v in synthetic_state_dict(cfg, seed=0).items()}
     with torch.no_grad():
         refs = []
