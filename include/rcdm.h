@@ -75,6 +75,10 @@ typedef struct rcdm_unet rcdm_unet;
 RCDM_API const char* rcdm_version(void);
 RCDM_API const char* rcdm_last_error(void);            /* thread-local message of the last failing call */
 RCDM_API int rcdm_device_count(void);                  /* number of visible CUDA devices (0 => nothing can run) */
+RCDM_API int rcdm_set_stream_k_min(int k_blocks);       /* tuning knob: minimum k-blocks (64 wide) a GEMM launch must save before the
+                                                           stream-K decomposition is used; 0 disables it; returns the previous value */
+RCDM_API int rcdm_set_gemm_pair(int on);                /* tuning knob: use the CTA-pair (tcgen05 cta_group::2, 256-row tile) GEMM kernel
+                                                           (default 1); returns the previous value */
 RCDM_API uint64_t rcdm_kernel_launches(void);          /* kernels launched by this library since load (bench evidence) */
 
 /* ---- model life cycle (host only until the first weight arrives) ---- */

@@ -38,6 +38,8 @@ SIGNATURES = {
     "rcdm_last_error": (C.c_char_p, []),
     "rcdm_device_count": (_I, []),
     "rcdm_kernel_launches": (C.c_uint64, []),
+    "rcdm_set_stream_k_min": (_I, [_I]),
+    "rcdm_set_gemm_pair": (_I, [_I]),
     "rcdm_unet_create": (_I, [C.POINTER(UNetConfig), C.POINTER(_P)]),
     "rcdm_unet_destroy": (None, [_P]),
     "rcdm_unet_num_weights": (_I, [_P]),

@@ -69,6 +69,8 @@ int rcdm_device_count(void) {
   return n;
 }
 uint64_t rcdm_kernel_launches(void) { return g_launches.load(); }
+int rcdm_set_stream_k_min(int k_blocks) { return gemm_set_sk_min(k_blocks); }
+int rcdm_set_gemm_pair(int on) { return gemm_set_pair(on); }
 
 int rcdm_unet_create(const rcdm_unet_config* cfg, rcdm_unet** out) {
   API_BEGIN

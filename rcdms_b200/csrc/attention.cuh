@@ -405,4 +405,93 @@ __global__ void temporal_attn_kernel(const T* __restrict__ qkv, T* __restrict__ 
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// temporal attention, tiled: one CTA = PT consecutive pixels of one clip half b.  The F frame blocks
+// [PT rows x 3C] of the fused QKV matrix are contiguous in memory -> copied to shared memory with coalesced 16-byte
+// cp.async; thread (pixel, head, query frame i) computes one row of the F x F attention from shared memory and
+// overwrites its own q_i slice with o_i (no other thread reads q_i); the q-third of the tile is then written back
+// with coalesced 16-byte stores.  HBM/L2 traffic = the algorithmic minimum (read 3C, write C per row).
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+template <typename T, int F>
+__global__ void __launch_bounds__(512)
+temporal_attn_tile_kernel(const T* __restrict__ qkv, T* __restrict__ out, int hw, int heads, int d, int PT,
+                          float scale) {
+  extern __shared__ __align__(16) uint8_t tsm[];
+  T* sm = reinterpret_cast<T*>(tsm);  // [F][PT][3C]
+  const int C = heads * d, ld = 3 * C;
+  const int tiles_per_b = hw / PT;
+  const int b = blockIdx.x / tiles_per_b, pix0 = (blockIdx.x - b * tiles_per_b) * PT;
+  const size_t row_b = (size_t)b * F * hw + pix0;
+  const int chunks_per_f = PT * ld / 8;
+  pdl_sync();
+  for (int idx = threadIdx.x; idx < F * chunks_per_f; idx += blockDim.x) {
+    const int f = idx / chunks_per_f, c = idx - f * chunks_per_f;
+    cp_async16(sm + (size_t)f * PT * ld + (size_t)c * 8, qkv + (row_b + (size_t)f * hw) * ld + (size_t)c * 8);
+  }
+  cp_async_wait_all();
+  __syncthreads();
+  if (threadIdx.x < PT * heads * F) {
+    const int i = threadIdx.x % F;
+    const int h = (threadIdx.x / F) % heads;
+    const int p = threadIdx.x / (F * heads);
+    T* qp = sm + (size_t)(i * PT + p) * ld + h * d;
+    float s[F];
+#pragma unroll
+    for (int j = 0; j < F; ++j) s[j] = 0.f;
+    for (int c = 0; c < d; c += 8) {
+      float qf[8];
+      unpack8<T>(*reinterpret_cast<const uint4*>(qp + c), qf);
+#pragma unroll
+      for (int j = 0; j < F; ++j) {
+        float kf[8];
+        unpack8<T>(*reinterpret_cast<const uint4*>(sm + (size_t)(j * PT + p) * ld + C + h * d + c), kf);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) s[j] = fmaf(qf[e], kf[e], s[j]);
+      }
+    }
+    float mx = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < F; ++j) {
+      s[j] *= scale;
+      mx = fmaxf(mx, s[j]);
+    }
+    float sum = 0.f;
+#pragma unroll
+    for (int j = 0; j < F; ++j) {
+      s[j] = __expf(s[j] - mx);
+      sum += s[j];
+    }
+    const float inv = 1.0f / sum;
+#pragma unroll
+    for (int j = 0; j < F; ++j) s[j] *= inv;
+    for (int c = 0; c < d; c += 8) {
+      float o[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) o[e] = 0.f;
+#pragma unroll
+      for (int j = 0; j < F; ++j) {
+        float vf[8];
+        unpack8<T>(*reinterpret_cast<const uint4*>(sm + (size_t)(j * PT + p) * ld + 2 * C + h * d + c), vf);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o[e] = fmaf(s[j], vf[e], o[e]);
+      }
+      *reinterpret_cast<uint4*>(qp + c) = pack8<T>(o);  // in place: only this thread ever reads q_i
+    }
+  }
+  __syncthreads();
+  const int cvec = C / 8;
+  for (int idx = threadIdx.x; idx < F * PT * cvec; idx += blockDim.x) {
+    const int c8 = idx % cvec;
+    const int fp = idx / cvec;  // f * PT + p
+    const int f = fp / PT, p = fp - f * PT;
+    *reinterpret_cast<uint4*>(out + (row_b + (size_t)f * hw + p) * C + (size_t)c8 * 8) =
+        *reinterpret_cast<const uint4*>(sm + (size_t)fp * ld + (size_t)c8 * 8);
+  }
+}
+
 }  // namespace rcdm

@@ -126,32 +126,73 @@ void attn_simple_launch(const AttnDesc& d, cudaStream_t s) {
   else attn_simple_kernel<__nv_bfloat16><<<blocks, 128, 0, s>>>(d);
 }
 
+template <typename T, int F> static void temporal_tiled(const void* qkv, void* out, int batch, int hw, int heads, int d,
+                                                        int PT, float scale, cudaStream_t s) {
+  const int C = heads * d;
+  const size_t smem = (size_t)F * PT * 3 * C * sizeof(T);
+  const int threads = (PT * heads * F + 31) / 32 * 32;
+  static bool attr_done = false;  // per instantiation
+  if (!attr_done) {
+    cudaFuncSetAttribute(temporal_attn_tile_kernel<T, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    attr_done = true;
+  }
+  launch_k(temporal_attn_tile_kernel<T, F>, dim3(batch * (hw / PT)), dim3(threads), smem, s,
+           reinterpret_cast<const T*>(qkv), reinterpret_cast<T*>(out), hw, heads, d, PT, scale);
+}
+
 void temporal_attn_launch(int dt, const void* qkv, void* out, int batch, int frames, int hw, int heads, int d,
                           cudaStream_t s) {
   const size_t total = (size_t)batch * hw * heads;
   const int blocks = (int)((total + 127) / 128);
   const float scale = 1.0f / sqrtf((float)d);
+  // tiled kernel (coalesced through shared memory): PT = pixels per CTA, a power of two dividing hw with
+  // <= 80 KB of shared memory and <= 512 threads; the one-thread-per-(pixel, head) kernel is the fallback
+  static const bool tiled_on = [] {
+    const char* e = getenv("RCDM_TEMPORAL_TILED");
+    return !(e && e[0] == '0');
+  }();
+  int PT = 0;
+  if (tiled_on && frames >= 1 && frames <= 5) {
+    // small tiles: load / compute / store phases of a CTA do not overlap, so several CTAs per SM must
+    const char* kb = getenv("RCDM_TEMPORAL_SMEM_KB");
+    const size_t budget = (size_t)(kb ? atoi(kb) : 40) * 1024;
+    const size_t per_pixel = (size_t)frames * 3 * heads * d * 2;
+    for (int cand = 32; cand >= 1; cand >>= 1)
+      if (hw % cand == 0 && (cand * per_pixel <= budget || cand == 1) && cand * per_pixel <= 100 * 1024 &&
+          cand * heads * frames <= 512) {
+        PT = cand;
+        break;
+      }
+  }
+#define RCDM_TT(T, F) temporal_tiled<T, F>(qkv, out, batch, hw, heads, d, PT, scale, s)
 #define RCDM_TA(T, F)                                                                                              \
   launch_k(temporal_attn_kernel<T, F>, dim3(blocks), dim3(128), 0, s, reinterpret_cast<const T*>(qkv),         \
            reinterpret_cast<T*>(out), batch, hw, heads, d, scale)
+#define RCDM_T(T, F)       \
+  do {                     \
+    if (PT) RCDM_TT(T, F); \
+    else RCDM_TA(T, F);    \
+  } while (0)
   if (dt == DT_F16) {
     switch (frames) {
-      case 1: RCDM_TA(__half, 1); break;
-      case 2: RCDM_TA(__half, 2); break;
-      case 3: RCDM_TA(__half, 3); break;
-      case 4: RCDM_TA(__half, 4); break;
-      default: RCDM_TA(__half, 5); break;
+      case 1: RCDM_T(__half, 1); break;
+      case 2: RCDM_T(__half, 2); break;
+      case 3: RCDM_T(__half, 3); break;
+      case 4: RCDM_T(__half, 4); break;
+      default: RCDM_T(__half, 5); break;
     }
   } else {
     switch (frames) {
-      case 1: RCDM_TA(__nv_bfloat16, 1); break;
-      case 2: RCDM_TA(__nv_bfloat16, 2); break;
-      case 3: RCDM_TA(__nv_bfloat16, 3); break;
-      case 4: RCDM_TA(__nv_bfloat16, 4); break;
-      default: RCDM_TA(__nv_bfloat16, 5); break;
+      case 1: RCDM_T(__nv_bfloat16, 1); break;
+      case 2: RCDM_T(__nv_bfloat16, 2); break;
+      case 3: RCDM_T(__nv_bfloat16, 3); break;
+      case 4: RCDM_T(__nv_bfloat16, 4); break;
+      default: RCDM_T(__nv_bfloat16, 5); break;
     }
   }
+#undef RCDM_T
 #undef RCDM_TA
+#undef RCDM_TT
 }
 
 }  // namespace rcdm

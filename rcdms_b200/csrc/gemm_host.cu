@@ -3,6 +3,7 @@
 // failures (RCDM_SIMPLE=1); it is never the benchmarked path.
 #include <cudaTypedefs.h>
 
+#include <cmath>
 #include <mutex>
 
 #include "launch.h"
@@ -88,6 +89,50 @@ int num_sms() {
       n = 148;
   }
   return n;
+}
+
+// ---- stream-K workspace: one fp32 partial tile + one flag per CTA; process-wide (one device, one stream at a time)
+static float* g_sk_ws = nullptr;
+static unsigned* g_sk_flags = nullptr;
+static int g_sk_slots = 0;
+static int g_sk_min = -1;
+static int sk_min_saving() {  // k-blocks a launch must save before stream-K pays for its fix-up traffic
+  if (g_sk_min < 0) {
+    const char* e = getenv("RCDM_SK_MIN");
+    g_sk_min = e ? atoi(e) : 24;
+  }
+  return g_sk_min;
+}
+int gemm_set_sk_min(int k_blocks) {
+  const int prev = sk_min_saving();
+  g_sk_min = k_blocks < 0 ? 0 : k_blocks;
+  return prev;
+}
+static int g_pair = -1;
+static int pair_enabled() {
+  if (g_pair < 0) {
+    const char* e = getenv("RCDM_GEMM_PAIR");
+    g_pair = e ? atoi(e) : 1;
+  }
+  return g_pair;
+}
+int gemm_set_pair(int on) {
+  const int prev = pair_enabled();
+  g_pair = on < 0 ? 0 : on;
+  return prev;
+}
+static bool sk_alloc(std::string* err) {
+  if (g_sk_ws) return true;
+  const int slots = num_sms();
+  cudaError_t e = cudaMalloc(&g_sk_ws, (size_t)slots * 128 * 160 * sizeof(float));
+  if (e == cudaSuccess) e = cudaMalloc(&g_sk_flags, (size_t)slots * sizeof(unsigned));
+  if (e == cudaSuccess) e = cudaMemset(g_sk_flags, 0, (size_t)slots * sizeof(unsigned));
+  if (e != cudaSuccess) {
+    if (err) *err = std::string("stream-K workspace: ") + cudaGetErrorString(e);
+    return false;
+  }
+  g_sk_slots = slots;
+  return true;
 }
 
 static int pick_bn(const GemmDesc& d) {
@@ -187,23 +232,62 @@ bool gemm_prepare(const GemmDesc& d, GemmLaunch* l, std::string* err) {
       }
     }
   }
+  const int m_tiles = has_conv ? ((d.NI + p.tn - 1) / p.tn) * p.tiles_y * p.tiles_x : (d.M + 127) / 128;
+  // CTA pairs (cta_group::2, 256-row tiles): measured on B200 to pay (3-9 %) only for deep-K, many-tile problems
+  // (the big 3x3 convolutions); small-K GEMMs are bound by their epilogue / L2 traffic and lose a little.
+  // RCDM_GEMM_PAIR = 0 never, 1 heuristic (default), 2 whenever there are >= 2 M tiles.
+  const int pair_mode = pair_enabled();
+  l->pair = (!d.no_pair && num_sms() >= 2 &&
+             ((pair_mode == 2 && m_tiles >= 2) || (pair_mode == 1 && kb >= 90 && m_tiles >= 16))) ? 1 : 0;
   {
     uint64_t dims[2] = {(uint64_t)d.Ktot, (uint64_t)d.w_rows};
     uint64_t str[1] = {(uint64_t)d.Ktot * 2};
-    uint32_t box[2] = {64, (uint32_t)bn};
+    uint32_t box[2] = {64, (uint32_t)(l->pair ? bn / 2 : bn)};
     if (!encode_tmap(&l->maps.b, d.w, 2, dims, str, box, true, err)) return false;
   }
-  const int m_tiles = has_conv ? ((d.NI + p.tn - 1) / p.tn) * p.tiles_y * p.tiles_x : (d.M + 127) / 128;
-  p.num_m_tiles = m_tiles;
+  p.num_m_tiles = l->pair ? (m_tiles + 1) / 2 : m_tiles;  // pair mode: counted in 256-row tile pairs
   p.num_n_tiles = (d.N + bn - 1) / bn;
   const int tiles = p.num_m_tiles * p.num_n_tiles;
-  const int sms = num_sms();
-  l->grid = dim3(tiles < sms ? tiles : sms, 1, 1);
+  const int sms = l->pair ? num_sms() / 2 : num_sms();    // workers: CTAs or CTA pairs
+  const int cta_per_worker = l->pair ? 2 : 1;
+  l->grid = dim3((tiles < sms ? tiles : sms) * cta_per_worker, 1, 1);
+  // ---- stream-K when data-parallel tiling leaves the last wave (or most of the GPU) idle
+  p.sk = 0;
+  const bool vec_ok = (d.N % 8 == 0) && (d.ldo % 8 == 0) && (!d.res || d.ldr % 8 == 0);
+  const int min_saving = sk_min_saving();
+  if (min_saving > 0 && vec_ok && !d.no_sk && g_sk_ws && sms * cta_per_worker <= g_sk_slots && tiles % sms != 0) {
+    const double waves = (double)tiles / sms;
+    const double saving_kb = (std::ceil(waves) - waves) * p.num_kb;
+    if (saving_kb >= min_saving && (long long)tiles * p.num_kb >= 4LL * sms) {
+      p.sk = 1;
+      p.sk_ws = g_sk_ws;
+      p.sk_flags = g_sk_flags;
+      l->grid = dim3(sms * cta_per_worker, 1, 1);
+    }
+  }
   return true;
 }
 
 template <typename T, int BN> static void launch_one(const GemmLaunch& l, cudaStream_t s) {
-  launch_k(gemm_tcgen05_kernel<T, BN>, l.grid, dim3(320), GemmCfg<BN>::SMEM_BYTES, s, l.maps, l.p);
+  if (!l.pair) {
+    launch_k(gemm_tcgen05_kernel<T, BN, false>, l.grid, dim3(320), GemmCfg<BN, false>::SMEM_BYTES, s, l.maps, l.p);
+    return;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = l.grid;
+  cfg.blockDim = dim3(320);
+  cfg.dynamicSmemBytes = GemmCfg<BN, true>::SMEM_BYTES;
+  cfg.stream = s;
+  cudaLaunchAttribute at[2];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 2;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
+  cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<T, BN, true>, l.maps, l.p);
 }
 
 void gemm_launch(const GemmLaunch& l, cudaStream_t s) {
@@ -219,11 +303,16 @@ void gemm_launch(const GemmLaunch& l, cudaStream_t s) {
 }
 
 template <typename T, int BN> static cudaError_t set_attr() {
-  return cudaFuncSetAttribute(gemm_tcgen05_kernel<T, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                              GemmCfg<BN>::SMEM_BYTES);
+  cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_kernel<T, BN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       GemmCfg<BN, false>::SMEM_BYTES);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(gemm_tcgen05_kernel<T, BN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             GemmCfg<BN, true>::SMEM_BYTES);
+  return e;
 }
 
 bool gemm_setup_attributes(std::string* err) {
+  if (!sk_alloc(err)) return false;
   cudaError_t e = pdl_upload_mode(pdl_mode() == 2);
   if (e == cudaSuccess) e = set_attr<__half, 64>();
   if (e == cudaSuccess) e = set_attr<__half, 128>();

@@ -47,6 +47,47 @@ struct GemmParams {
   const void* res;    // residual [M, ldr] or nullptr (may alias out)
   int ldr;
   int geglu;          // 1: out[m, j] = (acc[j] + b[j]) * gelu(acc[BN/2 + j] + b[BN/2 + j]) per tile
+  // stream-K: the (tile, k-block) iteration space is cut into gridDim.x equal contiguous ranges, so a GEMM whose
+  // tile count does not fill the SMs evenly still keeps every tensor core busy.  A CTA whose range starts inside a
+  // tile dumps that partial accumulator (fp32) to sk_ws[blockIdx.x] and raises sk_flags[blockIdx.x]; the CTA that
+  // owns the tile's first k-block adds the partials of the following CTAs (fixed order => deterministic) and runs
+  // the normal epilogue.  Requires all CTAs co-resident (grid <= #SMs, 1 CTA/SM).
+  int sk;
+  float* sk_ws;         // [gridDim.x][128 * BN]
+  unsigned* sk_flags;   // [gridDim.x], zero at rest
+};
+
+// Work decomposition shared by the three warp roles (they must enumerate identical sequences).
+struct GemmWork {
+  int sk, num_tiles, num_kb, step, tile;
+  long long u, u_end;
+  __device__ GemmWork(const GemmParams& p, int bid, int nblk) {
+    sk = p.sk;
+    num_tiles = p.num_m_tiles * p.num_n_tiles;
+    num_kb = p.num_kb;
+    step = nblk;
+    tile = bid;
+    const long long U = (long long)num_tiles * num_kb;
+    u = U * bid / nblk;
+    u_end = U * (bid + 1) / nblk;
+  }
+  __device__ bool next(int& t, int& kb0, int& kb1) {
+    if (!sk) {
+      if (tile >= num_tiles) return false;
+      t = tile;
+      kb0 = 0;
+      kb1 = num_kb;
+      tile += step;
+      return true;
+    }
+    if (u >= u_end) return false;
+    t = (int)(u / num_kb);
+    kb0 = (int)(u - (long long)t * num_kb);
+    const long long len = (u_end - u) < (long long)(num_kb - kb0) ? (u_end - u) : (long long)(num_kb - kb0);
+    kb1 = kb0 + (int)len;
+    u += len;
+    return true;
+  }
 };
 
 struct GemmMaps {
@@ -54,11 +95,15 @@ struct GemmMaps {
   CUtensorMap b;
 };
 
-template <int BN> struct GemmCfg {
+// PAIR = true: CTA-pair kernel (cluster of 2, tcgen05 cta_group::2).  The pair computes a 256 x BN tile: CTA r holds A
+// rows [128r, 128r+128) and B rows [r*BN/2, (r+1)*BN/2) in its own shared memory and its 128 accumulator rows in its own
+// TMEM.  Per MMA the SM then ingests 16 KB + BN*64 B instead of 16 KB + BN*128 B: the L2 -> SM port (~64 B/clk), not
+// the tensor pipe, bounds the single-CTA kernel (128x160: 115 B/clk at full MMA rate; pair 256x160: 83 B/clk).
+template <int BN, bool PAIR = false> struct GemmCfg {
   static constexpr int BM = 128, BK = 64;
-  static constexpr int STAGES = (BN <= 64) ? 6 : 5;
+  static constexpr int STAGES = PAIR ? (BN <= 64 ? 8 : BN <= 128 ? 7 : 6) : ((BN <= 64) ? 6 : 5);
   static constexpr int A_BYTES = BM * BK * 2;
-  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int B_BYTES = (PAIR ? BN / 2 : BN) * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   // 8 epilogue warps, each with a private slab: 32 rows x (BN/2 cols * 2 B + 16 B pad)
   static constexpr int SLAB_BYTES = 32 * (BN + 16);
@@ -74,10 +119,16 @@ template <int BN> struct GemmCfg {
 // Persistent, warp-specialised: grid = min(#tiles, #SMs), one CTA per SM.  Tiles are visited round-robin
 // (n fastest, so CTAs running concurrently share A rows in L2).  The TMA producer runs ahead across tile
 // boundaries; two TMEM accumulators let the MMA warp start tile i+1 while the epilogue warps drain tile i.
-template <typename T, int BN>
+template <typename T, int BN, bool PAIR>
 __global__ void __launch_bounds__(320, 1)
 gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, PAIR>;
+  // pair mode: the work decomposition runs over PAIRS (p.num_m_tiles counts 256-row tile pairs); this CTA's rows are
+  // m_tile = 2 * pair_tile + rank
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+  const int wid = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;        // worker (CTA or pair) index
+  const int nworkers = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int sk_stride = PAIR ? 2 : 1;                                     // stream-K slots: one per CTA
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -94,7 +145,6 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int num_tiles = p.num_m_tiles * p.num_n_tiles;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&maps.b);
@@ -108,15 +158,17 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
       }
       for (int i = 0; i < 2; ++i) {
         mbar_init(&tmem_full_bar[i], 1);
-        mbar_init(&tmem_empty_bar[i], 256);
+        mbar_init(&tmem_empty_bar[i], PAIR ? 512 : 256);  // pair: the leader's barrier collects both CTAs' epilogues
       }
       fence_mbar_init();
     }
     __syncwarp();
-    tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+    if constexpr (PAIR) tmem_alloc_2cta<Cfg::TMEM_COLS>(tmem_slot);
+    else tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
   }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (PAIR) cluster_sync_all();  // the peer's barriers are initialised before anything signals them
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   pdl_sync();  // everything above overlapped the previous kernel's tail; global memory is touched only below
@@ -126,44 +178,70 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
     if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int n_tile = tile % p.num_n_tiles, m_tile = tile / p.num_n_tiles;
+      GemmWork work(p, wid, nworkers);
+      int tile, kb0, kb1;
+      while (work.next(tile, kb0, kb1)) {
+        const int n_tile = tile % p.num_n_tiles;
+        const int m_tile = PAIR ? 2 * (tile / p.num_n_tiles) + (int)rank : tile / p.num_n_tiles;
         int t = m_tile;  // conv tile origin (only used by conv segments)
         const int tx = t % p.tiles_x;
         t /= p.tiles_x;
         const int ty = t % p.tiles_y;
         const int tb = t / p.tiles_y;
         const int x0 = tx * p.tw, y0 = ty * p.th, n0 = tb * p.tn;
-        int kb = 0;
-        for (int s = 0; s < p.nseg; ++s) {
-          const GemmSeg sg = p.seg[s];
-          const int ntap = (sg.mode == SEG_PLAIN) ? 1 : 9;
-          for (int tap = 0; tap < ntap; ++tap) {
-            int mi = sg.tmap, dx = 0, dy = 0;
-            if (sg.mode == SEG_CONV3) {
-              dy = tap / 3 - 1;
-              dx = tap % 3 - 1;
-            } else if (sg.mode == SEG_CONV3S2) {
-              const int ky = tap / 3, kx = tap % 3;
-              const int py = (ky + 1) & 1, px = (kx + 1) & 1;  // parity of (2y + ky - 1)
-              dy = (ky == 0) ? -1 : 0;
-              dx = (kx == 0) ? -1 : 0;
-              mi = sg.tmap + py * 2 + px;
-            }
-            for (int c = 0; c < sg.cblocks; ++c, ++kb) {
-              mbar_wait(&empty_bar[stage], phase ^ 1);
-              mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
-              void* sa = smem_a + stage * Cfg::A_BYTES;
-              void* sb = smem_b + stage * Cfg::B_BYTES;
-              if (sg.mode == SEG_PLAIN)
-                tma_load_2d(sa, &maps.a[mi], &full_bar[stage], c * 64, m_tile * 128);
-              else
-                tma_load_4d(sa, &maps.a[mi], &full_bar[stage], c * 64, x0 + dx, y0 + dy, n0);
-              tma_load_2d(sb, &maps.b, &full_bar[stage], kb * 64, n_tile * BN);
-              if (++stage == STAGES) {
-                stage = 0;
-                phase ^= 1;
-              }
+        // decode kb0 -> (segment, tap, channel block)
+        int s = 0, tap = 0, c = 0;
+        {
+          int rem = kb0;
+          for (; s < p.nseg - 1; ++s) {
+            const int n = (p.seg[s].mode == SEG_PLAIN ? 1 : 9) * p.seg[s].cblocks;
+            if (rem < n) break;
+            rem -= n;
+          }
+          tap = rem / p.seg[s].cblocks;
+          c = rem - tap * p.seg[s].cblocks;
+        }
+        GemmSeg sg = p.seg[s];
+        for (int kb = kb0; kb < kb1; ++kb) {
+          int mi = sg.tmap, dx = 0, dy = 0;
+          if (sg.mode == SEG_CONV3) {
+            dy = tap / 3 - 1;
+            dx = tap % 3 - 1;
+          } else if (sg.mode == SEG_CONV3S2) {
+            const int ky = tap / 3, kx = tap % 3;
+            const int py = (ky + 1) & 1, px = (kx + 1) & 1;  // parity of (2y + ky - 1)
+            dy = (ky == 0) ? -1 : 0;
+            dx = (kx == 0) ? -1 : 0;
+            mi = sg.tmap + py * 2 + px;
+          }
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          void* sa = smem_a + stage * Cfg::A_BYTES;
+          void* sb = smem_b + stage * Cfg::B_BYTES;
+          if constexpr (PAIR) {
+            // both CTAs' loads complete on the LEADER's full barrier (the leader alone issues the MMA)
+            if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
+            if (sg.mode == SEG_PLAIN)
+              tma_load_2d_2sm(sa, &maps.a[mi], &full_bar[stage], c * 64, m_tile * 128);
+            else
+              tma_load_4d_2sm(sa, &maps.a[mi], &full_bar[stage], c * 64, x0 + dx, y0 + dy, n0);
+            tma_load_2d_2sm(sb, &maps.b, &full_bar[stage], kb * 64, n_tile * BN + (int)rank * (BN / 2));
+          } else {
+            mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+            if (sg.mode == SEG_PLAIN)
+              tma_load_2d(sa, &maps.a[mi], &full_bar[stage], c * 64, m_tile * 128);
+            else
+              tma_load_4d(sa, &maps.a[mi], &full_bar[stage], c * 64, x0 + dx, y0 + dy, n0);
+            tma_load_2d(sb, &maps.b, &full_bar[stage], kb * 64, n_tile * BN);
+          }
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+          if (++c == sg.cblocks) {  // advance (segment, tap, channel block)
+            c = 0;
+            if (++tap == (sg.mode == SEG_PLAIN ? 1 : 9)) {
+              tap = 0;
+              if (s + 1 < p.nseg) sg = p.seg[++s];
             }
           }
         }
@@ -171,36 +249,44 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
     }
   } else if (warp == 1) {
     // =================================== MMA issuer ===================================
-    if (elect_one()) {
-      constexpr uint32_t idesc = umma_idesc_f16(DT<T>::umma_fmt, 128, BN, 0, 0);
+    if ((!PAIR || rank == 0) && elect_one()) {
+      constexpr uint32_t idesc = umma_idesc_f16(DT<T>::umma_fmt, PAIR ? 256 : 128, BN, 0, 0);
+      // K-major, 128B swizzle: rows at 128 B, 8-row groups at 1024 B; +32 B per 16-element K step (address field is
+      // bytes >> 4).  (Unrolling this loop over the stages with compile-time descriptors was measured: no gain for
+      // large K - the issue thread is not the limiter - and register spills in the epilogue for small K.)
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      GemmWork work(p, wid, nworkers);
+      int tile, kb0, kb1;
+      for (; work.next(tile, kb0, kb1); ++it) {
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
         mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);  // epilogue has drained this accumulator
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * Cfg::ACC_STRIDE;
-        for (int kb = 0; kb < p.num_kb; ++kb) {
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t a_addr = smem_u32(smem_a + stage * Cfg::A_BYTES);
           const uint32_t b_addr = smem_u32(smem_b + stage * Cfg::B_BYTES);
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
-            // K-major, 128B swizzle: rows at 128 B, 8-row groups at 1024 B; +32 B per 16-element K step
             const uint64_t ad = umma_smem_desc(a_addr + k * 32, 16, 1024, UMMA_SWIZZLE_128B);
             const uint64_t bd = umma_smem_desc(b_addr + k * 32, 16, 1024, UMMA_SWIZZLE_128B);
-            umma_f16_ss(d_tmem, ad, bd, idesc, (kb | k) != 0);
+            if constexpr (PAIR) umma_f16_ss_2cta(d_tmem, ad, bd, idesc, ((kb - kb0) | k) != 0);
+            else umma_f16_ss(d_tmem, ad, bd, idesc, ((kb - kb0) | k) != 0);
           }
-          umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs have read it
+          // frees the smem slot (in both CTAs of a pair) when these MMAs have read it
+          if constexpr (PAIR) umma_commit_2cta(&empty_bar[stage]);
+          else umma_commit(&empty_bar[stage]);
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
           }
         }
-        umma_commit(&tmem_full_bar[acc]);
+        if constexpr (PAIR) umma_commit_2cta(&tmem_full_bar[acc]);
+        else umma_commit(&tmem_full_bar[acc]);
       }
     }
   } else {
@@ -217,6 +303,7 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
     constexpr int OUT_W = BN;            // accumulator columns per tile
     constexpr int HALF = BN / 2;         // accumulator columns per warp (plain) ...
     constexpr int W_COLS = HALF;         // max output columns per warp (GEGLU uses HALF / 2)
+    constexpr int NCH = HALF / 16;       // 16-column TMEM chunks per warp
     constexpr int PITCH = W_COLS * 2 + 16;
     uint8_t* slab = staging + (size_t)(warp - 2) * Cfg::SLAB_BYTES;
     const int n_total = p.geglu ? p.N / 2 : p.N;
@@ -227,12 +314,107 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
     const bool l_active = l_row < RPI;
     constexpr int MAX_PASS = (BN == 160) ? 11 : 8;
     int it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-      const int n_tile = tile % p.num_n_tiles, m_tile = tile / p.num_n_tiles;
+    GemmWork work(p, wid, nworkers);
+    int tile, kb0, kb1;
+    // "accumulator drained": in a pair every epilogue thread of both CTAs arrives on the LEADER's barrier
+    auto release_acc = [&](int acc) {
+      tc_fence_before();
+      if constexpr (PAIR) mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_empty_bar[acc]), 0));
+      else mbar_arrive(&tmem_empty_bar[acc]);
+    };
+    for (; work.next(tile, kb0, kb1); ++it) {
+      const int n_tile = tile % p.num_n_tiles;
+      const int m_tile = PAIR ? 2 * (tile / p.num_n_tiles) + (int)rank : tile / p.num_n_tiles;
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       const uint32_t taddr = tmem_base + acc * Cfg::ACC_STRIDE + (uint32_t(q * 32) << 16);
       const int m_warp = m_tile * 128 + q * 32;
+      if (kb0 > 0) {
+        // ---- stream-K partial: this CTA's range began inside the tile -> dump the fp32 accumulator, raise the flag
+        mbar_wait(&tmem_full_bar[acc], acc_phase);
+        tc_fence_after();
+        // workspace layout = the warps' own access order: [slot][q][hs][16-col chunk][4 x uint4][lane] -> every
+        // store / load instruction of a warp covers 512 contiguous bytes
+        uint4* ws = reinterpret_cast<uint4*>(p.sk_ws) + (size_t)blockIdx.x * (128 * BN / 4) +
+                    (size_t)(q * 2 + hs) * (NCH * 4 * 32) + lane;
+#pragma unroll 1
+        for (int ch = 0; ch < NCH; ++ch) {
+          uint32_t r[16];
+          tmem_ld16(taddr + hs * HALF + ch * 16, r);
+          tmem_wait_ld();
+#pragma unroll
+          for (int g = 0; g < 4; ++g)
+            __stcg(ws + (ch * 4 + g) * 32, make_uint4(r[g * 4], r[g * 4 + 1], r[g * 4 + 2], r[g * 4 + 3]));
+        }
+        release_acc(acc);
+        asm volatile("bar.sync 1, 256;" ::: "memory");  // all 8 epilogue warps have stored their slice
+        if (warp == 2 && lane == 0) {
+          __threadfence();
+          asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p.sk_flags + blockIdx.x), "r"(1u) : "memory");
+        }
+        continue;
+      }
+      // stream-K head: the CTAs after this one hold the rest of the tile's K range
+      int ncontrib = 0;
+      if (p.sk && kb1 < p.num_kb) {
+        const long long U = (long long)work.num_tiles * p.num_kb, tile_end = (long long)(tile + 1) * p.num_kb;
+        int j = wid + 1;
+        while (j < nworkers && U * j / nworkers < tile_end) ++j;
+        ncontrib = j - wid - 1;
+      }
+      // Fix-up pre-pass (at most one tile per CTA): wait for the contributors' flags, add their partials into the
+      // TMEM accumulator (all NCH*4 16-byte loads of a contributor in flight at once), re-arm the flags; the normal
+      // epilogue below then runs unchanged.
+      auto sk_fixup = [&]() {
+        if (ncontrib == 0) return;
+        if (lane == 0) {
+          for (int j = 1; j <= ncontrib; ++j) {
+            unsigned spins = 0, seen = 0;
+            while (true) {
+              asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(p.sk_flags + blockIdx.x + j * sk_stride) : "memory");
+              if (seen) break;
+              if (++spins > (1u << 26)) {
+                printf("rcdm: stream-K partial never arrived (block %d waits for %d)\n", blockIdx.x, blockIdx.x + j * sk_stride);
+                __trap();
+              }
+            }
+          }
+        }
+        __syncwarp();
+        for (int j = 1; j <= ncontrib; ++j) {
+          const uint4* src = reinterpret_cast<const uint4*>(p.sk_ws) + (size_t)(blockIdx.x + j * sk_stride) * (128 * BN / 4) +
+                             (size_t)(q * 2 + hs) * (NCH * 4 * 32) + lane;
+          uint4 pr[NCH * 4];  // every 16-byte load of this contributor in flight at once
+#pragma unroll
+          for (int i = 0; i < NCH * 4; ++i) pr[i] = __ldcg(src + i * 32);
+#pragma unroll
+          for (int ch = 0; ch < NCH; ++ch) {
+            uint32_t r[16];
+            tmem_ld16(taddr + hs * HALF + ch * 16, r);
+            tmem_wait_ld();
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              const uint4 v = pr[ch * 4 + g];
+              r[g * 4] = __float_as_uint(__uint_as_float(r[g * 4]) + __uint_as_float(v.x));
+              r[g * 4 + 1] = __float_as_uint(__uint_as_float(r[g * 4 + 1]) + __uint_as_float(v.y));
+              r[g * 4 + 2] = __float_as_uint(__uint_as_float(r[g * 4 + 2]) + __uint_as_float(v.z));
+              r[g * 4 + 3] = __float_as_uint(__uint_as_float(r[g * 4 + 3]) + __uint_as_float(v.w));
+            }
+            tmem_st16(taddr + hs * HALF + ch * 16, r);
+          }
+        }
+        tmem_wait_st();
+        tc_fence_before();
+        asm volatile("bar.sync 1, 256;" ::: "memory");  // all partials consumed; other warps' columns are final
+        tc_fence_after();
+        if (warp == 2 && lane == 0)
+          for (int j = 1; j <= ncontrib; ++j) p.sk_flags[blockIdx.x + j * sk_stride] = 0;  // re-arm for the next launch
+      };
+      if (ncontrib > 0) {  // stream-K head (rare): fold the partials in first, while no prefetched residual is live
+        mbar_wait(&tmem_full_bar[acc], acc_phase);
+        tc_fence_after();
+        sk_fixup();
+      }
       if (vec_ok) {
         const int n_warp = n_tile * (p.geglu ? HALF : OUT_W) + hs * wcols;  // first output column of this warp
         const bool chunk_ok = l_active && (n_warp + l_chunk * 8 < n_total);
@@ -299,8 +481,7 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
             *reinterpret_cast<uint4*>(slab + lane * PITCH + c * 2 + 16) = pack8<T>(v + 8);
           }
         }
-        tc_fence_before();
-        mbar_arrive(&tmem_empty_bar[acc]);  // accumulator drained: the MMA warp may reuse it
+        release_acc(acc);  // accumulator drained: the MMA warp may reuse it
         __syncwarp();
         // ---- phase 2
         if (chunk_ok) {
@@ -346,15 +527,18 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
             }
           }
         }
-        tc_fence_before();
-        mbar_arrive(&tmem_empty_bar[acc]);
+        release_acc(acc);
       }
     }
   }
-  __syncthreads();
+  tc_fence_before();
+  __syncwarp();
+  if constexpr (PAIR) cluster_sync_all();  // neither CTA may exit while its peer can still touch its smem / barriers
+  else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+    if constexpr (PAIR) tmem_dealloc_2cta<Cfg::TMEM_COLS>(tmem_base);
+    else tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
   }
 }
 

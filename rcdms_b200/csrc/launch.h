@@ -58,17 +58,22 @@ struct GemmDesc {
   int ldr;
   int geglu;
   int force_bn;  // 0 = heuristic
+  int no_sk;     // 1 = never use the stream-K decomposition for this launch
+  int no_pair;   // 1 = never use the CTA-pair (cta_group::2) kernel for this launch
 };
 struct GemmLaunch {
   GemmMaps maps;
   GemmParams p;
   dim3 grid;
   int bn, dt;
+  int pair;  // 1 = CTA-pair kernel (cluster of 2, 256-row tiles)
 };
 bool gemm_prepare(const GemmDesc& d, GemmLaunch* l, std::string* err);
 void gemm_launch(const GemmLaunch& l, cudaStream_t s);
 void gemm_simple_launch(const GemmDesc& d, cudaStream_t s);  // CUDA-core debug path (same semantics)
-bool gemm_setup_attributes(std::string* err);                // opt-in dynamic smem; call once per process/device
+bool gemm_setup_attributes(std::string* err);
+int gemm_set_pair(int on);                                    // CTA-pair kernel on/off; returns the previous value
+int gemm_set_sk_min(int k_blocks);                           // stream-K threshold (0 = off); returns the previous value                // opt-in dynamic smem; call once per process/device
 constexpr int GEGLU_BN = 128;
 
 // ---- attention ---------------------------------------------------------------------------------------

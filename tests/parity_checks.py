@@ -195,6 +195,14 @@ def all_op_checks(dtypes=(torch.float16, torch.bfloat16), quick=False):
             yield lambda bn=bn, dt=dt: check_linear(512, 320, 256, dt, tile_n=bn)
         yield lambda dt=dt: check_linear(384, 192, 320, dt, bias=False)
         yield lambda dt=dt: check_linear(40960, 320, 1280, dt, residual=True)
+        # shapes whose tile count does not fill the SMs evenly -> stream-K decomposition (gemm_host.cu)
+        yield lambda dt=dt: check_linear(640, 1280, 5120, dt, residual=True)
+        yield lambda dt=dt: check_linear(2560, 1280, 5120, dt, residual=True)
+        yield lambda dt=dt: check_linear(10240, 640, 2560, dt, bias=False)
+        yield lambda dt=dt: check_conv3x3(10, 16, 16, 1280, 1280, 1, dt, residual=True)
+        yield lambda dt=dt: check_conv3x3(10, 8, 8, 1280, 640, 1, dt)
+        yield lambda dt=dt: check_conv3x3(10, 16, 16, 640, 1280, 2, dt)
+        yield lambda dt=dt: check_geglu(640, 640, dt)
         yield lambda dt=dt: check_linear(300, 320, 64, dt, simple=True)
         for (M, C) in [(256, 64), (1024, 320), (100, 128)]:
             yield lambda M=M, C=C, dt=dt: check_geglu(M, C, dt)
