@@ -139,6 +139,18 @@ RCDM_API int rcdm_denoise_loop(rcdm_unet* h, const void* latents_dev, int latent
 /* out[M,N] = A[M,K] W[N,K]^T (+bias fp32[N]) (+residual[M,N]); geglu: W/bias rows packed by rcdm_pack_geglu */
 RCDM_API int rcdm_gemm(int dtype, const void* a_dev, const void* w_dev, const float* bias_dev, const void* residual_dev,
               void* out_dev, int M, int N, int K, int geglu, int tile_n /*0 = auto*/, int simple, void* stream);
+/* same GEMM, plus per-row (sum, sum of squares) partials of the rounded output: stats_dev = float2[parts][M]
+ * (producer side of the folded LayerNorm; replaces the statistics pass of attention.py:412,429,435) */
+RCDM_API int rcdm_gemm_rowstats(int dtype, const void* a_dev, const void* w_dev, const float* bias_dev,
+                                const void* residual_dev, void* out_dev, int M, int N, int K, void* stats_dev,
+                                int* parts_out, void* stream);
+/* out = (LayerNorm(x; gamma, beta, eps) [+ pe[(row / rows_per_frame) % frames]]) W^T + bias with the normalisation
+ * folded around the tensor-core GEMM; geglu != 0: W / bias packed by rcdm_pack_geglu, gate applied (N/2 columns out).
+ * Replaces nn.LayerNorm -> Linear (attention.py:487-522, motion_module.py:236-246,301-311). */
+RCDM_API size_t rcdm_linear_ln_scratch_bytes(int M, int N, int K, int frames);
+RCDM_API int rcdm_linear_ln(int dtype, const void* x_dev, const void* w_dev, const float* gamma_dev, const float* beta_dev,
+                            const float* pe_dev, const float* bias_dev, void* out_dev, int M, int N, int K, int geglu,
+                            int frames, int rows_per_frame, float eps, void* scratch_dev, void* stream);
 RCDM_API int rcdm_pack_geglu(int dtype, const void* w_dev, const float* bias_dev, void* w_out_dev, float* bias_out_dev, int N,
                     int K, void* stream);
 /* 3x3 conv, pad 1, stride 1|2, channels-last x [n,h,w,cin], w_packed [cout, 9*cin] (tap-major) */

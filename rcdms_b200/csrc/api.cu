@@ -457,6 +457,103 @@ int rcdm_gemm(int dtype, const void* a_dev, const void* w_dev, const float* bias
   API_END
 }
 
+// GEMM whose epilogue also emits the per-row (sum, sum of squares) partials of its rounded output (producer side of
+// the folded LayerNorm); stats_dev: float2[parts][M], *parts_out = number of column parts written
+int rcdm_gemm_rowstats(int dtype, const void* a_dev, const void* w_dev, const float* bias_dev, const void* residual_dev,
+                       void* out_dev, int M, int N, int K, void* stats_dev, int* parts_out, void* stream) {
+  API_BEGIN
+  if (!dt16(dtype)) return set_err("rcdm_gemm_rowstats: dtype must be f16/bf16");
+  if (!stats_dev) return set_err("null argument");
+  if (ensure_device_ready()) return 1;
+  GemmDesc d;
+  memset(&d, 0, sizeof d);
+  d.dt = dtype;
+  d.M = M;
+  d.N = N;
+  d.nseg = 1;
+  d.seg[0] = ASeg{SEG_PLAIN, a_dev, K, K, 0, 0, 0};
+  d.w = w_dev;
+  d.Ktot = K;
+  d.w_rows = N;
+  d.out = out_dev;
+  d.ldo = N;
+  d.bias = bias_dev;
+  d.res = residual_dev;
+  d.ldr = N;
+  d.stats_out = reinterpret_cast<float2*>(stats_dev);
+  if (parts_out) *parts_out = gemm_stats_parts(N);
+  GemmLaunch l;
+  std::string e;
+  if (!gemm_prepare(d, &l, &e)) return set_err(e);
+  gemm_launch(l, reinterpret_cast<cudaStream_t>(stream));
+  g_launches++;
+  return check_launch("rcdm_gemm_rowstats");
+  API_END
+}
+
+size_t rcdm_linear_ln_scratch_bytes(int M, int N, int K, int frames) {
+  return ((size_t)N * K * 2 + 255) / 256 * 256 + ((size_t)(frames < 1 ? 1 : frames) * N * 4 + 255) / 256 * 256 +
+         (size_t)M * 8 + 256;
+}
+
+// out = (LayerNorm(x; gamma, beta, eps) [+ pe[frame(row)]]) W^T + bias, with the LayerNorm folded around the GEMM
+// (weights * gamma, epilogue rstd * (acc - mean * u) + c).  geglu != 0: W / bias rows packed by rcdm_pack_geglu and the
+// GEGLU gate applied (out has N/2 columns).  frame(row) = (row / rows_per_frame) % frames.
+int rcdm_linear_ln(int dtype, const void* x_dev, const void* w_dev, const float* gamma_dev, const float* beta_dev,
+                   const float* pe_dev, const float* bias_dev, void* out_dev, int M, int N, int K, int geglu, int frames,
+                   int rows_per_frame, float eps, void* scratch_dev, void* stream) {
+  API_BEGIN
+  if (!dt16(dtype)) return set_err("rcdm_linear_ln: dtype must be f16/bf16");
+  if (!x_dev || !w_dev || !gamma_dev || !beta_dev || !out_dev || !scratch_dev) return set_err("null argument");
+  if (frames < 1) frames = 1;
+  if (frames > 5) return set_err("rcdm_linear_ln: at most 5 frames");
+  if (ensure_device_ready()) return 1;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  unsigned char* sc = reinterpret_cast<unsigned char*>(scratch_dev);
+  void* wf = sc;
+  size_t off = ((size_t)N * K * 2 + 255) / 256 * 256;
+  float* c = reinterpret_cast<float*>(sc + off);
+  off += ((size_t)frames * N * 4 + 255) / 256 * 256;
+  float2* stats = reinterpret_cast<float2*>(sc + off);
+  const int fb = (N * 32 + 255) / 256, rb = (M * 32 + 255) / 256;
+  if (dtype == DT_F16) {
+    fold_ln_kernel<__half><<<fb, 256, 0, st>>>(reinterpret_cast<const __half*>(w_dev), reinterpret_cast<__half*>(wf),
+                                               gamma_dev, beta_dev, pe_dev, bias_dev, c, N, K, frames);
+    rowstats_kernel<__half><<<rb, 256, 0, st>>>(reinterpret_cast<const __half*>(x_dev), stats, M, K);
+  } else {
+    fold_ln_kernel<__nv_bfloat16><<<fb, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(w_dev),
+                                                      reinterpret_cast<__nv_bfloat16*>(wf), gamma_dev, beta_dev, pe_dev,
+                                                      bias_dev, c, N, K, frames);
+    rowstats_kernel<__nv_bfloat16><<<rb, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x_dev), stats, M, K);
+  }
+  GemmDesc d;
+  memset(&d, 0, sizeof d);
+  d.dt = dtype;
+  d.M = M;
+  d.N = N;
+  d.nseg = 1;
+  d.seg[0] = ASeg{SEG_PLAIN, x_dev, K, K, 0, 0, 0};
+  d.w = wf;
+  d.Ktot = K;
+  d.w_rows = N;
+  d.out = out_dev;
+  d.ldo = geglu ? N / 2 : N;
+  d.geglu = geglu;
+  d.stats_in = stats;
+  d.stats_parts = 1;
+  d.ln_c = c;
+  d.ln_frames = frames;
+  d.ln_rows_per_frame = rows_per_frame;
+  d.ln_eps = eps;
+  GemmLaunch l;
+  std::string e;
+  if (!gemm_prepare(d, &l, &e)) return set_err(e);
+  gemm_launch(l, st);
+  g_launches += 3;
+  return check_launch("rcdm_linear_ln");
+  API_END
+}
+
 int rcdm_pack_geglu(int dtype, const void* w_dev, const float* bias_dev, void* w_out_dev, float* bias_out_dev, int N,
                     int K, void* stream) {
   API_BEGIN

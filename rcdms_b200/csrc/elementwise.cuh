@@ -251,6 +251,64 @@ static __global__ void pack_vec_kernel(const void* __restrict__ src, int src_dt,
   dst[row] = accumulate ? dst[row] + v : v;
 }
 
+// LayerNorm fold (see GemmParams): one warp per weight row n.
+//   wf[n,k] = W[n,k] * gamma[k] - mean_k(W[n,:] * gamma)   (rounded to T; centred rows absorb the "- mean * u" term)
+//   c[f][n] = sum_k (beta[k] + pe[f][k]) * W[n,k] + bias[n]        (pe / bias optional; frames >= 1)
+template <typename T>
+__global__ void fold_ln_kernel(const T* __restrict__ W, T* __restrict__ Wf, const float* __restrict__ gamma,
+                               const float* __restrict__ beta, const float* __restrict__ pe,
+                               const float* __restrict__ bias, float* __restrict__ c, int N, int K, int frames) {
+  const int n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (n >= N) return;
+  float sg = 0.f, sb = 0.f, sp[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int k = lane; k < K; k += 32) {
+    const float w = DT<T>::to_f(W[(size_t)n * K + k]);
+    sg = fmaf(w, gamma[k], sg);
+    sb = fmaf(beta[k], w, sb);
+    if (pe) {
+#pragma unroll
+      for (int f = 0; f < 5; ++f)
+        if (f < frames) sp[f] = fmaf(pe[(size_t)f * K + k], w, sp[f]);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    sg += __shfl_xor_sync(0xffffffffu, sg, o);
+    sb += __shfl_xor_sync(0xffffffffu, sb, o);
+#pragma unroll
+    for (int f = 0; f < 5; ++f) sp[f] += __shfl_xor_sync(0xffffffffu, sp[f], o);
+  }
+  const float centre = sg / (float)K;
+  for (int k = lane; k < K; k += 32)
+    Wf[(size_t)n * K + k] = DT<T>::from_f(fmaf(DT<T>::to_f(W[(size_t)n * K + k]), gamma[k], -centre));
+  if (lane == 0) {
+    const float b = bias ? bias[n] : 0.f;
+    for (int f = 0; f < frames; ++f) c[(size_t)f * N + n] = sb + sp[f < 5 ? f : 0] + b;
+  }
+}
+
+// per-row (sum, sum of squares) of a [rows, C] matrix in the single-part layout stats[0][rows] (stand-alone entry
+// point rcdm_linear_ln; inside the UNet the producing GEMM's epilogue emits the statistics)
+template <typename T>
+__global__ void rowstats_kernel(const T* __restrict__ x, float2* __restrict__ stats, int rows, int C) {
+  const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (r >= rows) return;
+  float s = 0.f, ss = 0.f;
+  for (int k = lane; k < C; k += 32) {
+    const float v = DT<T>::to_f(x[(size_t)r * C + k]);
+    s += v;
+    ss = fmaf(v, v, ss);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  }
+  if (lane == 0) stats[r] = make_float2(s, ss);
+}
+
 template <typename T>
 __global__ void cast_rows_kernel(const void* __restrict__ src, int src_dt, T* __restrict__ dst, size_t n) {
   for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (size_t)gridDim.x * blockDim.x)

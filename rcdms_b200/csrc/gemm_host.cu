@@ -135,6 +135,11 @@ static bool sk_alloc(std::string* err) {
   return true;
 }
 
+int gemm_stats_parts(int N) {  // 2 column halves per N tile of the (heuristic) tile width, see pick_bn
+  const int bn = (N % 160 == 0) ? 160 : (N <= 64 ? 64 : 128);
+  return 2 * ((N + bn - 1) / bn);
+}
+
 static int pick_bn(const GemmDesc& d) {
   if (d.force_bn) return d.force_bn;
   if (d.geglu) return GEGLU_BN;
@@ -163,6 +168,18 @@ bool gemm_prepare(const GemmDesc& d, GemmLaunch* l, std::string* err) {
   p.res = d.res;
   p.ldr = d.ldr;
   p.geglu = d.geglu;
+  p.stats_out = d.stats_out;
+  p.stats_in = d.stats_in;
+  p.stats_parts = d.stats_parts;
+  p.ln_K = d.Ktot;
+  p.ln_c = d.ln_c;
+  p.ln_frames = d.ln_frames < 1 ? 1 : d.ln_frames;
+  p.ln_rows_per_frame = d.ln_rows_per_frame < 1 ? 1 : d.ln_rows_per_frame;
+  p.ln_eps = d.ln_eps;
+  if (d.stats_in && (!d.ln_c || d.N % 8 != 0 || (d.geglu && d.N % bn != 0) || d.nseg != 1 ||
+                     d.seg[0].mode != SEG_PLAIN))
+    return fail("folded LayerNorm needs the c vector, N % 8 == 0 and a single plain K segment");
+  if (d.stats_out && (d.geglu || d.N % 8 != 0)) return fail("row statistics need a plain vectorised epilogue");
   p.tw = 1;
   p.th = 1;
   p.tn = 128;

@@ -55,6 +55,20 @@ struct GemmParams {
   int sk;
   float* sk_ws;         // [gridDim.x][128 * BN]
   unsigned* sk_flags;   // [gridDim.x], zero at rest
+  // LayerNorm folded around the GEMM (attention.py:412,429,435 / motion_module.py:226,232 precede every q/k/v and
+  // feed-forward projection):  LN(x) W^T = rstd * (x (W*gamma)^T - mean * u) + c,  u[n] = sum_k (W*gamma)[n,k],
+  // c[f][n] = sum_k (beta[k] + pe[f][k]) W[n,k] + bias[n].  The folded weight rows are additionally CENTRED
+  // (Wf[n,:] = W[n,:]*gamma - mean_k(W[n,:]*gamma)), so x Wf^T already equals x (W*gamma)^T - mean*u and the epilogue
+  // is one FMA per element: out = rstd * acc + c.  The GEMM that PRODUCES x emits per-row partial (sum, sum of
+  // squares) of its rounded outputs, one float2 per (column-tile half, row): stats_out[part][M]; the GEMM that
+  // CONSUMES x sums the parts (only rstd is needed).
+  float2* stats_out;       // producer: [2 * num_n_tiles][M], or nullptr
+  const float2* stats_in;  // consumer: [stats_parts][M], or nullptr
+  int stats_parts;
+  int ln_K;                // row length the statistics cover (= K of the consumer)
+  const float* ln_c;       // [ln_frames][accumulator columns]
+  int ln_frames, ln_rows_per_frame;
+  float ln_eps;
 };
 
 // Work decomposition shared by the three warp roles (they must enumerate identical sequences).
@@ -110,15 +124,17 @@ template <int BN, bool PAIR = false> struct GemmCfg {
   static constexpr int STAGING_BYTES = 8 * SLAB_BYTES;
   static constexpr int ACC_STRIDE = BN <= 64 ? 64 : BN <= 128 ? 128 : 256;  // TMEM columns between the 2 accumulators
   static constexpr int TMEM_COLS = 2 * ACC_STRIDE;
-  static constexpr int BIAS_BYTES = 2 * BN * 4;  // two buffers (tile parity) of BN fp32 bias values
-  static constexpr int SMEM_BYTES =
-      STAGES * STAGE_BYTES + STAGING_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + BIAS_BYTES;
+  // two buffers (tile parity) of BN fp32 epilogue values: bias, or the folded-LayerNorm vector c
+  static constexpr int BIAS_BYTES = 2 * BN * 4;
+  // the dynamic shared memory window is declared __align__(1024) (128B-swizzle atoms), so there is no alignment slack
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + 256 /*barriers*/ + BIAS_BYTES;
   static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB per-CTA shared memory limit");
 };
 
 // Persistent, warp-specialised: grid = min(#tiles, #SMs), one CTA per SM.  Tiles are visited round-robin
 // (n fastest, so CTAs running concurrently share A rows in L2).  The TMA producer runs ahead across tile
 // boundaries; two TMEM accumulators let the MMA warp start tile i+1 while the epilogue warps drain tile i.
+// 10 warps = 3 on the fullest SM sub-partition (16384 registers each) => at most 168 registers per thread.
 template <typename T, int BN, bool PAIR>
 __global__ void __launch_bounds__(320, 1)
 gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
@@ -130,8 +146,12 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
   const int nworkers = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   const int sk_stride = PAIR ? 2 : 1;                                     // stream-K slots: one per CTA
   constexpr int STAGES = Cfg::STAGES;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw;
+  if ((smem_u32(smem) & 1023u) != 0u) {  // never observed; a misaligned window would corrupt the swizzled tiles
+    if (threadIdx.x == 0) printf("rcdm: dynamic shared memory is not 1024-byte aligned\n");
+    __trap();
+  }
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + STAGES * Cfg::A_BYTES;
   uint8_t* staging = smem + STAGES * Cfg::STAGE_BYTES;
@@ -141,7 +161,7 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
   uint64_t* tmem_full_bar = bars + 2 * STAGES;       // [2]
   uint64_t* tmem_empty_bar = bars + 2 * STAGES + 2;  // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
-  float* bias_sm = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);  // [2][BN]
+  float* bias_sm = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);  // [2 parity][BN]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -415,6 +435,46 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
         tc_fence_after();
         sk_fixup();
       }
+      // folded LayerNorm (consumer side): statistics of this thread's row, summed over the producer's column parts;
+      // out = ln_a * acc + c[frame][n]   (ln_a = rstd of the row; the weights are centred, see GemmParams)
+      const bool ln = p.stats_in != nullptr;
+      float ln_a = 1.f;
+      int ln_f = 0, ln_f0 = 0;
+      // c from shared memory when the whole tile lies in one frame (always, except the 8x8 level of the temporal
+      // projections where a 128-row tile spans two frames: those read c through L1)
+      const bool ln_smem = p.ln_frames == 1 || (p.ln_rows_per_frame % 128) == 0;
+      constexpr int ST_PRE = 4;  // statistic parts fetched ahead (C = 320: 4 parts, 640: 8, 1280: 16); more would spill
+      float2 st_pre[ST_PRE];
+      const int ln_m = min(m_warp + lane, p.M - 1);
+      if (ln) {
+#pragma unroll
+        for (int pp = 0; pp < ST_PRE; ++pp)
+          if (pp < p.stats_parts) st_pre[pp] = __ldg(&p.stats_in[(size_t)pp * p.M + ln_m]);
+        if (p.ln_frames > 1) {
+          ln_f = (ln_m / p.ln_rows_per_frame) % p.ln_frames;
+          ln_f0 = (min(m_tile * 128, p.M - 1) / p.ln_rows_per_frame) % p.ln_frames;
+        }
+      }
+      // consumed only after the accumulator wait, so the L2 latency of the loads above hides behind the main loop
+      auto ln_finish = [&]() {
+        float sx = 0.f, sxx = 0.f;
+#pragma unroll
+        for (int pp = 0; pp < ST_PRE; ++pp)
+          if (pp < p.stats_parts) {
+            sx += st_pre[pp].x;
+            sxx += st_pre[pp].y;
+          }
+        for (int pp = ST_PRE; pp < p.stats_parts; ++pp) {
+          const float2 v = __ldg(&p.stats_in[(size_t)pp * p.M + ln_m]);
+          sx += v.x;
+          sxx += v.y;
+        }
+        const float inv_k = 1.0f / (float)p.ln_K;
+        const float mean = sx * inv_k;
+        const float var = fmaxf(sxx * inv_k - mean * mean, 0.f);
+        ln_a = rsqrtf(var + p.ln_eps);
+      };
+      const float* ln_crow = p.ln_c + (size_t)ln_f * p.N;  // global fallback row of c
       if (vec_ok) {
         const int n_warp = n_tile * (p.geglu ? HALF : OUT_W) + hs * wcols;  // first output column of this warp
         const bool chunk_ok = l_active && (n_warp + l_chunk * 8 < n_total);
@@ -428,27 +488,74 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
               rv[u] = *reinterpret_cast<const uint4*>(res + (size_t)(m_warp + rr) * p.ldr + n_warp + l_chunk * 8);
           }
         }
-        mbar_wait(&tmem_full_bar[acc], acc_phase);
-        tc_fence_after();
-        // ---- bias slice of this warp's column half -> smem[tile parity].  The four warps sharing `hs` write
-        // identical values (benign); filling AFTER the wait makes the parity double-buffer race-free (tile i+2
-        // cannot become ready before every thread finished phase 1 of tile i).
-        float* bsm = bias_sm + (it & 1) * BN + hs * HALF;
-        if (p.bias) {
-          if (!p.geglu) {
-            for (int i = lane; i < HALF; i += 32) bsm[i] = (n_warp + i < n_total) ? __ldg(p.bias + n_warp + i) : 0.f;
-          } else {  // packed GEGLU bias: tile-local [h (HALF) | gate (HALF)]; h/gate columns hs*wcols..+wcols
-            for (int i = lane; i < wcols; i += 32) {
-              bsm[i] = __ldg(p.bias + n_tile * BN + hs * wcols + i);
-              bsm[wcols + i] = __ldg(p.bias + n_tile * BN + HALF + hs * wcols + i);
+        // ---- epilogue vectors of this warp's column half (bias, or LN u and c): fetched into registers BEFORE the
+        // accumulator wait (latency hidden), parked in smem[tile parity] AFTER it.  The four warps sharing `hs` write
+        // identical values (benign); storing after the wait keeps the parity double-buffer race-free (tile i+2 cannot
+        // become ready before every thread finished phase 1 of tile i).
+        constexpr int PV = (HALF + 31) / 32;
+        float pre0[PV];
+        {
+          const float* v0 = ln ? p.ln_c + (size_t)ln_f0 * p.N : p.bias;
+#pragma unroll
+          for (int j = 0; j < PV; ++j) {
+            const int i = lane + j * 32;
+            pre0[j] = 0.f;
+            if (i < HALF && v0) {
+              if (!p.geglu) {
+                if (n_warp + i < n_total) pre0[j] = __ldg(v0 + n_warp + i);
+              } else {  // packed GEGLU vectors: tile-local [h (HALF) | gate (HALF)]; this warp: h/gate cols hs*wcols..
+                pre0[j] = __ldg(v0 + n_tile * BN + (i < wcols ? hs * wcols + i : HALF + hs * wcols + (i - wcols)));
+              }
             }
           }
-        } else {
-          for (int i = lane; i < HALF; i += 32) bsm[i] = 0.f;
+        }
+        mbar_wait(&tmem_full_bar[acc], acc_phase);
+        tc_fence_after();
+        if (ln) ln_finish();
+        float* bsm = bias_sm + (it & 1) * BN + hs * HALF;  // bias, or c of the tile's frame in LN mode
+#pragma unroll
+        for (int j = 0; j < PV; ++j) {
+          const int i = lane + j * 32;
+          if (i < HALF) bsm[i] = pre0[j];
         }
         __syncwarp();
-        // ---- phase 1
-        if (!p.geglu) {
+        // ---- phase 1: v = scale * acc + vec  (plain: scale = 1, vec = bias; folded LayerNorm: scale = rstd, vec = c)
+        const float scale = ln_a;
+        if (ln && !ln_smem) {
+          // rare: a 128-row tile of a temporal projection spans several frames (8x8 level, tiny test configs): the
+          // per-frame vector c comes through L1 instead of shared memory
+          if (!p.geglu) {
+#pragma unroll 1
+            for (int c = 0; c < HALF; c += 16) {
+              uint32_t r[16];
+              tmem_ld16(taddr + hs * HALF + c, r);
+              tmem_wait_ld();
+              const int col = n_tile * BN + hs * HALF + c;
+              float v[16];
+#pragma unroll
+              for (int i = 0; i < 16; ++i)
+                v[i] = fmaf(__uint_as_float(r[i]), scale, (col + i < p.N) ? __ldg(ln_crow + col + i) : 0.f);
+              *reinterpret_cast<uint4*>(slab + lane * PITCH + c * 2) = pack8<T>(v);
+              *reinterpret_cast<uint4*>(slab + lane * PITCH + c * 2 + 16) = pack8<T>(v + 8);
+            }
+          } else {
+#pragma unroll 1
+            for (int c = 0; c < HALF / 2; c += 16) {
+              uint32_t rh[16], rg[16];
+              tmem_ld16(taddr + hs * (HALF / 2) + c, rh);
+              tmem_ld16(taddr + HALF + hs * (HALF / 2) + c, rg);
+              tmem_wait_ld();
+              const int colh = n_tile * BN + hs * (HALF / 2) + c;
+              float v[16];
+#pragma unroll
+              for (int i = 0; i < 16; ++i)
+                v[i] = fmaf(__uint_as_float(rh[i]), scale, __ldg(ln_crow + colh + i)) *
+                       gelu_erf_f(fmaf(__uint_as_float(rg[i]), scale, __ldg(ln_crow + colh + HALF + i)));
+              *reinterpret_cast<uint4*>(slab + lane * PITCH + c * 2) = pack8<T>(v);
+              *reinterpret_cast<uint4*>(slab + lane * PITCH + c * 2 + 16) = pack8<T>(v + 8);
+            }
+          }
+        } else if (!p.geglu) {
 #pragma unroll 1
           for (int c = 0; c < HALF; c += 16) {
             uint32_t r[16];
@@ -458,10 +565,10 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
               const float4 b4 = *reinterpret_cast<const float4*>(bsm + c + g * 4);  // smem broadcast
-              v[g * 4] = __uint_as_float(r[g * 4]) + b4.x;
-              v[g * 4 + 1] = __uint_as_float(r[g * 4 + 1]) + b4.y;
-              v[g * 4 + 2] = __uint_as_float(r[g * 4 + 2]) + b4.z;
-              v[g * 4 + 3] = __uint_as_float(r[g * 4 + 3]) + b4.w;
+              v[g * 4] = fmaf(__uint_as_float(r[g * 4]), scale, b4.x);
+              v[g * 4 + 1] = fmaf(__uint_as_float(r[g * 4 + 1]), scale, b4.y);
+              v[g * 4 + 2] = fmaf(__uint_as_float(r[g * 4 + 2]), scale, b4.z);
+              v[g * 4 + 3] = fmaf(__uint_as_float(r[g * 4 + 3]), scale, b4.w);
             }
             *reinterpret_cast<uint4*>(slab + lane * PITCH + c * 2) = pack8<T>(v);
             *reinterpret_cast<uint4*>(slab + lane * PITCH + c * 2 + 16) = pack8<T>(v + 8);
@@ -476,7 +583,8 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
             float v[16];
 #pragma unroll
             for (int i = 0; i < 16; ++i)
-              v[i] = (__uint_as_float(rh[i]) + bsm[c + i]) * gelu_erf_f(__uint_as_float(rg[i]) + bsm[wcols + c + i]);
+              v[i] = fmaf(__uint_as_float(rh[i]), scale, bsm[c + i]) *
+                     gelu_erf_f(fmaf(__uint_as_float(rg[i]), scale, bsm[wcols + c + i]));
             *reinterpret_cast<uint4*>(slab + lane * PITCH + c * 2) = pack8<T>(v);
             *reinterpret_cast<uint4*>(slab + lane * PITCH + c * 2 + 16) = pack8<T>(v + 8);
           }
@@ -484,21 +592,63 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
         release_acc(acc);  // accumulator drained: the MMA warp may reuse it
         __syncwarp();
         // ---- phase 2
-        if (chunk_ok) {
+        if (!p.stats_out) {
+          if (chunk_ok) {
+#pragma unroll
+            for (int u = 0; u < MAX_PASS; ++u) {
+              const int rr = u * RPI + l_row;
+              if (rr < 32 && m_warp + rr < p.M) {
+                uint4 sv = *reinterpret_cast<const uint4*>(slab + rr * PITCH + l_chunk * 16);
+                if (res) {
+                  using T2 = typename DT<T>::T2;
+                  T2* a2 = reinterpret_cast<T2*>(&sv);
+                  const T2* b2 = reinterpret_cast<const T2*>(&rv[u]);
+#pragma unroll
+                  for (int i = 0; i < 4; ++i) a2[i] = __hadd2(a2[i], b2[i]);
+                }
+                *reinterpret_cast<uint4*>(out + (size_t)(m_warp + rr) * p.ldo + n_warp + l_chunk * 8) = sv;
+              }
+            }
+          }
+        } else {
+          // same stores + per-row (sum, sum of squares) of the ROUNDED outputs: every lane leaves the partial of its
+          // 8 columns in the slab chunk it has just consumed; then lane r folds the CH partials of row r in a fixed
+          // order (deterministic) and the warp writes 32 consecutive float2 of this (column half) part
 #pragma unroll
           for (int u = 0; u < MAX_PASS; ++u) {
             const int rr = u * RPI + l_row;
-            if (rr < 32 && m_warp + rr < p.M) {
-              uint4 sv = *reinterpret_cast<const uint4*>(slab + rr * PITCH + l_chunk * 16);
-              if (res) {
-                using T2 = typename DT<T>::T2;
-                T2* a2 = reinterpret_cast<T2*>(&sv);
-                const T2* b2 = reinterpret_cast<const T2*>(&rv[u]);
+            if (l_active && rr < 32) {
+              float ps = 0.f, pss = 0.f;
+              if (chunk_ok && m_warp + rr < p.M) {
+                uint4 sv = *reinterpret_cast<const uint4*>(slab + rr * PITCH + l_chunk * 16);
+                if (res) {
+                  using T2 = typename DT<T>::T2;
+                  T2* a2 = reinterpret_cast<T2*>(&sv);
+                  const T2* b2 = reinterpret_cast<const T2*>(&rv[u]);
 #pragma unroll
-                for (int i = 0; i < 4; ++i) a2[i] = __hadd2(a2[i], b2[i]);
+                  for (int i = 0; i < 4; ++i) a2[i] = __hadd2(a2[i], b2[i]);
+                }
+                *reinterpret_cast<uint4*>(out + (size_t)(m_warp + rr) * p.ldo + n_warp + l_chunk * 8) = sv;
+                float f8[8];
+                unpack8<T>(sv, f8);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                  ps += f8[i];
+                  pss = fmaf(f8[i], f8[i], pss);
+                }
               }
-              *reinterpret_cast<uint4*>(out + (size_t)(m_warp + rr) * p.ldo + n_warp + l_chunk * 8) = sv;
+              *reinterpret_cast<float2*>(slab + rr * PITCH + l_chunk * 16) = make_float2(ps, pss);
             }
+          }
+          __syncwarp();
+          {
+            float ps = 0.f, pss = 0.f;
+            for (int ch = 0; ch < CH; ++ch) {
+              const float2 t = *reinterpret_cast<const float2*>(slab + lane * PITCH + ch * 16);
+              ps += t.x;
+              pss += t.y;
+            }
+            if (m_warp + lane < p.M) p.stats_out[(size_t)(n_tile * 2 + hs) * p.M + m_warp + lane] = make_float2(ps, pss);
           }
         }
         __syncwarp();  // the slab is rewritten for the next tile

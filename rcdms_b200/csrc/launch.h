@@ -60,6 +60,12 @@ struct GemmDesc {
   int force_bn;  // 0 = heuristic
   int no_sk;     // 1 = never use the stream-K decomposition for this launch
   int no_pair;   // 1 = never use the CTA-pair (cta_group::2) kernel for this launch
+  // folded LayerNorm (see GemmParams): producer side / consumer side
+  float2* stats_out;
+  const float2* stats_in;
+  int stats_parts, ln_frames, ln_rows_per_frame;
+  const float* ln_c;
+  float ln_eps;
 };
 struct GemmLaunch {
   GemmMaps maps;
@@ -72,6 +78,7 @@ bool gemm_prepare(const GemmDesc& d, GemmLaunch* l, std::string* err);
 void gemm_launch(const GemmLaunch& l, cudaStream_t s);
 void gemm_simple_launch(const GemmDesc& d, cudaStream_t s);  // CUDA-core debug path (same semantics)
 bool gemm_setup_attributes(std::string* err);
+int gemm_stats_parts(int N);                                  // column parts a producer GEMM with N output columns emits
 int gemm_set_pair(int on);                                    // CTA-pair kernel on/off; returns the previous value
 int gemm_set_sk_min(int k_blocks);                           // stream-K threshold (0 = off); returns the previous value                // opt-in dynamic smem; call once per process/device
 constexpr int GEGLU_BN = 128;

@@ -33,12 +33,20 @@ struct Slot {  // one state-dict entry of the reference and where / how it lands
   bool loaded = false;
 };
 
+// LayerNorm folded into the projection that consumes it (gemm_tcgen05.cuh): weights pre-multiplied by gamma plus the
+// two epilogue vectors; rebuilt from the raw weights by finalize_weights whenever a state-dict entry changes.
+struct LnFold {
+  Mat wf;  // [N, K] = W * gamma with every row centred (same row packing as the raw matrix)
+  Vec c;   // [frames][N] sum_k (beta[k] + pe[f][k]) W[n, k] + bias[n]
+  int frames = 1;
+};
 struct AttW {
   Mat qkv;  // self / temporal: [3C, C]
   Mat q;    // cross: [C, C]
   Mat kv;   // cross: [2C, ctx]
   Mat out;
   Vec outb;
+  LnFold qkv_ln, q_ln;
 };
 struct ResW {
   int cin = 0, cout = 0;
@@ -54,12 +62,14 @@ struct TfW {
   Vec ng, nb, pib, ln1g, ln1b, ln2g, ln2b, ln3g, ln3b, ff1b, ff2b, pob;
   Mat pi, ff1, ff2, po;
   AttW a1, a2;
+  LnFold ff1_ln;
 };
 struct MoW {
   int C = 0;
   Vec ng, nb, pib, lng[4], lnb[4], pe[4], ffng, ffnb, ff1b, ff2b, pob;
   Mat pi, ff1, ff2, po;
   AttW att[4];
+  LnFold ff1_ln;
 };
 struct LayerW {
   ResW res;
@@ -116,6 +126,7 @@ struct rcdm_unet_impl {
   bool taps_enabled = false;
   std::map<std::string, TapInfo> taps;
   int simple = 0;
+  int ln_fold = 1;  // LayerNorm folded into the consuming GEMM (RCDM_LN_FOLD=0: separate layernorm kernels)
   // per-call inputs (read by the recorded ops)
   const void* cur_sample = nullptr;
   int cur_sample_dt = 0;

@@ -84,6 +84,14 @@ struct Builder {
     return m;
   }
 
+  LnFold fold(const Mat& w, int frames = 1) {
+    LnFold f;
+    f.wf = mat(w.rows, w.cols);
+    f.c = vec(frames * w.rows);
+    f.frames = frames;
+    return f;
+  }
+
   void resnet(const std::string& p, int cin, int cout, ResW& r) {
     const int temb = h->temb_dim;
     r.cin = cin;
@@ -143,12 +151,15 @@ struct Builder {
     slot(p + ".proj_in.weight", {C, C, 1, 1}, SLOT_MAT, t.pi.off, C);
     t.pib = vslot(p + ".proj_in.bias", C);
     attn(b + ".attn1", C, C, false, t.a1);
+    t.a1.qkv_ln = fold(t.a1.qkv);
     t.ln1g = vslot(b + ".norm1.weight", C);
     t.ln1b = vslot(b + ".norm1.bias", C);
     attn(b + ".attn2", C, h->cfg.cross_attention_dim, true, t.a2);
+    t.a2.q_ln = fold(t.a2.q);
     t.ln2g = vslot(b + ".norm2.weight", C);
     t.ln2b = vslot(b + ".norm2.bias", C);
     ff(b + ".ff", C, t.ff1, t.ff1b, t.ff2, t.ff2b);
+    t.ff1_ln = fold(t.ff1);
     t.ln3g = vslot(b + ".norm3.weight", C);
     t.ln3b = vslot(b + ".norm3.bias", C);
     t.po = mat(C, C);
@@ -169,6 +180,7 @@ struct Builder {
     for (int i = 0; i < na; ++i) {
       const std::string a = b + ".attention_blocks." + std::to_string(i);
       attn(a, C, C, false, m.att[i]);
+      m.att[i].qkv_ln = fold(m.att[i].qkv, ml);
       m.pe[i] = vec(ml * C);
       slot(a + ".pos_encoder.pe", {1, ml, C}, SLOT_VEC, m.pe[i].off);
     }
@@ -177,6 +189,7 @@ struct Builder {
       m.lnb[i] = vslot(b + ".norms." + std::to_string(i) + ".bias", C);
     }
     ff(b + ".ff", C, m.ff1, m.ff1b, m.ff2, m.ff2b);
+    m.ff1_ln = fold(m.ff1);
     m.ffng = vslot(b + ".ff_norm.weight", C);
     m.ffnb = vslot(b + ".ff_norm.bias", C);
     m.po = lin(p + ".proj_out.weight", C, C);
@@ -338,8 +351,42 @@ static void finalize_res(rcdm_unet_impl* h, const ResW& r, cudaStream_t st) {
   add_vec_kernel<<<(r.cout + 255) / 256, 256, 0, st>>>(f(r.c2b), r.shortcut ? f(r.scb) : nullptr, f(r.c2beff), r.cout);
 }
 
+static void fold_one(rcdm_unet_impl* h, const Mat& w, const LnFold& lf, const Vec& g, const Vec& b, const Vec* pe,
+                     const Vec* bias, cudaStream_t st) {
+  auto f = [&](const Vec& v) { return reinterpret_cast<float*>(h->arena + v.off); };
+  const int N = w.rows, K = w.cols;
+  const int blocks = (N * 32 + 255) / 256;
+  if (h->dt == DT_F16)
+    fold_ln_kernel<__half><<<blocks, 256, 0, st>>>(reinterpret_cast<const __half*>(h->arena + w.off),
+                                                   reinterpret_cast<__half*>(h->arena + lf.wf.off), f(g), f(b),
+                                                   pe ? f(*pe) : nullptr, bias ? f(*bias) : nullptr, f(lf.c), N, K,
+                                                   lf.frames);
+  else
+    fold_ln_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(
+        reinterpret_cast<const __nv_bfloat16*>(h->arena + w.off), reinterpret_cast<__nv_bfloat16*>(h->arena + lf.wf.off),
+        f(g), f(b), pe ? f(*pe) : nullptr, bias ? f(*bias) : nullptr, f(lf.c), N, K, lf.frames);
+}
+static void fold_tf(rcdm_unet_impl* h, const TfW& t, cudaStream_t st) {
+  fold_one(h, t.a1.qkv, t.a1.qkv_ln, t.ln1g, t.ln1b, nullptr, nullptr, st);
+  fold_one(h, t.a2.q, t.a2.q_ln, t.ln2g, t.ln2b, nullptr, nullptr, st);
+  fold_one(h, t.ff1, t.ff1_ln, t.ln3g, t.ln3b, nullptr, &t.ff1b, st);
+}
+static void fold_mo(rcdm_unet_impl* h, const MoW& m, cudaStream_t st) {
+  for (int i = 0; i < h->cfg.motion_attn_blocks; ++i)
+    fold_one(h, m.att[i].qkv, m.att[i].qkv_ln, m.lng[i], m.lnb[i], &m.pe[i], nullptr, st);
+  fold_one(h, m.ff1, m.ff1_ln, m.ffng, m.ffnb, nullptr, &m.ff1b, st);
+}
+
 static void finalize_weights(rcdm_unet_impl* h, cudaStream_t st) {
   auto f = [&](const Vec& v) { return reinterpret_cast<float*>(h->arena + v.off); };
+  for (auto* blks : {&h->down, &h->up})
+    for (auto& blk : *blks)
+      for (auto& l : blk.layers) {
+        if (l.has_tf) fold_tf(h, l.tf, st);
+        if (l.has_mo) fold_mo(h, l.mo, st);
+      }
+  fold_tf(h, h->mid_tf, st);
+  if (h->mid_has_mo) fold_mo(h, h->mid_mo, st);
   for (auto& blk : h->down)
     for (auto& l : blk.layers) finalize_res(h, l.res, st);
   for (auto& blk : h->up)
@@ -472,15 +519,28 @@ struct Planner {
     }, kind, flops, bytes, d.M, d.N, (int)k_alg);
   }
   // plain GEMM: out[M,N] = A[M,K] W^T (+bias)(+res)
+  // ln != nullptr: the input is consumed through a folded LayerNorm (statistics at stats_off, emitted by the GEMM that
+  // produced the input); emit_stats: this GEMM's output feeds a folded LayerNorm -> write its row statistics
   void linear(size_t a_off, int M, int K, const Mat& w, const Vec* bias, size_t out_off, int ldo, const size_t* res_off,
-              int geglu = 0) {
+              int geglu = 0, const LnFold* ln = nullptr, size_t stats_off = 0, bool emit_stats = false,
+              int rows_per_frame = 1) {
     GemmDesc d;
     memset(&d, 0, sizeof d);
     d.M = M;
     d.N = w.rows;
     d.nseg = 1;
     d.seg[0] = ASeg{SEG_PLAIN, p(a_off), K, K, 0, 0, 0};
-    d.w = wm(w);
+    if (ln) {
+      d.stats_in = reinterpret_cast<const float2*>(p(stats_off));
+      d.stats_parts = gemm_stats_parts(K);
+      d.ln_c = wv(ln->c);
+      d.ln_frames = ln->frames > 1 ? h->F : 1;
+      d.ln_rows_per_frame = rows_per_frame;
+      d.ln_eps = 1e-5f;
+      bias = nullptr;  // folded into c
+    }
+    if (emit_stats) d.stats_out = reinterpret_cast<float2*>(p(stats_off));
+    d.w = ln ? wm(ln->wf) : wm(w);
     d.Ktot = w.cols;
     d.w_rows = w.rows;
     d.out = p(out_off);
@@ -615,14 +675,22 @@ struct Planner {
     const int heads = h->cfg.attention_heads, d = C / heads;
     Act n = new_act(C, x.H, x.W);
     groupnorm(x, nullptr, t.ng, t.nb, 1e-6f, true, false, n.off);
+    const bool fold = h->ln_fold && !h->simple;
+    // row statistics of y for the folded LayerNorms: [column parts][M] float2, rewritten by every producer of y
+    const size_t st_bytes = (size_t)gemm_stats_parts(C) * M * sizeof(float2);
+    const size_t st = fold ? alloc(st_bytes) : 0;
     Act y = new_act(C, x.H, x.W);
-    linear(n.off, M, C, t.pi, &t.pib, y.off, C, nullptr);
+    linear(n.off, M, C, t.pi, &t.pib, y.off, C, nullptr, 0, nullptr, st, fold);
     free_act(n);
     Act tmp = new_act(C, x.H, x.W);
     // self-attention
-    layernorm(y.off, tmp.off, M, C, t.ln1g, t.ln1b, nullptr, 1);
     Act qkv = new_act(3 * C, x.H, x.W);
-    linear(tmp.off, M, C, t.a1.qkv, nullptr, qkv.off, 3 * C, nullptr);
+    if (fold) {
+      linear(y.off, M, C, t.a1.qkv, nullptr, qkv.off, 3 * C, nullptr, 0, &t.a1.qkv_ln, st);
+    } else {
+      layernorm(y.off, tmp.off, M, C, t.ln1g, t.ln1b, nullptr, 1);
+      linear(tmp.off, M, C, t.a1.qkv, nullptr, qkv.off, 3 * C, nullptr);
+    }
     {
       AttnDesc a;
       memset(&a, 0, sizeof a);
@@ -641,11 +709,15 @@ struct Planner {
       attention(a);
     }
     free_act(qkv);
-    linear(tmp.off, M, C, t.a1.out, &t.a1.outb, y.off, C, &y.off);
+    linear(tmp.off, M, C, t.a1.out, &t.a1.outb, y.off, C, &y.off, 0, nullptr, st, fold);
     // cross-attention to the fused context
-    layernorm(y.off, tmp.off, M, C, t.ln2g, t.ln2b, nullptr, 1);
     Act q = new_act(C, x.H, x.W);
-    linear(tmp.off, M, C, t.a2.q, nullptr, q.off, C, nullptr);
+    if (fold) {
+      linear(y.off, M, C, t.a2.q, nullptr, q.off, C, nullptr, 0, &t.a2.q_ln, st);
+    } else {
+      layernorm(y.off, tmp.off, M, C, t.ln2g, t.ln2b, nullptr, 1);
+      linear(tmp.off, M, C, t.a2.q, nullptr, q.off, C, nullptr);
+    }
     {
       AttnDesc a;
       memset(&a, 0, sizeof a);
@@ -664,16 +736,21 @@ struct Planner {
       attention(a);
     }
     free_act(q);
-    linear(tmp.off, M, C, t.a2.out, &t.a2.outb, y.off, C, &y.off);
+    linear(tmp.off, M, C, t.a2.out, &t.a2.outb, y.off, C, &y.off, 0, nullptr, st, fold);
     // GEGLU feed-forward
-    layernorm(y.off, tmp.off, M, C, t.ln3g, t.ln3b, nullptr, 1);
     Act g = new_act(4 * C, x.H, x.W);
-    linear(tmp.off, M, C, t.ff1, &t.ff1b, g.off, 4 * C, nullptr, 1);
+    if (fold) {
+      linear(y.off, M, C, t.ff1, &t.ff1b, g.off, 4 * C, nullptr, 1, &t.ff1_ln, st);
+    } else {
+      layernorm(y.off, tmp.off, M, C, t.ln3g, t.ln3b, nullptr, 1);
+      linear(tmp.off, M, C, t.ff1, &t.ff1b, g.off, 4 * C, nullptr, 1);
+    }
     linear(g.off, M, 4 * C, t.ff2, &t.ff2b, y.off, C, &y.off);
     free_act(g);
     free_act(tmp);
     linear(y.off, M, C, t.po, &t.pob, x.off, C, &x.off);
     free_act(y);
+    if (fold) release(st, st_bytes);
   }
 
   // VanillaTemporalModule (motion_module.py:87-93,147-182,234-246,294-354); x updated in place
@@ -682,14 +759,21 @@ struct Planner {
     const int heads = h->cfg.motion_heads, d = C / heads;
     Act n = new_act(C, x.H, x.W);
     groupnorm(x, nullptr, m.ng, m.nb, 1e-6f, true, false, n.off);
+    const bool fold = h->ln_fold && !h->simple;
+    const size_t st_bytes = (size_t)gemm_stats_parts(C) * M * sizeof(float2);
+    const size_t st = fold ? alloc(st_bytes) : 0;
     Act y = new_act(C, x.H, x.W);
-    linear(n.off, M, C, m.pi, &m.pib, y.off, C, nullptr);
+    linear(n.off, M, C, m.pi, &m.pib, y.off, C, nullptr, 0, nullptr, st, fold);
     free_act(n);
     Act tmp = new_act(C, x.H, x.W);
     for (int i = 0; i < h->cfg.motion_attn_blocks; ++i) {
-      layernorm(y.off, tmp.off, M, C, m.lng[i], m.lnb[i], &m.pe[i], HW);
       Act qkv = new_act(3 * C, x.H, x.W);
-      linear(tmp.off, M, C, m.att[i].qkv, nullptr, qkv.off, 3 * C, nullptr);
+      if (fold) {  // LayerNorm + positional encoding folded into the QKV projection (c is per frame)
+        linear(y.off, M, C, m.att[i].qkv, nullptr, qkv.off, 3 * C, nullptr, 0, &m.att[i].qkv_ln, st, false, HW);
+      } else {
+        layernorm(y.off, tmp.off, M, C, m.lng[i], m.lnb[i], &m.pe[i], HW);
+        linear(tmp.off, M, C, m.att[i].qkv, nullptr, qkv.off, 3 * C, nullptr);
+      }
       if (!dry && !failed) {
         const void* qp = p(qkv.off);
         void* op = p(tmp.off);
@@ -700,16 +784,21 @@ struct Planner {
         }, "attn_temporal", 4.0 * B * HW * heads * (double)F * F * d, 2.0 * M * 4.0 * C);
       }
       free_act(qkv);
-      linear(tmp.off, M, C, m.att[i].out, &m.att[i].outb, y.off, C, &y.off);
+      linear(tmp.off, M, C, m.att[i].out, &m.att[i].outb, y.off, C, &y.off, 0, nullptr, st, fold);
     }
-    layernorm(y.off, tmp.off, M, C, m.ffng, m.ffnb, nullptr, 1);
     Act g = new_act(4 * C, x.H, x.W);
-    linear(tmp.off, M, C, m.ff1, &m.ff1b, g.off, 4 * C, nullptr, 1);
+    if (fold) {
+      linear(y.off, M, C, m.ff1, &m.ff1b, g.off, 4 * C, nullptr, 1, &m.ff1_ln, st);
+    } else {
+      layernorm(y.off, tmp.off, M, C, m.ffng, m.ffnb, nullptr, 1);
+      linear(tmp.off, M, C, m.ff1, &m.ff1b, g.off, 4 * C, nullptr, 1);
+    }
     linear(g.off, M, 4 * C, m.ff2, &m.ff2b, y.off, C, &y.off);
     free_act(g);
     free_act(tmp);
     linear(y.off, M, C, m.po, &m.pob, x.off, C, &x.off);
     free_act(y);
+    if (fold) release(st, st_bytes);
   }
 
   Act conv_sampler(const Act& x, const Mat& w, const Vec& b, int stride, int Ho, int Wo) {
@@ -991,6 +1080,8 @@ int unet_create(const rcdm_unet_config* cfg, rcdm_unet** out) {
   h->cfg = *cfg;
   const char* env = getenv("RCDM_SIMPLE");
   h->simple = env && env[0] == '1';
+  const char* lf = getenv("RCDM_LN_FOLD");
+  h->ln_fold = !(lf && lf[0] == '0');
   if (build_model(h)) {
     delete h;
     return 1;

@@ -58,6 +58,45 @@ def geglu_linear(a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, simple: b
     return out
 
 
+def linear_rowstats(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None,
+                    residual: Optional[torch.Tensor] = None):
+    """linear() whose epilogue also emits per-row (sum, sum of squares) partials of the rounded output.
+    Returns (out [M,N], stats fp32 [parts, M, 2])."""
+    M, K = a.shape
+    N = w.shape[0]
+    out = torch.empty((M, N), dtype=a.dtype, device=a.device)
+    stats = torch.zeros((64, M, 2), dtype=torch.float32, device=a.device)
+    parts = _lib.C.c_int(0)
+    _lib.check(_lib.lib().rcdm_gemm_rowstats(_dt16(a), a.data_ptr(), w.data_ptr(), _ptr(bias), _ptr(residual),
+                                             out.data_ptr(), M, N, K, stats.data_ptr(), _lib.C.byref(parts),
+                                             _lib.current_stream_ptr()))
+    return out, stats[:parts.value]
+
+
+def linear_ln(x: torch.Tensor, w: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor,
+              bias: Optional[torch.Tensor] = None, pe: Optional[torch.Tensor] = None, rows_per_frame: int = 1,
+              geglu: bool = False, eps: float = 1e-5) -> torch.Tensor:
+    """(LayerNorm(x) [+ pe[frame]]) @ w^T + bias with the LayerNorm folded around the tensor-core GEMM.
+    geglu: w [2J, K] / bias in the reference layout, output h * gelu(g) with J columns."""
+    M, K = x.shape
+    N = w.shape[0]
+    L = _lib.lib()
+    s = _lib.current_stream_ptr()
+    frames = pe.shape[0] if pe is not None else 1
+    if geglu:
+        wp = torch.empty_like(w)
+        bp = torch.empty((N,), dtype=torch.float32, device=x.device)
+        _lib.check(L.rcdm_pack_geglu(_dt(w), w.data_ptr(), bias.float().contiguous().data_ptr(), wp.data_ptr(),
+                                     bp.data_ptr(), N, K, s))
+        w, bias = wp, bp
+    scratch = torch.empty((L.rcdm_linear_ln_scratch_bytes(M, N, K, frames),), dtype=torch.uint8, device=x.device)
+    out = torch.empty((M, N // 2 if geglu else N), dtype=x.dtype, device=x.device)
+    _lib.check(L.rcdm_linear_ln(_dt16(x), x.data_ptr(), w.data_ptr(), gamma.data_ptr(), beta.data_ptr(), _ptr(pe),
+                                _ptr(bias), out.data_ptr(), M, N, K, int(geglu), frames, rows_per_frame, eps,
+                                scratch.data_ptr(), s))
+    return out
+
+
 def conv3x3(x_nhwc: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = None,
             residual: Optional[torch.Tensor] = None, stride: int = 1, simple: bool = False) -> torch.Tensor:
     """3x3 / pad 1 conv on channels-last x [n,h,w,cin]; weight in the reference layout [cout,cin,3,3]."""

@@ -118,6 +118,50 @@ def check_layernorm(rows, C, dtype, pe=False, seed=4):
     return _result(f"layernorm rows{rows} C{C} pe{int(pe)}", out, ref, dtype, rtol_mul=2.0)
 
 
+def check_linear_ln(M, N, K, dtype, pe=False, geglu=False, seed=8):
+    """LayerNorm folded around the GEMM vs LayerNorm (fp32) -> Linear (fp32) on the same rounded inputs."""
+    g = _gen(seed)
+    x = _rand((M, K), dtype, g) * 1.5 + 0.3
+    w = _rand((N, K), dtype, g, 1.0 / math.sqrt(K))
+    gamma = 1 + 0.2 * torch.randn((K,), generator=g, device="cuda")
+    beta = 0.2 * torch.randn((K,), generator=g, device="cuda")
+    bias = torch.randn((N,), generator=g, device="cuda") * 0.5 if (geglu or seed % 2 == 0) else None
+    frames, rpf = 5, max(1, M // 10)
+    pet = torch.randn((frames, K), generator=g, device="cuda") if pe else None
+    out = ops.linear_ln(x, w, gamma, beta, bias, pet, rpf, geglu)
+    ln = F.layer_norm(x.float(), (K,), gamma, beta, 1e-5)
+    if pe:
+        fr = (torch.arange(M, device="cuda") // rpf) % frames
+        ln = ln + pet[fr]
+    ref = ln @ w.float().t()
+    if bias is not None:
+        ref = ref + bias
+    if geglu:
+        h, gate = ref.chunk(2, dim=-1)
+        ref = h * F.gelu(gate)
+    # the folded weights (W * gamma, centred) are rounded to 16 bits once more, like the reference's 16-bit LayerNorm
+    # output; the GEGLU product h * gelu(g) carries both factors' errors and the bound is on the MAX of ~1e6 elements
+    return _result(f"linear_ln M{M} N{N} K{K} pe{int(pe)} geglu{int(geglu)}", out, ref, dtype,
+                   rtol_mul=6.0 if geglu else 3.0)
+
+
+def check_rowstats(M, N, K, dtype, residual=True, seed=9):
+    g = _gen(seed)
+    a = _rand((M, K), dtype, g)
+    w = _rand((N, K), dtype, g, 1.0 / math.sqrt(K))
+    b = torch.randn((N,), generator=g, device="cuda")
+    r = _rand((M, N), dtype, g) if residual else None
+    out, stats = ops.linear_rowstats(a, w, b, r)
+    plain = ops.linear(a, w, b, r)
+    tot = stats.sum(dim=0)
+    o32 = out.float()
+    ref = torch.stack([o32.sum(dim=1), (o32 * o32).sum(dim=1)], dim=1)
+    res = _result(f"rowstats M{M} N{N} K{K} r{int(residual)}", tot, ref, torch.float16, rtol_mul=0.1)
+    res["same_output_as_plain_gemm"] = bool(torch.equal(out, plain))
+    res["ok"] = res["ok"] and res["same_output_as_plain_gemm"]
+    return res
+
+
 def check_flash(batch, heads, sq, skv, d, dtype, simple=False, seed=5, qscale=1.0):
     g = _gen(seed)
     q = _rand((batch, sq, heads * d), dtype, g, qscale)
@@ -204,6 +248,13 @@ def all_op_checks(dtypes=(torch.float16, torch.bfloat16), quick=False):
         yield lambda dt=dt: check_conv3x3(10, 16, 16, 640, 1280, 2, dt)
         yield lambda dt=dt: check_geglu(640, 640, dt)
         yield lambda dt=dt: check_linear(300, 320, 64, dt, simple=True)
+        for (M, N, K, pe, gg) in [(640, 960, 320, False, False), (640, 960, 320, True, False), (1000, 320, 320, False, False),
+                                  (2560, 3840, 1280, True, False), (640, 2560, 320, False, True),
+                                  (300, 512, 64, True, True), (10240, 1920, 640, False, False)]:
+            yield lambda a=(M, N, K, pe, gg), dt=dt: check_linear_ln(a[0], a[1], a[2], dt, pe=a[3], geglu=a[4])
+        for (M, N, K, rs) in [(640, 320, 320, True), (1000, 640, 128, False), (2560, 1280, 1280, True), (130, 64, 64, True),
+                              (300, 192, 96, True)]:
+            yield lambda a=(M, N, K, rs), dt=dt: check_rowstats(a[0], a[1], a[2], dt, residual=a[3])
         for (M, C) in [(256, 64), (1024, 320), (100, 128)]:
             yield lambda M=M, C=C, dt=dt: check_geglu(M, C, dt)
         yield lambda dt=dt: check_geglu(128, 64, dt, simple=True)
