@@ -280,8 +280,14 @@ def run_ours(a):
         mm = [agg[k] for k in ("gemm", "gemm_geglu", "conv3x3") if k in agg]
         mm_ms, mm_fl, mm_n = sum(g["ms"] for g in mm), sum(g["flops"] for g in mm), sum(g["n"] for g in mm)
         achieved = mm_fl / (mm_ms / 1e3) / 1e12
+        traffic, traffic_note = None, None
+        tp = os.path.join(ROOT, "profiles", "r01_gemm_traffic.json")
+        if os.path.exists(tp):  # dram__bytes_read.sum + dram__bytes_write.sum per launch, from the committed ncu pass
+            tj = json.load(open(tp))
+            traffic, traffic_note = tj.get("dram_bytes_per_launch"), tj.get("note")
         roofline = dict(bound="tensor", kernel="gemm_tcgen05_kernel", achieved=achieved, peak=pk["tflops"], unit="TFLOP/s",
-                        frac=achieved / pk["tflops"], traffic=None, peak_source=pk["source"] + ", sustained bf16",
+                        frac=achieved / pk["tflops"], traffic=traffic, traffic_note=traffic_note,
+                        peak_source=pk["source"] + ", sustained bf16",
                         launches_per_forward=mm_n, share_of_forward=mm_ms / tot_ms,
                         flops_per_launch_avg=mm_fl / mm_n, ms_per_launch_avg=mm_ms / mm_n,
                         by_kind={k: dict(ms=round(v["ms"], 4), n=v["n"],

@@ -330,6 +330,267 @@ flash_attn_kernel(const __grid_constant__ AttnMaps maps, const AttnParams p) {
 }
 
 // ------------------------------------------------------------------------------------------
+// flash attention, generation 4: same data path as flash_attn_kernel (5-D TMA head slices, tcgen05 S = Q K^T and
+// O += P V with TMEM accumulators, lazy-rescale online softmax, PV-MMA row sums), re-balanced for the unit that
+// actually bounds head_dim 40: the MUFU exp2 pipe (ncu: XU 58 % busy, tensor 21 %, 8 warps per SM).
+//   * each softmax thread pulls its whole 64-column S row into registers and releases the TMEM S buffer at once
+//     (s_free), so ONE S buffer suffices: TMEM = 64 (S) + DPAD (O) columns -> 128 columns for DPAD <= 64
+//   * with 128 TMEM columns, 2 K/V stages and ~70 KB of shared memory, THREE CTAs share an SM (12 softmax warps
+//     instead of 8) and their exp / TMEM-load / barrier phases interleave on the MUFU pipe
+//   * the rare re-reference pass works from the registers (no second TMEM read of S)
+// ------------------------------------------------------------------------------------------
+template <int DPAD> struct Attn4Cfg {
+  static constexpr int BLOCK_M = 128, BLOCK_N = 64;
+  static constexpr int NCH = DPAD / 8;
+  static constexpr int Q_BYTES = NCH * BLOCK_M * 16;
+  static constexpr int KV_BYTES = NCH * BLOCK_N * 16;
+  static constexpr int KV_STAGES = 2;
+  static constexpr int P_BYTES = (BLOCK_N / 8) * BLOCK_M * 16;
+  static constexpr int TMEM_COLS = (BLOCK_N + DPAD) <= 128 ? 128 : 256;
+  static constexpr int SMEM_BYTES = Q_BYTES + 2 * KV_STAGES * KV_BYTES + 2 * P_BYTES + 1024 + 256;
+  static constexpr int CTAS_PER_SM = DPAD <= 48 ? 3 : (DPAD <= 80 ? 2 : 1);
+};
+
+template <typename T, int DPAD>
+__global__ void __launch_bounds__(160, Attn4Cfg<DPAD>::CTAS_PER_SM)
+flash_attn4_kernel(const __grid_constant__ AttnMaps maps, const AttnParams p) {
+  using Cfg = Attn4Cfg<DPAD>;
+  constexpr int KV = Cfg::KV_STAGES;
+  constexpr int BN = Cfg::BLOCK_N;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + Cfg::Q_BYTES;
+  uint8_t* sV = sK + KV * Cfg::KV_BYTES;
+  uint8_t* sP = sV + KV * Cfg::KV_BYTES;  // [2][P_BYTES]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * Cfg::P_BYTES);
+  uint64_t* q_full = bars;
+  uint64_t* kv_full = bars + 1;          // [KV]
+  uint64_t* kv_empty = bars + 1 + KV;    // [KV]
+  uint64_t* s_full = bars + 1 + 2 * KV;  // S_j is in TMEM
+  uint64_t* s_free = s_full + 1;         // every softmax thread holds S_j in registers
+  uint64_t* p_full = s_full + 2;         // [2]
+  uint64_t* pv_done = s_full + 4;
+  uint64_t* o_done = s_full + 5;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_full + 6);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q_tile = blockIdx.x, head = blockIdx.y, img = blockIdx.z;
+  const int n_kv = (p.S_kv + BN - 1) / BN;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      mbar_init(q_full, 1);
+      for (int i = 0; i < KV; ++i) {
+        mbar_init(&kv_full[i], 1);
+        mbar_init(&kv_empty[i], 1);
+      }
+      mbar_init(s_full, 1);
+      mbar_init(s_free, 128);
+      mbar_init(&p_full[0], 128);
+      mbar_init(&p_full[1], 128);
+      mbar_init(pv_done, 1);
+      mbar_init(o_done, 1);
+      fence_mbar_init();
+      tma_prefetch_desc(&maps.q);
+      tma_prefetch_desc(&maps.k);
+      tma_prefetch_desc(&maps.v);
+    }
+    __syncwarp();
+    tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_S = tmem_base;
+  const uint32_t tmem_O = tmem_base + BN;
+  pdl_sync();
+
+  if (warp == 4) {
+    if (elect_one()) {
+      constexpr uint32_t idesc_qk = umma_idesc_f16(DT<T>::umma_fmt, 128, BN, 0, 0);
+      constexpr uint32_t idesc_pv = umma_idesc_f16(DT<T>::umma_fmt, 128, DPAD, 0, 1);  // B (=V) is MN-major
+      const uint32_t q_addr = smem_u32(sQ);
+      auto load_kv = [&](int t) {
+        const int s = t % KV;
+        mbar_expect_tx(&kv_full[s], 2 * Cfg::KV_BYTES);
+        tma_load_5d(sK + s * Cfg::KV_BYTES, &maps.k, &kv_full[s], 0, t * BN, 0, head, img);
+        tma_load_5d(sV + s * Cfg::KV_BYTES, &maps.v, &kv_full[s], 0, t * BN, 0, head, img);
+      };
+      auto mma_qk = [&](int t) {
+        const int s = t % KV;
+        mbar_wait(&kv_full[s], (t / KV) & 1);
+        tc_fence_after();
+        const uint32_t k_addr = smem_u32(sK + s * Cfg::KV_BYTES);
+#pragma unroll
+        for (int ks = 0; ks < DPAD / 16; ++ks) {
+          const uint64_t ad = umma_smem_desc(q_addr + ks * 2 * (128 * 16), 128 * 16, 128, UMMA_SWIZZLE_NONE);
+          const uint64_t bd = umma_smem_desc(k_addr + ks * 2 * (BN * 16), BN * 16, 128, UMMA_SWIZZLE_NONE);
+          umma_f16_ss(tmem_S, ad, bd, idesc_qk, ks != 0);
+        }
+        umma_commit(s_full);
+      };
+      mbar_expect_tx(q_full, Cfg::Q_BYTES);
+      tma_load_5d(sQ, &maps.q, q_full, 0, q_tile * 128, 0, head, img);
+      for (int t = 0; t < KV && t < n_kv; ++t) load_kv(t);
+      mbar_wait(q_full, 0);
+      mma_qk(0);
+      for (int j = 0; j < n_kv; ++j) {
+        if (j + 1 < n_kv) {
+          mbar_wait(s_free, j & 1);  // S_j now lives in the softmax threads' registers: the TMEM buffer is free
+          tc_fence_after();
+          mma_qk(j + 1);             // overlaps the exponentials of tile j
+        }
+        mbar_wait(&p_full[j & 1], (j >> 1) & 1);
+        tc_fence_after();
+        const int s = j % KV;
+        const uint32_t p_addr = smem_u32(sP + (j & 1) * Cfg::P_BYTES);
+        const uint32_t v_addr = smem_u32(sV + s * Cfg::KV_BYTES);
+#pragma unroll
+        for (int ks = 0; ks < BN / 16; ++ks) {
+          const uint64_t ad = umma_smem_desc(p_addr + ks * 4096, 2048, 128, UMMA_SWIZZLE_NONE);
+          const uint64_t bd = umma_smem_desc(v_addr + ks * 256, 128, BN * 16, UMMA_SWIZZLE_NONE);
+          umma_f16_ss(tmem_O, ad, bd, idesc_pv, (j | ks) != 0);
+        }
+        umma_commit(&kv_empty[s]);
+        umma_commit(pv_done);
+        if (j == n_kv - 1) umma_commit(o_done);
+        if (j + KV < n_kv) {
+          mbar_wait(&kv_empty[s], (j / KV) & 1);
+          load_kv(j + KV);
+        }
+      }
+    }
+  } else {
+    // =================================== softmax warps: one thread per query row ===================================
+    const int row = warp * 32 + lane;
+    const uint32_t lane_sel = uint32_t(warp * 32) << 16;
+    const float sc = p.scale_log2;
+    float m_run = -INFINITY, l_run = 0.f;
+    const bool mma_sum = p.d < DPAD;  // spare padded column of V carries ones: the P V MMA accumulates the row sums
+    using T2 = typename DT<T>::T2;
+
+    for (int j = 0; j < n_kv; ++j) {
+      mbar_wait(s_full, j & 1);
+      tc_fence_after();
+      uint32_t r[BN];
+      tmem_ld32(tmem_S + lane_sel, r);
+      tmem_ld32(tmem_S + lane_sel + 32, r + 32);
+      tmem_wait_ld();
+      tc_fence_before();
+      mbar_arrive(s_free);
+      uint8_t* sP_row = sP + (j & 1) * Cfg::P_BYTES + row * 16;
+      const int kv_valid = min(BN, p.S_kv - j * BN);
+      if (mma_sum && row < BN)  // V tile j has landed (the MMA thread waited for it before S_j): set its ones column
+        *reinterpret_cast<T*>(sV + (j % KV) * Cfg::KV_BYTES + (p.d / 8) * (BN * 16) + row * 16) = DT<T>::from_f(1.0f);
+      if (kv_valid < BN) {
+#pragma unroll
+        for (int i = 0; i < BN; ++i)
+          if (i >= kv_valid) r[i] = 0xff800000u;  // -inf: exp2 -> 0
+      }
+      auto row_max = [&]() -> float {
+        float x0 = -INFINITY, x1 = -INFINITY;
+#pragma unroll
+        for (int i = 0; i < BN; i += 2) {
+          x0 = fmaxf(x0, __uint_as_float(r[i]));
+          x1 = fmaxf(x1, __uint_as_float(r[i + 1]));
+        }
+        return fmaxf(x0, x1);
+      };
+      // exponentiate the row against `mref`, write P; returns the row sum (0 when the MMA sums) and the largest
+      // probability written (in pmax)
+      auto exp_pass = [&](float mref, float& pmax) -> float {
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+        T2 mx2 = DT<T>::from_f2(0.f, 0.f);
+#pragma unroll
+        for (int g = 0; g < BN / 8; ++g) {
+          float pv[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) pv[i] = exp2f(fmaf(__uint_as_float(r[g * 8 + i]), sc, -mref));
+          if (!mma_sum) {
+            s0 += pv[0] + pv[4];
+            s1 += pv[1] + pv[5];
+            s2 += pv[2] + pv[6];
+            s3 += pv[3] + pv[7];
+          }
+          uint4 pk = pack8<T>(pv);
+          const T2* p2 = reinterpret_cast<const T2*>(&pk);
+          mx2 = __hmax2(mx2, __hmax2(__hmax2(p2[0], p2[1]), __hmax2(p2[2], p2[3])));
+          *reinterpret_cast<uint4*>(sP_row + g * 2048) = pk;  // P tile, K-major interleaved: [kv/8][row][8]
+        }
+        const float2 mxf = DT<T>::to_f2(mx2);
+        pmax = fmaxf(mxf.x, mxf.y);
+        return (s0 + s1) + (s2 + s3);
+      };
+      float pmax;
+      if (j == 0) {
+        m_run = row_max() * sc;
+        l_run = exp_pass(m_run, pmax);
+      } else {
+        const float sum = exp_pass(m_run, pmax);
+        if (__any_sync(0xffffffffu, pmax > 256.0f)) {
+          // rare: some probability left the comfortable 16-bit range -> re-reference to the new maximum
+          const float m_new = fmaxf(m_run, row_max() * sc);
+          const float alpha = exp2f(m_run - m_new);
+          const float sum2 = exp_pass(m_new, pmax);
+          mbar_wait(pv_done, (j - 1) & 1);  // O (incl. the row-sum column) must be quiescent: P_{j-1} V_{j-1} done
+          tc_fence_after();
+#pragma unroll 1
+          for (int c = 0; c < DPAD; c += 16) {
+            uint32_t o[16];
+            tmem_ld16(tmem_O + lane_sel + c, o);
+            tmem_wait_ld();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tmem_st16(tmem_O + lane_sel + c, o);
+          }
+          tmem_wait_st();
+          l_run = l_run * alpha + sum2;
+          m_run = m_new;
+        } else {
+          l_run += sum;
+        }
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(&p_full[j & 1]);
+    }
+    // ---- normalise and store
+    mbar_wait(o_done, 0);
+    tc_fence_after();
+    if (mma_sum) {
+      uint32_t o[16];
+      tmem_ld16(tmem_O + lane_sel + (p.d & ~15), o);
+      tmem_wait_ld();
+      l_run = __uint_as_float(o[p.d & 15]);
+    }
+    const float inv_l = 1.0f / l_run;
+    const int qrow = q_tile * 128 + row;
+    T* out = reinterpret_cast<T*>(p.out) + ((size_t)img * p.S_q + qrow) * p.ldo + head * p.d;
+#pragma unroll 1
+    for (int c = 0; c < DPAD; c += 16) {
+      uint32_t o[16];
+      tmem_ld16(tmem_O + lane_sel + c, o);
+      tmem_wait_ld();
+      if (qrow < p.S_q) {
+        float v[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(o[i]) * inv_l;
+        if (c < p.d) *reinterpret_cast<uint4*>(out + c) = pack8<T>(v);
+        if (c + 8 < p.d) *reinterpret_cast<uint4*>(out + c + 8) = pack8<T>(v + 8);
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // temporal attention: qkv [rows, 3C] with rows ordered (b, f, hw); out [rows, C]
 // one thread per (b, hw, head); F <= 8 frames
 // ------------------------------------------------------------------------------------------

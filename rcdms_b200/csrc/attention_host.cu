@@ -46,8 +46,18 @@ bool attn_prepare(const AttnDesc& d, AttnLaunch* l, std::string* err) {
   return true;
 }
 
+static int attn_version() {  // RCDM_ATTN_V = 3: previous generation (double-buffered S in TMEM); default 4
+  static const int v = [] {
+    const char* e = getenv("RCDM_ATTN_V");
+    return e ? atoi(e) : 4;
+  }();
+  return v;
+}
 template <typename T, int DPAD> static void launch_one(const AttnLaunch& l, cudaStream_t s) {
-  launch_k(flash_attn_kernel<T, DPAD>, l.grid, dim3(160), AttnCfg<DPAD>::SMEM_BYTES, s, l.maps, l.p);
+  if (attn_version() == 3)
+    launch_k(flash_attn_kernel<T, DPAD>, l.grid, dim3(160), AttnCfg<DPAD>::SMEM_BYTES, s, l.maps, l.p);
+  else
+    launch_k(flash_attn4_kernel<T, DPAD>, l.grid, dim3(160), Attn4Cfg<DPAD>::SMEM_BYTES, s, l.maps, l.p);
 }
 template <typename T> static void launch_dt(const AttnLaunch& l, cudaStream_t s) {
   switch (l.dpad) {
@@ -64,8 +74,12 @@ void attn_launch(const AttnLaunch& l, cudaStream_t s) {
 }
 
 template <typename T, int DPAD> static cudaError_t set_attr() {
-  return cudaFuncSetAttribute(flash_attn_kernel<T, DPAD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                              AttnCfg<DPAD>::SMEM_BYTES);
+  cudaError_t e = cudaFuncSetAttribute(flash_attn_kernel<T, DPAD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       AttnCfg<DPAD>::SMEM_BYTES);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(flash_attn4_kernel<T, DPAD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             Attn4Cfg<DPAD>::SMEM_BYTES);
+  return e;
 }
 template <typename T> static cudaError_t set_attr_dt() {
   cudaError_t e = set_attr<T, 16>();

@@ -235,6 +235,16 @@ __global__ void __launch_bounds__(512, 1) gn_fused_kernel(const GnArgs a, const 
       }
     };
     int r = rl;
+    for (; r + 7 * k < nrows; r += 8 * k) {  // 8 independent 16-byte loads in flight per thread
+      uint4 raw[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) raw[u] = __ldg(reinterpret_cast<const uint4*>(src + (row0 + r + u * k) * ld + cc));
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        if (r + u * k < cache_rows) cache[(size_t)(r + u * k) * vecs + v] = raw[u];
+        acc(raw[u]);
+      }
+    }
     for (; r + 3 * k < nrows; r += 4 * k) {
       uint4 raw[4];
 #pragma unroll

@@ -13,9 +13,22 @@ timeout 200 python scripts/bench_gemm_shapes.py > gpurun_out/bench_gemm_shapes.l
 cat gpurun_out/bench_gemm_shapes.log
 timeout 200 python scripts/bench_ops.py > gpurun_out/bench_ops.log 2>&1
 grep -i "norm\|temporal\|copy" gpurun_out/bench_ops.log
+timeout 200 python scripts/bench_ops.py flash 2>&1 | tee gpurun_out/bench_flash.log
+RCDM_ATTN_V=3 timeout 200 python scripts/bench_ops.py flash 2>&1 | tee gpurun_out/bench_flash_v3.log
 timeout 300 python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/bench.log 2>&1
 echo "bench rc=$?"; cut -c1-400 gpurun_out/bench.log
 for extra in "$@"; do
+  if [ "$extra" = "ncudram" ]; then
+    timeout 900 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --csv \
+      --log-file gpurun_out/launches_dram.csv python scripts/one_forward.py 2 > gpurun_out/ncu_launches_dram.log 2>&1
+    python scripts/traffic_summary.py gpurun_out/launches_dram.csv 0 gpurun_out/gemm_traffic.json | tail -30
+    continue
+  fi
+  if [ "$extra" = "fullbench" ]; then
+    timeout 600 python bench.py --steps 3 --warmup 3 > gpurun_out/bench_full.log 2>&1; tail -c 1200 gpurun_out/bench_full.log
+    timeout 600 python bench.py --impl reference --steps 1 --warmup 0 > gpurun_out/bench_ref.log 2>&1; cat gpurun_out/bench_ref.log | cut -c1-600
+    continue
+  fi
   if [ "$extra" = "ncu" ]; then
     timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches.csv \
       python scripts/one_forward.py 2 > gpurun_out/ncu_launches.log 2>&1
