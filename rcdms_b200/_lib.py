@@ -11,7 +11,8 @@ import os
 from typing import Optional
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "_C", "librcdm_b200.so")
+# RCDM_LIB selects an experiment build of the same library (scripts/build_variants.sh); never a different backend
+LIB_PATH = os.environ.get("RCDM_LIB") or os.path.join(HERE, "_C", "librcdm_b200.so")
 
 DT_F32, DT_F16, DT_BF16 = 0, 1, 2
 MAX_BLOCKS = 4

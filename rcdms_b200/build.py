@@ -16,7 +16,7 @@ from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-OUT_DIR = os.path.join(HERE, "_C")
+OUT_DIR = os.environ.get("RCDM_BUILD_DIR") or os.path.join(HERE, "_C")  # RCDM_BUILD_DIR: experiment variants only
 LIB = os.path.join(OUT_DIR, "librcdm_b200.so")
 SOURCES = ["gemm_host.cu", "attention_host.cu", "norm_host.cu", "unet.cu", "api.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

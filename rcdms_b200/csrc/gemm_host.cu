@@ -135,9 +135,9 @@ static bool sk_alloc(std::string* err) {
   return true;
 }
 
-int gemm_stats_parts(int N) {  // 2 column halves per N tile of the (heuristic) tile width, see pick_bn
+int gemm_stats_parts(int N) {  // one part per epilogue column group per N tile of the (heuristic) tile width
   const int bn = (N % 160 == 0) ? 160 : (N <= 64 ? 64 : 128);
-  return 2 * ((N + bn - 1) / bn);
+  return RCDM_EPI_GROUPS * ((N + bn - 1) / bn);
 }
 
 static int pick_bn(const GemmDesc& d) {
@@ -255,7 +255,8 @@ bool gemm_prepare(const GemmDesc& d, GemmLaunch* l, std::string* err) {
   // RCDM_GEMM_PAIR = 0 never, 1 heuristic (default), 2 whenever there are >= 2 M tiles.
   const int pair_mode = pair_enabled();
   l->pair = (!d.no_pair && num_sms() >= 2 &&
-             ((pair_mode == 2 && m_tiles >= 2) || (pair_mode == 1 && kb >= 90 && m_tiles >= 16))) ? 1 : 0;
+             ((d.force_pair && m_tiles >= 2) || (pair_mode == 2 && m_tiles >= 2) ||
+              (pair_mode == 1 && kb >= 90 && m_tiles >= 16))) ? 1 : 0;
   {
     uint64_t dims[2] = {(uint64_t)d.Ktot, (uint64_t)d.w_rows};
     uint64_t str[1] = {(uint64_t)d.Ktot * 2};
@@ -287,12 +288,13 @@ bool gemm_prepare(const GemmDesc& d, GemmLaunch* l, std::string* err) {
 
 template <typename T, int BN> static void launch_one(const GemmLaunch& l, cudaStream_t s) {
   if (!l.pair) {
-    launch_k(gemm_tcgen05_kernel<T, BN, false>, l.grid, dim3(320), GemmCfg<BN, false>::SMEM_BYTES, s, l.maps, l.p);
+    launch_k(gemm_tcgen05_kernel<T, BN, false>, l.grid, dim3(GemmCfg<BN, false>::THREADS), GemmCfg<BN, false>::SMEM_BYTES, s,
+             l.maps, l.p);
     return;
   }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = l.grid;
-  cfg.blockDim = dim3(320);
+  cfg.blockDim = dim3(GemmCfg<BN, true>::THREADS);
   cfg.dynamicSmemBytes = GemmCfg<BN, true>::SMEM_BYTES;
   cfg.stream = s;
   cudaLaunchAttribute at[2];

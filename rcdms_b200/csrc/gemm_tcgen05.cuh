@@ -22,6 +22,20 @@
 #pragma once
 #include "common.cuh"
 
+// Compile-time experiment switch for bottleneck analysis (never set in a product build; scripts/build_variants.sh):
+//   1 = epilogue skips the global stores, 2 = epilogue skips phase 1 math (TMEM -> slab) as well,
+//   3 = producer loads the A tile only for the first k-block of a tile (B still streams), 4 = neither A nor B after
+//   the first k-block of a tile (MMAs run on stale smem): isolates epilogue + MMA issue
+#ifndef RCDM_GEMM_EXPERIMENT
+#define RCDM_GEMM_EXPERIMENT 0
+#endif
+// Column groups of the epilogue: 4 * RCDM_EPI_GROUPS epilogue warps, each owning 32 rows x BN / RCDM_EPI_GROUPS
+// accumulator columns.  Measured on B200: 4 groups (16 warps, 96 registers per thread, spills) are 10-35 % SLOWER
+// than 2 groups (8 warps, 168 registers) on the small-K GEMMs, so 2 is the product setting.
+#ifndef RCDM_EPI_GROUPS
+#define RCDM_EPI_GROUPS 2
+#endif
+
 namespace rcdm {
 
 enum : int { SEG_PLAIN = 0, SEG_CONV3 = 1, SEG_CONV3S2 = 2 };
@@ -119,9 +133,14 @@ template <int BN, bool PAIR = false> struct GemmCfg {
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = (PAIR ? BN / 2 : BN) * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  // 8 epilogue warps, each with a private slab: 32 rows x (BN/2 cols * 2 B + 16 B pad)
-  static constexpr int SLAB_BYTES = 32 * (BN + 16);
-  static constexpr int STAGING_BYTES = 8 * SLAB_BYTES;
+  static constexpr int NG = RCDM_EPI_GROUPS;   // column groups; 4 * NG epilogue warps
+  static constexpr int QW = BN / NG;           // accumulator columns per epilogue warp
+  static constexpr int THREADS = 64 + 128 * NG;
+  // every epilogue warp has a private slab of 32 rows x QW 16-bit values; the pitch keeps the 16-byte row accesses of
+  // a quarter warp on distinct banks (QW = 40: 80 B = 20 words already does; otherwise + 16 B)
+  static constexpr int PITCH = (QW == 40) ? 80 : QW * 2 + 16;
+  static constexpr int SLAB_BYTES = 32 * PITCH;
+  static constexpr int STAGING_BYTES = 4 * NG * SLAB_BYTES;
   static constexpr int ACC_STRIDE = BN <= 64 ? 64 : BN <= 128 ? 128 : 256;  // TMEM columns between the 2 accumulators
   static constexpr int TMEM_COLS = 2 * ACC_STRIDE;
   // two buffers (tile parity) of BN fp32 epilogue values: bias, or the folded-LayerNorm vector c
@@ -136,7 +155,7 @@ template <int BN, bool PAIR = false> struct GemmCfg {
 // boundaries; two TMEM accumulators let the MMA warp start tile i+1 while the epilogue warps drain tile i.
 // 10 warps = 3 on the fullest SM sub-partition (16384 registers each) => at most 168 registers per thread.
 template <typename T, int BN, bool PAIR>
-__global__ void __launch_bounds__(320, 1)
+__global__ void __launch_bounds__(GemmCfg<BN, PAIR>::THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
   using Cfg = GemmCfg<BN, PAIR>;
   // pair mode: the work decomposition runs over PAIRS (p.num_m_tiles counts 256-row tile pairs); this CTA's rows are
@@ -178,7 +197,7 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
       }
       for (int i = 0; i < 2; ++i) {
         mbar_init(&tmem_full_bar[i], 1);
-        mbar_init(&tmem_empty_bar[i], PAIR ? 512 : 256);  // pair: the leader's barrier collects both CTAs' epilogues
+        mbar_init(&tmem_empty_bar[i], (PAIR ? 8 : 4) * Cfg::NG);  // one arrival per epilogue warp (pair: of both CTAs)
       }
       fence_mbar_init();
     }
@@ -246,12 +265,22 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
               tma_load_4d_2sm(sa, &maps.a[mi], &full_bar[stage], c * 64, x0 + dx, y0 + dy, n0);
             tma_load_2d_2sm(sb, &maps.b, &full_bar[stage], kb * 64, n_tile * BN + (int)rank * (BN / 2));
           } else {
+#if RCDM_GEMM_EXPERIMENT == 3 || RCDM_GEMM_EXPERIMENT == 4
+            const bool load_a = kb == kb0, load_b = (RCDM_GEMM_EXPERIMENT == 3) || kb == kb0;
+            mbar_expect_tx(&full_bar[stage], (load_a ? Cfg::A_BYTES : 0) + (load_b ? Cfg::B_BYTES : 0));
+            if (load_a) {
+              if (sg.mode == SEG_PLAIN) tma_load_2d(sa, &maps.a[mi], &full_bar[stage], c * 64, m_tile * 128);
+              else tma_load_4d(sa, &maps.a[mi], &full_bar[stage], c * 64, x0 + dx, y0 + dy, n0);
+            }
+            if (load_b) tma_load_2d(sb, &maps.b, &full_bar[stage], kb * 64, n_tile * BN);
+#else
             mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
             if (sg.mode == SEG_PLAIN)
               tma_load_2d(sa, &maps.a[mi], &full_bar[stage], c * 64, m_tile * 128);
             else
               tma_load_4d(sa, &maps.a[mi], &full_bar[stage], c * 64, x0 + dx, y0 + dy, n0);
             tma_load_2d(sb, &maps.b, &full_bar[stage], kb * 64, n_tile * BN);
+#endif
           }
           if (++stage == STAGES) {
             stage = 0;
@@ -310,37 +339,54 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
       }
     }
   } else {
-    // =================================== epilogue (8 warps) ===================================
-    // warp -> (q, hs): q = TMEM lane quarter (rows q*32..+31), hs = which half of the tile's output columns.
-    // phase 1 (thread <-> row):  TMEM -> registers, + bias (smem broadcast), GEGLU -> 16-bit private slab
+    // =================================== epilogue (4 * NG warps) ===================================
+    // warp -> (q, cg): q = TMEM lane quarter (rows q*32..+31), cg = which column group of the tile.
+    // phase 1 (thread <-> row):  TMEM -> registers, scale * acc + vector (smem broadcast), GEGLU -> 16-bit private slab
     // phase 2 (lane <-> fixed 16-byte column chunk, RPI rows per pass): slab (+ prefetched residual, packed
     //          half2 add == fp32 add + one rounding) -> coalesced global stores
+    constexpr int NG = Cfg::NG;
+    constexpr int QW = Cfg::QW;          // accumulator columns per warp
+    constexpr int TH = BN / 2;           // GEGLU: gate columns start at TH
+    constexpr int CW = (QW % 16 == 0) ? 16 : 8;  // TMEM columns per tcgen05.ld
+    constexpr int NCH = QW / CW;
+    constexpr int PITCH = Cfg::PITCH;
+    constexpr int EPI_THREADS = 128 * NG;
     const int q = warp & 3;
-    const int hs = (warp - 2) >> 2;
+    const int cg = (warp - 2) >> 2;
     T* out = reinterpret_cast<T*>(p.out);
     const T* res = reinterpret_cast<const T*>(p.res);
     const bool vec_ok = (p.N % 8 == 0) && (p.ldo % 8 == 0) && (!p.res || p.ldr % 8 == 0);
-    constexpr int OUT_W = BN;            // accumulator columns per tile
-    constexpr int HALF = BN / 2;         // accumulator columns per warp (plain) ...
-    constexpr int W_COLS = HALF;         // max output columns per warp (GEGLU uses HALF / 2)
-    constexpr int NCH = HALF / 16;       // 16-column TMEM chunks per warp
-    constexpr int PITCH = W_COLS * 2 + 16;
     uint8_t* slab = staging + (size_t)(warp - 2) * Cfg::SLAB_BYTES;
     const int n_total = p.geglu ? p.N / 2 : p.N;
-    const int wcols = p.geglu ? HALF / 2 : HALF;   // output columns this warp produces per tile
+    const int wcols = p.geglu ? QW / 2 : QW;       // output columns this warp produces per tile
     const int CH = wcols / 8;                      // 16-byte chunks per slab row
     const int RPI = 32 / CH;                       // rows per phase-2 pass
     const int l_row = lane / CH, l_chunk = lane - l_row * CH;
     const bool l_active = l_row < RPI;
-    constexpr int MAX_PASS = (BN == 160) ? 11 : 8;
+    constexpr int RPI_MIN = 32 / (QW / 8);
+    constexpr int MAX_PASS = (32 + RPI_MIN - 1) / RPI_MIN;
+    auto ld_chunk = [&](uint32_t addr, uint32_t* r) {
+      if constexpr (CW == 16) tmem_ld16(addr, r);
+      else tmem_ld8(addr, r);
+    };
+    auto st_chunk = [&](uint32_t addr, const uint32_t* r) {
+      if constexpr (CW == 16) tmem_st16(addr, r);
+      else tmem_st8(addr, r);
+    };
+    auto epi_bar = [&]() { asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory"); };
     int it = 0;
     GemmWork work(p, wid, nworkers);
     int tile, kb0, kb1;
     // "accumulator drained": in a pair every epilogue thread of both CTAs arrives on the LEADER's barrier
+    // one arrival per warp (after a warp sync), not per thread: 256 serialised arrivals on one mbarrier per tile were
+    // a measurable part of the per-tile latency chain  epilogue -> tmem_empty -> next MMA
     auto release_acc = [&](int acc) {
       tc_fence_before();
-      if constexpr (PAIR) mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_empty_bar[acc]), 0));
-      else mbar_arrive(&tmem_empty_bar[acc]);
+      __syncwarp();
+      if (lane == 0) {
+        if constexpr (PAIR) mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_empty_bar[acc]), 0));
+        else mbar_arrive(&tmem_empty_bar[acc]);
+      }
     };
     for (; work.next(tile, kb0, kb1); ++it) {
       const int n_tile = tile % p.num_n_tiles;
@@ -353,21 +399,21 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
         // ---- stream-K partial: this CTA's range began inside the tile -> dump the fp32 accumulator, raise the flag
         mbar_wait(&tmem_full_bar[acc], acc_phase);
         tc_fence_after();
-        // workspace layout = the warps' own access order: [slot][q][hs][16-col chunk][4 x uint4][lane] -> every
+        // workspace layout = the warps' own access order: [slot][q][cg][chunk][CW/4 x uint4][lane] -> every
         // store / load instruction of a warp covers 512 contiguous bytes
         uint4* ws = reinterpret_cast<uint4*>(p.sk_ws) + (size_t)blockIdx.x * (128 * BN / 4) +
-                    (size_t)(q * 2 + hs) * (NCH * 4 * 32) + lane;
+                    (size_t)(q * NG + cg) * (NCH * (CW / 4) * 32) + lane;
 #pragma unroll 1
         for (int ch = 0; ch < NCH; ++ch) {
-          uint32_t r[16];
-          tmem_ld16(taddr + hs * HALF + ch * 16, r);
+          uint32_t r[CW];
+          ld_chunk(taddr + cg * QW + ch * CW, r);
           tmem_wait_ld();
 #pragma unroll
-          for (int g = 0; g < 4; ++g)
-            __stcg(ws + (ch * 4 + g) * 32, make_uint4(r[g * 4], r[g * 4 + 1], r[g * 4 + 2], r[g * 4 + 3]));
+          for (int g = 0; g < CW / 4; ++g)
+            __stcg(ws + (ch * (CW / 4) + g) * 32, make_uint4(r[g * 4], r[g * 4 + 1], r[g * 4 + 2], r[g * 4 + 3]));
         }
         release_acc(acc);
-        asm volatile("bar.sync 1, 256;" ::: "memory");  // all 8 epilogue warps have stored their slice
+        epi_bar();  // all epilogue warps have stored their slice
         if (warp == 2 && lane == 0) {
           __threadfence();
           asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p.sk_flags + blockIdx.x), "r"(1u) : "memory");
@@ -403,29 +449,29 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
         __syncwarp();
         for (int j = 1; j <= ncontrib; ++j) {
           const uint4* src = reinterpret_cast<const uint4*>(p.sk_ws) + (size_t)(blockIdx.x + j * sk_stride) * (128 * BN / 4) +
-                             (size_t)(q * 2 + hs) * (NCH * 4 * 32) + lane;
-          uint4 pr[NCH * 4];  // every 16-byte load of this contributor in flight at once
+                             (size_t)(q * NG + cg) * (NCH * (CW / 4) * 32) + lane;
+          uint4 pr[NCH * (CW / 4)];  // every 16-byte load of this contributor in flight at once
 #pragma unroll
-          for (int i = 0; i < NCH * 4; ++i) pr[i] = __ldcg(src + i * 32);
+          for (int i = 0; i < NCH * (CW / 4); ++i) pr[i] = __ldcg(src + i * 32);
 #pragma unroll
           for (int ch = 0; ch < NCH; ++ch) {
-            uint32_t r[16];
-            tmem_ld16(taddr + hs * HALF + ch * 16, r);
+            uint32_t r[CW];
+            ld_chunk(taddr + cg * QW + ch * CW, r);
             tmem_wait_ld();
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              const uint4 v = pr[ch * 4 + g];
+            for (int g = 0; g < CW / 4; ++g) {
+              const uint4 v = pr[ch * (CW / 4) + g];
               r[g * 4] = __float_as_uint(__uint_as_float(r[g * 4]) + __uint_as_float(v.x));
               r[g * 4 + 1] = __float_as_uint(__uint_as_float(r[g * 4 + 1]) + __uint_as_float(v.y));
               r[g * 4 + 2] = __float_as_uint(__uint_as_float(r[g * 4 + 2]) + __uint_as_float(v.z));
               r[g * 4 + 3] = __float_as_uint(__uint_as_float(r[g * 4 + 3]) + __uint_as_float(v.w));
             }
-            tmem_st16(taddr + hs * HALF + ch * 16, r);
+            st_chunk(taddr + cg * QW + ch * CW, r);
           }
         }
         tmem_wait_st();
         tc_fence_before();
-        asm volatile("bar.sync 1, 256;" ::: "memory");  // all partials consumed; other warps' columns are final
+        epi_bar();  // all partials consumed; other warps' columns are final
         tc_fence_after();
         if (warp == 2 && lane == 0)
           for (int j = 1; j <= ncontrib; ++j) p.sk_flags[blockIdx.x + j * sk_stride] = 0;  // re-arm for the next launch
@@ -476,7 +522,7 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
       };
       const float* ln_crow = p.ln_c + (size_t)ln_f * p.N;  // global fallback row of c
       if (vec_ok) {
-        const int n_warp = n_tile * (p.geglu ? HALF : OUT_W) + hs * wcols;  // first output column of this warp
+        const int n_warp = n_tile * (p.geglu ? TH : BN) + cg * wcols;  // first output column of this warp
         const bool chunk_ok = l_active && (n_warp + l_chunk * 8 < n_total);
         // ---- residual prefetch (coalesced; issued before the accumulator is ready => hidden by the main loop)
         uint4 rv[MAX_PASS];
@@ -489,10 +535,10 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
           }
         }
         // ---- epilogue vectors of this warp's column half (bias, or LN u and c): fetched into registers BEFORE the
-        // accumulator wait (latency hidden), parked in smem[tile parity] AFTER it.  The four warps sharing `hs` write
+        // accumulator wait (latency hidden), parked in smem[tile parity] AFTER it.  The four warps sharing `cg` write
         // identical values (benign); storing after the wait keeps the parity double-buffer race-free (tile i+2 cannot
         // become ready before every thread finished phase 1 of tile i).
-        constexpr int PV = (HALF + 31) / 32;
+        constexpr int PV = (QW + 31) / 32;
         float pre0[PV];
         {
           const float* v0 = ln ? p.ln_c + (size_t)ln_f0 * p.N : p.bias;
@@ -500,11 +546,11 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
           for (int j = 0; j < PV; ++j) {
             const int i = lane + j * 32;
             pre0[j] = 0.f;
-            if (i < HALF && v0) {
+            if (i < QW && v0) {
               if (!p.geglu) {
                 if (n_warp + i < n_total) pre0[j] = __ldg(v0 + n_warp + i);
-              } else {  // packed GEGLU vectors: tile-local [h (HALF) | gate (HALF)]; this warp: h/gate cols hs*wcols..
-                pre0[j] = __ldg(v0 + n_tile * BN + (i < wcols ? hs * wcols + i : HALF + hs * wcols + (i - wcols)));
+              } else {  // packed GEGLU vectors: tile-local [h (TH) | gate (TH)]; this warp: h/gate cols cg*wcols..
+                pre0[j] = __ldg(v0 + n_tile * BN + (i < wcols ? cg * wcols + i : TH + cg * wcols + (i - wcols)));
               }
             }
           }
@@ -512,13 +558,17 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
         mbar_wait(&tmem_full_bar[acc], acc_phase);
         tc_fence_after();
         if (ln) ln_finish();
-        float* bsm = bias_sm + (it & 1) * BN + hs * HALF;  // bias, or c of the tile's frame in LN mode
+        float* bsm = bias_sm + (it & 1) * BN + cg * QW;  // bias, or c of the tile's frame in LN mode
 #pragma unroll
         for (int j = 0; j < PV; ++j) {
           const int i = lane + j * 32;
-          if (i < HALF) bsm[i] = pre0[j];
+          if (i < QW) bsm[i] = pre0[j];
         }
         __syncwarp();
+#if RCDM_GEMM_EXPERIMENT == 2
+        release_acc(acc);
+        continue;
+#endif
         // ---- phase 1: v = scale * acc + vec  (plain: scale = 1, vec = bias; folded LayerNorm: scale = rstd, vec = c)
         const float scale = ln_a;
         if (ln && !ln_smem) {
@@ -526,67 +576,90 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
           // per-frame vector c comes through L1 instead of shared memory
           if (!p.geglu) {
 #pragma unroll 1
-            for (int c = 0; c < HALF; c += 16) {
-              uint32_t r[16];
-              tmem_ld16(taddr + hs * HALF + c, r);
+            for (int c = 0; c < QW; c += 8) {
+              uint32_t r[8];
+              tmem_ld8(taddr + cg * QW + c, r);
               tmem_wait_ld();
-              const int col = n_tile * BN + hs * HALF + c;
-              float v[16];
+              const int col = n_tile * BN + cg * QW + c;
+              float v[8];
 #pragma unroll
-              for (int i = 0; i < 16; ++i)
+              for (int i = 0; i < 8; ++i)
                 v[i] = fmaf(__uint_as_float(r[i]), scale, (col + i < p.N) ? __ldg(ln_crow + col + i) : 0.f);
               *reinterpret_cast<uint4*>(slab + lane * PITCH + c * 2) = pack8<T>(v);
-              *reinterpret_cast<uint4*>(slab + lane * PITCH + c * 2 + 16) = pack8<T>(v + 8);
             }
           } else {
 #pragma unroll 1
-            for (int c = 0; c < HALF / 2; c += 16) {
-              uint32_t rh[16], rg[16];
-              tmem_ld16(taddr + hs * (HALF / 2) + c, rh);
-              tmem_ld16(taddr + HALF + hs * (HALF / 2) + c, rg);
+            for (int c = 0; c < QW / 2; c += 8) {
+              uint32_t rh[8], rg[8];
+              tmem_ld8(taddr + cg * (QW / 2) + c, rh);
+              tmem_ld8(taddr + TH + cg * (QW / 2) + c, rg);
               tmem_wait_ld();
-              const int colh = n_tile * BN + hs * (HALF / 2) + c;
-              float v[16];
+              const int colh = n_tile * BN + cg * (QW / 2) + c;
+              float v[8];
 #pragma unroll
-              for (int i = 0; i < 16; ++i)
+              for (int i = 0; i < 8; ++i)
                 v[i] = fmaf(__uint_as_float(rh[i]), scale, __ldg(ln_crow + colh + i)) *
-                       gelu_erf_f(fmaf(__uint_as_float(rg[i]), scale, __ldg(ln_crow + colh + HALF + i)));
+                       gelu_erf_f(fmaf(__uint_as_float(rg[i]), scale, __ldg(ln_crow + colh + TH + i)));
               *reinterpret_cast<uint4*>(slab + lane * PITCH + c * 2) = pack8<T>(v);
-              *reinterpret_cast<uint4*>(slab + lane * PITCH + c * 2 + 16) = pack8<T>(v + 8);
             }
           }
         } else if (!p.geglu) {
-#pragma unroll 1
-          for (int c = 0; c < HALF; c += 16) {
-            uint32_t r[16];
-            tmem_ld16(taddr + hs * HALF + c, r);
-            tmem_wait_ld();
-            float v[16];
+          // the TMEM load of chunk c+1 is in flight while chunk c is scaled, packed and parked in the slab
+          uint32_t r[2][CW];
+          ld_chunk(taddr + cg * QW, r[0]);
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              const float4 b4 = *reinterpret_cast<const float4*>(bsm + c + g * 4);  // smem broadcast
-              v[g * 4] = fmaf(__uint_as_float(r[g * 4]), scale, b4.x);
-              v[g * 4 + 1] = fmaf(__uint_as_float(r[g * 4 + 1]), scale, b4.y);
-              v[g * 4 + 2] = fmaf(__uint_as_float(r[g * 4 + 2]), scale, b4.z);
-              v[g * 4 + 3] = fmaf(__uint_as_float(r[g * 4 + 3]), scale, b4.w);
+          for (int ci = 0; ci < NCH; ++ci) {
+            const int c = ci * CW;
+            tmem_wait_ld();
+            if (ci + 1 < NCH) ld_chunk(taddr + cg * QW + c + CW, r[(ci + 1) & 1]);
+            const uint32_t* rc = r[ci & 1];
+#pragma unroll
+            for (int g = 0; g < CW / 8; ++g) {
+              const float4 b0 = *reinterpret_cast<const float4*>(bsm + c + g * 8);  // smem broadcast
+              const float4 b1 = *reinterpret_cast<const float4*>(bsm + c + g * 8 + 4);
+              float v[8];
+              v[0] = fmaf(__uint_as_float(rc[g * 8]), scale, b0.x);
+              v[1] = fmaf(__uint_as_float(rc[g * 8 + 1]), scale, b0.y);
+              v[2] = fmaf(__uint_as_float(rc[g * 8 + 2]), scale, b0.z);
+              v[3] = fmaf(__uint_as_float(rc[g * 8 + 3]), scale, b0.w);
+              v[4] = fmaf(__uint_as_float(rc[g * 8 + 4]), scale, b1.x);
+              v[5] = fmaf(__uint_as_float(rc[g * 8 + 5]), scale, b1.y);
+              v[6] = fmaf(__uint_as_float(rc[g * 8 + 6]), scale, b1.z);
+              v[7] = fmaf(__uint_as_float(rc[g * 8 + 7]), scale, b1.w);
+              *reinterpret_cast<uint4*>(slab + lane * PITCH + (c + g * 8) * 2) = pack8<T>(v);
             }
-            *reinterpret_cast<uint4*>(slab + lane * PITCH + c * 2) = pack8<T>(v);
-            *reinterpret_cast<uint4*>(slab + lane * PITCH + c * 2 + 16) = pack8<T>(v + 8);
           }
         } else {
-#pragma unroll 1
-          for (int c = 0; c < HALF / 2; c += 16) {
-            uint32_t rh[16], rg[16];
-            tmem_ld16(taddr + hs * (HALF / 2) + c, rh);
-            tmem_ld16(taddr + HALF + hs * (HALF / 2) + c, rg);
-            tmem_wait_ld();
-            float v[16];
+          // GEGLU: h columns [cg * QW/2, +QW/2), gate columns TH + the same; outputs QW/2 per warp
+          constexpr int GW = QW / 2;
+          constexpr int GCW = (GW % 16 == 0) ? 16 : 8;
+          constexpr int GNCH = GW / GCW;
+          uint32_t rh[2][GCW], rg[2][GCW];
+          auto ldg_chunk = [&](uint32_t addr, uint32_t* r) {
+            if constexpr (GCW == 16) tmem_ld16(addr, r);
+            else tmem_ld8(addr, r);
+          };
+          ldg_chunk(taddr + cg * GW, rh[0]);
+          ldg_chunk(taddr + TH + cg * GW, rg[0]);
 #pragma unroll
-            for (int i = 0; i < 16; ++i)
-              v[i] = fmaf(__uint_as_float(rh[i]), scale, bsm[c + i]) *
-                     gelu_erf_f(fmaf(__uint_as_float(rg[i]), scale, bsm[wcols + c + i]));
-            *reinterpret_cast<uint4*>(slab + lane * PITCH + c * 2) = pack8<T>(v);
-            *reinterpret_cast<uint4*>(slab + lane * PITCH + c * 2 + 16) = pack8<T>(v + 8);
+          for (int ci = 0; ci < GNCH; ++ci) {
+            const int c = ci * GCW;
+            tmem_wait_ld();
+            if (ci + 1 < GNCH) {
+              ldg_chunk(taddr + cg * GW + c + GCW, rh[(ci + 1) & 1]);
+              ldg_chunk(taddr + TH + cg * GW + c + GCW, rg[(ci + 1) & 1]);
+            }
+            const uint32_t* ph = rh[ci & 1];
+            const uint32_t* pg = rg[ci & 1];
+#pragma unroll
+            for (int g = 0; g < GCW / 8; ++g) {
+              float v[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i)
+                v[i] = fmaf(__uint_as_float(ph[g * 8 + i]), scale, bsm[c + g * 8 + i]) *
+                       gelu_erf_f(fmaf(__uint_as_float(pg[g * 8 + i]), scale, bsm[wcols + c + g * 8 + i]));
+              *reinterpret_cast<uint4*>(slab + lane * PITCH + (c + g * 8) * 2) = pack8<T>(v);
+            }
           }
         }
         release_acc(acc);  // accumulator drained: the MMA warp may reuse it
@@ -606,7 +679,11 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
 #pragma unroll
                   for (int i = 0; i < 4; ++i) a2[i] = __hadd2(a2[i], b2[i]);
                 }
+#if RCDM_GEMM_EXPERIMENT != 1
                 *reinterpret_cast<uint4*>(out + (size_t)(m_warp + rr) * p.ldo + n_warp + l_chunk * 8) = sv;
+#else
+                if (sv.x == 0x12345678u) out[0] = DT<T>::from_f(0.f);  // keep the value alive without the store
+#endif
               }
             }
           }
@@ -648,16 +725,16 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
               ps += t.x;
               pss += t.y;
             }
-            if (m_warp + lane < p.M) p.stats_out[(size_t)(n_tile * 2 + hs) * p.M + m_warp + lane] = make_float2(ps, pss);
+            if (m_warp + lane < p.M) p.stats_out[(size_t)(n_tile * NG + cg) * p.M + m_warp + lane] = make_float2(ps, pss);
           }
         }
         __syncwarp();  // the slab is rewritten for the next tile
       } else {
-        // ---- scalar fallback (conv_out: N = 4): thread <-> row, direct stores; only the hs == 0 warps work
+        // ---- scalar fallback (conv_out: N = 4): thread <-> row, direct stores; only the cg == 0 warps work
         const int m = m_warp + lane;
         mbar_wait(&tmem_full_bar[acc], acc_phase);
         tc_fence_after();
-        if (hs == 0) {
+        if (cg == 0) {
 #pragma unroll 1
           for (int c = 0; c < BN; c += 16) {
             const int n = n_tile * BN + c;

@@ -60,6 +60,7 @@ struct GemmDesc {
   int force_bn;  // 0 = heuristic
   int no_sk;     // 1 = never use the stream-K decomposition for this launch
   int no_pair;   // 1 = never use the CTA-pair (cta_group::2) kernel for this launch
+  int force_pair;  // 1 = always use it (when there are >= 2 M tiles); set by the plan-time autotuner
   // folded LayerNorm (see GemmParams): producer side / consumer side
   float2* stats_out;
   const float2* stats_in;

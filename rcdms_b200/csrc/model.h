@@ -126,6 +126,8 @@ struct rcdm_unet_impl {
   bool taps_enabled = false;
   std::map<std::string, TapInfo> taps;
   int simple = 0;
+  int autotune = 0;  // RCDM_AUTOTUNE=1: plan-time choice of the GEMM tile width / CTA pairing per distinct problem
+  std::map<std::string, std::pair<int, int>> tune_cache;  // problem signature -> (tile width, pair)
   int ln_fold = 1;  // LayerNorm folded into the consuming GEMM (RCDM_LN_FOLD=0: separate layernorm kernels)
   // per-call inputs (read by the recorded ops)
   const void* cur_sample = nullptr;

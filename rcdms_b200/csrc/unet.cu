@@ -512,11 +512,68 @@ struct Planner {
     }
     GemmLaunch l;
     std::string e;
+    if (h->autotune) tune(d);
     if (!gemm_prepare(d, &l, &e)) return fail(e);
     push([l](cudaStream_t s) {
       gemm_launch(l, s);
       g_launches++;
     }, kind, flops, bytes, d.M, d.N, (int)k_alg);
+  }
+  // Plan-time autotuning: every distinct GEMM problem is timed once (CUDA events, real buffers of the arena) with
+  // each admissible tile width x {single CTA, CTA pair}; the winner is cached by problem signature.  The K summation
+  // order of an output element does not depend on these two choices, so results stay bitwise identical; the stream-K
+  // decision (which does change the order) stays with the deterministic heuristic.
+  void tune(GemmDesc& d) {
+    char key[160];
+    snprintf(key, sizeof key, "%d/%d/%d/%d/%d%d%d/%d/%d/%d/%d/%d/%d", d.M, d.N, d.Ktot, d.nseg, d.seg[0].mode, d.seg[1].mode,
+             d.seg[2].mode, d.geglu, d.res != nullptr, d.stats_out != nullptr, d.stats_in != nullptr, d.Ho, d.bias != nullptr);
+    auto it = h->tune_cache.find(key);
+    if (it == h->tune_cache.end()) {
+      std::vector<int> bns;
+      if (d.geglu) bns = {GEGLU_BN};
+      else if (d.stats_out) bns = {0};  // the consumer reads 2 * N-tiles statistic parts: keep the heuristic width
+      else {
+        bns = {64, 128};
+        if (d.N % 160 == 0) bns.push_back(160);
+        if (d.N <= 64) bns = {64};
+      }
+      cudaStream_t ts;
+      cudaEvent_t e0, e1;
+      cudaStreamCreateWithFlags(&ts, cudaStreamNonBlocking);
+      cudaEventCreate(&e0);
+      cudaEventCreate(&e1);
+      float best = 1e30f;
+      std::pair<int, int> pick{0, 0};
+      for (int bn : bns)
+        for (int pr = 0; pr < 2; ++pr) {
+          GemmDesc c = d;
+          c.force_bn = bn;
+          c.no_pair = pr ? 0 : 1;
+          c.force_pair = pr;
+          GemmLaunch l;
+          std::string err;
+          if (!gemm_prepare(c, &l, &err)) continue;
+          if (pr && !l.pair) continue;  // pairing not applicable (single M tile)
+          for (int w = 0; w < 2; ++w) gemm_launch(l, ts);
+          cudaEventRecord(e0, ts);
+          for (int r = 0; r < 6; ++r) gemm_launch(l, ts);
+          cudaEventRecord(e1, ts);
+          if (cudaEventSynchronize(e1) != cudaSuccess) continue;
+          float ms = 0.f;
+          cudaEventElapsedTime(&ms, e0, e1);
+          if (ms < best) {
+            best = ms;
+            pick = {bn, pr};
+          }
+        }
+      cudaEventDestroy(e0);
+      cudaEventDestroy(e1);
+      cudaStreamDestroy(ts);
+      it = h->tune_cache.emplace(key, pick).first;
+    }
+    d.force_bn = it->second.first;
+    d.no_pair = it->second.second ? 0 : 1;
+    d.force_pair = it->second.second;
   }
   // plain GEMM: out[M,N] = A[M,K] W^T (+bias)(+res)
   // ln != nullptr: the input is consumed through a folded LayerNorm (statistics at stats_off, emitted by the GEMM that
@@ -1080,6 +1137,8 @@ int unet_create(const rcdm_unet_config* cfg, rcdm_unet** out) {
   h->cfg = *cfg;
   const char* env = getenv("RCDM_SIMPLE");
   h->simple = env && env[0] == '1';
+  const char* at = getenv("RCDM_AUTOTUNE");
+  h->autotune = at && at[0] == '1';  // measured: no gain over the heuristics at the 512x512 shapes => opt-in
   const char* lf = getenv("RCDM_LN_FOLD");
   h->ln_fold = !(lf && lf[0] == '0');
   if (build_model(h)) {
