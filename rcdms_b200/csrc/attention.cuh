@@ -678,12 +678,15 @@ __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
-template <typename T, int F>
+// DH = compile-time head dim (40 / 80 / 160: loops fully unrolled, address arithmetic folded; the kernel is bound by
+// instruction issue, ncu: 70 % issue-active) or 0 = runtime `d_rt`.
+template <typename T, int F, int DH>
 __global__ void __launch_bounds__(512)
-temporal_attn_tile_kernel(const T* __restrict__ qkv, T* __restrict__ out, int hw, int heads, int d, int PT,
+temporal_attn_tile_kernel(const T* __restrict__ qkv, T* __restrict__ out, int hw, int heads, int d_rt, int PT,
                           float scale) {
   extern __shared__ __align__(16) uint8_t tsm[];
   T* sm = reinterpret_cast<T*>(tsm);  // [F][PT][3C]
+  const int d = DH > 0 ? DH : d_rt;
   const int C = heads * d, ld = 3 * C;
   const int tiles_per_b = hw / PT;
   const int b = blockIdx.x / tiles_per_b, pix0 = (blockIdx.x - b * tiles_per_b) * PT;
@@ -704,13 +707,17 @@ temporal_attn_tile_kernel(const T* __restrict__ qkv, T* __restrict__ out, int hw
     float s[F];
 #pragma unroll
     for (int j = 0; j < F; ++j) s[j] = 0.f;
-    for (int c = 0; c < d; c += 8) {
+    const T* kbase = sm + (size_t)p * ld + C + h * d;       // + j * PT * ld per frame; V at + C
+    const int fstride = PT * ld;
+#pragma unroll
+    for (int c = 0; c < (DH > 0 ? DH : 1 << 30); c += 8) {
+      if (DH == 0 && c >= d) break;
       float qf[8];
       unpack8<T>(*reinterpret_cast<const uint4*>(qp + c), qf);
 #pragma unroll
       for (int j = 0; j < F; ++j) {
         float kf[8];
-        unpack8<T>(*reinterpret_cast<const uint4*>(sm + (size_t)(j * PT + p) * ld + C + h * d + c), kf);
+        unpack8<T>(*reinterpret_cast<const uint4*>(kbase + j * fstride + c), kf);
 #pragma unroll
         for (int e = 0; e < 8; ++e) s[j] = fmaf(qf[e], kf[e], s[j]);
       }
@@ -730,14 +737,16 @@ temporal_attn_tile_kernel(const T* __restrict__ qkv, T* __restrict__ out, int hw
     const float inv = 1.0f / sum;
 #pragma unroll
     for (int j = 0; j < F; ++j) s[j] *= inv;
-    for (int c = 0; c < d; c += 8) {
+#pragma unroll
+    for (int c = 0; c < (DH > 0 ? DH : 1 << 30); c += 8) {
+      if (DH == 0 && c >= d) break;
       float o[8];
 #pragma unroll
       for (int e = 0; e < 8; ++e) o[e] = 0.f;
 #pragma unroll
       for (int j = 0; j < F; ++j) {
         float vf[8];
-        unpack8<T>(*reinterpret_cast<const uint4*>(sm + (size_t)(j * PT + p) * ld + 2 * C + h * d + c), vf);
+        unpack8<T>(*reinterpret_cast<const uint4*>(kbase + C + j * fstride + c), vf);
 #pragma unroll
         for (int e = 0; e < 8; ++e) o[e] = fmaf(s[j], vf[e], o[e]);
       }

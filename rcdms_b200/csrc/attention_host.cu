@@ -140,18 +140,25 @@ void attn_simple_launch(const AttnDesc& d, cudaStream_t s) {
   else attn_simple_kernel<__nv_bfloat16><<<blocks, 128, 0, s>>>(d);
 }
 
-template <typename T, int F> static void temporal_tiled(const void* qkv, void* out, int batch, int hw, int heads, int d,
-                                                        int PT, float scale, cudaStream_t s) {
+template <typename T, int F, int DH> static void temporal_tiled_d(const void* qkv, void* out, int batch, int hw, int heads,
+                                                                 int d, int PT, float scale, cudaStream_t s) {
   const int C = heads * d;
   const size_t smem = (size_t)F * PT * 3 * C * sizeof(T);
   const int threads = (PT * heads * F + 31) / 32 * 32;
   static bool attr_done = false;  // per instantiation
   if (!attr_done) {
-    cudaFuncSetAttribute(temporal_attn_tile_kernel<T, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    cudaFuncSetAttribute(temporal_attn_tile_kernel<T, F, DH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
     attr_done = true;
   }
-  launch_k(temporal_attn_tile_kernel<T, F>, dim3(batch * (hw / PT)), dim3(threads), smem, s,
+  launch_k(temporal_attn_tile_kernel<T, F, DH>, dim3(batch * (hw / PT)), dim3(threads), smem, s,
            reinterpret_cast<const T*>(qkv), reinterpret_cast<T*>(out), hw, heads, d, PT, scale);
+}
+template <typename T, int F> static void temporal_tiled(const void* qkv, void* out, int batch, int hw, int heads, int d,
+                                                        int PT, float scale, cudaStream_t s) {
+  if (F == 5 && d == 40) temporal_tiled_d<T, F, 40>(qkv, out, batch, hw, heads, d, PT, scale, s);
+  else if (F == 5 && d == 80) temporal_tiled_d<T, F, 80>(qkv, out, batch, hw, heads, d, PT, scale, s);
+  else if (F == 5 && d == 160) temporal_tiled_d<T, F, 160>(qkv, out, batch, hw, heads, d, PT, scale, s);
+  else temporal_tiled_d<T, F, 0>(qkv, out, batch, hw, heads, d, PT, scale, s);
 }
 
 void temporal_attn_launch(int dt, const void* qkv, void* out, int batch, int frames, int hw, int heads, int d,

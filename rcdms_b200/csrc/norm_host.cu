@@ -71,7 +71,9 @@ void gn_configure(GnLaunch* l, int dt, const void* x0, int C0, const void* x1, i
     const int rpc = (rows_per_stat + cps - 1) / cps;
     cps = (rows_per_stat + rpc - 1) / rpc;  // drop CTAs that would own no rows
     if (kf > rpc) kf = rpc;
-    const size_t scratch_b = (size_t)kf * 2 * C * 4;
+    size_t scratch_b = (size_t)kf * 2 * C * 4;
+    if (scratch_b < (size_t)cps * groups * 8) scratch_b = (size_t)cps * groups * 8;  // also holds the batch's partials
+    scratch_b = (scratch_b + 15) & ~size_t(15);
     const size_t budget = 232448 - 1024 - scratch_b;
     size_t cache_rows = budget / ((size_t)C * 2);
     if (cache_rows > (size_t)rpc) cache_rows = rpc;

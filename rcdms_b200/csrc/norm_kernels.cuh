@@ -207,7 +207,9 @@ __global__ void __launch_bounds__(512, 1) gn_fused_kernel(const GnArgs a, const 
   const int vecs = C / 8;
   // blockDim.x == vecs * k rounded up to a whole number of warps; threads with rl >= k only help in the reductions
   float* red = reinterpret_cast<float*>(gsm);                                // [k][2][C]
-  uint4* cache = reinterpret_cast<uint4*>(gsm + (size_t)k * 2 * C * 4);      // [cache_rows][vecs]
+  // scratch = max(block-reduction array, the batch's cps x groups partials); must match gn_configure (norm_host.cu)
+  const size_t scratch_b = max((size_t)k * 2 * C * 4, (size_t)cps * a.groups * 8);
+  uint4* cache = reinterpret_cast<uint4*>(gsm + ((scratch_b + 15) & ~size_t(15)));  // [cache_rows][vecs]
   const int v = threadIdx.x % vecs, rl = threadIdx.x / vecs;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
   const int sb = blockIdx.x / cps, part = blockIdx.x - sb * cps;
@@ -311,10 +313,16 @@ __global__ void __launch_bounds__(512, 1) gn_fused_kernel(const GnArgs a, const 
       }
     }
     __syncthreads();
+    // all cps * groups partials of this batch -> shared memory in ONE round trip (coalesced, every load in flight),
+    // instead of a serial chain of L2 loads per group; `red` is dead by now and large enough (host-checked)
+    float2* psm = reinterpret_cast<float2*>(red);
+    for (int i = threadIdx.x; i < cps * a.groups; i += blockDim.x)
+      psm[i] = __ldcg(&a.partial[(size_t)sb * cps * a.groups + i]);
+    __syncthreads();
     for (int g = warp; g < a.groups; g += nw) {
       double gs = 0.0, gss = 0.0;
       for (int pp = lane; pp < cps; pp += 32) {
-        const float2 z = __ldcg(&a.partial[((size_t)sb * cps + pp) * a.groups + g]);
+        const float2 z = psm[pp * a.groups + g];
         gs += z.x;
         gss += z.y;
       }
