@@ -414,6 +414,12 @@ flash_attn4_kernel(const __grid_constant__ AttnMaps maps, const AttnParams p) {
       const uint32_t q_addr = smem_u32(sQ);
       auto load_kv = [&](int t) {
         const int s = t % KV;
+#if RCDM_ATTN_EXPERIMENT == 5
+        if (t >= KV) {  // bottleneck analysis only: no K/V traffic after the first tiles
+          mbar_expect_tx(&kv_full[s], 0);
+          return;
+        }
+#endif
         mbar_expect_tx(&kv_full[s], 2 * Cfg::KV_BYTES);
         tma_load_5d(sK + s * Cfg::KV_BYTES, &maps.k, &kv_full[s], 0, t * BN, 0, head, img);
         tma_load_5d(sV + s * Cfg::KV_BYTES, &maps.v, &kv_full[s], 0, t * BN, 0, head, img);

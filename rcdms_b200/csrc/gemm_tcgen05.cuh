@@ -25,7 +25,9 @@
 // Compile-time experiment switch for bottleneck analysis (never set in a product build; scripts/build_variants.sh):
 //   1 = epilogue skips the global stores, 2 = epilogue skips phase 1 math (TMEM -> slab) as well,
 //   3 = producer loads the A tile only for the first k-block of a tile (B still streams), 4 = neither A nor B after
-//   the first k-block of a tile (MMAs run on stale smem): isolates epilogue + MMA issue
+//   the first k-block of a tile (MMAs run on stale smem): isolates epilogue + MMA issue,
+//   5 = phase 1 without the TMEM loads, 6 = no phase 2 (slab reads / residual add / stores), 7 = phase 1 loads TMEM
+//   but skips the math and the slab stores
 #ifndef RCDM_GEMM_EXPERIMENT
 #define RCDM_GEMM_EXPERIMENT 0
 #endif
@@ -129,7 +131,7 @@ struct GemmMaps {
 // the tensor pipe, bounds the single-CTA kernel (128x160: 115 B/clk at full MMA rate; pair 256x160: 83 B/clk).
 template <int BN, bool PAIR = false> struct GemmCfg {
   static constexpr int BM = 128, BK = 64;
-  static constexpr int STAGES = PAIR ? (BN <= 64 ? 8 : BN <= 128 ? 7 : 6) : ((BN <= 64) ? 6 : 5);
+  static constexpr int STAGES = PAIR ? (BN <= 64 ? 8 : BN <= 128 ? 7 : 6) : ((BN <= 64) ? 6 : (BN <= 128 ? 5 : 4));
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = (PAIR ? BN / 2 : BN) * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
@@ -606,13 +608,24 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
         } else if (!p.geglu) {
           // the TMEM load of chunk c+1 is in flight while chunk c is scaled, packed and parked in the slab
           uint32_t r[2][CW];
+#if RCDM_GEMM_EXPERIMENT == 5
+#pragma unroll
+          for (int i = 0; i < CW; ++i) r[0][i] = r[1][i] = __float_as_uint(0.001f * (float)(i + lane));
+#else
           ld_chunk(taddr + cg * QW, r[0]);
+#endif
 #pragma unroll
           for (int ci = 0; ci < NCH; ++ci) {
             const int c = ci * CW;
+#if RCDM_GEMM_EXPERIMENT != 5
             tmem_wait_ld();
             if (ci + 1 < NCH) ld_chunk(taddr + cg * QW + c + CW, r[(ci + 1) & 1]);
+#endif
             const uint32_t* rc = r[ci & 1];
+#if RCDM_GEMM_EXPERIMENT == 7
+            if (rc[0] == 0x7fc12345u) slab[lane] = 1;  // keep the loads alive
+            continue;
+#endif
 #pragma unroll
             for (int g = 0; g < CW / 8; ++g) {
               const float4 b0 = *reinterpret_cast<const float4*>(bsm + c + g * 8);  // smem broadcast
@@ -664,6 +677,9 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
         }
         release_acc(acc);  // accumulator drained: the MMA warp may reuse it
         __syncwarp();
+#if RCDM_GEMM_EXPERIMENT == 6
+        continue;
+#endif
         // ---- phase 2
         if (!p.stats_out) {
           if (chunk_ok) {
