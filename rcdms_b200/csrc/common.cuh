@@ -188,6 +188,18 @@ __device__ __forceinline__ void tma_load_5d(void* smem, const CUtensorMap* m, ui
       : "memory");
 }
 
+// TMA store (tile mode) of a dense shared-memory box to global memory; out-of-range rows / columns are clipped.
+// Bulk-group completion: commit, then wait for the smem READS (buffer reusable) or for full completion.
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* smem, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(smem_u32(smem)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
 // ------------------------------------------------------------------------------------------
 // Thread-block cluster / CTA-pair (cta_group::2) primitives
 // ------------------------------------------------------------------------------------------

@@ -263,6 +263,26 @@ bool gemm_prepare(const GemmDesc& d, GemmLaunch* l, std::string* err) {
     uint32_t box[2] = {64, (uint32_t)(l->pair ? bn / 2 : bn)};
     if (!encode_tmap(&l->maps.b, d.w, 2, dims, str, box, true, err)) return false;
   }
+  // ---- epilogue through the staging buffers + TMA: needs 16-byte aligned rows of the output / residual
+  {
+    const int n_out = d.geglu ? d.N / 2 : d.N;
+    const int wcols = (d.geglu ? bn / 2 : bn) / RCDM_EPI_GROUPS;
+    const bool ok = (d.N % 8 == 0) && (d.ldo % 8 == 0) && (!d.res || d.ldr % 8 == 0) && n_out % 8 == 0 &&
+                    (reinterpret_cast<uintptr_t>(d.out) & 15) == 0 &&
+                    (!d.res || (reinterpret_cast<uintptr_t>(d.res) & 15) == 0) && (wcols * 2) % 16 == 0;
+    p.epi_tma = ok ? 1 : 0;
+    if (ok) {
+      uint64_t dims[2] = {(uint64_t)n_out, (uint64_t)d.M};
+      uint32_t box[2] = {(uint32_t)wcols, 128};
+      uint64_t str[1] = {(uint64_t)d.ldo * 2};
+      if (!encode_tmap(&l->maps.o, d.out, 2, dims, str, box, false, err)) return false;
+      if (d.res) {
+        uint64_t strr[1] = {(uint64_t)d.ldr * 2};
+        if (!encode_tmap(&l->maps.r, d.res, 2, dims, strr, box, false, err)) return false;
+      }
+    }
+    if (!ok && (d.stats_out || d.stats_in || d.geglu)) return fail("this epilogue needs 16-byte aligned output rows");
+  }
   p.num_m_tiles = l->pair ? (m_tiles + 1) / 2 : m_tiles;  // pair mode: counted in 256-row tile pairs
   p.num_n_tiles = (d.N + bn - 1) / bn;
   const int tiles = p.num_m_tiles * p.num_n_tiles;
@@ -271,7 +291,7 @@ bool gemm_prepare(const GemmDesc& d, GemmLaunch* l, std::string* err) {
   l->grid = dim3((tiles < sms ? tiles : sms) * cta_per_worker, 1, 1);
   // ---- stream-K when data-parallel tiling leaves the last wave (or most of the GPU) idle
   p.sk = 0;
-  const bool vec_ok = (d.N % 8 == 0) && (d.ldo % 8 == 0) && (!d.res || d.ldr % 8 == 0);
+  const bool vec_ok = p.epi_tma != 0;
   const int min_saving = sk_min_saving();
   if (min_saving > 0 && vec_ok && !d.no_sk && g_sk_ws && sms * cta_per_worker <= g_sk_slots && tiles % sms != 0) {
     const double waves = (double)tiles / sms;

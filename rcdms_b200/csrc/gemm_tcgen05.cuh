@@ -6,9 +6,10 @@
 //   warp 0     TMA producer  (one elected lane)  : HBM/L2 -> 128B-swizzled smem ring (5-6 stages), runs ahead
 //                                                  across tile boundaries
 //   warp 1     MMA issuer    (one elected lane)  : tcgen05.mma into one of TWO TMEM accumulators; owns TMEM alloc
-//   warps 2-9  epilogue (8 warps)                : residual prefetch (coalesced, before the accumulator is ready)
-//                                                  -> tcgen05.ld (+bias / GEGLU) -> 16-bit smem staging slab
-//                                                  -> 16-byte lane-contiguous global stores (+residual)
+//   warps 2-9  epilogue (8 warps)                : tcgen05.ld -> scale * acc + vector (+GEGLU) (+residual tile, which the
+//                                                  producer TMA-loaded into the staging buffer a tile ahead)
+//                                                  -> 16-bit staging buffer (2 buffers) -> ONE TMA store per column
+//                                                  group, issued by one thread (no per-thread global stores)
 // so the main loop of tile i+1 overlaps the epilogue of tile i.
 //
 // The K loop runs over up to three "segments", each reading A through its own TMA tensor map(s):
@@ -23,11 +24,10 @@
 #include "common.cuh"
 
 // Compile-time experiment switch for bottleneck analysis (never set in a product build; scripts/build_variants.sh):
-//   1 = epilogue skips the global stores, 2 = epilogue skips phase 1 math (TMEM -> slab) as well,
 //   3 = producer loads the A tile only for the first k-block of a tile (B still streams), 4 = neither A nor B after
-//   the first k-block of a tile (MMAs run on stale smem): isolates epilogue + MMA issue,
-//   5 = phase 1 without the TMEM loads, 6 = no phase 2 (slab reads / residual add / stores), 7 = phase 1 loads TMEM
-//   but skips the math and the slab stores
+//   the first k-block of a tile (MMAs run on stale smem): isolates epilogue + MMA issue.
+// (Measured with the earlier per-thread-store epilogue: the slab -> registers -> global "phase 2" cost 27 % of a
+//  K = 320 GEMM and the TMEM loads nothing, which is why the epilogue now ends in TMA stores.)
 #ifndef RCDM_GEMM_EXPERIMENT
 #define RCDM_GEMM_EXPERIMENT 0
 #endif
@@ -63,6 +63,7 @@ struct GemmParams {
   const void* res;    // residual [M, ldr] or nullptr (may alias out)
   int ldr;
   int geglu;          // 1: out[m, j] = (acc[j] + b[j]) * gelu(acc[BN/2 + j] + b[BN/2 + j]) per tile
+  int epi_tma;        // 1: vectorised epilogue through the staging buffers + TMA (maps.o / maps.r valid)
   // stream-K: the (tile, k-block) iteration space is cut into gridDim.x equal contiguous ranges, so a GEMM whose
   // tile count does not fill the SMs evenly still keeps every tensor core busy.  A CTA whose range starts inside a
   // tile dumps that partial accumulator (fp32) to sk_ws[blockIdx.x] and raises sk_flags[blockIdx.x]; the CTA that
@@ -123,6 +124,8 @@ struct GemmWork {
 struct GemmMaps {
   CUtensorMap a[4];
   CUtensorMap b;
+  CUtensorMap o;  // output   [M, n_out]: box (columns of one epilogue warp group, 128 rows), TMA store
+  CUtensorMap r;  // residual [M, n_out]: same box, TMA load into the staging buffer
 };
 
 // PAIR = true: CTA-pair kernel (cluster of 2, tcgen05 cta_group::2).  The pair computes a 256 x BN tile: CTA r holds A
@@ -131,18 +134,18 @@ struct GemmMaps {
 // the tensor pipe, bounds the single-CTA kernel (128x160: 115 B/clk at full MMA rate; pair 256x160: 83 B/clk).
 template <int BN, bool PAIR = false> struct GemmCfg {
   static constexpr int BM = 128, BK = 64;
-  static constexpr int STAGES = PAIR ? (BN <= 64 ? 8 : BN <= 128 ? 7 : 6) : ((BN <= 64) ? 6 : (BN <= 128 ? 5 : 4));
+  static constexpr int STAGES = PAIR ? (BN <= 64 ? 8 : BN <= 128 ? 6 : 5) : ((BN <= 64) ? 6 : (BN <= 128 ? 5 : 4));
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = (PAIR ? BN / 2 : BN) * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int NG = RCDM_EPI_GROUPS;   // column groups; 4 * NG epilogue warps
   static constexpr int QW = BN / NG;           // accumulator columns per epilogue warp
   static constexpr int THREADS = 64 + 128 * NG;
-  // every epilogue warp has a private slab of 32 rows x QW 16-bit values; the pitch keeps the 16-byte row accesses of
-  // a quarter warp on distinct banks (QW = 40: 80 B = 20 words already does; otherwise + 16 B)
-  static constexpr int PITCH = (QW == 40) ? 80 : QW * 2 + 16;
-  static constexpr int SLAB_BYTES = 32 * PITCH;
-  static constexpr int STAGING_BYTES = 4 * NG * SLAB_BYTES;
+  // staging buffer = the 128 x BN 16-bit output tile as NG dense [128 rows][QW] parts (TMA box layout); two buffers
+  // (tile parity) so the residual of tile i+1 loads while tile i is written and stored
+  static constexpr int PART_BYTES = 128 * QW * 2;
+  static constexpr int STG_BYTES = NG * PART_BYTES;
+  static constexpr int STAGING_BYTES = 2 * STG_BYTES;
   static constexpr int ACC_STRIDE = BN <= 64 ? 64 : BN <= 128 ? 128 : 256;  // TMEM columns between the 2 accumulators
   static constexpr int TMEM_COLS = 2 * ACC_STRIDE;
   // two buffers (tile parity) of BN fp32 epilogue values: bias, or the folded-LayerNorm vector c
@@ -181,7 +184,8 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
   uint64_t* empty_bar = bars + STAGES;
   uint64_t* tmem_full_bar = bars + 2 * STAGES;       // [2]
   uint64_t* tmem_empty_bar = bars + 2 * STAGES + 2;  // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  uint64_t* res_full = bars + 2 * STAGES + 4;        // [2] residual tile landed in staging[b]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 6);
   float* bias_sm = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);  // [2 parity][BN]
 
   const int warp = threadIdx.x >> 5;
@@ -190,6 +194,10 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&maps.b);
     tma_prefetch_desc(&maps.a[0]);
+    if (p.epi_tma) {
+      tma_prefetch_desc(&maps.o);
+      if (p.res) tma_prefetch_desc(&maps.r);
+    }
   }
   if (warp == 1) {
     if (lane == 0) {
@@ -200,6 +208,7 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
       for (int i = 0; i < 2; ++i) {
         mbar_init(&tmem_full_bar[i], 1);
         mbar_init(&tmem_empty_bar[i], (PAIR ? 8 : 4) * Cfg::NG);  // one arrival per epilogue warp (pair: of both CTAs)
+        mbar_init(&res_full[i], 1);
       }
       fence_mbar_init();
     }
@@ -343,30 +352,23 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
   } else {
     // =================================== epilogue (4 * NG warps) ===================================
     // warp -> (q, cg): q = TMEM lane quarter (rows q*32..+31), cg = which column group of the tile.
-    // phase 1 (thread <-> row):  TMEM -> registers, scale * acc + vector (smem broadcast), GEGLU -> 16-bit private slab
-    // phase 2 (lane <-> fixed 16-byte column chunk, RPI rows per pass): slab (+ prefetched residual, packed
-    //          half2 add == fp32 add + one rounding) -> coalesced global stores
+    // thread <-> row: TMEM -> registers, scale * acc + vector (smem broadcast), GEGLU, + residual (packed half2 add ==
+    // fp32 add + one rounding) -> this row's slice of the staging buffer; then one thread issues the TMA stores.
     constexpr int NG = Cfg::NG;
     constexpr int QW = Cfg::QW;          // accumulator columns per warp
     constexpr int TH = BN / 2;           // GEGLU: gate columns start at TH
     constexpr int CW = (QW % 16 == 0) ? 16 : 8;  // TMEM columns per tcgen05.ld
     constexpr int NCH = QW / CW;
-    constexpr int PITCH = Cfg::PITCH;
     constexpr int EPI_THREADS = 128 * NG;
     const int q = warp & 3;
     const int cg = (warp - 2) >> 2;
     T* out = reinterpret_cast<T*>(p.out);
     const T* res = reinterpret_cast<const T*>(p.res);
-    const bool vec_ok = (p.N % 8 == 0) && (p.ldo % 8 == 0) && (!p.res || p.ldr % 8 == 0);
-    uint8_t* slab = staging + (size_t)(warp - 2) * Cfg::SLAB_BYTES;
+    const bool vec_ok = p.epi_tma != 0;
     const int n_total = p.geglu ? p.N / 2 : p.N;
     const int wcols = p.geglu ? QW / 2 : QW;       // output columns this warp produces per tile
-    const int CH = wcols / 8;                      // 16-byte chunks per slab row
-    const int RPI = 32 / CH;                       // rows per phase-2 pass
-    const int l_row = lane / CH, l_chunk = lane - l_row * CH;
-    const bool l_active = l_row < RPI;
-    constexpr int RPI_MIN = 32 / (QW / 8);
-    constexpr int MAX_PASS = (32 + RPI_MIN - 1) / RPI_MIN;
+    const int tile_cols = p.geglu ? TH : BN;       // output columns per tile
+    const bool storer = warp == 2 && lane == 0;    // issues the TMA stores / residual loads, owns the bulk groups
     auto ld_chunk = [&](uint32_t addr, uint32_t* r) {
       if constexpr (CW == 16) tmem_ld16(addr, r);
       else tmem_ld8(addr, r);
@@ -377,8 +379,29 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
     };
     auto epi_bar = [&]() { asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory"); };
     int it = 0;
+    int ot = 0;  // output-producing work items so far (stream-K partial dumps do not count)
     GemmWork work(p, wid, nworkers);
+    GemmWork peek(p, wid, nworkers);  // runs one output tile ahead (storer thread only): residual prefetch
     int tile, kb0, kb1;
+    // residual tile of output item `o` (tile index `t`) -> staging[o & 1] by TMA, completion on res_full[o & 1]
+    auto issue_residual = [&](int t, int o) {
+      const int nt = t % p.num_n_tiles;
+      const int mt = PAIR ? 2 * (t / p.num_n_tiles) + (int)rank : t / p.num_n_tiles;
+      const int b = o & 1;
+      int parts = 0;
+      for (int g = 0; g < NG; ++g) parts += (nt * BN + g * QW) < p.N;
+      mbar_expect_tx(&res_full[b], parts * Cfg::PART_BYTES);
+      for (int g = 0; g < parts; ++g)
+        tma_load_2d(staging + b * Cfg::STG_BYTES + g * Cfg::PART_BYTES, &maps.r, &res_full[b], nt * BN + g * QW, mt * 128);
+    };
+    if (storer && vec_ok && res) {  // residual of the first output tile
+      int nt, nk0, nk1;
+      while (peek.next(nt, nk0, nk1))
+        if (nk0 == 0) {
+          issue_residual(nt, 0);
+          break;
+        }
+    }
     // "accumulator drained": in a pair every epilogue thread of both CTAs arrives on the LEADER's barrier
     // one arrival per warp (after a warp sync), not per thread: 256 serialised arrivals on one mbarrier per tile were
     // a measurable part of the per-tile latency chain  epilogue -> tmem_empty -> next MMA
@@ -524,22 +547,27 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
       };
       const float* ln_crow = p.ln_c + (size_t)ln_f * p.N;  // global fallback row of c
       if (vec_ok) {
-        const int n_warp = n_tile * (p.geglu ? TH : BN) + cg * wcols;  // first output column of this warp
-        const bool chunk_ok = l_active && (n_warp + l_chunk * 8 < n_total);
-        // ---- residual prefetch (coalesced; issued before the accumulator is ready => hidden by the main loop)
-        uint4 rv[MAX_PASS];
-        if (res) {
-#pragma unroll
-          for (int u = 0; u < MAX_PASS; ++u) {
-            const int rr = u * RPI + l_row;
-            if (chunk_ok && rr < 32 && m_warp + rr < p.M)
-              rv[u] = *reinterpret_cast<const uint4*>(res + (size_t)(m_warp + rr) * p.ldr + n_warp + l_chunk * 8);
+        const int n_warp = n_tile * tile_cols + cg * wcols;  // first output column of this warp
+        const int sb = ot & 1;                               // staging buffer of this tile
+        if (storer) {
+          // the store of the previous tile has finished READING its staging buffer -> that buffer may be refilled
+          // (groups retire in order, so the buffer this tile writes - last read two tiles ago - is free as well; the
+          // other warps learn it through the named barrier at the end of the previous tile)
+          if (ot > 0) bulk_wait_read0();
+          if (res) {  // residual of the NEXT output tile -> the other buffer, one tile ahead of its use
+            int nt, nk0, nk1;
+            bool have = false;
+            while (peek.next(nt, nk0, nk1))
+              if (nk0 == 0) {
+                have = true;
+                break;
+              }
+            if (have) issue_residual(nt, ot + 1);
           }
         }
-        // ---- epilogue vectors of this warp's column half (bias, or LN u and c): fetched into registers BEFORE the
-        // accumulator wait (latency hidden), parked in smem[tile parity] AFTER it.  The four warps sharing `cg` write
-        // identical values (benign); storing after the wait keeps the parity double-buffer race-free (tile i+2 cannot
-        // become ready before every thread finished phase 1 of tile i).
+        // ---- epilogue vector of this warp's columns (bias, or LN c): fetched into registers BEFORE the accumulator
+        // wait (latency hidden), parked in smem[tile parity] AFTER it.  The four warps sharing `cg` write identical
+        // values (benign); storing after the wait keeps the parity double-buffer race-free.
         constexpr int PV = (QW + 31) / 32;
         float pre0[PV];
         {
@@ -567,12 +595,34 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
           if (i < QW) bsm[i] = pre0[j];
         }
         __syncwarp();
-#if RCDM_GEMM_EXPERIMENT == 2
-        release_acc(acc);
-        continue;
-#endif
-        // ---- phase 1: v = scale * acc + vec  (plain: scale = 1, vec = bias; folded LayerNorm: scale = rstd, vec = c)
+        if (res) mbar_wait(&res_full[sb], (ot >> 1) & 1);  // the residual tile is in the staging buffer
+        // ---- thread <-> row: v = scale * acc + vec (+GEGLU), rounded to 16 bits, (+ residual, rounded again like the
+        // reference's `x + attn(...)` on 16-bit tensors), written to this row's slice of the staging buffer
         const float scale = ln_a;
+        uint8_t* srow = staging + sb * Cfg::STG_BYTES + cg * Cfg::PART_BYTES + (size_t)(q * 32 + lane) * (wcols * 2);
+        float st_s = 0.f, st_ss = 0.f;  // row statistics of the final values (folded-LayerNorm producer)
+        using T2 = typename DT<T>::T2;
+        auto finish8 = [&](float* v, int c) {  // 8 outputs at columns c.. of this warp's slice
+          uint4 pk = pack8<T>(v);
+          uint4* dst = reinterpret_cast<uint4*>(srow + c * 2);
+          if (res) {
+            const uint4 rv = *dst;
+            T2* a2 = reinterpret_cast<T2*>(&pk);
+            const T2* b2 = reinterpret_cast<const T2*>(&rv);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) a2[i] = __hadd2(a2[i], b2[i]);
+          }
+          if (p.stats_out && n_warp + c < n_total) {
+            float f8[8];
+            unpack8<T>(pk, f8);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              st_s += f8[i];
+              st_ss = fmaf(f8[i], f8[i], st_ss);
+            }
+          }
+          *dst = pk;
+        };
         if (ln && !ln_smem) {
           // rare: a 128-row tile of a temporal projection spans several frames (8x8 level, tiny test configs): the
           // per-frame vector c comes through L1 instead of shared memory
@@ -587,7 +637,7 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
 #pragma unroll
               for (int i = 0; i < 8; ++i)
                 v[i] = fmaf(__uint_as_float(r[i]), scale, (col + i < p.N) ? __ldg(ln_crow + col + i) : 0.f);
-              *reinterpret_cast<uint4*>(slab + lane * PITCH + c * 2) = pack8<T>(v);
+              finish8(v, c);
             }
           } else {
 #pragma unroll 1
@@ -602,30 +652,19 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
               for (int i = 0; i < 8; ++i)
                 v[i] = fmaf(__uint_as_float(rh[i]), scale, __ldg(ln_crow + colh + i)) *
                        gelu_erf_f(fmaf(__uint_as_float(rg[i]), scale, __ldg(ln_crow + colh + TH + i)));
-              *reinterpret_cast<uint4*>(slab + lane * PITCH + c * 2) = pack8<T>(v);
+              finish8(v, c);
             }
           }
         } else if (!p.geglu) {
-          // the TMEM load of chunk c+1 is in flight while chunk c is scaled, packed and parked in the slab
+          // the TMEM load of chunk c+1 is in flight while chunk c is processed
           uint32_t r[2][CW];
-#if RCDM_GEMM_EXPERIMENT == 5
-#pragma unroll
-          for (int i = 0; i < CW; ++i) r[0][i] = r[1][i] = __float_as_uint(0.001f * (float)(i + lane));
-#else
           ld_chunk(taddr + cg * QW, r[0]);
-#endif
 #pragma unroll
           for (int ci = 0; ci < NCH; ++ci) {
             const int c = ci * CW;
-#if RCDM_GEMM_EXPERIMENT != 5
             tmem_wait_ld();
             if (ci + 1 < NCH) ld_chunk(taddr + cg * QW + c + CW, r[(ci + 1) & 1]);
-#endif
             const uint32_t* rc = r[ci & 1];
-#if RCDM_GEMM_EXPERIMENT == 7
-            if (rc[0] == 0x7fc12345u) slab[lane] = 1;  // keep the loads alive
-            continue;
-#endif
 #pragma unroll
             for (int g = 0; g < CW / 8; ++g) {
               const float4 b0 = *reinterpret_cast<const float4*>(bsm + c + g * 8);  // smem broadcast
@@ -639,7 +678,7 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
               v[5] = fmaf(__uint_as_float(rc[g * 8 + 5]), scale, b1.y);
               v[6] = fmaf(__uint_as_float(rc[g * 8 + 6]), scale, b1.z);
               v[7] = fmaf(__uint_as_float(rc[g * 8 + 7]), scale, b1.w);
-              *reinterpret_cast<uint4*>(slab + lane * PITCH + (c + g * 8) * 2) = pack8<T>(v);
+              finish8(v, c + g * 8);
             }
           }
         } else {
@@ -671,80 +710,23 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
               for (int i = 0; i < 8; ++i)
                 v[i] = fmaf(__uint_as_float(ph[g * 8 + i]), scale, bsm[c + g * 8 + i]) *
                        gelu_erf_f(fmaf(__uint_as_float(pg[g * 8 + i]), scale, bsm[wcols + c + g * 8 + i]));
-              *reinterpret_cast<uint4*>(slab + lane * PITCH + (c + g * 8) * 2) = pack8<T>(v);
+              finish8(v, c + g * 8);
             }
           }
         }
         release_acc(acc);  // accumulator drained: the MMA warp may reuse it
-        __syncwarp();
-#if RCDM_GEMM_EXPERIMENT == 6
-        continue;
-#endif
-        // ---- phase 2
-        if (!p.stats_out) {
-          if (chunk_ok) {
-#pragma unroll
-            for (int u = 0; u < MAX_PASS; ++u) {
-              const int rr = u * RPI + l_row;
-              if (rr < 32 && m_warp + rr < p.M) {
-                uint4 sv = *reinterpret_cast<const uint4*>(slab + rr * PITCH + l_chunk * 16);
-                if (res) {
-                  using T2 = typename DT<T>::T2;
-                  T2* a2 = reinterpret_cast<T2*>(&sv);
-                  const T2* b2 = reinterpret_cast<const T2*>(&rv[u]);
-#pragma unroll
-                  for (int i = 0; i < 4; ++i) a2[i] = __hadd2(a2[i], b2[i]);
-                }
-#if RCDM_GEMM_EXPERIMENT != 1
-                *reinterpret_cast<uint4*>(out + (size_t)(m_warp + rr) * p.ldo + n_warp + l_chunk * 8) = sv;
-#else
-                if (sv.x == 0x12345678u) out[0] = DT<T>::from_f(0.f);  // keep the value alive without the store
-#endif
-              }
-            }
-          }
-        } else {
-          // same stores + per-row (sum, sum of squares) of the ROUNDED outputs: every lane leaves the partial of its
-          // 8 columns in the slab chunk it has just consumed; then lane r folds the CH partials of row r in a fixed
-          // order (deterministic) and the warp writes 32 consecutive float2 of this (column half) part
-#pragma unroll
-          for (int u = 0; u < MAX_PASS; ++u) {
-            const int rr = u * RPI + l_row;
-            if (l_active && rr < 32) {
-              float ps = 0.f, pss = 0.f;
-              if (chunk_ok && m_warp + rr < p.M) {
-                uint4 sv = *reinterpret_cast<const uint4*>(slab + rr * PITCH + l_chunk * 16);
-                if (res) {
-                  using T2 = typename DT<T>::T2;
-                  T2* a2 = reinterpret_cast<T2*>(&sv);
-                  const T2* b2 = reinterpret_cast<const T2*>(&rv[u]);
-#pragma unroll
-                  for (int i = 0; i < 4; ++i) a2[i] = __hadd2(a2[i], b2[i]);
-                }
-                *reinterpret_cast<uint4*>(out + (size_t)(m_warp + rr) * p.ldo + n_warp + l_chunk * 8) = sv;
-                float f8[8];
-                unpack8<T>(sv, f8);
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                  ps += f8[i];
-                  pss = fmaf(f8[i], f8[i], pss);
-                }
-              }
-              *reinterpret_cast<float2*>(slab + rr * PITCH + l_chunk * 16) = make_float2(ps, pss);
-            }
-          }
-          __syncwarp();
-          {
-            float ps = 0.f, pss = 0.f;
-            for (int ch = 0; ch < CH; ++ch) {
-              const float2 t = *reinterpret_cast<const float2*>(slab + lane * PITCH + ch * 16);
-              ps += t.x;
-              pss += t.y;
-            }
-            if (m_warp + lane < p.M) p.stats_out[(size_t)(n_tile * NG + cg) * p.M + m_warp + lane] = make_float2(ps, pss);
-          }
+        if (p.stats_out && m_warp + lane < p.M)
+          p.stats_out[(size_t)(n_tile * NG + cg) * p.M + m_warp + lane] = make_float2(st_s, st_ss);
+        fence_proxy_async_smem();  // this thread's staging writes -> visible to the TMA store
+        epi_bar();
+        if (storer) {
+          for (int g = 0; g < NG; ++g)
+            if (n_tile * tile_cols + g * wcols < n_total)
+              tma_store_2d(&maps.o, staging + sb * Cfg::STG_BYTES + g * Cfg::PART_BYTES, n_tile * tile_cols + g * wcols,
+                           m_tile * 128);
+          bulk_commit();
         }
-        __syncwarp();  // the slab is rewritten for the next tile
+        ++ot;
       } else {
         // ---- scalar fallback (conv_out: N = 4): thread <-> row, direct stores; only the cg == 0 warps work
         const int m = m_warp + lane;
@@ -773,6 +755,7 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
         release_acc(acc);
       }
     }
+    if (storer) bulk_wait0();  // every TMA store of this CTA has completed before its shared memory goes away
   }
   tc_fence_before();
   __syncwarp();
