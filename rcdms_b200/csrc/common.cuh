@@ -58,26 +58,33 @@ template <typename T> __device__ __forceinline__ uint4 pack8(const float* f) {
 }
 
 __device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
-// erf-GELU (diffusers GEGLU uses F.gelu's exact/erf form).  erf via Abramowitz-Stegun 7.1.28,
-//   erf(|x|) = 1 - (1 + a1|x| + ... + a6|x|^6)^-16      (|error| <= 3e-7, far below 16-bit output rounding),
-// i.e. 6 FMA + 4 squarings + ONE MUFU (rcp): the GEGLU epilogue is MUFU/issue bound, and the 7.1.26 form used before
-// needed a second MUFU (ex2).  Large |x| overflows the power to +inf -> rcp 0 -> erf = +-1 exactly.
-__device__ __forceinline__ float erf_as(float x) {
+// erf-GELU (diffusers GEGLU uses F.gelu's exact/erf form):  gelu(x) = 0.5 x (1 + erf(x / sqrt 2)).
+// erfc(t) = 2^-p(t) with a degree-5 polynomial p (least-squares fit of -log2 erfc on [0, 6], p(0) = 0: scripts/fit_gelu.py),
+// evaluated directly in |x| (the 1/sqrt 2 is folded into the coefficients):
+//   |gelu_approx - gelu| <= 2.6e-6 for all x, far below 16-bit output rounding.  4 FMA + 1 MUL + one MUFU (ex2), and
+//   gelu(x) = 0.5 (x + |x|) - 0.5 |x| 2^-p(|x|)  needs no sign handling.  The GEGLU epilogue is bound by instruction
+//   issue; the Abramowitz-Stegun 7.1.28 form used before cost 7 instructions more per element.
+__device__ __forceinline__ float gelu_erf_f(float x) {
   const float ax = fabsf(x);
-  float q = fmaf(0.0000430638f, ax, 0.0002765672f);
-  q = fmaf(q, ax, 0.0001520143f);
-  q = fmaf(q, ax, 0.0092705272f);
-  q = fmaf(q, ax, 0.0422820123f);
-  q = fmaf(q, ax, 0.0705230784f);
-  q = fmaf(q, ax, 1.0f);
-  q *= q;
-  q *= q;
-  q *= q;
-  q *= q;
-  const float r = 1.0f - __fdividef(1.0f, q);
-  return copysignf(r, x);
+  float pl = fmaf(4.1915522222e-04f, ax, -6.7505475000e-03f);
+  pl = fmaf(pl, ax, 5.1185331499e-02f);
+  pl = fmaf(pl, ax, 4.6037139500e-01f);
+  pl = fmaf(pl, ax, 1.1508150914e+00f);
+  pl *= ax;
+  const float e = exp2f(-pl);
+  const float t = 0.5f * ax;
+  return fmaf(-t, e, fmaf(0.5f, x, t));
 }
-__device__ __forceinline__ float gelu_erf_f(float x) { return 0.5f * x * (1.0f + erf_as(x * 0.70710678118654752f)); }
+// erf itself (kept for completeness / tests of the approximation)
+__device__ __forceinline__ float erf_as(float x) {
+  const float ax = fabsf(x) * 1.4142135623730951f;  // argument of the gelu-scaled polynomial
+  float pl = fmaf(4.1915522222e-04f, ax, -6.7505475000e-03f);
+  pl = fmaf(pl, ax, 5.1185331499e-02f);
+  pl = fmaf(pl, ax, 4.6037139500e-01f);
+  pl = fmaf(pl, ax, 1.1508150914e+00f);
+  pl *= ax;
+  return copysignf(1.0f - exp2f(-pl), x);
+}
 
 // ------------------------------------------------------------------------------------------
 // shared-memory address / elect
