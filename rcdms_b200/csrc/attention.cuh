@@ -351,7 +351,9 @@ template <int DPAD> struct Attn4Cfg {
   static constexpr int CTAS_PER_SM = DPAD <= 48 ? 3 : (DPAD <= 80 ? 2 : 1);
 };
 
-template <typename T, int DPAD>
+// MSUM (compile time): the head dim leaves a spare padded column (d < DPAD), so the P V MMA accumulates the row sums
+// and the softmax threads carry no fp32 sums at all.
+template <typename T, int DPAD, bool MSUM>
 __global__ void __launch_bounds__(160, Attn4Cfg<DPAD>::CTAS_PER_SM)
 flash_attn4_kernel(const __grid_constant__ AttnMaps maps, const AttnParams p) {
   using Cfg = Attn4Cfg<DPAD>;
@@ -474,7 +476,7 @@ flash_attn4_kernel(const __grid_constant__ AttnMaps maps, const AttnParams p) {
     const uint32_t lane_sel = uint32_t(warp * 32) << 16;
     const float sc = p.scale_log2;
     float m_run = -INFINITY, l_run = 0.f;
-    const bool mma_sum = p.d < DPAD;  // spare padded column of V carries ones: the P V MMA accumulates the row sums
+    constexpr bool mma_sum = MSUM;  // spare padded column of V carries ones: the P V MMA accumulates the row sums
     using T2 = typename DT<T>::T2;
 
     for (int j = 0; j < n_kv; ++j) {
@@ -514,7 +516,7 @@ flash_attn4_kernel(const __grid_constant__ AttnMaps maps, const AttnParams p) {
           float pv[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i) pv[i] = exp2f(fmaf(__uint_as_float(r[g * 8 + i]), sc, -mref));
-          if (!mma_sum) {
+          if constexpr (!mma_sum) {
             s0 += pv[0] + pv[4];
             s1 += pv[1] + pv[5];
             s2 += pv[2] + pv[6];

@@ -56,8 +56,10 @@ static int attn_version() {  // RCDM_ATTN_V = 3: previous generation (double-buf
 template <typename T, int DPAD> static void launch_one(const AttnLaunch& l, cudaStream_t s) {
   if (attn_version() == 3)
     launch_k(flash_attn_kernel<T, DPAD>, l.grid, dim3(160), AttnCfg<DPAD>::SMEM_BYTES, s, l.maps, l.p);
+  else if (l.p.d < DPAD)
+    launch_k(flash_attn4_kernel<T, DPAD, true>, l.grid, dim3(160), Attn4Cfg<DPAD>::SMEM_BYTES, s, l.maps, l.p);
   else
-    launch_k(flash_attn4_kernel<T, DPAD>, l.grid, dim3(160), Attn4Cfg<DPAD>::SMEM_BYTES, s, l.maps, l.p);
+    launch_k(flash_attn4_kernel<T, DPAD, false>, l.grid, dim3(160), Attn4Cfg<DPAD>::SMEM_BYTES, s, l.maps, l.p);
 }
 template <typename T> static void launch_dt(const AttnLaunch& l, cudaStream_t s) {
   switch (l.dpad) {
@@ -77,7 +79,10 @@ template <typename T, int DPAD> static cudaError_t set_attr() {
   cudaError_t e = cudaFuncSetAttribute(flash_attn_kernel<T, DPAD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        AttnCfg<DPAD>::SMEM_BYTES);
   if (e == cudaSuccess)
-    e = cudaFuncSetAttribute(flash_attn4_kernel<T, DPAD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    e = cudaFuncSetAttribute(flash_attn4_kernel<T, DPAD, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             Attn4Cfg<DPAD>::SMEM_BYTES);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(flash_attn4_kernel<T, DPAD, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              Attn4Cfg<DPAD>::SMEM_BYTES);
   return e;
 }
