@@ -34,3 +34,33 @@ def test_errors_are_python_exceptions():
         ops.linear(a, w)
     with pytest.raises(TypeError):
         ops.linear(a.float(), w.float())
+
+
+@pytest.mark.parametrize("pair,sk", [(0, 0), (2, 0), (0, 1), (2, 1)])
+def test_gemm_scheduling_variants_agree(pair, sk):
+    """CTA-pair (cta_group::2) kernel and stream-K decomposition forced on / off through the tuning knobs: every
+    combination must pass the same parity checks, and pairing must not change a single bit (same K order)."""
+    from rcdms_b200 import _lib, ops
+    L = _lib.lib()
+    prev_pair, prev_sk = L.rcdm_set_gemm_pair(pair), L.rcdm_set_stream_k_min(sk)
+    try:
+        for thunk in (lambda: pc.check_linear(640, 320, 320, torch.float16, residual=True),
+                      lambda: pc.check_linear(2560, 1280, 1280, torch.float16, residual=True),
+                      lambda: pc.check_linear(1000, 128, 96, torch.bfloat16),
+                      lambda: pc.check_geglu(640, 640, torch.float16),
+                      lambda: pc.check_linear_ln(640, 960, 320, torch.float16, pe=True),
+                      lambda: pc.check_rowstats(2560, 1280, 1280, torch.float16),
+                      lambda: pc.check_conv3x3(10, 16, 16, 320, 640, 1, torch.float16),
+                      lambda: pc.check_conv3x3(10, 8, 8, 1280, 640, 1, torch.float16),
+                      lambda: pc.check_conv3x3(5, 16, 16, 192, 320, 2, torch.float16)):
+            r = thunk()
+            assert r["ok"], (pair, sk, r)
+        g = torch.Generator(device="cuda").manual_seed(11)
+        a = torch.randn((2560, 640), generator=g, device="cuda").half()
+        w = (torch.randn((1280, 640), generator=g, device="cuda") / 25).half()
+        out = ops.linear(a, w)
+        L.rcdm_set_gemm_pair(0)
+        assert torch.equal(out, ops.linear(a, w)), "pairing changed the result bitwise"
+    finally:
+        L.rcdm_set_gemm_pair(prev_pair)
+        L.rcdm_set_stream_k_min(prev_sk)
