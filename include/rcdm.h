@@ -139,6 +139,16 @@ RCDM_API int rcdm_denoise_loop(rcdm_unet* h, const void* latents_dev, int latent
 /* out[M,N] = A[M,K] W[N,K]^T (+bias fp32[N]) (+residual[M,N]); geglu: W/bias rows packed by rcdm_pack_geglu */
 RCDM_API int rcdm_gemm(int dtype, const void* a_dev, const void* w_dev, const float* bias_dev, const void* residual_dev,
               void* out_dev, int M, int N, int K, int geglu, int tile_n /*0 = auto*/, int simple, void* stream);
+/* general form: explicit row pitches in elements (lda >= K; ldr / ldo <= 0: dense) and an epilogue activation.
+ * RCDM_GEMM_GELU: out = gelu_erf(A W^T + bias) (+ residual) — diffusers FeedForward(activation_fn="gelu") of the stage-1
+ * prior's BasicTransformerBlock (myprior_transformer.py:149-160); RCDM_GEMM_SILU: TimestepEmbedding.act. */
+#define RCDM_GEMM_GEGLU 1
+#define RCDM_GEMM_GELU 2
+#define RCDM_GEMM_SILU 4
+#define RCDM_GEMM_SIMPLE 8
+RCDM_API int rcdm_gemm_ex(int dtype, const void* a_dev, int lda, const void* w_dev, const float* bias_dev,
+                          const void* residual_dev, int ldr, void* out_dev, int ldo, int M, int N, int K, int flags,
+                          void* stream);
 /* same GEMM, plus per-row (sum, sum of squares) partials of the rounded output: stats_dev = float2[parts][M]
  * (producer side of the folded LayerNorm; replaces the statistics pass of attention.py:412,429,435) */
 RCDM_API int rcdm_gemm_rowstats(int dtype, const void* a_dev, const void* w_dev, const float* bias_dev,
@@ -173,6 +183,27 @@ RCDM_API int rcdm_flash_attn(int dtype, const void* q_dev, int ldq, const void* 
 /* attention over the frame axis: qkv [(b f hw), 3C] -> out [(b f hw), C] */
 RCDM_API int rcdm_temporal_attn(int dtype, const void* qkv_dev, void* out_dev, int batch, int frames, int hw, int heads, int d,
                        void* stream);
+
+
+/* ---- stage-1 frame prior: the kernels MyPriorTransformer / Seq_Inpaint_Prior_Pipeline need on top
+ * of rcdm_gemm_ex / rcdm_layernorm / rcdm_temporal_attn ---- */
+/* CrossAttention._attention with the prior's additive mask (attention.py:171-199; mask: myprior_transformer.py:160-165,
+ * 386-390): softmax(q k^T / sqrt(d) + key_bias[b, j] + (causal && j > i ? -10000 : 0)) v on the fused projection output
+ * qkv [(batch, S), ld] (q | k | v at columns 0 | C | 2C, C = heads * d).  key_bias: fp32 [batch, S] or NULL.  S <= 256. */
+RCDM_API int rcdm_masked_attn(int dtype, const void* qkv_dev, int ld, const float* key_bias_dev, int causal, void* out_dev,
+                              int ldo, int batch, int heads, int S, int d, void* stream);
+/* token matrix of one sampling step (myprior_transformer.py:335-384): x = base with row t_row <- temb_table[*step] + pos[t_row]
+ * and row h_row <- hproj[b % n_lat] + pos[h_row]; all 16-bit, C % 8 == 0; step_dev: device int (NULL: step 0). */
+RCDM_API int rcdm_prior_assemble(int dtype, const void* base_dev, const void* temb_table_dev, const void* hproj_dev,
+                                 const void* pos_dev, void* x_dev, int batch, int S, int C, int t_row, int h_row, int n_lat,
+                                 const int* step_dev, void* stream);
+/* CFG combine + UnCLIPScheduler.step (prior_pipeline.py:316-333) on n = frames * D elements, rounding where torch does.
+ * pred (2n | n), latents (n, updated in place), noise_table [steps][n], coef_table float[steps][8] = {c_x0, c_x, sigma,
+ * eps_scale, eps_div, clip_range (<= 0: none), epsilon-prediction?, 0}; reads row *step_dev and, when advance != 0,
+ * increments it afterwards (CUDA-graph replay). */
+RCDM_API int rcdm_unclip_cfg_step(int dtype, const void* pred_dev, void* latents_dev, const void* noise_table_dev,
+                                  const float* coef_table_dev, int n, int do_cfg, float guidance_scale, int* step_dev,
+                                  int advance, void* stream);
 
 #ifdef __cplusplus
 }

@@ -193,3 +193,113 @@ class DDIMSchedulerRef:
         pred_sample_direction = (1 - alpha_prod_t_prev) ** 0.5 * pred_epsilon
         prev_sample = alpha_prod_t_prev ** 0.5 * pred_original_sample + pred_sample_direction
         return DDIMSchedulerOutput(prev_sample=prev_sample, pred_original_sample=pred_original_sample)
+
+
+# ----------------------------------------------------------------------------------------
+# UnCLIP scheduler (diffusers.schedulers.scheduling_unclip.UnCLIPScheduler, 0.24.0 semantics)
+# used by the stage-1 prior: stage1_batchtest_rcdms_model.py:31,101; src/pipelines/prior_pipeline.py:286-287,
+# 330-336.  Restated from the published algorithm — parity unpinned (see module header); pinned by the
+# closed-form known answers in tests/test_scheduler_known_answers.py.
+# ----------------------------------------------------------------------------------------
+def betas_for_alpha_bar(num_diffusion_timesteps: int, max_beta: float = 0.999) -> torch.Tensor:
+    """squaredcos_cap_v2: alpha_bar(t) = cos((t + 0.008) / 1.008 * pi / 2)^2, beta_i = min(1 - ab(t2)/ab(t1), max_beta),
+    computed in Python doubles and stored as float32."""
+    def alpha_bar(t):
+        return math.cos((t + 0.008) / 1.008 * math.pi / 2) ** 2
+
+    betas = []
+    for i in range(num_diffusion_timesteps):
+        t1 = i / num_diffusion_timesteps
+        t2 = (i + 1) / num_diffusion_timesteps
+        betas.append(min(1 - alpha_bar(t2) / alpha_bar(t1), max_beta))
+    return torch.tensor(betas, dtype=torch.float32)
+
+
+@dataclass
+class UnCLIPSchedulerOutput:
+    prev_sample: torch.Tensor
+    pred_original_sample: Optional[torch.Tensor] = None
+
+
+class UnCLIPSchedulerRef:
+    """Restated UnCLIPScheduler (DDPM variant with an explicit ``prev_timestep``)."""
+
+    init_noise_sigma = 1.0
+
+    def __init__(self, num_train_timesteps=1000, variance_type="fixed_small_log", clip_sample=True,
+                 clip_sample_range=1.0, prediction_type="epsilon", beta_schedule="squaredcos_cap_v2"):
+        if beta_schedule != "squaredcos_cap_v2":
+            raise ValueError("UnCLIPScheduler only supports `beta_schedule`: 'squaredcos_cap_v2'")
+        self.betas = betas_for_alpha_bar(num_train_timesteps)
+        self.alphas = 1.0 - self.betas
+        self.alphas_cumprod = torch.cumprod(self.alphas, dim=0)
+        self.one = torch.tensor(1.0)
+        self.num_inference_steps = None
+        self.timesteps = torch.from_numpy(np.arange(0, num_train_timesteps)[::-1].copy())
+        self.variance_type = variance_type
+        self.config = _Cfg(num_train_timesteps=num_train_timesteps, variance_type=variance_type,
+                           clip_sample=clip_sample, clip_sample_range=clip_sample_range,
+                           prediction_type=prediction_type, beta_schedule=beta_schedule)
+
+    def scale_model_input(self, sample, timestep=None):
+        return sample
+
+    def set_timesteps(self, num_inference_steps: int, device=None):
+        self.num_inference_steps = num_inference_steps
+        step_ratio = (self.config.num_train_timesteps - 1) / (self.num_inference_steps - 1)
+        timesteps = (np.arange(0, num_inference_steps) * step_ratio).round()[::-1].copy().astype(np.int64)
+        self.timesteps = torch.from_numpy(timesteps).to(device)
+
+    def _get_variance(self, t, prev_timestep=None, predicted_variance=None, variance_type=None):
+        if prev_timestep is None:
+            prev_timestep = t - 1
+        alpha_prod_t = self.alphas_cumprod[t]
+        alpha_prod_t_prev = self.alphas_cumprod[prev_timestep] if prev_timestep >= 0 else self.one
+        beta_prod_t = 1 - alpha_prod_t
+        beta_prod_t_prev = 1 - alpha_prod_t_prev
+        beta = self.betas[t] if prev_timestep == t - 1 else 1 - alpha_prod_t / alpha_prod_t_prev
+        variance = beta_prod_t_prev / beta_prod_t * beta
+        variance_type = variance_type or self.config.variance_type
+        if variance_type == "fixed_small_log":
+            variance = torch.log(torch.clamp(variance, min=1e-20))
+            variance = torch.exp(0.5 * variance)
+        else:
+            raise NotImplementedError("learned_range needs a variance head the RCDMs prior does not have")
+        return variance
+
+    def step(self, model_output, timestep, sample, prev_timestep=None, generator=None, return_dict=True,
+             variance_noise=None):
+        """``variance_noise`` (oracle-only extension): use this tensor instead of drawing from ``generator`` so that
+        two implementations can be compared on identical noise."""
+        t = int(timestep)
+        prev_timestep = t - 1 if prev_timestep is None else int(prev_timestep)
+        alpha_prod_t = self.alphas_cumprod[t]
+        alpha_prod_t_prev = self.alphas_cumprod[prev_timestep] if prev_timestep >= 0 else self.one
+        beta_prod_t = 1 - alpha_prod_t
+        beta_prod_t_prev = 1 - alpha_prod_t_prev
+        if prev_timestep == t - 1:
+            beta = self.betas[t]
+            alpha = self.alphas[t]
+        else:
+            beta = 1 - alpha_prod_t / alpha_prod_t_prev
+            alpha = 1 - beta
+        if self.config.prediction_type == "epsilon":
+            pred_original_sample = (sample - beta_prod_t ** 0.5 * model_output) / alpha_prod_t ** 0.5
+        elif self.config.prediction_type == "sample":
+            pred_original_sample = model_output
+        else:
+            raise ValueError(self.config.prediction_type)
+        if self.config.clip_sample:
+            pred_original_sample = torch.clamp(pred_original_sample, -self.config.clip_sample_range,
+                                               self.config.clip_sample_range)
+        pred_original_sample_coeff = (alpha_prod_t_prev ** 0.5 * beta) / beta_prod_t
+        current_sample_coeff = alpha ** 0.5 * beta_prod_t_prev / beta_prod_t
+        pred_prev_sample = pred_original_sample_coeff * pred_original_sample + current_sample_coeff * sample
+        variance = 0
+        if t > 0:
+            if variance_noise is None:
+                variance_noise = torch.randn(model_output.shape, generator=generator, dtype=model_output.dtype,
+                                             device=model_output.device)
+            variance = self._get_variance(t, prev_timestep=prev_timestep) * variance_noise
+        pred_prev_sample = pred_prev_sample + variance
+        return UnCLIPSchedulerOutput(prev_sample=pred_prev_sample, pred_original_sample=pred_original_sample)

@@ -36,11 +36,59 @@ def golden_inputs(cfg, b, f, h, w, L, seed):
     return x, ctx
 
 
+def load_reference_prior(cfg):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, REF)
+    sys.path.insert(0, os.path.join(ROOT, "oracle", "diffusers_shim"))
+    from src.models.myprior_transformer import MyPriorTransformer  # the reference's class, unmodified
+    init = {k: (list(v) if isinstance(v, tuple) else v) for k, v in cfg.items()}
+    return MyPriorTransformer.from_config(init)
+
+
+def prior_goldens(out_dir):
+    """Stage-1 prior: reference MyPriorTransformer forwards on the synthetic state dict."""
+    from rcdms_b200.prior_spec import prior_tiny_config
+    from rcdms_b200.synthetic import synthetic_prior_inputs, synthetic_prior_state_dict
+    cases = [
+        ("prior_tiny", prior_tiny_config(), 500),
+        ("prior_tiny_norms", prior_tiny_config(norm_in_type="layer", embedding_proj_norm_type="layer", num_layers=1,
+                                               added_emb_type=None, additional_embeddings=5), 17),
+        ("prior_wide", prior_tiny_config(num_attention_heads=8, num_layers=1, embedding_dim=96, num_embeddings=27), 999),
+    ]
+    for name, cfg, t in cases:
+        model = load_reference_prior(cfg).eval()
+        sd = synthetic_prior_state_dict(cfg, seed=0)
+        model.load_state_dict(sd, strict=True)
+        inp = synthetic_prior_inputs(cfg, clip_index=3)
+        x = torch.cat([inp["latents"]] * 2)
+        taps, hooks = {}, []
+        for mod_name in ("transformer_blocks.0", "transformer_blocks.1"):
+            mod = dict(model.named_modules())[mod_name]
+            hooks.append(mod.register_forward_hook(lambda m, i, o, n=mod_name: taps.__setitem__(n, o.detach().clone())))
+        with torch.no_grad():
+            out = model(x, torch.tensor(t), inp["prompt_embeds"], inp["text_hidden"],
+                        torch.cat([inp["imgs_proj_embeds1"]] * 2), torch.cat([inp["mask_label"]] * 2),
+                        inp["text_mask"]).predicted_image_embedding
+            for hk in hooks:
+                hk.remove()
+            out_nomask = model(x, t, inp["prompt_embeds"], inp["text_hidden"], torch.cat([inp["imgs_proj_embeds1"]] * 2),
+                               torch.cat([inp["mask_label"]] * 2), None, return_dict=False)[0]
+        torch.save(dict(cfg=cfg, timestep=t, out=out.clone(), out_nomask=out_nomask.clone(),
+                        taps={k: v[:, -2:].clone() for k, v in taps.items()},
+                        state_dict_names=[(k, tuple(v.shape)) for k, v in model.state_dict().items()]),
+                   os.path.join(out_dir, f"{name}.pt"))
+        print(name, tuple(out.shape), float(out.abs().mean()))
+
+
 def main():
     from rcdms_b200.synthetic import synthetic_state_dict
     from rcdms_b200.unet_spec import full_config, tiny_config
     out_dir = os.path.join(ROOT, "tests", "golden")
     os.makedirs(out_dir, exist_ok=True)
+    if "prior" in sys.argv[1:] or not sys.argv[1:]:
+        prior_goldens(out_dir)
+        if "prior" in sys.argv[1:]:
+            return
     torch.manual_seed(0)
     cases = [
         # name, cfg, (b, f, h, w, L), timestep, taps kept

@@ -15,6 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("RCDM_LIB") or os.path.join(HERE, "_C", "librcdm_b200.so")
 
 DT_F32, DT_F16, DT_BF16 = 0, 1, 2
+GEMM_GEGLU, GEMM_GELU, GEMM_SILU, GEMM_SIMPLE = 1, 2, 4, 8
 MAX_BLOCKS = 4
 
 
@@ -58,6 +59,10 @@ SIGNATURES = {
     "rcdm_denoise_loop": (_I, [_P, _P, _I, _P, _I, _P, _I, _P, _I, _I, _I, _I, _I, _I, C.POINTER(_I64),
                                C.POINTER(_F), C.POINTER(_F), _I, _F, _I, _P, _P]),
     "rcdm_gemm": (_I, [_I, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
+    "rcdm_gemm_ex": (_I, [_I, _P, _I, _P, _P, _P, _I, _P, _I, _I, _I, _I, _I, _P]),
+    "rcdm_masked_attn": (_I, [_I, _P, _I, _P, _I, _P, _I, _I, _I, _I, _I, _P]),
+    "rcdm_prior_assemble": (_I, [_I, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P]),
+    "rcdm_unclip_cfg_step": (_I, [_I, _P, _P, _P, _P, _I, _I, _F, _P, _I, _P]),
     "rcdm_pack_geglu": (_I, [_I, _P, _P, _P, _P, _I, _I, _P]),
     "rcdm_conv3x3": (_I, [_I, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
     "rcdm_pack_conv3x3": (_I, [_I, _P, _P, _I, _I, _P]),

@@ -5,6 +5,7 @@
 
 #include "elementwise.cuh"
 #include "internal.h"
+#include "prior_kernels.cuh"
 
 using namespace rcdm;
 
@@ -454,6 +455,139 @@ int rcdm_gemm(int dtype, const void* a_dev, const void* w_dev, const float* bias
   }
   g_launches++;
   return check_launch("rcdm_gemm");
+  API_END
+}
+
+// General form of rcdm_gemm: explicit row pitches (A rows may be strided, e.g. one token of every sample) and the
+// epilogue activation of the stage-1 prior (flags: RCDM_GEMM_GEGLU | _GELU | _SILU | _SIMPLE).
+int rcdm_gemm_ex(int dtype, const void* a_dev, int lda, const void* w_dev, const float* bias_dev,
+                 const void* residual_dev, int ldr, void* out_dev, int ldo, int M, int N, int K, int flags,
+                 void* stream) {
+  API_BEGIN
+  if (!dt16(dtype)) return set_err("rcdm_gemm_ex: dtype must be f16/bf16");
+  if (!a_dev || !w_dev || !out_dev || M <= 0 || N <= 0 || K <= 0) return set_err("rcdm_gemm_ex: bad argument");
+  const int geglu = (flags & RCDM_GEMM_GEGLU) ? 1 : 0;
+  const int act = (flags & RCDM_GEMM_GELU) ? 1 : (flags & RCDM_GEMM_SILU) ? 2 : 0;
+  if (geglu && (act || residual_dev)) return set_err("rcdm_gemm_ex: GEGLU excludes an activation / residual");
+  if (lda < K || lda % 8) return set_err("rcdm_gemm_ex: lda must be >= K and a multiple of 8");
+  if (ensure_device_ready()) return 1;
+  GemmDesc d;
+  memset(&d, 0, sizeof d);
+  d.dt = dtype;
+  d.M = M;
+  d.N = N;
+  d.nseg = 1;
+  d.seg[0] = ASeg{SEG_PLAIN, a_dev, K, lda, 0, 0, 0};
+  d.w = w_dev;
+  d.Ktot = K;
+  d.w_rows = N;
+  d.out = out_dev;
+  d.ldo = ldo > 0 ? ldo : (geglu ? N / 2 : N);
+  d.bias = bias_dev;
+  d.res = residual_dev;
+  d.ldr = ldr > 0 ? ldr : N;
+  d.geglu = geglu;
+  d.act = act;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (flags & RCDM_GEMM_SIMPLE) {
+    gemm_simple_launch(d, st);
+  } else {
+    GemmLaunch l;
+    std::string e;
+    if (!gemm_prepare(d, &l, &e)) return set_err(e);
+    gemm_launch(l, st);
+  }
+  g_launches++;
+  return check_launch("rcdm_gemm_ex");
+  API_END
+}
+
+// ---- stage-1 frame prior (prior_kernels.cuh) ----
+int rcdm_masked_attn(int dtype, const void* qkv_dev, int ld, const float* key_bias_dev, int causal, void* out_dev,
+                     int ldo, int batch, int heads, int S, int d, void* stream) {
+  API_BEGIN
+  if (!dt16(dtype)) return set_err("rcdm_masked_attn: dtype must be f16/bf16");
+  if (!qkv_dev || !out_dev || batch <= 0 || heads <= 0 || S <= 0) return set_err("rcdm_masked_attn: bad argument");
+  if (S > 32 * MASKED_ATTN_KPL) return set_err("rcdm_masked_attn: at most 256 tokens");
+  if (d <= 0 || d > 256 || d % 4) return set_err("rcdm_masked_attn: head dim must be a multiple of 4, <= 256");
+  if (ld < 3 * heads * d || ld % 2 || ldo < heads * d || ldo % 2) return set_err("rcdm_masked_attn: bad row pitch");
+  if (ensure_device_ready()) return 1;
+  const size_t smem = masked_attn_smem_bytes(S, d);
+  if (smem > 200 * 1024) return set_err("rcdm_masked_attn: S * d too large for shared memory");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const dim3 grid(batch * heads, (S + MASKED_ATTN_QCHUNK - 1) / MASKED_ATTN_QCHUNK);
+  const float scale = 1.0f / sqrtf((float)d);
+  if (dtype == DT_F16) {
+    static bool attr = false;
+    if (!attr) {
+      CUDA_OK(cudaFuncSetAttribute(masked_attn_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      attr = true;
+    }
+    masked_attn_kernel<__half><<<grid, MASKED_ATTN_WARPS * 32, smem, st>>>(
+        reinterpret_cast<const __half*>(qkv_dev), ld, key_bias_dev, causal, reinterpret_cast<__half*>(out_dev), ldo, S,
+        heads, d, scale);
+  } else {
+    static bool attr = false;
+    if (!attr) {
+      CUDA_OK(cudaFuncSetAttribute(masked_attn_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   200 * 1024));
+      attr = true;
+    }
+    masked_attn_kernel<__nv_bfloat16><<<grid, MASKED_ATTN_WARPS * 32, smem, st>>>(
+        reinterpret_cast<const __nv_bfloat16*>(qkv_dev), ld, key_bias_dev, causal,
+        reinterpret_cast<__nv_bfloat16*>(out_dev), ldo, S, heads, d, scale);
+  }
+  g_launches++;
+  return check_launch("rcdm_masked_attn");
+  API_END
+}
+
+int rcdm_prior_assemble(int dtype, const void* base_dev, const void* temb_table_dev, const void* hproj_dev,
+                        const void* pos_dev, void* x_dev, int batch, int S, int C, int t_row, int h_row, int n_lat,
+                        const int* step_dev, void* stream) {
+  API_BEGIN
+  if (!dt16(dtype)) return set_err("rcdm_prior_assemble: dtype must be f16/bf16");
+  if (!base_dev || !temb_table_dev || !hproj_dev || !pos_dev || !x_dev) return set_err("null argument");
+  if (C % 8 || n_lat <= 0 || t_row < 0 || t_row >= S || h_row < 0 || h_row >= S)
+    return set_err("rcdm_prior_assemble: bad argument");
+  if (ensure_device_ready()) return 1;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const size_t total = (size_t)batch * S * (C / 8);
+  if (dtype == DT_F16)
+    prior_assemble_kernel<__half><<<grid_for(total, 256), 256, 0, st>>>(
+        reinterpret_cast<const __half*>(base_dev), reinterpret_cast<const __half*>(temb_table_dev),
+        reinterpret_cast<const __half*>(hproj_dev), reinterpret_cast<const __half*>(pos_dev),
+        reinterpret_cast<__half*>(x_dev), batch, S, C, t_row, h_row, n_lat, step_dev);
+  else
+    prior_assemble_kernel<__nv_bfloat16><<<grid_for(total, 256), 256, 0, st>>>(
+        reinterpret_cast<const __nv_bfloat16*>(base_dev), reinterpret_cast<const __nv_bfloat16*>(temb_table_dev),
+        reinterpret_cast<const __nv_bfloat16*>(hproj_dev), reinterpret_cast<const __nv_bfloat16*>(pos_dev),
+        reinterpret_cast<__nv_bfloat16*>(x_dev), batch, S, C, t_row, h_row, n_lat, step_dev);
+  g_launches++;
+  return check_launch("rcdm_prior_assemble");
+  API_END
+}
+
+int rcdm_unclip_cfg_step(int dtype, const void* pred_dev, void* latents_dev, const void* noise_table_dev,
+                         const float* coef_table_dev, int n, int do_cfg, float guidance_scale, int* step_dev,
+                         int advance, void* stream) {
+  API_BEGIN
+  if (!dt16(dtype)) return set_err("rcdm_unclip_cfg_step: dtype must be f16/bf16");
+  if (!pred_dev || !latents_dev || !coef_table_dev || n <= 0) return set_err("rcdm_unclip_cfg_step: bad argument");
+  if (ensure_device_ready()) return 1;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (dtype == DT_F16)
+    unclip_cfg_step_kernel<__half><<<1, 1024, 0, st>>>(reinterpret_cast<const __half*>(pred_dev),
+                                                       reinterpret_cast<__half*>(latents_dev),
+                                                       reinterpret_cast<const __half*>(noise_table_dev), coef_table_dev,
+                                                       n, do_cfg, guidance_scale, step_dev, advance);
+  else
+    unclip_cfg_step_kernel<__nv_bfloat16><<<1, 1024, 0, st>>>(
+        reinterpret_cast<const __nv_bfloat16*>(pred_dev), reinterpret_cast<__nv_bfloat16*>(latents_dev),
+        reinterpret_cast<const __nv_bfloat16*>(noise_table_dev), coef_table_dev, n, do_cfg, guidance_scale, step_dev,
+        advance);
+  g_launches++;
+  return check_launch("rcdm_unclip_cfg_step");
   API_END
 }
 

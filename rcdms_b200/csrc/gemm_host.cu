@@ -168,6 +168,7 @@ bool gemm_prepare(const GemmDesc& d, GemmLaunch* l, std::string* err) {
   p.res = d.res;
   p.ldr = d.ldr;
   p.geglu = d.geglu;
+  p.act = d.act;
   p.stats_out = d.stats_out;
   p.stats_in = d.stats_in;
   p.stats_parts = d.stats_parts;
@@ -281,7 +282,9 @@ bool gemm_prepare(const GemmDesc& d, GemmLaunch* l, std::string* err) {
         if (!encode_tmap(&l->maps.r, d.res, 2, dims, strr, box, false, err)) return false;
       }
     }
-    if (!ok && (d.stats_out || d.stats_in || d.geglu)) return fail("this epilogue needs 16-byte aligned output rows");
+    if (!ok && (d.stats_out || d.stats_in || d.geglu || d.act))
+      return fail("this epilogue needs 16-byte aligned output rows");
+    if (d.act && d.geglu) return fail("act (plain GELU) and geglu are mutually exclusive");
   }
   p.num_m_tiles = l->pair ? (m_tiles + 1) / 2 : m_tiles;  // pair mode: counted in 256-row tile pairs
   p.num_n_tiles = (d.N + bn - 1) / bn;
@@ -422,6 +425,8 @@ __global__ void gemm_simple_kernel(const SimpleArgs sa) {
     } else {
       v = simple_dot<T>(d, m, j);
       if (d.bias) v += d.bias[j];
+      if (d.act == 1) v = gelu_erf_f(v);
+      else if (d.act == 2) v = silu_f(v);
       if (d.res) v += DT<T>::to_f(reinterpret_cast<const T*>(d.res)[(size_t)m * d.ldr + j]);
     }
     reinterpret_cast<T*>(d.out)[(size_t)m * d.ldo + j] = DT<T>::from_f(v);

@@ -63,6 +63,8 @@ struct GemmParams {
   const void* res;    // residual [M, ldr] or nullptr (may alias out)
   int ldr;
   int geglu;          // 1: out[m, j] = (acc[j] + b[j]) * gelu(acc[BN/2 + j] + b[BN/2 + j]) per tile
+  int act;            // 1: out = gelu_erf(acc + b) (diffusers FeedForward(activation_fn="gelu"), the stage-1 prior);
+                      // 2: out = silu(acc + b) (TimestepEmbedding.act); applied before the residual; not with geglu
   int epi_tma;        // 1: vectorised epilogue through the staging buffers + TMA (maps.o / maps.r valid)
   // stream-K: the (tile, k-block) iteration space is cut into gridDim.x equal contiguous ranges, so a GEMM whose
   // tile count does not fill the SMs evenly still keeps every tensor core busy.  A CTA whose range starts inside a
@@ -603,6 +605,13 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
         float st_s = 0.f, st_ss = 0.f;  // row statistics of the final values (folded-LayerNorm producer)
         using T2 = typename DT<T>::T2;
         auto finish8 = [&](float* v, int c) {  // 8 outputs at columns c.. of this warp's slice
+          if (p.act == 1) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = gelu_erf_f(v[i]);
+          } else if (p.act == 2) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = silu_f(v[i]);
+          }
           uint4 pk = pack8<T>(v);
           uint4* dst = reinterpret_cast<uint4*>(srow + c * 2);
           if (res) {

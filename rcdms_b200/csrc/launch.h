@@ -57,6 +57,7 @@ struct GemmDesc {
   const void* res;
   int ldr;
   int geglu;
+  int act;       // 1 = erf GELU, 2 = SiLU on (acc + bias), before the residual add
   int force_bn;  // 0 = heuristic
   int no_sk;     // 1 = never use the stream-K decomposition for this launch
   int no_pair;   // 1 = never use the CTA-pair (cta_group::2) kernel for this launch

@@ -123,9 +123,9 @@ void gn_run(const GnLaunch& l, cudaStream_t s) {
 bool ln_run(int dt, const void* x, void* o, const float* gp, const float* bp, int nrows, int C, float eps,
             const float* pep, int rows_per_frame, int frames, cudaStream_t s) {
   const int maxv = (C / 8 + 31) / 32;
-  if (maxv > 5 || C % 8) return false;
+  if (maxv > 8 || C % 8) return false;  // C <= 2048 (the stage-1 prior's width)
   // rows per warp: keep ~8 16-byte loads in flight per lane
-  const int rpw = maxv <= 1 ? 8 : maxv == 2 ? 4 : 2;
+  const int rpw = maxv <= 1 ? 8 : maxv == 2 ? 4 : maxv <= 5 ? 2 : 1;
   const int warps = (nrows + rpw - 1) / rpw;
   const int blocks = (warps + 7) / 8;
 #define RCDM_LN(T, V, R)                                                                                           \
@@ -135,12 +135,14 @@ bool ln_run(int dt, const void* x, void* o, const float* gp, const float* bp, in
     if (maxv <= 1) RCDM_LN(__half, 1, 8);
     else if (maxv == 2) RCDM_LN(__half, 2, 4);
     else if (maxv == 3) RCDM_LN(__half, 3, 2);
-    else RCDM_LN(__half, 5, 2);
+    else if (maxv <= 5) RCDM_LN(__half, 5, 2);
+    else RCDM_LN(__half, 8, 1);
   } else {
     if (maxv <= 1) RCDM_LN(__nv_bfloat16, 1, 8);
     else if (maxv == 2) RCDM_LN(__nv_bfloat16, 2, 4);
     else if (maxv == 3) RCDM_LN(__nv_bfloat16, 3, 2);
-    else RCDM_LN(__nv_bfloat16, 5, 2);
+    else if (maxv <= 5) RCDM_LN(__nv_bfloat16, 5, 2);
+    else RCDM_LN(__nv_bfloat16, 8, 1);
   }
 #undef RCDM_LN
   g_launches++;

@@ -1,1 +1,2 @@
 from .unet import UNet3DConditionModel, UNet3DConditionOutput  # noqa: F401
+from .myprior_transformer import MyPriorTransformer, PriorTransformerOutput  # noqa: F401

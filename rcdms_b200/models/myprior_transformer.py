@@ -1,0 +1,426 @@
+"""Drop-in ``MyPriorTransformer`` (stage-1 frame prior) whose forward runs on librcdm_b200.so kernels only.
+
+Mirrors the reference module API (``src/models/myprior_transformer.py:37-448``): constructor keywords, ``from_config`` /
+``from_pretrained_2d``, ``.config``, ``.dtype``, the exact state-dict names and shapes (``load_state_dict(strict=True)``
+works on a reference checkpoint, ``stage1_batchtest_rcdms_model.py:102-103``), ``forward(hidden_states, timestep,
+proj_embedding, encoder_hidden_states, proj_embedding1, mask_label, attention_mask, return_dict)`` and
+``post_process_latents``.  SURVEY.md §8(f) rank 1.
+
+The host side is Python like the reference's; every operation on activations is a C-ABI call (``include/rcdm.h``):
+
+* ``rcdm_layernorm``          — the LayerNorms (width <= 2048), with the temporal positional encoding fused in
+* ``rcdm_gemm_ex``            — every Linear on the tcgen05 GEMM (bias / residual / erf-GELU / SiLU / GEGLU epilogues)
+* ``rcdm_masked_attn``        — self-attention with the causal + text-padding mask (``attention.py:171-199``)
+* ``rcdm_temporal_attn``      — the prior-state motion modules' attention over the 5 frames (``motion_module.py:150-174``)
+* ``rcdm_prior_assemble``     — per-step token matrix;  ``rcdm_unclip_cfg_step`` — CFG + scheduler step (pipeline)
+
+torch is used for device memory and for once-per-clip glue (concatenating the step-invariant tokens).  There is no
+PyTorch implementation of the network here — without the CUDA library / a CUDA device the forward raises.
+"""
+from __future__ import annotations
+
+import json
+import math
+import os
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Tuple, Union
+
+import torch
+import torch.nn as nn
+
+from .. import _lib
+from ..prior_spec import (PRIOR_BUFFER_SUFFIX, PRIOR_DEFAULT_CONFIG, PRIOR_VIDEO_LENGTH, prior_dims,
+                          prior_state_dict_spec)
+from .unet import _Config, _Params
+
+
+@dataclass
+class PriorTransformerOutput:
+    predicted_image_embedding: torch.Tensor
+
+
+def _f32(t: torch.Tensor) -> torch.Tensor:
+    return t.detach().float().contiguous()
+
+
+class _Lin:
+    """One packed Linear: 16-bit weight [N, K] + fp32 bias (the GEMM epilogue vector)."""
+
+    __slots__ = ("w", "b", "n", "k")
+
+    def __init__(self, w: torch.Tensor, b: Optional[torch.Tensor], dtype):
+        self.w = w.detach().to(dtype).contiguous()
+        self.b = _f32(b) if b is not None else None
+        self.n, self.k = self.w.shape
+
+
+class _Plan:
+    """Activation buffers for one (batch, dtype): allocated once so that a step can be replayed from a CUDA graph."""
+
+    def __init__(self, B: int, d: Dict, dtype, device):
+        S, C = d["seq"], d["inner"]
+        M = B * S
+        e = lambda *s: torch.empty(s, dtype=dtype, device=device)  # noqa: E731
+        self.B, self.M = B, M
+        self.X, self.Y, self.A, self.Hm = e(M, C), e(M, C), e(M, C), e(M, C)
+        self.QKV = e(M, 3 * C)
+        self.H = e(M, 4 * C)
+        self.out = e(B, d["clip_dim"])
+        self.hproj = e(B, C)
+
+
+class MyPriorTransformer(nn.Module):
+    def __init__(self, **kwargs):
+        super().__init__()
+        unknown = set(kwargs) - set(PRIOR_DEFAULT_CONFIG)
+        if unknown:
+            raise TypeError(f"unexpected config keys: {sorted(unknown)}")
+        cfg = {**PRIOR_DEFAULT_CONFIG, **kwargs}
+        if cfg["norm_in_type"] not in (None, "layer"):
+            raise ValueError(f"Unsupported norm_in_type: {cfg['norm_in_type']}.")
+        if cfg["embedding_proj_norm_type"] not in (None, "layer"):
+            raise ValueError(f"unsupported embedding_proj_norm_type: {cfg['embedding_proj_norm_type']}")
+        if cfg["encoder_hid_proj_type"] not in (None, "linear"):
+            raise ValueError(f"unsupported encoder_hid_proj_type: {cfg['encoder_hid_proj_type']}")
+        if cfg["added_emb_type"] not in (None, "prd"):
+            raise ValueError(f"`added_emb_type`: {cfg['added_emb_type']} is not supported. Make sure to choose one of "
+                             "`'prd'` or `None`.")
+        if cfg["time_embed_act_fn"] != "silu":
+            raise NotImplementedError("time_embed_act_fn must be 'silu' (the kandinsky-2-2 prior's)")
+        if cfg["encoder_hid_proj_type"] is None:
+            raise NotImplementedError("encoder_hid_proj_type=None is not on the RCDMs stage-1 path")
+        assert cfg["unet_use_cross_frame_attention"] is not None  # attention.py:393
+        assert cfg["unet_use_temporal_attention"] is not None     # attention.py:437
+        if cfg["unet_use_cross_frame_attention"] or cfg["unet_use_temporal_attention"]:
+            raise NotImplementedError("unet_use_cross_frame_attention / unet_use_temporal_attention must be false "
+                                      "(configs/testing.yaml:4-5)")
+        if cfg["use_motion_module"]:
+            mm = cfg["motion_module_kwargs"] or {}
+            if cfg["motion_module_type"] != "Vanilla":
+                raise ValueError("motion_module_type must be 'Vanilla' (motion_module.py:47-50)")
+            if any(t != "Temporal_Self" for t in mm.get("attention_block_types", ())):
+                raise NotImplementedError("only Temporal_Self attention blocks are on the RCDMs path")
+            if mm.get("num_transformer_block", 1) != 1 or mm.get("temporal_attention_dim_div", 1) != 1:
+                raise NotImplementedError("num_transformer_block / temporal_attention_dim_div must be 1")
+            if not mm.get("temporal_position_encoding", False):
+                raise NotImplementedError("temporal_position_encoding must be true (configs/testing.yaml:12)")
+            if mm.get("temporal_position_encoding_max_len", 24) < PRIOR_VIDEO_LENGTH:
+                raise ValueError("temporal_position_encoding_max_len must cover the 5 frames of a clip")
+        self._internal_dict = _Config(cfg)
+        self._dims = prior_dims(cfg)
+        self.num_attention_heads = cfg["num_attention_heads"]
+        self.attention_head_dim = cfg["attention_head_dim"]
+        self.additional_embeddings = cfg["additional_embeddings"]
+        for name, shape in prior_state_dict_spec(cfg):
+            self._register(name, shape)
+        with torch.no_grad():  # the reference initialises both to zeros (myprior_transformer.py:136,139)
+            self.positional_embedding.zero_()
+            if cfg["added_emb_type"] == "prd":
+                self.prd_embedding.zero_()
+        self.clip_mean = torch.tensor(-0.016)  # myprior_transformer.py:170-171
+        self.clip_std = torch.tensor(0.415)
+        self._packed = None
+        self._packed_versions = None
+        self._plans: Dict[Tuple, _Plan] = {}
+
+    # ---- parameter tree with the reference's names -------------------------------------------------------------
+    def _register(self, name: str, shape: Tuple[int, ...]) -> None:
+        *path, leaf = name.split(".")
+        mod: nn.Module = self
+        for p in path:
+            if p not in mod._modules:
+                mod.add_module(p, _Params())
+            mod = mod._modules[p]
+        if name.endswith(PRIOR_BUFFER_SUFFIX):
+            from ..synthetic import positional_encoding
+            mod.register_buffer(leaf, positional_encoding(shape[1], shape[2]))
+        else:
+            mod.register_parameter(leaf, nn.Parameter(torch.empty(shape), requires_grad=False))
+
+    @property
+    def config(self) -> _Config:
+        return self._internal_dict
+
+    @property
+    def dtype(self) -> torch.dtype:
+        return self.proj_in.weight.dtype
+
+    @property
+    def device(self) -> torch.device:
+        return self.proj_in.weight.device
+
+    @classmethod
+    def from_config(cls, config: Dict, **kwargs) -> "MyPriorTransformer":
+        keep = {k: v for k, v in dict(config).items() if k in PRIOR_DEFAULT_CONFIG}
+        keep.update({k: v for k, v in kwargs.items() if k in PRIOR_DEFAULT_CONFIG})
+        return cls(**keep)
+
+    @classmethod
+    def from_pretrained_2d(cls, pretrained_model_path, subfolder=None, unet_additional_kwargs=None):
+        """Reference: ``myprior_transformer.py:416-448`` — kandinsky ``prior/config.json`` with num_embeddings = 91 and
+        additional_embeddings = 6 forced, 2-D weights minus ``positional_embedding`` loaded non-strictly."""
+        if subfolder is not None:
+            pretrained_model_path = os.path.join(pretrained_model_path, subfolder)
+        print(f"loaded temporal prior's pretrained weights from {pretrained_model_path} ...")
+        config_file = os.path.join(pretrained_model_path, "config.json")
+        if not os.path.isfile(config_file):
+            raise RuntimeError(f"{config_file} does not exist")
+        with open(config_file, "r") as f:
+            config = json.load(f)
+        config["_class_name"] = cls.__name__
+        config["num_embeddings"] = 91
+        config["additional_embeddings"] = 6
+        model = cls.from_config(config, **(unet_additional_kwargs or {}))
+        model_file = os.path.join(pretrained_model_path, "diffusion_pytorch_model.bin")
+        if not os.path.isfile(model_file):
+            raise RuntimeError(f"{model_file} does not exist")
+        state_dict = torch.load(model_file, map_location="cpu")
+        match = {k: v for k, v in state_dict.items() if not k.startswith("positional_embedding")}
+        m, u = model.load_state_dict(match, strict=False)
+        print(f"### missing keys: {len(m)}; \n### unexpected keys: {len(u)};")
+        params = [p.numel() if "temporal" in n else 0 for n, p in model.named_parameters()]
+        print(f"### Temporal Module Parameters: {sum(params) / 1e6} M")
+        return model
+
+    def post_process_latents(self, prior_latents: torch.Tensor) -> torch.Tensor:
+        return (prior_latents * self.clip_std) + self.clip_mean
+
+    # ---- weight packing (once per load_state_dict / .to()) -----------------------------------------------------
+    def _versions(self):
+        return tuple((t.data_ptr(), t._version) for t in self.state_dict(keep_vars=True).values())
+
+    def _ensure_packed(self):
+        dt = self.dtype
+        if dt not in (torch.float16, torch.bfloat16):
+            raise TypeError("the B200 prior path computes in float16 or bfloat16 (tensor cores); "
+                            f"call .half() / .to(torch.bfloat16) first (module dtype is {dt})")
+        if self.device.type != "cuda":
+            raise RuntimeError("MyPriorTransformer.forward needs the module on a CUDA device "
+                               "(no CPU fallback exists for the prior path)")
+        v = self._versions()
+        if self._packed is not None and v == self._packed_versions:
+            return self._packed
+        _lib.lib()  # fail loudly when the extension is missing
+        sd = {k: t.detach() for k, t in self.state_dict(keep_vars=True).items()}
+        d = self._dims
+
+        def lin(p, bias=True):
+            return _Lin(sd[p + ".weight"], sd.get(p + ".bias") if bias else None, dt)
+
+        def norm(p):
+            return (_f32(sd[p + ".weight"]), _f32(sd[p + ".bias"]))
+
+        def qkv(p, bias):
+            w = torch.cat([sd[f"{p}.to_{n}.weight"] for n in "qkv"], dim=0)
+            b = torch.cat([sd[f"{p}.to_{n}.bias"] for n in "qkv"], dim=0) if bias else None
+            return _Lin(w, b, dt)
+
+        P = dict(time1=lin("time_embedding.linear_1"), time2=lin("time_embedding.linear_2"), proj_in=lin("proj_in"),
+                 emb=lin("embedding_proj"), emb1=lin("embedding_proj1"), emb2=lin("embedding_proj2"),
+                 ehs=lin("encoder_hidden_states_proj"), norm_out=norm("norm_out"),
+                 clip=lin("proj_to_clip_embeddings"),
+                 pos=sd["positional_embedding"][0].to(dt).contiguous(),
+                 prd=sd["prd_embedding"].to(dt) if "prd_embedding" in sd else None,
+                 emb_norm=norm("embedding_proj_norm") if "embedding_proj_norm.weight" in sd else None,
+                 norm_in=norm("norm_in") if "norm_in.weight" in sd else None, layers=[])
+        for i in range(d["layers"]):
+            p = f"transformer_blocks.{2 * i}"
+            lay = dict(n1=norm(p + ".norm1"), qkv=qkv(p + ".attn1", True), o=lin(p + ".attn1.to_out.0"),
+                       n3=norm(p + ".norm3"), ff1=lin(p + ".ff.net.0.proj"), ff2=lin(p + ".ff.net.2"), motion=None)
+            if d["motion"]:
+                m = f"transformer_blocks.{2 * i + 1}.temporal_transformer"
+                t = m + ".transformer_blocks.0"
+                att = []
+                for a in range(d["n_tattn"]):
+                    q = f"{t}.attention_blocks.{a}"
+                    att.append(dict(n=norm(f"{t}.norms.{a}"), qkv=qkv(q, False), o=lin(q + ".to_out.0"),
+                                    pe=_f32(sd[q + ".pos_encoder.pe"][0, :PRIOR_VIDEO_LENGTH])))
+                lay["motion"] = dict(pn=norm(m + ".prior_norm"), pi=lin(m + ".proj_in"), att=att,
+                                     fn=norm(t + ".ff_norm"), ff1=self._pack_geglu(lin(t + ".ff.net.0.proj")),
+                                     ff2=lin(t + ".ff.net.2"), po=lin(m + ".proj_out"))
+            P["layers"].append(lay)
+        torch.cuda.current_stream().synchronize()
+        self._packed, self._packed_versions = P, v
+        self._plans.clear()
+        return P
+
+    @staticmethod
+    def _pack_geglu(l: _Lin) -> _Lin:
+        """Row-interleave [h | gate] per 128-wide tile so that the GEMM epilogue applies the gate (rcdm_pack_geglu)."""
+        wp = torch.empty_like(l.w)
+        bp = torch.empty_like(l.b)
+        _lib.check(_lib.lib().rcdm_pack_geglu(_lib.torch_dtype_id(l.w.dtype), l.w.data_ptr(), l.b.data_ptr(),
+                                              wp.data_ptr(), bp.data_ptr(), l.n, l.k, _lib.current_stream_ptr()))
+        l.w, l.b = wp, bp
+        return l
+
+    def _plan(self, B: int) -> _Plan:
+        key = (B, self.dtype, str(self.device))
+        if key not in self._plans:
+            self._plans[key] = _Plan(B, self._dims, self.dtype, self.device)
+        return self._plans[key]
+
+    # ---- single-kernel launches ----------------------------------------------------------------------------------
+    @property
+    def _simple(self) -> bool:  # debug switch: CUDA-core reference GEMM (same C entry point) for every Linear
+        return os.environ.get("RCDM_PRIOR_SIMPLE", "0") not in ("", "0")
+
+    def _gemm(self, a: torch.Tensor, l: _Lin, out: torch.Tensor, res: Optional[torch.Tensor] = None, flags: int = 0,
+              M: Optional[int] = None, lda: Optional[int] = None, a_off: int = 0) -> torch.Tensor:
+        M = a.shape[0] if M is None else M
+        if self._simple:
+            flags |= _lib.GEMM_SIMPLE
+        _lib.check(_lib.lib().rcdm_gemm_ex(
+            _lib.torch_dtype_id(a.dtype), a.data_ptr() + a_off * a.element_size(), lda or l.k, l.w.data_ptr(),
+            l.b.data_ptr() if l.b is not None else None, res.data_ptr() if res is not None else None, 0,
+            out.data_ptr(), 0, M, l.n, l.k, flags, _lib.current_stream_ptr()))
+        return out
+
+    @staticmethod
+    def _ln(x: torch.Tensor, gb, out: torch.Tensor, pe: Optional[torch.Tensor] = None, rows_per_frame: int = 1,
+            frames: int = 1, rows: Optional[int] = None) -> torch.Tensor:
+        rows = x.shape[0] if rows is None else rows
+        _lib.check(_lib.lib().rcdm_layernorm(_lib.torch_dtype_id(x.dtype), x.data_ptr(), gb[0].data_ptr(),
+                                             gb[1].data_ptr(), out.data_ptr(), rows, x.shape[-1], 1e-5,
+                                             pe.data_ptr() if pe is not None else None, rows_per_frame, frames,
+                                             _lib.current_stream_ptr()))
+        return out
+
+    # ---- pieces of the forward (also driven step by step by Seq_Inpaint_Prior_Pipeline) -------------------------
+    def time_embedding_table(self, timesteps) -> torch.Tensor:
+        """``time_embedding(time_proj(t))`` for a list of timesteps -> [len, inner] (``myprior_transformer.py:322-328``)."""
+        P, d = self._ensure_packed(), self._dims
+        t = torch.as_tensor(timesteps, device=self.device).reshape(-1).float()
+        half = d["inner"] // 2
+        freq = torch.exp(-math.log(10000) * torch.arange(half, dtype=torch.float32, device=self.device) / half)
+        arg = t[:, None] * freq[None, :]
+        proj = torch.cat([torch.cos(arg), torch.sin(arg)], dim=-1).to(self.dtype).contiguous()  # flip_sin_to_cos
+        n = proj.shape[0]
+        h = torch.empty((n, P["time1"].n), dtype=self.dtype, device=self.device)
+        out = torch.empty((n, P["time2"].n), dtype=self.dtype, device=self.device)
+        self._gemm(proj, P["time1"], h, flags=_lib.GEMM_SILU)
+        return self._gemm(h, P["time2"], out)
+
+    def static_tokens(self, proj_embedding: torch.Tensor, encoder_hidden_states: torch.Tensor,
+                      proj_embedding1: torch.Tensor, mask_label: torch.Tensor) -> torch.Tensor:
+        """Step-invariant part of the token matrix, positional embedding added: [B, S, inner]; the time / hidden-state
+        rows are left zero (``rcdm_prior_assemble`` writes them every step).  ``myprior_transformer.py:330-384``."""
+        P, d = self._ensure_packed(), self._dims
+        dt, dev = self.dtype, self.device
+        B = proj_embedding.shape[0]
+        if encoder_hidden_states is None:
+            raise ValueError("`encoder_hidden_states_proj` requires `encoder_hidden_states` to be set")
+        L = encoder_hidden_states.shape[1]
+        n_static = L + 3 + 2 + (1 if P["prd"] is not None else 0)
+        if n_static != d["seq"]:
+            raise ValueError(f"token count {n_static} (text {L} + 5 conditioning tokens + prd) does not match "
+                             f"num_embeddings + additional_embeddings = {d['seq']}")
+
+        def rows(x, width):
+            x = x.to(device=dev, dtype=dt).reshape(-1, width).contiguous()
+            return x
+
+        pe = rows(proj_embedding, d["proj_dim"])
+        if P["emb_norm"] is not None:
+            pe = self._ln(pe, P["emb_norm"], torch.empty_like(pe))
+        C = d["inner"]
+        new = lambda n: torch.empty((n, C), dtype=dt, device=dev)  # noqa: E731
+        pe0 = self._gemm(pe, P["emb"], new(B))
+        pe1 = self._gemm(rows(proj_embedding1, d["proj_dim"]), P["emb1"], new(B))
+        ml = self._gemm(rows(mask_label, d["proj_dim"]), P["emb2"], new(B))
+        ehs = self._gemm(rows(encoder_hidden_states, d["emb"]), P["ehs"], new(B * L)).reshape(B, L, C)
+        zero = torch.zeros((B, 1, C), dtype=dt, device=dev)
+        parts = [ehs, pe0[:, None], pe1[:, None], ml[:, None], zero, zero]
+        if P["prd"] is not None:
+            parts.append(P["prd"].expand(B, -1, -1))
+        return (torch.cat(parts, dim=1) + P["pos"][None]).contiguous()
+
+    def key_bias(self, attention_mask: Optional[torch.Tensor], B: int) -> Optional[torch.Tensor]:
+        """fp32 [B, S] additive key bias: -10000 on padded text keys, 0 on the additional tokens
+        (``myprior_transformer.py:386-388``); the causal part is applied inside ``rcdm_masked_attn``."""
+        if attention_mask is None:
+            return None
+        m = (1 - attention_mask.to(device=self.device, dtype=torch.float32)) * -10000.0
+        return torch.nn.functional.pad(m, (0, self.additional_embeddings), value=0.0).contiguous()
+
+    def run_tokens(self, plan: _Plan, base: torch.Tensor, temb_table: torch.Tensor, latents_rows: torch.Tensor,
+                   n_lat: int, key_bias: Optional[torch.Tensor], step_dev: Optional[torch.Tensor]) -> torch.Tensor:
+        """One prior evaluation on prepared inputs; only C-ABI launches on the current stream (graph-capturable).
+        latents_rows [n_lat, embedding_dim] (the CFG duplication ``torch.cat([latents] * 2)`` is the modulo inside
+        ``rcdm_prior_assemble``); returns plan.out [B, clip_dim]."""
+        P, d = self._packed, self._dims
+        L = _lib.lib()
+        dtid = _lib.torch_dtype_id(self.dtype)
+        s = _lib.current_stream_ptr()
+        B, S, C = plan.B, d["seq"], d["inner"]
+        X, Y, A, Hm, QKV, H = plan.X, plan.Y, plan.A, plan.Hm, plan.QKV, plan.H
+        self._gemm(latents_rows, P["proj_in"], plan.hproj, M=n_lat)
+        t_row = S - 2 - (1 if P["prd"] is not None else 0)
+        _lib.check(L.rcdm_prior_assemble(dtid, base.data_ptr(), temb_table.data_ptr(), plan.hproj.data_ptr(),
+                                         P["pos"].data_ptr(), X.data_ptr(), B, S, C, t_row, t_row + 1, n_lat,
+                                         step_dev.data_ptr() if step_dev is not None else None, s))
+        if P["norm_in"] is not None:
+            self._ln(X, P["norm_in"], Y)
+            X, Y = Y, X
+        heads, hd = d["heads"], d["head_dim"]
+        mh = d["motion_heads"]
+        for lay in P["layers"]:
+            # BasicTransformerBlock (attention.py:479-526): x += attn1(LN(x), mask); x += FF_gelu(LN(x))
+            self._ln(X, lay["n1"], Y)
+            self._gemm(Y, lay["qkv"], QKV)
+            _lib.check(L.rcdm_masked_attn(dtid, QKV.data_ptr(), 3 * C, key_bias.data_ptr() if key_bias is not None
+                                          else None, int(key_bias is not None), A.data_ptr(), C, B, heads, S, hd, s))
+            self._gemm(A, lay["o"], X, res=X)
+            self._ln(X, lay["n3"], Y)
+            self._gemm(Y, lay["ff1"], H, flags=_lib.GEMM_GELU)
+            self._gemm(H, lay["ff2"], X, res=X)
+            mo = lay["motion"]
+            if mo is None:
+                continue
+            # TemporalTransformer3DModel, prior_state=True (motion_module.py:150-174)
+            self._ln(X, mo["pn"], Y)
+            self._gemm(Y, mo["pi"], Hm)
+            for att in mo["att"]:
+                self._ln(Hm, att["n"], Y, pe=att["pe"], rows_per_frame=S, frames=PRIOR_VIDEO_LENGTH)
+                self._gemm(Y, att["qkv"], QKV)
+                _lib.check(L.rcdm_temporal_attn(dtid, QKV.data_ptr(), A.data_ptr(), B // PRIOR_VIDEO_LENGTH,
+                                                PRIOR_VIDEO_LENGTH, S, mh, C // mh, s))
+                self._gemm(A, att["o"], Hm, res=Hm)
+            self._ln(Hm, mo["fn"], Y)
+            self._gemm(Y, mo["ff1"], H, flags=_lib.GEMM_GEGLU)
+            self._gemm(H, mo["ff2"], Hm, res=Hm)
+            self._gemm(Hm, mo["po"], X, res=X)
+        # norm_out on the last token of every sample only, then proj_to_clip_embeddings (myprior_transformer.py:397-402)
+        # (LayerNorm is row-wise, so normalising every row and projecting row S-1 of each sample through a strided A
+        # operand gives the same values without a gather)
+        self._ln(X, P["norm_out"], Y)
+        return self._gemm(Y, P["clip"], plan.out, M=B, lda=S * C, a_off=(S - 1) * C)
+
+    # ---- reference-facing forward ------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def forward(self, hidden_states: torch.Tensor, timestep: Union[torch.Tensor, float, int],
+                proj_embedding: torch.Tensor, encoder_hidden_states: Optional[torch.Tensor] = None,
+                proj_embedding1: Optional[torch.Tensor] = None, mask_label: Optional[torch.Tensor] = None,
+                attention_mask: Optional[torch.Tensor] = None, return_dict: bool = True):
+        self._ensure_packed()
+        d = self._dims
+        B = hidden_states.shape[0]
+        if self.config.use_motion_module and B % PRIOR_VIDEO_LENGTH:
+            raise ValueError(f"batch {B} is not a multiple of the hard-coded video_length = {PRIOR_VIDEO_LENGTH} "
+                             "(motion_module.py:151)")
+        if proj_embedding1 is None or mask_label is None:
+            raise ValueError("proj_embedding1 and mask_label are required (myprior_transformer.py:337-338)")
+        if torch.is_tensor(timestep):
+            if timestep.numel() != 1:
+                if not bool((timestep == timestep.flatten()[0]).all()):
+                    raise NotImplementedError("per-sample timesteps: the prior loop passes one scalar t per step")
+                timestep = timestep.flatten()[0]
+            timestep = float(timestep)
+        plan = self._plan(B)
+        base = self.static_tokens(proj_embedding, encoder_hidden_states, proj_embedding1, mask_label)
+        temb = self.time_embedding_table([timestep])
+        lat = hidden_states.to(device=self.device, dtype=self.dtype).reshape(B, d["emb"]).contiguous()
+        out = self.run_tokens(plan, base, temb, lat, B, self.key_bias(attention_mask, B), None).clone()
+        if not return_dict:
+            return (out,)
+        return PriorTransformerOutput(predicted_image_embedding=out)

@@ -181,3 +181,51 @@ def ddim_cfg_step(eps: torch.Tensor, latents_f32: torch.Tensor, alpha_bar_t: flo
         _dt(masked_latents) if masked_latents is not None else 0, clips, f, h, w, int(do_cfg), float(guidance_scale),
         float(alpha_bar_t), float(alpha_bar_prev), _lib.current_stream_ptr()))
     return lat_out, nxt
+
+
+# ---- stage-1 frame prior kernels ------------------------------------------------------------
+def linear_ex(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None,
+              residual: Optional[torch.Tensor] = None, act: Optional[str] = None, simple: bool = False,
+              rows: Optional[int] = None, lda: Optional[int] = None, a_offset: int = 0) -> torch.Tensor:
+    """rcdm_gemm_ex: out = act(a @ w^T + bias) (+ residual); act in {None, "gelu", "silu"}.  ``rows`` / ``lda`` /
+    ``a_offset`` (elements) select a strided row subset of ``a`` (e.g. the last token of every sample)."""
+    K = w.shape[1]
+    N = w.shape[0]
+    M = a.shape[0] if rows is None else rows
+    flags = {None: 0, "gelu": _lib.GEMM_GELU, "silu": _lib.GEMM_SILU}[act] | (_lib.GEMM_SIMPLE if simple else 0)
+    out = torch.empty((M, N), dtype=a.dtype, device=a.device)
+    _lib.check(_lib.lib().rcdm_gemm_ex(_dt16(a), a.data_ptr() + a_offset * a.element_size(), lda or K, w.data_ptr(),
+                                       _ptr(bias), _ptr(residual), 0, out.data_ptr(), 0, M, N, K, flags,
+                                       _lib.current_stream_ptr()))
+    return out
+
+
+def masked_attention(qkv: torch.Tensor, heads: int, key_bias: Optional[torch.Tensor] = None,
+                     causal: bool = False) -> torch.Tensor:
+    """qkv [batch, S, 3C] (q | k | v) -> [batch, S, C]: softmax(q k^T / sqrt(d) + key_bias[b, j] + causal) v."""
+    b, S, c3 = qkv.shape
+    C = c3 // 3
+    out = torch.empty((b, S, C), dtype=qkv.dtype, device=qkv.device)
+    _lib.check(_lib.lib().rcdm_masked_attn(_dt16(qkv), qkv.data_ptr(), c3, _ptr(key_bias), int(causal), out.data_ptr(),
+                                           C, b, heads, S, C // heads, _lib.current_stream_ptr()))
+    return out
+
+
+def prior_assemble(base: torch.Tensor, temb_table: torch.Tensor, hproj: torch.Tensor, pos: torch.Tensor, t_row: int,
+                   h_row: int, step: Optional[torch.Tensor] = None) -> torch.Tensor:
+    B, S, C = base.shape
+    x = torch.empty_like(base)
+    _lib.check(_lib.lib().rcdm_prior_assemble(_dt16(base), base.data_ptr(), temb_table.data_ptr(), hproj.data_ptr(),
+                                              pos.data_ptr(), x.data_ptr(), B, S, C, t_row, h_row, hproj.shape[0],
+                                              _ptr(step), _lib.current_stream_ptr()))
+    return x
+
+
+def unclip_cfg_step(pred: torch.Tensor, latents: torch.Tensor, noise_table: torch.Tensor, coef_table: torch.Tensor,
+                    do_cfg: bool, guidance_scale: float, step: torch.Tensor, advance: bool = True) -> torch.Tensor:
+    """In-place CFG + UnCLIP step on ``latents`` (frames, D); returns ``latents``."""
+    _lib.check(_lib.lib().rcdm_unclip_cfg_step(_dt16(latents), pred.data_ptr(), latents.data_ptr(),
+                                               noise_table.data_ptr(), coef_table.data_ptr(), latents.numel(),
+                                               int(do_cfg), float(guidance_scale), step.data_ptr(), int(advance),
+                                               _lib.current_stream_ptr()))
+    return latents

@@ -113,3 +113,107 @@ class DDIMScheduler:
         if not return_dict:
             return (prev_sample,)
         return DDIMStepOutput(prev_sample=prev_sample, pred_original_sample=x0)
+
+
+# -------------------------------------------------------------------------------------------------------------------
+# UnCLIP scheduler (stage-1 frame prior)
+# -------------------------------------------------------------------------------------------------------------------
+@dataclass
+class UnCLIPStepOutput:
+    prev_sample: torch.Tensor
+    pred_original_sample: Optional[torch.Tensor] = None
+
+
+class UnCLIPScheduler:
+    """Host-side scheduler with the surface ``Seq_Inpaint_Prior_Pipeline`` uses from ``diffusers.UnCLIPScheduler``
+    (0.24.0): ``set_timesteps``, ``timesteps``, ``init_noise_sigma``, ``step(pred, timestep=, sample=, generator=,
+    prev_timestep=).prev_sample`` (reference call sites: ``src/pipelines/prior_pipeline.py:111,286-287,322-333``;
+    constructed at ``stage1_batchtest_rcdms_model.py:101``).
+
+    The tables (cosine betas, alpha-bar, timestep indices) are host fp32/int64.  The per-step arithmetic on the
+    embeddings normally runs in the fused CUDA kernel (``rcdm_unclip_cfg_step``) fed by ``step_coefficients``;
+    ``step`` is the same formula on torch tensors for API completeness."""
+
+    def __init__(self, num_train_timesteps: int = 1000, variance_type: str = "fixed_small_log",
+                 clip_sample: bool = True, clip_sample_range: float = 1.0, prediction_type: str = "epsilon",
+                 beta_schedule: str = "squaredcos_cap_v2"):
+        if beta_schedule != "squaredcos_cap_v2":
+            raise ValueError("UnCLIPScheduler only supports `beta_schedule`: 'squaredcos_cap_v2'")
+        if variance_type != "fixed_small_log":
+            raise NotImplementedError("variance_type 'learned_range' needs a variance head the RCDMs prior lacks")
+        if prediction_type not in ("epsilon", "sample"):
+            raise ValueError(f"prediction_type given as {prediction_type} must be one of `epsilon` or `sample`")
+        # cosine schedule in float64, stored as float32 (diffusers' betas_for_alpha_bar)
+        i = np.arange(num_train_timesteps + 1, dtype=np.float64) / num_train_timesteps
+        abar = np.cos((i + 0.008) / 1.008 * np.pi / 2) ** 2
+        betas = np.minimum(1.0 - abar[1:] / abar[:-1], 0.999)
+        self.betas = torch.tensor(betas.tolist(), dtype=torch.float32)
+        self.alphas = 1.0 - self.betas
+        self.alphas_cumprod = torch.cumprod(self.alphas, dim=0)
+        self.one = torch.tensor(1.0)
+        self.init_noise_sigma = 1.0
+        self.variance_type = variance_type
+        self._internal_dict = FrozenConfig(
+            num_train_timesteps=num_train_timesteps, variance_type=variance_type, clip_sample=clip_sample,
+            clip_sample_range=clip_sample_range, prediction_type=prediction_type, beta_schedule=beta_schedule)
+        self.num_inference_steps: Optional[int] = None
+        self.timesteps = torch.arange(num_train_timesteps - 1, -1, -1, dtype=torch.int64)
+
+    @property
+    def config(self) -> FrozenConfig:
+        return self._internal_dict
+
+    def scale_model_input(self, sample: torch.Tensor, timestep=None) -> torch.Tensor:
+        return sample
+
+    def set_timesteps(self, num_inference_steps: int, device=None) -> None:
+        self.num_inference_steps = num_inference_steps
+        ratio = (self.config.num_train_timesteps - 1) / (num_inference_steps - 1)
+        ts = np.flip((np.arange(num_inference_steps) * ratio).round()).copy().astype(np.int64)
+        self.timesteps = torch.from_numpy(ts).to(device)
+
+    def _terms(self, t: int, prev_t: Optional[int]):
+        prev_t = t - 1 if prev_t is None else int(prev_t)
+        a_t = self.alphas_cumprod[t]
+        a_prev = self.alphas_cumprod[prev_t] if prev_t >= 0 else self.one
+        b_t, b_prev = 1 - a_t, 1 - a_prev
+        if prev_t == t - 1:
+            beta, alpha = self.betas[t], self.alphas[t]
+        else:
+            beta = 1 - a_t / a_prev
+            alpha = 1 - beta
+        return a_t, a_prev, b_t, b_prev, beta, alpha
+
+    def step_coefficients(self, timestep: int, prev_timestep: Optional[int] = None):
+        """(x0_coeff, sample_coeff, sigma, eps_scale, eps_div) as fp32 python floats for one step — what the fused
+        CUDA step consumes: x_prev = x0_coeff * clip(x0) + sample_coeff * x + sigma * noise (sigma = 0 at t = 0);
+        for epsilon prediction x0 = (x - eps_scale * pred) / eps_div."""
+        t = int(timestep)
+        a_t, a_prev, b_t, b_prev, beta, alpha = self._terms(t, prev_timestep)
+        c_x0 = (a_prev ** 0.5 * beta) / b_t
+        c_x = alpha ** 0.5 * b_prev / b_t
+        sigma = 0.0
+        if t > 0:
+            var = b_prev / b_t * beta
+            sigma = float(torch.exp(0.5 * torch.log(torch.clamp(var, min=1e-20))))
+        return float(c_x0), float(c_x), sigma, float(b_t ** 0.5), float(a_t ** 0.5)
+
+    def step(self, model_output: torch.Tensor, timestep, sample: torch.Tensor, prev_timestep=None, generator=None,
+             return_dict: bool = True):
+        t = int(timestep)
+        a_t, a_prev, b_t, b_prev, beta, alpha = self._terms(t, prev_timestep)
+        if self.config.prediction_type == "epsilon":
+            x0 = (sample - b_t ** 0.5 * model_output) / a_t ** 0.5
+        else:
+            x0 = model_output
+        if self.config.clip_sample:
+            x0 = torch.clamp(x0, -self.config.clip_sample_range, self.config.clip_sample_range)
+        prev = (a_prev ** 0.5 * beta) / b_t * x0 + alpha ** 0.5 * b_prev / b_t * sample
+        if t > 0:
+            noise = torch.randn(model_output.shape, generator=generator, device=model_output.device,
+                                dtype=model_output.dtype)
+            var = b_prev / b_t * beta
+            prev = prev + torch.exp(0.5 * torch.log(torch.clamp(var, min=1e-20))) * noise
+        if not return_dict:
+            return (prev,)
+        return UnCLIPStepOutput(prev_sample=prev, pred_original_sample=x0)

@@ -85,3 +85,45 @@ def synthetic_clip_inputs(clip_index: int, h: int, w: int, ctx_len: int = 85, ct
     mask[:, :, 0] = 1.0
     ctx = torch.randn((2 * frames, ctx_len, ctx_dim), generator=g)
     return dict(latents=latents, masked_latents=masked_latents, mask=mask, ctx=ctx)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# stage-1 frame prior
+# ---------------------------------------------------------------------------------------------------------------
+def synthetic_prior_state_dict(cfg: Dict, seed: int = 0, dtype=torch.float32, device="cpu") -> Dict[str, torch.Tensor]:
+    """Deterministic weights for ``MyPriorTransformer`` (same rules as ``synthetic_tensor``; the zero-initialised
+    temporal ``proj_out`` is again NOT zero so that the motion modules are exercised).  ``positional_embedding`` /
+    ``prd_embedding`` (zeros in the reference's init) get small random values."""
+    from .prior_spec import prior_state_dict_spec
+    out = {}
+    for name, shape in prior_state_dict_spec(cfg):
+        out[name] = synthetic_tensor("prior." + name, shape, seed).to(device=device, dtype=dtype)
+    return out
+
+
+def synthetic_prior_inputs(cfg: Dict, clip_index: int = 0, frames: int = 5, seed: int = 42,
+                           steps: int = 0) -> Dict[str, torch.Tensor]:
+    """Per-clip inputs of the prior sampling loop (fp32, CPU), shaped like ``prior_pipeline.py:283-298`` after
+    ``_encode_prompt``: CFG rows ordered [negative x frames, positive x frames].
+
+    latents ~ N(0,1) (f, D); prompt_embeds (2f, D); text_hidden (2f, L, D); text_mask (2f, L) bool — the empty negative
+    prompt keeps 2 tokens (BOS/EOS), positive prompts 12..L tokens; imgs_proj_embeds1 / mask_label (f, 1, D) (CLIP image
+    embeds of the source frames / of the white-black mask label images, ``stage1_batchtest_rcdms_model.py:166-178``);
+    noise (steps-1, f, D): the variance noise of every step but the last (when ``steps`` > 0)."""
+    D, L = cfg["embedding_dim"], cfg["num_embeddings"]
+    g = torch.Generator(device="cpu")
+    g.manual_seed(seed + clip_index)
+    latents = torch.randn((frames, D), generator=g)
+    prompt_embeds = torch.randn((2 * frames, D), generator=g)
+    text_hidden = torch.randn((2 * frames, L, D), generator=g)
+    text_mask = torch.zeros((2 * frames, L), dtype=torch.bool)
+    text_mask[:frames, :2] = True
+    for i in range(frames):
+        n = min(L, 12 + (7 * i + 3 * clip_index) % max(1, L - 11))
+        text_mask[frames + i, :n] = True
+    out = dict(latents=latents, prompt_embeds=prompt_embeds, text_hidden=text_hidden, text_mask=text_mask,
+               imgs_proj_embeds1=torch.randn((frames, 1, D), generator=g),
+               mask_label=torch.randn((frames, 1, D), generator=g))
+    if steps > 0:
+        out["noise"] = torch.randn((max(steps - 1, 1), frames, D), generator=g)
+    return out

@@ -1,0 +1,231 @@
+"""Stage-1 frame prior, CPU tier: the oracle restatement pinned to goldens produced by the
+REFERENCE ``MyPriorTransformer`` (imported unmodified through oracle/diffusers_shim by ``python -m oracle.make_golden
+prior``), UnCLIP scheduler known answers for oracle and product, the host-side loop logic and the module surface."""
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle.diffusers_restated import UnCLIPSchedulerRef
+from oracle.prior_ref import CLIP_MEAN, CLIP_STD, make_prior_scheduler, prior_forward, prior_loop
+from rcdms_b200.models.myprior_transformer import MyPriorTransformer
+from rcdms_b200.pipelines.prior_pipeline import Seq_Inpaint_Prior_Pipeline
+from rcdms_b200.prior_spec import PRIOR_SCHEDULER_KWARGS, prior_full_config, prior_state_dict_spec, prior_tiny_config
+from rcdms_b200.schedulers import UnCLIPScheduler
+from rcdms_b200.synthetic import synthetic_prior_inputs, synthetic_prior_state_dict
+
+from conftest import GOLDEN
+
+CASES = ["prior_tiny", "prior_tiny_norms", "prior_wide"]
+
+
+def _run_oracle(gold, masked=True, taps=None):
+    cfg = gold["cfg"]
+    sd = synthetic_prior_state_dict(cfg, seed=0)
+    inp = synthetic_prior_inputs(cfg, clip_index=3)
+    x = torch.cat([inp["latents"]] * 2)
+    with torch.no_grad():
+        return prior_forward(sd, cfg, x, gold["timestep"], inp["prompt_embeds"], inp["text_hidden"],
+                             torch.cat([inp["imgs_proj_embeds1"]] * 2), torch.cat([inp["mask_label"]] * 2),
+                             inp["text_mask"] if masked else None, taps=taps)
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_oracle_matches_reference_golden(name):
+    gold = torch.load(os.path.join(GOLDEN, f"{name}.pt"))
+    taps = {}
+    y = _run_oracle(gold, True, taps)
+    assert y.shape == gold["out"].shape
+    assert (y - gold["out"]).abs().max().item() < 2e-5  # fp32 CPU, same op order
+    assert (_run_oracle(gold, False) - gold["out_nomask"]).abs().max().item() < 2e-5
+    assert (gold["out"] - gold["out_nomask"]).abs().max().item() > 1e-3  # the mask matters in the fixture
+    for k, v in gold["taps"].items():
+        assert (taps[k][:, -2:] - v).abs().max().item() < 2e-4 * max(1.0, v.abs().max().item()), k
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_state_dict_spec_matches_reference(name):
+    gold = torch.load(os.path.join(GOLDEN, f"{name}.pt"))
+    assert prior_state_dict_spec(gold["cfg"]) == [(k, tuple(s)) for k, s in gold["state_dict_names"]]
+    m = MyPriorTransformer.from_config(gold["cfg"])
+    assert [(k, tuple(v.shape)) for k, v in m.state_dict().items()] == prior_state_dict_spec(gold["cfg"])
+    res = m.load_state_dict(synthetic_prior_state_dict(gold["cfg"]), strict=True)
+    assert not res.missing_keys and not res.unexpected_keys
+
+
+def test_full_config_parameter_count():
+    spec = prior_state_dict_spec(prior_full_config())
+    n = sum(int(np.prod(s)) for k, s in spec if not k.endswith("pos_encoder.pe"))
+    # 20 x (BasicTransformerBlock 12 C^2 + motion module 22 C^2) at C = 2048 plus the embeddings' projections
+    assert 2.85e9 < n < 2.95e9, n
+    assert dict(spec)["positional_embedding"] == (1, 97, 2048)
+    assert dict(spec)["encoder_hidden_states_proj1.weight"] == (2048, 1664)
+
+
+# ---- UnCLIP scheduler known answers (closed form; diffusers 0.24.0 is absent: parity unpinned) -------------------
+def _schedulers():
+    return [("oracle", make_prior_scheduler()), ("product", UnCLIPScheduler(**PRIOR_SCHEDULER_KWARGS))]
+
+
+@pytest.mark.parametrize("which", [0, 1])
+def test_unclip_tables(which):
+    name, s = _schedulers()[which]
+
+    def ab(t):
+        return math.cos((t + 0.008) / 1.008 * math.pi / 2) ** 2
+
+    for i in (0, 1, 250, 500, 998):
+        want = min(1 - ab((i + 1) / 1000) / ab(i / 1000), 0.999)
+        assert abs(float(s.betas[i]) - want) < 1e-7 * max(1.0, want / 1e-3), (name, i)
+    assert float(s.betas[999]) == pytest.approx(0.999, abs=1e-7)  # capped
+    assert abs(float(s.betas[0]) - 4.128422369831242e-05) < 1e-11, name
+    assert abs(float(s.alphas_cumprod[500]) - 0.4922850430011749) < 1e-6, name
+    # closed form: prod(1 - beta) telescopes to ab(t) / ab(0) while no beta is capped
+    assert abs(float(s.alphas_cumprod[500]) - ab(501 / 1000) / ab(0)) < 1e-5, name
+    assert s.init_noise_sigma == 1.0
+
+
+@pytest.mark.parametrize("which", [0, 1])
+@pytest.mark.parametrize("n,head,tail", [(25, [999, 957, 916, 874], [83, 42, 0]), (100, [999, 989, 979], [20, 10, 0]),
+                                         (10, [999, 888, 777], [222, 111, 0])])
+def test_unclip_timesteps(which, n, head, tail):
+    name, s = _schedulers()[which]
+    s.set_timesteps(n)
+    ts = s.timesteps
+    assert ts.dtype == torch.int64 and len(ts) == n, name
+    assert ts[: len(head)].tolist() == head and ts[-len(tail):].tolist() == tail, name
+    assert ts.tolist() == (np.arange(n) * (999 / (n - 1))).round()[::-1].astype(np.int64).tolist()
+
+
+def test_unclip_step_oracle_vs_product():
+    a, b = make_prior_scheduler(), UnCLIPScheduler(**PRIOR_SCHEDULER_KWARGS)
+    assert torch.equal(a.betas, b.betas) and torch.equal(a.alphas_cumprod, b.alphas_cumprod)
+    a.set_timesteps(25)
+    b.set_timesteps(25)
+    ts = a.timesteps
+    x, p = torch.linspace(-3, 3, 16), torch.linspace(8, -8, 16)  # |p| > 5 exercises clip_sample_range
+    for i in (0, 7, 23, 24):
+        prev = ts[i + 1] if i + 1 < len(ts) else None
+        g1, g2 = torch.Generator().manual_seed(5), torch.Generator().manual_seed(5)
+        o1 = a.step(p, ts[i], x, prev_timestep=prev, generator=g1).prev_sample
+        o2 = b.step(p, ts[i], x, prev_timestep=prev, generator=g2).prev_sample
+        assert torch.equal(o1, o2), i
+        c_x0, c_x, sigma, _, _ = b.step_coefficients(int(ts[i]), None if prev is None else int(prev))
+        noise = torch.randn(p.shape, generator=torch.Generator().manual_seed(5))
+        want = c_x0 * p.clamp(-5, 5) + c_x * x + sigma * noise
+        assert torch.allclose(o1, want, atol=1e-6), i
+        assert (sigma == 0.0) == (int(ts[i]) == 0)
+    # last step (t = 0, prev = -1): alpha_bar_prev = 1 -> x_prev = clip(x0) exactly up to the tiny current-sample term
+    c_x0, c_x, sigma, _, _ = b.step_coefficients(0, None)
+    assert abs(c_x0 - 1.0) < 1e-3 and c_x == 0.0 and sigma == 0.0
+    # epsilon prediction (not the kandinsky config, but part of the scheduler surface)
+    e1 = UnCLIPSchedulerRef(prediction_type="epsilon", clip_sample_range=1.0)
+    e2 = UnCLIPScheduler(prediction_type="epsilon", clip_sample_range=1.0)
+    o1 = e1.step(p / 8, 500, x / 3, generator=torch.Generator().manual_seed(1)).prev_sample
+    o2 = e2.step(p / 8, 500, x / 3, generator=torch.Generator().manual_seed(1)).prev_sample
+    assert torch.equal(o1, o2)
+    with pytest.raises(ValueError):
+        UnCLIPScheduler(beta_schedule="linear")
+
+
+# ---- host-side loop logic (python loop of the product pipeline == oracle loop) -----------------------------------
+class _OraclePrior:
+    """Stand-in with the module surface the pipeline's python loop uses; arithmetic = oracle forward (CPU)."""
+
+    def __init__(self, cfg):
+        self.cfg, self.sd = cfg, synthetic_prior_state_dict(cfg)
+        self.config = type("C", (), {"embedding_dim": cfg["embedding_dim"]})()
+
+    def __call__(self, x, timestep, proj_embedding, encoder_hidden_states, proj_embedding1, mask_label, attention_mask):
+        out = prior_forward(self.sd, self.cfg, x, timestep, proj_embedding, encoder_hidden_states, proj_embedding1,
+                            mask_label, attention_mask)
+        return type("O", (), {"predicted_image_embedding": out})()
+
+    def post_process_latents(self, x):
+        return x * CLIP_STD + CLIP_MEAN
+
+
+@pytest.mark.parametrize("guidance", [4.0, 1.0])
+def test_pipeline_python_loop_matches_oracle_loop(guidance):
+    cfg = prior_tiny_config(num_layers=1)
+    steps = 4
+    inp = synthetic_prior_inputs(cfg, clip_index=1, steps=steps)
+    fake = _OraclePrior(cfg)
+    pipe = Seq_Inpaint_Prior_Pipeline(prior=fake, image_encoder=None, text_encoder=None, tokenizer=None,
+                                      scheduler=UnCLIPScheduler(**PRIOR_SCHEDULER_KWARGS))
+    kw = dict(prompt_embeds=inp["prompt_embeds"], text_mask=inp["text_mask"], imgs_proj_embeds1=inp["imgs_proj_embeds1"],
+              mask_label=inp["mask_label"])
+    if guidance <= 1:
+        kw["prompt_embeds"], kw["text_mask"] = kw["prompt_embeds"][5:], kw["text_mask"][5:]
+        hidden = inp["text_hidden"][5:]
+    else:
+        hidden = inp["text_hidden"]
+    with torch.no_grad():
+        mine = pipe.sample(inp["latents"], kw["prompt_embeds"], hidden, kw["text_mask"], inp["imgs_proj_embeds1"],
+                           inp["mask_label"], steps, guidance, noise=inp["noise"])
+        ref = prior_loop(lambda x, t, pe, ehs, p1, ml, tm: prior_forward(fake.sd, cfg, x, t, pe, ehs, p1, ml, tm),
+                         inp["latents"], kw["prompt_embeds"], hidden, kw["text_mask"], inp["imgs_proj_embeds1"],
+                         inp["mask_label"], steps, guidance, noise=inp["noise"])
+    assert torch.allclose(fake.post_process_latents(mine), ref, atol=1e-5)
+    assert pipe.num_timesteps == steps and pipe.do_classifier_free_guidance == (guidance > 1)
+
+
+def test_generator_consumption_order_matches_reference_loop():
+    """Noise drawn up front == noise drawn step by step: same generator state, same numbers (CPU generator)."""
+    g1, g2 = torch.Generator().manual_seed(9), torch.Generator().manual_seed(9)
+    a = torch.stack([torch.randn((5, 64), generator=g1) for _ in range(3)])
+    b = [torch.randn((5, 64), generator=g2) for _ in range(3)]
+    assert all(torch.equal(a[i], b[i]) for i in range(3))
+
+
+# ---- module surface / error behaviour ------------------------------------------------------------------------------
+def test_module_surface_and_errors():
+    cfg = prior_tiny_config()
+    m = MyPriorTransformer.from_config(cfg, unknown_key=1)
+    assert m.config.num_embeddings == 11 and m.dtype == torch.float32
+    assert float(m.positional_embedding.abs().max()) == 0.0  # zero-initialised like the reference
+    x = torch.full((5, 64), 2.0)
+    assert torch.allclose(m.post_process_latents(x), x * 0.415 - 0.016)
+    with pytest.raises(TypeError):  # fp32 module: no tensor-core path, and no CPU fallback either
+        m(torch.zeros(10, 64), 5, torch.zeros(10, 64), torch.zeros(10, 11, 64), torch.zeros(10, 1, 64),
+          torch.zeros(10, 1, 64))
+    with pytest.raises(RuntimeError):  # half module on the CPU
+        m.half()(torch.zeros(10, 64), 5, torch.zeros(10, 64), torch.zeros(10, 11, 64), torch.zeros(10, 1, 64),
+                 torch.zeros(10, 1, 64))
+    with pytest.raises(ValueError):
+        MyPriorTransformer(**{**cfg, "added_emb_type": "foo"})
+    with pytest.raises(ValueError):
+        MyPriorTransformer(**{**cfg, "norm_in_type": "group"})
+    with pytest.raises(TypeError):
+        MyPriorTransformer(bogus=1)
+    with pytest.raises(RuntimeError):
+        MyPriorTransformer.from_pretrained_2d("/nonexistent", subfolder="prior", unet_additional_kwargs={})
+
+
+def test_from_pretrained_2d_roundtrip(tmp_path):
+    """``from_pretrained_2d`` (myprior_transformer.py:416-448): config.json + .bin, num_embeddings / additional_embeddings
+    forced to 91 / 6, ``positional_embedding`` dropped from the 2-D checkpoint."""
+    import json
+    from rcdms_b200.prior_spec import _motion_kwargs
+    base = {k: v for k, v in prior_tiny_config().items() if k not in _motion_kwargs()}
+    base.update(num_embeddings=77, additional_embeddings=4, num_layers=1)
+    d = tmp_path / "prior"
+    d.mkdir()
+    (d / "config.json").write_text(json.dumps(base))
+    cfg2d = {**prior_tiny_config(num_layers=1), "num_embeddings": 77, "additional_embeddings": 4,
+             "use_motion_module": False}
+    sd2d = synthetic_prior_state_dict(cfg2d)
+    torch.save(sd2d, d / "diffusion_pytorch_model.bin")
+    m = MyPriorTransformer.from_pretrained_2d(str(tmp_path), subfolder="prior", unet_additional_kwargs=_motion_kwargs())
+    assert m.config.num_embeddings == 91 and m.config.additional_embeddings == 6
+    assert m.positional_embedding.shape == (1, 97, 128) and float(m.positional_embedding.abs().max()) == 0.0
+    assert torch.equal(m.proj_in.weight, sd2d["proj_in.weight"])
+    assert "transformer_blocks.1.temporal_transformer.proj_out.weight" in m.state_dict()
+
+
+def test_src_import_paths():
+    from src.models.myprior_transformer import MyPriorTransformer as A
+    from src.pipelines.prior_pipeline import Seq_Inpaint_Prior_Pipeline as B
+    assert A is MyPriorTransformer and B is Seq_Inpaint_Prior_Pipeline
