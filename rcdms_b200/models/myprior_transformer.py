@@ -189,14 +189,17 @@ class MyPriorTransformer(nn.Module):
     def _versions(self):
         return tuple((t.data_ptr(), t._version) for t in self.state_dict(keep_vars=True).values())
 
+    def _require_cuda(self) -> None:
+        if self.device.type != "cuda":
+            raise RuntimeError("MyPriorTransformer.forward needs the module on a CUDA device "
+                               "(no CPU fallback exists for the prior path)")
+
     def _ensure_packed(self):
         dt = self.dtype
         if dt not in (torch.float16, torch.bfloat16):
             raise TypeError("the B200 prior path computes in float16 or bfloat16 (tensor cores); "
                             f"call .half() / .to(torch.bfloat16) first (module dtype is {dt})")
-        if self.device.type != "cuda":
-            raise RuntimeError("MyPriorTransformer.forward needs the module on a CUDA device "
-                               "(no CPU fallback exists for the prior path)")
+        self._require_cuda()
         v = self._versions()
         if self._packed is not None and v == self._packed_versions:
             return self._packed
@@ -239,7 +242,6 @@ class MyPriorTransformer(nn.Module):
                                      fn=norm(t + ".ff_norm"), ff1=self._pack_geglu(lin(t + ".ff.net.0.proj")),
                                      ff2=lin(t + ".ff.net.2"), po=lin(m + ".proj_out"))
             P["layers"].append(lay)
-        torch.cuda.current_stream().synchronize()
         self._packed, self._packed_versions = P, v
         self._plans.clear()
         return P

@@ -229,3 +229,73 @@ def test_src_import_paths():
     from src.models.myprior_transformer import MyPriorTransformer as A
     from src.pipelines.prior_pipeline import Seq_Inpaint_Prior_Pipeline as B
     assert A is MyPriorTransformer and B is Seq_Inpaint_Prior_Pipeline
+
+
+# ---- host orchestration of the product module / pipeline against the oracle, through a CPU emulation of the C ABI ----
+@pytest.fixture
+def fake_cabi(monkeypatch):
+    """Route the product's C-ABI calls to tests/fake_rcdm_lib.FakeLib (CPU fp16 emulation of the entry points) so the
+    host code can run in the CPU tier.  The product itself has no such path: it raises without CUDA."""
+    from fake_rcdm_lib import FakeLib
+    from rcdms_b200 import _lib
+    fake = FakeLib()
+    monkeypatch.setattr(_lib, "lib", lambda: fake)
+    monkeypatch.setattr(_lib, "current_stream_ptr", lambda: 0)
+    monkeypatch.setattr(MyPriorTransformer, "_require_cuda", lambda self: None)
+    return fake
+
+
+def _half_module(cfg):
+    sd = synthetic_prior_state_dict(cfg)
+    m = MyPriorTransformer.from_config(cfg)
+    m.load_state_dict(sd, strict=True)
+    return m.half(), {k: v.half().float() for k, v in sd.items()}
+
+
+@pytest.mark.parametrize("cfg,t,masked", [
+    (prior_tiny_config(), 500, True), (prior_tiny_config(), 3, False),
+    (prior_tiny_config(norm_in_type="layer", embedding_proj_norm_type="layer", num_layers=1, added_emb_type=None,
+                       additional_embeddings=5), 17, True),
+    (prior_tiny_config(use_motion_module=False, num_layers=1), 999, True)])
+def test_host_forward_orchestration_matches_oracle(fake_cabi, cfg, t, masked):
+    m, sdr = _half_module(cfg)
+    inp = synthetic_prior_inputs(cfg, clip_index=3)
+    a = [torch.cat([inp["latents"]] * 2), inp["prompt_embeds"], inp["text_hidden"],
+         torch.cat([inp["imgs_proj_embeds1"]] * 2), torch.cat([inp["mask_label"]] * 2)]
+    a16 = [x.half() for x in a]
+    mask = inp["text_mask"] if masked else None
+    y = m(a16[0], t, a16[1], a16[2], a16[3], a16[4], mask).predicted_image_embedding
+    with torch.no_grad():
+        ref = prior_forward(sdr, cfg, *[x.float() for x in [a16[0]]], t, a16[1].float(), a16[2].float(), a16[3].float(),
+                            a16[4].float(), mask)
+    assert y.dtype == torch.float16 and y.shape == ref.shape
+    assert (y.float() - ref).abs().max().item() < 2e-2 * max(1.0, ref.abs().max().item())
+    assert (y.float() - ref).abs().mean().item() < 2e-3
+    kinds = [c[0] for c in fake_cabi.calls]
+    assert kinds.count("mattn") == cfg["num_layers"]
+    assert kinds.count("tattn") == (2 * cfg["num_layers"] if cfg["use_motion_module"] else 0)
+
+
+@pytest.mark.parametrize("guidance", [4.0, 1.0])
+def test_host_native_loop_orchestration_matches_oracle(fake_cabi, monkeypatch, guidance):
+    cfg = prior_tiny_config(num_layers=1)
+    steps = 4
+    m, sdr = _half_module(cfg)
+    inp = synthetic_prior_inputs(cfg, clip_index=1, steps=steps)
+    h = {k: v.half() if v.is_floating_point() else v for k, v in inp.items()}
+    pipe = Seq_Inpaint_Prior_Pipeline(prior=m, image_encoder=None, text_encoder=None, tokenizer=None,
+                                      scheduler=UnCLIPScheduler(**PRIOR_SCHEDULER_KWARGS))
+    pipe.use_cuda_graph = False
+    monkeypatch.setattr(pipe, "_native_ok", lambda latents, cb: True)  # CPU tensors, emulated C ABI
+    sel = slice(None) if guidance > 1 else slice(5, None)
+    out = pipe.sample(h["latents"], h["prompt_embeds"][sel], h["text_hidden"][sel], h["text_mask"][sel],
+                      h["imgs_proj_embeds1"], h["mask_label"], steps, guidance, noise=h["noise"])
+    f = {k: v.float() if v.is_floating_point() else v for k, v in h.items()}
+    with torch.no_grad():
+        ref = prior_loop(lambda x, t, pe, ehs, p1, ml, tm: prior_forward(sdr, cfg, x, t, pe, ehs, p1, ml, tm),
+                         f["latents"], f["prompt_embeds"][sel], f["text_hidden"][sel], f["text_mask"][sel],
+                         f["imgs_proj_embeds1"], f["mask_label"], steps, guidance, noise=f["noise"])
+    mine = m.post_process_latents(out).float()
+    assert (mine - ref).abs().max().item() < 3e-2 * max(1.0, ref.abs().max().item())
+    assert [c[0] for c in fake_cabi.calls].count("unclip") == steps
+    assert torch.equal(h["latents"], inp["latents"].half())  # the caller's latents are not modified
