@@ -39,7 +39,8 @@ def test_errors_are_python_exceptions():
 @pytest.mark.parametrize("pair,sk", [(0, 0), (2, 0), (0, 1), (2, 1)])
 def test_gemm_scheduling_variants_agree(pair, sk):
     """CTA-pair (cta_group::2) kernel and stream-K decomposition forced on / off through the tuning knobs: every
-    combination must pass the same parity checks, and pairing must not change a single bit (same K order)."""
+    combination must pass the same parity checks, and without stream-K pairing must not change a single bit (same K
+    order per output element; with stream-K the split points depend on the worker count, so only parity is required)."""
     from rcdms_b200 import _lib, ops
     L = _lib.lib()
     prev_pair, prev_sk = L.rcdm_set_gemm_pair(pair), L.rcdm_set_stream_k_min(sk)
@@ -60,7 +61,11 @@ def test_gemm_scheduling_variants_agree(pair, sk):
         w = (torch.randn((1280, 640), generator=g, device="cuda") / 25).half()
         out = ops.linear(a, w)
         L.rcdm_set_gemm_pair(0)
-        assert torch.equal(out, ops.linear(a, w)), "pairing changed the result bitwise"
+        ref = ops.linear(a, w)
+        if sk == 0:
+            assert torch.equal(out, ref), "pairing changed the result bitwise"
+        else:
+            assert (out.float() - ref.float()).abs().max().item() <= 2e-3 * ref.float().abs().max().item()
     finally:
         L.rcdm_set_gemm_pair(prev_pair)
         L.rcdm_set_stream_k_min(prev_sk)
