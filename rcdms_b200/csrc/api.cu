@@ -515,6 +515,24 @@ int rcdm_masked_attn(int dtype, const void* qkv_dev, int ld, const float* key_bi
   const size_t smem = masked_attn_smem_bytes(S, d);
   if (smem > 200 * 1024) return set_err("rcdm_masked_attn: S * d too large for shared memory");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  // the prior's shape (d = 64, <= 112 tokens): tensor-core kernel, whole key range in registers
+  static const bool mma_on = [] {
+    const char* e = getenv("RCDM_MASKED_ATTN_MMA");
+    return !(e && e[0] == '0');
+  }();
+  if (mma_on && d == MATTN_D && S <= MATTN_NT * 8 && ld % 2 == 0) {
+    const float sc = 1.0f / sqrtf((float)d);
+    if (dtype == DT_F16)
+      masked_attn_mma_kernel<__half><<<batch * heads, 224, masked_attn_mma_smem_bytes(), st>>>(
+          reinterpret_cast<const __half*>(qkv_dev), ld, key_bias_dev, causal, reinterpret_cast<__half*>(out_dev), ldo, S,
+          heads, sc);
+    else
+      masked_attn_mma_kernel<__nv_bfloat16><<<batch * heads, 224, masked_attn_mma_smem_bytes(), st>>>(
+          reinterpret_cast<const __nv_bfloat16*>(qkv_dev), ld, key_bias_dev, causal,
+          reinterpret_cast<__nv_bfloat16*>(out_dev), ldo, S, heads, sc);
+    g_launches++;
+    return check_launch("rcdm_masked_attn");
+  }
   const dim3 grid(batch * heads, (S + MASKED_ATTN_QCHUNK - 1) / MASKED_ATTN_QCHUNK);
   const float scale = 1.0f / sqrtf((float)d);
   if (dtype == DT_F16) {

@@ -1,6 +1,7 @@
 // Host side of the attention kernels: 5-D TMA maps over the fused projection outputs, launch, and a
 // CUDA-core debug kernel with identical semantics (RCDM_SIMPLE=1 only).
 #include "launch.h"
+#include "prior_kernels.cuh"
 
 namespace rcdm {
 
@@ -171,6 +172,29 @@ void temporal_attn_launch(int dt, const void* qkv, void* out, int batch, int fra
   const size_t total = (size_t)batch * hw * heads;
   const int blocks = (int)((total + 127) / 128);
   const float scale = 1.0f / sqrtf((float)d);
+  // wide heads (the stage-1 prior's motion modules, d = 256): d / 8 lanes per (location, head), shuffle-reduced scores
+  static const bool wide_on = [] {
+    const char* e = getenv("RCDM_TEMPORAL_WIDE");
+    return !(e && e[0] == '0');
+  }();
+  if (wide_on && frames == 5 && (d == 64 || d == 128 || d == 256)) {
+    const int lph = d / 8;
+    const int wblocks = (int)((total * lph + 255) / 256);
+#define RCDM_TW(T, L)                                                                                      \
+  launch_k(temporal_attn_wide_kernel<T, 5, L>, dim3(wblocks), dim3(256), 0, s, reinterpret_cast<const T*>(qkv), \
+           reinterpret_cast<T*>(out), batch, hw, heads, scale)
+    if (dt == DT_F16) {
+      if (lph == 8) RCDM_TW(__half, 8);
+      else if (lph == 16) RCDM_TW(__half, 16);
+      else RCDM_TW(__half, 32);
+    } else {
+      if (lph == 8) RCDM_TW(__nv_bfloat16, 8);
+      else if (lph == 16) RCDM_TW(__nv_bfloat16, 16);
+      else RCDM_TW(__nv_bfloat16, 32);
+    }
+#undef RCDM_TW
+    return;
+  }
   // tiled kernel (coalesced through shared memory): PT = pixels per CTA, a power of two dividing hw with
   // <= 80 KB of shared memory and <= 512 threads; the one-thread-per-(pixel, head) kernel is the fallback
   static const bool tiled_on = [] {

@@ -43,7 +43,10 @@ def _gen(seed=0):
 @pytest.mark.parametrize("b,S,heads,d,dtype,masked", [
     (10, 97, 32, 64, torch.float16, True), (10, 97, 32, 64, torch.bfloat16, True), (10, 97, 32, 64, torch.float16, False),
     (5, 17, 2, 64, torch.float16, True), (5, 17, 8, 16, torch.float16, True), (3, 256, 2, 128, torch.float16, True),
-    (2, 33, 3, 40, torch.bfloat16, True)])
+    (2, 33, 3, 40, torch.bfloat16, True),
+    # d = 64, S <= 112: the mma.sync kernel (full / ragged last row tile / single tile); S = 113 falls back
+    (4, 112, 4, 64, torch.float16, True), (2, 16, 2, 64, torch.bfloat16, False), (3, 113, 2, 64, torch.float16, True),
+    (2, 100, 3, 64, torch.bfloat16, True), (1, 8, 1, 64, torch.float16, True)])
 def test_masked_attention(b, S, heads, d, dtype, masked):
     g = _gen(1)
     C = heads * d
@@ -120,7 +123,9 @@ def test_layernorm_wide(rows, C, dtype, pe):
 
 
 @pytest.mark.parametrize("b,hw,heads,d,dtype", [(2, 97, 8, 256, torch.float16), (2, 97, 8, 256, torch.bfloat16),
-                                                (1, 17, 8, 16, torch.float16), (2, 33, 8, 24, torch.float16)])
+                                                (1, 17, 8, 16, torch.float16), (2, 33, 8, 24, torch.float16),
+                                                (2, 33, 8, 64, torch.float16), (1, 50, 4, 128, torch.bfloat16),
+                                                (3, 7, 2, 256, torch.float16)])
 def test_temporal_attention_prior_shapes(b, hw, heads, d, dtype):
     g = _gen(5)
     C, f = heads * d, 5
@@ -243,6 +248,23 @@ def test_prior_forward_matches_reference_golden(name):
     assert d.mean().item() <= 3 * r["fmean"] + 2e-4, (d.mean().item(), r["fmean"])
     r2 = _forward_case(gold["cfg"], torch.float16, gold["timestep"], masked=False)
     assert (r2["y"].float().cpu() - gold["out_nomask"]).abs().max().item() <= max(4 * r2["fmax"], 8e-3)
+
+
+def test_masked_attention_mma_and_generic_kernels_agree():
+    """RCDM_MASKED_ATTN_MMA is read once per process, so the generic kernel is reached through a shape the tensor-core
+    kernel does not take (row pitch irrelevant; S = 113) and both are compared on the overlapping 97-token problem by
+    embedding it into a 113-token one whose extra keys are masked out and whose extra queries are ignored."""
+    g = _gen(8)
+    b, S, S2, heads, d = 4, 97, 113, 4, 64
+    C = heads * d
+    qkv = torch.randn((b, S2, 3 * C), generator=g, device="cuda").half()
+    kb = torch.zeros((b, S2), device="cuda")
+    kb[:, 60:80] = -10000.0
+    kb2 = kb.clone()
+    kb2[:, S:] = -30000.0  # keys 97.. contribute exp(-3e4) = 0 exactly
+    small = ops.masked_attention(qkv[:, :S].contiguous(), heads, kb[:, :S].contiguous(), causal=True)   # mma kernel
+    big = ops.masked_attention(qkv, heads, kb2, causal=True)[:, :S]                                     # generic kernel
+    assert (small.float() - big.float()).abs().max().item() <= 2e-3
 
 
 def test_prior_simple_and_tensorcore_paths_agree():
