@@ -523,11 +523,11 @@ int rcdm_masked_attn(int dtype, const void* qkv_dev, int ld, const float* key_bi
   if (mma_on && d == MATTN_D && S <= MATTN_NT * 8 && ld % 2 == 0) {
     const float sc = 1.0f / sqrtf((float)d);
     if (dtype == DT_F16)
-      masked_attn_mma_kernel<__half><<<batch * heads, 224, masked_attn_mma_smem_bytes(), st>>>(
+      masked_attn_mma_kernel<__half><<<batch * heads, MATTN_THREADS, masked_attn_mma_smem_bytes(), st>>>(
           reinterpret_cast<const __half*>(qkv_dev), ld, key_bias_dev, causal, reinterpret_cast<__half*>(out_dev), ldo, S,
           heads, sc);
     else
-      masked_attn_mma_kernel<__nv_bfloat16><<<batch * heads, 224, masked_attn_mma_smem_bytes(), st>>>(
+      masked_attn_mma_kernel<__nv_bfloat16><<<batch * heads, MATTN_THREADS, masked_attn_mma_smem_bytes(), st>>>(
           reinterpret_cast<const __nv_bfloat16*>(qkv_dev), ld, key_bias_dev, causal,
           reinterpret_cast<__nv_bfloat16*>(out_dev), ldo, S, heads, sc);
     g_launches++;

@@ -128,7 +128,7 @@ masked_attn_kernel(const T* __restrict__ qkv, int ld, const float* __restrict__ 
 //   S = Q K^T   mma.sync.m16n8k16 (A = Q from global, B = K rows from shared memory, pitch d + 8 -> conflict-free)
 //   P = round16(exp(S - max) / sum)   in the accumulator registers, which ARE the A fragments of the second MMA
 //   O = P V     B = V^T from shared memory (transposed on the way in, pitch NT*8 + 8)
-// One CTA per (batch, head), one warp per 16-row tile.  Replaces ~50 M CUDA-core warp instructions of the generic
+// One CTA per (batch, head); 4 warps, warp w takes the 16-row tiles w and (tiles - 1 - w), which balances the causal work.  Replaces ~50 M CUDA-core warp instructions of the generic
 // kernel (70 us per launch, 13 % of a prior step) by ~25 k MMAs.
 // ---------------------------------------------------------------------------------------------------------------
 template <typename T> struct MmaOp;
@@ -155,8 +155,9 @@ inline size_t masked_attn_mma_smem_bytes() {
   return (size_t)(MATTN_NT * 8) * MATTN_KP * 2 + (size_t)MATTN_D * MATTN_VP * 2;
 }
 
+constexpr int MATTN_THREADS = 128;  // 4 warps: warp w owns row tiles w and (tiles - 1 - w) -> equal causal work
 template <typename T>
-__global__ void __launch_bounds__(224)
+__global__ void __launch_bounds__(MATTN_THREADS, 4)
 masked_attn_mma_kernel(const T* __restrict__ qkv, int ld, const float* __restrict__ key_bias, int causal,
                        T* __restrict__ out, int ldo, int S, int heads, float scale) {
   using T2 = typename DT<T>::T2;
@@ -169,21 +170,41 @@ masked_attn_mma_kernel(const T* __restrict__ qkv, int ld, const float* __restric
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
   const T* base = qkv + (size_t)b * S * ld + h * D;
   pdl_sync();
-  const T2 zero2 = DT<T>::from_f2(0.f, 0.f);
-  for (int i = tid; i < SK * (D / 2); i += blockDim.x) {
-    const int j = i / (D / 2), c = (i % (D / 2)) * 2;
-    T2 kv = zero2, vv = zero2;
+  // causal: the CTA's last row tile sees keys < 16 * tiles, and row tile w only key tiles nt < 2 w + 2
+  const int row_tiles = (S + 15) / 16;
+  const int sk_used = causal ? min(SK, row_tiles * 16) : SK;
+  const bool vec16 = (ld % 8 == 0) && ((reinterpret_cast<uintptr_t>(qkv) & 15) == 0);
+  for (int i = tid; i < sk_used * (D / 8); i += blockDim.x) {  // 16-byte global loads: 8 channels of one key
+    const int j = i / (D / 8), c = (i % (D / 8)) * 8;
+    uint4 kv = make_uint4(0, 0, 0, 0), vv = make_uint4(0, 0, 0, 0);
     if (j < S) {
-      kv = *reinterpret_cast<const T2*>(base + (size_t)j * ld + C + c);
-      vv = *reinterpret_cast<const T2*>(base + (size_t)j * ld + 2 * C + c);
+      const T* kp = base + (size_t)j * ld + C + c;
+      if (vec16) {
+        kv = __ldg(reinterpret_cast<const uint4*>(kp));
+        vv = __ldg(reinterpret_cast<const uint4*>(kp + C));
+      } else {
+        uint32_t* k4 = reinterpret_cast<uint32_t*>(&kv);
+        uint32_t* v4 = reinterpret_cast<uint32_t*>(&vv);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          k4[e] = *reinterpret_cast<const uint32_t*>(kp + 2 * e);
+          v4[e] = *reinterpret_cast<const uint32_t*>(kp + C + 2 * e);
+        }
+      }
     }
-    *reinterpret_cast<T2*>(Ks + j * KP + c) = kv;
-    Vt[c * VP + j] = vv.x;
-    Vt[(c + 1) * VP + j] = vv.y;
+    *reinterpret_cast<uint4*>(Ks + j * KP + c) = kv;  // KP * 2 = 144 bytes: 16-byte aligned rows
+    const T* ve = reinterpret_cast<const T*>(&vv);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) Vt[(c + e) * VP + j] = ve[e];
   }
   __syncthreads();
-  const int r0 = warp * 16;
-  if (r0 >= S) return;  // warp-uniform; no barrier follows
+  // no barrier below this point; every branch on `tile` is warp-uniform
+  if (2 * warp > row_tiles - 1) return;  // warps beyond the middle tile have nothing to do
+  for (int pass = 0; pass < 2; ++pass) {
+  const int tile = pass == 0 ? warp : row_tiles - 1 - warp;
+  if (pass == 1 && tile <= warp) break;  // the middle tile is its own partner
+  const int r0 = tile * 16;
+  const int nt_used = causal ? min(NT, 2 * tile + 2) : NT;
   const int row_a = r0 + g, row_b = r0 + g + 8;
   // ---- Q fragments (A operand, row-major 16 x 16 per k-step): a0 (g, 2t) a1 (g+8, 2t) a2 (g, 2t+8) a3 (g+8, 2t+8)
   uint32_t qa[D / 16][4];
@@ -200,11 +221,13 @@ masked_attn_mma_kernel(const T* __restrict__ qkv, int ld, const float* __restric
 #pragma unroll
   for (int nt = 0; nt < NT; ++nt) {
     sc[nt][0] = sc[nt][1] = sc[nt][2] = sc[nt][3] = 0.f;
-    const T* kr = Ks + (nt * 8 + g) * KP + 2 * t;  // B fragment: b0 (k = 2t, 2t+1; n = g), b1 (k + 8)
+    if (nt < nt_used) {
+      const T* kr = Ks + (nt * 8 + g) * KP + 2 * t;  // B fragment: b0 (k = 2t, 2t+1; n = g), b1 (k + 8)
 #pragma unroll
-    for (int ks = 0; ks < D / 16; ++ks)
-      MmaOp<T>::mma(sc[nt], qa[ks], *reinterpret_cast<const uint32_t*>(kr + ks * 16),
-                    *reinterpret_cast<const uint32_t*>(kr + ks * 16 + 8));
+      for (int ks = 0; ks < D / 16; ++ks)
+        MmaOp<T>::mma(sc[nt], qa[ks], *reinterpret_cast<const uint32_t*>(kr + ks * 16),
+                      *reinterpret_cast<const uint32_t*>(kr + ks * 16 + 8));
+    }
   }
   // ---- scale, additive mask, softmax over the full row (quad reduction: lanes 4g .. 4g+3 share rows g, g+8)
   float mxa = -INFINITY, mxb = -INFINITY;
@@ -213,8 +236,8 @@ masked_attn_mma_kernel(const T* __restrict__ qkv, int ld, const float* __restric
 #pragma unroll
     for (int e = 0; e < 2; ++e) {
       const int j = nt * 8 + 2 * t + e;
-      float kb = -INFINITY;
-      if (j < S) kb = key_bias ? __ldg(key_bias + (size_t)b * S + j) : 0.f;
+      float kb = -INFINITY;  // padding keys, and (causal) key tiles entirely above this row tile's diagonal
+      if (j < S && nt < nt_used) kb = key_bias ? __ldg(key_bias + (size_t)b * S + j) : 0.f;
       const float va = sc[nt][e] * scale + kb + ((causal && j > row_a) ? -10000.f : 0.f);
       const float vb = sc[nt][2 + e] * scale + kb + ((causal && j > row_b) ? -10000.f : 0.f);
       sc[nt][e] = va;
@@ -249,6 +272,7 @@ masked_attn_mma_kernel(const T* __restrict__ qkv, int ld, const float* __restric
   for (int n = 0; n < D / 8; ++n) oc[n][0] = oc[n][1] = oc[n][2] = oc[n][3] = 0.f;
 #pragma unroll
   for (int kj = 0; kj < NT / 2; ++kj) {
+    if (2 * kj >= nt_used) break;  // warp-uniform: the remaining probabilities are exactly zero
     uint32_t pa[4];
     T2 p0 = DT<T>::from_f2(sc[2 * kj][0] * ia, sc[2 * kj][1] * ia);
     T2 p1 = DT<T>::from_f2(sc[2 * kj][2] * ib, sc[2 * kj][3] * ib);
@@ -270,6 +294,7 @@ masked_attn_mma_kernel(const T* __restrict__ qkv, int ld, const float* __restric
     if (row_a < S) *reinterpret_cast<T2*>(out + ((size_t)b * S + row_a) * ldo + c) = DT<T>::from_f2(oc[n][0], oc[n][1]);
     if (row_b < S) *reinterpret_cast<T2*>(out + ((size_t)b * S + row_b) * ldo + c) = DT<T>::from_f2(oc[n][2], oc[n][3]);
   }
+  }  // pass
 }
 
 // ---------------------------------------------------------------------------------------------------------------
