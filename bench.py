@@ -44,6 +44,10 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-profile", action="store_true")
     ap.add_argument("--cpu-budget-s", type=float, default=150.0)
+    ap.add_argument("--workload", default="stage2", choices=["stage2", "prior"],
+                    help="stage2 (default, the headline metric) | prior: BASELINE config 4, the stage-1 frame-prior loop "
+                         "(SURVEY 8f rank 1), single GPU")
+    ap.add_argument("--prior-steps", type=int, default=100)
     return ap.parse_args()
 
 
@@ -323,9 +327,136 @@ def run_ours(a):
         dist.destroy_process_group()
 
 
+# ----------------------------------------------------------------------------------------------------------
+# --workload prior: BASELINE config 4 (stage-1 frame-prior transformer diffusion, 100 UnCLIP steps, 1 GPU)
+# ----------------------------------------------------------------------------------------------------------
+PRIOR_METRIC = "stage-1 prior frame-embeddings/sec @100 UnCLIP steps, 5-frame clip"
+
+
+def prior_cpu_seconds_per_forward(layers_sample=2):
+    """Oracle restatement of MyPriorTransformer.forward (fp32, all host threads) on a `layers_sample`-layer slice of
+    the shipped configuration, scaled to the 20 layers (the layers are identical in cost)."""
+    import torch
+    from oracle.prior_ref import prior_forward
+    from rcdms_b200.prior_spec import prior_full_config, prior_state_dict_spec
+    from rcdms_b200.synthetic import synthetic_prior_inputs
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cfg = prior_full_config(num_layers=layers_sample)
+    g = torch.Generator().manual_seed(0)
+    sd = {n: torch.randn(sh, generator=g) * 0.02 for n, sh in prior_state_dict_spec(cfg)}
+    inp = synthetic_prior_inputs(cfg, 0)
+    args = (torch.cat([inp["latents"]] * 2), 500, inp["prompt_embeds"], inp["text_hidden"],
+            torch.cat([inp["imgs_proj_embeds1"]] * 2), torch.cat([inp["mask_label"]] * 2), inp["text_mask"])
+    with torch.no_grad():
+        prior_forward(sd, cfg, *args)
+        t0 = time.time()
+        prior_forward(sd, cfg, *args)
+        dt = time.time() - t0
+    full = prior_full_config()["num_layers"]
+    return dt * full / layers_sample, dict(cores=cores, sample_s=dt, layers_sample=layers_sample)
+
+
+def run_prior(a):
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "scripts"))
+    from bench_prior import algorithmic_flops, device_random_weights
+    from rcdms_b200 import _lib
+    from rcdms_b200.models.myprior_transformer import MyPriorTransformer
+    from rcdms_b200.pipelines.prior_pipeline import Seq_Inpaint_Prior_Pipeline
+    from rcdms_b200.prior_spec import PRIOR_SCHEDULER_KWARGS, prior_full_config
+    from rcdms_b200.schedulers import UnCLIPScheduler
+    from rcdms_b200.synthetic import synthetic_prior_inputs
+    steps_n = a.prior_steps
+    if a.impl == "reference":
+        t_fwd, info = prior_cpu_seconds_per_forward()
+        v = 5.0 / (t_fwd * steps_n)
+        cb = dict(value=v, unit="frame-embeddings/s", cores=info["cores"], kind="port",
+                  sample=f"oracle forward of a {info['layers_sample']}-layer slice ({info['sample_s']:.1f} s), scaled to 20 "
+                         f"layers x {steps_n} steps")
+        print(json.dumps(dict(metric=PRIOR_METRIC, value=v, unit="frame-embeddings/s", n_gpus=1, steps=1, warmup=1,
+                              ms_per_step=t_fwd * steps_n * 1e3, higher_is_better=True, scaling="weak", vs_baseline=None,
+                              dtype="f32", data="synthetic", impl="reference",
+                              config=dict(workload="stage-1 prior, kandinsky-2-2 + motion modules, CFG 4.0"),
+                              cpu_baseline=cb, gpu_launches=0,
+                              e2e=dict(value=v, unit="frame-embeddings/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))))
+        return
+    pk = peaks()
+    dtype = torch.float16 if a.dtype == "fp16" else torch.bfloat16
+    cfg = prior_full_config()
+    model = device_random_weights(MyPriorTransformer.from_config(cfg), dtype)
+    pipe = Seq_Inpaint_Prior_Pipeline(prior=model, image_encoder=None, text_encoder=None, tokenizer=None,
+                                      scheduler=UnCLIPScheduler(**PRIOR_SCHEDULER_KWARGS))
+    pipe.use_cuda_graph = not a.no_graph
+    host = {k: (v.to(dtype) if v.is_floating_point() else v).pin_memory()
+            for k, v in synthetic_prior_inputs(cfg, 0).items()}
+    gen = torch.Generator(device="cuda").manual_seed(42)
+
+    def sample(dev):
+        return pipe.sample(dev["latents"], dev["prompt_embeds"], dev["text_hidden"], dev["text_mask"],
+                           dev["imgs_proj_embeds1"], dev["mask_label"], steps_n, 4.0, generator=gen)
+
+    dev = {k: v.cuda() for k, v in host.items()}
+    warm = max(a.warmup, 3)
+    for _ in range(warm):
+        sample(dev)
+    torch.cuda.synchronize()
+    sampler = ClockSampler(0)
+    sampler.start()
+    l0 = _lib.lib().rcdm_kernel_launches()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(a.steps):
+        out = sample(dev)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / a.steps
+    launches = (_lib.lib().rcdm_kernel_launches() - l0)
+    # the library counts host-issued launches; with the CUDA graph a sampling run issues one step twice on the host
+    # (warm-up + capture) and replays it steps_n - 1 times on the device: scale to the launches the GPU executed
+    launches_total = launches if a.no_graph else launches / 2.0 * steps_n
+    out_host = torch.empty(out.shape, dtype=out.dtype).pin_memory()
+    e0.record()
+    for _ in range(a.steps):
+        d = {k: v.cuda(non_blocking=True) for k, v in host.items()}
+        out_host.copy_(model.post_process_latents(sample(d)), non_blocking=True)
+    e1.record()
+    torch.cuda.synchronize()
+    ms_e2e = e0.elapsed_time(e1) / a.steps
+    clocks = sampler.stop()
+    fl = algorithmic_flops(cfg, 10) * steps_n
+    cb = None
+    if not a.no_cpu_baseline:
+        t_fwd, info = prior_cpu_seconds_per_forward()
+        cb = dict(value=5.0 / (t_fwd * steps_n), unit="frame-embeddings/s", cores=info["cores"], kind="port",
+                  sample=f"oracle forward of a {info['layers_sample']}-layer slice ({info['sample_s']:.1f} s), scaled to 20 "
+                         f"layers x {steps_n} steps")
+    tf = fl / (ms / 1e3) / 1e12
+    print(json.dumps(dict(
+        metric=PRIOR_METRIC, value=5.0 / (ms / 1e3), unit="frame-embeddings/s", n_gpus=1, steps=a.steps, warmup=warm,
+        ms_per_step=ms, higher_is_better=True, scaling="weak", vs_baseline=None,
+        dtype="f16" if a.dtype == "fp16" else "bf16", data="synthetic",
+        config=dict(workload="stage-1 prior: kandinsky-2-2 prior + 20 prior-state motion modules (2.88 B params), 97 tokens, "
+                             f"CFG 4.0 (10 rows), {steps_n} UnCLIP steps, 1 clip", cuda_graph=not a.no_graph,
+                    ms_per_unclip_step=ms / steps_n,
+                    l2="not flushed: 5.76 GB of fp16 weights stream through per step >> 126 MB L2"),
+        e2e=dict(value=5.0 / (ms_e2e / 1e3), unit="frame-embeddings/s", ms_per_step=ms_e2e,
+                 h2d_bytes_per_step=sum(v.numel() * v.element_size() for v in host.values()),
+                 d2h_bytes_per_step=out_host.numel() * out_host.element_size(),
+                 api="Seq_Inpaint_Prior_Pipeline.sample + post_process_latents (host pinned tensors in, host embeddings out)"),
+        gpu_launches=int(launches_total), clocks=clocks,
+        roofline=dict(bound="tensor", kernel="gemm_tcgen05_kernel", achieved=tf, peak=pk["tflops"], unit="TFLOP/s",
+                      frac=tf / pk["tflops"], traffic=None, peak_source=pk["source"],
+                      note="achieved = algorithmic FLOPs of the whole step / whole-step time (lower bound for the GEMM "
+                           "kernel, which is ~85 % of the step: profiles/r01_prior_*)"),
+        cpu_baseline=cb)), flush=True)
+
+
 def main():
     a = parse()
-    if a.impl == "reference":
+    if a.workload == "prior":
+        run_prior(a)
+    elif a.impl == "reference":
         run_reference(a)
     else:
         run_ours(a)
