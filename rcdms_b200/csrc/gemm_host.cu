@@ -255,7 +255,7 @@ bool gemm_prepare(const GemmDesc& d, GemmLaunch* l, std::string* err) {
   // (the big 3x3 convolutions); small-K GEMMs are bound by their epilogue / L2 traffic and lose a little.
   // RCDM_GEMM_PAIR = 0 never, 1 heuristic (default), 2 whenever there are >= 2 M tiles.
   const int pair_mode = pair_enabled();
-  l->pair = (!d.no_pair && num_sms() >= 2 &&
+  l->pair = (!d.no_pair && !d.act && num_sms() >= 2 &&  // activation epilogues exist for the single-CTA kernel only
              ((d.force_pair && m_tiles >= 2) || (pair_mode == 2 && m_tiles >= 2) ||
               (pair_mode == 1 && kb >= 90 && m_tiles >= 16))) ? 1 : 0;
   {
@@ -310,6 +310,11 @@ bool gemm_prepare(const GemmDesc& d, GemmLaunch* l, std::string* err) {
 }
 
 template <typename T, int BN> static void launch_one(const GemmLaunch& l, cudaStream_t s) {
+  if (l.p.act) {  // GELU / SiLU epilogue (stage-1 prior): separate instantiation, see gemm_tcgen05.cuh
+    launch_k(gemm_tcgen05_kernel<T, BN, false, true>, l.grid, dim3(GemmCfg<BN, false>::THREADS),
+             GemmCfg<BN, false>::SMEM_BYTES, s, l.maps, l.p);
+    return;
+  }
   if (!l.pair) {
     launch_k(gemm_tcgen05_kernel<T, BN, false>, l.grid, dim3(GemmCfg<BN, false>::THREADS), GemmCfg<BN, false>::SMEM_BYTES, s,
              l.maps, l.p);
@@ -350,6 +355,9 @@ template <typename T, int BN> static cudaError_t set_attr() {
   if (e == cudaSuccess)
     e = cudaFuncSetAttribute(gemm_tcgen05_kernel<T, BN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              GemmCfg<BN, true>::SMEM_BYTES);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(gemm_tcgen05_kernel<T, BN, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             GemmCfg<BN, false>::SMEM_BYTES);
   return e;
 }
 

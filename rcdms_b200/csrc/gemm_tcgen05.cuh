@@ -161,7 +161,10 @@ template <int BN, bool PAIR = false> struct GemmCfg {
 // (n fastest, so CTAs running concurrently share A rows in L2).  The TMA producer runs ahead across tile
 // boundaries; two TMEM accumulators let the MMA warp start tile i+1 while the epilogue warps drain tile i.
 // 10 warps = 3 on the fullest SM sub-partition (16384 registers each) => at most 168 registers per thread.
-template <typename T, int BN, bool PAIR>
+// ACT: compile-time switch for the epilogue activation (p.act).  The activation-free instantiation is the one every
+// UNet GEMM runs: a run-time branch inside `finish8` cost the epilogue-bound small-K GEMMs 15-19 % (measured), so the
+// stage-1 prior's GELU / SiLU epilogues get their own instantiation.
+template <typename T, int BN, bool PAIR, bool ACT = false>
 __global__ void __launch_bounds__(GemmCfg<BN, PAIR>::THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
   using Cfg = GemmCfg<BN, PAIR>;
@@ -605,12 +608,14 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
         float st_s = 0.f, st_ss = 0.f;  // row statistics of the final values (folded-LayerNorm producer)
         using T2 = typename DT<T>::T2;
         auto finish8 = [&](float* v, int c) {  // 8 outputs at columns c.. of this warp's slice
-          if (p.act == 1) {
+          if constexpr (ACT) {
+            if (p.act == 1) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) v[i] = gelu_erf_f(v[i]);
-          } else if (p.act == 2) {
+              for (int i = 0; i < 8; ++i) v[i] = gelu_erf_f(v[i]);
+            } else if (p.act == 2) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) v[i] = silu_f(v[i]);
+              for (int i = 0; i < 8; ++i) v[i] = silu_f(v[i]);
+            }
           }
           uint4 pk = pack8<T>(v);
           uint4* dst = reinterpret_cast<uint4*>(srow + c * 2);
