@@ -60,3 +60,11 @@ def run_sharded(n_clips: int, denoise_clips: Callable[[Sequence[int]], torch.Ten
     if local.shape[0] != len(mine):
         raise ValueError(f"denoise_clips returned {local.shape[0]} clips for {len(mine)} indices")
     return gather_latents(local, n_clips, group)
+
+
+def run_prior_sharded(n_clips: int, sample_clips: Callable[[Sequence[int]], torch.Tensor], group=None) -> torch.Tensor:
+    """Stage-1 prior, clip-sharded exactly like stage 2 (the reference spawns one process per GPU over a contiguous
+    clip range, ``stage1_batchtest_rcdms_model.py`` main): ``sample_clips(indices) -> (len(indices), frames, D)`` image
+    embeddings (``Seq_Inpaint_Prior_Pipeline`` per clip; inputs / generator seeded per CLIP index), then one all-gather.
+    ``gather_latents`` is shape-agnostic beyond the leading clip dimension."""
+    return run_sharded(n_clips, sample_clips, group)

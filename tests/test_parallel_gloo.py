@@ -48,3 +48,31 @@ def test_sharded_equals_single_process(tmp_path, n_clips):
 def test_gather_is_identity_without_process_group():
     x = torch.randn(3, 4, 5, 2, 2)
     assert gather_latents(x, 3) is x
+
+
+def _fake_prior_sample(indices):
+    # (clips, 5 frames, D) embeddings as a function of the clip index only, like a per-clip seeded generator would give
+    out = []
+    for i in indices:
+        g = torch.Generator().manual_seed(42 + i)
+        out.append(torch.randn((5, 16), generator=g))
+    return torch.stack(out) if out else torch.zeros((0, 5, 16))
+
+
+def _prior_worker(rank, world, port, n_clips, out_dir):
+    from rcdms_b200.parallel import run_prior_sharded
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        torch.save(run_prior_sharded(n_clips, _fake_prior_sample), os.path.join(out_dir, f"p{rank}.pt"))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_prior_sharded_equals_single_process(tmp_path):
+    world, n_clips = 2, 3
+    port = 29500 + (os.getpid() % 500) + 17
+    mp.spawn(_prior_worker, args=(world, port, n_clips, str(tmp_path)), nprocs=world, join=True)
+    ref = _fake_prior_sample(list(range(n_clips)))
+    for r in range(world):
+        assert torch.equal(torch.load(os.path.join(str(tmp_path), f"p{r}.pt")), ref)
