@@ -403,7 +403,6 @@ def run_prior(a):
     torch.cuda.synchronize()
     sampler = ClockSampler(0)
     sampler.start()
-    l0 = _lib.lib().rcdm_kernel_launches()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(a.steps):
@@ -411,10 +410,7 @@ def run_prior(a):
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / a.steps
-    launches = (_lib.lib().rcdm_kernel_launches() - l0)
-    # the library counts host-issued launches; with the CUDA graph a sampling run issues one step twice on the host
-    # (warm-up + capture) and replays it steps_n - 1 times on the device: scale to the launches the GPU executed
-    launches_total = launches if a.no_graph else launches / 2.0 * steps_n
+    launches_total = pipe.last_gpu_launches * a.steps  # graph replays included (counted by the pipeline)
     out_host = torch.empty(out.shape, dtype=out.dtype).pin_memory()
     e0.record()
     for _ in range(a.steps):

@@ -124,6 +124,23 @@ bool ln_run(int dt, const void* x, void* o, const float* gp, const float* bp, in
             const float* pep, int rows_per_frame, int frames, cudaStream_t s) {
   const int maxv = (C / 8 + 31) / 32;
   if (maxv > 8 || C % 8) return false;  // C <= 2048 (the stage-1 prior's width)
+  if (maxv > 5) {  // wide rows (the stage-1 prior, C = 2048): one CTA per row
+    static const bool wide_on = [] {
+      const char* e = getenv("RCDM_LN_WIDE");
+      return !(e && e[0] == '0');
+    }();
+    if (wide_on) {
+      if (dt == DT_F16)
+        launch_k(layernorm_wide_kernel<__half>, dim3(nrows), dim3(128), 0, s, reinterpret_cast<const __half*>(x),
+                 reinterpret_cast<__half*>(o), gp, bp, nrows, C, eps, pep, rows_per_frame, frames);
+      else
+        launch_k(layernorm_wide_kernel<__nv_bfloat16>, dim3(nrows), dim3(128), 0, s,
+                 reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<__nv_bfloat16*>(o), gp, bp, nrows, C, eps,
+                 pep, rows_per_frame, frames);
+      g_launches++;
+      return true;
+    }
+  }
   // rows per warp: keep ~8 16-byte loads in flight per lane
   const int rpw = maxv <= 1 ? 8 : maxv == 2 ? 4 : maxv <= 5 ? 2 : 1;
   const int warps = (nrows + rpw - 1) / rpw;

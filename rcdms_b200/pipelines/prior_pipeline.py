@@ -43,6 +43,7 @@ class Seq_Inpaint_Prior_Pipeline:
         self._num_timesteps = 0
         self.use_native_loop = True   # False -> python loop over prior()/scheduler.step() (same maths, for debugging)
         self.use_cuda_graph = True
+        self.last_gpu_launches = 0  # librcdm kernels executed by the last native sampling run (graph replays included)
         self._native_state = None   # persistent buffers + captured step graph of the last problem signature
 
     # ---- DiffusionPipeline-like plumbing ----------------------------------------------------------------------
@@ -192,6 +193,8 @@ class Seq_Inpaint_Prior_Pipeline:
                        noise):
         prior, sched = self.prior, self.scheduler
         prior._ensure_packed()
+        count = _lib.lib().rcdm_kernel_launches
+        c_begin = count()
         dev, dt = latents.device, latents.dtype
         F, D = latents.shape
         do_cfg = guidance_scale > 1
@@ -251,24 +254,35 @@ class Seq_Inpaint_Prior_Pipeline:
                                               st["coef"].data_ptr(), F * D, int(do_cfg), float(guidance_scale),
                                               step.data_ptr(), 1, _lib.current_stream_ptr()))
 
+        host_steps = 0  # times one_step() ran on the host in this call (each issues st["step_launches"] launches)
         if self.use_cuda_graph and n > 1:
             replays = n
             if st["graph"] is None:
                 s = torch.cuda.Stream(device=dev)
                 s.wait_stream(torch.cuda.current_stream(dev))
+                c0 = count()
                 with torch.cuda.stream(s):
                     one_step()  # warm-up outside capture: executes step 0 (lazy kernel attributes, allocator)
+                st["step_launches"] = int(count() - c0)
                 torch.cuda.current_stream(dev).wait_stream(s)
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g, stream=s):
                     one_step()  # capture only: nothing executes
                 st["graph"] = g
                 replays = n - 1
+                host_steps = 2
             for _ in range(replays):
                 st["graph"].replay()
         else:
-            for _ in range(n):
+            c0 = count()
+            one_step()
+            st["step_launches"] = int(count() - c0)
+            for _ in range(n - 1):
                 one_step()
+            host_steps = n
+        # kernels of this library the GPU executed for this clip: the prologue issued from the host + n steps
+        prologue = int(count() - c_begin) - host_steps * st["step_launches"]
+        self.last_gpu_launches = prologue + n * st["step_launches"]
         return lat.clone()
 
     @torch.no_grad()
