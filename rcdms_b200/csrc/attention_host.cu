@@ -177,21 +177,34 @@ void temporal_attn_launch(int dt, const void* qkv, void* out, int batch, int fra
     const char* e = getenv("RCDM_TEMPORAL_WIDE");
     return !(e && e[0] == '0');
   }();
-  if (wide_on && frames == 5 && (d == 64 || d == 128 || d == 256)) {
-    const int lph = d / 8;
+  // RCDM_TEMPORAL_WIDE_ALL=1: also for the UNet's head dims 40 / 80 / 160 (5 / 10 / 20 active lanes of 8 / 16 / 32)
+  static const bool wide_all = [] {
+    const char* e = getenv("RCDM_TEMPORAL_WIDE_ALL");
+    return e && e[0] == '1';
+  }();
+  const bool pow2 = d == 64 || d == 128 || d == 256;
+  const bool unet_d = d == 40 || d == 80 || d == 160;
+  if (wide_on && frames == 5 && (pow2 || (wide_all && unet_d))) {
+    const int lph = d <= 64 ? 8 : d <= 128 ? 16 : 32;
     const int wblocks = (int)((total * lph + 255) / 256);
-#define RCDM_TW(T, L)                                                                                      \
-  launch_k(temporal_attn_wide_kernel<T, 5, L>, dim3(wblocks), dim3(256), 0, s, reinterpret_cast<const T*>(qkv), \
+#define RCDM_TW(T, L, V)                                                                                      \
+  launch_k(temporal_attn_wide_kernel<T, 5, L, V>, dim3(wblocks), dim3(256), 0, s, reinterpret_cast<const T*>(qkv), \
            reinterpret_cast<T*>(out), batch, hw, heads, scale)
+#define RCDM_TWD(T)                                  \
+  switch (d) {                                       \
+    case 40: RCDM_TW(T, 8, 5); break;                \
+    case 64: RCDM_TW(T, 8, 8); break;                \
+    case 80: RCDM_TW(T, 16, 10); break;              \
+    case 128: RCDM_TW(T, 16, 16); break;             \
+    case 160: RCDM_TW(T, 32, 20); break;             \
+    default: RCDM_TW(T, 32, 32); break;              \
+  }
     if (dt == DT_F16) {
-      if (lph == 8) RCDM_TW(__half, 8);
-      else if (lph == 16) RCDM_TW(__half, 16);
-      else RCDM_TW(__half, 32);
+      RCDM_TWD(__half)
     } else {
-      if (lph == 8) RCDM_TW(__nv_bfloat16, 8);
-      else if (lph == 16) RCDM_TW(__nv_bfloat16, 16);
-      else RCDM_TW(__nv_bfloat16, 32);
+      RCDM_TWD(__nv_bfloat16)
     }
+#undef RCDM_TWD
 #undef RCDM_TW
     return;
   }

@@ -303,10 +303,12 @@ masked_attn_mma_kernel(const T* __restrict__ qkv, int ld, const float* __restric
 // frames (coalesced 16-byte global loads, no shared memory), the F x F partial scores are reduced across the slice
 // with shuffles, and every lane writes its 8 output channels of all F frames.  qkv [(b f hw), 3C] -> out [(b f hw), C].
 // ---------------------------------------------------------------------------------------------------------------
-template <typename T, int F, int LPH>
+// DV = active lanes of a slice = d / 8 (DV == LPH for power-of-two head dims; the UNet's d = 40 / 80 / 160 use
+// DV = 5 / 10 / 20 of LPH = 8 / 16 / 32 lanes, the idle lanes contribute zeros to the reductions).
+template <typename T, int F, int LPH, int DV = LPH>
 __global__ void __launch_bounds__(256)
 temporal_attn_wide_kernel(const T* __restrict__ qkv, T* __restrict__ out, int batch, int hw, int heads, float scale) {
-  constexpr int d = LPH * 8;
+  constexpr int d = DV * 8;
   const int C = heads * d, ld = 3 * C;
   const size_t slice = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) / LPH;  // (b, pix, head)
   const int sub = threadIdx.x % LPH;
@@ -319,13 +321,15 @@ temporal_attn_wide_kernel(const T* __restrict__ qkv, T* __restrict__ out, int ba
   const int pix = (int)(loc % hw);
   const int b = (int)(loc / hw);
   const size_t row0 = (size_t)b * F * hw + pix;
+  const bool lane_on = DV == LPH || sub < DV;
   float q[F][8], k[F][8], v[F][8];
 #pragma unroll
   for (int f = 0; f < F; ++f) {
     const T* p = qkv + (row0 + (size_t)f * hw) * ld + h * d + sub * 8;
-    unpack8<T>(__ldg(reinterpret_cast<const uint4*>(p)), q[f]);
-    unpack8<T>(__ldg(reinterpret_cast<const uint4*>(p + C)), k[f]);
-    unpack8<T>(__ldg(reinterpret_cast<const uint4*>(p + 2 * C)), v[f]);
+    const uint4 z = make_uint4(0, 0, 0, 0);
+    unpack8<T>(lane_on ? __ldg(reinterpret_cast<const uint4*>(p)) : z, q[f]);
+    unpack8<T>(lane_on ? __ldg(reinterpret_cast<const uint4*>(p + C)) : z, k[f]);
+    unpack8<T>(lane_on ? __ldg(reinterpret_cast<const uint4*>(p + 2 * C)) : z, v[f]);
   }
   float s[F][F];
 #pragma unroll
@@ -360,7 +364,7 @@ temporal_attn_wide_kernel(const T* __restrict__ qkv, T* __restrict__ out, int ba
 #pragma unroll
       for (int e = 0; e < 8; ++e) o8[e] = fmaf(pj, v[j][e], o8[e]);
     }
-    if (active)
+    if (active && lane_on)
       *reinterpret_cast<uint4*>(out + (row0 + (size_t)i * hw) * C + h * d + sub * 8) = pack8<T>(o8);
   }
 }
