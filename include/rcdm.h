@@ -1,4 +1,4 @@
-/* librcdm_b200 — C ABI of the B200-native RCDMs stage-2 denoise hot path.
+/* librcdm_b200 — C ABI of the B200-native RCDMs stage-2 denoise hot path (and of the stage-1 prior's kernels).
  *
  * The reference (muzishen/RCDMs) is pure Python and has no native boundary; these entry points are what a
  * maintainer binds (ctypes) behind the reference's own module API:
@@ -14,6 +14,11 @@
  *                        per-kernel entry points (the finest operator slot the reference defines is the
  *                        xformers attention hook, src/models/attention.py:153-156,244-251; rcdm_flash_attn sits
  *                        exactly there) so every kernel can be parity-tested and profiled alone.
+ *   rcdm_gemm_ex, rcdm_masked_attn, rcdm_prior_assemble, rcdm_unclip_cfg_step
+ *                        the stage-1 frame prior: MyPriorTransformer.forward
+ *                        src/models/myprior_transformer.py:275-411 and the sampling loop
+ *                        src/pipelines/prior_pipeline.py:299-343 are composed from these plus rcdm_layernorm /
+ *                        rcdm_temporal_attn by the Python host mirror (the reference's host side is Python too).
  *
  * Conventions: plain pointers and sizes only; every function returns 0 on success and a non-zero status on
  * failure (message via rcdm_last_error()); no C++ exception crosses the ABI.  All pointers named *_dev are
