@@ -127,3 +127,18 @@ def synthetic_prior_inputs(cfg: Dict, clip_index: int = 0, frames: int = 5, seed
     if steps > 0:
         out["noise"] = torch.randn((max(steps - 1, 1), frames, D), generator=g)
     return out
+
+
+def stack_prior_clips(clips) -> Dict[str, torch.Tensor]:
+    """Batch several clips' prior inputs (each as returned by ``synthetic_prior_inputs``) for ONE sampling run: the
+    classifier-free-guidance halves stay outermost — rows [negative clip 0..k | positive clip 0..k] — and every clip
+    keeps its 5 consecutive frame rows (the prior-state motion modules attend within groups of 5 rows)."""
+    f = clips[0]["latents"].shape[0]
+    out = dict(latents=torch.cat([c["latents"] for c in clips]),
+               imgs_proj_embeds1=torch.cat([c["imgs_proj_embeds1"] for c in clips]),
+               mask_label=torch.cat([c["mask_label"] for c in clips]))
+    for k in ("prompt_embeds", "text_hidden", "text_mask"):
+        out[k] = torch.cat([c[k][:f] for c in clips] + [c[k][f:] for c in clips])
+    if "noise" in clips[0]:
+        out["noise"] = torch.cat([c["noise"] for c in clips], dim=1)
+    return out

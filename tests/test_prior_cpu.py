@@ -299,3 +299,28 @@ def test_host_native_loop_orchestration_matches_oracle(fake_cabi, monkeypatch, g
     assert (mine - ref).abs().max().item() < 3e-2 * max(1.0, ref.abs().max().item())
     assert [c[0] for c in fake_cabi.calls].count("unclip") == steps
     assert torch.equal(h["latents"], inp["latents"].half())  # the caller's latents are not modified
+
+
+def test_batched_clips_equal_separate_runs(fake_cabi, monkeypatch):
+    """Several clips per sampling run (rows [neg clips | pos clips], 5 frame rows per clip): every clip's result equals
+    its stand-alone run — frames couple only within a clip, guidance pairs row i with row i + n."""
+    from rcdms_b200.synthetic import stack_prior_clips
+    cfg = prior_tiny_config(num_layers=1)
+    steps = 3
+    m, _ = _half_module(cfg)
+    pipe = Seq_Inpaint_Prior_Pipeline(prior=m, image_encoder=None, text_encoder=None, tokenizer=None,
+                                      scheduler=UnCLIPScheduler(**PRIOR_SCHEDULER_KWARGS))
+    pipe.use_cuda_graph = False
+    monkeypatch.setattr(pipe, "_native_ok", lambda latents, cb: True)
+    clips = [{k: (v.half() if v.is_floating_point() else v) for k, v in synthetic_prior_inputs(cfg, i, steps=steps).items()}
+             for i in range(3)]
+
+    def run(inp):
+        return pipe.sample(inp["latents"], inp["prompt_embeds"], inp["text_hidden"], inp["text_mask"],
+                           inp["imgs_proj_embeds1"], inp["mask_label"], steps, 4.0, noise=inp["noise"])
+
+    alone = [run(c) for c in clips]
+    both = run(stack_prior_clips(clips))
+    assert both.shape == (15, cfg["embedding_dim"])
+    for i, a in enumerate(alone):
+        assert torch.equal(both[5 * i: 5 * i + 5], a), i

@@ -361,3 +361,27 @@ def test_prior_generator_draws_match_reference_order():
     b = pipe.sample(dev["latents"], dev["prompt_embeds"], dev["text_hidden"], dev["text_mask"], dev["imgs_proj_embeds1"],
                     dev["mask_label"], steps, 4.0, noise=noise)
     assert torch.equal(a, b)
+
+
+def test_prior_batched_clips_match_separate_runs():
+    """Two clips in one sampling run (rows [neg clips | pos clips]) vs. each clip alone: identical up to the GEMM's
+    tile-schedule dependent summation order (different M), i.e. far inside the half-precision noise floor."""
+    from rcdms_b200.synthetic import stack_prior_clips
+    cfg = prior_tiny_config()
+    m, _ = _build(cfg, torch.float16)
+    pipe = Seq_Inpaint_Prior_Pipeline(prior=m, image_encoder=None, text_encoder=None, tokenizer=None,
+                                      scheduler=UnCLIPScheduler(**PRIOR_SCHEDULER_KWARGS))
+    steps = 4
+    clips = [{k: (v.cuda().half() if v.is_floating_point() else v.cuda())
+              for k, v in synthetic_prior_inputs(cfg, i, steps=steps).items()} for i in range(2)]
+
+    def run(inp):
+        return pipe.sample(inp["latents"], inp["prompt_embeds"], inp["text_hidden"], inp["text_mask"],
+                           inp["imgs_proj_embeds1"], inp["mask_label"], steps, 4.0, noise=inp["noise"])
+
+    alone = [run(c) for c in clips]
+    both = run(stack_prior_clips(clips))
+    assert both.shape == (10, cfg["embedding_dim"])
+    for i, a in enumerate(alone):
+        d = (both[5 * i: 5 * i + 5].float() - a.float()).abs().max().item()
+        assert d <= 2e-2 * max(1.0, a.float().abs().max().item()), (i, d)
