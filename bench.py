@@ -44,6 +44,10 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-profile", action="store_true")
     ap.add_argument("--cpu-budget-s", type=float, default=150.0)
+    ap.add_argument("--eager-gpu-baseline", action="store_true",
+                    help="also time the oracle restatement in torch eager (bench dtype) on this GPU: the stand-in for "
+                         "'the reference modules in eager fp16 on the B200' (SURVEY 8d); reported, never a product path")
+    ap.add_argument("--eager-gpu-only", action="store_true", help="run only the eager-GPU baseline leg and exit")
     ap.add_argument("--workload", default="stage2", choices=["stage2", "prior"],
                     help="stage2 (default, the headline metric) | prior: BASELINE config 4, the stage-1 frame-prior loop "
                          "(SURVEY 8f rank 1), single GPU")
@@ -306,6 +310,40 @@ def run_ours(a):
                             sample=f"1 of {a.ddim_steps} DDIM steps (UNet fp32 forward at {a.latent}x{a.latent} latents + "
                                    f"CFG + DDIM) of one clip, {t_step:.1f} s, extrapolated x{a.ddim_steps}")
 
+    eager_gpu = None
+    if a.eager_gpu_baseline and rank == 0 and world == 1:
+        # "the reference modules in PyTorch eager fp16 on the B200" — the reference itself cannot travel
+        # to the GPU box, so the oracle restatement (same torch op sequence, one launch per op, scores materialised)
+        # runs in the bench dtype on this GPU: a reported baseline like cpu_baseline, never a product path.
+        from oracle.loop_ref import make_scheduler
+        from oracle.unet_ref import unet_forward
+        from rcdms_b200.synthetic import synthetic_clip_inputs, synthetic_state_dict
+        from rcdms_b200.unet_spec import full_config
+        ecfg = full_config()
+        esd = {k: v.to("cuda", dtype) for k, v in synthetic_state_dict(ecfg, seed=0).items()}
+        ein = {k: v.to("cuda", dtype) for k, v in synthetic_clip_inputs(0, a.latent, a.latent, a.ctx_len).items()}
+        sch = make_scheduler()
+        sch.set_timesteps(a.ddim_steps)
+        lat = ein["latents"]
+        m2, l2 = torch.cat([ein["mask"]] * 2), torch.cat([ein["masked_latents"]] * 2)
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n_e = 3
+        with torch.no_grad():
+            for i, t in enumerate(sch.timesteps[: n_e + 1]):
+                if i == 1:
+                    ev0.record()
+                x = torch.cat([torch.cat([lat] * 2), m2, l2], dim=1)
+                eps = unet_forward(esd, ecfg, x, t, ein["ctx"])
+                eu, ec = eps.chunk(2)
+                lat = sch.step(eu + a.guidance * (ec - eu), t, lat, eta=0.0).prev_sample
+            ev1.record()
+        torch.cuda.synchronize()
+        ms_e = ev0.elapsed_time(ev1) / n_e
+        eager_gpu = dict(value=5.0 / (ms_e * a.ddim_steps / 1e3), unit="frames/s", ms_per_ddim_step=ms_e, kind="port",
+                         sample=f"{n_e} of {a.ddim_steps} DDIM steps of one clip after 1 warm-up step, oracle restatement "
+                                f"in torch eager {a.dtype} on this GPU, extrapolated")
+        del esd
+
     if rank == 0:
         h2d = sum(v.numel() * v.element_size() for v in host.values())
         d2h = out_host.numel() * out_host.element_size()
@@ -322,6 +360,8 @@ def run_ours(a):
                     e2e=dict(value=e2e_value, unit="frames/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
                              ms_per_step=ms_e2e / a.steps, api="RCDMsPipeline.denoise (host pinned tensors in, host latents out)"),
                     gpu_launches=int(launches), clocks=clocks, roofline=roofline, cpu_baseline=cpu_baseline)
+        if eager_gpu is not None:
+            line["gpu_eager_baseline"] = eager_gpu
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -451,9 +491,60 @@ def run_prior(a):
         cpu_baseline=cb)), flush=True)
 
 
+def run_eager_gpu_only(a):
+    """--eager-gpu-only: just the eager-GPU baseline leg (random weights drawn on the device: timing only)."""
+    import torch
+    from oracle.loop_ref import make_scheduler
+    from oracle.unet_ref import unet_forward
+    from rcdms_b200.synthetic import synthetic_clip_inputs
+    from rcdms_b200.unet_spec import BUFFER_SUFFIX, full_config, state_dict_spec
+    dtype = torch.float16 if a.dtype == "fp16" else torch.bfloat16
+    cfg = full_config()
+    g = torch.Generator(device="cuda").manual_seed(0)
+    sd = {}
+    for name, shape in state_dict_spec(cfg):
+        if name.endswith(BUFFER_SUFFIX):
+            from rcdms_b200.synthetic import positional_encoding
+            sd[name] = positional_encoding(shape[1], shape[2]).to("cuda", dtype)
+            continue
+        fan_in = 1
+        for d_ in shape[1:]:
+            fan_in *= d_
+        w = torch.randn(shape, generator=g, device="cuda") * (max(fan_in, 1) ** -0.5 if name.endswith("weight") and
+                                                             len(shape) > 1 else 0.02)
+        if len(shape) == 1 and name.endswith("weight"):
+            w = 1 + w
+        sd[name] = w.to(dtype)
+    ein = {k: v.to("cuda", dtype) for k, v in synthetic_clip_inputs(0, a.latent, a.latent, a.ctx_len).items()}
+    sch = make_scheduler()
+    sch.set_timesteps(a.ddim_steps)
+    lat = ein["latents"]
+    m2, l2 = torch.cat([ein["mask"]] * 2), torch.cat([ein["masked_latents"]] * 2)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n_e = max(1, a.steps)
+    with torch.no_grad():
+        for i, t in enumerate(sch.timesteps[: n_e + 1]):
+            if i == 1:
+                ev0.record()
+            x = torch.cat([torch.cat([lat] * 2), m2, l2], dim=1)
+            eps = unet_forward(sd, cfg, x, t, ein["ctx"])
+            eu, ec = eps.chunk(2)
+            lat = sch.step(eu + a.guidance * (ec - eu), t, lat, eta=0.0).prev_sample
+        ev1.record()
+    torch.cuda.synchronize()
+    ms_e = ev0.elapsed_time(ev1) / n_e
+    print(json.dumps(dict(metric=METRIC, gpu_eager_baseline=dict(
+        value=5.0 / (ms_e * a.ddim_steps / 1e3), unit="frames/s", ms_per_ddim_step=ms_e, kind="port", dtype=a.dtype,
+        finite=bool(torch.isfinite(lat).all()),
+        sample=f"{n_e} of {a.ddim_steps} DDIM steps of one clip after 1 warm-up step; oracle restatement of the reference "
+               f"UNet + CFG + DDIM in torch eager on this GPU (random weights), extrapolated x{a.ddim_steps}"))), flush=True)
+
+
 def main():
     a = parse()
-    if a.workload == "prior":
+    if a.eager_gpu_only:
+        run_eager_gpu_only(a)
+    elif a.workload == "prior":
         run_prior(a)
     elif a.impl == "reference":
         run_reference(a)
