@@ -491,6 +491,53 @@ def run_prior(a):
         cpu_baseline=cb)), flush=True)
 
 
+def run_eager_gpu_only_prior(a):
+    """--eager-gpu-only --workload prior: oracle restatement of the prior loop in torch eager on this GPU."""
+    import torch
+    from oracle.prior_ref import make_prior_scheduler, prior_forward
+    from rcdms_b200.prior_spec import prior_full_config, prior_state_dict_spec
+    from rcdms_b200.synthetic import positional_encoding, synthetic_prior_inputs
+    dtype = torch.float16 if a.dtype == "fp16" else torch.bfloat16
+    cfg = prior_full_config()
+    g = torch.Generator(device="cuda").manual_seed(0)
+    sd = {}
+    for name, shape in prior_state_dict_spec(cfg):
+        if name.endswith("pos_encoder.pe"):
+            sd[name] = positional_encoding(shape[1], shape[2]).to("cuda", dtype)
+            continue
+        is_norm = any(k in "." + name for k in (".norm", "norms.", "ff_norm", "prior_norm"))
+        if is_norm:
+            sd[name] = (torch.ones(shape, device="cuda") if name.endswith("weight") else torch.zeros(shape, device="cuda")).to(dtype)
+            continue
+        fan_in = shape[1] if (len(shape) == 2 and name.endswith("weight")) else 256
+        sd[name] = ((torch.rand(shape, generator=g, device="cuda") * 2 - 1) * fan_in ** -0.5).to(dtype)
+    inp = {k: (v.to("cuda", dtype) if v.is_floating_point() else v.cuda()) for k, v in synthetic_prior_inputs(cfg, 0).items()}
+    sch = make_prior_scheduler()
+    sch.set_timesteps(a.prior_steps)
+    ts = sch.timesteps
+    lat = inp["latents"]
+    p1, ml = torch.cat([inp["imgs_proj_embeds1"]] * 2), torch.cat([inp["mask_label"]] * 2)
+    gen = torch.Generator(device="cuda").manual_seed(1)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n_e = max(1, a.steps)
+    with torch.no_grad():
+        for i in range(n_e + 1):
+            if i == 1:
+                ev0.record()
+            pred = prior_forward(sd, cfg, torch.cat([lat] * 2), ts[i], inp["prompt_embeds"], inp["text_hidden"], p1, ml,
+                                 inp["text_mask"])
+            pu, pt = pred.chunk(2)
+            lat = sch.step(pu + 4.0 * (pt - pu), timestep=ts[i], sample=lat, generator=gen, prev_timestep=ts[i + 1]).prev_sample
+        ev1.record()
+    torch.cuda.synchronize()
+    ms_e = ev0.elapsed_time(ev1) / n_e
+    print(json.dumps(dict(metric=PRIOR_METRIC, gpu_eager_baseline=dict(
+        value=5.0 / (ms_e * a.prior_steps / 1e3), unit="frame-embeddings/s", ms_per_unclip_step=ms_e, kind="port",
+        dtype=a.dtype, finite=bool(torch.isfinite(lat).all()),
+        sample=f"{n_e} of {a.prior_steps} UnCLIP steps of one clip after 1 warm-up step; oracle restatement of "
+               f"MyPriorTransformer + CFG + UnCLIP in torch eager on this GPU (random weights), extrapolated"))), flush=True)
+
+
 def run_eager_gpu_only(a):
     """--eager-gpu-only: just the eager-GPU baseline leg (random weights drawn on the device: timing only)."""
     import torch
@@ -543,7 +590,7 @@ def run_eager_gpu_only(a):
 def main():
     a = parse()
     if a.eager_gpu_only:
-        run_eager_gpu_only(a)
+        (run_eager_gpu_only_prior if a.workload == "prior" else run_eager_gpu_only)(a)
     elif a.workload == "prior":
         run_prior(a)
     elif a.impl == "reference":
