@@ -84,6 +84,11 @@ RCDM_API int rcdm_set_stream_k_min(int k_blocks);       /* tuning knob: minimum 
                                                            stream-K decomposition is used; 0 disables it; returns the previous value */
 RCDM_API int rcdm_set_gemm_pair(int on);                /* tuning knob: use the CTA-pair (tcgen05 cta_group::2, 256-row tile) GEMM kernel
                                                            (default 1); returns the previous value */
+/* debug / experiment switches.  The library reads NO environment variables; every switch has a compiled-in default (the
+ * measured-best setting).  name: "pdl", "sk_min", "gemm_pair", "masked_attn_mma", "attn_v", "temporal_wide",
+ * "temporal_wide_all", "temporal_tiled", "temporal_smem_kb", "gn_fused", "ln_wide", "gn_stats".  Returns the previous
+ * value, -1 for an unknown name. */
+RCDM_API int rcdm_debug_set_option(const char* name, int value);
 RCDM_API uint64_t rcdm_kernel_launches(void);          /* kernels launched by this library since load (bench evidence) */
 
 /* ---- model life cycle (host only until the first weight arrives) ---- */
@@ -96,6 +101,10 @@ RCDM_API int rcdm_unet_weight_info(const rcdm_unet* h, int index, char* name_buf
 /* copy + repack one state-dict entry (contiguous, reference layout, dtype RCDM_DT_*) into the kernel layout */
 RCDM_API int rcdm_unet_load_weight(rcdm_unet* h, const char* name, const void* data_dev, int dtype, const int64_t* dims,
                           int ndim, void* stream);
+/* the same for `count` entries at once - ONE packing launch for a whole load_state_dict (stage2_batchtest_rcdms_model.py:243);
+ * dims: count x 4 int64 (unused trailing dims ignored), ndims: count ints.  Nothing is loaded if any entry is rejected. */
+RCDM_API int rcdm_unet_load_weights(rcdm_unet* h, int count, const char* const* names, const void* const* data_dev,
+                                    const int* dtypes, const int64_t* dims, const int* ndims, void* stream);
 RCDM_API int rcdm_unet_weights_missing(const rcdm_unet* h); /* entries not loaded yet (0 => ready) */
 
 /* ---- forward: sample (b, in_ch, f, h, w) NCFHW, ctx (b*f, L, cross_dim), out (b, out_ch, f, h, w) ---- */
@@ -120,6 +129,10 @@ RCDM_API int rcdm_unet_profile(rcdm_unet* h, const void* sample_dev, int sample_
 RCDM_API int64_t rcdm_unet_read_tap(rcdm_unet* h, const char* name, float* out_dev, int64_t capacity, int* rows, int* channels,
                            void* stream);
 RCDM_API int rcdm_unet_enable_taps(rcdm_unet* h, int enable); /* keep tapped activations alive (costs memory) */
+/* per-handle debug switches, effective from the next rcdm_unet_prepare: "simple" (1: every GEMM / attention through the
+ * CUDA-core reference kernels, for bisecting a parity failure; never benchmarked), "ln_fold" (0: separate LayerNorm
+ * kernels), "autotune" (1: plan-time tile selection). */
+RCDM_API int rcdm_unet_set_option(rcdm_unet* h, const char* name, int value);
 
 /* ---- fused CFG + DDIM step (+ next 9-channel UNet input).  All tensors NCFHW.  eta = 0. ----
  * eps (2B|B, 4, f, h, w); latents_f32 (B,4,f,h,w) fp32 master copy updated in place; latents_out optional copy in

@@ -17,14 +17,44 @@ import sys
 import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-REF = os.environ.get("RCDMS_REFERENCE", "/root/reference")
+
+
+def reference_root() -> str:
+    """Where the unmodified reference lives: RCDMS_REFERENCE, else a driver-installed baseline/_ref, else /root/reference."""
+    for cand in (os.environ.get("RCDMS_REFERENCE"), os.path.join(ROOT, "baseline", "_ref"), "/root/reference"):
+        if cand and os.path.isfile(os.path.join(cand, "src", "models", "unet.py")):
+            return cand
+    raise RuntimeError("reference checkout not found (set RCDMS_REFERENCE)")
+
+
+def load_reference_module(name: str):
+    """Import ``<reference>/src/models/<name>.py`` UNCHANGED under the private package ``_rcdms_reference.models``.
+
+    The repo ships its own ``src/`` import shim (the drop-in boundary), so a plain ``from src.models.unet import ...``
+    can resolve to the product instead of the reference depending on ``sys.path`` order and on what is cached in
+    ``sys.modules``.  A private package name cannot be shadowed; the reference's files use relative imports only
+    (``from .unet_blocks import ...``), so they load unchanged.  The result is asserted to come from the reference tree."""
+    import importlib
+    import inspect
+    import types
+    ref = reference_root()
+    shim = os.path.join(ROOT, "oracle", "diffusers_shim")
+    if shim not in sys.path:
+        sys.path.insert(0, shim)
+    for pkg, sub in (("_rcdms_reference", "src"), ("_rcdms_reference.models", os.path.join("src", "models"))):
+        if pkg not in sys.modules:
+            m = types.ModuleType(pkg)
+            m.__path__ = [os.path.join(ref, sub)]
+            sys.modules[pkg] = m
+    mod = importlib.import_module(f"_rcdms_reference.models.{name}")
+    src = os.path.realpath(inspect.getsourcefile(mod))
+    if not src.startswith(os.path.realpath(ref) + os.sep):
+        raise RuntimeError(f"golden recipe imported {src}, not the reference under {ref}")
+    return mod
 
 
 def load_reference_unet(cfg):
-    sys.path.insert(0, os.path.join(ROOT, "oracle", "diffusers_shim"))
-    sys.path.insert(0, REF)
-    sys.path.insert(0, ROOT)
-    from src.models.unet import UNet3DConditionModel  # the reference's class, unmodified
+    UNet3DConditionModel = load_reference_module("unet").UNet3DConditionModel  # the reference's class, unmodified
     init = {k: (list(v) if isinstance(v, tuple) else v) for k, v in cfg.items()}
     return UNet3DConditionModel.from_config(init)
 
@@ -37,10 +67,7 @@ def golden_inputs(cfg, b, f, h, w, L, seed):
 
 
 def load_reference_prior(cfg):
-    sys.path.insert(0, ROOT)
-    sys.path.insert(0, REF)
-    sys.path.insert(0, os.path.join(ROOT, "oracle", "diffusers_shim"))
-    from src.models.myprior_transformer import MyPriorTransformer  # the reference's class, unmodified
+    MyPriorTransformer = load_reference_module("myprior_transformer").MyPriorTransformer  # unmodified reference class
     init = {k: (list(v) if isinstance(v, tuple) else v) for k, v in cfg.items()}
     return MyPriorTransformer.from_config(init)
 

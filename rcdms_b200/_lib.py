@@ -40,6 +40,7 @@ SIGNATURES = {
     "rcdm_last_error": (C.c_char_p, []),
     "rcdm_device_count": (_I, []),
     "rcdm_kernel_launches": (C.c_uint64, []),
+    "rcdm_debug_set_option": (_I, [C.c_char_p, _I]),
     "rcdm_set_stream_k_min": (_I, [_I]),
     "rcdm_set_gemm_pair": (_I, [_I]),
     "rcdm_unet_create": (_I, [C.POINTER(UNetConfig), C.POINTER(_P)]),
@@ -47,6 +48,8 @@ SIGNATURES = {
     "rcdm_unet_num_weights": (_I, [_P]),
     "rcdm_unet_weight_info": (_I, [_P, _I, C.c_char_p, _I, C.POINTER(_I64), C.POINTER(_I)]),
     "rcdm_unet_load_weight": (_I, [_P, C.c_char_p, _P, _I, C.POINTER(_I64), _I, _P]),
+    "rcdm_unet_load_weights": (_I, [_P, _I, C.POINTER(C.c_char_p), C.POINTER(_P), C.POINTER(_I), C.POINTER(_I64),
+                                    C.POINTER(_I), _P]),
     "rcdm_unet_weights_missing": (_I, [_P]),
     "rcdm_unet_prepare": (_I, [_P, _I, _I, _I, _I, _I]),
     "rcdm_unet_workspace_bytes": (C.c_size_t, [_P]),
@@ -55,6 +58,7 @@ SIGNATURES = {
                                C.c_char_p, C.POINTER(_I), C.POINTER(_I), _P]),
     "rcdm_unet_read_tap": (_I64, [_P, C.c_char_p, _P, _I64, C.POINTER(_I), C.POINTER(_I), _P]),
     "rcdm_unet_enable_taps": (_I, [_P, _I]),
+    "rcdm_unet_set_option": (_I, [_P, C.c_char_p, _I]),
     "rcdm_ddim_cfg_step": (_I, [_P, _I, _P, _P, _I, _P, _I, _P, _I, _P, _I, _I, _I, _I, _I, _I, _F, _F, _F, _P]),
     "rcdm_denoise_loop": (_I, [_P, _P, _I, _P, _I, _P, _I, _P, _I, _I, _I, _I, _I, _I, C.POINTER(_I64),
                                C.POINTER(_F), C.POINTER(_F), _I, _F, _I, _P, _P]),

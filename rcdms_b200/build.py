@@ -22,6 +22,10 @@ SOURCES = ["gemm_host.cu", "attention_host.cu", "norm_host.cu", "unet.cu", "api.
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--use_fast_math",
               "-diag-suppress", "177"]
+# IEEE arithmetic (no --use_fast_math) for the translation units that hold the scheduler-step kernels, whose results
+# are specified bit for bit against torch's op sequence (ddim_cfg_step_kernel, unclip_cfg_step_kernel), and the
+# timestep sinusoid (sinf / cosf of arguments up to ~1000 rad).  Their hot loops use explicit intrinsics where wanted.
+IEEE_SOURCES = {"api.cu", "unet.cu"}
 
 
 def _nvcc() -> str:
@@ -38,7 +42,7 @@ def _digest() -> str:
             if f.endswith((".cu", ".cuh", ".h")):
                 h.update(f.encode())
                 h.update(open(os.path.join(root, f), "rb").read())
-    h.update(" ".join(NVCC_FLAGS).encode())
+    h.update(" ".join(NVCC_FLAGS + sorted(IEEE_SOURCES)).encode())
     return h.hexdigest()
 
 
@@ -56,7 +60,8 @@ def build(force: bool = False, verbose: bool = True) -> str:
 
     def compile_one(src: str) -> str:
         obj = os.path.join(OUT_DIR, src.replace(".cu", ".o"))
-        cmd = [nvcc, *NVCC_FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
+        flags = [f for f in NVCC_FLAGS if not (src in IEEE_SOURCES and f == "--use_fast_math")]
+        cmd = [nvcc, *flags, "-c", os.path.join(CSRC, src), "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"nvcc failed for {src}:\n{r.stdout}\n{r.stderr}")

@@ -70,6 +70,14 @@ int rcdm_device_count(void) {
   return n;
 }
 uint64_t rcdm_kernel_launches(void) { return g_launches.load(); }
+int rcdm_debug_set_option(const char* name, int value) {
+  int prev = 0;
+  if (opt_set(name, value, &prev)) {
+    set_err(std::string("rcdm_debug_set_option: unknown option ") + (name ? name : "(null)"));
+    return -1;
+  }
+  return prev;
+}
 int rcdm_set_stream_k_min(int k_blocks) { return gemm_set_sk_min(k_blocks); }
 int rcdm_set_gemm_pair(int on) { return gemm_set_pair(on); }
 
@@ -105,6 +113,12 @@ int rcdm_unet_load_weight(rcdm_unet* h, const char* name, const void* data_dev, 
   return unet_load_weight(h, name, data_dev, dtype, dims, ndim, stream);
   API_END
 }
+int rcdm_unet_load_weights(rcdm_unet* h, int count, const char* const* names, const void* const* data_dev,
+                           const int* dtypes, const int64_t* dims, const int* ndims, void* stream) {
+  API_BEGIN
+  return unet_load_weights(h, count, names, data_dev, dtypes, dims, ndims, stream);
+  API_END
+}
 int rcdm_unet_weights_missing(const rcdm_unet* h) {
   if (!h) return -1;
   int n = 0;
@@ -117,6 +131,17 @@ int rcdm_unet_prepare(rcdm_unet* h, int batch, int frames, int height, int width
   API_END
 }
 size_t rcdm_unet_workspace_bytes(const rcdm_unet* h) { return h ? h->ws_bytes : 0; }
+int rcdm_unet_set_option(rcdm_unet* h, const char* name, int value) {
+  if (!h || !name) return set_err("null argument");
+  int* field = !strcmp(name, "simple") ? &h->simple : !strcmp(name, "autotune") ? &h->autotune :
+               !strcmp(name, "ln_fold") ? &h->ln_fold : nullptr;
+  if (!field) return set_err(std::string("rcdm_unet_set_option: unknown option ") + name);
+  if (*field != value) {
+    *field = value;
+    h->planned = false;  // force a re-plan
+  }
+  return 0;
+}
 int rcdm_unet_enable_taps(rcdm_unet* h, int enable) {
   if (!h) return set_err("null handle");
   if (h->taps_enabled != (enable != 0)) {
@@ -450,6 +475,7 @@ int rcdm_gemm(int dtype, const void* a_dev, const void* w_dev, const float* bias
   } else {
     GemmLaunch l;
     std::string e;
+    d.sk = sk_workspace_for_stream(st, &e);
     if (!gemm_prepare(d, &l, &e)) return set_err(e);
     gemm_launch(l, st);
   }
@@ -494,6 +520,7 @@ int rcdm_gemm_ex(int dtype, const void* a_dev, int lda, const void* w_dev, const
   } else {
     GemmLaunch l;
     std::string e;
+    d.sk = sk_workspace_for_stream(st, &e);
     if (!gemm_prepare(d, &l, &e)) return set_err(e);
     gemm_launch(l, st);
   }
@@ -516,10 +543,7 @@ int rcdm_masked_attn(int dtype, const void* qkv_dev, int ld, const float* key_bi
   if (smem > 200 * 1024) return set_err("rcdm_masked_attn: S * d too large for shared memory");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   // the prior's shape (d = 64, <= 112 tokens): tensor-core kernel, whole key range in registers
-  static const bool mma_on = [] {
-    const char* e = getenv("RCDM_MASKED_ATTN_MMA");
-    return !(e && e[0] == '0');
-  }();
+  const bool mma_on = opt(OPT_MASKED_ATTN_MMA) != 0;
   if (mma_on && d == MATTN_D && S <= MATTN_NT * 8 && ld % 2 == 0) {
     const float sc = 1.0f / sqrtf((float)d);
     if (dtype == DT_F16)
@@ -636,6 +660,7 @@ int rcdm_gemm_rowstats(int dtype, const void* a_dev, const void* w_dev, const fl
   if (parts_out) *parts_out = gemm_stats_parts(N);
   GemmLaunch l;
   std::string e;
+  d.sk = sk_workspace_for_stream(reinterpret_cast<cudaStream_t>(stream), &e);
   if (!gemm_prepare(d, &l, &e)) return set_err(e);
   gemm_launch(l, reinterpret_cast<cudaStream_t>(stream));
   g_launches++;
@@ -699,6 +724,7 @@ int rcdm_linear_ln(int dtype, const void* x_dev, const void* w_dev, const float*
   d.ln_eps = eps;
   GemmLaunch l;
   std::string e;
+  d.sk = sk_workspace_for_stream(st, &e);
   if (!gemm_prepare(d, &l, &e)) return set_err(e);
   gemm_launch(l, st);
   g_launches += 3;
@@ -773,6 +799,7 @@ int rcdm_conv3x3(int dtype, const void* x_dev, const void* w_packed_dev, const f
   } else {
     GemmLaunch l;
     std::string e;
+    d.sk = sk_workspace_for_stream(st, &e);
     if (!gemm_prepare(d, &l, &e)) return set_err(e);
     gemm_launch(l, st);
   }

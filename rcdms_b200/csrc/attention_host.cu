@@ -47,13 +47,7 @@ bool attn_prepare(const AttnDesc& d, AttnLaunch* l, std::string* err) {
   return true;
 }
 
-static int attn_version() {  // RCDM_ATTN_V = 3: previous generation (double-buffered S in TMEM); default 4
-  static const int v = [] {
-    const char* e = getenv("RCDM_ATTN_V");
-    return e ? atoi(e) : 4;
-  }();
-  return v;
-}
+static int attn_version() { return opt(OPT_ATTN_V); }  // 3: previous generation (double-buffered S in TMEM); default 4
 template <typename T, int DPAD> static void launch_one(const AttnLaunch& l, cudaStream_t s) {
   if (attn_version() == 3)
     launch_k(flash_attn_kernel<T, DPAD>, l.grid, dim3(160), AttnCfg<DPAD>::SMEM_BYTES, s, l.maps, l.p);
@@ -96,7 +90,7 @@ template <typename T> static cudaError_t set_attr_dt() {
   return e;
 }
 bool attn_setup_attributes(std::string* err) {
-  cudaError_t e = pdl_upload_mode(pdl_mode() == 2);
+  cudaError_t e = cudaSuccess;
   if (e == cudaSuccess) e = set_attr_dt<__half>();
   if (e == cudaSuccess) e = set_attr_dt<__nv_bfloat16>();
   if (e != cudaSuccess) {
@@ -173,16 +167,10 @@ void temporal_attn_launch(int dt, const void* qkv, void* out, int batch, int fra
   const int blocks = (int)((total + 127) / 128);
   const float scale = 1.0f / sqrtf((float)d);
   // wide heads (the stage-1 prior's motion modules, d = 256): d / 8 lanes per (location, head), shuffle-reduced scores
-  static const bool wide_on = [] {
-    const char* e = getenv("RCDM_TEMPORAL_WIDE");
-    return !(e && e[0] == '0');
-  }();
+  const bool wide_on = opt(OPT_TEMPORAL_WIDE) != 0;
   // also for the UNet's head dims 40 / 80 / 160 (5 / 10 / 20 active lanes of 8 / 16 / 32): measured 0.894 -> 0.784 ms
-  // per UNet forward against the tiled shared-memory kernel (2.1 -> 2.4 TB/s); RCDM_TEMPORAL_WIDE_ALL=0 restores it
-  static const bool wide_all = [] {
-    const char* e = getenv("RCDM_TEMPORAL_WIDE_ALL");
-    return !(e && e[0] == '0');
-  }();
+  // per UNet forward against the tiled shared-memory kernel (2.1 -> 2.4 TB/s); OPT_TEMPORAL_WIDE_ALL = 0 restores it
+  const bool wide_all = opt(OPT_TEMPORAL_WIDE_ALL) != 0;
   const bool pow2 = d == 64 || d == 128 || d == 256;
   const bool unet_d = d == 40 || d == 80 || d == 160;
   if (wide_on && frames == 5 && (pow2 || (wide_all && unet_d))) {
@@ -211,15 +199,11 @@ void temporal_attn_launch(int dt, const void* qkv, void* out, int batch, int fra
   }
   // tiled kernel (coalesced through shared memory): PT = pixels per CTA, a power of two dividing hw with
   // <= 80 KB of shared memory and <= 512 threads; the one-thread-per-(pixel, head) kernel is the fallback
-  static const bool tiled_on = [] {
-    const char* e = getenv("RCDM_TEMPORAL_TILED");
-    return !(e && e[0] == '0');
-  }();
+  const bool tiled_on = opt(OPT_TEMPORAL_TILED) != 0;
   int PT = 0;
   if (tiled_on && frames >= 1 && frames <= 5) {
     // small tiles: load / compute / store phases of a CTA do not overlap, so several CTAs per SM must
-    const char* kb = getenv("RCDM_TEMPORAL_SMEM_KB");
-    const size_t budget = (size_t)(kb ? atoi(kb) : 40) * 1024;
+    const size_t budget = (size_t)opt(OPT_TEMPORAL_SMEM_KB) * 1024;
     const size_t per_pixel = (size_t)frames * 3 * heads * d * 2;
     for (int cand = 32; cand >= 1; cand >>= 1)
       if (hw % cand == 0 && (cand * per_pixel <= budget || cand == 1) && cand * per_pixel <= 100 * 1024 &&

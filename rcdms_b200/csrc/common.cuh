@@ -109,20 +109,13 @@ __device__ __forceinline__ bool elect_one() {
 // its memory is visible; it must precede the first global-memory access.  pdl_trigger() lets the successor start
 // its own prologue.  Both are no-ops for a kernel launched without the attribute.
 // ------------------------------------------------------------------------------------------
-// c_pdl_early (per translation unit, uploaded by pdl_upload_mode): 1 = trigger the successor before waiting.
-static __constant__ int c_pdl_early;
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+// (triggering BEFORE the wait was measured too: no better inside the CUDA-graph replay, so only this order is kept)
 __device__ __forceinline__ void pdl_sync() {
-  if (c_pdl_early) {
-    pdl_trigger();
-    pdl_wait();
-  } else {
-    pdl_wait();
-    pdl_trigger();
-  }
+  pdl_wait();
+  pdl_trigger();
 }
-static inline cudaError_t pdl_upload_mode(int early) { return cudaMemcpyToSymbol(c_pdl_early, &early, sizeof(int)); }
 
 // ------------------------------------------------------------------------------------------
 // mbarrier

@@ -251,6 +251,47 @@ static __global__ void pack_vec_kernel(const void* __restrict__ src, int src_dt,
   dst[row] = accumulate ? dst[row] + v : v;
 }
 
+// Whole-state-dict packing in ONE launch: a device table of jobs (one per state-dict entry), each owning a contiguous
+// range of CTAs; a CTA finds its job by binary search over the ranges' first block index.
+struct PackJob {
+  const void* src;
+  void* dst;       // T* (matrix / conv kinds) or float* (vector kind)
+  int src_dt;
+  int kind;        // 0 matrix [N,K], 1 conv3x3 [N,Cin,3,3] -> tap-major, 2 fp32 vector [N]
+  int N, K, ldd, col_off, row_off, Cin, geglu_bn;
+  int block0;      // first CTA of this job
+  int nblocks;
+};
+template <typename T>
+__global__ void pack_many_kernel(const PackJob* __restrict__ jobs, int njobs) {
+  int lo = 0, hi = njobs - 1;
+  while (lo < hi) {  // last job with block0 <= blockIdx.x
+    const int mid = (lo + hi + 1) >> 1;
+    if (jobs[mid].block0 <= (int)blockIdx.x) lo = mid;
+    else hi = mid - 1;
+  }
+  const PackJob j = jobs[lo];
+  const size_t total = (size_t)j.N * (j.kind == 2 ? 1 : j.K);
+  const size_t stride = (size_t)j.nblocks * blockDim.x;
+  for (size_t idx = (size_t)(blockIdx.x - j.block0) * blockDim.x + threadIdx.x; idx < total; idx += stride) {
+    const float v = load_any(j.src, j.src_dt, idx);
+    if (j.kind == 2) {
+      const int row = (j.geglu_bn > 0 ? geglu_row((int)idx, j.N, j.geglu_bn) : (int)idx) + j.row_off;
+      reinterpret_cast<float*>(j.dst)[row] = v;
+    } else {
+      const int n = (int)(idx / j.K);
+      const int k = (int)(idx % j.K);
+      int kk = k;
+      if (j.kind == 1) {  // src k = c*9 + tap
+        const int c = k / 9, tap = k % 9;
+        kk = tap * j.Cin + c;
+      }
+      const int row = (j.geglu_bn > 0 ? geglu_row(n, j.N, j.geglu_bn) : n) + j.row_off;
+      reinterpret_cast<T*>(j.dst)[(size_t)row * j.ldd + j.col_off + kk] = DT<T>::from_f(v);
+    }
+  }
+}
+
 // LayerNorm fold (see GemmParams): one warp per weight row n.
 //   wf[n,k] = W[n,k] * gamma[k] - mean_k(W[n,:] * gamma)   (rounded to T; centred rows absorb the "- mean * u" term)
 //   c[f][n] = sum_k (beta[k] + pe[f][k]) * W[n,k] + bias[n]        (pe / bias optional; frames >= 1)

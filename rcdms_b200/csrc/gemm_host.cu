@@ -3,7 +3,10 @@
 // failures (RCDM_SIMPLE=1); it is never the benchmarked path.
 #include <cudaTypedefs.h>
 
+#include <atomic>
 #include <cmath>
+#include <cstring>
+#include <map>
 #include <mutex>
 
 #include "launch.h"
@@ -69,13 +72,22 @@ bool encode_tmap(CUtensorMap* out, const void* base, int rank, const uint64_t* d
 // ------------------------------------------------------------------------------------------
 // GEMM prepare / launch
 // ------------------------------------------------------------------------------------------
-int pdl_mode() {
-  static const int mode = [] {
-    const char* e = getenv("RCDM_PDL");
-    return e ? atoi(e) : 0;
-  }();
-  return mode;
+static std::atomic<int> g_opts[OPT_COUNT] = {{0}, {24}, {1}, {1}, {4}, {1}, {1}, {1}, {40}, {1}, {1}, {1}};
+static const char* const g_opt_names[OPT_COUNT] = {"pdl", "sk_min", "gemm_pair", "masked_attn_mma", "attn_v",
+                                                    "temporal_wide", "temporal_wide_all", "temporal_tiled",
+                                                    "temporal_smem_kb", "gn_fused", "ln_wide", "gn_stats"};
+int opt(int id) { return g_opts[id].load(std::memory_order_relaxed); }
+int opt_set(const char* name, int value, int* previous) {
+  for (int i = 0; i < OPT_COUNT; ++i)
+    if (name && !strcmp(name, g_opt_names[i])) {
+      const int prev = g_opts[i].exchange(value);
+      if (previous) *previous = prev;
+      return 0;
+    }
+  return 1;
 }
+
+int pdl_mode() { return opt(OPT_PDL); }
 bool pdl_enabled() { return pdl_mode() > 0; }
 
 static bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
@@ -91,50 +103,54 @@ int num_sms() {
   return n;
 }
 
-// ---- stream-K workspace: one fp32 partial tile + one flag per CTA; process-wide (one device, one stream at a time)
-static float* g_sk_ws = nullptr;
-static unsigned* g_sk_flags = nullptr;
-static int g_sk_slots = 0;
-static int g_sk_min = -1;
-static int sk_min_saving() {  // k-blocks a launch must save before stream-K pays for its fix-up traffic
-  if (g_sk_min < 0) {
-    const char* e = getenv("RCDM_SK_MIN");
-    g_sk_min = e ? atoi(e) : 24;
-  }
-  return g_sk_min;
-}
-int gemm_set_sk_min(int k_blocks) {
-  const int prev = sk_min_saving();
-  g_sk_min = k_blocks < 0 ? 0 : k_blocks;
-  return prev;
-}
-static int g_pair = -1;
-static int pair_enabled() {
-  if (g_pair < 0) {
-    const char* e = getenv("RCDM_GEMM_PAIR");
-    g_pair = e ? atoi(e) : 1;
-  }
-  return g_pair;
-}
-int gemm_set_pair(int on) {
-  const int prev = pair_enabled();
-  g_pair = on < 0 ? 0 : on;
-  return prev;
-}
-static bool sk_alloc(std::string* err) {
-  if (g_sk_ws) return true;
+// ---- stream-K workspace: one fp32 partial tile + one arrival flag per CTA.  A workspace belongs to ONE stream of work
+// at a time (two stream-K GEMMs overlapping on the same slots would consume each other's partials), so it is owned by
+// whoever serialises the launches: a UNet handle (its plan runs on one stream at a time), or - for the stand-alone
+// entry points - the (device, stream) pair the launch goes to.
+bool sk_workspace_alloc(SkWorkspace* w, std::string* err) {
+  if (w->ws) return true;
   const int slots = num_sms();
-  cudaError_t e = cudaMalloc(&g_sk_ws, (size_t)slots * 128 * 160 * sizeof(float));
-  if (e == cudaSuccess) e = cudaMalloc(&g_sk_flags, (size_t)slots * sizeof(unsigned));
-  if (e == cudaSuccess) e = cudaMemset(g_sk_flags, 0, (size_t)slots * sizeof(unsigned));
+  cudaError_t e = cudaGetDevice(&w->device);
+  if (e == cudaSuccess) e = cudaMalloc(&w->ws, (size_t)slots * 128 * 160 * sizeof(float));
+  if (e == cudaSuccess) e = cudaMalloc(&w->flags, (size_t)slots * sizeof(unsigned));
+  if (e == cudaSuccess) e = cudaMemset(w->flags, 0, (size_t)slots * sizeof(unsigned));
   if (e != cudaSuccess) {
     if (err) *err = std::string("stream-K workspace: ") + cudaGetErrorString(e);
+    sk_workspace_free(w);
     return false;
   }
-  g_sk_slots = slots;
+  w->slots = slots;
   return true;
 }
-
+void sk_workspace_free(SkWorkspace* w) {
+  if (w->ws) cudaFree(w->ws);
+  if (w->flags) cudaFree(w->flags);
+  w->ws = nullptr;
+  w->flags = nullptr;
+  w->slots = 0;
+}
+const SkWorkspace* sk_workspace_for_stream(cudaStream_t s, std::string* err) {
+  static std::mutex mu;
+  static std::map<std::pair<int, cudaStream_t>, SkWorkspace> by_stream;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+  std::lock_guard<std::mutex> lk(mu);
+  SkWorkspace& w = by_stream[{dev, s}];
+  if (!sk_workspace_alloc(&w, err)) return nullptr;
+  return &w;
+}
+static int sk_min_saving() { return opt(OPT_SK_MIN); }  // k-blocks a launch must save before stream-K pays for its fix-up
+int gemm_set_sk_min(int k_blocks) {
+  int prev = 0;
+  opt_set("sk_min", k_blocks < 0 ? 0 : k_blocks, &prev);
+  return prev;
+}
+static int pair_enabled() { return opt(OPT_GEMM_PAIR); }
+int gemm_set_pair(int on) {
+  int prev = 0;
+  opt_set("gemm_pair", on < 0 ? 0 : on, &prev);
+  return prev;
+}
 int gemm_stats_parts(int N) {  // one part per epilogue column group per N tile of the (heuristic) tile width
   const int bn = (N % 160 == 0) ? 160 : (N <= 64 ? 64 : 128);
   return RCDM_EPI_GROUPS * ((N + bn - 1) / bn);
@@ -253,7 +269,7 @@ bool gemm_prepare(const GemmDesc& d, GemmLaunch* l, std::string* err) {
   const int m_tiles = has_conv ? ((d.NI + p.tn - 1) / p.tn) * p.tiles_y * p.tiles_x : (d.M + 127) / 128;
   // CTA pairs (cta_group::2, 256-row tiles): measured on B200 to pay (3-9 %) only for deep-K, many-tile problems
   // (the big 3x3 convolutions); small-K GEMMs are bound by their epilogue / L2 traffic and lose a little.
-  // RCDM_GEMM_PAIR = 0 never, 1 heuristic (default), 2 whenever there are >= 2 M tiles.
+  // OPT_GEMM_PAIR = 0 never, 1 heuristic (default), 2 whenever there are >= 2 M tiles.
   const int pair_mode = pair_enabled();
   l->pair = (!d.no_pair && !d.act && num_sms() >= 2 &&  // activation epilogues exist for the single-CTA kernel only
              ((d.force_pair && m_tiles >= 2) || (pair_mode == 2 && m_tiles >= 2) ||
@@ -296,13 +312,13 @@ bool gemm_prepare(const GemmDesc& d, GemmLaunch* l, std::string* err) {
   p.sk = 0;
   const bool vec_ok = p.epi_tma != 0;
   const int min_saving = sk_min_saving();
-  if (min_saving > 0 && vec_ok && !d.no_sk && g_sk_ws && sms * cta_per_worker <= g_sk_slots && tiles % sms != 0) {
+  if (min_saving > 0 && vec_ok && !d.no_sk && d.sk && d.sk->ws && sms * cta_per_worker <= d.sk->slots && tiles % sms != 0) {
     const double waves = (double)tiles / sms;
     const double saving_kb = (std::ceil(waves) - waves) * p.num_kb;
     if (saving_kb >= min_saving && (long long)tiles * p.num_kb >= 4LL * sms) {
       p.sk = 1;
-      p.sk_ws = g_sk_ws;
-      p.sk_flags = g_sk_flags;
+      p.sk_ws = d.sk->ws;
+      p.sk_flags = d.sk->flags;
       l->grid = dim3(sms * cta_per_worker, 1, 1);
     }
   }
@@ -362,8 +378,7 @@ template <typename T, int BN> static cudaError_t set_attr() {
 }
 
 bool gemm_setup_attributes(std::string* err) {
-  if (!sk_alloc(err)) return false;
-  cudaError_t e = pdl_upload_mode(pdl_mode() == 2);
+  cudaError_t e = cudaSuccess;
   if (e == cudaSuccess) e = set_attr<__half, 64>();
   if (e == cudaSuccess) e = set_attr<__half, 128>();
   if (e == cudaSuccess) e = set_attr<__half, 160>();

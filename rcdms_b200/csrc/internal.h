@@ -16,6 +16,8 @@ int unet_create(const rcdm_unet_config* cfg, rcdm_unet** out);
 void unet_destroy(rcdm_unet* h);
 int unet_load_weight(rcdm_unet* h, const char* name, const void* data, int dtype, const int64_t* dims, int ndim,
                      void* stream);
+int unet_load_weights(rcdm_unet* h, int count, const char* const* names, const void* const* data, const int* dtypes,
+                      const int64_t* dims, const int* ndims, void* stream);
 int unet_prepare(rcdm_unet* h, int batch, int frames, int height, int width, int ctx_len);
 int unet_run(rcdm_unet* h, bool run_ctx, bool run_step, cudaStream_t st);
 

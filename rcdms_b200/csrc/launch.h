@@ -12,8 +12,30 @@
 
 namespace rcdm {
 
-// ---- kernel launch with programmatic stream serialization (PDL); RCDM_PDL=0 in the environment disables it ----
-bool pdl_enabled();  // RCDM_PDL = 0 (off, default: measured slower inside CUDA graphs) | 1 (wait, then trigger) | 2 (trigger, then wait)
+// ---- debug / experiment switches -------------------------------------------------------------------------------
+// The product library reads NO environment variables: every switch has a compiled-in default (the measured-best
+// setting) and can only be changed explicitly through the ABI (rcdm_debug_set_option), which tests and the profiling
+// scripts use to bisect a parity failure or to reproduce a rejected variant.
+enum Opt : int {
+  OPT_PDL = 0,            // 0 off (default: measured slower inside CUDA graphs) | 1 programmatic dependent launch
+  OPT_SK_MIN,             // k-blocks a launch must save before stream-K is used (default 24; 0 = never)
+  OPT_GEMM_PAIR,          // 0 never | 1 heuristic (default) | 2 whenever there are >= 2 M tiles
+  OPT_MASKED_ATTN_MMA,    // stage-1 prior: tensor-core masked attention (default 1)
+  OPT_ATTN_V,             // 4 (default) | 3: previous flash-attention generation (double-buffered S in TMEM)
+  OPT_TEMPORAL_WIDE,      // warp-slice temporal attention for d = 64/128/256 (default 1)
+  OPT_TEMPORAL_WIDE_ALL,  // ... also for the UNet's d = 40/80/160 (default 1)
+  OPT_TEMPORAL_TILED,     // tiled shared-memory temporal attention for the remaining head dims (default 1)
+  OPT_TEMPORAL_SMEM_KB,   // its shared-memory budget per CTA (default 40)
+  OPT_GN_FUSED,           // single-launch GroupNorm with a grid barrier (default 1; 0 = two-kernel path)
+  OPT_LN_WIDE,            // CTA-per-row LayerNorm for rows wider than 1280 (default 1)
+  OPT_GN_STATS,           // GroupNorm statistics from the producing GEMM's epilogue + streaming apply (default 1)
+  OPT_COUNT
+};
+int opt(int id);
+int opt_set(const char* name, int value, int* previous);  // 0 = ok, 1 = unknown name
+
+// ---- kernel launch with programmatic stream serialization (PDL); off by default (OPT_PDL) ----
+bool pdl_enabled();
 int pdl_mode();
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
@@ -43,6 +65,18 @@ struct ASeg {
   int ld;           // plain: row pitch in elements
   int H, W, NI;     // conv: INPUT spatial dims and image count
 };
+// stream-K partial-tile workspace (gemm_host.cu): owned by whoever serialises the launches that use it
+struct SkWorkspace {
+  float* ws = nullptr;        // [slots][128 * 160] fp32
+  unsigned* flags = nullptr;  // [slots], zero at rest
+  int slots = 0;
+  int device = -1;
+};
+bool sk_workspace_alloc(SkWorkspace* w, std::string* err);  // on the current device; no-op when already allocated
+void sk_workspace_free(SkWorkspace* w);
+// per-(device, stream) workspace for the stand-alone entry points (lives for the process)
+const SkWorkspace* sk_workspace_for_stream(cudaStream_t s, std::string* err);
+
 struct GemmDesc {
   int dt;  // DT_F16 / DT_BF16
   int M, N;
@@ -60,6 +94,7 @@ struct GemmDesc {
   int act;       // 1 = erf GELU, 2 = SiLU on (acc + bias), before the residual add
   int force_bn;  // 0 = heuristic
   int no_sk;     // 1 = never use the stream-K decomposition for this launch
+  const SkWorkspace* sk;  // stream-K workspace of the launching stream / handle; nullptr = no stream-K
   int no_pair;   // 1 = never use the CTA-pair (cta_group::2) kernel for this launch
   int force_pair;  // 1 = always use it (when there are >= 2 M tiles); set by the plan-time autotuner
   // folded LayerNorm (see GemmParams): producer side / consumer side

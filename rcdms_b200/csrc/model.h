@@ -108,6 +108,8 @@ struct rcdm_unet_impl {
   size_t arena_bytes = 0;
   unsigned char* arena = nullptr;
   bool dirty = true;  // derived vectors need (re)finalising
+  unsigned char* pack_jobs = nullptr;  // device table of rcdm_unet_load_weights
+  size_t pack_jobs_bytes = 0;
   Mat conv_in_w, l1w, l2w, temb_all, conv_out_w;
   Vec conv_in_b, l1b, l2b, temb_static_b, bias_eff_all, c1b_all, tb_all, cno_g, cno_b, conv_out_b;
   int conv_in_kpad = 0, temb_dim = 0, temb_rows = 0;
@@ -123,12 +125,13 @@ struct rcdm_unet_impl {
   size_t ws_bytes = 0;
   std::vector<Op> ctx_ops, step_ops;
   std::vector<OpMeta> step_meta;
+  SkWorkspace sk;  // stream-K partial tiles of this handle's GEMMs (never shared with another handle / stream)
   bool taps_enabled = false;
   std::map<std::string, TapInfo> taps;
   int simple = 0;
-  int autotune = 0;  // RCDM_AUTOTUNE=1: plan-time choice of the GEMM tile width / CTA pairing per distinct problem
+  int autotune = 0;  // rcdm_unet_set_option("autotune", 1): plan-time choice of the GEMM tile width / CTA pairing per distinct problem
   std::map<std::string, std::pair<int, int>> tune_cache;  // problem signature -> (tile width, pair)
-  int ln_fold = 1;  // LayerNorm folded into the consuming GEMM (RCDM_LN_FOLD=0: separate layernorm kernels)
+  int ln_fold = 1;  // LayerNorm folded into the consuming GEMM (rcdm_unet_set_option("ln_fold", 0): separate layernorm kernels)
   // per-call inputs (read by the recorded ops)
   const void* cur_sample = nullptr;
   int cur_sample_dt = 0;

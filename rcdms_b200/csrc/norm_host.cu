@@ -56,10 +56,7 @@ void gn_configure(GnLaunch* l, int dt, const void* x0, int C0, const void* x1, i
   l->dt = dt;
   l->rows_per_cta_2k = a.rows_per_cta;
   // ---- fused single-launch path
-  static const bool fused_on = [] {
-    const char* e = getenv("RCDM_GN_FUSED");
-    return !(e && e[0] == '0');
-  }();
+  const bool fused_on = opt(OPT_GN_FUSED) != 0;
   l->fused = 0;
   if (fused_on && vecs <= 512 && a.nstat <= 8192 && groups <= 64) {
     const int sms = num_sms();
@@ -89,7 +86,7 @@ void gn_configure(GnLaunch* l, int dt, const void* x0, int C0, const void* x1, i
 }
 
 bool gn_setup_attributes(std::string* err) {
-  cudaError_t e = pdl_upload_mode(pdl_mode() == 2);
+  cudaError_t e = cudaSuccess;
   if (e == cudaSuccess)
     e = cudaFuncSetAttribute(gn_fused_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 1024);
   if (e == cudaSuccess)
@@ -125,10 +122,7 @@ bool ln_run(int dt, const void* x, void* o, const float* gp, const float* bp, in
   const int maxv = (C / 8 + 31) / 32;
   if (maxv > 8 || C % 8) return false;  // C <= 2048 (the stage-1 prior's width)
   if (maxv > 5) {  // wide rows (the stage-1 prior, C = 2048): one CTA per row
-    static const bool wide_on = [] {
-      const char* e = getenv("RCDM_LN_WIDE");
-      return !(e && e[0] == '0');
-    }();
+    const bool wide_on = opt(OPT_LN_WIDE) != 0;
     if (wide_on) {
       if (dt == DT_F16)
         launch_k(layernorm_wide_kernel<__half>, dim3(nrows), dim3(128), 0, s, reinterpret_cast<const __half*>(x),

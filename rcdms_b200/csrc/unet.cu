@@ -512,6 +512,7 @@ struct Planner {
     }
     GemmLaunch l;
     std::string e;
+    d.sk = &h->sk;  // the handle's own stream-K workspace: its plan runs on one stream at a time
     if (h->autotune) tune(d);
     if (!gemm_prepare(d, &l, &e)) return fail(e);
     push([l](cudaStream_t s) {
@@ -1135,12 +1136,8 @@ int unet_create(const rcdm_unet_config* cfg, rcdm_unet** out) {
   if (!cfg || !out) return set_err("null argument");
   rcdm_unet* h = new rcdm_unet();
   h->cfg = *cfg;
-  const char* env = getenv("RCDM_SIMPLE");
-  h->simple = env && env[0] == '1';
-  const char* at = getenv("RCDM_AUTOTUNE");
-  h->autotune = at && at[0] == '1';  // measured: no gain over the heuristics at the 512x512 shapes => opt-in
-  const char* lf = getenv("RCDM_LN_FOLD");
-  h->ln_fold = !(lf && lf[0] == '0');
+  // debug switches (rcdm_unet_set_option before rcdm_unet_prepare): simple = 0, autotune = 0 (measured: no gain over the
+  // heuristics at the 512x512 shapes), ln_fold = 1
   if (build_model(h)) {
     delete h;
     return 1;
@@ -1170,6 +1167,8 @@ void unet_destroy(rcdm_unet* h) {
   if (!h) return;
   release_plan(h);
   if (h->arena) cudaFree(h->arena);
+  sk_workspace_free(&h->sk);
+  if (h->pack_jobs) cudaFree(h->pack_jobs);
   if (h->loop_buf) cudaFree(h->loop_buf);
   if (h->loop_stream) cudaStreamDestroy(h->loop_stream);
   if (h->ev_in) cudaEventDestroy(h->ev_in);
@@ -1188,6 +1187,7 @@ static int ensure_arena(rcdm_unet_impl* h) {
   CUDA_OK(cudaMemset(h->arena, 0, h->arena_bytes));
   std::string e;
   if (!gemm_setup_attributes(&e) || !attn_setup_attributes(&e) || !gn_setup_attributes(&e)) return set_err(e);
+  if (!sk_workspace_alloc(&h->sk, &e)) return set_err(e);
   return 0;
 }
 
@@ -1211,6 +1211,83 @@ int unet_load_weight(rcdm_unet* h, const char* name, const void* data, int dtype
   else pack_dispatch<__nv_bfloat16>(h, s, data, dtype, st);
   CUDA_OK(cudaGetLastError());
   s.loaded = true;
+  h->dirty = true;
+  return 0;
+}
+
+// The whole state dict in one launch (a model load used to be 1 286 one-tensor launches).
+int unet_load_weights(rcdm_unet* h, int count, const char* const* names, const void* const* data, const int* dtypes,
+                      const int64_t* dims, const int* ndims, void* stream) {
+  if (!h || !names || !data || !dtypes || !dims || !ndims || count < 0) return set_err("null argument");
+  std::vector<PackJob> jobs;
+  std::vector<int> touched;
+  jobs.reserve(count);
+  long long block = 0;
+  for (int i = 0; i < count; ++i) {
+    if (!names[i] || !data[i]) return set_err("null state-dict entry");
+    auto it = h->slot_index.find(names[i]);
+    if (it == h->slot_index.end()) return set_err(std::string("unexpected key in state_dict: ") + names[i]);
+    const Slot& s = h->slots[it->second];
+    if (ndims[i] != s.ndim) return set_err(std::string("size mismatch for ") + names[i]);
+    for (int k = 0; k < s.ndim; ++k)
+      if (dims[(size_t)i * 4 + k] != s.dims[k]) return set_err(std::string("size mismatch for ") + names[i]);
+    if (dtypes[i] < 0 || dtypes[i] > 2) return set_err("bad dtype");
+    touched.push_back(it->second);
+    if (s.kind == SLOT_IGNORE) continue;
+    PackJob j;
+    memset(&j, 0, sizeof j);
+    j.src = data[i];
+    j.src_dt = dtypes[i];
+    j.N = (int)s.dims[0];
+    j.K = 1;
+    for (int k = 1; k < s.ndim; ++k) j.K *= (int)s.dims[k];
+    if (s.kind == SLOT_VEC) {
+      j.N *= j.K;
+      j.K = 1;
+      j.kind = 2;
+    } else {
+      j.kind = s.kind == SLOT_CONV3 ? 1 : 0;
+    }
+    j.ldd = s.ldd;
+    j.col_off = s.col_off;
+    j.row_off = s.row_off;
+    j.Cin = s.cin;
+    j.geglu_bn = s.geglu_bn;
+    j.dst = nullptr;  // resolved below (the arena may not exist yet)
+    const size_t total = (size_t)j.N * j.K;
+    size_t nb = (total + 256 * 16 - 1) / (256 * 16);
+    j.nblocks = (int)(nb < 1 ? 1 : nb > 4096 ? 4096 : nb);
+    j.block0 = (int)block;
+    block += j.nblocks;
+    jobs.push_back(j);
+  }
+  if (ensure_arena(h)) return 1;
+  {
+    size_t ji = 0;
+    for (int i = 0; i < count; ++i) {
+      const Slot& s = h->slots[touched[i]];
+      if (s.kind == SLOT_IGNORE) continue;
+      jobs[ji++].dst = h->arena + s.dst;
+    }
+  }
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (!jobs.empty()) {
+    const size_t bytes = jobs.size() * sizeof(PackJob);
+    if (h->pack_jobs_bytes < bytes) {
+      if (h->pack_jobs) CUDA_OK(cudaFree(h->pack_jobs));
+      h->pack_jobs = nullptr;
+      CUDA_OK(cudaMalloc(&h->pack_jobs, bytes));
+      h->pack_jobs_bytes = bytes;
+    }
+    // pageable source: the copy is staged before the call returns, so the host vector may go out of scope
+    CUDA_OK(cudaMemcpyAsync(h->pack_jobs, jobs.data(), bytes, cudaMemcpyHostToDevice, st));
+    const PackJob* jd = reinterpret_cast<const PackJob*>(h->pack_jobs);
+    if (h->dt == DT_F16) pack_many_kernel<__half><<<(unsigned)block, 256, 0, st>>>(jd, (int)jobs.size());
+    else pack_many_kernel<__nv_bfloat16><<<(unsigned)block, 256, 0, st>>>(jd, (int)jobs.size());
+    g_launches++;
+    CUDA_OK(cudaGetLastError());
+  }
+  for (int idx : touched) h->slots[idx].loaded = true;
   h->dirty = true;
   return 0;
 }

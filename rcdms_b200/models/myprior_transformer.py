@@ -263,9 +263,11 @@ class MyPriorTransformer(nn.Module):
         return self._plans[key]
 
     # ---- single-kernel launches ----------------------------------------------------------------------------------
+    debug_simple = False  # explicit debug switch: CUDA-core reference GEMM (same C entry point) for every Linear
+
     @property
-    def _simple(self) -> bool:  # debug switch: CUDA-core reference GEMM (same C entry point) for every Linear
-        return os.environ.get("RCDM_PRIOR_SIMPLE", "0") not in ("", "0")
+    def _simple(self) -> bool:
+        return bool(self.debug_simple)
 
     def _gemm(self, a: torch.Tensor, l: _Lin, out: torch.Tensor, res: Optional[torch.Tensor] = None, flags: int = 0,
               M: Optional[int] = None, lda: Optional[int] = None, a_off: int = 0) -> torch.Tensor:

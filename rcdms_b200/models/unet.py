@@ -108,6 +108,7 @@ class UNet3DConditionModel(nn.Module):
         for name, shape in self._spec:
             self._register(name, shape)
         self._handle = None       # native handle (created lazily, per compute dtype)
+        self._debug_options = {}  # explicit per-handle debug switches (rcdm_unet_set_option); empty = product defaults
         self._handle_dtype = None
         self._bound_versions = None
         self._planned = None
@@ -193,21 +194,39 @@ class UNet3DConditionModel(nn.Module):
             cc = _c_config(self.config, dt)
             _lib.check(L.rcdm_unet_create(_lib.C.byref(cc), _lib.C.byref(h)))
             self._handle, self._handle_dtype, self._bound_versions, self._planned = h, dt, None, None
+            for k, v in self._debug_options.items():
+                _lib.check(L.rcdm_unet_set_option(h, k.encode(), int(v)))
         versions = self._versions()
         if versions != self._bound_versions:
             stream = _lib.current_stream_ptr()
-            dims_t = _lib.C.c_int64 * 4
-            keep = []
+            items, keep = [], []
             for name, t in self.state_dict(keep_vars=True).items():
                 t = t.detach()
                 if not t.is_contiguous():
                     t = t.contiguous()
                     keep.append(t)
-                dims = dims_t(*(list(t.shape) + [0] * (4 - t.dim())))
-                _lib.check(L.rcdm_unet_load_weight(self._handle, name.encode(), t.data_ptr(),
-                                                   _lib.torch_dtype_id(t.dtype), dims, t.dim(), stream))
+                items.append((name, t))
+            n, Cc = len(items), _lib.C
+            names = (Cc.c_char_p * n)(*[k.encode() for k, _ in items])
+            ptrs = (Cc.c_void_p * n)(*[t.data_ptr() for _, t in items])
+            dts = (Cc.c_int * n)(*[_lib.torch_dtype_id(t.dtype) for _, t in items])
+            nds = (Cc.c_int * n)(*[t.dim() for _, t in items])
+            dims = (Cc.c_int64 * (4 * n))()
+            for i, (_, t) in enumerate(items):
+                for k, d in enumerate(t.shape):
+                    dims[4 * i + k] = d
+            # the whole state dict in ONE packing launch
+            _lib.check(L.rcdm_unet_load_weights(self._handle, n, names, ptrs, dts, dims, nds, stream))
             torch.cuda.current_stream().synchronize()
             self._bound_versions = versions
+
+    def set_debug_option(self, name: str, value: int) -> None:
+        """Explicit debug switch of the native handle ("simple": CUDA-core reference kernels for bisecting a parity
+        failure; "ln_fold"; "autotune").  Never set on a product path; the library reads no environment variables."""
+        self._debug_options[name] = int(value)
+        if self._handle is not None:
+            _lib.check(_lib.lib().rcdm_unet_set_option(self._handle, name.encode(), int(value)))
+            self._planned = None
 
     def _release(self) -> None:
         if getattr(self, "_handle", None) is not None:

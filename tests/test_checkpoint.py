@@ -81,3 +81,41 @@ def test_flat_file_round_trip(tmp_path, dtype):
     assert all(torch.equal(v, ref[k]) for k, v in unet.state_dict().items())
     with pytest.raises(ValueError):
         ck.load_flat(path)
+
+
+@pytest.mark.gpu
+def test_checkpoint_to_forward_on_gpu(tmp_path):
+    """A split DeepSpeed ``["module"]`` file (and its offline flat-file conversion) loaded through
+    ``load_stage2_checkpoint`` must reproduce the forward of the directly loaded model bit for bit on the device
+    (``stage2_batchtest_rcdms_model.py:225-243`` then ``RCDMs_pipeline.py:488``)."""
+    cfg = tiny_config()
+    path, lm, gm, unet_sd = _deepspeed_file(tmp_path, cfg)
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn((2, cfg["in_channels"], 5, 16, 16), generator=g).cuda().half()
+    ctx = torch.randn((10, 7, cfg["cross_attention_dim"]), generator=g).cuda().half()
+
+    def forward(m):
+        m = m.to(device="cuda", dtype=torch.float16)
+        return m(x, 501, encoder_hidden_states=ctx, return_dict=False)[0]
+
+    direct = UNet3DConditionModel.from_config(cfg)
+    direct.load_state_dict(unet_sd, strict=True)
+    y_direct = forward(direct)
+    assert torch.isfinite(y_direct).all() and y_direct.abs().mean().item() > 1e-3
+
+    from_ds = UNet3DConditionModel.from_config(cfg)
+    lm2 = local_feature(text_dim=96, vis_dim=16, hidden_dim=96, num_heads=8)
+    gm2 = local_feature(text_dim=96, vis_dim=12, hidden_dim=96, num_heads=8)
+    assert ck.load_stage2_checkpoint(path, from_ds, lm2, gm2) == ["stray.key"]
+    assert torch.equal(forward(from_ds), y_direct)
+
+    flat = str(tmp_path / "stage2.rcdmflat")
+    ck.convert_stage2_checkpoint(path, flat, torch.float16)
+    from_flat = UNet3DConditionModel.from_config(cfg)
+    ck.load_stage2_checkpoint(flat, from_flat, local_feature(96, 16, 96, 8), local_feature(96, 12, 96, 8))
+    assert torch.equal(forward(from_flat), y_direct)
+
+    # a checkpoint with different weights must give a different output (the loader is not a no-op)
+    other = UNet3DConditionModel.from_config(cfg)
+    other.load_state_dict(synthetic_state_dict(cfg, seed=4), strict=True)
+    assert not torch.equal(forward(other), y_direct)

@@ -15,9 +15,9 @@ from rcdms_b200.unet_spec import RCDMS_SCHEDULER_KWARGS, tiny_config
 pytestmark = pytest.mark.gpu
 
 
-def _pipe(dtype=torch.float16):
-    cfg = tiny_config()
-    unet = uc.build_model(cfg, dtype)
+def _pipe(dtype=torch.float16, cfg=None, sd=None):
+    cfg = cfg or tiny_config()
+    unet = uc.build_model(cfg, dtype, sd)
     torch.manual_seed(0)
     D = cfg["cross_attention_dim"]
     lm = local_feature(D, 16, D, 8).to("cuda", dtype)
@@ -27,8 +27,8 @@ def _pipe(dtype=torch.float16):
     return cfg, pipe
 
 
-def _inputs(cfg, clips, h, dtype):
-    ins = [synthetic_clip_inputs(k, h, h, ctx_len=7, ctx_dim=cfg["cross_attention_dim"]) for k in range(clips)]
+def _inputs(cfg, clips, h, dtype, ctx_len=7):
+    ins = [synthetic_clip_inputs(k, h, h, ctx_len=ctx_len, ctx_dim=cfg["cross_attention_dim"]) for k in range(clips)]
     lat = torch.cat([i["latents"] for i in ins]).to("cuda", dtype)
     ml = torch.cat([i["masked_latents"] for i in ins]).to("cuda", dtype)
     mask = torch.cat([i["mask"] for i in ins]).to("cuda", dtype)
@@ -67,6 +67,36 @@ def test_native_loop_matches_python_loop_and_oracle(clips, steps):
     assert torch.isfinite(nat).all()
     assert diff.max().item() < 1e-2 * ref.abs().max().item(), (diff.max().item(), ref.abs().max().item())
     assert diff.mean().item() < 2e-3 * ref.pow(2).mean().sqrt().item(), (diff.mean().item(), ref.pow(2).mean().sqrt().item())
+
+
+def test_native_loop_at_the_benchmarked_shape():
+    """BASELINE config 2's loop (full-width UNet, 64x64 latents, L = 85, fp16, CFG 2.0), shortened to 5 DDIM steps:
+    graph replay == eager launches == python loop bitwise, and all of them track the fp32 oracle loop."""
+    from rcdms_b200.unet_spec import full_config
+    dtype, steps = torch.float16, 5
+    cfg = full_config()
+    sd32 = synthetic_state_dict(cfg, seed=0)
+    _, pipe = _pipe(dtype, cfg, sd32)
+    ins, lat, ml, mask, ctx = _inputs(cfg, 1, 64, dtype, ctx_len=85)
+    m2, ml2 = torch.cat([mask] * 2), torch.cat([ml] * 2)
+    nat = pipe.denoise(lat, m2, ml2, ctx, steps, 2.0)
+    assert torch.equal(nat, pipe.denoise(lat, m2, ml2, ctx, steps, 2.0)), "graph replay must be deterministic"
+    pipe.use_cuda_graph = False
+    assert torch.equal(nat, pipe.denoise(lat, m2, ml2, ctx, steps, 2.0)), "graph and eager launches must agree bitwise"
+    pipe.use_native_loop = False
+    py = pipe.denoise(lat, m2, ml2, ctx, steps, 2.0)
+    assert torch.equal(nat, py), f"native vs python loop: {(nat.float() - py.float()).abs().max().item()}"
+    sd = {k: v.half().float().cuda() for k, v in sd32.items()}
+    with torch.no_grad():
+        ref = denoise_loop(lambda x, t, cc: unet_forward(sd, cfg, x, t, cc), lat.float(), mask.float(), ml.float(),
+                           ctx.float(), steps, 2.0)
+        # the reference's own fp16 noise after the same 5 steps (oracle in eager fp16 on this GPU)
+        sdh = {k: v.half() for k, v in sd.items()}
+        half = denoise_loop(lambda x, t, cc: unet_forward(sdh, cfg, x, t, cc), lat, mask, ml, ctx, steps, 2.0)
+    diff, floor = (nat.float() - ref).abs(), (half.float() - ref).abs()
+    assert torch.isfinite(nat).all()
+    assert diff.max().item() <= max(3 * floor.max().item(), 1e-2 * ref.abs().max().item()), (diff.max().item(), floor.max().item())
+    assert diff.mean().item() <= 2 * floor.mean().item() + 1e-4, (diff.mean().item(), floor.mean().item())
 
 
 def test_full_call_through_pipeline():

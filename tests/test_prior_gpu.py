@@ -268,14 +268,16 @@ def test_masked_attention_mma_and_generic_kernels_agree():
 
 
 def test_prior_simple_and_tensorcore_paths_agree():
-    """RCDM_PRIOR_SIMPLE=1 routes every Linear through the CUDA-core GEMM of the same C entry point."""
+    """``debug_simple`` routes every Linear through the CUDA-core GEMM of the same C entry point (explicit switch; the
+    library reads no environment variables)."""
+    from rcdms_b200.models.myprior_transformer import MyPriorTransformer
     cfg = prior_tiny_config()
     a = _forward_case(cfg, torch.float16, 500)
-    os.environ["RCDM_PRIOR_SIMPLE"] = "1"
+    MyPriorTransformer.debug_simple = True
     try:
         b = _forward_case(cfg, torch.float16, 500)
     finally:
-        os.environ.pop("RCDM_PRIOR_SIMPLE", None)
+        MyPriorTransformer.debug_simple = False
     _assert_floor(a)
     _assert_floor(b)
     assert (a["y"].float() - b["y"].float()).abs().max().item() <= max(3 * a["fmax"], 5e-3)

@@ -54,6 +54,36 @@ def test_matches_reference_golden(name, cfg_fn):
     assert d.mean().item() <= 3 * fl["mean_abs"] + 2e-4, (d.mean().item(), fl)
 
 
+_FULL_SD = {}
+
+
+def _full_sd():
+    if "sd" not in _FULL_SD:
+        _FULL_SD["sd"] = uc.synthetic_state_dict(full_config(), seed=0)
+    return _FULL_SD["sd"]
+
+
+# The shapes bench.py times (BASELINE.json configs 2, 3 and the 256x256 CPU case): full-width UNet, 64x64 / 32x32 latents.
+# These select code paths the tiny configs never reach: stream-K, CTA pairs, d = 40 flash attention over 4096 tokens,
+# wide temporal attention, cross-frame GroupNorm with several CTAs per statistic.
+@pytest.mark.parametrize("shape,t,dtype", [((2, 5, 64, 64, 85), 981, torch.float16),    # config 2: 1 clip, CFG, PororoSV
+                                            ((2, 5, 32, 32, 85), 501, torch.float16),    # config 1's latent size
+                                            ((4, 5, 64, 64, 91), 21, torch.bfloat16)])   # config 3's path: bf16, 2 clips, L=91
+def test_full_unet_matches_oracle_at_benchmarked_shapes(shape, t, dtype):
+    res = uc.run_case(full_config(), shape, t, dtype, taps=True, sd=_full_sd())
+    _assert_close(res)
+    # layer-by-layer: every block output must track the fp32 oracle (relative to that block's magnitude); the bound is
+    # the 16-bit output rounding (2^-11 / 2^-8 relative) accumulated over the preceding ~100 layers, x4 head-room
+    rel = 1.5e-2 if dtype == torch.float16 else 1.2e-1
+    assert len(res["tap_stats"]) >= 40
+    for name, st in res["tap_stats"].items():
+        assert "error" not in st, (name, st)
+        assert st["finite"], name
+        assert st["mean_abs"] <= rel * st["ref_mean_abs"], (name, st)
+    res.clear()
+    torch.cuda.empty_cache()
+
+
 def test_forward_contract():
     """Boundary behaviour of unet.py:322-463: new tensor, inputs untouched, tuple when return_dict=False,
     python-number and 0-dim cuda int64 timesteps agree, state_dict round trip."""

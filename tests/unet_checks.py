@@ -21,12 +21,10 @@ def golden_inputs(cfg, b, f, h, w, L, seed):
 
 def build_model(cfg, dtype, sd=None, simple=False):
     """Product module with the deterministic synthetic weights, on cuda:0 in `dtype`."""
-    if simple:
-        os.environ["RCDM_SIMPLE"] = "1"
-    else:
-        os.environ.pop("RCDM_SIMPLE", None)
     sd = sd if sd is not None else synthetic_state_dict(cfg, seed=0)
     m = UNet3DConditionModel.from_config(cfg)
+    if simple:
+        m.set_debug_option("simple", 1)  # explicit ABI switch (the library reads no environment variables)
     m.load_state_dict(sd, strict=True)
     m = m.to(device="cuda", dtype=dtype)
     return m
@@ -72,6 +70,7 @@ def run_case(cfg, shape, t, dtype, simple=False, taps=False, sd=None, seed=1234)
             bb, cc, ff, hh, ww = rt.shape
             rtok = rt.permute(0, 2, 3, 4, 1).reshape(-1, cc)
             res["tap_stats"][name] = stats(mine, rtok)
+    del sdr
     y16 = noise_floor(cfg, sd, x, t, ctx, dtype)
     res["floor"] = stats(y16, ref)
     return res
