@@ -26,6 +26,9 @@
 // Compile-time experiment switch for bottleneck analysis (never set in a product build; scripts/build_variants.sh):
 //   3 = producer loads the A tile only for the first k-block of a tile (B still streams), 4 = neither A nor B after
 //   the first k-block of a tile (MMAs run on stale smem): isolates epilogue + MMA issue.
+//   5 = the epilogue only waits for the accumulator and releases it (no TMEM loads, math, residual or stores),
+//   6 = full epilogue math but no residual TMA loads and no TMA stores, 7 = B is loaded only for the CTA's first tile
+//   ("weight-stationary" emulation), 9 = 4 + 5 (MMA issue alone).
 // (Measured with the earlier per-thread-store epilogue: the slab -> registers -> global "phase 2" cost 27 % of a
 //  K = 320 GEMM and the TMEM loads nothing, which is why the epilogue now ends in TMA stores.)
 #ifndef RCDM_GEMM_EXPERIMENT
@@ -281,8 +284,12 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
               tma_load_4d_2sm(sa, &maps.a[mi], &full_bar[stage], c * 64, x0 + dx, y0 + dy, n0);
             tma_load_2d_2sm(sb, &maps.b, &full_bar[stage], kb * 64, n_tile * BN + (int)rank * (BN / 2));
           } else {
-#if RCDM_GEMM_EXPERIMENT == 3 || RCDM_GEMM_EXPERIMENT == 4
+#if RCDM_GEMM_EXPERIMENT == 3 || RCDM_GEMM_EXPERIMENT == 4 || RCDM_GEMM_EXPERIMENT == 7 || RCDM_GEMM_EXPERIMENT == 9
+#if RCDM_GEMM_EXPERIMENT == 7
+            const bool load_a = true, load_b = tile == wid;
+#else
             const bool load_a = kb == kb0, load_b = (RCDM_GEMM_EXPERIMENT == 3) || kb == kb0;
+#endif
             mbar_expect_tx(&full_bar[stage], (load_a ? Cfg::A_BYTES : 0) + (load_b ? Cfg::B_BYTES : 0));
             if (load_a) {
               if (sg.mode == SEG_PLAIN) tma_load_2d(sa, &maps.a[mi], &full_bar[stage], c * 64, m_tile * 128);
@@ -368,7 +375,11 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
     const int q = warp & 3;
     const int cg = (warp - 2) >> 2;
     T* out = reinterpret_cast<T*>(p.out);
+#if RCDM_GEMM_EXPERIMENT == 6
+    const T* res = nullptr;
+#else
     const T* res = reinterpret_cast<const T*>(p.res);
+#endif
     const bool vec_ok = p.epi_tma != 0;
     const int n_total = p.geglu ? p.N / 2 : p.N;
     const int wcols = p.geglu ? QW / 2 : QW;       // output columns this warp produces per tile
@@ -425,6 +436,12 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
       const uint32_t acc_phase = (it >> 1) & 1;
       const uint32_t taddr = tmem_base + acc * Cfg::ACC_STRIDE + (uint32_t(q * 32) << 16);
       const int m_warp = m_tile * 128 + q * 32;
+#if RCDM_GEMM_EXPERIMENT == 5 || RCDM_GEMM_EXPERIMENT == 9
+      mbar_wait(&tmem_full_bar[acc], acc_phase);
+      tc_fence_after();
+      release_acc(acc);
+      continue;
+#endif
       if (kb0 > 0) {
         // ---- stream-K partial: this CTA's range began inside the tile -> dump the fp32 accumulator, raise the flag
         mbar_wait(&tmem_full_bar[acc], acc_phase);
@@ -733,6 +750,7 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
           p.stats_out[(size_t)(n_tile * NG + cg) * p.M + m_warp + lane] = make_float2(st_s, st_ss);
         fence_proxy_async_smem();  // this thread's staging writes -> visible to the TMA store
         epi_bar();
+#if RCDM_GEMM_EXPERIMENT != 6
         if (storer) {
           for (int g = 0; g < NG; ++g)
             if (n_tile * tile_cols + g * wcols < n_total)
@@ -740,6 +758,7 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
                            m_tile * 128);
           bulk_commit();
         }
+#endif
         ++ot;
       } else {
         // ---- scalar fallback (conv_out: N = 4): thread <-> row, direct stores; only the cg == 0 warps work

@@ -50,13 +50,19 @@ def conv(n, h, cin, cout):
     print(f"{tag:8s} conv n{n} {h}x{h} {cin}->{cout}: {us:7.1f} us", flush=True)
 
 
-L.rcdm_set_gemm_pair(0)
-gemm(40960, 320, 320, True)
-gemm(40960, 320, 320, False)
-gemm(40960, 960, 320, False)
-gemm(40960, 320, 1280, True)
-gemm(10240, 640, 640, True)
-gemm(2560, 1280, 1280, True)
-gemm(40960, 2560, 320, False, 1)
-conv(10, 64, 320, 320)
-conv(10, 64, 640, 320)
+for pair in (0, 2):
+    L.rcdm_set_gemm_pair(pair)
+    tag = tag.split("+")[0] + ("+pair" if pair else "")
+    gemm(40960, 320, 320, True)
+    gemm(40960, 320, 320, False)
+    gemm(40960, 960, 320, False)
+    gemm(40960, 320, 1280, True)
+    gemm(10240, 640, 640, True)
+    gemm(10240, 1920, 640, False)
+    gemm(2560, 1280, 1280, True)
+    gemm(2560, 3840, 1280, False)
+    gemm(40960, 2560, 320, False, 1)
+    gemm(10240, 5120, 640, False, 1)
+    gemm(2560, 10240, 1280, False, 1)
+    conv(10, 64, 320, 320)
+    conv(10, 32, 640, 640)
