@@ -44,9 +44,11 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-profile", action="store_true")
     ap.add_argument("--cpu-budget-s", type=float, default=150.0)
-    ap.add_argument("--eager-gpu-baseline", action="store_true",
-                    help="also time the oracle restatement in torch eager (bench dtype) on this GPU: the stand-in for "
-                         "'the reference modules in eager fp16 on the B200' (SURVEY 8d); reported, never a product path")
+    ap.add_argument("--no-eager-gpu-baseline", action="store_true",
+                    help="skip the eager-GPU leg (the oracle restatement in torch eager, bench dtype, on this GPU: the "
+                         "stand-in for 'the reference modules in eager fp16 on the B200', SURVEY 8d; on by default at N=1)")
+    ap.add_argument("--no-extra-configs", action="store_true",
+                    help="skip the extra BASELINE configs (N=1: config 3 bf16 x 8 clips; N>1: config 5, 8 clips per GPU)")
     ap.add_argument("--eager-gpu-only", action="store_true", help="run only the eager-GPU baseline leg and exit")
     ap.add_argument("--workload", default="stage2", choices=["stage2", "prior"],
                     help="stage2 (default, the headline metric) | prior: BASELINE config 4, the stage-1 frame-prior loop "
@@ -140,41 +142,95 @@ def cpu_reference_step_seconds(latent, ctx_len, ddim_steps, guidance, n_steps, n
 
 
 def run_reference(a):
+    """Reference arm: the reference's algorithm (oracle port; the Python reference cannot travel to the GPU box) on the
+    host CPU cores, same workload / metric / unit.  One "step" = a BOUNDED SAMPLE of one clip's denoise: ONE of its
+    `ddim_steps` DDIM steps (fp32 UNet forward with CFG at the configured latent size + scheduler step), ~10 s on 16
+    cores; value extrapolates the measured sample to the whole clip (x ddim_steps).  ms_per_step is the MEASURED duration
+    of a sample, so steps x ms_per_step is the wall time of the timed region."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     t_step, info = cpu_reference_step_seconds(a.latent, a.ctx_len, a.ddim_steps, a.guidance, a.steps,
-                                              min(a.warmup, 1), budget_s=240.0)
+                                              min(a.warmup, 1), budget_s=1e9)
     clip_s = t_step * a.ddim_steps
     value = 5.0 / clip_s
-    sample = (f"{info['executed']} of {a.ddim_steps} DDIM steps (UNet fp32 forward at {a.latent}x{a.latent} latents + CFG "
-              f"+ DDIM step) of one clip, extrapolated x{a.ddim_steps}")
-    line = dict(metric=METRIC, value=value, unit="frames/s", n_gpus=a.gpus, steps=a.steps, warmup=a.warmup,
-                ms_per_step=clip_s * 1e3, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
-                data="synthetic", impl="reference",
-                config=dict(workload=workload_name(a), clips_per_gpu=1, ddim_steps=a.ddim_steps, latent=a.latent,
-                            ctx_len=a.ctx_len, guidance=a.guidance,
-                            note="reference algorithm = oracle port of src/models/unet.py + diffusers DDIM on host CPU; "
-                                 "the Python reference itself cannot travel to the GPU box"),
+    sample = (f"each step = 1 of the {a.ddim_steps} DDIM steps of one clip (UNet fp32 forward at {a.latent}x{a.latent} "
+              f"latents with CFG + DDIM step), {info['executed']} steps timed, {t_step:.2f} s each; value = 5 frames / "
+              f"({a.ddim_steps} x that)")
+    line = dict(metric=METRIC, value=value, unit="frames/s", n_gpus=a.gpus, steps=info["executed"],
+                warmup=min(a.warmup, 1), ms_per_step=t_step * 1e3, higher_is_better=True, scaling="weak",
+                vs_baseline=None, dtype="f32", data="synthetic", impl="reference", config=config_dict(a, world),
+                sample_fraction_of_step_unit=1.0 / a.ddim_steps,
+                note="reference algorithm = oracle port of src/models/unet.py + diffusers DDIM on the host CPU cores; "
+                     "a step here is a bounded sample (1 DDIM step) of the clip the GPU arm denoises per step",
                 cpu_baseline=dict(value=value, unit="frames/s", cores=info["cores"], kind="port", sample=sample),
                 e2e=dict(value=value, unit="frames/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
     print(json.dumps(line), flush=True)
 
 
-def workload_name(a):
+def workload_name(a, clips=None, dtype=None, ctx_len=None):
     px = a.latent * 8
-    return (f"stage2 PororoSV {px}x{px}, {a.ddim_steps} DDIM steps, {a.dtype}, batch={a.clips} clip(s)/GPU, "
-            f"CFG {a.guidance}, L={a.ctx_len}")
+    ctx_len = ctx_len or a.ctx_len
+    ds = "FlintstonesSV" if ctx_len == 91 else "PororoSV"
+    return (f"stage2 {ds} {px}x{px}, {a.ddim_steps} DDIM steps, {dtype or a.dtype}, batch={clips or a.clips} clip(s)/GPU, "
+            f"CFG {a.guidance}, L={ctx_len}")
+
+
+def config_dict(a, world):
+    """The workload description - identical keys and values in both arms (ours / --impl reference) for the same flags."""
+    return dict(workload=workload_name(a), clips_per_gpu=a.clips, ddim_steps=a.ddim_steps, latent=a.latent,
+                ctx_len=a.ctx_len, guidance=a.guidance,
+                parallelism=f"clip-sharded x{world}, one all_gather of final latents",
+                l2="not flushed: per-step working set (2.55 GB fp16 weights + activations) >> 126 MB L2")
 
 
 # ----------------------------------------------------------------------------------------------------------
 # our arm
 # ----------------------------------------------------------------------------------------------------------
+def eager_gpu_leg(a, dtype, n_e=3):
+    """"the reference modules in PyTorch eager fp16 on the B200" - the denominator of the north_star's
+    10x target.  The Python reference cannot travel to the GPU box, so its restatement (oracle/unet_ref.py: the same
+    torch op sequence, one cuBLAS / cuDNN launch per op, attention scores materialised; pinned to the reference modules
+    by tests/golden) runs in the bench dtype on this GPU.  A reported baseline like cpu_baseline, never a product path."""
+    import torch
+    from oracle.loop_ref import make_scheduler
+    from oracle.unet_ref import unet_forward
+    from rcdms_b200.synthetic import synthetic_clip_inputs, synthetic_state_dict
+    from rcdms_b200.unet_spec import full_config
+    ecfg = full_config()
+    esd = {k: v.to("cuda", dtype) for k, v in synthetic_state_dict(ecfg, seed=0).items()}
+    ein = {k: v.to("cuda", dtype) for k, v in synthetic_clip_inputs(0, a.latent, a.latent, a.ctx_len).items()}
+    sch = make_scheduler()
+    sch.set_timesteps(a.ddim_steps)
+    lat = ein["latents"]
+    m2, l2 = torch.cat([ein["mask"]] * 2), torch.cat([ein["masked_latents"]] * 2)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.no_grad():
+        for i, t in enumerate(sch.timesteps[: n_e + 1]):
+            if i == 1:
+                ev0.record()
+            x = torch.cat([torch.cat([lat] * 2), m2, l2], dim=1)
+            eps = unet_forward(esd, ecfg, x, t, ein["ctx"])
+            eu, ec = eps.chunk(2)
+            lat = sch.step(eu + a.guidance * (ec - eu), t, lat, eta=0.0).prev_sample
+        ev1.record()
+    torch.cuda.synchronize()
+    ms_e = ev0.elapsed_time(ev1) / n_e
+    del esd
+    torch.cuda.empty_cache()
+    return dict(value=5.0 / (ms_e * a.ddim_steps / 1e3), unit="frames/s", ms_per_ddim_step=ms_e, kind="port",
+                sample=f"{n_e} of {a.ddim_steps} DDIM steps of one clip after 1 warm-up step, oracle restatement of the "
+                       f"reference UNet + CFG + DDIM in torch eager {a.dtype} on this GPU (cuBLAS / cuDNN, one launch per "
+                       f"op), extrapolated x{a.ddim_steps}; the reference's own nn.Modules are Python and absent on this box")
+
+
 def run_ours(a):
     import torch
     import torch.distributed as dist
     from rcdms_b200 import _lib
     from rcdms_b200.models import UNet3DConditionModel
+    from rcdms_b200.parallel import gather_latents
     from rcdms_b200.pipelines.RCDMs_pipeline import RCDMsPipeline
     from rcdms_b200.schedulers import DDIMScheduler
     from rcdms_b200.synthetic import synthetic_clip_inputs, synthetic_state_dict
@@ -187,88 +243,96 @@ def run_ours(a):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    dtype = torch.float16 if a.dtype == "fp16" else torch.bfloat16
     L = _lib.lib()  # fails loudly if the CUDA library is missing
-
     cfg = full_config()
-    unet = UNet3DConditionModel.from_config(cfg)
-    unet.load_state_dict(synthetic_state_dict(cfg, seed=0), strict=True)
-    unet = unet.to(device=dev, dtype=dtype)
+    sd = synthetic_state_dict(cfg, seed=0)
 
     class _VaeCfg:  # the pipeline only needs vae_scale_factor = 8 here; VAE/CLIP stay outside the hot path
         block_out_channels = (128, 256, 512, 512)
 
     class _Vae:
         config = _VaeCfg()
-    pipe = RCDMsPipeline(vae=_Vae(), text_encoder=None, tokenizer=None, unet=unet, local_module=None,
-                         global_module=None, scheduler=DDIMScheduler(**RCDMS_SCHEDULER_KWARGS))
-    pipe.use_cuda_graph = not a.no_graph
 
-    # per-clip synthetic inputs, clip index = global (rank-independent results); pinned host copies for e2e
-    clip_ids = [rank * a.clips + i for i in range(a.clips)]
-    ins = [synthetic_clip_inputs(k, a.latent, a.latent, a.ctx_len) for k in clip_ids]
-    host = dict(
-        latents=torch.cat([i["latents"] for i in ins]).to(dtype).pin_memory(),
-        masked=torch.cat([i["masked_latents"] for i in ins]).to(dtype).pin_memory(),
-        mask=torch.cat([i["mask"] for i in ins]).to(dtype).pin_memory(),
-        # ctx rows ordered (b f) with b = [uncond clips..., cond clips...]
-        ctx=torch.cat([i["ctx"][:5] for i in ins] + [i["ctx"][5:] for i in ins]).to(dtype).pin_memory())
-    devt = {k: v.to(dev) for k, v in host.items()}
-    out_host = torch.empty_like(host["latents"]).pin_memory()
+    def make_pipe(dtype):
+        unet = UNet3DConditionModel.from_config(cfg)
+        unet.load_state_dict(sd, strict=True)
+        unet = unet.to(device=dev, dtype=dtype)
+        pipe = RCDMsPipeline(vae=_Vae(), text_encoder=None, tokenizer=None, unet=unet, local_module=None,
+                             global_module=None, scheduler=DDIMScheduler(**RCDMS_SCHEDULER_KWARGS))
+        pipe.use_cuda_graph = not a.no_graph
+        return unet, pipe
 
-    def denoise_resident():
-        return pipe.denoise(devt["latents"], torch.cat([devt["mask"]] * 2), torch.cat([devt["masked"]] * 2), devt["ctx"],
-                            a.ddim_steps, a.guidance)
+    def measure(pipe, dtype, clips, ctx_len, steps, warm):
+        """(ms resident, ms e2e, host input bytes, host output bytes, launches) for `steps` denoises of `clips` clips per GPU."""
+        # per-clip synthetic inputs, clip index = global (rank-independent results); pinned host copies for e2e
+        clip_ids = [rank * clips + i for i in range(clips)]
+        ins = [synthetic_clip_inputs(k, a.latent, a.latent, ctx_len) for k in clip_ids]
+        host = dict(
+            latents=torch.cat([i["latents"] for i in ins]).to(dtype).pin_memory(),
+            masked=torch.cat([i["masked_latents"] for i in ins]).to(dtype).pin_memory(),
+            mask=torch.cat([i["mask"] for i in ins]).to(dtype).pin_memory(),
+            # ctx rows ordered (b f) with b = [uncond clips..., cond clips...]
+            ctx=torch.cat([i["ctx"][:5] for i in ins] + [i["ctx"][5:] for i in ins]).to(dtype).pin_memory())
+        devt = {k: v.to(dev) for k, v in host.items()}
+        out_host = torch.empty_like(host["latents"]).pin_memory()
 
-    def denoise_e2e():
-        d = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
-        lat = pipe.denoise(d["latents"], torch.cat([d["mask"]] * 2), torch.cat([d["masked"]] * 2), d["ctx"],
-                           a.ddim_steps, a.guidance)
-        out_host.copy_(lat, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-        return lat
+        def denoise_resident():
+            return pipe.denoise(devt["latents"], torch.cat([devt["mask"]] * 2), torch.cat([devt["masked"]] * 2),
+                                devt["ctx"], a.ddim_steps, a.guidance)
 
-    def gather(lat):
-        if world > 1:  # the path's only collective: final latents of every shard
-            buf = torch.empty((world,) + tuple(lat.shape), dtype=lat.dtype, device=dev)
-            dist.all_gather_into_tensor(buf, lat.contiguous())
-            return buf
-        return lat
+        def denoise_e2e():
+            d = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
+            lat = pipe.denoise(d["latents"], torch.cat([d["mask"]] * 2), torch.cat([d["masked"]] * 2), d["ctx"],
+                               a.ddim_steps, a.guidance)
+            out_host.copy_(lat, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            return lat
 
-    def timed(fn, k):
-        if world > 1:
-            dist.barrier()
+        def gather(lat):  # the path's only collective: final latents of every shard (SURVEY.md 8e)
+            return gather_latents(lat, clips * world)
+
+        def timed(fn, k):
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(k):
+                gather(fn())
+            e1.record()
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+            if world > 1:
+                dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+            return ms.item()
+
+        for _ in range(warm):
+            gather(denoise_resident())
         torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(k):
-            gather(fn())
-        e1.record()
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
-        if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return ms.item()
+        sampler = ClockSampler(local)
+        if rank == 0:
+            sampler.start()
+        l0 = L.rcdm_kernel_launches()
+        ms_res = timed(denoise_resident, steps)
+        launches = L.rcdm_kernel_launches() - l0
+        clocks = sampler.stop() if rank == 0 else None
+        gather(denoise_e2e())
+        ms_e2e = timed(denoise_e2e, steps)
+        h2d = sum(v.numel() * v.element_size() for v in host.values())
+        d2h = out_host.numel() * out_host.element_size()
+        return dict(ms=ms_res / steps, ms_e2e=ms_e2e / steps, h2d=h2d, d2h=d2h, launches=int(launches), clocks=clocks,
+                    devt=devt)
 
-    for _ in range(max(a.warmup, 3)):
-        gather(denoise_resident())
-    torch.cuda.synchronize()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-    launches0 = L.rcdm_kernel_launches()
-    ms_total = timed(denoise_resident, a.steps)
-    launches = L.rcdm_kernel_launches() - launches0
-    clocks = sampler.stop() if rank == 0 else None
-    gather(denoise_e2e())
-    ms_e2e = timed(denoise_e2e, a.steps)
-
-    ms_per_step = ms_total / a.steps
+    dtype = torch.float16 if a.dtype == "fp16" else torch.bfloat16
+    unet, pipe = make_pipe(dtype)
+    warm = max(a.warmup, 3)
+    r = measure(pipe, dtype, a.clips, a.ctx_len, a.steps, warm)
+    devt = r["devt"]
     frames = 5 * a.clips * world
-    value = frames / (ms_per_step / 1e3)
-    e2e_value = frames / (ms_e2e / a.steps / 1e3)
+    value = frames / (r["ms"] / 1e3)
+    e2e_value = frames / (r["ms_e2e"] / 1e3)
     flop_step = FLOP_PER_FORWARD_64 * (a.latent / 64.0) ** 2 * a.clips * a.ddim_steps  # per GPU per "step" (approx. off 64^2)
     pk = peaks()
 
@@ -289,10 +353,12 @@ def run_ours(a):
         mm_ms, mm_fl, mm_n = sum(g["ms"] for g in mm), sum(g["flops"] for g in mm), sum(g["n"] for g in mm)
         achieved = mm_fl / (mm_ms / 1e3) / 1e12
         traffic, traffic_note = None, None
-        tp = os.path.join(ROOT, "profiles", "r01_gemm_traffic.json")
-        if os.path.exists(tp):  # dram__bytes_read.sum + dram__bytes_write.sum per launch, from the committed ncu pass
-            tj = json.load(open(tp))
-            traffic, traffic_note = tj.get("dram_bytes_per_launch"), tj.get("note")
+        for tname in ("r02_gemm_traffic.json", "r01_gemm_traffic.json"):
+            tp = os.path.join(ROOT, "profiles", tname)
+            if os.path.exists(tp):  # dram__bytes_read.sum + dram__bytes_write.sum per launch, from the committed ncu pass
+                tj = json.load(open(tp))
+                traffic, traffic_note = tj.get("dram_bytes_per_launch"), f"profiles/{tname}: " + str(tj.get("note"))
+                break
         roofline = dict(bound="tensor", kernel="gemm_tcgen05_kernel", achieved=achieved, peak=pk["tflops"], unit="TFLOP/s",
                         frac=achieved / pk["tflops"], traffic=traffic, traffic_note=traffic_note,
                         peak_source=pk["source"] + ", sustained bf16",
@@ -303,6 +369,29 @@ def run_ours(a):
                                          gbs=round(v["bytes"] / max(v["ms"], 1e-9) / 1e6, 1)) for k, v in agg.items()},
                         forward_ms_sum_of_ops=tot_ms)
 
+    # ---- the other BASELINE.json configurations, measured in the same run (reported, not the headline):
+    #   N = 1: config 3 (FlintstonesSV, bf16, 8 clips batched on the GPU, L = 91);  N > 1: config 5 (8 clips per GPU, fp16)
+    extra = []
+    if not a.no_extra_configs and a.clips == 1 and a.latent == 64:
+        del devt, r["devt"]
+        if world == 1:
+            del unet, pipe
+            torch.cuda.empty_cache()
+            _, pipe3 = make_pipe(torch.bfloat16)
+            e = measure(pipe3, torch.bfloat16, 8, 91, 1, 2)
+            extra.append(dict(workload=workload_name(a, 8, "bf16", 91), baseline_config=3, dtype="bf16",
+                              value=5 * 8 / (e["ms"] / 1e3), unit="frames/s", ms_per_step=e["ms"],
+                              ms_per_ddim_step=e["ms"] / a.ddim_steps, e2e_value=5 * 8 / (e["ms_e2e"] / 1e3),
+                              clocks=e["clocks"], steps=1, warmup=2))
+            del pipe3
+            torch.cuda.empty_cache()
+        else:
+            e = measure(pipe, dtype, 8, a.ctx_len, 1, 2)
+            extra.append(dict(workload=workload_name(a, 8) + f", {8 * world} clips over {world} GPUs", baseline_config=5,
+                              dtype=a.dtype, value=5 * 8 * world / (e["ms"] / 1e3), unit="frames/s", ms_per_step=e["ms"],
+                              ms_per_ddim_step=e["ms"] / a.ddim_steps, e2e_value=5 * 8 * world / (e["ms_e2e"] / 1e3),
+                              clocks=e["clocks"], steps=1, warmup=2))
+
     cpu_baseline = None
     if not a.no_cpu_baseline and rank == 0 and world == 1:
         t_step, info = cpu_reference_step_seconds(a.latent, a.ctx_len, a.ddim_steps, a.guidance, 1, 0, a.cpu_budget_s)
@@ -311,57 +400,24 @@ def run_ours(a):
                                    f"CFG + DDIM) of one clip, {t_step:.1f} s, extrapolated x{a.ddim_steps}")
 
     eager_gpu = None
-    if a.eager_gpu_baseline and rank == 0 and world == 1:
-        # "the reference modules in PyTorch eager fp16 on the B200" — the reference itself cannot travel
-        # to the GPU box, so the oracle restatement (same torch op sequence, one launch per op, scores materialised)
-        # runs in the bench dtype on this GPU: a reported baseline like cpu_baseline, never a product path.
-        from oracle.loop_ref import make_scheduler
-        from oracle.unet_ref import unet_forward
-        from rcdms_b200.synthetic import synthetic_clip_inputs, synthetic_state_dict
-        from rcdms_b200.unet_spec import full_config
-        ecfg = full_config()
-        esd = {k: v.to("cuda", dtype) for k, v in synthetic_state_dict(ecfg, seed=0).items()}
-        ein = {k: v.to("cuda", dtype) for k, v in synthetic_clip_inputs(0, a.latent, a.latent, a.ctx_len).items()}
-        sch = make_scheduler()
-        sch.set_timesteps(a.ddim_steps)
-        lat = ein["latents"]
-        m2, l2 = torch.cat([ein["mask"]] * 2), torch.cat([ein["masked_latents"]] * 2)
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        n_e = 3
-        with torch.no_grad():
-            for i, t in enumerate(sch.timesteps[: n_e + 1]):
-                if i == 1:
-                    ev0.record()
-                x = torch.cat([torch.cat([lat] * 2), m2, l2], dim=1)
-                eps = unet_forward(esd, ecfg, x, t, ein["ctx"])
-                eu, ec = eps.chunk(2)
-                lat = sch.step(eu + a.guidance * (ec - eu), t, lat, eta=0.0).prev_sample
-            ev1.record()
-        torch.cuda.synchronize()
-        ms_e = ev0.elapsed_time(ev1) / n_e
-        eager_gpu = dict(value=5.0 / (ms_e * a.ddim_steps / 1e3), unit="frames/s", ms_per_ddim_step=ms_e, kind="port",
-                         sample=f"{n_e} of {a.ddim_steps} DDIM steps of one clip after 1 warm-up step, oracle restatement "
-                                f"in torch eager {a.dtype} on this GPU, extrapolated")
-        del esd
+    if not a.no_eager_gpu_baseline and rank == 0 and world == 1:
+        eager_gpu = eager_gpu_leg(a, dtype)
 
     if rank == 0:
-        h2d = sum(v.numel() * v.element_size() for v in host.values())
-        d2h = out_host.numel() * out_host.element_size()
-        line = dict(metric=METRIC, value=value, unit="frames/s", n_gpus=world, steps=a.steps, warmup=max(a.warmup, 3),
-                    ms_per_step=ms_per_step, higher_is_better=True, scaling="weak", vs_baseline=None,
-                    dtype="f16" if a.dtype == "fp16" else "bf16", data="synthetic",
-                    config=dict(workload=workload_name(a), clips_per_gpu=a.clips, ddim_steps=a.ddim_steps,
-                                latent=a.latent, ctx_len=a.ctx_len, guidance=a.guidance, cuda_graph=not a.no_graph,
-                                parallelism=f"clip-sharded x{world}, one all_gather of final latents",
-                                l2="not flushed: per-step working set (2.55 GB fp16 weights + activations) >> 126 MB L2",
-                                ms_per_ddim_step=ms_per_step / a.ddim_steps,
-                                achieved_tflops_per_gpu=flop_step / (ms_per_step / 1e3) / 1e12,
-                                frac_of_sustained_bf16_peak=flop_step / (ms_per_step / 1e3) / 1e12 / pk["tflops"]),
-                    e2e=dict(value=e2e_value, unit="frames/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
-                             ms_per_step=ms_e2e / a.steps, api="RCDMsPipeline.denoise (host pinned tensors in, host latents out)"),
-                    gpu_launches=int(launches), clocks=clocks, roofline=roofline, cpu_baseline=cpu_baseline)
+        line = dict(metric=METRIC, value=value, unit="frames/s", n_gpus=world, steps=a.steps, warmup=warm,
+                    ms_per_step=r["ms"], higher_is_better=True, scaling="weak", vs_baseline=None,
+                    dtype="f16" if a.dtype == "fp16" else "bf16", data="synthetic", config=config_dict(a, world),
+                    derived=dict(cuda_graph=not a.no_graph, ms_per_ddim_step=r["ms"] / a.ddim_steps,
+                                 achieved_tflops_per_gpu=flop_step / (r["ms"] / 1e3) / 1e12,
+                                 frac_of_sustained_bf16_peak=flop_step / (r["ms"] / 1e3) / 1e12 / pk["tflops"]),
+                    e2e=dict(value=e2e_value, unit="frames/s", h2d_bytes_per_step=r["h2d"], d2h_bytes_per_step=r["d2h"],
+                             ms_per_step=r["ms_e2e"], api="RCDMsPipeline.denoise (host pinned tensors in, host latents out)"),
+                    gpu_launches=r["launches"], clocks=r["clocks"], roofline=roofline, cpu_baseline=cpu_baseline)
         if eager_gpu is not None:
             line["gpu_eager_baseline"] = eager_gpu
+            line["derived"]["speedup_vs_gpu_eager"] = eager_gpu["ms_per_ddim_step"] / (r["ms"] / a.ddim_steps)
+        if extra:
+            line["extra_configs"] = extra
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -37,3 +37,27 @@ def test_our_arm_fails_loudly_without_a_gpu():
         r = _run("--steps", "1", "--warmup", "1", "--no-cpu-baseline", *extra, timeout=300)
         assert r.returncode != 0, "bench.py must not fall back to a CPU path"
         assert not [l for l in r.stdout.splitlines() if l.startswith("{")], r.stdout[-500:]
+
+
+def test_stage2_reference_arm_line_and_config_keys():
+    """The stage-2 reference arm at a small latent size: one JSON line, the SAME config keys / values our arm prints for
+    the same flags (so the driver's same_config check holds), and ms_per_step = the measured duration of one bounded
+    sample (so steps x ms_per_step fits in the run's wall time)."""
+    import time
+    sys.path.insert(0, ROOT)
+    import argparse
+    import bench
+    t0 = time.time()
+    r = _run("--impl", "reference", "--latent", "8", "--ddim-steps", "10", "--steps", "2", "--warmup", "1")
+    wall = time.time() - t0
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.strip().splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert REQUIRED <= set(d), REQUIRED - set(d)
+    assert d["impl"] == "reference" and d["unit"] == "frames/s" and d["steps"] == 2
+    a = argparse.Namespace(latent=8, ddim_steps=10, dtype="fp16", clips=1, guidance=2.0, ctx_len=85)
+    assert d["config"] == bench.config_dict(a, 1)
+    assert d["steps"] * d["ms_per_step"] / 1e3 <= wall
+    assert abs(d["value"] - 5.0 / (d["ms_per_step"] / 1e3 * 10)) < 1e-9 * max(1.0, d["value"])
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
