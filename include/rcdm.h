@@ -192,6 +192,19 @@ RCDM_API size_t rcdm_groupnorm_scratch_bytes(int rows, int rows_per_stat, int gr
 RCDM_API int rcdm_groupnorm(int dtype, const void* x_dev, const float* gamma_dev, const float* beta_dev, void* out_dev,
                    int rows, int channels, int groups, int rows_per_stat, float eps, int silu, void* scratch_dev,
                    void* stream);
+/* GroupNorm with the statistics produced by the GEMM that wrote the tensor (no statistics pass, no grid barrier):
+ * rcdm_gemm_gnstats = rcdm_gemm whose epilogue also accumulates, per (image of `hw` rows, chunk of 10 channels), the sum
+ * and sum of squares of its rounded output into acc_dev (rcdm_gn_acc_bytes(M / hw, N) bytes, zeroed by the caller;
+ * 128-bit fixed point, integer atomics => order-independent); rcdm_groupnorm_from_stats then normalises (+SiLU) the virtual
+ * channel concat [x0 | x1] in one streaming pass.  Replaces nn.GroupNorm of resnet.py:185,194, attention.py:328,
+ * motion_module.py:162, unet.py:455 (statistics over rows_per_stat = hw rows per frame, or frames * hw). */
+RCDM_API size_t rcdm_gn_acc_bytes(int images, int channels);
+RCDM_API int rcdm_gemm_gnstats(int dtype, const void* a_dev, const void* w_dev, const float* bias_dev,
+                               const void* residual_dev, void* out_dev, int M, int N, int K, int hw, void* acc_dev,
+                               void* stream);
+RCDM_API int rcdm_groupnorm_from_stats(int dtype, const void* x0_dev, int C0, const void* acc0_dev, const void* x1_dev, int C1,
+                                       const void* acc1_dev, const float* gamma_dev, const float* beta_dev, void* out_dev,
+                                       int rows, int rows_per_stat, int hw, int groups, float eps, int silu, void* stream);
 RCDM_API int rcdm_layernorm(int dtype, const void* x_dev, const float* gamma_dev, const float* beta_dev, void* out_dev,
                    int rows, int channels, float eps, const float* pe_dev, int rows_per_frame, int frames,
                    void* stream);

@@ -75,6 +75,9 @@ SIGNATURES = {
     "rcdm_linear_ln": (_I, [_I, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _F, _P, _P]),
     "rcdm_groupnorm_scratch_bytes": (C.c_size_t, [_I, _I, _I]),
     "rcdm_groupnorm": (_I, [_I, _P, _P, _P, _P, _I, _I, _I, _I, _F, _I, _P, _P]),
+    "rcdm_gn_acc_bytes": (C.c_size_t, [_I, _I]),
+    "rcdm_gemm_gnstats": (_I, [_I, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P]),
+    "rcdm_groupnorm_from_stats": (_I, [_I, _P, _I, _P, _P, _I, _P, _P, _P, _P, _I, _I, _I, _I, _F, _I, _P]),
     "rcdm_layernorm": (_I, [_I, _P, _P, _P, _P, _I, _I, _F, _P, _I, _I, _P]),
     "rcdm_flash_attn": (_I, [_I, _P, _I, _P, _P, _I, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
     "rcdm_temporal_attn": (_I, [_I, _P, _P, _I, _I, _I, _I, _I, _P]),

@@ -134,7 +134,7 @@ size_t rcdm_unet_workspace_bytes(const rcdm_unet* h) { return h ? h->ws_bytes : 
 int rcdm_unet_set_option(rcdm_unet* h, const char* name, int value) {
   if (!h || !name) return set_err("null argument");
   int* field = !strcmp(name, "simple") ? &h->simple : !strcmp(name, "autotune") ? &h->autotune :
-               !strcmp(name, "ln_fold") ? &h->ln_fold : nullptr;
+               !strcmp(name, "ln_fold") ? &h->ln_fold : !strcmp(name, "gn_stats") ? &h->gn_stats : nullptr;
   if (!field) return set_err(std::string("rcdm_unet_set_option: unknown option ") + name);
   if (*field != value) {
     *field = value;
@@ -665,6 +665,65 @@ int rcdm_gemm_rowstats(int dtype, const void* a_dev, const void* w_dev, const fl
   gemm_launch(l, reinterpret_cast<cudaStream_t>(stream));
   g_launches++;
   return check_launch("rcdm_gemm_rowstats");
+  API_END
+}
+
+// GEMM whose epilogue also accumulates the GroupNorm chunk statistics of its rounded output (see GemmParams::gn_acc):
+// acc_dev = u64[M / hw][N / 10][4], zeroed by the caller; hw = rows per image.
+size_t rcdm_gn_acc_bytes(int images, int channels) { return gemm_gn_acc_bytes(images, channels); }
+int rcdm_gemm_gnstats(int dtype, const void* a_dev, const void* w_dev, const float* bias_dev, const void* residual_dev,
+                      void* out_dev, int M, int N, int K, int hw, void* acc_dev, void* stream) {
+  API_BEGIN
+  if (!dt16(dtype)) return set_err("rcdm_gemm_gnstats: dtype must be f16/bf16");
+  if (!acc_dev) return set_err("null argument");
+  if (!gemm_gn_stats_ok(M, N, hw)) return set_err("rcdm_gemm_gnstats: needs N % 160 == 0, M % 128 == 0, hw % 32 == 0");
+  if (ensure_device_ready()) return 1;
+  GemmDesc d;
+  memset(&d, 0, sizeof d);
+  d.dt = dtype;
+  d.M = M;
+  d.N = N;
+  d.nseg = 1;
+  d.seg[0] = ASeg{SEG_PLAIN, a_dev, K, K, 0, 0, 0};
+  d.w = w_dev;
+  d.Ktot = K;
+  d.w_rows = N;
+  d.out = out_dev;
+  d.ldo = N;
+  d.bias = bias_dev;
+  d.res = residual_dev;
+  d.ldr = N;
+  d.gn_acc = reinterpret_cast<unsigned long long*>(acc_dev);
+  d.gn_hw = hw;
+  GemmLaunch l;
+  std::string e;
+  d.sk = sk_workspace_for_stream(reinterpret_cast<cudaStream_t>(stream), &e);
+  if (!gemm_prepare(d, &l, &e)) return set_err(e);
+  gemm_launch(l, reinterpret_cast<cudaStream_t>(stream));
+  g_launches++;
+  return check_launch("rcdm_gemm_gnstats");
+  API_END
+}
+
+// GroupNorm(+SiLU) of the (virtual) channel concat [x0 | x1] with the statistics taken from the accumulators the producing
+// GEMMs' epilogues filled: one streaming pass, no statistics read of the tensors (x1 / acc1 may be NULL, C1 = 0).
+int rcdm_groupnorm_from_stats(int dtype, const void* x0_dev, int C0, const void* acc0_dev, const void* x1_dev, int C1,
+                              const void* acc1_dev, const float* gamma_dev, const float* beta_dev, void* out_dev, int rows,
+                              int rows_per_stat, int hw, int groups, float eps, int silu, void* stream) {
+  API_BEGIN
+  if (!dt16(dtype)) return set_err("rcdm_groupnorm_from_stats: dtype must be f16/bf16");
+  const int C = C0 + C1;
+  if (!x0_dev || !acc0_dev || !out_dev || (C1 > 0 && (!x1_dev || !acc1_dev))) return set_err("null argument");
+  if (C0 % 10 || C1 % 10 || C % 8 || groups <= 0 || groups > 64 || C % groups || (C / groups) % 10 || hw <= 0 ||
+      rows_per_stat % hw || rows % rows_per_stat)
+    return set_err("rcdm_groupnorm_from_stats: bad shape (group width and both channel counts must be multiples of 10)");
+  if (ensure_device_ready()) return 1;
+  GnLaunch l;
+  gn_configure_from_stats(&l, dtype, x0_dev, C0, reinterpret_cast<const unsigned long long*>(acc0_dev), x1_dev, C1,
+                          reinterpret_cast<const unsigned long long*>(acc1_dev), rows, rows_per_stat, hw, groups, eps,
+                          gamma_dev, beta_dev, out_dev, silu);
+  gn_run(l, reinterpret_cast<cudaStream_t>(stream));
+  return check_launch("rcdm_groupnorm_from_stats");
   API_END
 }
 

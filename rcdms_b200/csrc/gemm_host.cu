@@ -156,7 +156,10 @@ int gemm_stats_parts(int N) {  // one part per epilogue column group per N tile 
   return RCDM_EPI_GROUPS * ((N + bn - 1) / bn);
 }
 
+bool gemm_gn_stats_ok(int M, int N, int hw) { return N % 160 == 0 && M % 128 == 0 && hw > 0 && hw % 32 == 0 && M % hw == 0; }
+
 static int pick_bn(const GemmDesc& d) {
+  if (d.gn_acc) return 160;
   if (d.force_bn) return d.force_bn;
   if (d.geglu) return GEGLU_BN;
   if (d.N % 160 == 0) return 160;
@@ -197,6 +200,11 @@ bool gemm_prepare(const GemmDesc& d, GemmLaunch* l, std::string* err) {
                      d.seg[0].mode != SEG_PLAIN))
     return fail("folded LayerNorm needs the c vector, N % 8 == 0 and a single plain K segment");
   if (d.stats_out && (d.geglu || d.N % 8 != 0)) return fail("row statistics need a plain vectorised epilogue");
+  p.gn_acc = d.gn_acc;
+  p.gn_hw = d.gn_hw;
+  l->gn = d.gn_acc ? 1 : 0;
+  if (d.gn_acc && (d.geglu || d.act || d.stats_in || !gemm_gn_stats_ok(d.M, d.N, d.gn_hw)))
+    return fail("GroupNorm statistics need a plain epilogue, N % 160 == 0, M % 128 == 0 and hw % 32 == 0");
   p.tw = 1;
   p.th = 1;
   p.tn = 128;
@@ -298,7 +306,7 @@ bool gemm_prepare(const GemmDesc& d, GemmLaunch* l, std::string* err) {
         if (!encode_tmap(&l->maps.r, d.res, 2, dims, strr, box, false, err)) return false;
       }
     }
-    if (!ok && (d.stats_out || d.stats_in || d.geglu || d.act))
+    if (!ok && (d.stats_out || d.stats_in || d.geglu || d.act || d.gn_acc))
       return fail("this epilogue needs 16-byte aligned output rows");
     if (d.act && d.geglu) return fail("act (plain GELU) and geglu are mutually exclusive");
   }
@@ -332,6 +340,13 @@ template <typename T, int BN> static void launch_one(const GemmLaunch& l, cudaSt
     return;
   }
   if (!l.pair) {
+    if constexpr (BN == 160) {
+      if (l.gn) {
+        launch_k(gemm_tcgen05_kernel<T, BN, false, false, true>, l.grid, dim3(GemmCfg<BN, false>::THREADS),
+                 GemmCfg<BN, false>::SMEM_BYTES, s, l.maps, l.p);
+        return;
+      }
+    }
     launch_k(gemm_tcgen05_kernel<T, BN, false>, l.grid, dim3(GemmCfg<BN, false>::THREADS), GemmCfg<BN, false>::SMEM_BYTES, s,
              l.maps, l.p);
     return;
@@ -350,6 +365,12 @@ template <typename T, int BN> static void launch_one(const GemmLaunch& l, cudaSt
   at[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = at;
   cfg.numAttrs = pdl_enabled() ? 2 : 1;
+  if constexpr (BN == 160) {
+    if (l.gn) {
+      cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<T, BN, true, false, true>, l.maps, l.p);
+      return;
+    }
+  }
   cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<T, BN, true>, l.maps, l.p);
 }
 
@@ -374,6 +395,14 @@ template <typename T, int BN> static cudaError_t set_attr() {
   if (e == cudaSuccess)
     e = cudaFuncSetAttribute(gemm_tcgen05_kernel<T, BN, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              GemmCfg<BN, false>::SMEM_BYTES);
+  if constexpr (BN == 160) {
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(gemm_tcgen05_kernel<T, BN, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               GemmCfg<BN, false>::SMEM_BYTES);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(gemm_tcgen05_kernel<T, BN, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               GemmCfg<BN, true>::SMEM_BYTES);
+  }
   return e;
 }
 

@@ -8,9 +8,13 @@
 //   warp 1     MMA issuer    (one elected lane)  : tcgen05.mma into one of TWO TMEM accumulators; owns TMEM alloc
 //   warps 2-9  epilogue (8 warps)                : tcgen05.ld -> scale * acc + vector (+GEGLU) (+residual tile, which the
 //                                                  producer TMA-loaded into the staging buffer a tile ahead)
-//                                                  -> 16-bit staging buffer (2 buffers) -> ONE TMA store per column
-//                                                  group, issued by one thread (no per-thread global stores)
-// so the main loop of tile i+1 overlaps the epilogue of tile i.
+//                                                  -> 16-bit staging buffer (2 buffers)
+//   warp 10    store warp    (one elected lane)  : waits for a staging buffer to be complete, issues ONE TMA store per column
+//                                                  group, waits until the store has read the buffer, then TMA-loads the
+//                                                  residual tile that will use this buffer next (two tiles ahead)
+// so the main loop of tile i+1 overlaps the epilogue of tile i, and no epilogue thread ever waits for a store to drain
+// (measured on the K = 320 GEMMs: with the store issued and drained by an epilogue thread, the per-tile chain
+//  "store drained -> this thread's math -> barrier -> store" cost 20 % of the launch).
 //
 // The K loop runs over up to three "segments", each reading A through its own TMA tensor map(s):
 //   SEG_PLAIN    A is a row-major [M, K] matrix             (Linear, conv1x1, im2col'ed conv_in)
@@ -91,7 +95,28 @@ struct GemmParams {
   const float* ln_c;       // [ln_frames][accumulator columns]
   int ln_frames, ln_rows_per_frame;
   float ln_eps;
+  // GroupNorm statistics of the OUTPUT, emitted by the epilogue (GN template flag; resnet.py:185,194 / attention.py:328 /
+  // motion_module.py:162 / unet.py:455 consume them): per (image = gn_hw consecutive rows, chunk of GN_CHUNK = 10
+  // consecutive channels) the sum and the sum of squares of the rounded output values, accumulated into 128-bit fixed
+  // point (two u64 halves each; integer atomics => the result does not depend on the arrival order, so graph replays
+  // stay bit-identical): gn_acc[(img * N / 10 + chunk) * 4 + {0: sum hi, 1: sum lo, 2: sumsq hi, 3: sumsq lo}].
+  // The consumer (gn_apply_kernel) folds the chunks of a group (any width that is a multiple of 10, over one or all
+  // frames, over the two tensors of an un-materialised skip concat) into mean / rstd.  Zeroed once per step.
+  unsigned long long* gn_acc;
+  int gn_hw;
 };
+constexpr int GN_CHUNK = 10;
+// value v (fp32) -> fixed point v * 2^40 split into (hi = floor(v * 2^-8), lo = remainder < 2^48); exact for |v| >= 2^-16
+// (24-bit significand), |error| < 2^-40 below; hi fits 64 bits for every finite fp32 sum of <= 2^20 fp16 values
+__device__ __forceinline__ void gn_fixed_split(float v, unsigned long long& hi, unsigned long long& lo) {
+  const double d = (double)v * 1099511627776.0;                         // 2^40
+  const long long h = __double2ll_rd(d * 3.552713678800501e-15);        // 2^-48
+  hi = (unsigned long long)h;
+  lo = (unsigned long long)__double2ll_rn(d - (double)h * 281474976710656.0);  // 2^48
+}
+__host__ __device__ __forceinline__ double gn_fixed_join(unsigned long long hi, unsigned long long lo) {
+  return ((double)(long long)hi * 281474976710656.0 + (double)lo) * 9.094947017729282e-13;  // 2^-40
+}
 
 // Work decomposition shared by the three warp roles (they must enumerate identical sequences).
 struct GemmWork {
@@ -145,7 +170,7 @@ template <int BN, bool PAIR = false> struct GemmCfg {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int NG = RCDM_EPI_GROUPS;   // column groups; 4 * NG epilogue warps
   static constexpr int QW = BN / NG;           // accumulator columns per epilogue warp
-  static constexpr int THREADS = 64 + 128 * NG;
+  static constexpr int THREADS = 64 + 128 * NG + 32;  // producer, MMA, 4 * NG epilogue warps, store warp
   // staging buffer = the 128 x BN 16-bit output tile as NG dense [128 rows][QW] parts (TMA box layout); two buffers
   // (tile parity) so the residual of tile i+1 loads while tile i is written and stored
   static constexpr int PART_BYTES = 128 * QW * 2;
@@ -163,11 +188,11 @@ template <int BN, bool PAIR = false> struct GemmCfg {
 // Persistent, warp-specialised: grid = min(#tiles, #SMs), one CTA per SM.  Tiles are visited round-robin
 // (n fastest, so CTAs running concurrently share A rows in L2).  The TMA producer runs ahead across tile
 // boundaries; two TMEM accumulators let the MMA warp start tile i+1 while the epilogue warps drain tile i.
-// 10 warps = 3 on the fullest SM sub-partition (16384 registers each) => at most 168 registers per thread.
+// 11 warps = 3 on the fullest SM sub-partition (16384 registers each) => at most 168 registers per thread.
 // ACT: compile-time switch for the epilogue activation (p.act).  The activation-free instantiation is the one every
 // UNet GEMM runs: a run-time branch inside `finish8` cost the epilogue-bound small-K GEMMs 15-19 % (measured), so the
 // stage-1 prior's GELU / SiLU epilogues get their own instantiation.
-template <typename T, int BN, bool PAIR, bool ACT = false>
+template <typename T, int BN, bool PAIR, bool ACT = false, bool GN = false>
 __global__ void __launch_bounds__(GemmCfg<BN, PAIR>::THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
   using Cfg = GemmCfg<BN, PAIR>;
@@ -193,7 +218,10 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
   uint64_t* tmem_full_bar = bars + 2 * STAGES;       // [2]
   uint64_t* tmem_empty_bar = bars + 2 * STAGES + 2;  // [2]
   uint64_t* res_full = bars + 2 * STAGES + 4;        // [2] residual tile landed in staging[b]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 6);
+  uint64_t* stg_full = bars + 2 * STAGES + 6;        // [2] every epilogue warp has written its slice of staging[b]
+  uint64_t* stg_free = bars + 2 * STAGES + 8;        // [2] the TMA store has finished reading staging[b]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 10);
+  static_assert((2 * STAGES + 10) * 8 + 4 <= 256, "barrier block overflows its 256 bytes");
   float* bias_sm = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);  // [2 parity][BN]
 
   const int warp = threadIdx.x >> 5;
@@ -217,6 +245,8 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
         mbar_init(&tmem_full_bar[i], 1);
         mbar_init(&tmem_empty_bar[i], (PAIR ? 8 : 4) * Cfg::NG);  // one arrival per epilogue warp (pair: of both CTAs)
         mbar_init(&res_full[i], 1);
+        mbar_init(&stg_full[i], 4 * Cfg::NG);  // one arrival per epilogue warp of THIS CTA
+        mbar_init(&stg_free[i], 1);
       }
       fence_mbar_init();
     }
@@ -361,7 +391,7 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
         else umma_commit(&tmem_full_bar[acc]);
       }
     }
-  } else {
+  } else if (warp < 2 + 4 * Cfg::NG) {
     // =================================== epilogue (4 * NG warps) ===================================
     // warp -> (q, cg): q = TMEM lane quarter (rows q*32..+31), cg = which column group of the tile.
     // thread <-> row: TMEM -> registers, scale * acc + vector (smem broadcast), GEGLU, + residual (packed half2 add ==
@@ -384,7 +414,6 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
     const int n_total = p.geglu ? p.N / 2 : p.N;
     const int wcols = p.geglu ? QW / 2 : QW;       // output columns this warp produces per tile
     const int tile_cols = p.geglu ? TH : BN;       // output columns per tile
-    const bool storer = warp == 2 && lane == 0;    // issues the TMA stores / residual loads, owns the bulk groups
     auto ld_chunk = [&](uint32_t addr, uint32_t* r) {
       if constexpr (CW == 16) tmem_ld16(addr, r);
       else tmem_ld8(addr, r);
@@ -397,27 +426,7 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
     int it = 0;
     int ot = 0;  // output-producing work items so far (stream-K partial dumps do not count)
     GemmWork work(p, wid, nworkers);
-    GemmWork peek(p, wid, nworkers);  // runs one output tile ahead (storer thread only): residual prefetch
     int tile, kb0, kb1;
-    // residual tile of output item `o` (tile index `t`) -> staging[o & 1] by TMA, completion on res_full[o & 1]
-    auto issue_residual = [&](int t, int o) {
-      const int nt = t % p.num_n_tiles;
-      const int mt = PAIR ? 2 * (t / p.num_n_tiles) + (int)rank : t / p.num_n_tiles;
-      const int b = o & 1;
-      int parts = 0;
-      for (int g = 0; g < NG; ++g) parts += (nt * BN + g * QW) < p.N;
-      mbar_expect_tx(&res_full[b], parts * Cfg::PART_BYTES);
-      for (int g = 0; g < parts; ++g)
-        tma_load_2d(staging + b * Cfg::STG_BYTES + g * Cfg::PART_BYTES, &maps.r, &res_full[b], nt * BN + g * QW, mt * 128);
-    };
-    if (storer && vec_ok && res) {  // residual of the first output tile
-      int nt, nk0, nk1;
-      while (peek.next(nt, nk0, nk1))
-        if (nk0 == 0) {
-          issue_residual(nt, 0);
-          break;
-        }
-    }
     // "accumulator drained": in a pair every epilogue thread of both CTAs arrives on the LEADER's barrier
     // one arrival per warp (after a warp sync), not per thread: 256 serialised arrivals on one mbarrier per tile were
     // a measurable part of the per-tile latency chain  epilogue -> tmem_empty -> next MMA
@@ -571,22 +580,6 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
       if (vec_ok) {
         const int n_warp = n_tile * tile_cols + cg * wcols;  // first output column of this warp
         const int sb = ot & 1;                               // staging buffer of this tile
-        if (storer) {
-          // the store of the previous tile has finished READING its staging buffer -> that buffer may be refilled
-          // (groups retire in order, so the buffer this tile writes - last read two tiles ago - is free as well; the
-          // other warps learn it through the named barrier at the end of the previous tile)
-          if (ot > 0) bulk_wait_read0();
-          if (res) {  // residual of the NEXT output tile -> the other buffer, one tile ahead of its use
-            int nt, nk0, nk1;
-            bool have = false;
-            while (peek.next(nt, nk0, nk1))
-              if (nk0 == 0) {
-                have = true;
-                break;
-              }
-            if (have) issue_residual(nt, ot + 1);
-          }
-        }
         // ---- epilogue vector of this warp's columns (bias, or LN c): fetched into registers BEFORE the accumulator
         // wait (latency hidden), parked in smem[tile parity] AFTER it.  The four warps sharing `cg` write identical
         // values (benign); storing after the wait keeps the parity double-buffer race-free.
@@ -617,14 +610,21 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
           if (i < QW) bsm[i] = pre0[j];
         }
         __syncwarp();
-        if (res) mbar_wait(&res_full[sb], (ot >> 1) & 1);  // the residual tile is in the staging buffer
+        // staging[sb] is ours to write: the residual tile has landed in it (the store warp loads it only after the store
+        // of the tile that used the buffer before has been read), or - no residual - that store has been read
+        if (res) mbar_wait(&res_full[sb], (ot >> 1) & 1);
+        else mbar_wait(&stg_free[sb], ((ot >> 1) & 1) ^ 1);
         // ---- thread <-> row: v = scale * acc + vec (+GEGLU), rounded to 16 bits, (+ residual, rounded again like the
         // reference's `x + attn(...)` on 16-bit tensors), written to this row's slice of the staging buffer
         const float scale = ln_a;
         uint8_t* srow = staging + sb * Cfg::STG_BYTES + cg * Cfg::PART_BYTES + (size_t)(q * 32 + lane) * (wcols * 2);
         float st_s = 0.f, st_ss = 0.f;  // row statistics of the final values (folded-LayerNorm producer)
+        constexpr int GNC = GN ? QW / GN_CHUNK : 1;  // GroupNorm chunks of this warp's columns
+        float gn_s[GNC], gn_ss[GNC];
+#pragma unroll
+        for (int i = 0; i < GNC; ++i) gn_s[i] = gn_ss[i] = 0.f;
         using T2 = typename DT<T>::T2;
-        auto finish8 = [&](float* v, int c) {  // 8 outputs at columns c.. of this warp's slice
+        auto finish8 = [&](float* v, int c) -> uint4 {  // 8 outputs at columns c.. of this warp's slice; returns them packed
           if constexpr (ACT) {
             if (p.act == 1) {
 #pragma unroll
@@ -653,6 +653,20 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
             }
           }
           *dst = pk;
+          return pk;
+        };
+        // GroupNorm chunk sums of 8 final values at columns c.. ; called only where c is a compile-time constant after
+        // unrolling (the accumulators must stay in registers)
+        auto gn_add8 = [&](const uint4& pk, int c) {
+          if constexpr (GN) {
+            float f8[8];
+            unpack8<T>(pk, f8);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              gn_s[(c + i) / GN_CHUNK] += f8[i];
+              gn_ss[(c + i) / GN_CHUNK] = fmaf(f8[i], f8[i], gn_ss[(c + i) / GN_CHUNK]);
+            }
+          }
         };
         if (ln && !ln_smem) {
           // rare: a 128-row tile of a temporal projection spans several frames (8x8 level, tiny test configs): the
@@ -709,7 +723,7 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
               v[5] = fmaf(__uint_as_float(rc[g * 8 + 5]), scale, b1.y);
               v[6] = fmaf(__uint_as_float(rc[g * 8 + 6]), scale, b1.z);
               v[7] = fmaf(__uint_as_float(rc[g * 8 + 7]), scale, b1.w);
-              finish8(v, c + g * 8);
+              gn_add8(finish8(v, c + g * 8), c + g * 8);
             }
           }
         } else {
@@ -748,17 +762,42 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
         release_acc(acc);  // accumulator drained: the MMA warp may reuse it
         if (p.stats_out && m_warp + lane < p.M)
           p.stats_out[(size_t)(n_tile * NG + cg) * p.M + m_warp + lane] = make_float2(st_s, st_ss);
-        fence_proxy_async_smem();  // this thread's staging writes -> visible to the TMA store
-        epi_bar();
-#if RCDM_GEMM_EXPERIMENT != 6
-        if (storer) {
-          for (int g = 0; g < NG; ++g)
-            if (n_tile * tile_cols + g * wcols < n_total)
-              tma_store_2d(&maps.o, staging + sb * Cfg::STG_BYTES + g * Cfg::PART_BYTES, n_tile * tile_cols + g * wcols,
-                           m_tile * 128);
-          bulk_commit();
+        if constexpr (GN) {
+          // sum the 2 * GNC per-row values over the warp's 32 rows with a reduce-scatter butterfly (fixed tree, 2 * GNC
+          // shuffles instead of 5 per value): afterwards lanes 2k and 2k+1 hold value k (k < GNC: sum of chunk k,
+          // else sum of squares of chunk k - GNC); lane 2k adds it to the tensor's fixed-point accumulators
+          static_assert(GNC == 8, "the butterfly below reduces 16 values over 32 lanes");
+          float vals[16];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            vals[i] = gn_s[i];
+            vals[8 + i] = gn_ss[i];
+          }
+#pragma unroll
+          for (int w = 8, m = 16; w >= 1; w >>= 1, m >>= 1) {
+            const bool up = (lane & m) != 0;
+#pragma unroll
+            for (int i = 0; i < w; ++i) {
+              const float send = up ? vals[i] : vals[i + w];
+              const float keep = up ? vals[i + w] : vals[i];
+              vals[i] = keep + __shfl_xor_sync(0xffffffffu, send, m);
+            }
+          }
+          const float total = vals[0] + __shfl_xor_sync(0xffffffffu, vals[0], 1);
+          if ((lane & 1) == 0) {
+            const int k = lane >> 1;
+            const int img = m_warp / p.gn_hw;
+            const int chunk = n_warp / GN_CHUNK + (k & 7);
+            unsigned long long hi, lo;
+            gn_fixed_split(total, hi, lo);
+            unsigned long long* a = p.gn_acc + ((size_t)img * (p.N / GN_CHUNK) + chunk) * 4 + (k >> 3) * 2;
+            atomicAdd(a, hi);
+            atomicAdd(a + 1, lo);
+          }
         }
-#endif
+        fence_proxy_async_smem();  // this thread's staging writes -> visible to the TMA store
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&stg_full[sb]);  // the store warp issues the TMA stores when all 4 * NG warps arrived
         ++ot;
       } else {
         // ---- scalar fallback (conv_out: N = 4): thread <-> row, direct stores; only the cg == 0 warps work
@@ -788,7 +827,67 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
         release_acc(acc);
       }
     }
-    if (storer) bulk_wait0();  // every TMA store of this CTA has completed before its shared memory goes away
+  } else {
+    // =================================== store warp ===================================
+    // Walks the output-producing work items of this CTA in order.  Item o uses staging buffer o & 1:
+    //   [residual of item o TMA-loaded into it] -> epilogue warps turn it into the output tile -> stg_full[o & 1]
+    //   -> TMA stores -> (reads done) -> residual of item o + 2 loaded into the same buffer, or stg_free[o & 1] raised.
+    // The bulk async-groups belong to this thread, so only this thread ever waits for a store.
+    if (p.epi_tma && RCDM_GEMM_EXPERIMENT != 5 && RCDM_GEMM_EXPERIMENT != 9 && elect_one()) {
+      const bool has_res = p.res != nullptr && RCDM_GEMM_EXPERIMENT != 6;
+      const int n_total = p.geglu ? p.N / 2 : p.N;
+      const int wcols = p.geglu ? Cfg::QW / 2 : Cfg::QW;
+      const int tile_cols = p.geglu ? BN / 2 : BN;
+      constexpr int NG = Cfg::NG;
+      auto issue_residual = [&](int t, int o) {  // residual tile of output item o (tile index t) -> staging[o & 1]
+        const int nt = t % p.num_n_tiles;
+        const int mt = PAIR ? 2 * (t / p.num_n_tiles) + (int)rank : t / p.num_n_tiles;
+        const int b = o & 1;
+        int parts = 0;
+        for (int g = 0; g < NG; ++g) parts += (nt * BN + g * Cfg::QW) < p.N;
+        mbar_expect_tx(&res_full[b], parts * Cfg::PART_BYTES);
+        for (int g = 0; g < parts; ++g)
+          tma_load_2d(staging + b * Cfg::STG_BYTES + g * Cfg::PART_BYTES, &maps.r, &res_full[b], nt * BN + g * Cfg::QW,
+                      mt * 128);
+      };
+      GemmWork work(p, wid, nworkers);
+      GemmWork peek(p, wid, nworkers);  // runs two output items ahead of `work`
+      int pt, pk0, pk1;
+      auto next_output = [&](GemmWork& w, int& t) {  // next work item that produces an output tile (kb0 == 0)
+        int k0, k1;
+        while (w.next(t, k0, k1))
+          if (k0 == 0) return true;
+        return false;
+      };
+      (void)pk0;
+      (void)pk1;
+      bool have_peek = next_output(peek, pt);
+      if (has_res && have_peek) issue_residual(pt, 0);
+      if (have_peek) have_peek = next_output(peek, pt);
+      if (has_res && have_peek) issue_residual(pt, 1);
+      int tile;
+      for (int o = 0; next_output(work, tile); ++o) {
+        const int n_tile = tile % p.num_n_tiles;
+        const int m_tile = PAIR ? 2 * (tile / p.num_n_tiles) + (int)rank : tile / p.num_n_tiles;
+        const int sb = o & 1;
+        mbar_wait(&stg_full[sb], (o >> 1) & 1);
+#if RCDM_GEMM_EXPERIMENT != 6
+        for (int g = 0; g < NG; ++g)
+          if (n_tile * tile_cols + g * wcols < n_total)
+            tma_store_2d(&maps.o, staging + sb * Cfg::STG_BYTES + g * Cfg::PART_BYTES, n_tile * tile_cols + g * wcols,
+                         m_tile * 128);
+        bulk_commit();
+        bulk_wait_read0();  // the buffer may be refilled
+#endif
+        if (have_peek) have_peek = next_output(peek, pt);  // item o + 2
+        if (has_res) {
+          if (have_peek) issue_residual(pt, o + 2);
+        } else {
+          mbar_arrive(&stg_free[sb]);
+        }
+      }
+      bulk_wait0();  // every TMA store of this CTA has completed before its shared memory goes away
+    }
   }
   tc_fence_before();
   __syncwarp();

@@ -32,6 +32,7 @@ struct GnLaunch {
   int fused, cps, cache_rows, fthreads, fgrid, fk;
   size_t fsmem;
   int rows_per_cta_2k;  // rows_per_cta of the two-kernel path (a.rows_per_cta is the fused value when fused)
+  int from_stats;       // 1: statistics come from the producing GEMMs' epilogues -> gn_apply_stats_kernel alone
 };
 int num_sms();
 bool gn_setup_attributes(std::string* err);
@@ -39,6 +40,10 @@ size_t gn_scratch_bytes(int nstat, int groups);
 // scratch must be zero-initialised once (the kernels leave the counters zero)
 void gn_configure(GnLaunch* l, int dt, const void* x0, int C0, const void* x1, int C1, int rows, int rows_per_stat,
                   int groups, float eps, const float* gamma, const float* beta, void* out, int silu, void* scratch);
+// statistics from the producers' epilogue accumulators (acc1 / C1 = 0: single tensor); hw = rows per image
+void gn_configure_from_stats(GnLaunch* l, int dt, const void* x0, int C0, const unsigned long long* acc0, const void* x1,
+                             int C1, const unsigned long long* acc1, int rows, int rows_per_stat, int hw, int groups,
+                             float eps, const float* gamma, const float* beta, void* out, int silu);
 void gn_run(const GnLaunch& l, cudaStream_t s);
 bool ln_run(int dt, const void* x, void* out, const float* gamma, const float* beta, int rows, int C, float eps,
             const float* pe, int rows_per_frame, int frames, cudaStream_t s);

@@ -103,13 +103,20 @@ struct GemmDesc {
   int stats_parts, ln_frames, ln_rows_per_frame;
   const float* ln_c;
   float ln_eps;
+  // GroupNorm statistics of the output from the epilogue (see GemmParams::gn_acc); requires N % 160 == 0, M % 128 == 0,
+  // gn_hw % 32 == 0 (gemm_gn_stats_ok)
+  unsigned long long* gn_acc;
+  int gn_hw;
 };
+bool gemm_gn_stats_ok(int M, int N, int hw);  // can a GEMM / conv with this output shape emit GroupNorm statistics?
+inline size_t gemm_gn_acc_bytes(int n_img, int N) { return (size_t)n_img * (N / GN_CHUNK) * 4 * sizeof(unsigned long long); }
 struct GemmLaunch {
   GemmMaps maps;
   GemmParams p;
   dim3 grid;
   int bn, dt;
   int pair;  // 1 = CTA-pair kernel (cluster of 2, 256-row tiles)
+  int gn;    // 1 = the epilogue also emits GroupNorm chunk statistics
 };
 bool gemm_prepare(const GemmDesc& d, GemmLaunch* l, std::string* err);
 void gemm_launch(const GemmLaunch& l, cudaStream_t s);

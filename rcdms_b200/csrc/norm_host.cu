@@ -85,6 +85,46 @@ void gn_configure(GnLaunch* l, int dt, const void* x0, int C0, const void* x1, i
   }
 }
 
+void gn_configure_from_stats(GnLaunch* l, int dt, const void* x0, int C0, const unsigned long long* acc0, const void* x1,
+                             int C1, const unsigned long long* acc1, int rows, int rows_per_stat, int hw, int groups,
+                             float eps, const float* gamma, const float* beta, void* out, int silu) {
+  memset(l, 0, sizeof *l);
+  GnArgs& a = l->a;
+  const int C = C0 + C1;
+  a.x0 = x0;
+  a.x1 = x1;
+  a.C0 = C0;
+  a.C1 = C1;
+  a.groups = groups;
+  a.rows_per_stat = rows_per_stat;
+  a.nstat = rows / rows_per_stat;
+  a.eps = eps;
+  a.gamma = gamma;
+  a.beta = beta;
+  a.out = out;
+  a.silu = silu;
+  a.acc0 = acc0;
+  a.acc1 = acc1;
+  a.hw = hw;
+  // pure streaming pass: ~8 CTAs per SM in flight; a CTA's rows lie inside one statistic batch
+  int target = (num_sms() * 8) / a.nstat;
+  if (target < 1) target = 1;
+  int chunks = 1;
+  for (int c = target; c >= 1; --c)
+    if (rows_per_stat % c == 0 && rows_per_stat / c >= 4) {
+      chunks = c;
+      break;
+    }
+  a.rows_per_cta = rows_per_stat / chunks;
+  const int vecs = C / 8;
+  int k = (256 + vecs - 1) / vecs;  // >= 8 * groups threads for the statistics prologue
+  while (vecs * k < 8 * groups) ++k;
+  l->threads = (vecs * k + 31) / 32 * 32;
+  l->grid = dim3(chunks, a.nstat);
+  l->dt = dt;
+  l->from_stats = 1;
+}
+
 bool gn_setup_attributes(std::string* err) {
   cudaError_t e = cudaSuccess;
   if (e == cudaSuccess)
@@ -99,6 +139,12 @@ bool gn_setup_attributes(std::string* err) {
 }
 
 void gn_run(const GnLaunch& l, cudaStream_t s) {
+  if (l.from_stats) {
+    if (l.dt == DT_F16) launch_k(gn_apply_stats_kernel<__half>, l.grid, dim3(l.threads), 0, s, l.a);
+    else launch_k(gn_apply_stats_kernel<__nv_bfloat16>, l.grid, dim3(l.threads), 0, s, l.a);
+    g_launches += 1;
+    return;
+  }
   if (l.fused) {
     if (l.dt == DT_F16)
       launch_k(gn_fused_kernel<__half>, dim3(l.fgrid), dim3(l.fthreads), l.fsmem, s, l.a, l.cps, l.cache_rows, l.fk);

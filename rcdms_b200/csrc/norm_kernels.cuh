@@ -7,6 +7,7 @@
 // motion_module.py:226,232) followed by `x + pe[:, :f]` (motion_module.py:264-267).
 #pragma once
 #include "common.cuh"
+#include "gemm_tcgen05.cuh"  // gn_fixed_join, GN_CHUNK
 
 namespace rcdm {
 
@@ -26,6 +27,11 @@ struct GnArgs {
   const float* beta;   // [C]
   void* out;           // [rows, C]
   int silu;
+  // statistics from the producing GEMMs' epilogues (gn_apply_stats_kernel): per-tensor fixed-point accumulators
+  // [image][C_tensor / 10][4] (GemmParams::gn_acc), `hw` rows per image
+  const unsigned long long* acc0;
+  const unsigned long long* acc1;
+  int hw;
 };
 
 // grid (chunks, nstat); block = vecs * k threads, vecs = C/8; thread owns 8 fixed channels.
@@ -185,6 +191,88 @@ __global__ void gn_apply_kernel(const GnArgs a) {
     for (int u = 0; u < 4; ++u) emit(raw[u], row0 + r + u * k);
   }
   for (; r < a.rows_per_cta; r += k) emit(__ldg(reinterpret_cast<const uint4*>(src + (row0 + r) * ld + cc)), row0 + r);
+}
+
+// GroupNorm apply with the statistics taken from the PRODUCING GEMMs' epilogues (gemm_tcgen05.cuh, GN = true): no
+// statistics pass over the tensor and no grid barrier - one streaming read + one write at full occupancy.
+// Prologue (per CTA): 8 lanes per group fold the 10-channel chunk accumulators of the group (over the frames of the
+// statistic batch and across the two tensors of an un-materialised skip concat) in double precision, in a fixed order,
+// into mean / rstd.  Same CTA / thread geometry as gn_apply_kernel; blockDim.x >= 8 * groups.
+template <typename T>
+__global__ void gn_apply_stats_kernel(const GnArgs a) {
+  __shared__ float2 gstat[64];
+  const int C = a.C0 + a.C1;
+  const int vecs = C / 8;
+  const int k = blockDim.x / vecs;
+  const int v = threadIdx.x % vecs;
+  const int rl = threadIdx.x / vecs;
+  const int chunk = blockIdx.x, sb = blockIdx.y;
+  const int cpg = C / a.groups;
+  pdl_sync();
+  {
+    const int g = threadIdx.x >> 3, sub = threadIdx.x & 7;
+    if (g < a.groups) {  // whole warps: 8 * groups is a multiple of 32
+      const int frames = a.rows_per_stat / a.hw;
+      const int npg = cpg / 10, first = g * npg, n0 = a.C0 / 10, n1 = a.C1 / 10;
+      double s = 0.0, ss = 0.0;
+      for (int idx = sub; idx < frames * npg; idx += 8) {
+        const int f = idx / npg, j = first + idx - f * npg;
+        const size_t img = (size_t)sb * frames + f;
+        const unsigned long long* q = j < n0 ? a.acc0 + (img * n0 + j) * 4 : a.acc1 + (img * n1 + (j - n0)) * 4;
+        const ulonglong2 sum = __ldcg(reinterpret_cast<const ulonglong2*>(q));        // (hi, lo) of the sum
+        const ulonglong2 sq = __ldcg(reinterpret_cast<const ulonglong2*>(q) + 1);     // (hi, lo) of the sum of squares
+        s += gn_fixed_join(sum.x, sum.y);
+        ss += gn_fixed_join(sq.x, sq.y);
+      }
+#pragma unroll
+      for (int o = 4; o > 0; o >>= 1) {
+        s += __shfl_xor_sync(0xffffffffu, s, o);
+        ss += __shfl_xor_sync(0xffffffffu, ss, o);
+      }
+      if (sub == 0) {
+        const double n = (double)a.rows_per_stat * cpg;
+        const double mean = s / n;
+        double var = ss / n - mean * mean;
+        if (var < 0) var = 0;
+        gstat[g] = make_float2((float)mean, (float)(1.0 / sqrt(var + (double)a.eps)));
+      }
+    }
+  }
+  __syncthreads();
+  if (rl >= k) return;
+  const int c = v * 8;
+  float sc[8], sh[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float2 st = gstat[(c + i) / cpg];
+    const float g = __ldg(a.gamma + c + i);
+    sc[i] = st.y * g;
+    sh[i] = __ldg(a.beta + c + i) - st.x * st.y * g;
+  }
+  const T* src = reinterpret_cast<const T*>(c < a.C0 ? a.x0 : a.x1);
+  const int ld = c < a.C0 ? a.C0 : a.C1;
+  const int cc = c < a.C0 ? c : c - a.C0;
+  const size_t row0 = (size_t)sb * a.rows_per_stat + (size_t)chunk * a.rows_per_cta;
+  T* dst = reinterpret_cast<T*>(a.out);
+  auto emit = [&](const uint4& raw, size_t row) {
+    float f[8];
+    unpack8<T>(raw, f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float y = fmaf(f[i], sc[i], sh[i]);
+      f[i] = a.silu ? silu_f(y) : y;
+    }
+    __stcg(reinterpret_cast<uint4*>(dst + row * C + c), pack8<T>(f));
+  };
+  int r = rl;
+  for (; r + 3 * k < a.rows_per_cta; r += 4 * k) {
+    uint4 raw[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) raw[u] = __ldcg(reinterpret_cast<const uint4*>(src + (row0 + r + u * k) * ld + cc));
+#pragma unroll
+    for (int u = 0; u < 4; ++u) emit(raw[u], row0 + r + u * k);
+  }
+  for (; r < a.rows_per_cta; r += k) emit(__ldcg(reinterpret_cast<const uint4*>(src + (row0 + r) * ld + cc)), row0 + r);
 }
 
 // ------------------------------------------------------------------------------------------

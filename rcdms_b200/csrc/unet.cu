@@ -401,9 +401,11 @@ static void finalize_weights(rcdm_unet_impl* h, cudaStream_t st) {
 // ==========================================================================================
 // plan
 // ==========================================================================================
+constexpr size_t NO_GN = ~size_t(0);
 struct Act {
   size_t off = 0;
   int C = 0, H = 0, W = 0;
+  size_t gn = NO_GN;  // workspace offset of this tensor's GroupNorm chunk accumulators (written by its producer's epilogue)
 };
 
 struct Planner {
@@ -415,6 +417,17 @@ struct Planner {
   std::string err;
   bool failed = false;
   size_t gn_scratch = 0;  // persistent scratch for GroupNorm (counters stay zero between launches)
+  // GroupNorm statistics from the producers' epilogues: one accumulator block per normalised tensor, all inside one
+  // region that the first op of a step zeroes (sized by the dry pass)
+  size_t gn_region = 0, gn_used = 0;
+  bool gn_stats_on() const { return h->gn_stats && !h->simple; }
+  size_t new_gn(int C, int H, int W) {
+    if (!gn_stats_on() || !gemm_gn_stats_ok(h->B * h->F * H * W, C, H * W)) return NO_GN;
+    const size_t off = gn_region + gn_used;
+    gn_used += (gemm_gn_acc_bytes(h->B * h->F, C) + 255) & ~size_t(255);
+    return off;
+  }
+  unsigned long long* gnp(size_t off) const { return reinterpret_cast<unsigned long long*>(h->ws + off); }
 
   size_t alloc(size_t bytes) {
     bytes = (bytes + 1023) & ~size_t(1023);
@@ -581,9 +594,13 @@ struct Planner {
   // produced the input); emit_stats: this GEMM's output feeds a folded LayerNorm -> write its row statistics
   void linear(size_t a_off, int M, int K, const Mat& w, const Vec* bias, size_t out_off, int ldo, const size_t* res_off,
               int geglu = 0, const LnFold* ln = nullptr, size_t stats_off = 0, bool emit_stats = false,
-              int rows_per_frame = 1) {
+              int rows_per_frame = 1, size_t gn_off = NO_GN, int gn_hw = 0) {
     GemmDesc d;
     memset(&d, 0, sizeof d);
+    if (gn_off != NO_GN) {
+      d.gn_acc = gnp(gn_off);
+      d.gn_hw = gn_hw;
+    }
     d.M = M;
     d.N = w.rows;
     d.nseg = 1;
@@ -615,10 +632,20 @@ struct Planner {
     if (dry || failed) return;
     const int hw = x0.H * x0.W;
     GnLaunch l;
+    // algorithmic bytes: one read + one write of the tensor
+    const double bytes = 2.0 * rows(x0) * (x0.C + (x1 ? x1->C : 0)) * 2.0;
+    if (x0.gn != NO_GN && (!x1 || x1->gn != NO_GN)) {
+      // statistics were emitted by the producing GEMMs' epilogues: one streaming normalise (+SiLU) pass
+      gn_configure_from_stats(&l, h->dt, p(x0.off), x0.C, gnp(x0.gn), x1 ? p(x1->off) : nullptr, x1 ? x1->C : 0,
+                              x1 ? gnp(x1->gn) : nullptr, rows(x0), per_frame ? hw : h->F * hw, hw,
+                              h->cfg.norm_num_groups, eps, wv(g), wv(b), p(out_off), silu ? 1 : 0);
+      push([l](cudaStream_t s) { gn_run(l, s); }, "groupnorm", 0.0, bytes);
+      return;
+    }
     gn_configure(&l, h->dt, p(x0.off), x0.C, x1 ? p(x1->off) : nullptr, x1 ? x1->C : 0, rows(x0),
                  per_frame ? hw : h->F * hw, h->cfg.norm_num_groups, eps, wv(g), wv(b), p(out_off), silu ? 1 : 0,
                  p(gn_scratch));
-    push([l](cudaStream_t s) { gn_run(l, s); }, "groupnorm", 0.0, 3.0 * rows(x0) * (x0.C + (x1 ? x1->C : 0)) * 2.0);
+    push([l](cudaStream_t s) { gn_run(l, s); }, "groupnorm", 0.0, bytes);
   }
   void layernorm(size_t x_off, size_t out_off, int nrows, int C, const Vec& g, const Vec& b, const Vec* pe,
                  int rows_per_frame) {
@@ -675,9 +702,14 @@ struct Planner {
     Act n = new_act(cin, in0.H, in0.W);
     groupnorm(in0, in1, r.n1g, r.n1b, h->cfg.norm_eps, false, true, n.off);
     Act h1 = new_act(r.cout, in0.H, in0.W);
+    h1.gn = new_gn(r.cout, in0.H, in0.W);
     {
       GemmDesc d;
       memset(&d, 0, sizeof d);
+      if (h1.gn != NO_GN) {
+        d.gn_acc = gnp(h1.gn);
+        d.gn_hw = in0.H * in0.W;
+      }
       d.M = M;
       d.N = r.cout;
       d.nseg = 1;
@@ -698,9 +730,14 @@ struct Planner {
     groupnorm(h1, nullptr, r.n2g, r.n2b, h->cfg.norm_eps, false, true, n2.off);
     free_act(h1);
     Act out = new_act(r.cout, in0.H, in0.W);
+    out.gn = new_gn(r.cout, in0.H, in0.W);
     {
       GemmDesc d;
       memset(&d, 0, sizeof d);
+      if (out.gn != NO_GN) {
+        d.gn_acc = gnp(out.gn);
+        d.gn_hw = in0.H * in0.W;
+      }
       d.M = M;
       d.N = r.cout;
       d.nseg = 1;
@@ -728,7 +765,7 @@ struct Planner {
   }
 
   // Transformer3DModel + BasicTransformerBlock (attention.py:318-365, 479-526); x updated in place
-  void transformer(const Act& x, const TfW& t, size_t kv_off) {
+  void transformer(Act& x, const TfW& t, size_t kv_off) {
     const int C = t.C, M = rows(x), HW = x.H * x.W, NI = h->B * h->F;
     const int heads = h->cfg.attention_heads, d = C / heads;
     Act n = new_act(C, x.H, x.W);
@@ -806,13 +843,14 @@ struct Planner {
     linear(g.off, M, 4 * C, t.ff2, &t.ff2b, y.off, C, &y.off);
     free_act(g);
     free_act(tmp);
-    linear(y.off, M, C, t.po, &t.pob, x.off, C, &x.off);
+    x.gn = new_gn(C, x.H, x.W);  // x is rewritten in place: its statistics are new
+    linear(y.off, M, C, t.po, &t.pob, x.off, C, &x.off, 0, nullptr, 0, false, 1, x.gn, HW);
     free_act(y);
     if (fold) release(st, st_bytes);
   }
 
   // VanillaTemporalModule (motion_module.py:87-93,147-182,234-246,294-354); x updated in place
-  void motion(const Act& x, const MoW& m) {
+  void motion(Act& x, const MoW& m) {
     const int C = m.C, M = rows(x), HW = x.H * x.W;
     const int heads = h->cfg.motion_heads, d = C / heads;
     Act n = new_act(C, x.H, x.W);
@@ -854,15 +892,21 @@ struct Planner {
     linear(g.off, M, 4 * C, m.ff2, &m.ff2b, y.off, C, &y.off);
     free_act(g);
     free_act(tmp);
-    linear(y.off, M, C, m.po, &m.pob, x.off, C, &x.off);
+    x.gn = new_gn(C, x.H, x.W);
+    linear(y.off, M, C, m.po, &m.pob, x.off, C, &x.off, 0, nullptr, 0, false, 1, x.gn, HW);
     free_act(y);
     if (fold) release(st, st_bytes);
   }
 
   Act conv_sampler(const Act& x, const Mat& w, const Vec& b, int stride, int Ho, int Wo) {
     Act out = new_act(w.rows, Ho, Wo);
+    out.gn = new_gn(w.rows, Ho, Wo);
     GemmDesc d;
     memset(&d, 0, sizeof d);
+    if (out.gn != NO_GN) {
+      d.gn_acc = gnp(out.gn);
+      d.gn_hw = Ho * Wo;
+    }
     d.M = rows(out);
     d.N = w.rows;
     d.nseg = 1;
@@ -889,6 +933,8 @@ static int plan_network(rcdm_unet_impl* h, bool dry, size_t* peak) {
   // ---- persistent regions
   const size_t gn_bytes = gn_scratch_bytes(NI, c.norm_num_groups);
   P.gn_scratch = P.alloc(gn_bytes);
+  const size_t gn_region_bytes = dry ? 0 : h->gn_acc_bytes;  // measured by the dry pass
+  P.gn_region = gn_region_bytes ? P.alloc(gn_region_bytes) : 0;
   const int c0 = c.block_out_channels[0];
   const size_t e1 = P.alloc((size_t)h->temb_dim * 4), e2 = P.alloc((size_t)h->temb_dim * 4);
   const size_t ctx16 = P.alloc((size_t)NI * h->L * c.cross_attention_dim * 2);
@@ -932,6 +978,10 @@ static int plan_network(rcdm_unet_impl* h, bool dry, size_t* peak) {
 
   // ---- step ops
   P.ops = &h->step_ops;
+  if (!dry && gn_region_bytes) {  // GroupNorm chunk accumulators of every normalised tensor: zero at the start of a step
+    void* reg = P.p(P.gn_region);
+    P.push([=](cudaStream_t s) { cudaMemsetAsync(reg, 0, gn_region_bytes, s); });
+  }
   if (!dry) {
     float* e1p = reinterpret_cast<float*>(P.p(e1));
     float* e2p = reinterpret_cast<float*>(P.p(e2));
@@ -986,7 +1036,8 @@ static int plan_network(rcdm_unet_impl* h, bool dry, size_t* peak) {
         g_launches++;
       });
     }
-    P.linear(a_off, M, kpad, h->conv_in_w, &h->conv_in_b, x.off, c0, nullptr);
+    x.gn = P.new_gn(c0, h->H, h->W);
+    P.linear(a_off, M, kpad, h->conv_in_w, &h->conv_in_b, x.off, c0, nullptr, 0, nullptr, 0, false, 1, x.gn, h->H * h->W);
     P.release(a_off, (size_t)M * kpad * 2);
   }
   P.tap("conv_in", x);
@@ -1128,7 +1179,9 @@ static int plan_network(rcdm_unet_impl* h, bool dry, size_t* peak) {
     P.free_act(o);
   }
   if (P.failed) return set_err("plan: " + P.err);
-  *peak = P.peak;
+  if (dry) h->gn_acc_bytes = P.gn_used;
+  else if (P.gn_used != h->gn_acc_bytes) return set_err("plan: GroupNorm accumulator region changed between passes");
+  *peak = P.peak + (dry ? h->gn_acc_bytes + 1024 : 0);
   return 0;
 }
 
@@ -1137,7 +1190,8 @@ int unet_create(const rcdm_unet_config* cfg, rcdm_unet** out) {
   rcdm_unet* h = new rcdm_unet();
   h->cfg = *cfg;
   // debug switches (rcdm_unet_set_option before rcdm_unet_prepare): simple = 0, autotune = 0 (measured: no gain over the
-  // heuristics at the 512x512 shapes), ln_fold = 1
+  // heuristics at the 512x512 shapes), ln_fold = 1, gn_stats = library option at creation time
+  h->gn_stats = opt(OPT_GN_STATS);
   if (build_model(h)) {
     delete h;
     return 1;

@@ -229,3 +229,30 @@ def unclip_cfg_step(pred: torch.Tensor, latents: torch.Tensor, noise_table: torc
                                                int(do_cfg), float(guidance_scale), step.data_ptr(), int(advance),
                                                _lib.current_stream_ptr()))
     return latents
+
+
+def linear_gnstats(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], residual: Optional[torch.Tensor],
+                   hw: int):
+    """linear() whose epilogue also accumulates the GroupNorm chunk statistics of its output.
+    Returns (out [M, N], acc uint8 buffer for group_norm_from_stats)."""
+    M, K = a.shape
+    N = w.shape[0]
+    L = _lib.lib()
+    out = torch.empty((M, N), dtype=a.dtype, device=a.device)
+    acc = torch.zeros((L.rcdm_gn_acc_bytes(M // hw, N),), dtype=torch.uint8, device=a.device)
+    _lib.check(L.rcdm_gemm_gnstats(_dt16(a), a.data_ptr(), w.data_ptr(), _ptr(bias), _ptr(residual), out.data_ptr(), M, N,
+                                   K, hw, acc.data_ptr(), _lib.current_stream_ptr()))
+    return out, acc
+
+
+def group_norm_from_stats(x0: torch.Tensor, acc0: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, groups: int,
+                          rows_per_stat: int, hw: int, eps: float, silu: bool, x1: Optional[torch.Tensor] = None,
+                          acc1: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """GroupNorm(+SiLU) of the virtual concat [x0 | x1] from the producers' statistics (one streaming pass)."""
+    rows, C0 = x0.shape
+    C1 = x1.shape[1] if x1 is not None else 0
+    out = torch.empty((rows, C0 + C1), dtype=x0.dtype, device=x0.device)
+    _lib.check(_lib.lib().rcdm_groupnorm_from_stats(_dt16(x0), x0.data_ptr(), C0, acc0.data_ptr(), _ptr(x1), C1, _ptr(acc1),
+                                                    gamma.data_ptr(), beta.data_ptr(), out.data_ptr(), rows, rows_per_stat,
+                                                    hw, groups, eps, int(silu), _lib.current_stream_ptr()))
+    return out

@@ -103,6 +103,41 @@ def check_groupnorm(nstat, rows_per_stat, C, dtype, silu=True, eps=1e-5, seed=3)
     return _result(f"groupnorm nstat{nstat} rows{rows_per_stat} C{C} silu{int(silu)}", out, ref, dtype, rtol_mul=2.0)
 
 
+def check_groupnorm_from_stats(n_img, hw, frames_per_stat, C0, C1, K, dtype, silu=True, eps=1e-5, residual=False, seed=11):
+    """Two GEMMs write x0 [rows, C0] / x1 [rows, C1] and emit their GroupNorm chunk statistics from the epilogue; the
+    streaming apply kernel normalises the virtual concat.  Reference: F.group_norm of the GEMM OUTPUTS (as stored, i.e.
+    rounded) over (frames_per_stat * hw) rows per statistic batch."""
+    g = _gen(seed)
+    rows = n_img * hw
+    outs, accs = [], []
+    for C in (C0, C1):
+        if C == 0:
+            continue
+        a = _rand((rows, K), dtype, g)
+        w = _rand((C, K), dtype, g, 1.0 / math.sqrt(K))
+        b = torch.randn((C,), generator=g, device="cuda") * 0.5 + 0.3
+        r = _rand((rows, C), dtype, g) if residual else None
+        o, acc = ops.linear_gnstats(a, w, b, r, hw)
+        ref_o = a.float() @ w.float().t() + b + (r.float() if residual else 0)
+        assert (o.float() - ref_o).abs().max().item() < 0.1 * ref_o.abs().max().item()
+        outs.append(o)
+        accs.append(acc)
+    C = C0 + C1
+    gamma = 1 + 0.2 * torch.randn((C,), generator=g, device="cuda")
+    beta = 0.2 * torch.randn((C,), generator=g, device="cuda")
+    rps = frames_per_stat * hw
+    out = ops.group_norm_from_stats(outs[0], accs[0], gamma, beta, 32, rps, hw, eps, silu,
+                                    outs[1] if C1 else None, accs[1] if C1 else None)
+    x = torch.cat([o.float() for o in outs], dim=1)
+    xr = x.reshape(rows // rps, rps, C).permute(0, 2, 1)
+    ref = F.group_norm(xr, 32, gamma, beta, eps)
+    if silu:
+        ref = F.silu(ref)
+    ref = ref.permute(0, 2, 1).reshape(rows, C)
+    return _result(f"groupnorm_from_stats img{n_img} hw{hw} fps{frames_per_stat} C{C0}+{C1} silu{int(silu)} r{int(residual)}",
+                   out, ref, dtype, rtol_mul=2.0)
+
+
 def check_layernorm(rows, C, dtype, pe=False, seed=4):
     g = _gen(seed)
     x = _rand((rows, C), dtype, g) * 1.5 + 0.3
@@ -271,6 +306,15 @@ def all_op_checks(dtypes=(torch.float16, torch.bfloat16), quick=False):
                                    (16, 4096, 320, False), (160, 64, 1280, True), (1, 7, 64, True)]:
             yield lambda a=(ns, rps, C), silu=silu, dt=dt: check_groupnorm(*a, dt, silu=silu,
                                                                            eps=1e-5 if silu else 1e-6)
+        # statistics from the producing GEMMs' epilogues + streaming apply: (images, hw, frames per statistic, C0, C1, K)
+        #   resnet norms span the 5 frames (and an un-materialised skip concat whose groups straddle the two tensors:
+        #   1280 + 640 -> groups of 60, 640 + 320 -> groups of 30); transformer / motion norms are per frame
+        for (ni, hw, fps, c0, c1, K, silu, rs) in [(10, 64, 5, 320, 0, 64, True, False), (10, 256, 1, 320, 0, 320, False, True),
+                                                  (10, 1024, 5, 640, 320, 64, True, True), (10, 64, 5, 1280, 640, 128, True, False),
+                                                  (10, 4096, 5, 320, 320, 64, True, False), (10, 4096, 1, 320, 0, 64, False, True),
+                                                  (20, 64, 5, 1280, 1280, 64, True, True), (10, 256, 1, 1280, 0, 64, False, False)]:
+            yield lambda a=(ni, hw, fps, c0, c1, K), silu=silu, rs=rs, dt=dt: check_groupnorm_from_stats(
+                *a, dt, silu=silu, eps=1e-5 if silu else 1e-6, residual=rs)
         for (rows, C, pe) in [(640, 320, False), (640, 320, True), (100, 64, True), (2560, 1280, True),
                               (1000, 640, False), (77, 256, False)]:
             yield lambda a=(rows, C, pe), dt=dt: check_layernorm(a[0], a[1], dt, pe=a[2])

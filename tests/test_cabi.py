@@ -39,7 +39,8 @@ def test_no_torch_or_cuda_runtime_dependency():
     """plain C ABI: the .so must not link libtorch / libc10 (torch types never cross the boundary)"""
     import subprocess
     out = subprocess.run(["ldd", _lib.LIB_PATH], capture_output=True, text=True).stdout
-    assert "torch" not in out and "c10" not in out and "libcuda.so" not in out, out
+    names = [ln.split()[0] for ln in out.splitlines() if ln.strip()]  # library names only (load addresses are random hex)
+    assert not [n for n in names if "torch" in n or "libc10" in n or "libcuda.so" in n], out
 
 
 def _create(lib, cfg):
