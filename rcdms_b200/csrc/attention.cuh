@@ -339,6 +339,24 @@ flash_attn_kernel(const __grid_constant__ AttnMaps maps, const AttnParams p) {
 //     instead of 8) and their exp / TMEM-load / barrier phases interleave on the MUFU pipe
 //   * the rare re-reference pass works from the registers (no second TMEM read of S)
 // ------------------------------------------------------------------------------------------
+// 2^x on the FMA / ALU pipes (no MUFU): Cody-Waite split x = floor(x) + f by a round-down add of 1.5 * 2^23 (floor(x)
+// lands in the low mantissa bits), degree-3 minimax polynomial of 2^f on [0, 1) (max relative error 7.5e-5, a third of
+// fp16's half-ulp), exponent patched in with one integer add.  7 FMA/ALU instructions against one quarter-rate MUFU.EX2:
+// the d = 40 softmax is bound by the 16 exp/clk/SM of the MUFU, so a fraction of every row's exponentials
+// (ATTN_POLY_PER8 of each 8) goes through here and the two pipes run side by side (the FlashAttention-4 trick).
+#ifndef RCDM_ATTN_POLY_PER8
+#define RCDM_ATTN_POLY_PER8 3
+#endif
+__device__ __forceinline__ float exp2_poly(float x) {
+  x = fmaxf(x, -126.0f);
+  const float t = __fadd_rd(x, 12582912.0f);
+  const float f = x - (t - 12582912.0f);
+  float p = fmaf(f, 0.07802393287420273f, 0.22606699168682098f);
+  p = fmaf(p, f, 0.6958341598510742f);
+  p = fmaf(p, f, 0.9999250769615173f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+}
+
 template <int DPAD> struct Attn4Cfg {
   static constexpr int BLOCK_M = 128, BLOCK_N = 64;
   static constexpr int NCH = DPAD / 8;
@@ -515,7 +533,15 @@ flash_attn4_kernel(const __grid_constant__ AttnMaps maps, const AttnParams p) {
         for (int g = 0; g < BN / 8; ++g) {
           float pv[8];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) pv[i] = exp2f(fmaf(__uint_as_float(r[g * 8 + i]), sc, -mref));
+          for (int i = 0; i < 8; ++i) {
+            const float x = fmaf(__uint_as_float(r[g * 8 + i]), sc, -mref);
+            // interleave the polynomial elements between the MUFU ones (1, 4, 6, 3 of each 8)
+            constexpr int order[8] = {1, 4, 6, 3, 0, 2, 5, 7};
+            bool poly = false;
+#pragma unroll
+            for (int q = 0; q < RCDM_ATTN_POLY_PER8; ++q) poly |= (order[q] == i);
+            pv[i] = poly ? exp2_poly(x) : exp2f(x);
+          }
           if constexpr (!mma_sum) {
             s0 += pv[0] + pv[4];
             s1 += pv[1] + pv[5];

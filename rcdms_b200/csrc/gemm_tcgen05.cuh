@@ -624,7 +624,9 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
 #pragma unroll
         for (int i = 0; i < GNC; ++i) gn_s[i] = gn_ss[i] = 0.f;
         using T2 = typename DT<T>::T2;
-        auto finish8 = [&](float* v, int c) -> uint4 {  // 8 outputs at columns c.. of this warp's slice; returns them packed
+        // 8 outputs at columns c.. of this warp's slice; returns them packed.  rv_pre: the residual values of these 8
+        // columns when the caller fetched them ahead (see the software pipeline below), else read from the staging row here
+        auto finish8 = [&](float* v, int c, const uint4* rv_pre = nullptr) -> uint4 {
           if constexpr (ACT) {
             if (p.act == 1) {
 #pragma unroll
@@ -637,7 +639,7 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
           uint4 pk = pack8<T>(v);
           uint4* dst = reinterpret_cast<uint4*>(srow + c * 2);
           if (res) {
-            const uint4 rv = *dst;
+            const uint4 rv = rv_pre ? *rv_pre : *dst;
             T2* a2 = reinterpret_cast<T2*>(&pk);
             const T2* b2 = reinterpret_cast<const T2*>(&rv);
 #pragma unroll
@@ -701,62 +703,89 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
             }
           }
         } else if (!p.geglu) {
-          // the TMEM load of chunk c+1 is in flight while chunk c is processed
+          // Software pipeline over steps of 8 columns: the TMEM load of chunk c+1 is in flight while chunk c is processed,
+          // and the shared-memory operands of step s+1 (8 epilogue-vector values, 8 residual values) are requested BEFORE
+          // step s is computed and stored.  (ncu, K = 320 GEMMs: with the loads issued where they are used, every FFMA
+          // waited ~30 cycles on its LDS - the compiler may not hoist a shared load above the preceding staging store -
+          // and the 2 epilogue warps per scheduler could not hide it: 0.2 instructions per cycle.)
+          constexpr int SPC = CW / 8;     // steps per TMEM chunk
+          constexpr int NS = QW / 8;      // steps per tile
           uint32_t r[2][CW];
+          float4 bq[2][2];
+          uint4 rq[2];
+          auto fetch = [&](int st, int slot) {
+            bq[slot][0] = *reinterpret_cast<const float4*>(bsm + st * 8);  // smem broadcast
+            bq[slot][1] = *reinterpret_cast<const float4*>(bsm + st * 8 + 4);
+            if (res) rq[slot] = *reinterpret_cast<const uint4*>(srow + st * 16);
+          };
           ld_chunk(taddr + cg * QW, r[0]);
+          fetch(0, 0);
 #pragma unroll
-          for (int ci = 0; ci < NCH; ++ci) {
-            const int c = ci * CW;
-            tmem_wait_ld();
-            if (ci + 1 < NCH) ld_chunk(taddr + cg * QW + c + CW, r[(ci + 1) & 1]);
-            const uint32_t* rc = r[ci & 1];
-#pragma unroll
-            for (int g = 0; g < CW / 8; ++g) {
-              const float4 b0 = *reinterpret_cast<const float4*>(bsm + c + g * 8);  // smem broadcast
-              const float4 b1 = *reinterpret_cast<const float4*>(bsm + c + g * 8 + 4);
-              float v[8];
-              v[0] = fmaf(__uint_as_float(rc[g * 8]), scale, b0.x);
-              v[1] = fmaf(__uint_as_float(rc[g * 8 + 1]), scale, b0.y);
-              v[2] = fmaf(__uint_as_float(rc[g * 8 + 2]), scale, b0.z);
-              v[3] = fmaf(__uint_as_float(rc[g * 8 + 3]), scale, b0.w);
-              v[4] = fmaf(__uint_as_float(rc[g * 8 + 4]), scale, b1.x);
-              v[5] = fmaf(__uint_as_float(rc[g * 8 + 5]), scale, b1.y);
-              v[6] = fmaf(__uint_as_float(rc[g * 8 + 6]), scale, b1.z);
-              v[7] = fmaf(__uint_as_float(rc[g * 8 + 7]), scale, b1.w);
-              gn_add8(finish8(v, c + g * 8), c + g * 8);
+          for (int st = 0; st < NS; ++st) {
+            const int ci = st / SPC, g = st % SPC;
+            if (g == 0) {
+              tmem_wait_ld();
+              if (ci + 1 < NCH) ld_chunk(taddr + cg * QW + (ci + 1) * CW, r[(ci + 1) & 1]);
             }
+            if (st + 1 < NS) fetch(st + 1, (st + 1) & 1);
+            const uint32_t* rc = r[ci & 1];
+            const float4 b0 = bq[st & 1][0], b1 = bq[st & 1][1];
+            float v[8];
+            v[0] = fmaf(__uint_as_float(rc[g * 8]), scale, b0.x);
+            v[1] = fmaf(__uint_as_float(rc[g * 8 + 1]), scale, b0.y);
+            v[2] = fmaf(__uint_as_float(rc[g * 8 + 2]), scale, b0.z);
+            v[3] = fmaf(__uint_as_float(rc[g * 8 + 3]), scale, b0.w);
+            v[4] = fmaf(__uint_as_float(rc[g * 8 + 4]), scale, b1.x);
+            v[5] = fmaf(__uint_as_float(rc[g * 8 + 5]), scale, b1.y);
+            v[6] = fmaf(__uint_as_float(rc[g * 8 + 6]), scale, b1.z);
+            v[7] = fmaf(__uint_as_float(rc[g * 8 + 7]), scale, b1.w);
+            gn_add8(finish8(v, st * 8, &rq[st & 1]), st * 8);
           }
         } else {
-          // GEGLU: h columns [cg * QW/2, +QW/2), gate columns TH + the same; outputs QW/2 per warp
+          // GEGLU: h columns [cg * QW/2, +QW/2), gate columns TH + the same; outputs QW/2 per warp.  Same software
+          // pipeline: the 16 epilogue-vector values of step s+1 are requested before step s is computed.
           constexpr int GW = QW / 2;
           constexpr int GCW = (GW % 16 == 0) ? 16 : 8;
           constexpr int GNCH = GW / GCW;
+          constexpr int GSPC = GCW / 8, GNS = GW / 8;
           uint32_t rh[2][GCW], rg[2][GCW];
+          float4 bh[2][2], bg[2][2];
           auto ldg_chunk = [&](uint32_t addr, uint32_t* r) {
             if constexpr (GCW == 16) tmem_ld16(addr, r);
             else tmem_ld8(addr, r);
           };
+          auto fetch = [&](int st, int slot) {
+            bh[slot][0] = *reinterpret_cast<const float4*>(bsm + st * 8);
+            bh[slot][1] = *reinterpret_cast<const float4*>(bsm + st * 8 + 4);
+            bg[slot][0] = *reinterpret_cast<const float4*>(bsm + wcols + st * 8);
+            bg[slot][1] = *reinterpret_cast<const float4*>(bsm + wcols + st * 8 + 4);
+          };
           ldg_chunk(taddr + cg * GW, rh[0]);
           ldg_chunk(taddr + TH + cg * GW, rg[0]);
+          fetch(0, 0);
 #pragma unroll
-          for (int ci = 0; ci < GNCH; ++ci) {
-            const int c = ci * GCW;
-            tmem_wait_ld();
-            if (ci + 1 < GNCH) {
-              ldg_chunk(taddr + cg * GW + c + GCW, rh[(ci + 1) & 1]);
-              ldg_chunk(taddr + TH + cg * GW + c + GCW, rg[(ci + 1) & 1]);
+          for (int st = 0; st < GNS; ++st) {
+            const int ci = st / GSPC, g = st % GSPC;
+            if (g == 0) {
+              tmem_wait_ld();
+              if (ci + 1 < GNCH) {
+                ldg_chunk(taddr + cg * GW + (ci + 1) * GCW, rh[(ci + 1) & 1]);
+                ldg_chunk(taddr + TH + cg * GW + (ci + 1) * GCW, rg[(ci + 1) & 1]);
+              }
             }
+            if (st + 1 < GNS) fetch(st + 1, (st + 1) & 1);
             const uint32_t* ph = rh[ci & 1];
             const uint32_t* pg = rg[ci & 1];
+            const float bhv[8] = {bh[st & 1][0].x, bh[st & 1][0].y, bh[st & 1][0].z, bh[st & 1][0].w,
+                                  bh[st & 1][1].x, bh[st & 1][1].y, bh[st & 1][1].z, bh[st & 1][1].w};
+            const float bgv[8] = {bg[st & 1][0].x, bg[st & 1][0].y, bg[st & 1][0].z, bg[st & 1][0].w,
+                                  bg[st & 1][1].x, bg[st & 1][1].y, bg[st & 1][1].z, bg[st & 1][1].w};
+            float v[8];
 #pragma unroll
-            for (int g = 0; g < GCW / 8; ++g) {
-              float v[8];
-#pragma unroll
-              for (int i = 0; i < 8; ++i)
-                v[i] = fmaf(__uint_as_float(ph[g * 8 + i]), scale, bsm[c + g * 8 + i]) *
-                       gelu_erf_f(fmaf(__uint_as_float(pg[g * 8 + i]), scale, bsm[wcols + c + g * 8 + i]));
-              finish8(v, c + g * 8);
-            }
+            for (int i = 0; i < 8; ++i)
+              v[i] = fmaf(__uint_as_float(ph[g * 8 + i]), scale, bhv[i]) *
+                     gelu_erf_f(fmaf(__uint_as_float(pg[g * 8 + i]), scale, bgv[i]));
+            finish8(v, st * 8);
           }
         }
         release_acc(acc);  // accumulator drained: the MMA warp may reuse it

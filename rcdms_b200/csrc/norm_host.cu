@@ -10,8 +10,8 @@ size_t gn_scratch_bytes(int nstat, int groups) {
 
 void gn_configure(GnLaunch* l, int dt, const void* x0, int C0, const void* x1, int C1, int rows, int rows_per_stat,
                   int groups, float eps, const float* gamma, const float* beta, void* out, int silu, void* scratch) {
+  memset(l, 0, sizeof *l);
   GnArgs& a = l->a;
-  memset(&a, 0, sizeof a);
   const int C = C0 + C1;
   a.x0 = x0;
   a.x1 = x1;

@@ -208,21 +208,61 @@ __global__ void gn_apply_stats_kernel(const GnArgs a) {
   const int rl = threadIdx.x / vecs;
   const int chunk = blockIdx.x, sb = blockIdx.y;
   const int cpg = C / a.groups;
+  const bool worker = rl < k;
+  const int c = v * 8;
+  const T* src = reinterpret_cast<const T*>(c < a.C0 ? a.x0 : a.x1);
+  const int ld = c < a.C0 ? a.C0 : a.C1;
+  const int cc = c < a.C0 ? c : c - a.C0;
+  const size_t row0 = (size_t)sb * a.rows_per_stat + (size_t)chunk * a.rows_per_cta;
   pdl_sync();
+  // ---- everything that does not depend on the statistics is requested first, so the L2 round trips of the accumulator
+  // reads, of gamma / beta and of the first rows overlap instead of following one another
+  constexpr int PRE = 4;
+  uint4 raw[PRE];
+  float gam[8], bet[8];
+  if (worker) {
+#pragma unroll
+    for (int u = 0; u < PRE; ++u)
+      if (rl + u * k < a.rows_per_cta) raw[u] = __ldcg(reinterpret_cast<const uint4*>(src + (row0 + rl + u * k) * ld + cc));
+    const float4 g0 = __ldg(reinterpret_cast<const float4*>(a.gamma + c)), g1 = __ldg(reinterpret_cast<const float4*>(a.gamma + c + 4));
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(a.beta + c)), b1 = __ldg(reinterpret_cast<const float4*>(a.beta + c + 4));
+    gam[0] = g0.x, gam[1] = g0.y, gam[2] = g0.z, gam[3] = g0.w, gam[4] = g1.x, gam[5] = g1.y, gam[6] = g1.z, gam[7] = g1.w;
+    bet[0] = b0.x, bet[1] = b0.y, bet[2] = b0.z, bet[3] = b0.w, bet[4] = b1.x, bet[5] = b1.y, bet[6] = b1.z, bet[7] = b1.w;
+  }
   {
     const int g = threadIdx.x >> 3, sub = threadIdx.x & 7;
     if (g < a.groups) {  // whole warps: 8 * groups is a multiple of 32
       const int frames = a.rows_per_stat / a.hw;
       const int npg = cpg / 10, first = g * npg, n0 = a.C0 / 10, n1 = a.C1 / 10;
+      const int total = frames * npg;  // <= 5 frames * 8 chunks: at most 5 accumulators per lane, all loads in flight
+      constexpr int MAXI = 5;
+      ulonglong2 sum[MAXI], sq[MAXI];
+#pragma unroll
+      for (int it = 0; it < MAXI; ++it) {
+        const int idx = sub + it * 8;
+        if (idx < total) {
+          const int f = idx / npg, j = first + idx - f * npg;
+          const size_t img = (size_t)sb * frames + f;
+          const unsigned long long* q = j < n0 ? a.acc0 + (img * n0 + j) * 4 : a.acc1 + (img * n1 + (j - n0)) * 4;
+          sum[it] = __ldcg(reinterpret_cast<const ulonglong2*>(q));      // (hi, lo) of the sum
+          sq[it] = __ldcg(reinterpret_cast<const ulonglong2*>(q) + 1);   // (hi, lo) of the sum of squares
+        }
+      }
       double s = 0.0, ss = 0.0;
-      for (int idx = sub; idx < frames * npg; idx += 8) {
+#pragma unroll
+      for (int it = 0; it < MAXI; ++it)
+        if (sub + it * 8 < total) {
+          s += gn_fixed_join(sum[it].x, sum[it].y);
+          ss += gn_fixed_join(sq[it].x, sq[it].y);
+        }
+      for (int idx = sub + MAXI * 8; idx < total; idx += 8) {  // (more than 5 frames x 8 chunks: not on the RCDMs path)
         const int f = idx / npg, j = first + idx - f * npg;
         const size_t img = (size_t)sb * frames + f;
         const unsigned long long* q = j < n0 ? a.acc0 + (img * n0 + j) * 4 : a.acc1 + (img * n1 + (j - n0)) * 4;
-        const ulonglong2 sum = __ldcg(reinterpret_cast<const ulonglong2*>(q));        // (hi, lo) of the sum
-        const ulonglong2 sq = __ldcg(reinterpret_cast<const ulonglong2*>(q) + 1);     // (hi, lo) of the sum of squares
-        s += gn_fixed_join(sum.x, sum.y);
-        ss += gn_fixed_join(sq.x, sq.y);
+        const ulonglong2 su = __ldcg(reinterpret_cast<const ulonglong2*>(q));
+        const ulonglong2 sv = __ldcg(reinterpret_cast<const ulonglong2*>(q) + 1);
+        s += gn_fixed_join(su.x, su.y);
+        ss += gn_fixed_join(sv.x, sv.y);
       }
 #pragma unroll
       for (int o = 4; o > 0; o >>= 1) {
@@ -234,29 +274,23 @@ __global__ void gn_apply_stats_kernel(const GnArgs a) {
         const double mean = s / n;
         double var = ss / n - mean * mean;
         if (var < 0) var = 0;
-        gstat[g] = make_float2((float)mean, (float)(1.0 / sqrt(var + (double)a.eps)));
+        gstat[g] = make_float2((float)mean, rsqrtf((float)var + a.eps));
       }
     }
   }
   __syncthreads();
-  if (rl >= k) return;
-  const int c = v * 8;
+  if (!worker) return;
   float sc[8], sh[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const float2 st = gstat[(c + i) / cpg];
-    const float g = __ldg(a.gamma + c + i);
-    sc[i] = st.y * g;
-    sh[i] = __ldg(a.beta + c + i) - st.x * st.y * g;
+    sc[i] = st.y * gam[i];
+    sh[i] = bet[i] - st.x * st.y * gam[i];
   }
-  const T* src = reinterpret_cast<const T*>(c < a.C0 ? a.x0 : a.x1);
-  const int ld = c < a.C0 ? a.C0 : a.C1;
-  const int cc = c < a.C0 ? c : c - a.C0;
-  const size_t row0 = (size_t)sb * a.rows_per_stat + (size_t)chunk * a.rows_per_cta;
   T* dst = reinterpret_cast<T*>(a.out);
-  auto emit = [&](const uint4& raw, size_t row) {
+  auto emit = [&](const uint4& rw, size_t row) {
     float f[8];
-    unpack8<T>(raw, f);
+    unpack8<T>(rw, f);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const float y = fmaf(f[i], sc[i], sh[i]);
@@ -264,15 +298,21 @@ __global__ void gn_apply_stats_kernel(const GnArgs a) {
     }
     __stcg(reinterpret_cast<uint4*>(dst + row * C + c), pack8<T>(f));
   };
+  // software pipeline: the next PRE rows are requested before the current PRE are normalised and stored
   int r = rl;
-  for (; r + 3 * k < a.rows_per_cta; r += 4 * k) {
-    uint4 raw[4];
+  while (r < a.rows_per_cta) {
+    uint4 cur[PRE];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) raw[u] = __ldcg(reinterpret_cast<const uint4*>(src + (row0 + r + u * k) * ld + cc));
+    for (int u = 0; u < PRE; ++u) cur[u] = raw[u];
+    const int rn = r + PRE * k;
 #pragma unroll
-    for (int u = 0; u < 4; ++u) emit(raw[u], row0 + r + u * k);
+    for (int u = 0; u < PRE; ++u)
+      if (rn + u * k < a.rows_per_cta) raw[u] = __ldcg(reinterpret_cast<const uint4*>(src + (row0 + rn + u * k) * ld + cc));
+#pragma unroll
+    for (int u = 0; u < PRE; ++u)
+      if (r + u * k < a.rows_per_cta) emit(cur[u], row0 + r + u * k);
+    r = rn;
   }
-  for (; r < a.rows_per_cta; r += k) emit(__ldcg(reinterpret_cast<const uint4*>(src + (row0 + r) * ld + cc)), row0 + r);
 }
 
 // ------------------------------------------------------------------------------------------

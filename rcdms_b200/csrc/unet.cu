@@ -639,13 +639,15 @@ struct Planner {
       gn_configure_from_stats(&l, h->dt, p(x0.off), x0.C, gnp(x0.gn), x1 ? p(x1->off) : nullptr, x1 ? x1->C : 0,
                               x1 ? gnp(x1->gn) : nullptr, rows(x0), per_frame ? hw : h->F * hw, hw,
                               h->cfg.norm_num_groups, eps, wv(g), wv(b), p(out_off), silu ? 1 : 0);
-      push([l](cudaStream_t s) { gn_run(l, s); }, "groupnorm", 0.0, bytes);
+      push([l](cudaStream_t s) { gn_run(l, s); }, "groupnorm", 0.0, bytes, rows(x0), x0.C + (x1 ? x1->C : 0),
+           per_frame ? 1 : h->F);
       return;
     }
     gn_configure(&l, h->dt, p(x0.off), x0.C, x1 ? p(x1->off) : nullptr, x1 ? x1->C : 0, rows(x0),
                  per_frame ? hw : h->F * hw, h->cfg.norm_num_groups, eps, wv(g), wv(b), p(out_off), silu ? 1 : 0,
                  p(gn_scratch));
-    push([l](cudaStream_t s) { gn_run(l, s); }, "groupnorm", 0.0, bytes);
+    push([l](cudaStream_t s) { gn_run(l, s); }, "groupnorm", 0.0, bytes, rows(x0), x0.C + (x1 ? x1->C : 0),
+         per_frame ? -1 : -h->F);  // k < 0: statistics computed by the GroupNorm kernel itself
   }
   void layernorm(size_t x_off, size_t out_off, int nrows, int C, const Vec& g, const Vec& b, const Vec* pe,
                  int rows_per_frame) {
