@@ -406,9 +406,10 @@ flash_attn4_kernel(const __grid_constant__ AttnMaps maps, const AttnParams p) {
         mbar_init(&kv_empty[i], 1);
       }
       mbar_init(s_full, 1);
-      mbar_init(s_free, 128);
-      mbar_init(&p_full[0], 128);
-      mbar_init(&p_full[1], 128);
+      // one arrival per softmax WARP (after a warp sync), not per thread: 128 arrivals serialise on the barrier word
+      mbar_init(s_free, 4);
+      mbar_init(&p_full[0], 4);
+      mbar_init(&p_full[1], 4);
       mbar_init(pv_done, 1);
       mbar_init(o_done, 1);
       fence_mbar_init();
@@ -505,7 +506,8 @@ flash_attn4_kernel(const __grid_constant__ AttnMaps maps, const AttnParams p) {
       tmem_ld32(tmem_S + lane_sel + 32, r + 32);
       tmem_wait_ld();
       tc_fence_before();
-      mbar_arrive(s_free);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(s_free);
       uint8_t* sP_row = sP + (j & 1) * Cfg::P_BYTES + row * 16;
       const int kv_valid = min(BN, p.S_kv - j * BN);
       if (mma_sum && row < BN)  // V tile j has landed (the MMA thread waited for it before S_j): set its ones column
@@ -588,7 +590,8 @@ flash_attn4_kernel(const __grid_constant__ AttnMaps maps, const AttnParams p) {
       }
       fence_proxy_async_smem();
       tc_fence_before();
-      mbar_arrive(&p_full[j & 1]);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full[j & 1]);
     }
     // ---- normalise and store
     mbar_wait(o_done, 0);

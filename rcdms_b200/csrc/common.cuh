@@ -188,6 +188,19 @@ __device__ __forceinline__ void tma_load_5d(void* smem, const CUtensorMap* m, ui
       : "memory");
 }
 
+// TMA prefetch of a tile into L2 (no shared memory, no barrier): hides the HBM latency of a tile that will be loaded later
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* m, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(reinterpret_cast<uint64_t>(m)),
+               "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_4d(const CUtensorMap* m, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+
 // TMA store (tile mode) of a dense shared-memory box to global memory; out-of-range rows / columns are clipped.
 // Bulk-group completion: commit, then wait for the smem READS (buffer reusable) or for full completion.
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* smem, int c0, int c1) {

@@ -164,7 +164,9 @@ struct GemmMaps {
 // the tensor pipe, bounds the single-CTA kernel (128x160: 115 B/clk at full MMA rate; pair 256x160: 83 B/clk).
 template <int BN, bool PAIR = false> struct GemmCfg {
   static constexpr int BM = 128, BK = 64;
-  static constexpr int STAGES = PAIR ? (BN <= 64 ? 8 : BN <= 128 ? 6 : 5) : ((BN <= 64) ? 6 : (BN <= 128 ? 5 : 4));
+  // (RCDM_GEMM_EXPERIMENT == 11: one stage less, to measure how far the main loop is bound by stages / load latency)
+  static constexpr int STAGES = (PAIR ? (BN <= 64 ? 8 : BN <= 128 ? 6 : 5) : ((BN <= 64) ? 6 : (BN <= 128 ? 5 : 4))) -
+                                (RCDM_GEMM_EXPERIMENT == 11 ? 1 : 0);
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = (PAIR ? BN / 2 : BN) * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
@@ -290,6 +292,15 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
           c = rem - tap * p.seg[s].cblocks;
         }
         GemmSeg sg = p.seg[s];
+#if RCDM_GEMM_EXPERIMENT == 10
+        // experiment: L2 prefetch of the NEXT tile's A rows (plain single-segment GEMMs, no stream-K)
+        if (!p.sk && p.nseg == 1 && sg.mode == SEG_PLAIN && tile + work.step < work.num_tiles) {
+          const int nt = tile + work.step;
+          const int nm = PAIR ? 2 * (nt / p.num_n_tiles) + (int)rank : nt / p.num_n_tiles;
+          if (nm != m_tile)
+            for (int c2 = 0; c2 < sg.cblocks; ++c2) tma_prefetch_2d(&maps.a[sg.tmap], c2 * 64, nm * 128);
+        }
+#endif
         for (int kb = kb0; kb < kb1; ++kb) {
           int mi = sg.tmap, dx = 0, dy = 0;
           if (sg.mode == SEG_CONV3) {

@@ -55,6 +55,9 @@ for pair in (0, 2):
     tag = tag.split("+")[0] + ("+pair" if pair else "")
     gemm(40960, 320, 320, True)
     gemm(40960, 320, 320, False)
+    gemm(20480, 320, 320, False)
+    gemm(10240, 320, 320, False)
+    gemm(81920, 320, 320, False)
     gemm(40960, 960, 320, False)
     gemm(40960, 320, 1280, True)
     gemm(10240, 640, 640, True)
