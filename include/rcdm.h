@@ -181,12 +181,25 @@ RCDM_API int rcdm_linear_ln(int dtype, const void* x_dev, const void* w_dev, con
                             int frames, int rows_per_frame, float eps, void* scratch_dev, void* stream);
 RCDM_API int rcdm_pack_geglu(int dtype, const void* w_dev, const float* bias_dev, void* w_out_dev, float* bias_out_dev, int N,
                     int K, void* stream);
-/* 3x3 conv, pad 1, stride 1|2, channels-last x [n,h,w,cin], w_packed [cout, 9*cin] (tap-major) */
+/* 3x3 conv, pad 1, stride 1|2, channels-last x [n,h,w,cin], w_packed [cout, 9*cin] (tap-major); stride = -2: stride 2
+ * with padding (0,1,0,1) (right / bottom only: diffusers Downsample2D(padding=0) of the VAE encoder) */
 RCDM_API int rcdm_conv3x3(int dtype, const void* x_dev, const void* w_packed_dev, const float* bias_dev,
                  const void* residual_dev, void* out_dev, int n, int h, int w, int cin, int cout, int stride,
                  int simple, void* stream);
 RCDM_API int rcdm_pack_conv3x3(int dtype, const void* w_dev /*[cout,cin,3,3] same dtype*/, void* w_out_dev, int cout, int cin,
                       void* stream);
+/* ---- AutoencoderKL pieces (RCDMs_pipeline.py:274-287 decode, :429-431 encode) ---- */
+/* 3x3 / pad 1 / stride 1 conv for a small input channel count (cin <= 16: the VAE's conv_in), CUDA cores */
+RCDM_API int rcdm_conv3x3_small(int dtype, const void* x_dev, const void* w_packed_dev, const float* bias_dev, void* out_dev,
+                                int n, int h, int w, int cin, int cout, void* stream);
+/* out[M, N] = x[M, K] w[N, K]^T + bias for N, K <= 16 (the 1x1 quant_conv / post_quant_conv on the latent channels) */
+RCDM_API int rcdm_linear_small(int dtype, const void* x_dev, const void* w_dev, const float* bias_dev, void* out_dev, int64_t M,
+                               int N, int K, void* stream);
+/* nearest-neighbour 2x upsample of channels-last images [n,h,w,c] -> [n,2h,2w,c] (Upsample2D before its conv) */
+RCDM_API int rcdm_upsample2x(int dtype, const void* x_dev, void* out_dev, int n, int h, int w, int c, void* stream);
+/* x[r, :cols] <- softmax(scale * x[r, :cols]) in place (row pitch ld): the VAE's single-head d = 512 attention is two
+ * tensor-core GEMMs (q k^T, P v) around this */
+RCDM_API int rcdm_softmax_rows(int dtype, void* x_dev, int rows, int cols, int ld, float scale, void* stream);
 /* GroupNorm(+SiLU) over rows_per_stat rows x (C/groups) channels of tokens [rows, C]; scratch >= rcdm_groupnorm_scratch_bytes */
 RCDM_API size_t rcdm_groupnorm_scratch_bytes(int rows, int rows_per_stat, int groups);
 RCDM_API int rcdm_groupnorm(int dtype, const void* x_dev, const float* gamma_dev, const float* beta_dev, void* out_dev,

@@ -70,6 +70,10 @@ SIGNATURES = {
     "rcdm_pack_geglu": (_I, [_I, _P, _P, _P, _P, _I, _I, _P]),
     "rcdm_conv3x3": (_I, [_I, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
     "rcdm_pack_conv3x3": (_I, [_I, _P, _P, _I, _I, _P]),
+    "rcdm_conv3x3_small": (_I, [_I, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
+    "rcdm_linear_small": (_I, [_I, _P, _P, _P, _P, _I64, _I, _I, _P]),
+    "rcdm_upsample2x": (_I, [_I, _P, _P, _I, _I, _I, _I, _P]),
+    "rcdm_softmax_rows": (_I, [_I, _P, _I, _I, _I, _F, _P]),
     "rcdm_gemm_rowstats": (_I, [_I, _P, _P, _P, _P, _P, _I, _I, _I, _P, C.POINTER(C.c_int), _P]),
     "rcdm_linear_ln_scratch_bytes": (C.c_size_t, [_I, _I, _I, _I]),
     "rcdm_linear_ln": (_I, [_I, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _F, _P, _P]),

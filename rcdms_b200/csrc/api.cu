@@ -831,8 +831,10 @@ int rcdm_conv3x3(int dtype, const void* x_dev, const void* w_packed_dev, const f
                  int simple, void* stream) {
   API_BEGIN
   if (!dt16(dtype)) return set_err("rcdm_conv3x3: dtype must be f16/bf16");
-  if (stride != 1 && stride != 2) return set_err("stride must be 1 or 2");
+  if (stride != 1 && stride != 2 && stride != -2) return set_err("stride must be 1, 2 or -2 (stride 2, padding (0,1,0,1))");
   if (ensure_device_ready()) return 1;
+  const int seg_mode = stride == 1 ? SEG_CONV3 : stride == 2 ? SEG_CONV3S2 : SEG_CONV3S2A;
+  if (stride < 0) stride = 2;
   const int Ho = h / stride, Wo = w / stride;
   GemmDesc d;
   memset(&d, 0, sizeof d);
@@ -840,7 +842,7 @@ int rcdm_conv3x3(int dtype, const void* x_dev, const void* w_packed_dev, const f
   d.M = n * Ho * Wo;
   d.N = cout;
   d.nseg = 1;
-  d.seg[0] = ASeg{stride == 2 ? SEG_CONV3S2 : SEG_CONV3, x_dev, cin, cin, h, w, n};
+  d.seg[0] = ASeg{seg_mode, x_dev, cin, cin, h, w, n};
   d.w = w_packed_dev;
   d.Ktot = 9 * cin;
   d.w_rows = cout;
@@ -864,6 +866,81 @@ int rcdm_conv3x3(int dtype, const void* x_dev, const void* w_packed_dev, const f
   }
   g_launches++;
   return check_launch("rcdm_conv3x3");
+  API_END
+}
+
+// ---- the pieces AutoencoderKL needs beyond the UNet's kernels (RCDMs_pipeline.py:274-287,429-431) ----
+int rcdm_conv3x3_small(int dtype, const void* x_dev, const void* w_packed_dev, const float* bias_dev, void* out_dev, int n,
+                       int h, int w, int cin, int cout, void* stream) {
+  API_BEGIN
+  if (!dt16(dtype)) return set_err("rcdm_conv3x3_small: dtype must be f16/bf16");
+  if (!x_dev || !w_packed_dev || !out_dev) return set_err("null argument");
+  if (cout % 8 || cin < 1 || cin > 16) return set_err("rcdm_conv3x3_small: cout % 8 == 0 and cin <= 16");
+  if (ensure_device_ready()) return 1;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const size_t total = (size_t)n * h * w * (cout / 8);
+  if (dtype == DT_F16)
+    conv3x3_small_kernel<__half><<<grid_for(total, 256, 148 * 32), 256, 0, st>>>(
+        reinterpret_cast<const __half*>(x_dev), reinterpret_cast<const __half*>(w_packed_dev), bias_dev,
+        reinterpret_cast<__half*>(out_dev), n, h, w, cin, cout);
+  else
+    conv3x3_small_kernel<__nv_bfloat16><<<grid_for(total, 256, 148 * 32), 256, 0, st>>>(
+        reinterpret_cast<const __nv_bfloat16*>(x_dev), reinterpret_cast<const __nv_bfloat16*>(w_packed_dev), bias_dev,
+        reinterpret_cast<__nv_bfloat16*>(out_dev), n, h, w, cin, cout);
+  g_launches++;
+  return check_launch("rcdm_conv3x3_small");
+  API_END
+}
+
+int rcdm_linear_small(int dtype, const void* x_dev, const void* w_dev, const float* bias_dev, void* out_dev, int64_t M, int N,
+                      int K, void* stream) {
+  API_BEGIN
+  if (!dt16(dtype)) return set_err("rcdm_linear_small: dtype must be f16/bf16");
+  if (!x_dev || !w_dev || !out_dev || M <= 0 || N < 1 || N > 16 || K < 1 || K > 16) return set_err("rcdm_linear_small: N, K <= 16");
+  if (ensure_device_ready()) return 1;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (dtype == DT_F16)
+    linear_small_kernel<__half><<<grid_for((size_t)M, 256, 148 * 16), 256, 0, st>>>(
+        reinterpret_cast<const __half*>(x_dev), reinterpret_cast<const __half*>(w_dev), bias_dev,
+        reinterpret_cast<__half*>(out_dev), (size_t)M, N, K);
+  else
+    linear_small_kernel<__nv_bfloat16><<<grid_for((size_t)M, 256, 148 * 16), 256, 0, st>>>(
+        reinterpret_cast<const __nv_bfloat16*>(x_dev), reinterpret_cast<const __nv_bfloat16*>(w_dev), bias_dev,
+        reinterpret_cast<__nv_bfloat16*>(out_dev), (size_t)M, N, K);
+  g_launches++;
+  return check_launch("rcdm_linear_small");
+  API_END
+}
+
+int rcdm_upsample2x(int dtype, const void* x_dev, void* out_dev, int n, int h, int w, int c, void* stream) {
+  API_BEGIN
+  if (!dt16(dtype)) return set_err("rcdm_upsample2x: dtype must be f16/bf16");
+  if (!x_dev || !out_dev || c % 8) return set_err("rcdm_upsample2x: bad argument (c % 8 == 0)");
+  if (ensure_device_ready()) return 1;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const size_t total = (size_t)n * 4 * h * w * (c / 8);
+  if (dtype == DT_F16)
+    upsample2x_kernel<__half><<<grid_for(total, 256, 148 * 32), 256, 0, st>>>(reinterpret_cast<const __half*>(x_dev),
+                                                                              reinterpret_cast<__half*>(out_dev), n, h, w, c);
+  else
+    upsample2x_kernel<__nv_bfloat16><<<grid_for(total, 256, 148 * 32), 256, 0, st>>>(
+        reinterpret_cast<const __nv_bfloat16*>(x_dev), reinterpret_cast<__nv_bfloat16*>(out_dev), n, h, w, c);
+  g_launches++;
+  return check_launch("rcdm_upsample2x");
+  API_END
+}
+
+int rcdm_softmax_rows(int dtype, void* x_dev, int rows, int cols, int ld, float scale, void* stream) {
+  API_BEGIN
+  if (!dt16(dtype)) return set_err("rcdm_softmax_rows: dtype must be f16/bf16");
+  if (!x_dev || rows <= 0 || cols <= 0 || cols % 8 || ld % 8 || ld < cols) return set_err("rcdm_softmax_rows: bad argument");
+  if (ensure_device_ready()) return 1;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int threads = cols >= 2048 ? 256 : 128;
+  if (dtype == DT_F16) softmax_rows_kernel<__half><<<rows, threads, 0, st>>>(reinterpret_cast<__half*>(x_dev), cols, ld, scale);
+  else softmax_rows_kernel<__nv_bfloat16><<<rows, threads, 0, st>>>(reinterpret_cast<__nv_bfloat16*>(x_dev), cols, ld, scale);
+  g_launches++;
+  return check_launch("rcdm_softmax_rows");
   API_END
 }
 

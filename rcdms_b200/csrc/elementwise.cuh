@@ -80,6 +80,98 @@ __global__ void upsample2x_kernel(const T* __restrict__ x, T* __restrict__ y, in
   }
 }
 
+// 3x3 / pad 1 / stride 1 convolution for a SMALL input channel count (VAE conv_in: 4 -> 512 at 64x64, 3 -> 128 at 512x512;
+// < 0.2 % of the VAE's FLOPs): CUDA cores, one thread per (pixel, 8 output channels), fp32 accumulation.
+// x [n,h,w,cin] channels-last, w packed [cout, 9*cin] tap-major (rcdm_pack_conv3x3), out [n,h,w,cout].
+template <typename T>
+__global__ void conv3x3_small_kernel(const T* __restrict__ x, const T* __restrict__ w, const float* __restrict__ bias,
+                                     T* __restrict__ out, int N, int H, int W, int Cin, int Cout) {
+  const int og = Cout / 8;
+  const size_t total = (size_t)N * H * W * og;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    const int g = (int)(idx % og);
+    size_t pix = idx / og;
+    const int xx = (int)(pix % W);
+    const int yy = (int)((pix / W) % H);
+    const int n = (int)(pix / ((size_t)W * H));
+    float acc[8];
+#pragma unroll
+    for (int o = 0; o < 8; ++o) acc[o] = bias ? __ldg(bias + g * 8 + o) : 0.f;
+    for (int tap = 0; tap < 9; ++tap) {
+      const int sy = yy + tap / 3 - 1, sx = xx + tap % 3 - 1;
+      if (sy < 0 || sy >= H || sx < 0 || sx >= W) continue;
+      const T* src = x + (((size_t)n * H + sy) * W + sx) * Cin;
+      for (int c = 0; c < Cin; ++c) {
+        const float xv = DT<T>::to_f(src[c]);
+#pragma unroll
+        for (int o = 0; o < 8; ++o)
+          acc[o] = fmaf(xv, DT<T>::to_f(__ldg(w + (size_t)(g * 8 + o) * 9 * Cin + tap * Cin + c)), acc[o]);
+      }
+    }
+    *reinterpret_cast<uint4*>(out + pix * Cout + g * 8) = pack8<T>(acc);
+  }
+}
+
+// out[m, n] = sum_k x[m, k] w[n, k] + bias[n] for tiny N, K (<= 16: the VAE's 1x1 quant_conv / post_quant_conv on 8 / 4
+// latent channels); one thread per row.
+template <typename T>
+__global__ void linear_small_kernel(const T* __restrict__ x, const T* __restrict__ w, const float* __restrict__ bias,
+                                    T* __restrict__ out, size_t M, int N, int K) {
+  for (size_t m = (size_t)blockIdx.x * blockDim.x + threadIdx.x; m < M; m += (size_t)gridDim.x * blockDim.x) {
+    float xv[16];
+    for (int k = 0; k < K; ++k) xv[k] = DT<T>::to_f(x[m * K + k]);
+    for (int n = 0; n < N; ++n) {
+      float acc = bias ? __ldg(bias + n) : 0.f;
+      for (int k = 0; k < K; ++k) acc = fmaf(xv[k], DT<T>::to_f(__ldg(w + n * K + k)), acc);
+      out[m * N + n] = DT<T>::from_f(acc);
+    }
+  }
+}
+
+// row softmax in place: x[r, 0..cols) <- softmax(scale * x[r, :]) (fp32 inside, one rounding out); one CTA per row.
+// The VAE's single-head d = 512 attention over 4096 tokens (diffusers Attention in AutoencoderKL's mid block) is
+// two tensor-core GEMMs around this kernel.
+template <typename T>
+__global__ void softmax_rows_kernel(T* __restrict__ x, int cols, int ld, float scale) {
+  __shared__ float red[32];
+  T* row = x + (size_t)blockIdx.x * ld;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  float mx = -INFINITY;
+  for (int c = threadIdx.x * 8; c < cols; c += blockDim.x * 8) {
+    float f[8];
+    unpack8<T>(*reinterpret_cast<const uint4*>(row + c), f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) mx = fmaxf(mx, f[i]);
+  }
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if (lane == 0) red[warp] = mx;
+  __syncthreads();
+  mx = -INFINITY;
+  for (int i = 0; i < nw; ++i) mx = fmaxf(mx, red[i]);
+  __syncthreads();
+  float sum = 0.f;
+  const float l2e = 1.4426950408889634f * scale;
+  for (int c = threadIdx.x * 8; c < cols; c += blockDim.x * 8) {
+    float f[8];
+    unpack8<T>(*reinterpret_cast<const uint4*>(row + c), f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) sum += exp2f((f[i] - mx) * l2e);
+  }
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  if (lane == 0) red[warp] = sum;
+  __syncthreads();
+  sum = 0.f;
+  for (int i = 0; i < nw; ++i) sum += red[i];
+  const float inv = 1.0f / sum;
+  for (int c = threadIdx.x * 8; c < cols; c += blockDim.x * 8) {
+    float f[8];
+    unpack8<T>(*reinterpret_cast<const uint4*>(row + c), f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) f[i] = exp2f((f[i] - mx) * l2e) * inv;
+    *reinterpret_cast<uint4*>(row + c) = pack8<T>(f);
+  }
+}
+
 // ---- timestep embedding (unet.py:367-389 + resnet.py:190-191), all in fp32 from 16-bit weights ----------
 // step 1: sinusoid (flip_sin_to_cos, freq_shift 0) -> rounded to T (".to(dtype)") -> linear_1 -> SiLU
 // one warp per output feature.  t comes from device memory (int64) when t_dev != nullptr.

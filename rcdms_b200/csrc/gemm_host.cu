@@ -263,7 +263,7 @@ bool gemm_prepare(const GemmDesc& d, GemmLaunch* l, std::string* err) {
         uint64_t dims[4] = {(uint64_t)a.C, (uint64_t)a.W, (uint64_t)a.H, (uint64_t)a.NI};
         uint64_t str[3] = {(uint64_t)a.C * 2, (uint64_t)a.W * a.C * 2, (uint64_t)a.H * a.W * a.C * 2};
         if (!encode_tmap(&l->maps.a[mi], a.ptr, 4, dims, str, box, true, err)) return false;
-      } else if (a.mode == SEG_CONV3S2) {
+      } else if (a.mode == SEG_CONV3S2 || a.mode == SEG_CONV3S2A) {
         for (int py = 0; py < 2; ++py)
           for (int px = 0; px < 2; ++px) {
             const char* base = reinterpret_cast<const char*>(a.ptr) + ((size_t)py * a.W + px) * a.C * 2;
@@ -442,9 +442,10 @@ __device__ float simple_dot(const GemmDesc& d, int m, int wrow) {
       koff += a.C;
     } else {
       const int x = m % d.Wo, y = (m / d.Wo) % d.Ho, n = m / (d.Wo * d.Ho);
-      const int st = a.mode == SEG_CONV3S2 ? 2 : 1;
+      const int st = (a.mode == SEG_CONV3S2 || a.mode == SEG_CONV3S2A) ? 2 : 1;
+      const int off = a.mode == SEG_CONV3S2A ? 0 : 1;  // padding (0,1,0,1): taps start at the pixel itself
       for (int tap = 0; tap < 9; ++tap) {
-        const int sy = y * st + tap / 3 - 1, sx = x * st + tap % 3 - 1;
+        const int sy = y * st + tap / 3 - off, sx = x * st + tap % 3 - off;
         if (sy >= 0 && sy < a.H && sx >= 0 && sx < a.W) {
           const T* src = ap + (((size_t)n * a.H + sy) * a.W + sx) * a.C;
           for (int c = 0; c < a.C; ++c) acc += DT<T>::to_f(src[c]) * DT<T>::to_f(w[koff + tap * a.C + c]);

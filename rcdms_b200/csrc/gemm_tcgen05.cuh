@@ -22,6 +22,8 @@
 //                read at spatial offset (kx-1, ky-1); TMA out-of-bounds zero fill implements the padding,
 //                so no im2col buffer ever exists ("im2col-free" implicit GEMM)
 //   SEG_CONV3S2  3x3, stride 2, pad 1: four parity-subsampled 4-D maps (y%2, x%2), tap -> (map, offset)
+//   SEG_CONV3S2A 3x3, stride 2, padding (0,1,0,1) (right / bottom only: diffusers Downsample2D with padding=0, the VAE
+//                encoder): same four maps, tap row = 2y + ky -> parity ky & 1, offset ky >> 1
 // Segments accumulate into the same TMEM tile, which is how conv2 + the 1x1 shortcut of a resblock (whose input
 // is the un-materialised concat [h | skip]) become a single launch.
 #pragma once
@@ -47,7 +49,7 @@
 
 namespace rcdm {
 
-enum : int { SEG_PLAIN = 0, SEG_CONV3 = 1, SEG_CONV3S2 = 2 };
+enum : int { SEG_PLAIN = 0, SEG_CONV3 = 1, SEG_CONV3S2 = 2, SEG_CONV3S2A = 3 };
 
 struct GemmSeg {
   int mode;     // SEG_*
@@ -312,6 +314,11 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
             dy = (ky == 0) ? -1 : 0;
             dx = (kx == 0) ? -1 : 0;
             mi = sg.tmap + py * 2 + px;
+          } else if (sg.mode == SEG_CONV3S2A) {
+            const int ky = tap / 3, kx = tap % 3;
+            dy = ky >> 1;
+            dx = kx >> 1;
+            mi = sg.tmap + (ky & 1) * 2 + (kx & 1);
           }
           mbar_wait(&empty_bar[stage], phase ^ 1);
           void* sa = smem_a + stage * Cfg::A_BYTES;

@@ -139,8 +139,11 @@ class RCDMsPipeline:
     def decode_latents(self, latents):
         f = latents.shape[2]
         lat = (latents / 0.18215).permute(0, 2, 1, 3, 4).flatten(0, 1)
-        frames = [self.vae.decode(lat[i:i + 1]).sample for i in range(lat.shape[0])]  # one frame at a time (:279-282)
-        video = torch.cat(frames)
+        if getattr(self.vae, "batched_decode", False):
+            video = self.vae.decode(lat).sample  # the B200 AutoencoderKL decodes all frames of the clip(s) in one batch
+        else:
+            frames = [self.vae.decode(lat[i:i + 1]).sample for i in range(lat.shape[0])]  # one frame at a time (:279-282)
+            video = torch.cat(frames)
         video = video.reshape(-1, f, *video.shape[1:]).permute(0, 2, 1, 3, 4)
         video = (video / 2 + 0.5).clamp(0, 1)
         return video.cpu().float().numpy()
