@@ -186,6 +186,14 @@ RCDM_API int rcdm_pack_geglu(int dtype, const void* w_dev, const float* bias_dev
 RCDM_API int rcdm_conv3x3(int dtype, const void* x_dev, const void* w_packed_dev, const float* bias_dev,
                  const void* residual_dev, void* out_dev, int n, int h, int w, int cin, int cout, int stride,
                  int simple, void* stream);
+/* Upsample3D / Upsample2D: nearest 2x upsample followed by conv3x3 / pad 1 (resnet.py:32-80) WITHOUT materialising the
+ * 4x tensor: per output parity class the 3x3 taps collapse to 2x2 taps on the original activation (weights summed), so
+ * four tensor-core launches with K = 4 cin (4/9 of the FLOPs) write [n, 2h, 2w, cout] through strided TMA stores.
+ * wf_dev: rcdm_upsample_conv3x3_weight_bytes(cout, cin) bytes holding the folded weights; fold != 0 (re)computes them. */
+RCDM_API size_t rcdm_upsample_conv3x3_weight_bytes(int cout, int cin);
+RCDM_API int rcdm_upsample_conv3x3(int dtype, const void* x_dev, const void* w_packed_dev, const float* bias_dev,
+                                   void* out_dev, int n, int h, int w, int cin, int cout, void* wf_dev, int fold,
+                                   void* stream);
 RCDM_API int rcdm_pack_conv3x3(int dtype, const void* w_dev /*[cout,cin,3,3] same dtype*/, void* w_out_dev, int cout, int cin,
                       void* stream);
 /* ---- AutoencoderKL pieces (RCDMs_pipeline.py:274-287 decode, :429-431 encode) ---- */

@@ -70,6 +70,8 @@ SIGNATURES = {
     "rcdm_pack_geglu": (_I, [_I, _P, _P, _P, _P, _I, _I, _P]),
     "rcdm_conv3x3": (_I, [_I, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
     "rcdm_pack_conv3x3": (_I, [_I, _P, _P, _I, _I, _P]),
+    "rcdm_upsample_conv3x3_weight_bytes": (C.c_size_t, [_I, _I]),
+    "rcdm_upsample_conv3x3": (_I, [_I, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _I, _P]),
     "rcdm_conv3x3_small": (_I, [_I, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "rcdm_linear_small": (_I, [_I, _P, _P, _P, _P, _I64, _I, _I, _P]),
     "rcdm_upsample2x": (_I, [_I, _P, _P, _I, _I, _I, _I, _P]),

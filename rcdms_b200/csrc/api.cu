@@ -869,6 +869,57 @@ int rcdm_conv3x3(int dtype, const void* x_dev, const void* w_packed_dev, const f
   API_END
 }
 
+// Upsample (nearest 2x) + conv3x3 / pad 1 without the 4x tensor: fold the weights per output parity class, then four
+// tensor-core launches of a 2x2 conv on the original activation (K = 4 cin).  wf_dev: scratch / cache for the folded
+// weights, rcdm_upsample_conv3x3_weight_bytes(cout, cin) bytes; fold != 0 (re)computes it from w_packed_dev.
+size_t rcdm_upsample_conv3x3_weight_bytes(int cout, int cin) { return (size_t)16 * cout * cin * 2; }
+int rcdm_upsample_conv3x3(int dtype, const void* x_dev, const void* w_packed_dev, const float* bias_dev, void* out_dev,
+                          int n, int h, int w, int cin, int cout, void* wf_dev, int fold, void* stream) {
+  API_BEGIN
+  if (!dt16(dtype)) return set_err("rcdm_upsample_conv3x3: dtype must be f16/bf16");
+  if (!x_dev || !out_dev || !wf_dev || (fold && !w_packed_dev)) return set_err("null argument");
+  if (ensure_device_ready()) return 1;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (fold) {
+    const size_t total = (size_t)16 * cout * cin;
+    if (dtype == DT_F16)
+      fold_upsample_kernel<__half><<<grid_for(total, 256), 256, 0, st>>>(reinterpret_cast<const __half*>(w_packed_dev),
+                                                                        reinterpret_cast<__half*>(wf_dev), cout, cin);
+    else
+      fold_upsample_kernel<__nv_bfloat16><<<grid_for(total, 256), 256, 0, st>>>(
+          reinterpret_cast<const __nv_bfloat16*>(w_packed_dev), reinterpret_cast<__nv_bfloat16*>(wf_dev), cout, cin);
+    g_launches++;
+  }
+  for (int cls = 0; cls < 4; ++cls) {
+    GemmDesc d;
+    memset(&d, 0, sizeof d);
+    d.dt = dtype;
+    d.M = n * h * w;
+    d.N = cout;
+    d.nseg = 1;
+    d.seg[0] = ASeg{SEG_UP2, x_dev, cin, cin, h, w, n};
+    d.w = reinterpret_cast<const char*>(wf_dev) + (size_t)cls * cout * 4 * cin * 2;
+    d.Ktot = 4 * cin;
+    d.w_rows = cout;
+    d.Ho = h;
+    d.Wo = w;
+    d.NI = n;
+    d.out = out_dev;
+    d.ldo = cout;
+    d.bias = bias_dev;
+    d.up_py = cls >> 1;
+    d.up_px = cls & 1;
+    GemmLaunch l;
+    std::string e;
+    d.sk = sk_workspace_for_stream(st, &e);
+    if (!gemm_prepare(d, &l, &e)) return set_err(e);
+    gemm_launch(l, st);
+    g_launches++;
+  }
+  return check_launch("rcdm_upsample_conv3x3");
+  API_END
+}
+
 // ---- the pieces AutoencoderKL needs beyond the UNet's kernels (RCDMs_pipeline.py:274-287,429-431) ----
 int rcdm_conv3x3_small(int dtype, const void* x_dev, const void* w_packed_dev, const float* bias_dev, void* out_dev, int n,
                        int h, int w, int cin, int cout, void* stream) {

@@ -343,6 +343,27 @@ static __global__ void pack_vec_kernel(const void* __restrict__ src, int src_dt,
   dst[row] = accumulate ? dst[row] + v : v;
 }
 
+// Upsample3D folded into its conv (gemm_tcgen05.cuh, SEG_UP2): for output parity class (py, px) the 3x3 taps that land on
+// the same input pixel are summed (in fp32, one rounding): rows S(0,0) = {0}, S(0,1) = {1,2}, S(1,0) = {0,1}, S(1,1) = {2}.
+// w [Cout, 9*Cin] tap-major (packed conv layout) -> wf [4 classes][Cout][4*Cin] with k = (ty*2 + tx)*Cin + c.
+template <typename T>
+__global__ void fold_upsample_kernel(const T* __restrict__ w, T* __restrict__ wf, int Cout, int Cin) {
+  const size_t total = (size_t)4 * Cout * 4 * Cin;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(idx % Cin);
+    const int t2 = (int)((idx / Cin) % 4);
+    const int co = (int)((idx / ((size_t)4 * Cin)) % Cout);
+    const int cls = (int)(idx / ((size_t)4 * Cin * Cout));
+    const int py = cls >> 1, px = cls & 1, ty = t2 >> 1, tx = t2 & 1;
+    const int ky0 = py == 0 ? (ty == 0 ? 0 : 1) : (ty == 0 ? 0 : 2), ky1 = py == 0 ? (ty == 0 ? 0 : 2) : (ty == 0 ? 1 : 2);
+    const int kx0 = px == 0 ? (tx == 0 ? 0 : 1) : (tx == 0 ? 0 : 2), kx1 = px == 0 ? (tx == 0 ? 0 : 2) : (tx == 0 ? 1 : 2);
+    float acc = 0.f;
+    for (int ky = ky0; ky <= ky1; ++ky)
+      for (int kx = kx0; kx <= kx1; ++kx) acc += DT<T>::to_f(w[(size_t)co * 9 * Cin + (ky * 3 + kx) * Cin + c]);
+    wf[idx] = DT<T>::from_f(acc);
+  }
+}
+
 // Whole-state-dict packing in ONE launch: a device table of jobs (one per state-dict entry), each owning a contiguous
 // range of CTAs; a CTA finds its job by binary search over the ranges' first block index.
 struct PackJob {

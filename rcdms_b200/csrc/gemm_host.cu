@@ -232,17 +232,18 @@ bool gemm_prepare(const GemmDesc& d, GemmLaunch* l, std::string* err) {
     } else {
       if (a.C % 64 != 0) return fail("conv channels must be a multiple of 64");
       has_conv = true;
-      if (a.mode == SEG_CONV3) {
+      if (a.mode == SEG_CONV3 || a.mode == SEG_UP2) {
         if (nmap + 1 > 4) return fail("too many tensor maps");
-        if (a.H != d.Ho || a.W != d.Wo) return fail("conv3 s1: input/output grid mismatch");
+        if (a.H != d.Ho || a.W != d.Wo) return fail("conv3 s1 / folded upsample: input/output grid mismatch");
+        if (a.mode == SEG_UP2 && (d.nseg != 1 || d.res)) return fail("folded upsample: single segment, no residual");
         nmap += 1;  // encoded below once the tile geometry is known
       } else {
         if (nmap + 4 > 4) return fail("too many tensor maps");
         if (a.H != 2 * d.Ho || a.W != 2 * d.Wo) return fail("conv3 s2: input must be 2x the output grid");
         nmap += 4;
       }
-      kb += 9 * p.seg[s].cblocks;
-      kcols += 9 * a.C;
+      kb += seg_taps(a.mode) * p.seg[s].cblocks;
+      kcols += seg_taps(a.mode) * a.C;
     }
   }
   if (kcols != d.Ktot) return fail("segment K does not add up to the weight K");
@@ -259,7 +260,7 @@ bool gemm_prepare(const GemmDesc& d, GemmLaunch* l, std::string* err) {
       const ASeg& a = d.seg[s];
       const int mi = p.seg[s].tmap;
       uint32_t box[4] = {64, (uint32_t)p.tw, (uint32_t)p.th, (uint32_t)p.tn};
-      if (a.mode == SEG_CONV3) {
+      if (a.mode == SEG_CONV3 || a.mode == SEG_UP2) {
         uint64_t dims[4] = {(uint64_t)a.C, (uint64_t)a.W, (uint64_t)a.H, (uint64_t)a.NI};
         uint64_t str[3] = {(uint64_t)a.C * 2, (uint64_t)a.W * a.C * 2, (uint64_t)a.H * a.W * a.C * 2};
         if (!encode_tmap(&l->maps.a[mi], a.ptr, 4, dims, str, box, true, err)) return false;
@@ -296,7 +297,19 @@ bool gemm_prepare(const GemmDesc& d, GemmLaunch* l, std::string* err) {
                     (reinterpret_cast<uintptr_t>(d.out) & 15) == 0 &&
                     (!d.res || (reinterpret_cast<uintptr_t>(d.res) & 15) == 0) && (wcols * 2) % 16 == 0;
     p.epi_tma = ok ? 1 : 0;
-    if (ok) {
+    const bool up2 = d.seg[0].mode == SEG_UP2;
+    p.up_py = d.up_py;
+    p.up_px = d.up_px;
+    p.out4d = up2 ? 1 : 0;
+    if (up2 && !ok) return fail("folded upsample needs the TMA epilogue (N % 8 == 0, aligned rows)");
+    if (ok && up2) {
+      // class (py, px) of the [NI, 2 Ho, 2 Wo, ldo] output: pixel (2 y + py, 2 x + px) <-> class-grid pixel (y, x)
+      const char* base = reinterpret_cast<const char*>(d.out) + ((size_t)d.up_py * 2 * d.Wo + d.up_px) * d.ldo * 2;
+      uint64_t dims[4] = {(uint64_t)n_out, (uint64_t)d.Wo, (uint64_t)d.Ho, (uint64_t)d.NI};
+      uint64_t str[3] = {(uint64_t)2 * d.ldo * 2, (uint64_t)2 * (2 * d.Wo) * d.ldo * 2, (uint64_t)(2 * d.Ho) * (2 * d.Wo) * d.ldo * 2};
+      uint32_t box[4] = {(uint32_t)wcols, (uint32_t)p.tw, (uint32_t)p.th, (uint32_t)p.tn};
+      if (!encode_tmap(&l->maps.o, base, 4, dims, str, box, false, err)) return false;
+    } else if (ok) {
       uint64_t dims[2] = {(uint64_t)n_out, (uint64_t)d.M};
       uint32_t box[2] = {(uint32_t)wcols, 128};
       uint64_t str[1] = {(uint64_t)d.ldo * 2};

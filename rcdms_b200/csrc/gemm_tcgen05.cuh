@@ -22,6 +22,10 @@
 //                read at spatial offset (kx-1, ky-1); TMA out-of-bounds zero fill implements the padding,
 //                so no im2col buffer ever exists ("im2col-free" implicit GEMM)
 //   SEG_CONV3S2  3x3, stride 2, pad 1: four parity-subsampled 4-D maps (y%2, x%2), tap -> (map, offset)
+//   SEG_UP2      nearest-2x upsample FOLDED into the following 3x3 / pad 1 conv (Upsample3D, resnet.py:32-80): the output
+//                pixels of parity (py, px) see only 2 x 2 distinct input pixels, (y + ty - 1 + py, x + tx - 1 + px), with
+//                the 3x3 weights that fall on the same input pixel summed beforehand -> one launch per parity class on
+//                the ORIGINAL activation (K = 4 Cin instead of 9 Cin, no 4x tensor), output through a strided 4-D map
 //   SEG_CONV3S2A 3x3, stride 2, padding (0,1,0,1) (right / bottom only: diffusers Downsample2D with padding=0, the VAE
 //                encoder): same four maps, tap row = 2y + ky -> parity ky & 1, offset ky >> 1
 // Segments accumulate into the same TMEM tile, which is how conv2 + the 1x1 shortcut of a resblock (whose input
@@ -49,7 +53,8 @@
 
 namespace rcdm {
 
-enum : int { SEG_PLAIN = 0, SEG_CONV3 = 1, SEG_CONV3S2 = 2, SEG_CONV3S2A = 3 };
+enum : int { SEG_PLAIN = 0, SEG_CONV3 = 1, SEG_CONV3S2 = 2, SEG_CONV3S2A = 3, SEG_UP2 = 4 };
+__host__ __device__ constexpr int seg_taps(int mode) { return mode == SEG_PLAIN ? 1 : mode == SEG_UP2 ? 4 : 9; }
 
 struct GemmSeg {
   int mode;     // SEG_*
@@ -106,6 +111,8 @@ struct GemmParams {
   // frames, over the two tensors of an un-materialised skip concat) into mean / rstd.  Zeroed once per step.
   unsigned long long* gn_acc;
   int gn_hw;
+  // SEG_UP2: output parity class of this launch; out4d: the output tile is stored through a 4-D map (cols, x, y, image)
+  int up_py, up_px, out4d;
 };
 constexpr int GN_CHUNK = 10;
 // value v (fp32) -> fixed point v * 2^40 split into (hi = floor(v * 2^-8), lo = remainder < 2^48); exact for |v| >= 2^-16
@@ -286,7 +293,7 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
         {
           int rem = kb0;
           for (; s < p.nseg - 1; ++s) {
-            const int n = (p.seg[s].mode == SEG_PLAIN ? 1 : 9) * p.seg[s].cblocks;
+            const int n = seg_taps(p.seg[s].mode) * p.seg[s].cblocks;
             if (rem < n) break;
             rem -= n;
           }
@@ -314,6 +321,9 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
             dy = (ky == 0) ? -1 : 0;
             dx = (kx == 0) ? -1 : 0;
             mi = sg.tmap + py * 2 + px;
+          } else if (sg.mode == SEG_UP2) {
+            dy = (tap >> 1) - 1 + p.up_py;
+            dx = (tap & 1) - 1 + p.up_px;
           } else if (sg.mode == SEG_CONV3S2A) {
             const int ky = tap / 3, kx = tap % 3;
             dy = ky >> 1;
@@ -359,7 +369,7 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
           }
           if (++c == sg.cblocks) {  // advance (segment, tap, channel block)
             c = 0;
-            if (++tap == (sg.mode == SEG_PLAIN ? 1 : 9)) {
+            if (++tap == seg_taps(sg.mode)) {
               tap = 0;
               if (s + 1 < p.nseg) sg = p.seg[++s];
             }
@@ -919,10 +929,21 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
         const int sb = o & 1;
         mbar_wait(&stg_full[sb], (o >> 1) & 1);
 #if RCDM_GEMM_EXPERIMENT != 6
-        for (int g = 0; g < NG; ++g)
-          if (n_tile * tile_cols + g * wcols < n_total)
-            tma_store_2d(&maps.o, staging + sb * Cfg::STG_BYTES + g * Cfg::PART_BYTES, n_tile * tile_cols + g * wcols,
-                         m_tile * 128);
+        if (p.out4d) {  // conv tile origin on the output grid (same decomposition as the producer's)
+          int t = m_tile;
+          const int tx = t % p.tiles_x;
+          t /= p.tiles_x;
+          const int ty = t % p.tiles_y, tb = t / p.tiles_y;
+          for (int g = 0; g < NG; ++g)
+            if (n_tile * tile_cols + g * wcols < n_total)
+              tma_store_4d(&maps.o, staging + sb * Cfg::STG_BYTES + g * Cfg::PART_BYTES, n_tile * tile_cols + g * wcols,
+                           tx * p.tw, ty * p.th, tb * p.tn);
+        } else {
+          for (int g = 0; g < NG; ++g)
+            if (n_tile * tile_cols + g * wcols < n_total)
+              tma_store_2d(&maps.o, staging + sb * Cfg::STG_BYTES + g * Cfg::PART_BYTES, n_tile * tile_cols + g * wcols,
+                           m_tile * 128);
+        }
         bulk_commit();
         bulk_wait_read0();  // the buffer may be refilled
 #endif

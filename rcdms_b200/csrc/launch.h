@@ -59,7 +59,7 @@ bool encode_tmap(CUtensorMap* out, const void* base, int rank, const uint64_t* d
 
 // ---- GEMM / implicit-GEMM conv -------------------------------------------------------------------------
 struct ASeg {
-  int mode;         // SEG_PLAIN / SEG_CONV3 / SEG_CONV3S2
+  int mode;         // SEG_PLAIN / SEG_CONV3 / SEG_CONV3S2 / SEG_CONV3S2A / SEG_UP2
   const void* ptr;  // plain: [M, ld]; conv: NHWC activation [NI, H, W, C]
   int C;            // K of this segment per tap
   int ld;           // plain: row pitch in elements
@@ -107,6 +107,9 @@ struct GemmDesc {
   // gn_hw % 32 == 0 (gemm_gn_stats_ok)
   unsigned long long* gn_acc;
   int gn_hw;
+  // SEG_UP2 (upsample folded into the conv): parity class of this launch; `out` is the FULL-resolution tensor
+  // [NI, 2 Ho, 2 Wo, ldo] and the class's pixels are written through a strided 4-D map
+  int up_py, up_px;
 };
 bool gemm_gn_stats_ok(int M, int N, int hw);  // can a GEMM / conv with this output shape emit GroupNorm statistics?
 inline size_t gemm_gn_acc_bytes(int n_img, int N) { return (size_t)n_img * (N / GN_CHUNK) * 4 * sizeof(unsigned long long); }

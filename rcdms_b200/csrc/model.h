@@ -82,6 +82,7 @@ struct BlockW {
   bool sampler = false;
   Mat sw;
   Vec sb;
+  Mat swf;  // up blocks: the sampler weights folded per output parity class, [4 * C, 4 * C] (SEG_UP2)
   int C = 0;
 };
 

@@ -285,6 +285,7 @@ static int build_model(rcdm_unet_impl* h) {
       blk.sw = b.mat(out_c, 9 * out_c);
       b.slot(p + ".upsamplers.0.conv.weight", {out_c, out_c, 3, 3}, SLOT_CONV3, blk.sw.off, 9 * out_c, 0, 0, 0, out_c);
       blk.sb = b.vslot(p + ".upsamplers.0.conv.bias", out_c);
+      blk.swf = b.mat(4 * out_c, 4 * out_c);
     }
   }
   const int mc = c.block_out_channels[c.num_blocks - 1];
@@ -387,6 +388,17 @@ static void finalize_weights(rcdm_unet_impl* h, cudaStream_t st) {
       }
   fold_tf(h, h->mid_tf, st);
   if (h->mid_has_mo) fold_mo(h, h->mid_mo, st);
+  for (auto& blk : h->up)
+    if (blk.sampler) {  // Upsample3D folded into its conv: per-parity-class 2x2 weights
+      const size_t total = (size_t)16 * blk.C * blk.C;
+      if (h->dt == DT_F16)
+        fold_upsample_kernel<__half><<<grid_for(total, 256), 256, 0, st>>>(
+            reinterpret_cast<const __half*>(h->arena + blk.sw.off), reinterpret_cast<__half*>(h->arena + blk.swf.off), blk.C, blk.C);
+      else
+        fold_upsample_kernel<__nv_bfloat16><<<grid_for(total, 256), 256, 0, st>>>(
+            reinterpret_cast<const __nv_bfloat16*>(h->arena + blk.sw.off),
+            reinterpret_cast<__nv_bfloat16*>(h->arena + blk.swf.off), blk.C, blk.C);
+    }
   for (auto& blk : h->down)
     for (auto& l : blk.layers) finalize_res(h, l.res, st);
   for (auto& blk : h->up)
@@ -507,6 +519,7 @@ struct Planner {
     double k_alg = 0;
     bool conv = false;
     for (int i = 0; i < d.nseg; ++i) {
+      // algorithmic K: a folded upsample (SEG_UP2) executes 4 taps but stands for the reference's 9
       k_alg += d.seg[i].mode == SEG_PLAIN ? d.seg[i].C : 9.0 * d.seg[i].C;
       conv |= d.seg[i].mode != SEG_PLAIN;
     }
@@ -1116,7 +1129,39 @@ static int plan_network(rcdm_unet_impl* h, bool dry, size_t* peak) {
         P.tap(bp + ".motion_modules." + std::to_string(j), x);
       }
     }
-    if (blk.sampler) {  // Upsample3D: nearest 2x then conv3x3 (resnet.py:46-80)
+    if (blk.sampler && !h->simple) {
+      // Upsample3D (resnet.py:46-80): nearest 2x folded into the conv - four launches (one per output parity class) of a
+      // 2x2 conv on the un-upsampled activation, K = 4 C; the 4x tensor is never materialised
+      Act o = P.new_act(blk.C, 2 * x.H, 2 * x.W);
+      o.gn = P.new_gn(blk.C, x.H, x.W);  // statistics per image from the four class launches (class grid = x's grid)
+      for (int cls = 0; cls < 4; ++cls) {
+        GemmDesc d;
+        memset(&d, 0, sizeof d);
+        if (o.gn != NO_GN) {
+          d.gn_acc = P.gnp(o.gn);
+          d.gn_hw = x.H * x.W;
+        }
+        d.M = P.rows(x);
+        d.N = blk.C;
+        d.nseg = 1;
+        d.seg[0] = ASeg{SEG_UP2, P.p(x.off), x.C, x.C, x.H, x.W, NI};
+        d.w = h->arena + blk.swf.off + (size_t)cls * blk.C * 4 * x.C * 2;
+        d.Ktot = 4 * x.C;
+        d.w_rows = blk.C;
+        d.Ho = x.H;
+        d.Wo = x.W;
+        d.NI = NI;
+        d.out = P.p(o.off);
+        d.ldo = blk.C;
+        d.bias = P.wv(blk.sb);
+        d.up_py = cls >> 1;
+        d.up_px = cls & 1;
+        P.gemm(d);
+      }
+      P.free_act(x);
+      x = o;
+      P.tap(bp + ".upsamplers.0", x);
+    } else if (blk.sampler) {  // debug (CUDA-core) plan: materialised nearest 2x, then the conv
       Act u = P.new_act(x.C, 2 * x.H, 2 * x.W);
       if (!dry) {
         const void* src = P.p(x.off);

@@ -256,3 +256,18 @@ def group_norm_from_stats(x0: torch.Tensor, acc0: torch.Tensor, gamma: torch.Ten
                                                     gamma.data_ptr(), beta.data_ptr(), out.data_ptr(), rows, rows_per_stat,
                                                     hw, groups, eps, int(silu), _lib.current_stream_ptr()))
     return out
+
+
+def upsample_conv3x3(x_nhwc: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """conv3x3(pad 1)(nearest_upsample_2x(x)) with the upsample folded into the conv (no 4x tensor, K = 4 cin)."""
+    n, h, w, cin = x_nhwc.shape
+    cout = weight.shape[0]
+    L, s = _lib.lib(), _lib.current_stream_ptr()
+    wp = torch.empty((cout, 9 * cin), dtype=x_nhwc.dtype, device=x_nhwc.device)
+    wsrc = weight.to(x_nhwc.dtype).contiguous()
+    _lib.check(L.rcdm_pack_conv3x3(_dt(wsrc), wsrc.data_ptr(), wp.data_ptr(), cout, cin, s))
+    wf = torch.empty((L.rcdm_upsample_conv3x3_weight_bytes(cout, cin),), dtype=torch.uint8, device=x_nhwc.device)
+    out = torch.empty((n, 2 * h, 2 * w, cout), dtype=x_nhwc.dtype, device=x_nhwc.device)
+    _lib.check(L.rcdm_upsample_conv3x3(_dt(x_nhwc), x_nhwc.data_ptr(), wp.data_ptr(), _ptr(bias), out.data_ptr(), n, h, w,
+                                       cin, cout, wf.data_ptr(), 1, s))
+    return out

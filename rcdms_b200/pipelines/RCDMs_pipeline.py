@@ -28,7 +28,15 @@ from ..schedulers import DDIMScheduler, FrozenConfig
 class local_feature(nn.Module):
     """Context fusion (reference ``RCDMs_pipeline.py:35-55`` = ``fine_stack`` / ``semantic_stack`` of
     ``stage2_batchtest_rcdms_model.py:117-149``): text tokens query the visual tokens through one
-    ``nn.MultiheadAttention``.  Runs once per clip; stays PyTorch by design."""
+    ``nn.MultiheadAttention`` (seq-first), after a Linear on each side.  Parameters are the reference's own torch modules
+    (same state-dict names: ``text_fc``, ``vis_fc``, ``multihead_attn.in_proj_weight / in_proj_bias / out_proj``), so the
+    DeepSpeed checkpoint split loads unchanged.
+
+    On a CUDA device in float16 / bfloat16 the forward is six C-ABI launches of ``librcdm_b200``: four tcgen05 GEMMs
+    (text_fc, vis_fc, the q and the fused k|v in-projections), ``rcdm_flash_attn`` (8 heads, d = 96, 257 or 1 keys) and the
+    out-projection GEMM.  Anywhere else it raises unless ``allow_torch_path`` is set (CPU-tier host-logic tests only)."""
+
+    allow_torch_path = False
 
     def __init__(self, text_dim: int, vis_dim: int, hidden_dim: int = 768, num_heads: int = 8):
         super().__init__()
@@ -37,10 +45,45 @@ class local_feature(nn.Module):
         self.vis_fc = nn.Linear(vis_dim, hidden_dim)
         self.multihead_attn = nn.MultiheadAttention(embed_dim=hidden_dim, num_heads=num_heads)  # (seq, batch, dim)
 
-    def forward(self, vis_f: torch.Tensor, text_f: torch.Tensor) -> torch.Tensor:
+    def forward_torch(self, vis_f: torch.Tensor, text_f: torch.Tensor) -> torch.Tensor:
+        """The reference's op sequence in torch (``stage2_batchtest_rcdms_model.py:142-147``)."""
         q = self.text_fc(text_f).transpose(0, 1)
         kv = self.vis_fc(vis_f).transpose(0, 1)
         return self.multihead_attn(q, kv, kv)[0].transpose(0, 1)
+
+    @staticmethod
+    def _lin(a: torch.Tensor, w: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+        from .. import ops
+        if a.shape[1] % 8:  # the TMA rows need 16-byte multiples: zero-pad K (plumbing; e.g. 12-wide test embeddings)
+            pad = 8 - a.shape[1] % 8
+            a = torch.nn.functional.pad(a, (0, pad))
+            w = torch.nn.functional.pad(w, (0, pad))
+        return ops.linear(a.contiguous(), w.contiguous(), b.float().contiguous())
+
+    @torch.no_grad()
+    def forward(self, vis_f: torch.Tensor, text_f: torch.Tensor) -> torch.Tensor:
+        native = text_f.is_cuda and vis_f.is_cuda and text_f.dtype in (torch.float16, torch.bfloat16) \
+            and self.text_fc.weight.dtype == text_f.dtype
+        if not native:
+            if not self.allow_torch_path:
+                raise RuntimeError("local_feature runs on the B200 kernels: CUDA tensors and a float16 / bfloat16 module "
+                                   "(set allow_torch_path = True for the reference's torch ops in host-logic tests)")
+            return self.forward_torch(vis_f, text_f)
+        from .. import _lib
+        B, L, _ = text_f.shape
+        Sv, D, H = vis_f.shape[1], self.hidden_dim, self.num_heads
+        vis_f = vis_f.to(text_f.dtype)
+        w_in, b_in = self.multihead_attn.in_proj_weight, self.multihead_attn.in_proj_bias
+        q = self._lin(self._lin(text_f.reshape(B * L, -1), self.text_fc.weight, self.text_fc.bias), w_in[:D], b_in[:D])
+        kv = self._lin(self._lin(vis_f.reshape(B * Sv, -1), self.vis_fc.weight, self.vis_fc.bias), w_in[D:], b_in[D:])
+        d = D // H
+        att = torch.empty_like(q)
+        simple = 0 if (d % 8 == 0 and d <= 160) else 1  # odd head dims (tiny test modules): the library's CUDA-core kernel
+        _lib.check(_lib.lib().rcdm_flash_attn(_lib.torch_dtype_id(q.dtype), q.data_ptr(), D, kv.data_ptr(),
+                                              kv.data_ptr() + D * kv.element_size(), 2 * D, att.data_ptr(), D, B, H, L, Sv, d,
+                                              simple, _lib.current_stream_ptr()))
+        out = self._lin(att, self.multihead_attn.out_proj.weight, self.multihead_attn.out_proj.bias)
+        return out.reshape(B, L, D)
 
 
 @dataclass

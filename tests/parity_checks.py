@@ -89,6 +89,20 @@ def check_conv3x3(n, h, w, cin, cout, stride, dtype, residual=False, simple=Fals
                    dtype, rtol_mul=2.0 if residual else 1.0)
 
 
+def check_upsample_conv3x3(n, h, w, cin, cout, dtype, seed=13):
+    """Upsample3D (nearest 2x, resnet.py:65) + conv3x3 folded into four 2x2 convs vs F.interpolate + F.conv2d in fp32.
+    The folded weights are sums of up to four 16-bit weights rounded once, so the result differs from the reference by
+    one extra weight rounding: same x2 tolerance as the other twice-rounded ops."""
+    g = _gen(seed)
+    x = _rand((n, h, w, cin), dtype, g)
+    wt = _rand((cout, cin, 3, 3), dtype, g, 1.0 / math.sqrt(9 * cin))
+    b = torch.randn((cout,), generator=g, device="cuda")
+    out = ops.upsample_conv3x3(x, wt, b)
+    up = F.interpolate(x.float().permute(0, 3, 1, 2), scale_factor=2.0, mode="nearest")
+    ref = F.conv2d(up, wt.float(), b, padding=1).permute(0, 2, 3, 1)
+    return _result(f"upsample_conv3x3 n{n} {h}x{w} {cin}->{cout}", out, ref, dtype, rtol_mul=2.0)
+
+
 def check_groupnorm(nstat, rows_per_stat, C, dtype, silu=True, eps=1e-5, seed=3):
     g = _gen(seed)
     x = _rand((nstat * rows_per_stat, C), dtype, g) * 2 + 0.5
@@ -224,6 +238,28 @@ def check_temporal(batch, frames, hw, heads, d, dtype, seed=6):
     return _result(f"temporal b{batch} f{frames} hw{hw} h{heads} d{d}", out, ref, dtype, rtol_mul=3.0)
 
 
+def check_context_fusion(B, L, text_dim, Sv, vis_dim, hidden, heads, dtype, seed=12):
+    """local_feature (fine_stack / semantic_stack, stage2_batchtest_rcdms_model.py:117-149) on the B200 kernels vs the
+    reference's own torch ops (nn.Linear + nn.MultiheadAttention) in fp32 on the same rounded weights / inputs."""
+    from rcdms_b200.pipelines.RCDMs_pipeline import local_feature
+    torch.manual_seed(seed)
+    m = local_feature(text_dim, vis_dim, hidden, heads)
+    with torch.no_grad():
+        for prm in m.parameters():
+            if prm.dim() == 1:
+                prm.normal_(0, 0.1)  # MHA biases are zero-initialised: make them count
+    g = _gen(seed)
+    text = _rand((B, L, text_dim), dtype, g)
+    vis = _rand((B, Sv, vis_dim), dtype, g)
+    mh = m.to("cuda", dtype)
+    out = mh(vis, text)
+    ref_m = local_feature(text_dim, vis_dim, hidden, heads).to("cuda")
+    ref_m.load_state_dict({k: v.float() for k, v in mh.state_dict().items()})
+    with torch.no_grad():
+        ref = ref_m.forward_torch(vis.float(), text.float())
+    return _result(f"context_fusion B{B} L{L} Sv{Sv} vis{vis_dim} hid{hidden}", out, ref, dtype, rtol_mul=4.0)
+
+
 def check_ddim(clips, f, h, w, dtype, cfg=True, seed=7):
     from oracle.loop_ref import make_scheduler
     g = _gen(seed)
@@ -298,6 +334,9 @@ def all_op_checks(dtypes=(torch.float16, torch.bfloat16), quick=False):
                                         (10, 32, 32, 64, 4, 1), (10, 8, 8, 64, 128, 2), (2, 64, 64, 64, 64, 2),
                                         (10, 2, 2, 128, 128, 2), (5, 16, 16, 192, 320, 2)]:
             yield lambda a=(n, h, w, cin, cout, s), dt=dt: check_conv3x3(*a, dt, residual=(a[4] % 8 == 0))
+        for (n, h, w, cin, cout) in [(10, 8, 8, 1280, 1280), (10, 16, 16, 1280, 1280), (2, 32, 32, 640, 640), (3, 4, 8, 64, 128),
+                                     (10, 2, 2, 64, 64)]:
+            yield lambda a=(n, h, w, cin, cout), dt=dt: check_upsample_conv3x3(*a, dt)
         yield lambda dt=dt: check_conv3x3(4, 8, 8, 64, 64, 1, dt, simple=True)
         yield lambda dt=dt: check_conv3x3(4, 8, 8, 64, 64, 2, dt, simple=True)
         for (ns, rps, C, silu) in [(2, 5 * 64, 320, True), (10, 64, 64, False), (2, 5 * 4096, 320, True),
@@ -328,5 +367,10 @@ def all_op_checks(dtypes=(torch.float16, torch.bfloat16), quick=False):
         for (b, f, hw, hds, d) in [(2, 5, 64, 8, 40), (2, 5, 16, 8, 8), (2, 5, 4096, 8, 40), (2, 5, 1, 8, 32),
                                    (2, 5, 256, 8, 160), (1, 3, 10, 8, 80)]:
             yield lambda a=(b, f, hw, hds, d), dt=dt: check_temporal(*a, dt)
+        # context fusion: PororoSV / FlintstonesSV shapes (257 CLIP patch tokens of width 1664; one 1280-wide embedding)
+        yield lambda dt=dt: check_context_fusion(2, 85, 768, 257, 1664, 768, 8, dt)
+        yield lambda dt=dt: check_context_fusion(8, 91, 768, 1, 1280, 768, 8, dt)
+        yield lambda dt=dt: check_context_fusion(3, 7, 96, 9, 16, 96, 8, dt)   # d = 12: the library's CUDA-core attention
+        yield lambda dt=dt: check_context_fusion(4, 7, 96, 1, 12, 96, 8, dt)   # K = 12 zero-padded to 16
         yield lambda dt=dt: check_ddim(1, 5, 64, 64, dt, cfg=True)
         yield lambda dt=dt: check_ddim(3, 5, 8, 8, dt, cfg=False)

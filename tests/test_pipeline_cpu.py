@@ -35,6 +35,7 @@ def make_pipe(L=7, D=96):
     unet = TinyUNet()
     lm = local_feature(text_dim=D, vis_dim=16, hidden_dim=D, num_heads=8)
     gm = local_feature(text_dim=D, vis_dim=12, hidden_dim=D, num_heads=8)
+    lm.allow_torch_path = gm.allow_torch_path = True  # CPU tier: host logic only (the product path is CUDA-only)
     pipe = RCDMsPipeline(FakeVAE(), FakeTextEncoder(L, D), FakeTokenizer(), unet, lm, gm,
                          DDIMScheduler(**RCDMS_SCHEDULER_KWARGS))
     return pipe, unet

@@ -40,9 +40,11 @@ def test_decode_matches_oracle(cfg_fn, n, h, dtype):
         ref = vae_ref.vae_decode(sdr, cfg, z.float())
         half = vae_ref.vae_decode(sdh, cfg, z)
     _floor_check(y, ref, half)
-    # batched decode == frame-by-frame decode (the reference's loop, RCDMs_pipeline.py:279-282), bitwise
+    # batched decode == frame-by-frame decode (the reference's loop, RCDMs_pipeline.py:279-282) up to the summation order
+    # of the stream-K GEMM decomposition, whose split points depend on the number of tiles in the launch
     if n > 1:
-        assert torch.equal(y[1:2], m.decode(z[1:2]).sample)
+        one = m.decode(z[1:2]).sample
+        assert (y[1:2].float() - one.float()).abs().max().item() <= 4e-3 * ref.abs().max().item()
 
 
 @pytest.mark.parametrize("cfg_fn,n,hw,dtype", [(vae_tiny_config, 5, 64, torch.float16), (vae_full_config, 1, 256, torch.float16)])
@@ -77,4 +79,4 @@ def test_pipeline_decode_latents_batches_frames():
     assert vid.shape == (1, 3, 5, 32, 32) and vid.min() >= 0.0 and vid.max() <= 1.0
     frames = torch.cat([m.decode((lat[:, :, i] / 0.18215)).sample for i in range(5)])
     ref = (frames / 2 + 0.5).clamp(0, 1).float().cpu().reshape(1, 5, 3, 32, 32).permute(0, 2, 1, 3, 4)
-    assert torch.equal(torch.from_numpy(vid), ref)
+    assert (torch.from_numpy(vid) - ref).abs().max().item() <= 4e-3
