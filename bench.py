@@ -47,6 +47,7 @@ def parse():
     ap.add_argument("--no-eager-gpu-baseline", action="store_true",
                     help="skip the eager-GPU leg (the oracle restatement in torch eager, bench dtype, on this GPU: the "
                          "stand-in for 'the reference modules in eager fp16 on the B200', SURVEY 8d; on by default at N=1)")
+    ap.add_argument("--no-pixels", action="store_true", help="skip the end-to-end-to-pixels leg (denoise + VAE decode)")
     ap.add_argument("--no-extra-configs", action="store_true",
                     help="skip the extra BASELINE configs (N=1: config 3 bf16 x 8 clips; N>1: config 5, 8 clips per GPU)")
     ap.add_argument("--eager-gpu-only", action="store_true", help="run only the eager-GPU baseline leg and exit")
@@ -369,6 +370,58 @@ def run_ours(a):
                                          gbs=round(v["bytes"] / max(v["ms"], 1e-9) / 1e6, 1)) for k, v in agg.items()},
                         forward_ms_sum_of_ops=tot_ms)
 
+    # ---- end to end to PIXELS (SURVEY 8d "also report end-to-end including VAE decode"): pinned host inputs -> denoise ->
+    # AutoencoderKL.decode of all frames on the same kernels (rcdms_b200.models.vae) -> clamp -> fp32 frames on the host
+    e2e_pixels = None
+    if not a.no_pixels and rank == 0 and world == 1 and a.latent == 64:
+        from rcdms_b200.models import AutoencoderKL
+        from rcdms_b200.vae_spec import synthetic_vae_state_dict, vae_full_config
+        vcfg = vae_full_config()
+        vae = AutoencoderKL.from_config(vcfg)
+        vae.load_state_dict(synthetic_vae_state_dict(vcfg, seed=0), strict=True)
+        vae = vae.to(device=dev, dtype=dtype)
+        ins = [synthetic_clip_inputs(k, a.latent, a.latent, a.ctx_len) for k in range(a.clips)]
+        hostp = dict(latents=torch.cat([i["latents"] for i in ins]).to(dtype).pin_memory(),
+                     masked=torch.cat([i["masked_latents"] for i in ins]).to(dtype).pin_memory(),
+                     mask=torch.cat([i["mask"] for i in ins]).to(dtype).pin_memory(),
+                     ctx=torch.cat([i["ctx"][:5] for i in ins] + [i["ctx"][5:] for i in ins]).to(dtype).pin_memory())
+        px = a.latent * 8
+        pix_host = torch.empty((a.clips * 5, 3, px, px), dtype=torch.float32).pin_memory()
+
+        def to_pixels():
+            d = {k: v.to(dev, non_blocking=True) for k, v in hostp.items()}
+            lat = pipe.denoise(d["latents"], torch.cat([d["mask"]] * 2), torch.cat([d["masked"]] * 2), d["ctx"],
+                               a.ddim_steps, a.guidance)
+            frames = (lat / 0.18215).permute(0, 2, 1, 3, 4).flatten(0, 1)          # RCDMs_pipeline.py:276-278
+            video = (vae.decode(frames).sample / 2 + 0.5).clamp(0, 1)               # :281-284 (all frames in one batch)
+            pix_host.copy_(video.float(), non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            return frames
+
+        frames = to_pixels()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(a.steps):
+            to_pixels()
+        e1.record()
+        torch.cuda.synchronize()
+        ms_pix = e0.elapsed_time(e1) / a.steps
+        e0.record()
+        for _ in range(3):
+            vae.decode(frames)
+        e1.record()
+        torch.cuda.synchronize()
+        e2e_pixels = dict(value=5 * a.clips / (ms_pix / 1e3), unit="frames/s", ms_per_step=ms_pix,
+                          vae_decode_ms=e0.elapsed_time(e1) / 3,
+                          h2d_bytes_per_step=sum(v.numel() * v.element_size() for v in hostp.values()),
+                          d2h_bytes_per_step=pix_host.numel() * pix_host.element_size(),
+                          api="RCDMsPipeline.denoise + AutoencoderKL.decode (rcdms_b200 kernels) + clamp; host pinned "
+                              "tensors in, fp32 frames (clips*5, 3, 512, 512) on the host out",
+                          vae="SD-1.5 AutoencoderKL architecture (83.65 M parameters), synthetic weights")
+        del vae, frames
+        torch.cuda.empty_cache()
+
     # ---- the other BASELINE.json configurations, measured in the same run (reported, not the headline):
     #   N = 1: config 3 (FlintstonesSV, bf16, 8 clips batched on the GPU, L = 91);  N > 1: config 5 (8 clips per GPU, fp16)
     extra = []
@@ -416,6 +469,8 @@ def run_ours(a):
         if eager_gpu is not None:
             line["gpu_eager_baseline"] = eager_gpu
             line["derived"]["speedup_vs_gpu_eager"] = eager_gpu["ms_per_ddim_step"] / (r["ms"] / a.ddim_steps)
+        if e2e_pixels is not None:
+            line["e2e_pixels"] = e2e_pixels
         if extra:
             line["extra_configs"] = extra
         print(json.dumps(line), flush=True)

@@ -390,9 +390,8 @@ flash_attn4_kernel(const __grid_constant__ AttnMaps maps, const AttnParams p) {
   uint64_t* s_full = bars + 1 + 2 * KV;  // S_j is in TMEM
   uint64_t* s_free = s_full + 1;         // every softmax thread holds S_j in registers
   uint64_t* p_full = s_full + 2;         // [2]
-  uint64_t* pv_done = s_full + 4;
-  uint64_t* o_done = s_full + 5;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_full + 6);
+  uint64_t* o_done = s_full + 4;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_full + 5);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q_tile = blockIdx.x, head = blockIdx.y, img = blockIdx.z;
@@ -410,7 +409,6 @@ flash_attn4_kernel(const __grid_constant__ AttnMaps maps, const AttnParams p) {
       mbar_init(s_free, 4);
       mbar_init(&p_full[0], 4);
       mbar_init(&p_full[1], 4);
-      mbar_init(pv_done, 1);
       mbar_init(o_done, 1);
       fence_mbar_init();
       tma_prefetch_desc(&maps.q);
@@ -480,8 +478,7 @@ flash_attn4_kernel(const __grid_constant__ AttnMaps maps, const AttnParams p) {
           const uint64_t bd = umma_smem_desc(v_addr + ks * 256, 128, BN * 16, UMMA_SWIZZLE_NONE);
           umma_f16_ss(tmem_O, ad, bd, idesc_pv, (j | ks) != 0);
         }
-        umma_commit(&kv_empty[s]);
-        umma_commit(pv_done);
+        umma_commit(&kv_empty[s]);  // P_j V_j done: the K/V stage is free (also what the rare O rescale waits for)
         if (j == n_kv - 1) umma_commit(o_done);
         if (j + KV < n_kv) {
           mbar_wait(&kv_empty[s], (j / KV) & 1);
@@ -570,7 +567,9 @@ flash_attn4_kernel(const __grid_constant__ AttnMaps maps, const AttnParams p) {
           const float m_new = fmaxf(m_run, row_max() * sc);
           const float alpha = exp2f(m_run - m_new);
           const float sum2 = exp_pass(m_new, pmax);
-          mbar_wait(pv_done, (j - 1) & 1);  // O (incl. the row-sum column) must be quiescent: P_{j-1} V_{j-1} done
+          // O (incl. the row-sum column) must be quiescent: P_{j-1} V_{j-1} done = its K/V stage released.  (That
+          // barrier cannot run ahead: its next completion needs P_{j-1+KV} from these same threads.)
+          mbar_wait(&kv_empty[(j - 1) % KV], ((j - 1) / KV) & 1);
           tc_fence_after();
 #pragma unroll 1
           for (int c = 0; c < DPAD; c += 16) {

@@ -352,6 +352,12 @@ template <typename T, int BN> static void launch_one(const GemmLaunch& l, cudaSt
              GemmCfg<BN, false>::SMEM_BYTES, s, l.maps, l.p);
     return;
   }
+  if (!l.pair && l.p.sk && !l.gn) {
+    // stream-K: CTAs wait for each other's partial tiles through flags in global memory -> cooperative launch
+    launch_coop(gemm_tcgen05_kernel<T, BN, false>, l.grid, dim3(GemmCfg<BN, false>::THREADS), GemmCfg<BN, false>::SMEM_BYTES, s,
+                l.maps, l.p);
+    return;
+  }
   if (!l.pair) {
     if constexpr (BN == 160) {
       if (l.gn) {

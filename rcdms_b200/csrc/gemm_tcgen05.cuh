@@ -189,8 +189,10 @@ template <int BN, bool PAIR = false> struct GemmCfg {
   static constexpr int STAGING_BYTES = 2 * STG_BYTES;
   static constexpr int ACC_STRIDE = BN <= 64 ? 64 : BN <= 128 ? 128 : 256;  // TMEM columns between the 2 accumulators
   static constexpr int TMEM_COLS = 2 * ACC_STRIDE;
-  // two buffers (tile parity) of BN fp32 epilogue values: bias, or the folded-LayerNorm vector c
-  static constexpr int BIAS_BYTES = 2 * BN * 4;
+  // BN fp32 epilogue values (bias, or the folded-LayerNorm vector c) per TMEM lane quarter: every epilogue warp owns a
+  // private slice (its quarter's row, its column group), so no shared-memory word is written by one warp and read by
+  // another (compute-sanitizer racecheck clean) and no tile-parity double buffer is needed
+  static constexpr int BIAS_BYTES = 4 * BN * 4;
   // the dynamic shared memory window is declared __align__(1024) (128B-swizzle atoms), so there is no alignment slack
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + 256 /*barriers*/ + BIAS_BYTES;
   static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB per-CTA shared memory limit");
@@ -233,7 +235,7 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
   uint64_t* stg_free = bars + 2 * STAGES + 8;        // [2] the TMA store has finished reading staging[b]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 10);
   static_assert((2 * STAGES + 10) * 8 + 4 <= 256, "barrier block overflows its 256 bytes");
-  float* bias_sm = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);  // [2 parity][BN]
+  float* bias_sm = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);  // [4 lane quarters][BN]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -609,8 +611,7 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
         const int n_warp = n_tile * tile_cols + cg * wcols;  // first output column of this warp
         const int sb = ot & 1;                               // staging buffer of this tile
         // ---- epilogue vector of this warp's columns (bias, or LN c): fetched into registers BEFORE the accumulator
-        // wait (latency hidden), parked in smem[tile parity] AFTER it.  The four warps sharing `cg` write identical
-        // values (benign); storing after the wait keeps the parity double-buffer race-free.
+        // wait (latency hidden), parked in this warp's private smem slice AFTER it (broadcast reads in the column loop)
         constexpr int PV = (QW + 31) / 32;
         float pre0[PV];
         {
@@ -631,7 +632,7 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
         mbar_wait(&tmem_full_bar[acc], acc_phase);
         tc_fence_after();
         if (ln) ln_finish();
-        float* bsm = bias_sm + (it & 1) * BN + cg * QW;  // bias, or c of the tile's frame in LN mode
+        float* bsm = bias_sm + q * BN + cg * QW;  // bias, or c of the tile's frame in LN mode (this warp's slice)
 #pragma unroll
         for (int j = 0; j < PV; ++j) {
           const int i = lane + j * 32;
@@ -823,15 +824,16 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
           // sum the 2 * GNC per-row values over the warp's 32 rows with a reduce-scatter butterfly (fixed tree, 2 * GNC
           // shuffles instead of 5 per value): afterwards lanes 2k and 2k+1 hold value k (k < GNC: sum of chunk k,
           // else sum of squares of chunk k - GNC); lane 2k adds it to the tensor's fixed-point accumulators
-          static_assert(GNC == 8, "the butterfly below reduces 16 values over 32 lanes");
-          float vals[16];
+          constexpr int NV = 2 * GNC;  // 16 (two column groups) or 8 (four): a power of two <= 32
+          static_assert(NV == 16 || NV == 8, "the butterfly below reduces 16 or 8 values over 32 lanes");
+          float vals[NV];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
+          for (int i = 0; i < GNC; ++i) {
             vals[i] = gn_s[i];
-            vals[8 + i] = gn_ss[i];
+            vals[GNC + i] = gn_ss[i];
           }
 #pragma unroll
-          for (int w = 8, m = 16; w >= 1; w >>= 1, m >>= 1) {
+          for (int w = NV / 2, m = 16; w >= 1; w >>= 1, m >>= 1) {
             const bool up = (lane & m) != 0;
 #pragma unroll
             for (int i = 0; i < w; ++i) {
@@ -840,14 +842,19 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
               vals[i] = keep + __shfl_xor_sync(0xffffffffu, send, m);
             }
           }
-          const float total = vals[0] + __shfl_xor_sync(0xffffffffu, vals[0], 1);
-          if ((lane & 1) == 0) {
-            const int k = lane >> 1;
+          // vals[0] now holds value k = (lane >> SH) & (NV - 1) summed over the lanes that differ in the top log2(NV)
+          // bits; the remaining SH low bits are folded with plain butterflies
+          constexpr int SH = NV == 16 ? 1 : 2;
+          float total = vals[0];
+#pragma unroll
+          for (int o = 1 << (SH - 1); o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
+          if ((lane & ((1 << SH) - 1)) == 0 && m_warp < p.M) {  // (a pair's last 256-row tile may be half outside M)
+            const int k = lane >> SH;
             const int img = m_warp / p.gn_hw;
-            const int chunk = n_warp / GN_CHUNK + (k & 7);
+            const int chunk = n_warp / GN_CHUNK + (k % GNC);
             unsigned long long hi, lo;
             gn_fixed_split(total, hi, lo);
-            unsigned long long* a = p.gn_acc + ((size_t)img * (p.N / GN_CHUNK) + chunk) * 4 + (k >> 3) * 2;
+            unsigned long long* a = p.gn_acc + ((size_t)img * (p.N / GN_CHUNK) + chunk) * 4 + (k / GNC) * 2;
             atomicAdd(a, hi);
             atomicAdd(a + 1, lo);
           }

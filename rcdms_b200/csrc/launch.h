@@ -51,6 +51,23 @@ inline cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_
   cfg.numAttrs = pdl_enabled() ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
 }
+// Cooperative launch: for the kernels whose CTAs synchronise through global memory (the GroupNorm grid barrier, the
+// stream-K fix-up): the driver GUARANTEES that all CTAs are co-resident or refuses the launch (an error, never a spin
+// that ends in a trap when another stream / process holds SMs).
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_coop(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeCooperative;
+  at[0].val.cooperative = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
+}
 
 // ---- TMA tensor-map encoding (driver entry point resolved at run time; no link-time libcuda dependency) ----
 // dims/box innermost-first; strides_bytes has rank-1 entries (dimension 0 is contiguous). 16-bit elements.

@@ -146,7 +146,14 @@ void gn_run(const GnLaunch& l, cudaStream_t s) {
     return;
   }
   if (l.fused) {
-    if (l.dt == DT_F16)
+    // cps > 1: the CTAs of a statistic batch meet at a barrier in global memory -> cooperative launch (co-residency
+    // guaranteed by the driver); cps == 1: no inter-CTA dependency, ordinary launch
+    if (l.cps > 1) {
+      if (l.dt == DT_F16)
+        launch_coop(gn_fused_kernel<__half>, dim3(l.fgrid), dim3(l.fthreads), l.fsmem, s, l.a, l.cps, l.cache_rows, l.fk);
+      else
+        launch_coop(gn_fused_kernel<__nv_bfloat16>, dim3(l.fgrid), dim3(l.fthreads), l.fsmem, s, l.a, l.cps, l.cache_rows, l.fk);
+    } else if (l.dt == DT_F16)
       launch_k(gn_fused_kernel<__half>, dim3(l.fgrid), dim3(l.fthreads), l.fsmem, s, l.a, l.cps, l.cache_rows, l.fk);
     else
       launch_k(gn_fused_kernel<__nv_bfloat16>, dim3(l.fgrid), dim3(l.fthreads), l.fsmem, s, l.a, l.cps, l.cache_rows, l.fk);

@@ -186,6 +186,16 @@ class MyPriorTransformer(nn.Module):
         return (prior_latents * self.clip_std) + self.clip_mean
 
     # ---- weight packing (once per load_state_dict / .to()) -----------------------------------------------------
+    def refresh_weights(self) -> None:
+        """Force re-packing of the device weights (and re-capture of the step graph) on the next forward: needed after
+        writes through ``param.data`` that do not bump the version counter."""
+        self._packed_versions = None
+
+    def load_state_dict(self, *args, **kwargs):
+        out = super().load_state_dict(*args, **kwargs)
+        self._packed_versions = None
+        return out
+
     def _versions(self):
         return tuple((t.data_ptr(), t._version) for t in self.state_dict(keep_vars=True).values())
 

@@ -220,6 +220,22 @@ class UNet3DConditionModel(nn.Module):
             torch.cuda.current_stream().synchronize()
             self._bound_versions = versions
 
+    def refresh_weights(self) -> None:
+        """Force re-packing of the device weights on the next forward.  Needed after writes that bypass autograd's version
+        counter (``param.data.copy_()``, LoRA / EMA merges on ``.data``): ordinary in-place ops, ``load_state_dict`` and
+        ``.to()`` are detected automatically."""
+        self._bound_versions = None
+
+    def load_state_dict(self, *args, **kwargs):
+        out = super().load_state_dict(*args, **kwargs)
+        self._bound_versions = None
+        return out
+
+    def _apply(self, fn, *args, **kwargs):
+        out = super()._apply(fn, *args, **kwargs)
+        self._bound_versions = None
+        return out
+
     def set_debug_option(self, name: str, value: int) -> None:
         """Explicit debug switch of the native handle ("simple": CUDA-core reference kernels for bisecting a parity
         failure; "ln_fold"; "autotune").  Never set on a product path; the library reads no environment variables."""
