@@ -269,7 +269,7 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
   }
   tc_fence_before();
   if constexpr (PAIR) cluster_sync_all();  // the peer's barriers are initialised before anything signals them
-  else __syncthreads();
+  __syncthreads();  // (also in a pair: the CTA-scope barrier is what orders the TMEM-slot write for racecheck)
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   pdl_sync();  // everything above overlapped the previous kernel's tail; global memory is touched only below
