@@ -85,7 +85,7 @@ RCDM_API int rcdm_set_stream_k_min(int k_blocks);       /* tuning knob: minimum 
 RCDM_API int rcdm_set_gemm_pair(int on);                /* tuning knob: use the CTA-pair (tcgen05 cta_group::2, 256-row tile) GEMM kernel
                                                            (default 1); returns the previous value */
 /* debug / experiment switches.  The library reads NO environment variables; every switch has a compiled-in default (the
- * measured-best setting).  name: "pdl", "sk_min", "gemm_pair", "masked_attn_mma", "attn_v", "temporal_wide",
+ * measured-best setting).  name: "pdl", "sk_min", "gemm_pair", "masked_attn_mma", "temporal_wide",
  * "temporal_wide_all", "temporal_tiled", "temporal_smem_kb", "gn_fused", "ln_wide", "gn_stats".  Returns the previous
  * value, -1 for an unknown name. */
 RCDM_API int rcdm_debug_set_option(const char* name, int value);

@@ -717,6 +717,7 @@ int rcdm_groupnorm_from_stats(int dtype, const void* x0_dev, int C0, const void*
   if (C0 % 10 || C1 % 10 || C % 8 || groups <= 0 || groups > 64 || C % groups || (C / groups) % 10 || hw <= 0 ||
       rows_per_stat % hw || rows % rows_per_stat)
     return set_err("rcdm_groupnorm_from_stats: bad shape (group width and both channel counts must be multiples of 10)");
+  if (C > 3072) return set_err("rcdm_groupnorm_from_stats: at most 3072 channels");
   if (ensure_device_ready()) return 1;
   GnLaunch l;
   gn_configure_from_stats(&l, dtype, x0_dev, C0, reinterpret_cast<const unsigned long long*>(acc0_dev), x1_dev, C1,
@@ -795,7 +796,8 @@ int rcdm_pack_geglu(int dtype, const void* w_dev, const float* bias_dev, void* w
                     int K, void* stream) {
   API_BEGIN
   if (!dt16(dtype)) return set_err("dtype must be f16/bf16");
-  if (N % GEGLU_BN) return set_err("GEGLU pack: N must be a multiple of 128");
+  const int GEGLU_BN = geglu_bn(N);
+  if (N % GEGLU_BN) return set_err("GEGLU pack: N must be a multiple of 128 (or of 160)");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (dtype == DT_F16)
     pack_weight_kernel<__half><<<grid_for((size_t)N * K, 256), 256, 0, st>>>(

@@ -1,9 +1,9 @@
 // Attention kernels for sm_100a.
 //
-// flash_attn_kernel: softmax(scale * Q K^T) V without materialising the scores (the reference writes an
+// flash_attn4_kernel: softmax(scale * Q K^T) V without materialising the scores (the reference writes an
 // (80, 4096, 4096) score tensor per 64x64 layer: attention.py:170-199).  One CTA = 128 queries of one
 // (image, head).  Both GEMMs run on tcgen05 with accumulators in TMEM:
-//     S_j = Q K_j^T (128 x 64 fp32, two TMEM buffers)        O += P_j V_j   (128 x DPAD fp32, TMEM cols [128, ...))
+//     S_j = Q K_j^T (128 x 64 fp32, one TMEM buffer)         O += P_j V_j   (128 x DPAD fp32, TMEM cols [64, ...))
 // Q/K/V head slices are fetched straight out of the fused projection output [rows, ld] by 5-D TMA maps
 // (8 elems, row, 16-byte chunk, head, image) into the no-swizzle "interleaved" UMMA layout
 // [chunk][row][8 elems]; out-of-range chunks / rows are zero-filled by TMA, which pads head_dim 40 -> 48 and
@@ -40,304 +40,23 @@ struct AttnMaps {
   CUtensorMap q, k, v;
 };
 
-template <int DPAD> struct AttnCfg {
-  static constexpr int BLOCK_M = 128, BLOCK_N = 64;
-  static constexpr int NCH = DPAD / 8;                   // 16-byte chunks per head row
-  static constexpr int Q_BYTES = NCH * BLOCK_M * 16;     // Q tile
-  static constexpr int KV_BYTES = NCH * BLOCK_N * 16;    // one K (or V) tile
-  static constexpr int KV_STAGES = DPAD <= 48 ? 3 : 2;
-  static constexpr int P_BYTES = (BLOCK_N / 8) * BLOCK_M * 16;  // one P buffer (two are kept)
-  static constexpr int TMEM_COLS = (2 * BLOCK_N + DPAD) <= 256 ? 256 : 512;
-  static constexpr int SMEM_BYTES = Q_BYTES + 2 * KV_STAGES * KV_BYTES + 2 * P_BYTES + 1024 + 256;
-};
-
-// Software pipeline (per CTA): S and P are double-buffered, so the tensor core computes S_{j+1} = Q K_{j+1}^T while
-// the softmax warps exponentiate S_j, and O += P_j V_j runs while they work on S_{j+1}; the softmax warps never
-// wait for an MMA in steady state.  TMEM: S0 | S1 (64 cols each) | O (DPAD cols).
-template <typename T, int DPAD>
-__global__ void __launch_bounds__(160, AttnCfg<DPAD>::SMEM_BYTES <= 113 * 1024 ? 2 : 1)
-flash_attn_kernel(const __grid_constant__ AttnMaps maps, const AttnParams p) {
-  using Cfg = AttnCfg<DPAD>;
-  constexpr int KV = Cfg::KV_STAGES;
-  constexpr int BN = Cfg::BLOCK_N;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sQ = smem;
-  uint8_t* sK = sQ + Cfg::Q_BYTES;
-  uint8_t* sV = sK + KV * Cfg::KV_BYTES;
-  uint8_t* sP = sV + KV * Cfg::KV_BYTES;  // [2][P_BYTES]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * Cfg::P_BYTES);
-  uint64_t* q_full = bars;
-  uint64_t* kv_full = bars + 1;        // [KV]
-  uint64_t* kv_empty = bars + 1 + KV;  // [KV]
-  uint64_t* s_full = bars + 1 + 2 * KV;  // [2]
-  uint64_t* p_full = s_full + 2;         // [2]
-  uint64_t* pv_done = s_full + 4;
-  uint64_t* o_done = s_full + 5;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_full + 6);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int q_tile = blockIdx.x, head = blockIdx.y, img = blockIdx.z;
-  const int n_kv = (p.S_kv + BN - 1) / BN;
-
-  if (warp == 4) {
-    if (lane == 0) {
-      mbar_init(q_full, 1);
-      for (int i = 0; i < KV; ++i) {
-        mbar_init(&kv_full[i], 1);
-        mbar_init(&kv_empty[i], 1);
-      }
-      for (int i = 0; i < 2; ++i) {
-        mbar_init(&s_full[i], 1);
-        mbar_init(&p_full[i], 128);
-      }
-      mbar_init(pv_done, 1);
-      mbar_init(o_done, 1);
-      fence_mbar_init();
-      tma_prefetch_desc(&maps.q);
-      tma_prefetch_desc(&maps.k);
-      tma_prefetch_desc(&maps.v);
-    }
-    __syncwarp();
-    tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_O = tmem_base + 2 * BN;
-  pdl_sync();
-
-  if (warp == 4) {
-    if (elect_one()) {
-      constexpr uint32_t idesc_qk = umma_idesc_f16(DT<T>::umma_fmt, 128, BN, 0, 0);
-      constexpr uint32_t idesc_pv = umma_idesc_f16(DT<T>::umma_fmt, 128, DPAD, 0, 1);  // B (=V) is MN-major
-      const uint32_t q_addr = smem_u32(sQ);
-      auto load_kv = [&](int t) {
-        const int s = t % KV;
-        mbar_expect_tx(&kv_full[s], 2 * Cfg::KV_BYTES);
-        tma_load_5d(sK + s * Cfg::KV_BYTES, &maps.k, &kv_full[s], 0, t * BN, 0, head, img);
-        tma_load_5d(sV + s * Cfg::KV_BYTES, &maps.v, &kv_full[s], 0, t * BN, 0, head, img);
-      };
-      // S_t = Q K_t^T : A, B K-major interleaved [chunk][row][8]; one K=16 step = 2 chunks
-      auto mma_qk = [&](int t) {
-        const int s = t % KV;
-        mbar_wait(&kv_full[s], (t / KV) & 1);
-        tc_fence_after();
-        const uint32_t k_addr = smem_u32(sK + s * Cfg::KV_BYTES);
-#pragma unroll
-        for (int ks = 0; ks < DPAD / 16; ++ks) {
-          const uint64_t ad = umma_smem_desc(q_addr + ks * 2 * (128 * 16), 128 * 16, 128, UMMA_SWIZZLE_NONE);
-          const uint64_t bd = umma_smem_desc(k_addr + ks * 2 * (BN * 16), BN * 16, 128, UMMA_SWIZZLE_NONE);
-          umma_f16_ss(tmem_base + (t & 1) * BN, ad, bd, idesc_qk, ks != 0);
-        }
-        umma_commit(&s_full[t & 1]);
-      };
-      mbar_expect_tx(q_full, Cfg::Q_BYTES);
-      tma_load_5d(sQ, &maps.q, q_full, 0, q_tile * 128, 0, head, img);
-      for (int t = 0; t < KV && t < n_kv; ++t) load_kv(t);
-      mbar_wait(q_full, 0);
-      mma_qk(0);
-      for (int j = 0; j < n_kv; ++j) {
-        if (j + 1 < n_kv) mma_qk(j + 1);  // overlaps the softmax of tile j
-        // ---- O += P_j V_j : A = P K-major interleaved, B = V MN-major interleaved (16 kv rows = 256 B per step)
-        mbar_wait(&p_full[j & 1], (j >> 1) & 1);
-        tc_fence_after();
-        const int s = j % KV;
-        const uint32_t p_addr = smem_u32(sP + (j & 1) * Cfg::P_BYTES);
-        const uint32_t v_addr = smem_u32(sV + s * Cfg::KV_BYTES);
-#pragma unroll
-        for (int ks = 0; ks < (RCDM_ATTN_EXPERIMENT == 4 ? 1 : BN / 16); ++ks) {
-          const uint64_t ad = umma_smem_desc(p_addr + ks * 4096, 2048, 128, UMMA_SWIZZLE_NONE);
-          const uint64_t bd = umma_smem_desc(v_addr + ks * 256, 128, BN * 16, UMMA_SWIZZLE_NONE);
-          umma_f16_ss(tmem_O, ad, bd, idesc_pv, (j | ks) != 0);
-        }
-        umma_commit(&kv_empty[s]);
-        umma_commit(pv_done);
-        if (j == n_kv - 1) umma_commit(o_done);
-        if (j + KV < n_kv) {  // refill the stage just consumed
-          mbar_wait(&kv_empty[s], (j / KV) & 1);
-          load_kv(j + KV);
-        }
-      }
-    }
-  } else {
-    // =================================== softmax warps ===================================
-    // One thread per query row.  Lazy online softmax: the first KV tile fixes the reference maximum m_run with a
-    // separate max pass; every later tile is ONE pass that exponentiates against m_run while tracking the largest
-    // probability, and only if some probability exceeds 2^8 does the warp re-reference the tile and rescale O.
-    const int row = warp * 32 + lane;
-    const uint32_t lane_sel = uint32_t(warp * 32) << 16;
-    const float sc = p.scale_log2;
-    float m_run = -INFINITY, l_run = 0.f;
-    // Row sums for free: when the head dim leaves a spare padded column (d = 40 in a 48-wide tile), column d of
-    // every V row is set to 1 so that the P V MMA accumulates sum_j P_ij (of the ROUNDED probabilities) in TMEM.
-    const bool mma_sum = p.d < DPAD;
-    using T2 = typename DT<T>::T2;
-
-    // exponentiate one 64-column S row against `mref`, write P; returns the row sum (0 when MS) and, in `pmax`,
-    // the largest probability written
-    auto exp_pass = [&](auto ms_tag, uint32_t tS, uint8_t* sP_row, float mref, int kv_valid, float& pmax) -> float {
-      constexpr bool MS = decltype(ms_tag)::value;
-      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-      T2 mx2 = DT<T>::from_f2(0.f, 0.f);
-      const bool full = kv_valid >= BN;
-      // two 32-column chunks; the TMEM load of chunk 1 is in flight while chunk 0 is exponentiated
-      uint32_t rbuf[2][32];
-#if RCDM_ATTN_EXPERIMENT == 2
-#pragma unroll
-      for (int i = 0; i < 32; ++i) rbuf[0][i] = rbuf[1][i] = __float_as_uint(0.01f * (float)(i + lane));
-#else
-      tmem_ld32(tS + lane_sel, rbuf[0]);
-      tmem_wait_ld();
-#endif
-#pragma unroll
-      for (int k = 0; k < 2; ++k) {
-        uint32_t* r = rbuf[k];
-#if RCDM_ATTN_EXPERIMENT != 2
-        if (k == 0) tmem_ld32(tS + lane_sel + 32, rbuf[1]);
-#endif
-        const int c = k * 32;
-        if (!full) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (c + i >= kv_valid) r[i] = 0xff800000u;  // -inf: exp2 -> 0
-        }
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          float pv[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-#if RCDM_ATTN_EXPERIMENT == 1
-            pv[i] = fmaf(__uint_as_float(r[g * 8 + i]), sc, -mref);
-#else
-            pv[i] = exp2f(fmaf(__uint_as_float(r[g * 8 + i]), sc, -mref));
-#endif
-          }
-          if constexpr (!MS) {
-            s0 += pv[0] + pv[4];
-            s1 += pv[1] + pv[5];
-            s2 += pv[2] + pv[6];
-            s3 += pv[3] + pv[7];
-          }
-          uint4 pk = pack8<T>(pv);
-          const T2* p2 = reinterpret_cast<const T2*>(&pk);
-          mx2 = __hmax2(mx2, __hmax2(__hmax2(p2[0], p2[1]), __hmax2(p2[2], p2[3])));
-          // P tile, K-major interleaved: [chunk = kv/8][row][8 elems]
-#if RCDM_ATTN_EXPERIMENT != 3
-          *reinterpret_cast<uint4*>(sP_row + (c / 8 + g) * 2048) = pk;
-#endif
-        }
-#if RCDM_ATTN_EXPERIMENT != 2
-        if (k == 0) tmem_wait_ld();
-#endif
-      }
-      const float2 mxf = DT<T>::to_f2(mx2);
-      pmax = fmaxf(mxf.x, mxf.y);
-      return (s0 + s1) + (s2 + s3);
-    };
-    auto row_max = [&](uint32_t tS, int kv_valid) -> float {
-      float x0 = -INFINITY, x1 = -INFINITY;
-      uint32_t r[64];
-      tmem_ld32(tS + lane_sel, r);
-      tmem_ld32(tS + lane_sel + 32, r + 32);
-      tmem_wait_ld();
-#pragma unroll
-      for (int i = 0; i < 64; i += 2) {
-        if (i < kv_valid) x0 = fmaxf(x0, __uint_as_float(r[i]));
-        if (i + 1 < kv_valid) x1 = fmaxf(x1, __uint_as_float(r[i + 1]));
-      }
-      return fmaxf(x0, x1);
-    };
-    auto run_pass = [&](uint32_t tS, uint8_t* sP_row, float mref, int kv_valid, float& pmax) -> float {
-      return mma_sum ? exp_pass(std::true_type{}, tS, sP_row, mref, kv_valid, pmax)
-                     : exp_pass(std::false_type{}, tS, sP_row, mref, kv_valid, pmax);
-    };
-
-    for (int j = 0; j < n_kv; ++j) {
-      mbar_wait(&s_full[j & 1], (j >> 1) & 1);
-      tc_fence_after();
-      const uint32_t tS = tmem_base + (j & 1) * BN;
-      uint8_t* sP_row = sP + (j & 1) * Cfg::P_BYTES + row * 16;
-      const int kv_valid = min(BN, p.S_kv - j * BN);
-      if (mma_sum && row < BN)  // V tile j has landed (same barrier as K_j): set its "ones" column
-        *reinterpret_cast<T*>(sV + (j % KV) * Cfg::KV_BYTES + (p.d / 8) * (BN * 16) + row * 16) = DT<T>::from_f(1.0f);
-      float pmax;
-      if (j == 0) {
-        m_run = row_max(tS, kv_valid) * sc;
-        l_run = run_pass(tS, sP_row, m_run, kv_valid, pmax);
-      } else {
-        const float sum = run_pass(tS, sP_row, m_run, kv_valid, pmax);
-        if (__any_sync(0xffffffffu, pmax > 256.0f)) {
-          // rare: some probability left the comfortable 16-bit range -> re-reference to the new maximum
-          const float m_new = fmaxf(m_run, row_max(tS, kv_valid) * sc);
-          const float alpha = exp2f(m_run - m_new);
-          const float sum2 = run_pass(tS, sP_row, m_new, kv_valid, pmax);
-          mbar_wait(pv_done, (j - 1) & 1);  // O (incl. the row-sum column) must be quiescent: P_{j-1} V_{j-1} done
-          tc_fence_after();
-#pragma unroll 1
-          for (int c = 0; c < DPAD; c += 16) {
-            uint32_t r[16];
-            tmem_ld16(tmem_O + lane_sel + c, r);
-            tmem_wait_ld();
-#pragma unroll
-            for (int i = 0; i < 16; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
-            tmem_st16(tmem_O + lane_sel + c, r);
-          }
-          tmem_wait_st();
-          l_run = l_run * alpha + sum2;
-          m_run = m_new;
-        } else {
-          l_run += sum;
-        }
-      }
-      fence_proxy_async_smem();
-      tc_fence_before();
-      mbar_arrive(&p_full[j & 1]);
-    }
-    // ---- normalise and store
-    mbar_wait(o_done, 0);
-    tc_fence_after();
-    if (mma_sum) {
-      uint32_t r[16];
-      tmem_ld16(tmem_O + lane_sel + (p.d & ~15), r);
-      tmem_wait_ld();
-      l_run = __uint_as_float(r[p.d & 15]);
-    }
-    const float inv_l = 1.0f / l_run;
-    const int qrow = q_tile * 128 + row;
-    T* out = reinterpret_cast<T*>(p.out) + ((size_t)img * p.S_q + qrow) * p.ldo + head * p.d;
-#pragma unroll 1
-    for (int c = 0; c < DPAD; c += 16) {
-      uint32_t r[16];
-      tmem_ld16(tmem_O + lane_sel + c, r);
-      tmem_wait_ld();
-      if (qrow < p.S_q) {
-        float v[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]) * inv_l;
-        if (c < p.d) *reinterpret_cast<uint4*>(out + c) = pack8<T>(v);
-        if (c + 8 < p.d) *reinterpret_cast<uint4*>(out + c + 8) = pack8<T>(v + 8);
-      }
-    }
-    tc_fence_before();
-  }
-  __syncthreads();
-  if (warp == 4) {
-    tc_fence_after();
-    tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
-  }
-}
-
 // ------------------------------------------------------------------------------------------
-// flash attention, generation 4: same data path as flash_attn_kernel (5-D TMA head slices, tcgen05 S = Q K^T and
-// O += P V with TMEM accumulators, lazy-rescale online softmax, PV-MMA row sums), re-balanced for the unit that
-// actually bounds head_dim 40: the MUFU exp2 pipe (ncu: XU 58 % busy, tensor 21 %, 8 warps per SM).
+// flash attention (5-D TMA head slices, tcgen05 S = Q K^T and O += P V with TMEM accumulators, lazy-rescale online
+// softmax, PV-MMA row sums), balanced for the unit that bounds head_dim 40: the MUFU exp2 pipe (ncu of the first
+// version, S double-buffered in TMEM and 2 CTAs per SM: XU 58 % busy, tensor 21 %, 8 softmax warps per SM).
 //   * each softmax thread pulls its whole 64-column S row into registers and releases the TMEM S buffer at once
 //     (s_free), so ONE S buffer suffices: TMEM = 64 (S) + DPAD (O) columns -> 128 columns for DPAD <= 64
 //   * with 128 TMEM columns, 2 K/V stages and ~70 KB of shared memory, THREE CTAs share an SM (12 softmax warps
 //     instead of 8) and their exp / TMEM-load / barrier phases interleave on the MUFU pipe
 //   * the rare re-reference pass works from the registers (no second TMEM read of S)
+//   * K and V travel through SEPARATE two-stage rings: the K stage of tile j is free as soon as Q K_j^T has completed
+//     (start of the softmax of tile j), so K_{j+2} is requested a whole tile earlier than a joint K/V stage (free only
+//     after P_j V_j) allows, and V_{j+1} two tiles before P_{j+1} V_{j+1} needs it.  (ncu with joint stages: the MMA warp
+//     spent 40 % of its time waiting for the 16-byte-granular head-slice gathers; a third joint stage cost the third
+//     resident CTA its shared memory and was 18 % slower.)
+//   * head_dim 40: the V box covers only the 5 real 16-byte chunks; the padded 6th chunk of every V stage is written once
+//     at kernel start (a one in column 40, zeros behind it), so the P V MMA accumulates the row sums in O's column 40
+//     without any per-tile write
 // ------------------------------------------------------------------------------------------
 // 2^x on the FMA / ALU pipes (no MUFU): Cody-Waite split x = floor(x) + f by a round-down add of 1.5 * 2^23 (floor(x)
 // lands in the low mantissa bits), degree-3 minimax polynomial of 2^f on [0, 1) (max relative error 7.5e-5, a third of
@@ -385,9 +104,11 @@ flash_attn4_kernel(const __grid_constant__ AttnMaps maps, const AttnParams p) {
   uint8_t* sP = sV + KV * Cfg::KV_BYTES;  // [2][P_BYTES]
   uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * Cfg::P_BYTES);
   uint64_t* q_full = bars;
-  uint64_t* kv_full = bars + 1;          // [KV]
-  uint64_t* kv_empty = bars + 1 + KV;    // [KV]
-  uint64_t* s_full = bars + 1 + 2 * KV;  // S_j is in TMEM
+  uint64_t* k_full = bars + 1;           // [KV] K tile landed
+  uint64_t* v_full = bars + 1 + KV;      // [KV] V tile landed
+  uint64_t* k_empty = bars + 1 + 2 * KV; // [KV] Q K_j^T has read the K stage
+  uint64_t* v_empty = bars + 1 + 3 * KV; // [KV] P_j V_j has read the V stage (also: O is quiescent up to tile j)
+  uint64_t* s_full = bars + 1 + 4 * KV;  // S_j is in TMEM
   uint64_t* s_free = s_full + 1;         // every softmax thread holds S_j in registers
   uint64_t* p_full = s_full + 2;         // [2]
   uint64_t* o_done = s_full + 4;
@@ -401,8 +122,10 @@ flash_attn4_kernel(const __grid_constant__ AttnMaps maps, const AttnParams p) {
     if (lane == 0) {
       mbar_init(q_full, 1);
       for (int i = 0; i < KV; ++i) {
-        mbar_init(&kv_full[i], 1);
-        mbar_init(&kv_empty[i], 1);
+        mbar_init(&k_full[i], 1);
+        mbar_init(&v_full[i], 1);
+        mbar_init(&k_empty[i], 1);
+        mbar_init(&v_empty[i], 1);
       }
       mbar_init(s_full, 1);
       // one arrival per softmax WARP (after a warp sync), not per thread: 128 arrivals serialise on the barrier word
@@ -431,21 +154,33 @@ flash_attn4_kernel(const __grid_constant__ AttnMaps maps, const AttnParams p) {
       constexpr uint32_t idesc_qk = umma_idesc_f16(DT<T>::umma_fmt, 128, BN, 0, 0);
       constexpr uint32_t idesc_pv = umma_idesc_f16(DT<T>::umma_fmt, 128, DPAD, 0, 1);  // B (=V) is MN-major
       const uint32_t q_addr = smem_u32(sQ);
-      auto load_kv = [&](int t) {
+      // V box: the real chunks only when the P V MMA sums the rows through the (pre-set) padded chunk
+      const uint32_t v_bytes = MSUM ? (uint32_t)(p.d / 8) * (BN * 16) : (uint32_t)Cfg::KV_BYTES;
+      auto load_k = [&](int t) {
         const int s = t % KV;
 #if RCDM_ATTN_EXPERIMENT == 5
         if (t >= KV) {  // bottleneck analysis only: no K/V traffic after the first tiles
-          mbar_expect_tx(&kv_full[s], 0);
+          mbar_expect_tx(&k_full[s], 0);
           return;
         }
 #endif
-        mbar_expect_tx(&kv_full[s], 2 * Cfg::KV_BYTES);
-        tma_load_5d(sK + s * Cfg::KV_BYTES, &maps.k, &kv_full[s], 0, t * BN, 0, head, img);
-        tma_load_5d(sV + s * Cfg::KV_BYTES, &maps.v, &kv_full[s], 0, t * BN, 0, head, img);
+        mbar_expect_tx(&k_full[s], Cfg::KV_BYTES);
+        tma_load_5d(sK + s * Cfg::KV_BYTES, &maps.k, &k_full[s], 0, t * BN, 0, head, img);
+      };
+      auto load_v = [&](int t) {
+        const int s = t % KV;
+#if RCDM_ATTN_EXPERIMENT == 5
+        if (t >= KV) {
+          mbar_expect_tx(&v_full[s], 0);
+          return;
+        }
+#endif
+        mbar_expect_tx(&v_full[s], v_bytes);
+        tma_load_5d(sV + s * Cfg::KV_BYTES, &maps.v, &v_full[s], 0, t * BN, 0, head, img);
       };
       auto mma_qk = [&](int t) {
         const int s = t % KV;
-        mbar_wait(&kv_full[s], (t / KV) & 1);
+        mbar_wait(&k_full[s], (t / KV) & 1);
         tc_fence_after();
         const uint32_t k_addr = smem_u32(sK + s * Cfg::KV_BYTES);
 #pragma unroll
@@ -454,11 +189,13 @@ flash_attn4_kernel(const __grid_constant__ AttnMaps maps, const AttnParams p) {
           const uint64_t bd = umma_smem_desc(k_addr + ks * 2 * (BN * 16), BN * 16, 128, UMMA_SWIZZLE_NONE);
           umma_f16_ss(tmem_S, ad, bd, idesc_qk, ks != 0);
         }
+        umma_commit(&k_empty[s]);  // the K stage is free once these MMAs have read it
         umma_commit(s_full);
       };
       mbar_expect_tx(q_full, Cfg::Q_BYTES);
       tma_load_5d(sQ, &maps.q, q_full, 0, q_tile * 128, 0, head, img);
-      for (int t = 0; t < KV && t < n_kv; ++t) load_kv(t);
+      for (int t = 0; t < KV && t < n_kv; ++t) load_k(t);
+      for (int t = 0; t < KV && t < n_kv; ++t) load_v(t);
       mbar_wait(q_full, 0);
       mma_qk(0);
       for (int j = 0; j < n_kv; ++j) {
@@ -467,9 +204,20 @@ flash_attn4_kernel(const __grid_constant__ AttnMaps maps, const AttnParams p) {
           tc_fence_after();
           mma_qk(j + 1);             // overlaps the exponentials of tile j
         }
+        // refills, issued while the softmax threads work on tile j: K_{j+KV} into the stage Q K_j^T released (it completed
+        // before S_j was handed over), V_{j-1+KV} into the stage P_{j-1} V_{j-1} released (issued at the end of tile j-1)
+        if (j + KV < n_kv) {
+          mbar_wait(&k_empty[j % KV], (j / KV) & 1);
+          load_k(j + KV);
+        }
+        if (j >= 1 && j - 1 + KV < n_kv) {
+          mbar_wait(&v_empty[(j - 1) % KV], ((j - 1) / KV) & 1);
+          load_v(j - 1 + KV);
+        }
         mbar_wait(&p_full[j & 1], (j >> 1) & 1);
-        tc_fence_after();
         const int s = j % KV;
+        mbar_wait(&v_full[s], (j / KV) & 1);
+        tc_fence_after();
         const uint32_t p_addr = smem_u32(sP + (j & 1) * Cfg::P_BYTES);
         const uint32_t v_addr = smem_u32(sV + s * Cfg::KV_BYTES);
 #pragma unroll
@@ -478,12 +226,8 @@ flash_attn4_kernel(const __grid_constant__ AttnMaps maps, const AttnParams p) {
           const uint64_t bd = umma_smem_desc(v_addr + ks * 256, 128, BN * 16, UMMA_SWIZZLE_NONE);
           umma_f16_ss(tmem_O, ad, bd, idesc_pv, (j | ks) != 0);
         }
-        umma_commit(&kv_empty[s]);  // P_j V_j done: the K/V stage is free (also what the rare O rescale waits for)
+        umma_commit(&v_empty[s]);  // P_j V_j done: the V stage is free (also what the rare O rescale waits for)
         if (j == n_kv - 1) umma_commit(o_done);
-        if (j + KV < n_kv) {
-          mbar_wait(&kv_empty[s], (j / KV) & 1);
-          load_kv(j + KV);
-        }
       }
     }
   } else {
@@ -494,6 +238,17 @@ flash_attn4_kernel(const __grid_constant__ AttnMaps maps, const AttnParams p) {
     float m_run = -INFINITY, l_run = 0.f;
     constexpr bool mma_sum = MSUM;  // spare padded column of V carries ones: the P V MMA accumulates the row sums
     using T2 = typename DT<T>::T2;
+    if (mma_sum && row < BN) {
+      // the padded chunk of every V stage (never touched by TMA: the V box ends at the last real chunk): [1, 0, ..., 0];
+      // made visible to the tensor core by the fence that precedes this thread's first p_full arrival
+      uint4 one = make_uint4(0u, 0u, 0u, 0u);
+      *reinterpret_cast<T*>(&one) = DT<T>::from_f(1.0f);
+      for (int c = p.d / 8; c < DPAD / 8; ++c)  // (further padded chunks, if any: zeros)
+#pragma unroll
+        for (int s = 0; s < KV; ++s)
+          *reinterpret_cast<uint4*>(sV + s * Cfg::KV_BYTES + c * (BN * 16) + row * 16) =
+              c == p.d / 8 ? one : make_uint4(0u, 0u, 0u, 0u);
+    }
 
     for (int j = 0; j < n_kv; ++j) {
       mbar_wait(s_full, j & 1);
@@ -507,8 +262,6 @@ flash_attn4_kernel(const __grid_constant__ AttnMaps maps, const AttnParams p) {
       if (lane == 0) mbar_arrive(s_free);
       uint8_t* sP_row = sP + (j & 1) * Cfg::P_BYTES + row * 16;
       const int kv_valid = min(BN, p.S_kv - j * BN);
-      if (mma_sum && row < BN)  // V tile j has landed (the MMA thread waited for it before S_j): set its ones column
-        *reinterpret_cast<T*>(sV + (j % KV) * Cfg::KV_BYTES + (p.d / 8) * (BN * 16) + row * 16) = DT<T>::from_f(1.0f);
       if (kv_valid < BN) {
 #pragma unroll
         for (int i = 0; i < BN; ++i)
@@ -569,7 +322,7 @@ flash_attn4_kernel(const __grid_constant__ AttnMaps maps, const AttnParams p) {
           const float sum2 = exp_pass(m_new, pmax);
           // O (incl. the row-sum column) must be quiescent: P_{j-1} V_{j-1} done = its K/V stage released.  (That
           // barrier cannot run ahead: its next completion needs P_{j-1+KV} from these same threads.)
-          mbar_wait(&kv_empty[(j - 1) % KV], ((j - 1) / KV) & 1);
+          mbar_wait(&v_empty[(j - 1) % KV], ((j - 1) / KV) & 1);
           tc_fence_after();
 #pragma unroll 1
           for (int c = 0; c < DPAD; c += 16) {

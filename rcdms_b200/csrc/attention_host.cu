@@ -34,7 +34,8 @@ bool attn_prepare(const AttnDesc& d, AttnLaunch* l, std::string* err) {
   l->dt = d.dt;
   if (!head_map(&l->maps.q, d.q, d.ldq, d.S_q, d.heads, d.d, d.batch, dpad, 128, err)) return false;
   if (!head_map(&l->maps.k, d.k, d.ldkv, d.S_kv, d.heads, d.d, d.batch, dpad, 64, err)) return false;
-  if (!head_map(&l->maps.v, d.v, d.ldkv, d.S_kv, d.heads, d.d, d.batch, dpad, 64, err)) return false;
+  // V: only the real 16-byte chunks when the head dim leaves a padded chunk (the kernel presets that chunk, see MSUM)
+  if (!head_map(&l->maps.v, d.v, d.ldkv, d.S_kv, d.heads, d.d, d.batch, d.d < dpad ? d.d : dpad, 64, err)) return false;
   l->p.S_q = d.S_q;
   l->p.S_kv = d.S_kv;
   l->p.heads = d.heads;
@@ -47,11 +48,8 @@ bool attn_prepare(const AttnDesc& d, AttnLaunch* l, std::string* err) {
   return true;
 }
 
-static int attn_version() { return opt(OPT_ATTN_V); }  // 3: previous generation (double-buffered S in TMEM); default 4
 template <typename T, int DPAD> static void launch_one(const AttnLaunch& l, cudaStream_t s) {
-  if (attn_version() == 3)
-    launch_k(flash_attn_kernel<T, DPAD>, l.grid, dim3(160), AttnCfg<DPAD>::SMEM_BYTES, s, l.maps, l.p);
-  else if (l.p.d < DPAD)
+  if (l.p.d < DPAD)
     launch_k(flash_attn4_kernel<T, DPAD, true>, l.grid, dim3(160), Attn4Cfg<DPAD>::SMEM_BYTES, s, l.maps, l.p);
   else
     launch_k(flash_attn4_kernel<T, DPAD, false>, l.grid, dim3(160), Attn4Cfg<DPAD>::SMEM_BYTES, s, l.maps, l.p);
@@ -71,10 +69,7 @@ void attn_launch(const AttnLaunch& l, cudaStream_t s) {
 }
 
 template <typename T, int DPAD> static cudaError_t set_attr() {
-  cudaError_t e = cudaFuncSetAttribute(flash_attn_kernel<T, DPAD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       AttnCfg<DPAD>::SMEM_BYTES);
-  if (e == cudaSuccess)
-    e = cudaFuncSetAttribute(flash_attn4_kernel<T, DPAD, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  cudaError_t e = cudaFuncSetAttribute(flash_attn4_kernel<T, DPAD, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              Attn4Cfg<DPAD>::SMEM_BYTES);
   if (e == cudaSuccess)
     e = cudaFuncSetAttribute(flash_attn4_kernel<T, DPAD, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,

@@ -72,8 +72,8 @@ bool encode_tmap(CUtensorMap* out, const void* base, int rank, const uint64_t* d
 // ------------------------------------------------------------------------------------------
 // GEMM prepare / launch
 // ------------------------------------------------------------------------------------------
-static std::atomic<int> g_opts[OPT_COUNT] = {{0}, {24}, {1}, {1}, {4}, {1}, {1}, {1}, {40}, {1}, {1}, {1}};
-static const char* const g_opt_names[OPT_COUNT] = {"pdl", "sk_min", "gemm_pair", "masked_attn_mma", "attn_v",
+static std::atomic<int> g_opts[OPT_COUNT] = {{0}, {24}, {1}, {1}, {1}, {1}, {1}, {40}, {1}, {1}, {1}};
+static const char* const g_opt_names[OPT_COUNT] = {"pdl", "sk_min", "gemm_pair", "masked_attn_mma",
                                                     "temporal_wide", "temporal_wide_all", "temporal_tiled",
                                                     "temporal_smem_kb", "gn_fused", "ln_wide", "gn_stats"};
 int opt(int id) { return g_opts[id].load(std::memory_order_relaxed); }
@@ -161,7 +161,7 @@ bool gemm_gn_stats_ok(int M, int N, int hw) { return N % 160 == 0 && M % 128 == 
 static int pick_bn(const GemmDesc& d) {
   if (d.gn_acc) return 160;
   if (d.force_bn) return d.force_bn;
-  if (d.geglu) return GEGLU_BN;
+  if (d.geglu) return geglu_bn(d.N);
   if (d.N % 160 == 0) return 160;
   if (d.N <= 64) return 64;
   return 128;

@@ -2,8 +2,9 @@
 //
 //   D[M, N] = sum over K-segments of A_seg[M, K_seg] * W[N, K_total]^T   (+ epilogue)
 //
-// Persistent kernel, one CTA per SM, looping over 128 x BN output tiles.  Warp roles (192 threads):
-//   warp 0     TMA producer  (one elected lane)  : HBM/L2 -> 128B-swizzled smem ring (5-6 stages), runs ahead
+// Persistent kernel, one CTA per SM, looping over 128 x BN output tiles.  Warp roles:
+//   warp 0, 11 TMA producers (one elected lane each; they take the k-blocks alternately, see RCDM_GEMM_PRODUCERS)
+//                                                : HBM/L2 -> 128B-swizzled smem ring (4-6 stages), run ahead
 //                                                  across tile boundaries
 //   warp 1     MMA issuer    (one elected lane)  : tcgen05.mma into one of TWO TMEM accumulators; owns TMEM alloc
 //   warps 2-9  epilogue (8 warps)                : tcgen05.ld -> scale * acc + vector (+GEGLU) (+residual tile, which the
@@ -49,6 +50,14 @@
 // than 2 groups (8 warps, 168 registers) on the small-K GEMMs, so 2 is the product setting.
 #ifndef RCDM_EPI_GROUPS
 #define RCDM_EPI_GROUPS 2
+#endif
+// TMA producer threads (one elected lane each of RCDM_GEMM_PRODUCERS warps; k-block g of a CTA is loaded by producer
+// g % RCDM_GEMM_PRODUCERS).  Measured with scripts/micro/tma_box_bench.cu on the K = 320 access pattern (A 16 KB + B 20 KB
+// boxes, L2-resident): ONE issuing thread sustains 34 B/clk/SM whatever the ring depth (each cp.async.bulk.tensor costs its
+// issuing thread ~500 cycles before the next one leaves), TWO threads in different warps 58-60 B/clk/SM - and the 128 x 160
+// tile needs 36 KB per 320 MMA cycles.
+#ifndef RCDM_GEMM_PRODUCERS
+#define RCDM_GEMM_PRODUCERS 2
 #endif
 
 namespace rcdm {
@@ -181,7 +190,10 @@ template <int BN, bool PAIR = false> struct GemmCfg {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int NG = RCDM_EPI_GROUPS;   // column groups; 4 * NG epilogue warps
   static constexpr int QW = BN / NG;           // accumulator columns per epilogue warp
-  static constexpr int THREADS = 64 + 128 * NG + 32;  // producer, MMA, 4 * NG epilogue warps, store warp
+  static constexpr int NPROD = RCDM_GEMM_PRODUCERS;
+  // producer 0, MMA, 4 * NG epilogue warps, store warp, producers 1..NPROD-1
+  static constexpr int THREADS = 64 + 128 * NG + 32 + 32 * (NPROD - 1);
+  static constexpr int STORE_WARP = 2 + 4 * NG;
   // staging buffer = the 128 x BN 16-bit output tile as NG dense [128 rows][QW] parts (TMA box layout); two buffers
   // (tile parity) so the residual of tile i+1 loads while tile i is written and stored
   static constexpr int PART_BYTES = 128 * QW * 2;
@@ -274,9 +286,12 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
   const uint32_t tmem_base = *tmem_slot;
   pdl_sync();  // everything above overlapped the previous kernel's tail; global memory is touched only below
 
-  if (warp == 0) {
-    // =================================== TMA producer ===================================
+  if (warp == 0 || warp > Cfg::STORE_WARP) {
+    // =================================== TMA producers ===================================
+    // every producer walks the same (tile, k-block) sequence; k-block number g of this CTA belongs to producer g % NPROD
     if (elect_one()) {
+      const int pid = warp == 0 ? 0 : warp - Cfg::STORE_WARP;
+      int turn = 0;  // g % NPROD
       int stage = 0;
       uint32_t phase = 0;
       GemmWork work(p, wid, nworkers);
@@ -332,6 +347,7 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
             dx = kx >> 1;
             mi = sg.tmap + (ky & 1) * 2 + (kx & 1);
           }
+          if (turn == pid) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           void* sa = smem_a + stage * Cfg::A_BYTES;
           void* sb = smem_b + stage * Cfg::B_BYTES;
@@ -365,6 +381,8 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
             tma_load_2d(sb, &maps.b, &full_bar[stage], kb * 64, n_tile * BN);
 #endif
           }
+          }
+          if (++turn == Cfg::NPROD) turn = 0;
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
@@ -891,7 +909,7 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
         release_acc(acc);
       }
     }
-  } else {
+  } else if (warp == Cfg::STORE_WARP) {
     // =================================== store warp ===================================
     // Walks the output-producing work items of this CTA in order.  Item o uses staging buffer o & 1:
     //   [residual of item o TMA-loaded into it] -> epilogue warps turn it into the output tile -> stg_full[o & 1]

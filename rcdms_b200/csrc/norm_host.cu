@@ -106,20 +106,20 @@ void gn_configure_from_stats(GnLaunch* l, int dt, const void* x0, int C0, const 
   a.acc0 = acc0;
   a.acc1 = acc1;
   a.hw = hw;
-  // pure streaming pass: ~8 CTAs per SM in flight; a CTA's rows lie inside one statistic batch
-  int target = (num_sms() * 8) / a.nstat;
-  if (target < 1) target = 1;
-  int chunks = 1;
-  for (int c = target; c >= 1; --c)
-    if (rows_per_stat % c == 0 && rows_per_stat / c >= 4) {
-      chunks = c;
-      break;
-    }
-  a.rows_per_cta = rows_per_stat / chunks;
+  // pure streaming pass: 2 CTAs per SM (what the kernel's registers allow), every CTA inside one statistic batch; the
+  // chunk count need not divide the batch (the kernel clips the last chunk)
+  int chunks = (num_sms() * 2) / a.nstat;
+  if (chunks < 1) chunks = 1;
+  if (chunks > rows_per_stat) chunks = rows_per_stat;
+  a.rows_per_cta = (rows_per_stat + chunks - 1) / chunks;
+  chunks = (rows_per_stat + a.rows_per_cta - 1) / a.rows_per_cta;  // drop CTAs that would own no rows
   const int vecs = C / 8;
-  int k = (256 + vecs - 1) / vecs;  // >= 8 * groups threads for the statistics prologue
-  while (vecs * k < 8 * groups) ++k;
+  // k row lanes: ~320 threads, at most 384, at least the 8 * groups threads of the statistics prologue
+  int k = 320 / vecs;
+  if (k < 1) k = 1;
+  while (vecs * (k + 1) <= 384 && vecs * k < 288) ++k;
   l->threads = (vecs * k + 31) / 32 * 32;
+  if (l->threads < 8 * groups) l->threads = 8 * groups;
   l->grid = dim3(chunks, a.nstat);
   l->dt = dt;
   l->from_stats = 1;

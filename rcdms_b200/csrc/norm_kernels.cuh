@@ -194,12 +194,15 @@ __global__ void gn_apply_kernel(const GnArgs a) {
 }
 
 // GroupNorm apply with the statistics taken from the PRODUCING GEMMs' epilogues (gemm_tcgen05.cuh, GN = true): no
-// statistics pass over the tensor and no grid barrier - one streaming read + one write at full occupancy.
+// statistics pass over the tensor and no grid barrier - one streaming read + one write.  Two CTAs per SM (register bound),
+// each walking ~rows / (2 * #SMs) rows, so the statistics prologue (one L2 round trip + the fp64 fold) is paid once per SM
+// slot and overlaps the first row loads.  (ncu, round 2: with 16-64 rows per CTA the 640-CTA grid ran 2.2 waves of
+// prologue-dominated CTAs: 24.5 us for the 52 MB of the 64x64-latent tensors, 2.1 TB/s.)
 // Prologue (per CTA): 8 lanes per group fold the 10-channel chunk accumulators of the group (over the frames of the
 // statistic batch and across the two tensors of an un-materialised skip concat) in double precision, in a fixed order,
 // into mean / rstd.  Same CTA / thread geometry as gn_apply_kernel; blockDim.x >= 8 * groups.
 template <typename T>
-__global__ void gn_apply_stats_kernel(const GnArgs a) {
+__global__ void __launch_bounds__(384, 2) gn_apply_stats_kernel(const GnArgs a) {
   __shared__ float2 gstat[64];
   const int C = a.C0 + a.C1;
   const int vecs = C / 8;
@@ -214,6 +217,8 @@ __global__ void gn_apply_stats_kernel(const GnArgs a) {
   const int ld = c < a.C0 ? a.C0 : a.C1;
   const int cc = c < a.C0 ? c : c - a.C0;
   const size_t row0 = (size_t)sb * a.rows_per_stat + (size_t)chunk * a.rows_per_cta;
+  // the grid is sized for the machine (2 CTAs per SM), not for a divisor of the batch: the last chunk may be short
+  const int nrows = max(0, min(a.rows_per_cta, a.rows_per_stat - chunk * a.rows_per_cta));
   pdl_sync();
   // ---- everything that does not depend on the statistics is requested first, so the L2 round trips of the accumulator
   // reads, of gamma / beta and of the first rows overlap instead of following one another
@@ -223,7 +228,7 @@ __global__ void gn_apply_stats_kernel(const GnArgs a) {
   if (worker) {
 #pragma unroll
     for (int u = 0; u < PRE; ++u)
-      if (rl + u * k < a.rows_per_cta) raw[u] = __ldcg(reinterpret_cast<const uint4*>(src + (row0 + rl + u * k) * ld + cc));
+      if (rl + u * k < nrows) raw[u] = __ldcg(reinterpret_cast<const uint4*>(src + (row0 + rl + u * k) * ld + cc));
     const float4 g0 = __ldg(reinterpret_cast<const float4*>(a.gamma + c)), g1 = __ldg(reinterpret_cast<const float4*>(a.gamma + c + 4));
     const float4 b0 = __ldg(reinterpret_cast<const float4*>(a.beta + c)), b1 = __ldg(reinterpret_cast<const float4*>(a.beta + c + 4));
     gam[0] = g0.x, gam[1] = g0.y, gam[2] = g0.z, gam[3] = g0.w, gam[4] = g1.x, gam[5] = g1.y, gam[6] = g1.z, gam[7] = g1.w;
@@ -300,17 +305,17 @@ __global__ void gn_apply_stats_kernel(const GnArgs a) {
   };
   // software pipeline: the next PRE rows are requested before the current PRE are normalised and stored
   int r = rl;
-  while (r < a.rows_per_cta) {
+  while (r < nrows) {
     uint4 cur[PRE];
 #pragma unroll
     for (int u = 0; u < PRE; ++u) cur[u] = raw[u];
     const int rn = r + PRE * k;
 #pragma unroll
     for (int u = 0; u < PRE; ++u)
-      if (rn + u * k < a.rows_per_cta) raw[u] = __ldcg(reinterpret_cast<const uint4*>(src + (row0 + rn + u * k) * ld + cc));
+      if (rn + u * k < nrows) raw[u] = __ldcg(reinterpret_cast<const uint4*>(src + (row0 + rn + u * k) * ld + cc));
 #pragma unroll
     for (int u = 0; u < PRE; ++u)
-      if (r + u * k < a.rows_per_cta) emit(cur[u], row0 + r + u * k);
+      if (r + u * k < nrows) emit(cur[u], row0 + r + u * k);
     r = rn;
   }
 }

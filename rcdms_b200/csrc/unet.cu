@@ -136,9 +136,9 @@ struct Builder {
   }
   void ff(const std::string& p, int C, Mat& ff1, Vec& ff1b, Mat& ff2, Vec& ff2b) {
     ff1 = mat(8 * C, C);
-    slot(p + ".net.0.proj.weight", {8 * C, C}, SLOT_MAT, ff1.off, C, 0, 0, GEGLU_BN);
+    slot(p + ".net.0.proj.weight", {8 * C, C}, SLOT_MAT, ff1.off, C, 0, 0, geglu_bn(8 * C));
     ff1b = vec(8 * C);
-    slot(p + ".net.0.proj.bias", {8 * C}, SLOT_VEC, ff1b.off, 0, 0, 0, GEGLU_BN);
+    slot(p + ".net.0.proj.bias", {8 * C}, SLOT_VEC, ff1b.off, 0, 0, 0, geglu_bn(8 * C));
     ff2 = lin(p + ".net.2.weight", C, 4 * C);
     ff2b = vslot(p + ".net.2.bias", C);
   }
@@ -557,7 +557,7 @@ struct Planner {
     auto it = h->tune_cache.find(key);
     if (it == h->tune_cache.end()) {
       std::vector<int> bns;
-      if (d.geglu) bns = {GEGLU_BN};
+      if (d.geglu) bns = {geglu_bn(d.N)};
       else if (d.stats_out) bns = {0};  // the consumer reads 2 * N-tiles statistic parts: keep the heuristic width
       else {
         bns = {64, 128};
@@ -647,7 +647,7 @@ struct Planner {
     GnLaunch l;
     // algorithmic bytes: one read + one write of the tensor
     const double bytes = 2.0 * rows(x0) * (x0.C + (x1 ? x1->C : 0)) * 2.0;
-    if (x0.gn != NO_GN && (!x1 || x1->gn != NO_GN)) {
+    if (x0.gn != NO_GN && (!x1 || x1->gn != NO_GN) && x0.C + (x1 ? x1->C : 0) <= 3072) {
       // statistics were emitted by the producing GEMMs' epilogues: one streaming normalise (+SiLU) pass
       gn_configure_from_stats(&l, h->dt, p(x0.off), x0.C, gnp(x0.gn), x1 ? p(x1->off) : nullptr, x1 ? x1->C : 0,
                               x1 ? gnp(x1->gn) : nullptr, rows(x0), per_frame ? hw : h->F * hw, hw,
