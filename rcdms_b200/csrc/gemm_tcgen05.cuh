@@ -32,6 +32,7 @@
 // Segments accumulate into the same TMEM tile, which is how conv2 + the 1x1 shortcut of a resblock (whose input
 // is the un-materialised concat [h | skip]) become a single launch.
 #pragma once
+#include <type_traits>
 #include "common.cuh"
 
 // Compile-time experiment switch for bottleneck analysis (never set in a product build; scripts/build_variants.sh):
@@ -139,6 +140,7 @@ __host__ __device__ __forceinline__ double gn_fixed_join(unsigned long long hi, 
 // Work decomposition shared by the three warp roles (they must enumerate identical sequences).
 struct GemmWork {
   int sk, num_tiles, num_kb, step, tile;
+  int nn, step_m, step_n, cur_m, cur_n;  // (m, n) of `tile`, advanced without a division per tile (round-robin mode)
   long long u, u_end;
   __device__ GemmWork(const GemmParams& p, int bid, int nblk) {
     sk = p.sk;
@@ -146,26 +148,46 @@ struct GemmWork {
     num_kb = p.num_kb;
     step = nblk;
     tile = bid;
+    nn = p.num_n_tiles;
+    step_m = nblk / nn;
+    step_n = nblk - step_m * nn;
+    cur_m = bid / nn;
+    cur_n = bid - cur_m * nn;
     const long long U = (long long)num_tiles * num_kb;
     u = U * bid / nblk;
     u_end = U * (bid + 1) / nblk;
   }
-  __device__ bool next(int& t, int& kb0, int& kb1) {
+  // next work item: tile index t = mt * num_n_tiles + nt, k-block range [kb0, kb1)
+  __device__ bool next(int& t, int& kb0, int& kb1, int& mt, int& nt) {
     if (!sk) {
       if (tile >= num_tiles) return false;
       t = tile;
+      mt = cur_m;
+      nt = cur_n;
       kb0 = 0;
       kb1 = num_kb;
       tile += step;
+      cur_m += step_m;
+      cur_n += step_n;
+      if (cur_n >= nn) {
+        cur_n -= nn;
+        ++cur_m;
+      }
       return true;
     }
     if (u >= u_end) return false;
     t = (int)(u / num_kb);
+    mt = t / nn;
+    nt = t - mt * nn;
     kb0 = (int)(u - (long long)t * num_kb);
     const long long len = (u_end - u) < (long long)(num_kb - kb0) ? (u_end - u) : (long long)(num_kb - kb0);
     kb1 = kb0 + (int)len;
     u += len;
     return true;
+  }
+  __device__ bool next(int& t, int& kb0, int& kb1) {
+    int mt, nt;
+    return next(t, kb0, kb1, mt, nt);
   }
 };
 
@@ -295,10 +317,9 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
       int stage = 0;
       uint32_t phase = 0;
       GemmWork work(p, wid, nworkers);
-      int tile, kb0, kb1;
-      while (work.next(tile, kb0, kb1)) {
-        const int n_tile = tile % p.num_n_tiles;
-        const int m_tile = PAIR ? 2 * (tile / p.num_n_tiles) + (int)rank : tile / p.num_n_tiles;
+      int tile, kb0, kb1, mt_, n_tile;
+      while (work.next(tile, kb0, kb1, mt_, n_tile)) {
+        const int m_tile = PAIR ? 2 * mt_ + (int)rank : mt_;
         int t = m_tile;  // conv tile origin (only used by conv segments)
         const int tx = t % p.tiles_x;
         t /= p.tiles_x;
@@ -474,7 +495,7 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
     int it = 0;
     int ot = 0;  // output-producing work items so far (stream-K partial dumps do not count)
     GemmWork work(p, wid, nworkers);
-    int tile, kb0, kb1;
+    int tile, kb0, kb1, mt_, n_tile;
     // "accumulator drained": in a pair every epilogue thread of both CTAs arrives on the LEADER's barrier
     // one arrival per warp (after a warp sync), not per thread: 256 serialised arrivals on one mbarrier per tile were
     // a measurable part of the per-tile latency chain  epilogue -> tmem_empty -> next MMA
@@ -486,9 +507,8 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
         else mbar_arrive(&tmem_empty_bar[acc]);
       }
     };
-    for (; work.next(tile, kb0, kb1); ++it) {
-      const int n_tile = tile % p.num_n_tiles;
-      const int m_tile = PAIR ? 2 * (tile / p.num_n_tiles) + (int)rank : tile / p.num_n_tiles;
+    for (; work.next(tile, kb0, kb1, mt_, n_tile); ++it) {
+      const int m_tile = PAIR ? 2 * mt_ + (int)rank : mt_;
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       const uint32_t taddr = tmem_base + acc * Cfg::ACC_STRIDE + (uint32_t(q * 32) << 16);
@@ -672,8 +692,13 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
         for (int i = 0; i < GNC; ++i) gn_s[i] = gn_ss[i] = 0.f;
         using T2 = typename DT<T>::T2;
         // 8 outputs at columns c.. of this warp's slice; returns them packed.  rv_pre: the residual values of these 8
-        // columns when the caller fetched them ahead (see the software pipeline below), else read from the staging row here
-        auto finish8 = [&](float* v, int c, const uint4* rv_pre = nullptr) -> uint4 {
+        // columns when the caller fetched them ahead (see the software pipeline below), else read from the staging row here.
+        // RESC / STC (std::bool_constant): residual add / row statistics, compile-time so that the unrolled column loop is
+        // straight-line code (ncu, K = 320 GEMMs: with run-time tests per 8-column step a quarter of the epilogue warps'
+        // samples were instruction-fetch stalls behind the ~60 branches per tile, another tenth branch resolution).
+        // Columns beyond N need no test: their accumulators, epilogue-vector entries and (TMA zero-filled) residual values
+        // are all zero, so they add nothing to the statistics; a warp whose columns lie wholly beyond N passes STC = false.
+        auto finish8 = [&](auto RESC, auto STC, float* v, int c, const uint4* rv_pre = nullptr) -> uint4 {
           if constexpr (ACT) {
             if (p.act == 1) {
 #pragma unroll
@@ -685,14 +710,14 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
           }
           uint4 pk = pack8<T>(v);
           uint4* dst = reinterpret_cast<uint4*>(srow + c * 2);
-          if (res) {
+          if constexpr (decltype(RESC)::value) {
             const uint4 rv = rv_pre ? *rv_pre : *dst;
             T2* a2 = reinterpret_cast<T2*>(&pk);
             const T2* b2 = reinterpret_cast<const T2*>(&rv);
 #pragma unroll
             for (int i = 0; i < 4; ++i) a2[i] = __hadd2(a2[i], b2[i]);
           }
-          if (p.stats_out && n_warp + c < n_total) {
+          if constexpr (decltype(STC)::value) {
             float f8[8];
             unpack8<T>(pk, f8);
 #pragma unroll
@@ -703,6 +728,17 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
           }
           *dst = pk;
           return pk;
+        };
+        const bool do_stats = p.stats_out != nullptr && n_warp < n_total;
+        // run-time flags -> one of the four instantiations of `fn` (once per tile, outside the column loop)
+        auto dispatch = [&](auto&& fn) {
+          if (res) {
+            if (do_stats) fn(std::true_type{}, std::true_type{});
+            else fn(std::true_type{}, std::false_type{});
+          } else {
+            if (do_stats) fn(std::false_type{}, std::true_type{});
+            else fn(std::false_type{}, std::false_type{});
+          }
         };
         // GroupNorm chunk sums of 8 final values at columns c.. ; called only where c is a compile-time constant after
         // unrolling (the accumulators must stay in registers)
@@ -731,7 +767,7 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
 #pragma unroll
               for (int i = 0; i < 8; ++i)
                 v[i] = fmaf(__uint_as_float(r[i]), scale, (col + i < p.N) ? __ldg(ln_crow + col + i) : 0.f);
-              finish8(v, c);
+              dispatch([&](auto RESC, auto STC) { finish8(RESC, STC, v, c); });
             }
           } else {
 #pragma unroll 1
@@ -746,7 +782,7 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
               for (int i = 0; i < 8; ++i)
                 v[i] = fmaf(__uint_as_float(rh[i]), scale, __ldg(ln_crow + colh + i)) *
                        gelu_erf_f(fmaf(__uint_as_float(rg[i]), scale, __ldg(ln_crow + colh + TH + i)));
-              finish8(v, c);
+              finish8(std::false_type{}, std::false_type{}, v, c);  // (GEGLU: no residual, no statistics)
             }
           }
         } else if (!p.geglu) {
@@ -755,39 +791,41 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
           // step s is computed and stored.  (ncu, K = 320 GEMMs: with the loads issued where they are used, every FFMA
           // waited ~30 cycles on its LDS - the compiler may not hoist a shared load above the preceding staging store -
           // and the 2 epilogue warps per scheduler could not hide it: 0.2 instructions per cycle.)
-          constexpr int SPC = CW / 8;     // steps per TMEM chunk
-          constexpr int NS = QW / 8;      // steps per tile
-          uint32_t r[2][CW];
-          float4 bq[2][2];
-          uint4 rq[2];
-          auto fetch = [&](int st, int slot) {
-            bq[slot][0] = *reinterpret_cast<const float4*>(bsm + st * 8);  // smem broadcast
-            bq[slot][1] = *reinterpret_cast<const float4*>(bsm + st * 8 + 4);
-            if (res) rq[slot] = *reinterpret_cast<const uint4*>(srow + st * 16);
-          };
-          ld_chunk(taddr + cg * QW, r[0]);
-          fetch(0, 0);
+          dispatch([&](auto RESC, auto STC) {
+            constexpr int SPC = CW / 8;     // steps per TMEM chunk
+            constexpr int NS = QW / 8;      // steps per tile
+            uint32_t r[2][CW];
+            float4 bq[2][2];
+            uint4 rq[2];
+            auto fetch = [&](int st, int slot) {
+              bq[slot][0] = *reinterpret_cast<const float4*>(bsm + st * 8);  // smem broadcast
+              bq[slot][1] = *reinterpret_cast<const float4*>(bsm + st * 8 + 4);
+              if constexpr (decltype(RESC)::value) rq[slot] = *reinterpret_cast<const uint4*>(srow + st * 16);
+            };
+            ld_chunk(taddr + cg * QW, r[0]);
+            fetch(0, 0);
 #pragma unroll
-          for (int st = 0; st < NS; ++st) {
-            const int ci = st / SPC, g = st % SPC;
-            if (g == 0) {
-              tmem_wait_ld();
-              if (ci + 1 < NCH) ld_chunk(taddr + cg * QW + (ci + 1) * CW, r[(ci + 1) & 1]);
+            for (int st = 0; st < NS; ++st) {
+              const int ci = st / SPC, g = st % SPC;
+              if (g == 0) {
+                tmem_wait_ld();
+                if (ci + 1 < NCH) ld_chunk(taddr + cg * QW + (ci + 1) * CW, r[(ci + 1) & 1]);
+              }
+              if (st + 1 < NS) fetch(st + 1, (st + 1) & 1);
+              const uint32_t* rc = r[ci & 1];
+              const float4 b0 = bq[st & 1][0], b1 = bq[st & 1][1];
+              float v[8];
+              v[0] = fmaf(__uint_as_float(rc[g * 8]), scale, b0.x);
+              v[1] = fmaf(__uint_as_float(rc[g * 8 + 1]), scale, b0.y);
+              v[2] = fmaf(__uint_as_float(rc[g * 8 + 2]), scale, b0.z);
+              v[3] = fmaf(__uint_as_float(rc[g * 8 + 3]), scale, b0.w);
+              v[4] = fmaf(__uint_as_float(rc[g * 8 + 4]), scale, b1.x);
+              v[5] = fmaf(__uint_as_float(rc[g * 8 + 5]), scale, b1.y);
+              v[6] = fmaf(__uint_as_float(rc[g * 8 + 6]), scale, b1.z);
+              v[7] = fmaf(__uint_as_float(rc[g * 8 + 7]), scale, b1.w);
+              gn_add8(finish8(RESC, STC, v, st * 8, &rq[st & 1]), st * 8);
             }
-            if (st + 1 < NS) fetch(st + 1, (st + 1) & 1);
-            const uint32_t* rc = r[ci & 1];
-            const float4 b0 = bq[st & 1][0], b1 = bq[st & 1][1];
-            float v[8];
-            v[0] = fmaf(__uint_as_float(rc[g * 8]), scale, b0.x);
-            v[1] = fmaf(__uint_as_float(rc[g * 8 + 1]), scale, b0.y);
-            v[2] = fmaf(__uint_as_float(rc[g * 8 + 2]), scale, b0.z);
-            v[3] = fmaf(__uint_as_float(rc[g * 8 + 3]), scale, b0.w);
-            v[4] = fmaf(__uint_as_float(rc[g * 8 + 4]), scale, b1.x);
-            v[5] = fmaf(__uint_as_float(rc[g * 8 + 5]), scale, b1.y);
-            v[6] = fmaf(__uint_as_float(rc[g * 8 + 6]), scale, b1.z);
-            v[7] = fmaf(__uint_as_float(rc[g * 8 + 7]), scale, b1.w);
-            gn_add8(finish8(v, st * 8, &rq[st & 1]), st * 8);
-          }
+          });
         } else {
           // GEGLU: h columns [cg * QW/2, +QW/2), gate columns TH + the same; outputs QW/2 per warp.  Same software
           // pipeline: the 16 epilogue-vector values of step s+1 are requested before step s is computed.
@@ -832,7 +870,7 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
             for (int i = 0; i < 8; ++i)
               v[i] = fmaf(__uint_as_float(ph[g * 8 + i]), scale, bhv[i]) *
                      gelu_erf_f(fmaf(__uint_as_float(pg[g * 8 + i]), scale, bgv[i]));
-            finish8(v, st * 8);
+            finish8(std::false_type{}, std::false_type{}, v, st * 8);
           }
         }
         release_acc(acc);  // accumulator drained: the MMA warp may reuse it
