@@ -9,7 +9,7 @@
 // [chunk][row][8 elems]; out-of-range chunks / rows are zero-filled by TMA, which pads head_dim 40 -> 48 and
 // ragged KV lengths (context L = 85 / 91) for free.  V is consumed as an MN-major B operand, so no transpose.
 // Warps 0-3: online softmax (thread <-> query row), P written to smem as the A operand of the second GEMM.
-// Warp 4 (one lane): TMA producer + MMA issuer.
+// Warp 4 (one lane): MMA issuer.  Warp 5 (one lane): TMA loads.
 //
 // temporal_attn_kernel: the motion modules' attention over the f = 5 frames at each spatial location
 // (motion_module.py:294-354): a 5x5 problem per (location, head) -> CUDA cores, one thread per (location, head),
@@ -76,6 +76,25 @@ __device__ __forceinline__ float exp2_poly(float x) {
   return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
 }
 
+// Timeline instrumentation (variant builds only, -DRCDM_ATTN_TRACE=1; scripts/attn_trace.py): clock64 stamps of the barrier
+// hand-offs of every (CTA, K/V tile) into a device array, read back through rcdm_debug_attn_trace_read.
+#ifndef RCDM_ATTN_TRACE
+#define RCDM_ATTN_TRACE 0
+#endif
+#if RCDM_ATTN_TRACE
+constexpr int ATTN_TRACE_CTAS = 2560, ATTN_TRACE_TILES = 64;
+__device__ long long g_attn_trace[(size_t)ATTN_TRACE_CTAS * ATTN_TRACE_TILES * 16];
+__device__ int g_attn_smid[ATTN_TRACE_CTAS];
+#define ATTN_STAMP(tile, slot)                                                                                      \
+  do {                                                                                                              \
+    const int cta_ = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);                                \
+    if (cta_ < ATTN_TRACE_CTAS && (tile) < ATTN_TRACE_TILES)                                                        \
+      g_attn_trace[((size_t)cta_ * ATTN_TRACE_TILES + (tile)) * 16 + (slot)] = clock64();                           \
+  } while (0)
+#else
+#define ATTN_STAMP(tile, slot) do { } while (0)
+#endif
+
 template <int DPAD> struct Attn4Cfg {
   static constexpr int BLOCK_M = 128, BLOCK_N = 64;
   static constexpr int NCH = DPAD / 8;
@@ -86,12 +105,13 @@ template <int DPAD> struct Attn4Cfg {
   static constexpr int TMEM_COLS = (BLOCK_N + DPAD) <= 128 ? 128 : 256;
   static constexpr int SMEM_BYTES = Q_BYTES + 2 * KV_STAGES * KV_BYTES + 2 * P_BYTES + 1024 + 256;
   static constexpr int CTAS_PER_SM = DPAD <= 48 ? 3 : (DPAD <= 80 ? 2 : 1);
+  static constexpr int THREADS = 192;  // 4 softmax warps, MMA issuer, loader
 };
 
 // MSUM (compile time): the head dim leaves a spare padded column (d < DPAD), so the P V MMA accumulates the row sums
 // and the softmax threads carry no fp32 sums at all.
 template <typename T, int DPAD, bool MSUM>
-__global__ void __launch_bounds__(160, Attn4Cfg<DPAD>::CTAS_PER_SM)
+__global__ void __launch_bounds__(Attn4Cfg<DPAD>::THREADS, Attn4Cfg<DPAD>::CTAS_PER_SM)
 flash_attn4_kernel(const __grid_constant__ AttnMaps maps, const AttnParams p) {
   using Cfg = Attn4Cfg<DPAD>;
   constexpr int KV = Cfg::KV_STAGES;
@@ -149,11 +169,13 @@ flash_attn4_kernel(const __grid_constant__ AttnMaps maps, const AttnParams p) {
   const uint32_t tmem_O = tmem_base + BN;
   pdl_sync();
 
-  if (warp == 4) {
+  if (warp == 5) {
+    // =================================== loader warp (one elected lane) ===================================
+    // A thread that issues a cp.async.bulk.tensor is held ~500 cycles by it (timeline trace, scripts/attn_trace.py: with the
+    // loads issued by the MMA thread, that thread's serial work per K/V tile - Q K^T issue 350 + two loads 1080 + P V issue
+    // 480 cycles - WAS the tile period, 2400 cycles, and the softmax warps idled 35 % of the time waiting for S), so the
+    // loads have a warp of their own.
     if (elect_one()) {
-      constexpr uint32_t idesc_qk = umma_idesc_f16(DT<T>::umma_fmt, 128, BN, 0, 0);
-      constexpr uint32_t idesc_pv = umma_idesc_f16(DT<T>::umma_fmt, 128, DPAD, 0, 1);  // B (=V) is MN-major
-      const uint32_t q_addr = smem_u32(sQ);
       // V box: the real chunks only when the P V MMA sums the rows through the (pre-set) padded chunk
       const uint32_t v_bytes = MSUM ? (uint32_t)(p.d / 8) * (BN * 16) : (uint32_t)Cfg::KV_BYTES;
       auto load_k = [&](int t) {
@@ -178,34 +200,13 @@ flash_attn4_kernel(const __grid_constant__ AttnMaps maps, const AttnParams p) {
         mbar_expect_tx(&v_full[s], v_bytes);
         tma_load_5d(sV + s * Cfg::KV_BYTES, &maps.v, &v_full[s], 0, t * BN, 0, head, img);
       };
-      auto mma_qk = [&](int t) {
-        const int s = t % KV;
-        mbar_wait(&k_full[s], (t / KV) & 1);
-        tc_fence_after();
-        const uint32_t k_addr = smem_u32(sK + s * Cfg::KV_BYTES);
-#pragma unroll
-        for (int ks = 0; ks < DPAD / 16; ++ks) {
-          const uint64_t ad = umma_smem_desc(q_addr + ks * 2 * (128 * 16), 128 * 16, 128, UMMA_SWIZZLE_NONE);
-          const uint64_t bd = umma_smem_desc(k_addr + ks * 2 * (BN * 16), BN * 16, 128, UMMA_SWIZZLE_NONE);
-          umma_f16_ss(tmem_S, ad, bd, idesc_qk, ks != 0);
-        }
-        umma_commit(&k_empty[s]);  // the K stage is free once these MMAs have read it
-        umma_commit(s_full);
-      };
       mbar_expect_tx(q_full, Cfg::Q_BYTES);
       tma_load_5d(sQ, &maps.q, q_full, 0, q_tile * 128, 0, head, img);
       for (int t = 0; t < KV && t < n_kv; ++t) load_k(t);
       for (int t = 0; t < KV && t < n_kv; ++t) load_v(t);
-      mbar_wait(q_full, 0);
-      mma_qk(0);
+      // refills in the order the stages come free: K_{j+KV} into the stage Q K_j^T released (it completed before S_j was
+      // handed to the softmax threads), V_{j-1+KV} into the stage P_{j-1} V_{j-1} released (issued at the end of tile j-1)
       for (int j = 0; j < n_kv; ++j) {
-        if (j + 1 < n_kv) {
-          mbar_wait(s_free, j & 1);  // S_j now lives in the softmax threads' registers: the TMEM buffer is free
-          tc_fence_after();
-          mma_qk(j + 1);             // overlaps the exponentials of tile j
-        }
-        // refills, issued while the softmax threads work on tile j: K_{j+KV} into the stage Q K_j^T released (it completed
-        // before S_j was handed over), V_{j-1+KV} into the stage P_{j-1} V_{j-1} released (issued at the end of tile j-1)
         if (j + KV < n_kv) {
           mbar_wait(&k_empty[j % KV], (j / KV) & 1);
           load_k(j + KV);
@@ -214,20 +215,71 @@ flash_attn4_kernel(const __grid_constant__ AttnMaps maps, const AttnParams p) {
           mbar_wait(&v_empty[(j - 1) % KV], ((j - 1) / KV) & 1);
           load_v(j - 1 + KV);
         }
-        mbar_wait(&p_full[j & 1], (j >> 1) & 1);
-        const int s = j % KV;
-        mbar_wait(&v_full[s], (j / KV) & 1);
-        tc_fence_after();
-        const uint32_t p_addr = smem_u32(sP + (j & 1) * Cfg::P_BYTES);
-        const uint32_t v_addr = smem_u32(sV + s * Cfg::KV_BYTES);
+      }
+    }
+  } else if (warp == 4) {
+    // =================================== MMA issuer (one elected lane) ===================================
+    // This thread shares its scheduler with softmax warp 0 of every resident CTA (timeline trace: warp 0 lagged the other
+    // three by ~300 cycles per tile while this loop rebuilt its 14 shared-memory descriptors per tile, ~220 instructions),
+    // so everything that does not change is computed once: the descriptors of Q, of both K / V stages and of both P
+    // buffers live in registers, and the tile loop is unrolled by the stage / buffer parity.
+    if (elect_one()) {
+      static_assert(KV == 2, "the MMA loop is unrolled by the parity of the two K/V stages and P buffers");
+      constexpr uint32_t idesc_qk = umma_idesc_f16(DT<T>::umma_fmt, 128, BN, 0, 0);
+      constexpr uint32_t idesc_pv = umma_idesc_f16(DT<T>::umma_fmt, 128, DPAD, 0, 1);  // B (=V) is MN-major
+      constexpr int NQK = DPAD / 16, NPV = BN / 16;
+      uint64_t qd[NQK], kd[2][NQK], pd[2][NPV], vd[2][NPV];
 #pragma unroll
-        for (int ks = 0; ks < BN / 16; ++ks) {
-          const uint64_t ad = umma_smem_desc(p_addr + ks * 4096, 2048, 128, UMMA_SWIZZLE_NONE);
-          const uint64_t bd = umma_smem_desc(v_addr + ks * 256, 128, BN * 16, UMMA_SWIZZLE_NONE);
-          umma_f16_ss(tmem_O, ad, bd, idesc_pv, (j | ks) != 0);
+      for (int ks = 0; ks < NQK; ++ks) {
+        qd[ks] = umma_smem_desc(smem_u32(sQ) + ks * 2 * (128 * 16), 128 * 16, 128, UMMA_SWIZZLE_NONE);
+#pragma unroll
+        for (int st = 0; st < 2; ++st)
+          kd[st][ks] = umma_smem_desc(smem_u32(sK + st * Cfg::KV_BYTES) + ks * 2 * (BN * 16), BN * 16, 128, UMMA_SWIZZLE_NONE);
+      }
+#pragma unroll
+      for (int ks = 0; ks < NPV; ++ks)
+#pragma unroll
+        for (int st = 0; st < 2; ++st) {
+          pd[st][ks] = umma_smem_desc(smem_u32(sP + st * Cfg::P_BYTES) + ks * 4096, 2048, 128, UMMA_SWIZZLE_NONE);
+          vd[st][ks] = umma_smem_desc(smem_u32(sV + st * Cfg::KV_BYTES) + ks * 256, 128, BN * 16, UMMA_SWIZZLE_NONE);
         }
-        umma_commit(&v_empty[s]);  // P_j V_j done: the V stage is free (also what the rare O rescale waits for)
+      // S_t = Q K_t^T into the (single) S buffer; st = t % 2 at compile time
+      auto mma_qk = [&](int t, auto st_c) {
+        constexpr int st = decltype(st_c)::value;
+        mbar_wait(&k_full[st], (t >> 1) & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int ks = 0; ks < NQK; ++ks) umma_f16_ss(tmem_S, qd[ks], kd[st][ks], idesc_qk, ks != 0);
+        umma_commit(&k_empty[st]);  // the K stage is free once these MMAs have read it
+        umma_commit(s_full);
+      };
+      // tile j with j % 2 == par: hand S_{j+1} to the tensor core as soon as S_j is in registers, then O += P_j V_j
+      auto step = [&](int j, auto par_c) {
+        constexpr int par = decltype(par_c)::value;
+        if (j + 1 < n_kv) {
+          mbar_wait(s_free, j & 1);  // S_j now lives in the softmax threads' registers: the TMEM buffer is free
+          ATTN_STAMP(j, 12);
+          tc_fence_after();
+          mma_qk(j + 1, std::integral_constant<int, 1 - par>{});  // overlaps the exponentials of tile j
+          ATTN_STAMP(j, 13);
+        }
+        // the one long wait of this thread (the softmax of tile j): sleep between polls, the scheduler's issue slots
+        // belong to softmax warp 0
+        mbar_wait_backoff(&p_full[par], (j >> 1) & 1, 64);
+        ATTN_STAMP(j, 14);
+        mbar_wait(&v_full[par], (j >> 1) & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int ks = 0; ks < NPV; ++ks) umma_f16_ss(tmem_O, pd[par][ks], vd[par][ks], idesc_pv, (j | ks) != 0);
+        umma_commit(&v_empty[par]);  // P_j V_j done: the V stage is free (also what the rare O rescale waits for)
+        ATTN_STAMP(j, 15);
         if (j == n_kv - 1) umma_commit(o_done);
+      };
+      mbar_wait(q_full, 0);
+      mma_qk(0, std::integral_constant<int, 0>{});
+      for (int j = 0; j < n_kv; j += 2) {
+        step(j, std::integral_constant<int, 0>{});
+        if (j + 1 < n_kv) step(j + 1, std::integral_constant<int, 1>{});
       }
     }
   } else {
@@ -250,8 +302,18 @@ flash_attn4_kernel(const __grid_constant__ AttnMaps maps, const AttnParams p) {
               c == p.d / 8 ? one : make_uint4(0u, 0u, 0u, 0u);
     }
 
+#if RCDM_ATTN_TRACE
+    if (threadIdx.x == 0) {
+      unsigned smid_;
+      asm volatile("mov.u32 %0, %%smid;" : "=r"(smid_));
+      const int cta_ = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
+      if (cta_ < ATTN_TRACE_CTAS) g_attn_smid[cta_] = (int)smid_;
+    }
+#endif
     for (int j = 0; j < n_kv; ++j) {
+      if (lane == 0) ATTN_STAMP(j, warp);
       mbar_wait(s_full, j & 1);
+      if (lane == 0) ATTN_STAMP(j, 4 + warp);
       tc_fence_after();
       uint32_t r[BN];
       tmem_ld32(tmem_S + lane_sel, r);
@@ -343,7 +405,10 @@ flash_attn4_kernel(const __grid_constant__ AttnMaps maps, const AttnParams p) {
       fence_proxy_async_smem();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&p_full[j & 1]);
+      if (lane == 0) {
+        ATTN_STAMP(j, 8 + warp);
+        mbar_arrive(&p_full[j & 1]);
+      }
     }
     // ---- normalise and store
     mbar_wait(o_done, 0);

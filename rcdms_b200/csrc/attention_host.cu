@@ -50,9 +50,9 @@ bool attn_prepare(const AttnDesc& d, AttnLaunch* l, std::string* err) {
 
 template <typename T, int DPAD> static void launch_one(const AttnLaunch& l, cudaStream_t s) {
   if (l.p.d < DPAD)
-    launch_k(flash_attn4_kernel<T, DPAD, true>, l.grid, dim3(160), Attn4Cfg<DPAD>::SMEM_BYTES, s, l.maps, l.p);
+    launch_k(flash_attn4_kernel<T, DPAD, true>, l.grid, dim3(Attn4Cfg<DPAD>::THREADS), Attn4Cfg<DPAD>::SMEM_BYTES, s, l.maps, l.p);
   else
-    launch_k(flash_attn4_kernel<T, DPAD, false>, l.grid, dim3(160), Attn4Cfg<DPAD>::SMEM_BYTES, s, l.maps, l.p);
+    launch_k(flash_attn4_kernel<T, DPAD, false>, l.grid, dim3(Attn4Cfg<DPAD>::THREADS), Attn4Cfg<DPAD>::SMEM_BYTES, s, l.maps, l.p);
 }
 template <typename T> static void launch_dt(const AttnLaunch& l, cudaStream_t s) {
   switch (l.dpad) {
@@ -239,3 +239,13 @@ void temporal_attn_launch(int dt, const void* qkv, void* out, int batch, int fra
 }
 
 }  // namespace rcdm
+
+#if RCDM_ATTN_TRACE
+// variant builds only: copy the timeline stamps (and the SM id of every CTA) to the host
+extern "C" __attribute__((visibility("default"))) int rcdm_debug_attn_trace_read(long long* stamps, int* smids) {
+  cudaDeviceSynchronize();
+  if (cudaMemcpyFromSymbol(stamps, rcdm::g_attn_trace, sizeof(rcdm::g_attn_trace)) != cudaSuccess) return 1;
+  if (cudaMemcpyFromSymbol(smids, rcdm::g_attn_smid, sizeof(rcdm::g_attn_smid)) != cudaSuccess) return 1;
+  return 0;
+}
+#endif

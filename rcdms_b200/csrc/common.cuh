@@ -155,6 +155,21 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     }
   }
 }
+// Wait with back-off, for a lone elected thread that expects to wait long (a tile's worth of another role's work).
+// mbarrier.try_wait returns after a few tens of cycles when a single divergent lane executes it (ncu, flash attention:
+// 46 tries per wait of the MMA thread on p_full, ~6 instructions each), and those issue slots come out of the softmax
+// warp that shares the scheduler; the sleep hands them back.
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity, unsigned ns) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    __nanosleep(ns);
+    if (++spins > RCDM_MBAR_SPIN_LIMIT) {
+      printf("rcdm: mbarrier wait timed out (block %d,%d,%d thread %d)\n", blockIdx.x, blockIdx.y, blockIdx.z,
+             threadIdx.x);
+      __trap();
+    }
+  }
+}
 // generic-proxy smem writes -> visible to the async proxy (TMA / tcgen05.mma operand reads)
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 

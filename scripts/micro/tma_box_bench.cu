@@ -94,6 +94,51 @@ bench_kernel(const __grid_constant__ CUtensorMap a2, const __grid_constant__ CUt
   }
 }
 
+// Does a warp that issues TMA loads slow down the OTHER warps of its scheduler (SM sub-partition)?  Warp 0 (lane 0) streams
+// 16 KB boxes through a 4-stage ring like bench_kernel; warps 4..7 (one per sub-partition: warp w runs on sub-partition
+// w % 4) each run the same dependent-FMA loop and report their elapsed clocks.  `do_tma` = 0: warp 0 idles (baseline).
+__global__ void __launch_bounds__(256, 1)
+interfere_kernel(const __grid_constant__ CUtensorMap a2, int do_tma, int iters, int fma_iters, long long* out) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int stages = 4;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)stages * 16384);
+  __shared__ volatile int stop;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < stages; ++i) mbar_init(&bars[i], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    stop = 0;
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0) {
+    if (lane == 0 && do_tma) {
+      int it = 0;
+      for (; it < iters && !stop; ++it) {
+        const int s = it % stages;
+        if (it >= stages) mbar_wait(&bars[s], ((it / stages) - 1) & 1);
+        mbar_expect_tx(&bars[s], 16384);
+        tma_load_2d(smem + (size_t)s * 16384, &a2, &bars[s], (it % 5) * 64, ((int)blockIdx.x + (it / 5) % 2 * 148) * 128);
+      }
+      // drain
+      for (int k = (it > stages ? it - stages : 0); k < it; ++k) mbar_wait(&bars[k % stages], (k / stages) & 1);
+      if (blockIdx.x == 0) out[8] = it;
+    }
+  } else if (warp >= 4) {
+    float x = 1.0f + lane * 1e-3f, y = 0.5f;
+    const long long t0 = clock64();
+#pragma unroll 1
+    for (int i = 0; i < fma_iters; ++i) {
+#pragma unroll
+      for (int k = 0; k < 16; ++k) x = fmaf(x, 0.999f, y);  // dependent chain: 1 warp alone issues every ~4 clk
+    }
+    const long long t1 = clock64();
+    if (x == 123.456f) out[9] = 1;
+    if (lane == 0 && blockIdx.x == 0) out[warp - 4] = t1 - t0;
+    __syncwarp();
+    if (warp == 4 && lane == 0) stop = 1;
+  }
+}
+
 static PFN_cuTensorMapEncodeTiled_v12000 encode_fn() {
   void* p = nullptr;
   cudaDriverEntryPointQueryResult q;
@@ -145,6 +190,20 @@ int main() {
   cudaEventCreate(&e0);
   cudaEventCreate(&e1);
   printf("sms %d, nominal %d MHz; A [%d, %d] 16-bit (%.1f MB), B [%d, %d]\n", sms, clk / 1000, M, K, M * K * 2 / 1e6, N, K);
+  {
+    long long* dout;
+    cudaMalloc(&dout, 16 * sizeof(long long));
+    cudaFuncSetAttribute(interfere_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024);
+    CUtensorMap a2 = map2d(abuf, M, K, 128);
+    for (int do_tma = 0; do_tma < 2; ++do_tma) {
+      cudaMemset(dout, 0, 16 * sizeof(long long));
+      interfere_kernel<<<sms, 256, 4 * 16384 + 256>>>(a2, do_tma, 1 << 20, 4000, dout);
+      long long h[16];
+      cudaMemcpy(h, dout, sizeof h, cudaMemcpyDeviceToHost);
+      printf("interference do_tma=%d: FMA-loop clocks of the warps on sub-partitions 0..3 = %lld %lld %lld %lld (issuer on 0; boxes issued %lld) %s\n",
+             do_tma, h[0], h[1], h[2], h[3], h[8], cudaGetLastError() == cudaSuccess ? "" : "ERR");
+    }
+  }
   struct Cfg { int mode, kb, with_b; const char* name; };
   const Cfg cfgs[] = {{0, 1, 1, "A 16K + B 20K 2-D boxes"}, {1, 2, 1, "A 32K + B 40K 3-D boxes"},
                       {2, 1, 0, "A only 16K 2-D boxes"},    {3, 2, 0, "A only 32K 3-D boxes"},
