@@ -657,7 +657,7 @@ int rcdm_gemm_rowstats(int dtype, const void* a_dev, const void* w_dev, const fl
   d.res = residual_dev;
   d.ldr = N;
   d.stats_out = reinterpret_cast<float2*>(stats_dev);
-  if (parts_out) *parts_out = gemm_stats_parts(N);
+  if (parts_out) *parts_out = gemm_stats_parts(N, M);
   GemmLaunch l;
   std::string e;
   d.sk = sk_workspace_for_stream(reinterpret_cast<cudaStream_t>(stream), &e);

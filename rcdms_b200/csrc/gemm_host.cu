@@ -111,7 +111,7 @@ bool sk_workspace_alloc(SkWorkspace* w, std::string* err) {
   if (w->ws) return true;
   const int slots = num_sms();
   cudaError_t e = cudaGetDevice(&w->device);
-  if (e == cudaSuccess) e = cudaMalloc(&w->ws, (size_t)slots * 128 * 160 * sizeof(float));
+  if (e == cudaSuccess) e = cudaMalloc(&w->ws, (size_t)slots * 128 * 192 * sizeof(float));  // one fp32 tile of the widest kernel per CTA
   if (e == cudaSuccess) e = cudaMalloc(&w->flags, (size_t)slots * sizeof(unsigned));
   if (e == cudaSuccess) e = cudaMemset(w->flags, 0, (size_t)slots * sizeof(unsigned));
   if (e != cudaSuccess) {
@@ -151,8 +151,19 @@ int gemm_set_pair(int on) {
   opt_set("gemm_pair", on < 0 ? 0 : on, &prev);
   return prev;
 }
-int gemm_stats_parts(int N) {  // one part per epilogue column group per N tile of the (heuristic) tile width
-  const int bn = (N % 160 == 0) ? 160 : (N <= 64 ? 64 : 128);
+// Tile width of a plain GEMM (single row-major K segment; no GEGLU, activation, GroupNorm statistics or forced width).
+// 160 where it divides N, else 128 / 64 - and 192 where that saves whole waves of tiles: a wave costs about the bytes a
+// CTA pulls per k-block (128 rows of A + bn rows of B), and e.g. the 16x16-latent N = K = 1280 layers of the UNet
+// (M = 2560) are 160 tiles = TWO waves on 148 SMs at width 160 but 140 tiles = one wave at width 192.
+int gemm_plain_bn(int M, int N) {
+  const int base = (N % 160 == 0) ? 160 : (N <= 64 ? 64 : 128);
+  if (N < 192) return base;
+  const long mt = (M + 127) / 128, sms = num_sms();
+  auto cost = [&](int bn) { return ((mt * ((N + bn - 1) / bn) + sms - 1) / sms) * (128 + bn); };
+  return cost(192) * 100 < cost(base) * 92 ? 192 : base;
+}
+int gemm_stats_parts(int N, int M) {  // one part per epilogue column group per N tile of the producer's tile width
+  const int bn = gemm_plain_bn(M, N);
   return RCDM_EPI_GROUPS * ((N + bn - 1) / bn);
 }
 
@@ -162,6 +173,10 @@ static int pick_bn(const GemmDesc& d) {
   if (d.gn_acc) return 160;
   if (d.force_bn) return d.force_bn;
   if (d.geglu) return geglu_bn(d.N);
+  const bool plain = d.nseg == 1 && d.seg[0].mode == SEG_PLAIN && !d.act;
+  // (a row-statistics producer must use exactly this width: its consumer sums gemm_stats_parts(N, M) parts; and a
+  //  192-wide tile excludes the CTA-pair kernel, whatever the pairing option says)
+  if (plain) return gemm_plain_bn(d.M, d.N);
   if (d.N % 160 == 0) return 160;
   if (d.N <= 64) return 64;
   return 128;
@@ -280,7 +295,7 @@ bool gemm_prepare(const GemmDesc& d, GemmLaunch* l, std::string* err) {
   // (the big 3x3 convolutions); small-K GEMMs are bound by their epilogue / L2 traffic and lose a little.
   // OPT_GEMM_PAIR = 0 never, 1 heuristic (default), 2 whenever there are >= 2 M tiles.
   const int pair_mode = pair_enabled();
-  l->pair = (!d.no_pair && !d.act && num_sms() >= 2 &&  // activation epilogues exist for the single-CTA kernel only
+  l->pair = (!d.no_pair && !d.act && bn != 192 && num_sms() >= 2 &&  // activation epilogues / 192-wide tiles: single-CTA kernel only
              ((d.force_pair && m_tiles >= 2) || (pair_mode == 2 && m_tiles >= 2) ||
               (pair_mode == 1 && kb >= 90 && m_tiles >= 16))) ? 1 : 0;
   {
@@ -347,10 +362,12 @@ bool gemm_prepare(const GemmDesc& d, GemmLaunch* l, std::string* err) {
 }
 
 template <typename T, int BN> static void launch_one(const GemmLaunch& l, cudaStream_t s) {
-  if (l.p.act) {  // GELU / SiLU epilogue (stage-1 prior): separate instantiation, see gemm_tcgen05.cuh
-    launch_k(gemm_tcgen05_kernel<T, BN, false, true>, l.grid, dim3(GemmCfg<BN, false>::THREADS),
-             GemmCfg<BN, false>::SMEM_BYTES, s, l.maps, l.p);
-    return;
+  if constexpr (BN != 192) {
+    if (l.p.act) {  // GELU / SiLU epilogue (stage-1 prior): separate instantiation, see gemm_tcgen05.cuh
+      launch_k(gemm_tcgen05_kernel<T, BN, false, true>, l.grid, dim3(GemmCfg<BN, false>::THREADS),
+               GemmCfg<BN, false>::SMEM_BYTES, s, l.maps, l.p);
+      return;
+    }
   }
   if (!l.pair && l.p.sk && !l.gn) {
     // stream-K: CTAs wait for each other's partial tiles through flags in global memory -> cooperative launch
@@ -370,6 +387,7 @@ template <typename T, int BN> static void launch_one(const GemmLaunch& l, cudaSt
              l.maps, l.p);
     return;
   }
+  if constexpr (BN != 192) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = l.grid;
   cfg.blockDim = dim3(GemmCfg<BN, true>::THREADS);
@@ -391,16 +409,19 @@ template <typename T, int BN> static void launch_one(const GemmLaunch& l, cudaSt
     }
   }
   cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<T, BN, true>, l.maps, l.p);
+  }
 }
 
 void gemm_launch(const GemmLaunch& l, cudaStream_t s) {
   if (l.dt == DT_F16) {
     if (l.bn == 64) launch_one<__half, 64>(l, s);
     else if (l.bn == 128) launch_one<__half, 128>(l, s);
+    else if (l.bn == 192) launch_one<__half, 192>(l, s);
     else launch_one<__half, 160>(l, s);
   } else {
     if (l.bn == 64) launch_one<__nv_bfloat16, 64>(l, s);
     else if (l.bn == 128) launch_one<__nv_bfloat16, 128>(l, s);
+    else if (l.bn == 192) launch_one<__nv_bfloat16, 192>(l, s);
     else launch_one<__nv_bfloat16, 160>(l, s);
   }
 }
@@ -408,12 +429,14 @@ void gemm_launch(const GemmLaunch& l, cudaStream_t s) {
 template <typename T, int BN> static cudaError_t set_attr() {
   cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_kernel<T, BN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        GemmCfg<BN, false>::SMEM_BYTES);
-  if (e == cudaSuccess)
-    e = cudaFuncSetAttribute(gemm_tcgen05_kernel<T, BN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             GemmCfg<BN, true>::SMEM_BYTES);
-  if (e == cudaSuccess)
-    e = cudaFuncSetAttribute(gemm_tcgen05_kernel<T, BN, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             GemmCfg<BN, false>::SMEM_BYTES);
+  if constexpr (BN != 192) {  // (192-wide tiles: single-CTA plain kernel only)
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(gemm_tcgen05_kernel<T, BN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               GemmCfg<BN, true>::SMEM_BYTES);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(gemm_tcgen05_kernel<T, BN, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               GemmCfg<BN, false>::SMEM_BYTES);
+  }
   if constexpr (BN == 160) {
     if (e == cudaSuccess)
       e = cudaFuncSetAttribute(gemm_tcgen05_kernel<T, BN, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -430,6 +453,8 @@ bool gemm_setup_attributes(std::string* err) {
   if (e == cudaSuccess) e = set_attr<__half, 64>();
   if (e == cudaSuccess) e = set_attr<__half, 128>();
   if (e == cudaSuccess) e = set_attr<__half, 160>();
+  if (e == cudaSuccess) e = set_attr<__half, 192>();
+  if (e == cudaSuccess) e = set_attr<__nv_bfloat16, 192>();
   if (e == cudaSuccess) e = set_attr<__nv_bfloat16, 64>();
   if (e == cudaSuccess) e = set_attr<__nv_bfloat16, 128>();
   if (e == cudaSuccess) e = set_attr<__nv_bfloat16, 160>();

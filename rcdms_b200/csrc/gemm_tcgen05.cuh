@@ -205,7 +205,9 @@ struct GemmMaps {
 template <int BN, bool PAIR = false> struct GemmCfg {
   static constexpr int BM = 128, BK = 64;
   // (RCDM_GEMM_EXPERIMENT == 11: one stage less, to measure how far the main loop is bound by stages / load latency)
-  static constexpr int STAGES = (PAIR ? (BN <= 64 ? 8 : BN <= 128 ? 6 : 5) : ((BN <= 64) ? 6 : (BN <= 128 ? 5 : 4))) -
+  // (192-wide tiles - single CTA only - are used where they save a whole wave of tiles, see gemm_plain_bn: 3 stages)
+  static constexpr int STAGES = (PAIR ? (BN <= 64 ? 8 : BN <= 128 ? 6 : 5)
+                                      : ((BN <= 64) ? 6 : (BN <= 128 ? 5 : (BN <= 160 ? 4 : 3)))) -
                                 (RCDM_GEMM_EXPERIMENT == 11 ? 1 : 0);
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = (PAIR ? BN / 2 : BN) * BK * 2;

@@ -83,7 +83,7 @@ struct ASeg {
 };
 // stream-K partial-tile workspace (gemm_host.cu): owned by whoever serialises the launches that use it
 struct SkWorkspace {
-  float* ws = nullptr;        // [slots][128 * 160] fp32
+  float* ws = nullptr;        // [slots][128 * 192] fp32
   unsigned* flags = nullptr;  // [slots], zero at rest
   int slots = 0;
   int device = -1;
@@ -141,7 +141,8 @@ bool gemm_prepare(const GemmDesc& d, GemmLaunch* l, std::string* err);
 void gemm_launch(const GemmLaunch& l, cudaStream_t s);
 void gemm_simple_launch(const GemmDesc& d, cudaStream_t s);  // CUDA-core debug path (same semantics)
 bool gemm_setup_attributes(std::string* err);
-int gemm_stats_parts(int N);                                  // column parts a producer GEMM with N output columns emits
+int gemm_plain_bn(int M, int N);                              // tile width of a plain GEMM (see gemm_host.cu)
+int gemm_stats_parts(int N, int M);                           // column parts a producer GEMM [M, N] emits
 int gemm_set_pair(int on);                                    // CTA-pair kernel on/off; returns the previous value
 int gemm_set_sk_min(int k_blocks);                           // stream-K threshold (0 = off); returns the previous value                // opt-in dynamic smem; call once per process/device
 // Tile width of a GEGLU projection with N accumulator columns (h | gate halves interleaved per tile by the packing

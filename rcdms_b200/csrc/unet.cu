@@ -620,7 +620,7 @@ struct Planner {
     d.seg[0] = ASeg{SEG_PLAIN, p(a_off), K, K, 0, 0, 0};
     if (ln) {
       d.stats_in = reinterpret_cast<const float2*>(p(stats_off));
-      d.stats_parts = gemm_stats_parts(K);
+      d.stats_parts = gemm_stats_parts(K, M);
       d.ln_c = wv(ln->c);
       d.ln_frames = ln->frames > 1 ? h->F : 1;
       d.ln_rows_per_frame = rows_per_frame;
@@ -787,7 +787,7 @@ struct Planner {
     groupnorm(x, nullptr, t.ng, t.nb, 1e-6f, true, false, n.off);
     const bool fold = h->ln_fold && !h->simple;
     // row statistics of y for the folded LayerNorms: [column parts][M] float2, rewritten by every producer of y
-    const size_t st_bytes = (size_t)gemm_stats_parts(C) * M * sizeof(float2);
+    const size_t st_bytes = (size_t)gemm_stats_parts(C, M) * M * sizeof(float2);
     const size_t st = fold ? alloc(st_bytes) : 0;
     Act y = new_act(C, x.H, x.W);
     linear(n.off, M, C, t.pi, &t.pib, y.off, C, nullptr, 0, nullptr, st, fold);
@@ -871,7 +871,7 @@ struct Planner {
     Act n = new_act(C, x.H, x.W);
     groupnorm(x, nullptr, m.ng, m.nb, 1e-6f, true, false, n.off);
     const bool fold = h->ln_fold && !h->simple;
-    const size_t st_bytes = (size_t)gemm_stats_parts(C) * M * sizeof(float2);
+    const size_t st_bytes = (size_t)gemm_stats_parts(C, M) * M * sizeof(float2);
     const size_t st = fold ? alloc(st_bytes) : 0;
     Act y = new_act(C, x.H, x.W);
     linear(n.off, M, C, m.pi, &m.pib, y.off, C, nullptr, 0, nullptr, st, fold);
