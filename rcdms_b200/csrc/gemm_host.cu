@@ -291,13 +291,14 @@ bool gemm_prepare(const GemmDesc& d, GemmLaunch* l, std::string* err) {
     }
   }
   const int m_tiles = has_conv ? ((d.NI + p.tn - 1) / p.tn) * p.tiles_y * p.tiles_x : (d.M + 127) / 128;
-  // CTA pairs (cta_group::2, 256-row tiles): measured on B200 to pay (3-9 %) only for deep-K, many-tile problems
-  // (the big 3x3 convolutions); small-K GEMMs are bound by their epilogue / L2 traffic and lose a little.
+  // CTA pairs (cta_group::2, 256-row tiles: 28 % fewer operand bytes per SM).  Measured on B200 with the two-producer
+  // kernel: K = 320 layers lose 10-15 %, plain K = 640 / 1280 layers are unchanged, GEGLU projections with K >= 640 gain
+  // 6-7 %, 3x3 convolutions gain 8-10 % from K = 2880 on.
   // OPT_GEMM_PAIR = 0 never, 1 heuristic (default), 2 whenever there are >= 2 M tiles.
   const int pair_mode = pair_enabled();
   l->pair = (!d.no_pair && !d.act && bn != 192 && num_sms() >= 2 &&  // activation epilogues / 192-wide tiles: single-CTA kernel only
              ((d.force_pair && m_tiles >= 2) || (pair_mode == 2 && m_tiles >= 2) ||
-              (pair_mode == 1 && kb >= 90 && m_tiles >= 16))) ? 1 : 0;
+              (pair_mode == 1 && m_tiles >= 16 && (kb >= 90 || (has_conv && kb >= 40) || (d.geglu && kb >= 10))))) ? 1 : 0;
   {
     uint64_t dims[2] = {(uint64_t)d.Ktot, (uint64_t)d.w_rows};
     uint64_t str[1] = {(uint64_t)d.Ktot * 2};
@@ -541,3 +542,11 @@ void gemm_simple_launch(const GemmDesc& d, cudaStream_t s) {
 }
 
 }  // namespace rcdm
+
+#if RCDM_GEMM_TRACE
+// variant builds only: copy the GEMM timeline stamps to the host
+extern "C" __attribute__((visibility("default"))) int rcdm_debug_gemm_trace_read(long long* stamps) {
+  cudaDeviceSynchronize();
+  return cudaMemcpyFromSymbol(stamps, rcdm::g_gemm_trace, sizeof(rcdm::g_gemm_trace)) == cudaSuccess ? 0 : 1;
+}
+#endif

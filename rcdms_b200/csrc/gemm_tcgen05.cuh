@@ -61,7 +61,25 @@
 #define RCDM_GEMM_PRODUCERS 2
 #endif
 
+// Timeline instrumentation (variant builds only, -DRCDM_GEMM_TRACE=1; scripts/gemm_trace.py): clock64 stamps of the hand-offs
+// between the warp roles for the first 16 tiles of every CTA, read back through rcdm_debug_gemm_trace_read.
+#ifndef RCDM_GEMM_TRACE
+#define RCDM_GEMM_TRACE 0
+#endif
+
 namespace rcdm {
+
+#if RCDM_GEMM_TRACE
+constexpr int GEMM_TRACE_CTAS = 148, GEMM_TRACE_TILES = 16;
+__device__ long long g_gemm_trace[GEMM_TRACE_CTAS * GEMM_TRACE_TILES * 16];
+#define GEMM_STAMP(it, slot)                                                                                   \
+  do {                                                                                                         \
+    if (blockIdx.x < GEMM_TRACE_CTAS && (it) < GEMM_TRACE_TILES)                                               \
+      g_gemm_trace[((size_t)blockIdx.x * GEMM_TRACE_TILES + (it)) * 16 + (slot)] = clock64();                  \
+  } while (0)
+#else
+#define GEMM_STAMP(it, slot) do { } while (0)
+#endif
 
 enum : int { SEG_PLAIN = 0, SEG_CONV3 = 1, SEG_CONV3S2 = 2, SEG_CONV3S2A = 3, SEG_UP2 = 4 };
 __host__ __device__ constexpr int seg_taps(int mode) { return mode == SEG_PLAIN ? 1 : mode == SEG_UP2 ? 4 : 9; }
@@ -320,7 +338,9 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
       uint32_t phase = 0;
       GemmWork work(p, wid, nworkers);
       int tile, kb0, kb1, mt_, n_tile;
+      int pit = -1;  // work items so far (trace)
       while (work.next(tile, kb0, kb1, mt_, n_tile)) {
+        ++pit;
         const int m_tile = PAIR ? 2 * mt_ + (int)rank : mt_;
         int t = m_tile;  // conv tile origin (only used by conv segments)
         const int tx = t % p.tiles_x;
@@ -372,6 +392,7 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
           }
           if (turn == pid) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
+          if (kb == kb0 || kb == kb0 + 1) GEMM_STAMP(pit, pid);              // first k-block of this producer: slot free
           void* sa = smem_a + stage * Cfg::A_BYTES;
           void* sb = smem_b + stage * Cfg::B_BYTES;
           if constexpr (PAIR) {
@@ -404,6 +425,7 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
             tma_load_2d(sb, &maps.b, &full_bar[stage], kb * 64, n_tile * BN);
 #endif
           }
+          if (kb >= kb1 - 2) GEMM_STAMP(pit, 2 + pid);                       // last k-block of this producer: issued
           }
           if (++turn == Cfg::NPROD) turn = 0;
           if (++stage == STAGES) {
@@ -436,10 +458,13 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
         mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);  // epilogue has drained this accumulator
+        GEMM_STAMP(it, 4);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * Cfg::ACC_STRIDE;
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full_bar[stage], phase);
+          if (kb == kb0) GEMM_STAMP(it, 5);
+          if (kb == kb1 - 1) GEMM_STAMP(it, 6);
           tc_fence_after();
           const uint32_t a_addr = smem_u32(smem_a + stage * Cfg::A_BYTES);
           const uint32_t b_addr = smem_u32(smem_b + stage * Cfg::B_BYTES);
@@ -460,6 +485,7 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
         }
         if constexpr (PAIR) umma_commit_2cta(&tmem_full_bar[acc]);
         else umma_commit(&tmem_full_bar[acc]);
+        GEMM_STAMP(it, 7);
       }
     }
   } else if (warp < 2 + 4 * Cfg::NG) {
@@ -669,7 +695,9 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
             }
           }
         }
+        if (warp == 2 && lane == 0) GEMM_STAMP(it, 8);
         mbar_wait(&tmem_full_bar[acc], acc_phase);
+        if (warp == 2 && lane == 0) GEMM_STAMP(it, 9);
         tc_fence_after();
         if (ln) ln_finish();
         float* bsm = bias_sm + q * BN + cg * QW;  // bias, or c of the tile's frame in LN mode (this warp's slice)
@@ -683,6 +711,7 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
         // of the tile that used the buffer before has been read), or - no residual - that store has been read
         if (res) mbar_wait(&res_full[sb], (ot >> 1) & 1);
         else mbar_wait(&stg_free[sb], ((ot >> 1) & 1) ^ 1);
+        if (warp == 2 && lane == 0) GEMM_STAMP(it, 10);
         // ---- thread <-> row: v = scale * acc + vec (+GEGLU), rounded to 16 bits, (+ residual, rounded again like the
         // reference's `x + attn(...)` on 16-bit tensors), written to this row's slice of the staging buffer
         const float scale = ln_a;
@@ -876,6 +905,7 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
           }
         }
         release_acc(acc);  // accumulator drained: the MMA warp may reuse it
+        if (warp == 2 && lane == 0) GEMM_STAMP(it, 11);
         if (p.stats_out && m_warp + lane < p.M)
           p.stats_out[(size_t)(n_tile * NG + cg) * p.M + m_warp + lane] = make_float2(st_s, st_ss);
         if constexpr (GN) {
@@ -993,6 +1023,7 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
         const int m_tile = PAIR ? 2 * (tile / p.num_n_tiles) + (int)rank : tile / p.num_n_tiles;
         const int sb = o & 1;
         mbar_wait(&stg_full[sb], (o >> 1) & 1);
+        GEMM_STAMP(o, 12);
 #if RCDM_GEMM_EXPERIMENT != 6
         if (p.out4d) {  // conv tile origin on the output grid (same decomposition as the producer's)
           int t = m_tile;
@@ -1010,7 +1041,9 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
                            m_tile * 128);
         }
         bulk_commit();
+        GEMM_STAMP(o, 13);
         bulk_wait_read0();  // the buffer may be refilled
+        GEMM_STAMP(o, 14);
 #endif
         if (have_peek) have_peek = next_output(peek, pt);  // item o + 2
         if (has_res) {
@@ -1018,6 +1051,7 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
         } else {
           mbar_arrive(&stg_free[sb]);
         }
+        GEMM_STAMP(o, 15);
       }
       bulk_wait0();  // every TMA store of this CTA has completed before its shared memory goes away
     }
