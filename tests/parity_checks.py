@@ -306,8 +306,11 @@ def all_op_checks(dtypes=(torch.float16, torch.bfloat16), quick=False):
         for (M, N, K) in [(256, 160, 64), (640, 320, 320), (1000, 128, 96), (130, 64, 128), (4096, 960, 320),
                           (2560, 1280, 1280), (10, 256, 256), (850, 640, 768)]:
             yield lambda M=M, N=N, K=K, dt=dt: check_linear(M, N, K, dt, bias=True, residual=(N % 2 == 0 and M > 200))
-        for bn in (64, 128, 160):
+        for bn in (64, 128, 160, 192):
             yield lambda bn=bn, dt=dt: check_linear(512, 320, 256, dt, tile_n=bn)
+        # 192-wide tiles (chosen by gemm_plain_bn where they save a wave; here forced): ragged last tile, residual
+        yield lambda dt=dt: check_linear(1000, 200, 64, dt, residual=True, tile_n=192)
+        yield lambda dt=dt: check_linear(2560, 3840, 1280, dt, bias=False)
         yield lambda dt=dt: check_linear(384, 192, 320, dt, bias=False)
         yield lambda dt=dt: check_linear(40960, 320, 1280, dt, residual=True)
         # shapes whose tile count does not fill the SMs evenly -> stream-K decomposition (gemm_host.cu)
