@@ -167,6 +167,13 @@ RCDM_API int rcdm_gemm(int dtype, const void* a_dev, const void* w_dev, const fl
 RCDM_API int rcdm_gemm_ex(int dtype, const void* a_dev, int lda, const void* w_dev, const float* bias_dev,
                           const void* residual_dev, int ldr, void* out_dev, int ldo, int M, int N, int K, int flags,
                           void* stream);
+/* fused GEGLU feed-forward of the 320-channel transformer blocks (attention.py:434-436,523-526; motion_module.py:231-232,
+ * 244-246): out = y + GEGLU(LayerNorm(y) W1^T + b1) W2^T + b2 in one kernel, the [M, 1280] intermediate stays on the SM.
+ * w1 [2560, 320] / bias1 [2560] in the reference layout, w2 [320, 1280]; scratch: rcdm_ffn_geglu_scratch_bytes(M). */
+RCDM_API size_t rcdm_ffn_geglu_scratch_bytes(int M);
+RCDM_API int rcdm_ffn_geglu_ln(int dtype, const void* y_dev, const void* w1_dev, const float* gamma_dev, const float* beta_dev,
+                               const float* bias1_dev, const void* w2_dev, const float* bias2_dev, void* out_dev, int M,
+                               float eps, void* scratch_dev, void* stream);
 /* same GEMM, plus per-row (sum, sum of squares) partials of the rounded output: stats_dev = float2[parts][M]
  * (producer side of the folded LayerNorm; replaces the statistics pass of attention.py:412,429,435) */
 RCDM_API int rcdm_gemm_rowstats(int dtype, const void* a_dev, const void* w_dev, const float* bias_dev,

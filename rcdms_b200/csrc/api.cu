@@ -38,7 +38,7 @@ static int ensure_device_ready() {
       err = "no CUDA device: librcdm_b200 has no CPU fallback";
       return;
     }
-    ok = gemm_setup_attributes(&err) && attn_setup_attributes(&err) && gn_setup_attributes(&err);
+    ok = gemm_setup_attributes(&err) && attn_setup_attributes(&err) && gn_setup_attributes(&err) && ffn_setup_attributes(&err);
   });
   return ok ? 0 : set_err(err);
 }
@@ -789,6 +789,68 @@ int rcdm_linear_ln(int dtype, const void* x_dev, const void* w_dev, const float*
   gemm_launch(l, st);
   g_launches += 3;
   return check_launch("rcdm_linear_ln");
+  API_END
+}
+
+// Fused GEGLU feed-forward of the C = 320 transformer blocks (ffn_fused.cuh): out = y + GEGLU(LayerNorm(y) W1^T + b1) W2^T + b2.
+// w1 [2560, 320] / bias1 [2560] in the reference layout (h rows, then gate rows), w2 [320, 1280].  The weight folding /
+// packing and the row statistics of y (done once at load time / by the producing GEMM inside the UNet plan) run here per call.
+size_t rcdm_ffn_geglu_scratch_bytes(int M) {
+  const size_t wbytes = (size_t)2 * FfnCfg::J * FfnCfg::C * 2;
+  return 2 * wbytes + 2 * ((size_t)2 * FfnCfg::J * 4 + 256) + (size_t)(M > 0 ? M : 0) * 8 + 1024;
+}
+int rcdm_ffn_geglu_ln(int dtype, const void* y_dev, const void* w1_dev, const float* gamma_dev, const float* beta_dev,
+                      const float* bias1_dev, const void* w2_dev, const float* bias2_dev, void* out_dev, int M, float eps,
+                      void* scratch_dev, void* stream) {
+  API_BEGIN
+  if (!dt16(dtype)) return set_err("rcdm_ffn_geglu_ln: dtype must be f16/bf16");
+  if (!y_dev || !w1_dev || !gamma_dev || !beta_dev || !bias1_dev || !w2_dev || !out_dev || !scratch_dev || M <= 0)
+    return set_err("rcdm_ffn_geglu_ln: bad argument");
+  if (ensure_device_ready()) return 1;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  constexpr int N = 2 * FfnCfg::J, K = FfnCfg::C, BN = FFN_FUSED_GEGLU_BN;
+  unsigned char* sc = reinterpret_cast<unsigned char*>(scratch_dev);
+  const size_t wbytes = (size_t)N * K * 2;
+  void* wp = sc;
+  void* wf = sc + wbytes;
+  float* bp = reinterpret_cast<float*>(sc + 2 * wbytes);
+  float* c = reinterpret_cast<float*>(sc + 2 * wbytes + ((size_t)N * 4 + 256));
+  float2* stats = reinterpret_cast<float2*>(sc + 2 * wbytes + 2 * ((size_t)N * 4 + 256));
+  const int fb = (N * 32 + 255) / 256, rb = (M * 32 + 255) / 256;
+  pack_vec_kernel<<<(N + 255) / 256, 256, 0, st>>>(bias1_dev, DT_F32, bp, N, 0, BN, 0);
+  if (dtype == DT_F16) {
+    pack_weight_kernel<__half><<<grid_for((size_t)N * K, 256), 256, 0, st>>>(w1_dev, dtype, reinterpret_cast<__half*>(wp), N, K, K,
+                                                                             0, 0, 0, 0, BN);
+    fold_ln_kernel<__half><<<fb, 256, 0, st>>>(reinterpret_cast<const __half*>(wp), reinterpret_cast<__half*>(wf), gamma_dev,
+                                               beta_dev, nullptr, bp, c, N, K, 1);
+    rowstats_kernel<__half><<<rb, 256, 0, st>>>(reinterpret_cast<const __half*>(y_dev), stats, M, K);
+  } else {
+    pack_weight_kernel<__nv_bfloat16><<<grid_for((size_t)N * K, 256), 256, 0, st>>>(
+        w1_dev, dtype, reinterpret_cast<__nv_bfloat16*>(wp), N, K, K, 0, 0, 0, 0, BN);
+    fold_ln_kernel<__nv_bfloat16><<<fb, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(wp),
+                                                      reinterpret_cast<__nv_bfloat16*>(wf), gamma_dev, beta_dev, nullptr, bp, c,
+                                                      N, K, 1);
+    rowstats_kernel<__nv_bfloat16><<<rb, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(y_dev), stats, M, K);
+  }
+  FfnDesc d;
+  memset(&d, 0, sizeof d);
+  d.dt = dtype;
+  d.M = M;
+  d.y = y_dev;
+  d.stats_in = stats;
+  d.stats_parts = 1;
+  d.ln_eps = eps;
+  d.w1f = wf;
+  d.c1 = c;
+  d.w2 = w2_dev;
+  d.bias2 = bias2_dev;
+  d.out = out_dev;
+  FfnLaunch l;
+  std::string e;
+  if (!ffn_prepare(d, &l, &e)) return set_err(e);
+  ffn_launch(l, st);
+  g_launches += 5;
+  return check_launch("rcdm_ffn_geglu_ln");
   API_END
 }
 

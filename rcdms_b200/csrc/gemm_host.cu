@@ -37,6 +37,11 @@ static PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn(std::string* err) {
 
 bool encode_tmap(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                  const uint32_t* box, bool swizzle128, std::string* err) {
+  return encode_tmap_sw(out, base, rank, dims, strides_bytes, box, swizzle128 ? 128 : 0, err);
+}
+// swizzle_bytes: 0 (none) | 32 | 64 | 128
+bool encode_tmap_sw(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                    const uint32_t* box, int swizzle_bytes, std::string* err) {
   auto fn = get_encode_fn(err);
   if (!fn) return false;
   cuuint64_t gdim[5], gstr[4];
@@ -52,7 +57,10 @@ bool encode_tmap(CUtensorMap* out, const void* base, int rank, const uint64_t* d
     return false;
   }
   CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_UINT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bdim, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                  : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                  : swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     if (err) {
@@ -72,10 +80,10 @@ bool encode_tmap(CUtensorMap* out, const void* base, int rank, const uint64_t* d
 // ------------------------------------------------------------------------------------------
 // GEMM prepare / launch
 // ------------------------------------------------------------------------------------------
-static std::atomic<int> g_opts[OPT_COUNT] = {{0}, {24}, {1}, {1}, {1}, {1}, {1}, {40}, {1}, {1}, {1}};
+static std::atomic<int> g_opts[OPT_COUNT] = {{0}, {24}, {1}, {1}, {1}, {1}, {1}, {40}, {1}, {1}, {1}, {0}};
 static const char* const g_opt_names[OPT_COUNT] = {"pdl", "sk_min", "gemm_pair", "masked_attn_mma",
                                                     "temporal_wide", "temporal_wide_all", "temporal_tiled",
-                                                    "temporal_smem_kb", "gn_fused", "ln_wide", "gn_stats"};
+                                                    "temporal_smem_kb", "gn_fused", "ln_wide", "gn_stats", "ffn_fused"};
 int opt(int id) { return g_opts[id].load(std::memory_order_relaxed); }
 int opt_set(const char* name, int value, int* previous) {
   for (int i = 0; i < OPT_COUNT; ++i)
@@ -541,6 +549,71 @@ void gemm_simple_launch(const GemmDesc& d, cudaStream_t s) {
   else gemm_simple_kernel<__nv_bfloat16><<<blocks, 256, 0, s>>>(sa);
 }
 
+// ------------------------------------------------------------------------------------------
+// fused GEGLU feed-forward (ffn_fused.cuh)
+// ------------------------------------------------------------------------------------------
+bool ffn_prepare(const FfnDesc& d, FfnLaunch* l, std::string* err) {
+  auto fail = [&](const std::string& m) {
+    if (err) *err = "ffn_prepare: " + m;
+    return false;
+  };
+  if (d.dt != DT_F16 && d.dt != DT_BF16) return fail("dtype must be f16/bf16");
+  if (!d.y || !d.stats_in || !d.w1f || !d.c1 || !d.w2 || !d.out || d.M <= 0 || d.stats_parts <= 0) return fail("bad argument");
+  constexpr int C = FfnCfg::C, J = FfnCfg::J;
+  memset(&l->maps, 0, sizeof l->maps);
+  memset(&l->p, 0, sizeof l->p);
+  {
+    uint64_t dims[2] = {(uint64_t)C, (uint64_t)d.M};
+    uint64_t str[1] = {(uint64_t)C * 2};
+    uint32_t box[2] = {64, 128};
+    if (!encode_tmap_sw(&l->maps.a1, d.y, 2, dims, str, box, 128, err)) return false;
+  }
+  {  // W1f [2J, C] seen as (64 columns, 2J rows, C / 64 k-blocks): one box = a chunk's 64 rows x all k-blocks
+    uint64_t dims[3] = {64, (uint64_t)2 * J, (uint64_t)C / 64};
+    uint64_t str[2] = {(uint64_t)C * 2, 128};
+    uint32_t box[3] = {64, 64, (uint32_t)C / 64};
+    if (!encode_tmap_sw(&l->maps.b1, d.w1f, 3, dims, str, box, 128, err)) return false;
+  }
+  {
+    uint64_t dims[2] = {(uint64_t)J, (uint64_t)C};
+    uint64_t str[1] = {(uint64_t)J * 2};
+    uint32_t box[2] = {(uint32_t)FfnCfg::CH, 160};
+    if (!encode_tmap_sw(&l->maps.b2, d.w2, 2, dims, str, box, 64, err)) return false;
+  }
+  FfnParams& p = l->p;
+  p.M = d.M;
+  p.num_m_tiles = (d.M + 127) / 128;
+  p.stats_in = d.stats_in;
+  p.stats_parts = d.stats_parts;
+  p.ln_eps = d.ln_eps;
+  p.c1 = d.c1;
+  p.bias2 = d.bias2;
+  p.res = d.y;
+  p.out = d.out;
+  l->dt = d.dt;
+  const int sms = num_sms();
+  l->grid = dim3(p.num_m_tiles < sms ? p.num_m_tiles : sms);
+  return true;
+}
+void ffn_launch(const FfnLaunch& l, cudaStream_t s) {
+  if (l.dt == DT_F16)
+    launch_k(ffn_geglu_fused_kernel<__half>, l.grid, dim3(FfnCfg::THREADS), FfnCfg::SMEM_BYTES, s, l.maps, l.p);
+  else
+    launch_k(ffn_geglu_fused_kernel<__nv_bfloat16>, l.grid, dim3(FfnCfg::THREADS), FfnCfg::SMEM_BYTES, s, l.maps, l.p);
+}
+bool ffn_setup_attributes(std::string* err) {
+  cudaError_t e = cudaFuncSetAttribute(ffn_geglu_fused_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       FfnCfg::SMEM_BYTES);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(ffn_geglu_fused_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             FfnCfg::SMEM_BYTES);
+  if (e != cudaSuccess) {
+    if (err) *err = std::string("cudaFuncSetAttribute(ffn): ") + cudaGetErrorString(e);
+    return false;
+  }
+  return true;
+}
+
 }  // namespace rcdm
 
 #if RCDM_GEMM_TRACE
@@ -548,5 +621,12 @@ void gemm_simple_launch(const GemmDesc& d, cudaStream_t s) {
 extern "C" __attribute__((visibility("default"))) int rcdm_debug_gemm_trace_read(long long* stamps) {
   cudaDeviceSynchronize();
   return cudaMemcpyFromSymbol(stamps, rcdm::g_gemm_trace, sizeof(rcdm::g_gemm_trace)) == cudaSuccess ? 0 : 1;
+}
+#endif
+
+#if RCDM_FFN_TRACE
+extern "C" __attribute__((visibility("default"))) int rcdm_debug_ffn_trace_read(long long* stamps) {
+  cudaDeviceSynchronize();
+  return cudaMemcpyFromSymbol(stamps, rcdm::g_ffn_trace, sizeof(rcdm::g_ffn_trace)) == cudaSuccess ? 0 : 1;
 }
 #endif

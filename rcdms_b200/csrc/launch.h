@@ -9,6 +9,7 @@
 
 #include "attention.cuh"
 #include "gemm_tcgen05.cuh"
+#include "ffn_fused.cuh"
 
 namespace rcdm {
 
@@ -28,6 +29,8 @@ enum Opt : int {
   OPT_GN_FUSED,           // single-launch GroupNorm with a grid barrier (default 1; 0 = two-kernel path)
   OPT_LN_WIDE,            // CTA-per-row LayerNorm for rows wider than 1280 (default 1)
   OPT_GN_STATS,           // GroupNorm statistics from the producing GEMM's epilogue + streaming apply (default 1)
+  OPT_FFN_FUSED,          // fused GEGLU feed-forward kernel for the C = 320 transformer blocks (default 0: measured slower
+                          // than the two GEMMs; set BEFORE rcdm_unet_create - it decides the weight packing)
   OPT_COUNT
 };
 int opt(int id);
@@ -72,6 +75,8 @@ inline cudaError_t launch_coop(void (*kern)(KArgs...), dim3 grid, dim3 block, si
 // dims/box innermost-first; strides_bytes has rank-1 entries (dimension 0 is contiguous). 16-bit elements.
 bool encode_tmap(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                  const uint32_t* box, bool swizzle128, std::string* err);
+bool encode_tmap_sw(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                    const uint32_t* box, int swizzle_bytes /*0 | 32 | 64 | 128*/, std::string* err);
 
 // ---- GEMM / implicit-GEMM conv -------------------------------------------------------------------------
 struct ASeg {
@@ -149,6 +154,32 @@ int gemm_set_sk_min(int k_blocks);                           // stream-K thresho
 // kernels): 160 where it divides N (the UNet's 8 C = 2560 / 5120 / 10240: measured 7-11 % faster than 128 - fewer, wider
 // MMAs per shared-memory byte and 20 % fewer re-reads of A), else 128 (the stage-1 prior's 16384).
 inline int geglu_bn(int N) { return N % 160 == 0 ? 160 : 128; }
+
+// ---- fused GEGLU feed-forward (ffn_fused.cuh; C = 320 only) -----------------------------------------------------
+constexpr int FFN_FUSED_C = 320;       // channel width the fused kernel is built for
+constexpr int FFN_FUSED_GEGLU_BN = 64; // GEGLU packing width of its W1f / c1 (32 h rows | 32 gate rows per chunk)
+struct FfnDesc {
+  int dt;                   // DT_F16 | DT_BF16
+  int M;                    // rows
+  const void* y;            // [M, 320] input = residual
+  const float2* stats_in;   // [stats_parts][M] row statistics of y
+  int stats_parts;
+  float ln_eps;
+  const void* w1f;          // [2560, 320] folded (centred, gamma-scaled) weights, GEGLU-packed with width 64
+  const float* c1;          // [2560] folded constant vector, same packing
+  const void* w2;           // [320, 1280]
+  const float* bias2;       // [320]
+  void* out;                // [M, 320] (may alias y)
+};
+struct FfnLaunch {
+  FfnMaps maps;
+  FfnParams p;
+  dim3 grid;
+  int dt;
+};
+bool ffn_prepare(const FfnDesc& d, FfnLaunch* l, std::string* err);
+void ffn_launch(const FfnLaunch& l, cudaStream_t s);
+bool ffn_setup_attributes(std::string* err);
 
 // ---- attention ---------------------------------------------------------------------------------------
 struct AttnDesc {

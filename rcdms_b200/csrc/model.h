@@ -134,6 +134,7 @@ struct rcdm_unet_impl {
   std::map<std::string, std::pair<int, int>> tune_cache;  // problem signature -> (tile width, pair)
   int gn_stats = 1;  // GroupNorm statistics from the producing GEMMs' epilogues (0: gn_fused_kernel everywhere)
   size_t gn_acc_bytes = 0;  // size of the accumulator region (from the dry planning pass)
+  int ffn_pack64 = 0;  // C = 320 feed-forward weights GEGLU-packed with width 64 for the fused kernel (library option "ffn_fused" at creation)
   int ln_fold = 1;  // LayerNorm folded into the consuming GEMM (rcdm_unet_set_option("ln_fold", 0): separate layernorm kernels)
   // per-call inputs (read by the recorded ops)
   const void* cur_sample = nullptr;

@@ -135,10 +135,13 @@ struct Builder {
     a.outb = vslot(p + ".to_out.0.bias", C);
   }
   void ff(const std::string& p, int C, Mat& ff1, Vec& ff1b, Mat& ff2, Vec& ff2b) {
+    // GEGLU row interleave: the tile width of the GEGLU GEMM - or, for the 320-channel blocks, the chunk width of the
+    // fused feed-forward kernel (ffn_fused.cuh)
+    const int gbn = (C == FFN_FUSED_C && h->ffn_pack64) ? FFN_FUSED_GEGLU_BN : geglu_bn(8 * C);
     ff1 = mat(8 * C, C);
-    slot(p + ".net.0.proj.weight", {8 * C, C}, SLOT_MAT, ff1.off, C, 0, 0, geglu_bn(8 * C));
+    slot(p + ".net.0.proj.weight", {8 * C, C}, SLOT_MAT, ff1.off, C, 0, 0, gbn);
     ff1b = vec(8 * C);
-    slot(p + ".net.0.proj.bias", {8 * C}, SLOT_VEC, ff1b.off, 0, 0, 0, geglu_bn(8 * C));
+    slot(p + ".net.0.proj.bias", {8 * C}, SLOT_VEC, ff1b.off, 0, 0, 0, gbn);
     ff2 = lin(p + ".net.2.weight", C, 4 * C);
     ff2b = vslot(p + ".net.2.bias", C);
   }
@@ -637,8 +640,35 @@ struct Planner {
     d.res = res_off ? p(*res_off) : nullptr;
     d.ldr = ldo;
     d.geglu = geglu;
+    if (geglu && K == FFN_FUSED_C && h->ffn_pack64) d.force_bn = FFN_FUSED_GEGLU_BN;  // (packed for the fused kernel)
     if (K != w.cols) return fail("linear: K mismatch");
     gemm(d);
+  }
+  // fused GEGLU feed-forward of a 320-channel block (ffn_fused.cuh): y <- y + GEGLU(LN(y) W1^T + b1) W2^T + b2
+  bool ffn_fused_ok(int C, bool fold) const { return fold && C == FFN_FUSED_C && h->ffn_pack64 && opt(OPT_FFN_FUSED); }
+  void ffn_fused(size_t y_off, int M, const LnFold& ln, size_t stats_off, const Mat& w2, const Vec& b2) {
+    if (dry || failed) return;
+    FfnDesc d;
+    memset(&d, 0, sizeof d);
+    d.dt = h->dt;
+    d.M = M;
+    d.y = p(y_off);
+    d.stats_in = reinterpret_cast<const float2*>(p(stats_off));
+    d.stats_parts = gemm_stats_parts(FFN_FUSED_C, M);
+    d.ln_eps = 1e-5f;
+    d.w1f = wm(ln.wf);
+    d.c1 = wv(ln.c);
+    d.w2 = wm(w2);
+    d.bias2 = wv(b2);
+    d.out = p(y_off);
+    FfnLaunch l;
+    std::string e;
+    if (!ffn_prepare(d, &l, &e)) return fail(e);
+    const double C = FFN_FUSED_C, J = 4.0 * FFN_FUSED_C;
+    push([l](cudaStream_t s) {
+      ffn_launch(l, s);
+      g_launches++;
+    }, "ffn_fused", 2.0 * M * (2.0 * J * C + C * J), 2.0 * (2.0 * M * C + 2.0 * J * C + C * J), M, (int)C, (int)J);
   }
   void groupnorm(const Act& x0, const Act* x1, const Vec& g, const Vec& b, float eps, bool per_frame, bool silu,
                  size_t out_off) {
@@ -848,15 +878,19 @@ struct Planner {
     free_act(q);
     linear(tmp.off, M, C, t.a2.out, &t.a2.outb, y.off, C, &y.off, 0, nullptr, st, fold);
     // GEGLU feed-forward
-    Act g = new_act(4 * C, x.H, x.W);
-    if (fold) {
-      linear(y.off, M, C, t.ff1, &t.ff1b, g.off, 4 * C, nullptr, 1, &t.ff1_ln, st);
+    if (ffn_fused_ok(C, fold)) {
+      ffn_fused(y.off, M, t.ff1_ln, st, t.ff2, t.ff2b);
     } else {
-      layernorm(y.off, tmp.off, M, C, t.ln3g, t.ln3b, nullptr, 1);
-      linear(tmp.off, M, C, t.ff1, &t.ff1b, g.off, 4 * C, nullptr, 1);
+      Act g = new_act(4 * C, x.H, x.W);
+      if (fold) {
+        linear(y.off, M, C, t.ff1, &t.ff1b, g.off, 4 * C, nullptr, 1, &t.ff1_ln, st);
+      } else {
+        layernorm(y.off, tmp.off, M, C, t.ln3g, t.ln3b, nullptr, 1);
+        linear(tmp.off, M, C, t.ff1, &t.ff1b, g.off, 4 * C, nullptr, 1);
+      }
+      linear(g.off, M, 4 * C, t.ff2, &t.ff2b, y.off, C, &y.off);
+      free_act(g);
     }
-    linear(g.off, M, 4 * C, t.ff2, &t.ff2b, y.off, C, &y.off);
-    free_act(g);
     free_act(tmp);
     x.gn = new_gn(C, x.H, x.W);  // x is rewritten in place: its statistics are new
     linear(y.off, M, C, t.po, &t.pob, x.off, C, &x.off, 0, nullptr, 0, false, 1, x.gn, HW);
@@ -897,15 +931,19 @@ struct Planner {
       free_act(qkv);
       linear(tmp.off, M, C, m.att[i].out, &m.att[i].outb, y.off, C, &y.off, 0, nullptr, st, fold);
     }
-    Act g = new_act(4 * C, x.H, x.W);
-    if (fold) {
-      linear(y.off, M, C, m.ff1, &m.ff1b, g.off, 4 * C, nullptr, 1, &m.ff1_ln, st);
+    if (ffn_fused_ok(C, fold)) {
+      ffn_fused(y.off, M, m.ff1_ln, st, m.ff2, m.ff2b);
     } else {
-      layernorm(y.off, tmp.off, M, C, m.ffng, m.ffnb, nullptr, 1);
-      linear(tmp.off, M, C, m.ff1, &m.ff1b, g.off, 4 * C, nullptr, 1);
+      Act g = new_act(4 * C, x.H, x.W);
+      if (fold) {
+        linear(y.off, M, C, m.ff1, &m.ff1b, g.off, 4 * C, nullptr, 1, &m.ff1_ln, st);
+      } else {
+        layernorm(y.off, tmp.off, M, C, m.ffng, m.ffnb, nullptr, 1);
+        linear(tmp.off, M, C, m.ff1, &m.ff1b, g.off, 4 * C, nullptr, 1);
+      }
+      linear(g.off, M, 4 * C, m.ff2, &m.ff2b, y.off, C, &y.off);
+      free_act(g);
     }
-    linear(g.off, M, 4 * C, m.ff2, &m.ff2b, y.off, C, &y.off);
-    free_act(g);
     free_act(tmp);
     x.gn = new_gn(C, x.H, x.W);
     linear(y.off, M, C, m.po, &m.pob, x.off, C, &x.off, 0, nullptr, 0, false, 1, x.gn, HW);
@@ -1239,6 +1277,7 @@ int unet_create(const rcdm_unet_config* cfg, rcdm_unet** out) {
   // debug switches (rcdm_unet_set_option before rcdm_unet_prepare): simple = 0, autotune = 0 (measured: no gain over the
   // heuristics at the 512x512 shapes), ln_fold = 1, gn_stats = library option at creation time
   h->gn_stats = opt(OPT_GN_STATS);
+  h->ffn_pack64 = opt(OPT_FFN_FUSED) ? 1 : 0;
   if (build_model(h)) {
     delete h;
     return 1;
@@ -1287,7 +1326,7 @@ static int ensure_arena(rcdm_unet_impl* h) {
   CUDA_OK(cudaMalloc(&h->arena, h->arena_bytes));
   CUDA_OK(cudaMemset(h->arena, 0, h->arena_bytes));
   std::string e;
-  if (!gemm_setup_attributes(&e) || !attn_setup_attributes(&e) || !gn_setup_attributes(&e)) return set_err(e);
+  if (!gemm_setup_attributes(&e) || !attn_setup_attributes(&e) || !gn_setup_attributes(&e) || !ffn_setup_attributes(&e)) return set_err(e);
   if (!sk_workspace_alloc(&h->sk, &e)) return set_err(e);
   return 0;
 }

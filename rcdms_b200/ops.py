@@ -97,6 +97,22 @@ def linear_ln(x: torch.Tensor, w: torch.Tensor, gamma: torch.Tensor, beta: torch
     return out
 
 
+def ffn_geglu_ln(y: torch.Tensor, w1: torch.Tensor, bias1: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor,
+                 w2: torch.Tensor, bias2: torch.Tensor, eps: float = 1e-5) -> torch.Tensor:
+    """y + GEGLU(LayerNorm(y) @ w1^T + bias1) @ w2^T + bias2 in ONE kernel (320-channel transformer blocks only).
+    y [M, 320]; w1 [2560, 320] / bias1 [2560] in the reference layout (h rows, then gate rows); w2 [320, 1280]."""
+    M, C = y.shape
+    if C != 320 or tuple(w1.shape) != (2560, 320) or tuple(w2.shape) != (320, 1280):
+        raise ValueError("ffn_geglu_ln is built for C = 320")
+    L = _lib.lib()
+    scratch = torch.empty((L.rcdm_ffn_geglu_scratch_bytes(M),), dtype=torch.uint8, device=y.device)
+    out = torch.empty_like(y)
+    _lib.check(L.rcdm_ffn_geglu_ln(_dt16(y), y.data_ptr(), w1.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
+                                   bias1.float().contiguous().data_ptr(), w2.data_ptr(), bias2.float().contiguous().data_ptr(),
+                                   out.data_ptr(), M, eps, scratch.data_ptr(), _lib.current_stream_ptr()))
+    return out
+
+
 def conv3x3(x_nhwc: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = None,
             residual: Optional[torch.Tensor] = None, stride: int = 1, simple: bool = False) -> torch.Tensor:
     """3x3 / pad 1 conv on channels-last x [n,h,w,cin]; weight in the reference layout [cout,cin,3,3]."""

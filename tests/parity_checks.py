@@ -194,6 +194,32 @@ def check_linear_ln(M, N, K, dtype, pe=False, geglu=False, seed=8):
                    rtol_mul=6.0 if geglu else 3.0)
 
 
+def check_ffn_fused(M, dtype, seed=12):
+    """Fused GEGLU feed-forward (one kernel) vs fp32 LayerNorm -> Linear -> GEGLU -> Linear -> + residual on the same rounded
+    inputs, and vs the composition of the two separate kernels (folded-LayerNorm GEGLU GEMM, then GEMM + residual)."""
+    g = _gen(seed)
+    C, J = 320, 1280
+    y = _rand((M, C), dtype, g) * 1.5 + 0.3
+    w1 = _rand((2 * J, C), dtype, g, 1.0 / math.sqrt(C))
+    b1 = torch.randn((2 * J,), generator=g, device="cuda") * 0.5
+    gamma = 1 + 0.2 * torch.randn((C,), generator=g, device="cuda")
+    beta = 0.2 * torch.randn((C,), generator=g, device="cuda")
+    w2 = _rand((C, J), dtype, g, 1.0 / math.sqrt(J))
+    b2 = torch.randn((C,), generator=g, device="cuda") * 0.5
+    out = ops.ffn_geglu_ln(y, w1, b1, gamma, beta, w2, b2)
+    ln = F.layer_norm(y.float(), (C,), gamma, beta, 1e-5)
+    hg = ln @ w1.float().t() + b1
+    hmid = (hg[:, :J] * F.gelu(hg[:, J:])).to(dtype).float()  # the kernels round the intermediate to 16 bits
+    ref = hmid @ w2.float().t() + b2 + y.float()
+    res = _result(f"ffn_fused M{M}", out, ref, dtype, rtol_mul=3.0)
+    mid = ops.linear_ln(y, w1, gamma, beta, b1, None, 1, True)
+    two = ops.linear(mid, w2, b2, y)
+    d = (out.float() - two.float()).abs().max().item()
+    res["max_abs_vs_two_kernels"] = d
+    res["ok"] = res["ok"] and d <= 2e-2 * max(1.0, two.float().abs().max().item())
+    return res
+
+
 def check_rowstats(M, N, K, dtype, residual=True, seed=9):
     g = _gen(seed)
     a = _rand((M, K), dtype, g)
@@ -332,6 +358,8 @@ def all_op_checks(dtypes=(torch.float16, torch.bfloat16), quick=False):
         for (M, C) in [(256, 64), (1024, 320), (100, 128)]:
             yield lambda M=M, C=C, dt=dt: check_geglu(M, C, dt)
         yield lambda dt=dt: check_geglu(128, 64, dt, simple=True)
+        for M in (128, 1000, 20480):
+            yield lambda M=M, dt=dt: check_ffn_fused(M, dt)
         for (n, h, w, cin, cout, s) in [(10, 8, 8, 64, 64, 1), (2, 64, 64, 128, 160, 1), (10, 4, 4, 128, 64, 1),
                                         (10, 2, 2, 64, 128, 1), (10, 1, 1, 256, 256, 1), (3, 16, 16, 320, 640, 1),
                                         (10, 32, 32, 64, 4, 1), (10, 8, 8, 64, 128, 2), (2, 64, 64, 64, 64, 2),

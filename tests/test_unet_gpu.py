@@ -84,6 +84,26 @@ def test_full_unet_matches_oracle_at_benchmarked_shapes(shape, t, dtype):
     torch.cuda.empty_cache()
 
 
+def test_fused_feed_forward_path_matches_oracle():
+    """The opt-in fused GEGLU feed-forward kernel (library option "ffn_fused", read at module creation: it decides the
+    weight packing of the 320-channel blocks) must pass the same whole-UNet bound as the default two-GEMM path."""
+    from rcdms_b200 import _lib
+    L = _lib.lib()
+    prev = L.rcdm_debug_set_option(b"ffn_fused", 1)
+    try:
+        res = uc.run_case(full_config(), (2, 5, 16, 16, 85), 501, torch.float16, sd=_full_sd())
+        _assert_close(res)
+        y_fused = res["y"].clone()
+        res.clear()
+    finally:
+        L.rcdm_debug_set_option(b"ffn_fused", prev)
+    res = uc.run_case(full_config(), (2, 5, 16, 16, 85), 501, torch.float16, sd=_full_sd())
+    d = (y_fused.float() - res["y"].float()).abs().max().item()
+    assert d <= 3 * max(res["floor"]["max_abs"], 1e-3), d
+    res.clear()
+    torch.cuda.empty_cache()
+
+
 def test_forward_contract():
     """Boundary behaviour of unet.py:322-463: new tensor, inputs untouched, tuple when return_dict=False,
     python-number and 0-dim cuda int64 timesteps agree, state_dict round trip."""
