@@ -27,6 +27,12 @@ def run(name, fn):
     print(("ok     " if ok else "FAILED ") + name, flush=True)
 
 
+ONLY = sys.argv[1] if len(sys.argv) > 1 else ""
+if ONLY == "ffn":  # (re-run of a single family: python scripts/sanitize_ops.py ffn)
+    run("ffn fused 256 rows f16", lambda: pc.check_ffn_fused(256, f16))
+    run("ffn fused 200 rows bf16", lambda: pc.check_ffn_fused(200, torch.bfloat16))
+    print("ALL OK" if all(ok for _, ok in res) else "SOME FAILED", len(res), "checks")
+    sys.exit(0)
 for pair, sk in ((0, 0), (2, 1)):
     L.rcdm_set_gemm_pair(pair)
     L.rcdm_set_stream_k_min(sk)
@@ -54,6 +60,7 @@ run("flash d160", lambda: pc.check_flash(2, 8, 64, 64, 160, f16))
 run("temporal d40", lambda: pc.check_temporal(2, 5, 64, 8, 40, f16))
 run("ddim cfg step", lambda: pc.check_ddim(1, 5, 8, 8, f16))
 run("context fusion", lambda: pc.check_context_fusion(2, 7, 96, 9, 16, 96, 8, f16))
+run("ffn fused 256 rows", lambda: pc.check_ffn_fused(256, f16))
 
 # VAE pieces + tiny decode / encode
 from rcdms_b200.models import AutoencoderKL  # noqa: E402
