@@ -845,6 +845,7 @@ int rcdm_ffn_geglu_ln(int dtype, const void* y_dev, const void* w1_dev, const fl
   d.w2 = w2_dev;
   d.bias2 = bias2_dev;
   d.out = out_dev;
+  d.pair = opt(OPT_FFN_FUSED) >= 2 ? 1 : 0;
   FfnLaunch l;
   std::string e;
   if (!ffn_prepare(d, &l, &e)) return set_err(e);

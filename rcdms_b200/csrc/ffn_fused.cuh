@@ -372,8 +372,8 @@ ffn_geglu_fused_kernel(const __grid_constant__ FfnMaps maps, const FfnParams p) 
       for (int c = 0; c < 160; c += 16) {
         uint32_t r[16];
         tmem_ld16(tmem_base + lane_sel + cg * 160 + c, r);
-        const uint4 rv0 = __ldg(reinterpret_cast<const uint4*>(res + c));
-        const uint4 rv1 = __ldg(reinterpret_cast<const uint4*>(res + c + 8));
+        const uint4 rv0 = *reinterpret_cast<const uint4*>(res + c);      // (plain loads: res may alias out)
+        const uint4 rv1 = *reinterpret_cast<const uint4*>(res + c + 8);
         const float4* bp = reinterpret_cast<const float4*>(p.bias2 + cg * 160 + c);
         float bv[16];
 #pragma unroll
@@ -410,6 +410,351 @@ ffn_geglu_fused_kernel(const __grid_constant__ FfnMaps maps, const FfnParams p) 
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc<512>(tmem_base);
+  }
+}
+
+
+// ------------------------------------------------------------------------------------------------------------------------
+// CTA-pair version (cluster of 2, tcgen05 cta_group::2, M = 256): the pair owns 256 rows; CTA r keeps rows [128 r, +128)
+// resident and holds HALF of every weight chunk (W1f: 32 of the chunk's 64 packed rows; W2: 80 of each 160-row half), so the
+// same shared memory gives the W1f ring four stages instead of two (the refill latency of ~2 100 cycles was what bound the
+// single-CTA kernel) and every SM pulls half the weight bytes.  MMAs are issued by the leader CTA's two issuer threads;
+// loads of both CTAs complete on the leader's barriers, commits are multicast to both CTAs, and the epilogue warps of both
+// CTAs arrive on the leader's barriers (same scheme as the CTA-pair GEMM in gemm_tcgen05.cuh).
+// ------------------------------------------------------------------------------------------------------------------------
+struct FfnPairCfg {
+  static constexpr int C = 320, J = 4 * C, KB1 = C / 64, CH = 32, NCH = J / CH;
+  static constexpr int A1_KB_BYTES = 128 * 128;
+  static constexpr int A1_BYTES = KB1 * A1_KB_BYTES;        // 80 KB
+  static constexpr int B1_KB_BYTES = 32 * 128;              // this CTA's 32 packed rows x one k-block
+  static constexpr int B1_BYTES = KB1 * B1_KB_BYTES;        // 20 KB per chunk
+  static constexpr int B1_STAGES = 4;
+  static constexpr int B2_HALF_BYTES = 80 * 64;             // this CTA's 80 rows of one 160-row half x 32 columns
+  static constexpr int B2_BYTES = 2 * B2_HALF_BYTES;        // 10 KB per chunk
+  static constexpr int B2_STAGES = 3;
+  static constexpr int A2_BYTES = 128 * CH * 2;             // 8 KB
+  static constexpr int NB = 3;
+  static constexpr int NBAR = 48;
+  static constexpr int SMEM_BYTES = A1_BYTES + B1_STAGES * B1_BYTES + B2_STAGES * B2_BYTES + NB * A2_BYTES + NBAR * 8 + 16;
+  static constexpr int THREADS = 384;
+  static constexpr int TMEM_ACC1 = 320;
+  static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB per-CTA shared memory limit");
+};
+
+__device__ __forceinline__ void tma_load_3d_2sm(void* smem, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], "
+      "[%2];" ::"r"(smem_u32(smem)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+
+// maps: a1 as in the single-CTA kernel; b1 box (64, 32, C/64); b2 box (32, 80)
+template <typename T>
+__global__ void __launch_bounds__(FfnPairCfg::THREADS, 1)
+ffn_geglu_fused_pair_kernel(const __grid_constant__ FfnMaps maps, const FfnParams p) {
+  using Cfg = FfnPairCfg;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sA1 = smem;
+  uint8_t* sB1 = sA1 + Cfg::A1_BYTES;
+  uint8_t* sB2 = sB1 + Cfg::B1_STAGES * Cfg::B1_BYTES;
+  uint8_t* sA2 = sB2 + Cfg::B2_STAGES * Cfg::B2_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sA2 + Cfg::NB * Cfg::A2_BYTES);
+  uint64_t* a1_full = bars;          // [5]  (leader's is used)
+  uint64_t* a1_empty = bars + 5;     // [5]  multicast commit
+  uint64_t* b1_full = bars + 10;     // [4]  leader
+  uint64_t* b1_empty = bars + 14;    // [4]  multicast commit
+  uint64_t* b2_full = bars + 18;     // [3]  leader
+  uint64_t* b2_empty = bars + 21;    // [3]  multicast commit
+  uint64_t* acc1_full = bars + 24;   // [3]  multicast commit
+  uint64_t* acc1_empty = bars + 27;  // [3]  leader, 16 arrivals
+  uint64_t* a2_full = bars + 30;     // [3]  leader, 16 arrivals
+  uint64_t* a2_empty = bars + 33;    // [3]  multicast commit
+  uint64_t* acc2_full = bars + 36;   //      multicast commit
+  uint64_t* acc2_empty = bars + 37;  //      leader, 16 arrivals
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + Cfg::NBAR);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int wid = (int)(blockIdx.x >> 1), nworkers = (int)(gridDim.x >> 1);
+  const int num_pairs = (p.num_m_tiles + 1) / 2;
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&maps.a1);
+    tma_prefetch_desc(&maps.b1);
+    tma_prefetch_desc(&maps.b2);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int i = 0; i < 5; ++i) {
+        mbar_init(&a1_full[i], 1);
+        mbar_init(&a1_empty[i], 1);
+      }
+      for (int i = 0; i < Cfg::B1_STAGES; ++i) {
+        mbar_init(&b1_full[i], 1);
+        mbar_init(&b1_empty[i], 1);
+      }
+      for (int i = 0; i < Cfg::B2_STAGES; ++i) {
+        mbar_init(&b2_full[i], 1);
+        mbar_init(&b2_empty[i], 1);
+      }
+      for (int i = 0; i < Cfg::NB; ++i) {
+        mbar_init(&acc1_full[i], 1);
+        mbar_init(&acc1_empty[i], 16);
+        mbar_init(&a2_full[i], 16);
+        mbar_init(&a2_empty[i], 1);
+      }
+      mbar_init(acc2_full, 1);
+      mbar_init(acc2_empty, 16);
+      fence_mbar_init();
+    }
+    __syncwarp();
+    tmem_alloc_2cta<512>(tmem_slot);
+  }
+  tc_fence_before();
+  cluster_sync_all();  // the peer's barriers are initialised before anything signals them
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_sync();
+  // arrival on the LEADER's copy of a barrier (epilogue warps of both CTAs)
+  auto arrive_leader = [&](uint64_t* bar) { mbar_arrive_cluster(mapa_u32(smem_u32(bar), 0)); };
+
+  if (warp == 0) {
+    // =============================== producer: row tile (A1) and this CTA's half of the W1f chunks ===============================
+    if (elect_one()) {
+      uint32_t st1 = 0, ph1 = 0;
+      int t = 0;
+      for (int pt = wid; pt < num_pairs; pt += nworkers, ++t) {
+        const int mt = 2 * pt + (int)rank;
+        for (int kb = 0; kb < Cfg::KB1; ++kb) {
+          mbar_wait(&a1_empty[kb], (t & 1) ^ 1);
+          if (rank == 0) mbar_expect_tx(&a1_full[kb], 2 * Cfg::A1_KB_BYTES);
+          tma_load_2d_2sm(sA1 + kb * Cfg::A1_KB_BYTES, &maps.a1, &a1_full[kb], kb * 64, mt * 128);
+        }
+        for (int j = 0; j < Cfg::NCH; ++j) {
+          mbar_wait(&b1_empty[st1], ph1 ^ 1);
+          if (rank == 0) mbar_expect_tx(&b1_full[st1], 2 * Cfg::B1_BYTES);
+          tma_load_3d_2sm(sB1 + st1 * Cfg::B1_BYTES, &maps.b1, &b1_full[st1], 0, j * 64 + (int)rank * 32, 0);
+          if (++st1 == Cfg::B1_STAGES) {
+            st1 = 0;
+            ph1 ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 10) {
+    // =============================== producer: this CTA's half of the W2 chunks ===============================
+    if (elect_one()) {
+      uint32_t st2 = 0, ph2 = 0;
+      for (int pt = wid; pt < num_pairs; pt += nworkers) {
+        for (int j = 0; j < Cfg::NCH; ++j) {
+          mbar_wait(&b2_empty[st2], ph2 ^ 1);
+          if (rank == 0) mbar_expect_tx(&b2_full[st2], 2 * Cfg::B2_BYTES);
+          uint8_t* dst = sB2 + st2 * Cfg::B2_BYTES;
+          tma_load_2d_2sm(dst, &maps.b2, &b2_full[st2], j * Cfg::CH, (int)rank * 80);
+          tma_load_2d_2sm(dst + Cfg::B2_HALF_BYTES, &maps.b2, &b2_full[st2], j * Cfg::CH, 160 + (int)rank * 80);
+          if (++st2 == Cfg::B2_STAGES) {
+            st2 = 0;
+            ph2 ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =============================== MMA issuer, GEMM1 (leader CTA only) ===============================
+    if (rank == 0 && elect_one()) {
+      constexpr uint32_t idesc1 = umma_idesc_f16(DT<T>::umma_fmt, 256, 64, 0, 0);
+      const uint64_t a1_desc = umma_smem_desc(smem_u32(sA1), 16, 1024, UMMA_SWIZZLE_128B);
+      const uint64_t b1_desc = umma_smem_desc(smem_u32(sB1), 16, 1024, UMMA_SWIZZLE_128B);
+      uint32_t n1 = 0, p1 = 0, st1 = 0, ph1 = 0;
+      int t = 0;
+      for (int pt = wid; pt < num_pairs; pt += nworkers, ++t) {
+        for (int j = 0; j < Cfg::NCH; ++j) {
+          mbar_wait(&acc1_empty[n1], p1 ^ 1);
+          mbar_wait(&b1_full[st1], ph1);
+          tc_fence_after();
+          const uint32_t d1 = tmem_base + Cfg::TMEM_ACC1 + n1 * 64;
+          const uint64_t b1_stage = b1_desc + (uint64_t)((st1 * Cfg::B1_BYTES) >> 4);
+#pragma unroll
+          for (int kb = 0; kb < Cfg::KB1; ++kb) {
+            if (j == 0) {
+              mbar_wait(&a1_full[kb], t & 1);
+              tc_fence_after();
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const uint64_t ad = a1_desc + (uint64_t)((kb * Cfg::A1_KB_BYTES + k * 32) >> 4);
+              const uint64_t bd = b1_stage + (uint64_t)((kb * Cfg::B1_KB_BYTES + k * 32) >> 4);
+              umma_f16_ss_2cta(d1, ad, bd, idesc1, (kb | k) != 0);
+            }
+            if (j == Cfg::NCH - 1) umma_commit_2cta(&a1_empty[kb]);
+          }
+          umma_commit_2cta(&b1_empty[st1]);
+          umma_commit_2cta(&acc1_full[n1]);
+          if (++st1 == Cfg::B1_STAGES) {
+            st1 = 0;
+            ph1 ^= 1;
+          }
+          if (++n1 == Cfg::NB) {
+            n1 = 0;
+            p1 ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 11) {
+    // =============================== MMA issuer, GEMM2 (leader CTA only) ===============================
+    if (rank == 0 && elect_one()) {
+      constexpr uint32_t idesc2 = umma_idesc_f16(DT<T>::umma_fmt, 256, 160, 0, 0);
+      const uint64_t a2_desc = umma_smem_desc(smem_u32(sA2), 2048, 128, UMMA_SWIZZLE_NONE);
+      const uint64_t b2_desc = umma_smem_desc(smem_u32(sB2), 16, 512, UMMA_SWIZZLE_64B);
+      uint32_t n2 = 0, p2 = 0, st2 = 0, ph2 = 0;
+      int t = 0;
+      for (int pt = wid; pt < num_pairs; pt += nworkers, ++t) {
+        mbar_wait(acc2_empty, (t & 1) ^ 1);
+        tc_fence_after();
+        for (int i = 0; i < Cfg::NCH; ++i) {
+          mbar_wait(&a2_full[n2], p2);
+          mbar_wait(&b2_full[st2], ph2);
+          tc_fence_after();
+#pragma unroll
+          for (int k = 0; k < Cfg::CH / 16; ++k) {
+            const uint64_t ad = a2_desc + (uint64_t)((n2 * Cfg::A2_BYTES + k * 2 * 2048) >> 4);
+#pragma unroll
+            for (int nh = 0; nh < 2; ++nh) {
+              const uint64_t bd = b2_desc + (uint64_t)((st2 * Cfg::B2_BYTES + nh * Cfg::B2_HALF_BYTES + k * 32) >> 4);
+              umma_f16_ss_2cta(tmem_base + nh * 160, ad, bd, idesc2, (i | k) != 0);
+            }
+          }
+          umma_commit_2cta(&a2_empty[n2]);
+          umma_commit_2cta(&b2_empty[st2]);
+          if (++st2 == Cfg::B2_STAGES) {
+            st2 = 0;
+            ph2 ^= 1;
+          }
+          if (++n2 == Cfg::NB) {
+            n2 = 0;
+            p2 ^= 1;
+          }
+        }
+        umma_commit_2cta(acc2_full);
+      }
+    }
+  } else if (warp >= 2 && warp < 10) {
+    // =============================== epilogue warps (both CTAs) ===============================
+    const int q = warp & 3;
+    const int cg = (warp - 2) >> 2;
+    const uint32_t lane_sel = uint32_t(q * 32) << 16;
+    using T2 = typename DT<T>::T2;
+    uint32_t nb = 0, pb = 0;
+    int t = 0;
+    for (int pt = wid; pt < num_pairs; pt += nworkers, ++t) {
+      const int mt = 2 * pt + (int)rank;
+      const int row = q * 32 + lane;
+      const int m = mt * 128 + row;
+      const int mc = min(m, p.M - 1);
+      float sx = 0.f, sxx = 0.f;
+      for (int pp = 0; pp < p.stats_parts; ++pp) {
+        const float2 v = __ldg(&p.stats_in[(size_t)pp * p.M + mc]);
+        sx += v.x;
+        sxx += v.y;
+      }
+      const float inv_k = 1.0f / (float)Cfg::C;
+      const float mean = sx * inv_k;
+      const float rstd = rsqrtf(fmaxf(sxx * inv_k - mean * mean, 0.f) + p.ln_eps);
+      float4 chn[4], cgn[4];
+      auto fetch_c = [&](int j) {
+        const float4* ch = reinterpret_cast<const float4*>(p.c1 + (size_t)j * 64 + cg * 16);
+        const float4* cgp = reinterpret_cast<const float4*>(p.c1 + (size_t)j * 64 + 32 + cg * 16);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          chn[i] = __ldg(ch + i);
+          cgn[i] = __ldg(cgp + i);
+        }
+      };
+      fetch_c(0);
+      for (int j = 0; j < Cfg::NCH; ++j) {
+        float chf[16], cgf[16];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          chf[4 * i] = chn[i].x, chf[4 * i + 1] = chn[i].y, chf[4 * i + 2] = chn[i].z, chf[4 * i + 3] = chn[i].w;
+          cgf[4 * i] = cgn[i].x, cgf[4 * i + 1] = cgn[i].y, cgf[4 * i + 2] = cgn[i].z, cgf[4 * i + 3] = cgn[i].w;
+        }
+        if (j + 1 < Cfg::NCH) fetch_c(j + 1);
+        mbar_wait(&acc1_full[nb], pb);
+        tc_fence_after();
+        uint32_t rh[16], rg[16];
+        const uint32_t ta = tmem_base + lane_sel + Cfg::TMEM_ACC1 + nb * 64;
+        tmem_ld16(ta + cg * 16, rh);
+        tmem_ld16(ta + 32 + cg * 16, rg);
+        tmem_wait_ld();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) arrive_leader(&acc1_empty[nb]);
+        float v[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+          v[i] = fmaf(__uint_as_float(rh[i]), rstd, chf[i]) * gelu_erf_f(fmaf(__uint_as_float(rg[i]), rstd, cgf[i]));
+        const uint4 p0 = pack8<T>(v), p1 = pack8<T>(v + 8);
+        mbar_wait(&a2_empty[nb], pb ^ 1);
+        uint8_t* a2 = sA2 + nb * Cfg::A2_BYTES;
+        *reinterpret_cast<uint4*>(a2 + (2 * cg) * 2048 + row * 16) = p0;
+        *reinterpret_cast<uint4*>(a2 + (2 * cg + 1) * 2048 + row * 16) = p1;
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) arrive_leader(&a2_full[nb]);
+        if (++nb == Cfg::NB) {
+          nb = 0;
+          pb ^= 1;
+        }
+      }
+      mbar_wait(acc2_full, t & 1);
+      tc_fence_after();
+      const T* res = reinterpret_cast<const T*>(p.res) + (size_t)mc * Cfg::C + cg * 160;
+      T* out = reinterpret_cast<T*>(p.out) + (size_t)mc * Cfg::C + cg * 160;
+#pragma unroll 1
+      for (int c = 0; c < 160; c += 16) {
+        uint32_t r[16];
+        tmem_ld16(tmem_base + lane_sel + cg * 160 + c, r);
+        const uint4 rv0 = *reinterpret_cast<const uint4*>(res + c);
+        const uint4 rv1 = *reinterpret_cast<const uint4*>(res + c + 8);
+        const float4* bp = reinterpret_cast<const float4*>(p.bias2 + cg * 160 + c);
+        float bv[16];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float4 x = __ldg(bp + i);
+          bv[4 * i] = x.x, bv[4 * i + 1] = x.y, bv[4 * i + 2] = x.z, bv[4 * i + 3] = x.w;
+        }
+        tmem_wait_ld();
+        float v[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]) + bv[i];
+        uint4 o0 = pack8<T>(v), o1 = pack8<T>(v + 8);
+        T2* a0 = reinterpret_cast<T2*>(&o0);
+        T2* a1 = reinterpret_cast<T2*>(&o1);
+        const T2* b0 = reinterpret_cast<const T2*>(&rv0);
+        const T2* b1 = reinterpret_cast<const T2*>(&rv1);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          a0[i] = __hadd2(a0[i], b0[i]);
+          a1[i] = __hadd2(a1[i], b1[i]);
+        }
+        if (m < p.M) {
+          *reinterpret_cast<uint4*>(out + c) = o0;
+          *reinterpret_cast<uint4*>(out + c + 8) = o1;
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) arrive_leader(acc2_empty);
+    }
+  }
+  tc_fence_before();
+  __syncwarp();
+  cluster_sync_all();  // neither CTA may exit while its peer can still touch its shared memory / barriers
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_2cta<512>(tmem_base);
   }
 }
 

@@ -568,16 +568,18 @@ bool ffn_prepare(const FfnDesc& d, FfnLaunch* l, std::string* err) {
     uint32_t box[2] = {64, 128};
     if (!encode_tmap_sw(&l->maps.a1, d.y, 2, dims, str, box, 128, err)) return false;
   }
-  {  // W1f [2J, C] seen as (64 columns, 2J rows, C / 64 k-blocks): one box = a chunk's 64 rows x all k-blocks
+  const int pair = d.pair && num_sms() >= 2 ? 1 : 0;
+  {  // W1f [2J, C] seen as (64 columns, 2J rows, C / 64 k-blocks): one box = a chunk's 64 rows (pair: this CTA's 32) x all
+     // k-blocks
     uint64_t dims[3] = {64, (uint64_t)2 * J, (uint64_t)C / 64};
     uint64_t str[2] = {(uint64_t)C * 2, 128};
-    uint32_t box[3] = {64, 64, (uint32_t)C / 64};
+    uint32_t box[3] = {64, (uint32_t)(pair ? 32 : 64), (uint32_t)C / 64};
     if (!encode_tmap_sw(&l->maps.b1, d.w1f, 3, dims, str, box, 128, err)) return false;
   }
   {
     uint64_t dims[2] = {(uint64_t)J, (uint64_t)C};
     uint64_t str[1] = {(uint64_t)J * 2};
-    uint32_t box[2] = {(uint32_t)FfnCfg::CH, 160};
+    uint32_t box[2] = {(uint32_t)FfnCfg::CH, (uint32_t)(pair ? 80 : 160)};
     if (!encode_tmap_sw(&l->maps.b2, d.w2, 2, dims, str, box, 64, err)) return false;
   }
   FfnParams& p = l->p;
@@ -591,11 +593,34 @@ bool ffn_prepare(const FfnDesc& d, FfnLaunch* l, std::string* err) {
   p.res = d.y;
   p.out = d.out;
   l->dt = d.dt;
+  l->pair = pair;
   const int sms = num_sms();
-  l->grid = dim3(p.num_m_tiles < sms ? p.num_m_tiles : sms);
+  if (pair) {
+    const int pairs = (p.num_m_tiles + 1) / 2, workers = sms / 2;
+    l->grid = dim3(2 * (pairs < workers ? pairs : workers));
+  } else {
+    l->grid = dim3(p.num_m_tiles < sms ? p.num_m_tiles : sms);
+  }
   return true;
 }
 void ffn_launch(const FfnLaunch& l, cudaStream_t s) {
+  if (l.pair) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = l.grid;
+    cfg.blockDim = dim3(FfnPairCfg::THREADS);
+    cfg.dynamicSmemBytes = FfnPairCfg::SMEM_BYTES;
+    cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    if (l.dt == DT_F16) cudaLaunchKernelEx(&cfg, ffn_geglu_fused_pair_kernel<__half>, l.maps, l.p);
+    else cudaLaunchKernelEx(&cfg, ffn_geglu_fused_pair_kernel<__nv_bfloat16>, l.maps, l.p);
+    return;
+  }
   if (l.dt == DT_F16)
     launch_k(ffn_geglu_fused_kernel<__half>, l.grid, dim3(FfnCfg::THREADS), FfnCfg::SMEM_BYTES, s, l.maps, l.p);
   else
@@ -607,6 +632,12 @@ bool ffn_setup_attributes(std::string* err) {
   if (e == cudaSuccess)
     e = cudaFuncSetAttribute(ffn_geglu_fused_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              FfnCfg::SMEM_BYTES);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(ffn_geglu_fused_pair_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             FfnPairCfg::SMEM_BYTES);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(ffn_geglu_fused_pair_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             FfnPairCfg::SMEM_BYTES);
   if (e != cudaSuccess) {
     if (err) *err = std::string("cudaFuncSetAttribute(ffn): ") + cudaGetErrorString(e);
     return false;

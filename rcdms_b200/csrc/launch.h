@@ -170,12 +170,14 @@ struct FfnDesc {
   const void* w2;           // [320, 1280]
   const float* bias2;       // [320]
   void* out;                // [M, 320] (may alias y)
+  int pair;                 // 1: CTA-pair kernel
 };
 struct FfnLaunch {
   FfnMaps maps;
   FfnParams p;
   dim3 grid;
   int dt;
+  int pair;  // CTA-pair kernel (library option "ffn_fused" >= 2)
 };
 bool ffn_prepare(const FfnDesc& d, FfnLaunch* l, std::string* err);
 void ffn_launch(const FfnLaunch& l, cudaStream_t s);

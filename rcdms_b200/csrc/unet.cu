@@ -661,6 +661,7 @@ struct Planner {
     d.w2 = wm(w2);
     d.bias2 = wv(b2);
     d.out = p(y_off);
+    d.pair = opt(OPT_FFN_FUSED) >= 2 ? 1 : 0;
     FfnLaunch l;
     std::string e;
     if (!ffn_prepare(d, &l, &e)) return fail(e);

@@ -8,7 +8,10 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 import torch  # noqa: E402
 
 import parity_checks as pc  # noqa: E402
-from rcdms_b200 import ops  # noqa: E402
+from rcdms_b200 import _lib, ops  # noqa: E402
+
+if os.environ.get("FFN_MODE"):  # 1 = single-CTA kernel, 2 = CTA-pair kernel
+    _lib.lib().rcdm_debug_set_option(b"ffn_fused", int(os.environ["FFN_MODE"]))
 
 for dt in (torch.float16, torch.bfloat16):
     for M in (128, 1000, 20480):

@@ -69,3 +69,18 @@ def test_gemm_scheduling_variants_agree(pair, sk):
     finally:
         L.rcdm_set_gemm_pair(prev_pair)
         L.rcdm_set_stream_k_min(prev_sk)
+
+
+@pytest.mark.parametrize("mode", [1, 2])
+def test_fused_feed_forward_kernels(mode):
+    """Both builds of the opt-in fused GEGLU feed-forward (library option "ffn_fused": 1 = single-CTA kernel, 2 = CTA-pair
+    kernel; the standalone entry point takes the kernel from the option) against fp32 and the two-GEMM path."""
+    from rcdms_b200 import _lib
+    L = _lib.lib()
+    prev = L.rcdm_debug_set_option(b"ffn_fused", mode)
+    try:
+        for M, dt in ((128, torch.float16), (1000, torch.float16), (4224, torch.bfloat16)):
+            r = pc.check_ffn_fused(M, dt)
+            assert r["ok"], (mode, r)
+    finally:
+        L.rcdm_debug_set_option(b"ffn_fused", prev)
