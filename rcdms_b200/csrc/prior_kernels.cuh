@@ -305,8 +305,11 @@ masked_attn_mma_kernel(const T* __restrict__ qkv, int ld, const float* __restric
 // ---------------------------------------------------------------------------------------------------------------
 // DV = active lanes of a slice = d / 8 (DV == LPH for power-of-two head dims; the UNet's d = 40 / 80 / 160 use
 // DV = 5 / 10 / 20 of LPH = 8 / 16 / 32 lanes, the idle lanes contribute zeros to the reductions).
+#ifndef RCDM_TEMPORAL_MIN_CTAS
+#define RCDM_TEMPORAL_MIN_CTAS 2
+#endif
 template <typename T, int F, int LPH, int DV = LPH>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, RCDM_TEMPORAL_MIN_CTAS)
 temporal_attn_wide_kernel(const T* __restrict__ qkv, T* __restrict__ out, int batch, int hw, int heads, float scale) {
   constexpr int d = DV * 8;
   const int C = heads * d, ld = 3 * C;
