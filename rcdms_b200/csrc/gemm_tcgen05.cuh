@@ -255,7 +255,7 @@ template <int BN, bool PAIR = false> struct GemmCfg {
 // Persistent, warp-specialised: grid = min(#tiles, #SMs), one CTA per SM.  Tiles are visited round-robin
 // (n fastest, so CTAs running concurrently share A rows in L2).  The TMA producer runs ahead across tile
 // boundaries; two TMEM accumulators let the MMA warp start tile i+1 while the epilogue warps drain tile i.
-// 11 warps = 3 on the fullest SM sub-partition (16384 registers each) => at most 168 registers per thread.
+// 12 warps = 3 per SM sub-partition (16384 registers each) => at most 168 registers per thread.
 // ACT: compile-time switch for the epilogue activation (p.act).  The activation-free instantiation is the one every
 // UNet GEMM runs: a run-time branch inside `finish8` cost the epilogue-bound small-K GEMMs 15-19 % (measured), so the
 // stage-1 prior's GELU / SiLU epilogues get their own instantiation.
