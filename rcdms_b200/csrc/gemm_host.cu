@@ -35,6 +35,10 @@ static PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn(std::string* err) {
   return fn;
 }
 
+// L2 promotion of TMA loads (experiment switch; 256 B measured best / equal on the UNet step)
+#ifndef RCDM_TMA_L2_PROMOTION
+#define RCDM_TMA_L2_PROMOTION CU_TENSOR_MAP_L2_PROMOTION_L2_256B
+#endif
 bool encode_tmap(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                  const uint32_t* box, bool swizzle128, std::string* err) {
   return encode_tmap_sw(out, base, rank, dims, strides_bytes, box, swizzle128 ? 128 : 0, err);
@@ -61,7 +65,7 @@ bool encode_tmap_sw(CUtensorMap* out, const void* base, int rank, const uint64_t
                   swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
                   : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
                   : swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE,
-                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                  RCDM_TMA_L2_PROMOTION, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     if (err) {
       char buf[256];
