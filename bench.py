@@ -438,6 +438,7 @@ def run_ours(a):
                               clocks=e["clocks"], steps=1, warmup=2))
             del pipe3
             torch.cuda.empty_cache()
+            extra.append(prior_extra_config(a))
         else:
             e = measure(pipe, dtype, 8, a.ctx_len, 1, 2)
             extra.append(dict(workload=workload_name(a, 8) + f", {8 * world} clips over {world} GPUs", baseline_config=5,
@@ -506,6 +507,54 @@ def prior_cpu_seconds_per_forward(layers_sample=2):
         dt = time.time() - t0
     full = prior_full_config()["num_layers"]
     return dt * full / layers_sample, dict(cores=cores, sample_s=dt, layers_sample=layers_sample)
+
+
+def prior_extra_config(a, steps=1, warm=2):
+    """BASELINE config 4 (stage-1 frame prior, 100 UnCLIP steps, one clip) measured inside the default stage-2 run so that the
+    driver's record carries it: device-resident value only (the full line with e2e / cpu_baseline: --workload prior)."""
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "scripts"))
+    from bench_prior import algorithmic_flops, device_random_weights
+    from rcdms_b200.models.myprior_transformer import MyPriorTransformer
+    from rcdms_b200.pipelines.prior_pipeline import Seq_Inpaint_Prior_Pipeline
+    from rcdms_b200.prior_spec import PRIOR_SCHEDULER_KWARGS, prior_full_config
+    from rcdms_b200.schedulers import UnCLIPScheduler
+    from rcdms_b200.synthetic import stack_prior_clips, synthetic_prior_inputs
+    dtype = torch.float16
+    steps_n = a.prior_steps
+    cfg = prior_full_config()
+    model = device_random_weights(MyPriorTransformer.from_config(cfg), dtype)
+    pipe = Seq_Inpaint_Prior_Pipeline(prior=model, image_encoder=None, text_encoder=None, tokenizer=None,
+                                      scheduler=UnCLIPScheduler(**PRIOR_SCHEDULER_KWARGS))
+    pipe.use_cuda_graph = not a.no_graph
+    dev = {k: (v.to(dtype) if v.is_floating_point() else v).cuda()
+           for k, v in stack_prior_clips([synthetic_prior_inputs(cfg, 0)]).items()}
+    gen = torch.Generator(device="cuda").manual_seed(42)
+
+    def sample():
+        return pipe.sample(dev["latents"], dev["prompt_embeds"], dev["text_hidden"], dev["text_mask"],
+                           dev["imgs_proj_embeds1"], dev["mask_label"], steps_n, 4.0, generator=gen)
+
+    for _ in range(warm):
+        sample()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(0)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        sample()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    clocks = sampler.stop()
+    tf = algorithmic_flops(cfg, 10) * steps_n / (ms / 1e3) / 1e12
+    del pipe, model
+    torch.cuda.empty_cache()
+    return dict(workload="stage-1 prior: kandinsky-2-2 prior + 20 prior-state motion modules (2.88 B params), 97 tokens, CFG 4.0, "
+                         f"{steps_n} UnCLIP steps, 1 clip per run", baseline_config=4, dtype="f16", value=5.0 / (ms / 1e3),
+                unit="frame-embeddings/s", ms_per_step=ms, ms_per_unclip_step=ms / steps_n, achieved_tflops=tf, clocks=clocks,
+                steps=steps, warmup=warm)
 
 
 def run_prior(a):
