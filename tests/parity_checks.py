@@ -391,7 +391,10 @@ def all_op_checks(dtypes=(torch.float16, torch.bfloat16), quick=False):
         for (b, hds, sq, skv, d) in [(4, 8, 256, 256, 40), (3, 8, 64, 85, 40), (2, 8, 1024, 1024, 80),
                                      (2, 8, 256, 256, 160), (10, 8, 64, 64, 8), (10, 8, 16, 7, 16),
                                      (10, 8, 4, 4, 32), (10, 8, 1, 1, 32), (2, 2, 4096, 4096, 40),
-                                     (2, 8, 1024, 91, 80), (2, 4, 300, 200, 40)]:
+                                     (2, 8, 1024, 91, 80), (2, 4, 300, 200, 40),
+                                     # odd numbers of 64-key tiles (the MMA loop is unrolled by stage parity), ragged last tiles,
+                                     # a head dim whose padded chunk is not the 6th (d = 24 -> 32)
+                                     (2, 8, 256, 150, 40), (1, 4, 128, 320, 80), (2, 8, 130, 450, 160), (2, 2, 200, 129, 24)]:
             yield lambda a=(b, hds, sq, skv, d), dt=dt: check_flash(*a, dt)
         yield lambda dt=dt: check_flash(2, 4, 512, 512, 40, dt, qscale=8.0)
         yield lambda dt=dt: check_flash(2, 8, 64, 85, 40, dt, simple=True)
