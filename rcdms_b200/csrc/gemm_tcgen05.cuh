@@ -220,12 +220,15 @@ struct GemmMaps {
 // rows [128r, 128r+128) and B rows [r*BN/2, (r+1)*BN/2) in its own shared memory and its 128 accumulator rows in its own
 // TMEM.  Per MMA the SM then ingests 16 KB + BN*64 B instead of 16 KB + BN*128 B: the L2 -> SM port (~64 B/clk), not
 // the tensor pipe, bounds the single-CTA kernel (128x160: 115 B/clk at full MMA rate; pair 256x160: 83 B/clk).
+#ifndef RCDM_GEMM_STAGES64
+#define RCDM_GEMM_STAGES64 6
+#endif
 template <int BN, bool PAIR = false> struct GemmCfg {
   static constexpr int BM = 128, BK = 64;
   // (RCDM_GEMM_EXPERIMENT == 11: one stage less, to measure how far the main loop is bound by stages / load latency)
   // (192-wide tiles - single CTA only - are used where they save a whole wave of tiles, see gemm_plain_bn: 3 stages)
   static constexpr int STAGES = (PAIR ? (BN <= 64 ? 8 : BN <= 128 ? 6 : 5)
-                                      : ((BN <= 64) ? 6 : (BN <= 128 ? 5 : (BN <= 160 ? 4 : 3)))) -
+                                      : ((BN <= 64) ? RCDM_GEMM_STAGES64 : (BN <= 128 ? 5 : (BN <= 160 ? 4 : 3)))) -
                                 (RCDM_GEMM_EXPERIMENT == 11 ? 1 : 0);
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = (PAIR ? BN / 2 : BN) * BK * 2;

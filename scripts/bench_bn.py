@@ -29,6 +29,8 @@ def timeit(fn, reps=20, warm=3):
 
 
 SHAPES = [(970, 2048, 2048), (970, 6144, 2048), (970, 8192, 2048), (970, 2048, 8192)] if len(sys.argv) > 1 and sys.argv[1] == "prior" else None
+if len(sys.argv) > 1 and sys.argv[1] == "small":
+    SHAPES = [(640, 1280, 1280), (640, 3840, 1280), (640, 1280, 5120), (640, 1280, 2560)]
 for (M, N, K) in SHAPES or [(10240, 640, 640), (10240, 1920, 640), (10240, 640, 2560), (640, 1280, 1280), (640, 3840, 1280), (640, 1280, 5120),
                   (2560, 1280, 1280), (2560, 3840, 1280), (2560, 1280, 5120), (40960, 320, 320), (40960, 960, 320), (40960, 320, 1280)]:
     a = torch.randn((M, K), device="cuda").to(dt)
