@@ -55,6 +55,8 @@ def parse():
                     help="stage2 (default, the headline metric) | prior: BASELINE config 4, the stage-1 frame-prior loop "
                          "(SURVEY 8f rank 1), single GPU")
     ap.add_argument("--prior-steps", type=int, default=100)
+    ap.add_argument("--prior-standalone-ln", action="store_true",
+                    help="prior workload: every nn.LayerNorm as its own launch instead of folded around the GEMMs (A/B leg)")
     return ap.parse_args()
 
 
@@ -585,6 +587,7 @@ def run_prior(a):
     dtype = torch.float16 if a.dtype == "fp16" else torch.bfloat16
     cfg = prior_full_config()
     model = device_random_weights(MyPriorTransformer.from_config(cfg), dtype)
+    model.fold_layernorm = not a.prior_standalone_ln
     pipe = Seq_Inpaint_Prior_Pipeline(prior=model, image_encoder=None, text_encoder=None, tokenizer=None,
                                       scheduler=UnCLIPScheduler(**PRIOR_SCHEDULER_KWARGS))
     pipe.use_cuda_graph = not a.no_graph
@@ -636,7 +639,8 @@ def run_prior(a):
         dtype="f16" if a.dtype == "fp16" else "bf16", data="synthetic",
         config=dict(workload="stage-1 prior: kandinsky-2-2 prior + 20 prior-state motion modules (2.88 B params), 97 tokens, "
                              f"CFG 4.0 (10 rows per clip), {steps_n} UnCLIP steps, {a.clips} clip(s) per run", clips_per_gpu=a.clips,
-                    cuda_graph=not a.no_graph,
+                    cuda_graph=not a.no_graph, layernorm="standalone launches" if a.prior_standalone_ln else "folded around the GEMMs",
+                    launches_per_unclip_step=int(pipe.last_gpu_launches // steps_n),
                     ms_per_unclip_step=ms / steps_n,
                     l2="not flushed: 5.76 GB of fp16 weights stream through per step >> 126 MB L2"),
         e2e=dict(value=frames / (ms_e2e / 1e3), unit="frame-embeddings/s", ms_per_step=ms_e2e,

@@ -186,6 +186,24 @@ RCDM_API size_t rcdm_linear_ln_scratch_bytes(int M, int N, int K, int frames);
 RCDM_API int rcdm_linear_ln(int dtype, const void* x_dev, const void* w_dev, const float* gamma_dev, const float* beta_dev,
                             const float* pe_dev, const float* bias_dev, void* out_dev, int M, int N, int K, int geglu,
                             int frames, int rows_per_frame, float eps, void* scratch_dev, void* stream);
+/* The two halves of rcdm_linear_ln for a host that folds once at load time and chains GEMMs (stage-1 prior:
+ * myprior_transformer.py:275-411 through attention.py:479-526 / motion_module.py:150-174,234-246 - every nn.LayerNorm
+ * that sits between two Linear layers):
+ *   rcdm_fold_ln: wf[n,k] = w[n,k] gamma[k] - mean_k(w[n,:] gamma) (16 bit), c[f][n] = sum_k (beta[k] + pe[f][k]) w[n,k]
+ *                 + bias[n]; pe [frames][K] or NULL, bias or NULL; w may be packed by rcdm_pack_geglu (then so is bias).
+ *   rcdm_gemm_stats_parts(M, N): statistic parts per row a producer GEMM [M, N] emits (stats buffer: float2[parts][M]).
+ *   rcdm_rowstats: single-part statistics of a matrix no GEMM of this library produced.
+ *   rcdm_gemm_ln: rcdm_gemm_ex (dense output / residual rows) with
+ *                 stats_in_dev != NULL: w_dev = wf, vec_dev = c of rcdm_fold_ln, out = act(rstd(row) * A wf^T + c[frame(row)])
+ *                 (+ residual), frame(row) = (row / rows_per_frame) % frames; stats_in_dev == NULL: vec_dev = bias;
+ *                 stats_out_dev != NULL: also writes the (sum, sum of squares) parts of the rounded output rows. */
+RCDM_API int rcdm_fold_ln(int dtype, const void* w_dev, const float* gamma_dev, const float* beta_dev, const float* pe_dev,
+                          const float* bias_dev, void* wf_out_dev, float* c_out_dev, int N, int K, int frames, void* stream);
+RCDM_API int rcdm_gemm_stats_parts(int M, int N);
+RCDM_API int rcdm_rowstats(int dtype, const void* x_dev, void* stats_dev, int M, int K, void* stream);
+RCDM_API int rcdm_gemm_ln(int dtype, const void* a_dev, int lda, const void* w_dev, const float* vec_dev,
+                          const void* residual_dev, void* out_dev, int M, int N, int K, int flags, const void* stats_in_dev,
+                          int parts_in, int frames, int rows_per_frame, float eps, void* stats_out_dev, void* stream);
 RCDM_API int rcdm_pack_geglu(int dtype, const void* w_dev, const float* bias_dev, void* w_out_dev, float* bias_out_dev, int N,
                     int K, void* stream);
 /* 3x3 conv, pad 1, stride 1|2, channels-last x [n,h,w,cin], w_packed [cout, 9*cin] (tap-major); stride = -2: stride 2

@@ -792,6 +792,105 @@ int rcdm_linear_ln(int dtype, const void* x_dev, const void* w_dev, const float*
   API_END
 }
 
+// The two halves of rcdm_linear_ln as separate calls, for a host that folds its weights once at load time and chains
+// GEMMs (the stage-1 prior's Python host): rcdm_fold_ln = the load-time half (centred gamma-scaled weights + constant
+// vector), rcdm_gemm_ln = rcdm_gemm_ex that can consume row statistics (folded LayerNorm in front of it) and / or emit
+// the statistics of its own rounded output for the next folded LayerNorm.
+int rcdm_fold_ln(int dtype, const void* w_dev, const float* gamma_dev, const float* beta_dev, const float* pe_dev,
+                 const float* bias_dev, void* wf_out_dev, float* c_out_dev, int N, int K, int frames, void* stream) {
+  API_BEGIN
+  if (!dt16(dtype)) return set_err("rcdm_fold_ln: dtype must be f16/bf16");
+  if (!w_dev || !gamma_dev || !beta_dev || !wf_out_dev || !c_out_dev || N <= 0 || K <= 0) return set_err("rcdm_fold_ln: bad argument");
+  if (frames < 1) frames = 1;
+  if (frames > 5) return set_err("rcdm_fold_ln: at most 5 frames");
+  if (ensure_device_ready()) return 1;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int fb = (N * 32 + 255) / 256;
+  if (dtype == DT_F16)
+    fold_ln_kernel<__half><<<fb, 256, 0, st>>>(reinterpret_cast<const __half*>(w_dev), reinterpret_cast<__half*>(wf_out_dev),
+                                               gamma_dev, beta_dev, pe_dev, bias_dev, c_out_dev, N, K, frames);
+  else
+    fold_ln_kernel<__nv_bfloat16><<<fb, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(w_dev),
+                                                      reinterpret_cast<__nv_bfloat16*>(wf_out_dev), gamma_dev, beta_dev,
+                                                      pe_dev, bias_dev, c_out_dev, N, K, frames);
+  g_launches++;
+  return check_launch("rcdm_fold_ln");
+  API_END
+}
+
+int rcdm_gemm_stats_parts(int M, int N) { return gemm_stats_parts(N, M); }
+
+int rcdm_rowstats(int dtype, const void* x_dev, void* stats_dev, int M, int K, void* stream) {
+  API_BEGIN
+  if (!dt16(dtype)) return set_err("rcdm_rowstats: dtype must be f16/bf16");
+  if (!x_dev || !stats_dev || M <= 0 || K <= 0) return set_err("rcdm_rowstats: bad argument");
+  if (ensure_device_ready()) return 1;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int rb = (M * 32 + 255) / 256;
+  if (dtype == DT_F16)
+    rowstats_kernel<__half><<<rb, 256, 0, st>>>(reinterpret_cast<const __half*>(x_dev), reinterpret_cast<float2*>(stats_dev), M, K);
+  else
+    rowstats_kernel<__nv_bfloat16><<<rb, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x_dev),
+                                                       reinterpret_cast<float2*>(stats_dev), M, K);
+  g_launches++;
+  return check_launch("rcdm_rowstats");
+  API_END
+}
+
+int rcdm_gemm_ln(int dtype, const void* a_dev, int lda, const void* w_dev, const float* vec_dev, const void* residual_dev,
+                 void* out_dev, int M, int N, int K, int flags, const void* stats_in_dev, int parts_in, int frames,
+                 int rows_per_frame, float eps, void* stats_out_dev, void* stream) {
+  API_BEGIN
+  if (!dt16(dtype)) return set_err("rcdm_gemm_ln: dtype must be f16/bf16");
+  if (!a_dev || !w_dev || !out_dev || M <= 0 || N <= 0 || K <= 0) return set_err("rcdm_gemm_ln: bad argument");
+  const int geglu = (flags & RCDM_GEMM_GEGLU) ? 1 : 0;
+  const int act = (flags & RCDM_GEMM_GELU) ? 1 : (flags & RCDM_GEMM_SILU) ? 2 : 0;
+  if (flags & RCDM_GEMM_SIMPLE) return set_err("rcdm_gemm_ln: no CUDA-core form (use rcdm_layernorm + rcdm_gemm_ex)");
+  if (geglu && (act || residual_dev || stats_out_dev)) return set_err("rcdm_gemm_ln: GEGLU excludes an activation / residual / statistics");
+  if (lda < K || lda % 8) return set_err("rcdm_gemm_ln: lda must be >= K and a multiple of 8");
+  if (stats_in_dev && (!vec_dev || parts_in <= 0)) return set_err("rcdm_gemm_ln: folded LayerNorm needs the c vector and parts_in > 0");
+  if (stats_in_dev && lda != K) return set_err("rcdm_gemm_ln: folded LayerNorm needs dense A rows");
+  if (frames < 1) frames = 1;
+  if (frames > 5) return set_err("rcdm_gemm_ln: at most 5 frames");
+  if (ensure_device_ready()) return 1;
+  GemmDesc d;
+  memset(&d, 0, sizeof d);
+  d.dt = dtype;
+  d.M = M;
+  d.N = N;
+  d.nseg = 1;
+  d.seg[0] = ASeg{SEG_PLAIN, a_dev, K, lda, 0, 0, 0};
+  d.w = w_dev;
+  d.Ktot = K;
+  d.w_rows = N;
+  d.out = out_dev;
+  d.ldo = geglu ? N / 2 : N;
+  d.res = residual_dev;
+  d.ldr = N;
+  d.geglu = geglu;
+  d.act = act;
+  if (stats_in_dev) {
+    d.stats_in = reinterpret_cast<const float2*>(stats_in_dev);
+    d.stats_parts = parts_in;
+    d.ln_c = vec_dev;
+    d.ln_frames = frames;
+    d.ln_rows_per_frame = rows_per_frame;
+    d.ln_eps = eps;
+  } else {
+    d.bias = vec_dev;
+  }
+  d.stats_out = reinterpret_cast<float2*>(stats_out_dev);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  GemmLaunch l;
+  std::string e;
+  d.sk = sk_workspace_for_stream(st, &e);
+  if (!gemm_prepare(d, &l, &e)) return set_err(e);
+  gemm_launch(l, st);
+  g_launches++;
+  return check_launch("rcdm_gemm_ln");
+  API_END
+}
+
 // Fused GEGLU feed-forward of the C = 320 transformer blocks (ffn_fused.cuh): out = y + GEGLU(LayerNorm(y) W1^T + b1) W2^T + b2.
 // w1 [2560, 320] / bias1 [2560] in the reference layout (h rows, then gate rows), w2 [320, 1280].  The weight folding /
 // packing and the row statistics of y (done once at load time / by the producing GEMM inside the UNet plan) run here per call.

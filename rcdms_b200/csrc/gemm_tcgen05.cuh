@@ -646,11 +646,20 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
       const bool ln_smem = p.ln_frames == 1 || (p.ln_rows_per_frame % 128) == 0;
       constexpr int ST_PRE = 4;  // statistic parts fetched ahead (C = 320: 4 parts, 640: 8, 1280: 16); more would spill
       float2 st_pre[ST_PRE];
+      float st_xs = 0.f, st_xss = 0.f;  // parts beyond the prefetched ones (wide producers: N = 2048 of the prior emits 32)
       const int ln_m = min(m_warp + lane, p.M - 1);
       if (ln) {
 #pragma unroll
         for (int pp = 0; pp < ST_PRE; ++pp)
           if (pp < p.stats_parts) st_pre[pp] = __ldg(&p.stats_in[(size_t)pp * p.M + ln_m]);
+        // summed here, ahead of the accumulator wait as well (two live registers instead of a load chain of
+        // (parts - 4) / unroll L2 round trips between the wait and the first output column)
+#pragma unroll 4
+        for (int pp = ST_PRE; pp < p.stats_parts; ++pp) {
+          const float2 v = __ldg(&p.stats_in[(size_t)pp * p.M + ln_m]);
+          st_xs += v.x;
+          st_xss += v.y;
+        }
         if (p.ln_frames > 1) {
           ln_f = (ln_m / p.ln_rows_per_frame) % p.ln_frames;
           ln_f0 = (min(m_tile * 128, p.M - 1) / p.ln_rows_per_frame) % p.ln_frames;
@@ -665,11 +674,8 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
             sx += st_pre[pp].x;
             sxx += st_pre[pp].y;
           }
-        for (int pp = ST_PRE; pp < p.stats_parts; ++pp) {
-          const float2 v = __ldg(&p.stats_in[(size_t)pp * p.M + ln_m]);
-          sx += v.x;
-          sxx += v.y;
-        }
+        sx += st_xs;
+        sxx += st_xss;
         const float inv_k = 1.0f / (float)p.ln_K;
         const float mean = sx * inv_k;
         const float var = fmaxf(sxx * inv_k - mean * mean, 0.f);

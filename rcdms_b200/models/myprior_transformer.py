@@ -8,8 +8,10 @@ proj_embedding, encoder_hidden_states, proj_embedding1, mask_label, attention_ma
 
 The host side is Python like the reference's; every operation on activations is a C-ABI call (``include/rcdm.h``):
 
-* ``rcdm_layernorm``          — the LayerNorms (width <= 2048), with the temporal positional encoding fused in
 * ``rcdm_gemm_ex``            — every Linear on the tcgen05 GEMM (bias / residual / erf-GELU / SiLU / GEGLU epilogues)
+* ``rcdm_fold_ln`` / ``rcdm_gemm_ln`` / ``rcdm_rowstats`` — the 6 LayerNorms of a block pair folded around the GEMMs
+  (weights folded at load time, row statistics from the producing GEMM's epilogue; temporal positional encoding in the
+  per-frame constant vector); ``rcdm_layernorm`` remains for ``norm_in`` / ``norm_out`` / ``embedding_proj_norm``
 * ``rcdm_masked_attn``        — self-attention with the causal + text-padding mask (``attention.py:171-199``)
 * ``rcdm_temporal_attn``      — the prior-state motion modules' attention over the 5 frames (``motion_module.py:150-174``)
 * ``rcdm_prior_assemble``     — per-step token matrix;  ``rcdm_unclip_cfg_step`` — CFG + scheduler step (pipeline)
@@ -44,14 +46,16 @@ def _f32(t: torch.Tensor) -> torch.Tensor:
 
 
 class _Lin:
-    """One packed Linear: 16-bit weight [N, K] + fp32 bias (the GEMM epilogue vector)."""
+    """One packed Linear: 16-bit weight [N, K] + fp32 bias (the GEMM epilogue vector).  After ``_fold_ln`` the weight is
+    the centred gamma-scaled one of the LayerNorm in front of it and ``c`` [frames, N] replaces the bias."""
 
-    __slots__ = ("w", "b", "n", "k")
+    __slots__ = ("w", "b", "n", "k", "c", "frames")
 
     def __init__(self, w: torch.Tensor, b: Optional[torch.Tensor], dtype):
         self.w = w.detach().to(dtype).contiguous()
         self.b = _f32(b) if b is not None else None
         self.n, self.k = self.w.shape
+        self.c, self.frames = None, 1
 
 
 class _Plan:
@@ -67,6 +71,11 @@ class _Plan:
         self.H = e(M, 4 * C)
         self.out = e(B, d["clip_dim"])
         self.hproj = e(B, C)
+        # row statistics (sum, sum of squares) of the two residual streams, float2[parts][M]: written by the epilogue of the
+        # GEMM that produces the stream, read by the LayerNorm-folded GEMM that consumes it
+        self.parts = int(_lib.lib().rcdm_gemm_stats_parts(M, C))
+        self.SX = torch.empty((self.parts, M, 2), dtype=torch.float32, device=device)
+        self.SH = torch.empty((self.parts, M, 2), dtype=torch.float32, device=device)
 
 
 class MyPriorTransformer(nn.Module):
@@ -197,7 +206,8 @@ class MyPriorTransformer(nn.Module):
         return out
 
     def _versions(self):
-        return tuple((t.data_ptr(), t._version) for t in self.state_dict(keep_vars=True).values())
+        return (bool(self.debug_simple), bool(self.fold_layernorm)) + tuple(
+            (t.data_ptr(), t._version) for t in self.state_dict(keep_vars=True).values())
 
     def _require_cuda(self) -> None:
         if self.device.type != "cuda":
@@ -236,10 +246,14 @@ class MyPriorTransformer(nn.Module):
                  prd=sd["prd_embedding"].to(dt) if "prd_embedding" in sd else None,
                  emb_norm=norm("embedding_proj_norm") if "embedding_proj_norm.weight" in sd else None,
                  norm_in=norm("norm_in") if "norm_in.weight" in sd else None, layers=[])
+        fold = P["fold"] = self._fold_active
         for i in range(d["layers"]):
             p = f"transformer_blocks.{2 * i}"
             lay = dict(n1=norm(p + ".norm1"), qkv=qkv(p + ".attn1", True), o=lin(p + ".attn1.to_out.0"),
                        n3=norm(p + ".norm3"), ff1=lin(p + ".ff.net.0.proj"), ff2=lin(p + ".ff.net.2"), motion=None)
+            if fold:
+                self._fold_ln(lay["qkv"], lay["n1"])
+                self._fold_ln(lay["ff1"], lay["n3"])
             if d["motion"]:
                 m = f"transformer_blocks.{2 * i + 1}.temporal_transformer"
                 t = m + ".transformer_blocks.0"
@@ -248,13 +262,41 @@ class MyPriorTransformer(nn.Module):
                     q = f"{t}.attention_blocks.{a}"
                     att.append(dict(n=norm(f"{t}.norms.{a}"), qkv=qkv(q, False), o=lin(q + ".to_out.0"),
                                     pe=_f32(sd[q + ".pos_encoder.pe"][0, :PRIOR_VIDEO_LENGTH])))
-                lay["motion"] = dict(pn=norm(m + ".prior_norm"), pi=lin(m + ".proj_in"), att=att,
-                                     fn=norm(t + ".ff_norm"), ff1=self._pack_geglu(lin(t + ".ff.net.0.proj")),
-                                     ff2=lin(t + ".ff.net.2"), po=lin(m + ".proj_out"))
+                lay["motion"] = mo = dict(pn=norm(m + ".prior_norm"), pi=lin(m + ".proj_in"), att=att,
+                                          fn=norm(t + ".ff_norm"), ff1=self._pack_geglu(lin(t + ".ff.net.0.proj")),
+                                          ff2=lin(t + ".ff.net.2"), po=lin(m + ".proj_out"))
+                if fold:
+                    self._fold_ln(mo["pi"], mo["pn"])
+                    for a in att:
+                        self._fold_ln(a["qkv"], a["n"], pe=a["pe"])
+                    self._fold_ln(mo["ff1"], mo["fn"])  # after the GEGLU row interleave: folding is row-wise
             P["layers"].append(lay)
         self._packed, self._packed_versions = P, v
         self._plans.clear()
         return P
+
+    # LayerNorm folding (default): the 6 nn.LayerNorm of a block pair that sit between two Linear layers are folded around
+    # the consuming GEMM - centred gamma-scaled weights + constant vector at load time (rcdm_fold_ln), row statistics from
+    # the producing GEMM's epilogue (rcdm_gemm_ln) - so that no stand-alone LayerNorm pass runs inside the layer stack.
+    # False: every LayerNorm is its own rcdm_layernorm launch (the round-1 path; also what debug_simple uses).
+    fold_layernorm = True
+
+    @property
+    def _fold_active(self) -> bool:
+        return bool(self.fold_layernorm) and not self._simple
+
+    @staticmethod
+    def _fold_ln(l: _Lin, gb, pe: Optional[torch.Tensor] = None) -> _Lin:
+        """attention.py:487-522 / motion_module.py:236-246,301-311: LayerNorm (+ positional encoding per frame) -> Linear."""
+        frames = int(pe.shape[0]) if pe is not None else 1
+        wf = torch.empty_like(l.w)
+        c = torch.empty((frames, l.n), dtype=torch.float32, device=l.w.device)
+        _lib.check(_lib.lib().rcdm_fold_ln(_lib.torch_dtype_id(l.w.dtype), l.w.data_ptr(), gb[0].data_ptr(),
+                                           gb[1].data_ptr(), pe.data_ptr() if pe is not None else None,
+                                           l.b.data_ptr() if l.b is not None else None, wf.data_ptr(), c.data_ptr(),
+                                           l.n, l.k, frames, _lib.current_stream_ptr()))
+        l.w, l.c, l.b, l.frames = wf, c, None, frames
+        return l
 
     @staticmethod
     def _pack_geglu(l: _Lin) -> _Lin:
@@ -280,8 +322,24 @@ class MyPriorTransformer(nn.Module):
         return bool(self.debug_simple)
 
     def _gemm(self, a: torch.Tensor, l: _Lin, out: torch.Tensor, res: Optional[torch.Tensor] = None, flags: int = 0,
-              M: Optional[int] = None, lda: Optional[int] = None, a_off: int = 0) -> torch.Tensor:
+              M: Optional[int] = None, lda: Optional[int] = None, a_off: int = 0,
+              stats_in: Optional[Tuple[torch.Tensor, int]] = None, stats_out: Optional[torch.Tensor] = None,
+              rows_per_frame: int = 1) -> torch.Tensor:
+        """stats_in = (buffer, parts): ``l`` is LayerNorm-folded and the row statistics of ``a`` come from that buffer;
+        stats_out: the epilogue also writes the row statistics of ``out`` (for the next folded LayerNorm)."""
         M = a.shape[0] if M is None else M
+        if (l.c is not None) != (stats_in is not None):
+            raise RuntimeError("LayerNorm-folded weights need row statistics (and only they do)")
+        if stats_in is not None or stats_out is not None:
+            vec = l.c if stats_in is not None else l.b  # folded: constant vector c [frames, N]; else the bias
+            st_in, parts_in = stats_in if stats_in is not None else (None, 0)
+            _lib.check(_lib.lib().rcdm_gemm_ln(
+                _lib.torch_dtype_id(a.dtype), a.data_ptr(), l.k, l.w.data_ptr(),
+                vec.data_ptr() if vec is not None else None, res.data_ptr() if res is not None else None,
+                out.data_ptr(), M, l.n, l.k, flags, st_in.data_ptr() if st_in is not None else None, parts_in,
+                l.frames, rows_per_frame, 1e-5, stats_out.data_ptr() if stats_out is not None else None,
+                _lib.current_stream_ptr()))
+            return out
         if self._simple:
             flags |= _lib.GEMM_SIMPLE
         _lib.check(_lib.lib().rcdm_gemm_ex(
@@ -367,7 +425,7 @@ class MyPriorTransformer(nn.Module):
         dtid = _lib.torch_dtype_id(self.dtype)
         s = _lib.current_stream_ptr()
         B, S, C = plan.B, d["seq"], d["inner"]
-        X, Y, A, Hm, QKV, H = plan.X, plan.Y, plan.A, plan.Hm, plan.QKV, plan.H
+        X, Y = plan.X, plan.Y
         self._gemm(latents_rows, P["proj_in"], plan.hproj, M=n_lat)
         t_row = S - 2 - (1 if P["prd"] is not None else 0)
         _lib.check(L.rcdm_prior_assemble(dtid, base.data_ptr(), temb_table.data_ptr(), plan.hproj.data_ptr(),
@@ -376,6 +434,24 @@ class MyPriorTransformer(nn.Module):
         if P["norm_in"] is not None:
             self._ln(X, P["norm_in"], Y)
             X, Y = Y, X
+        if P["fold"]:
+            self._layers_folded(plan, X, key_bias)
+        else:
+            self._layers_standalone_ln(plan, X, Y, key_bias)
+        # norm_out on the last token of every sample only, then proj_to_clip_embeddings (myprior_transformer.py:397-402)
+        # (LayerNorm is row-wise, so normalising every row and projecting row S-1 of each sample through a strided A
+        # operand gives the same values without a gather)
+        self._ln(X, P["norm_out"], Y)
+        return self._gemm(Y, P["clip"], plan.out, M=B, lda=S * C, a_off=(S - 1) * C)
+
+    def _layers_standalone_ln(self, plan: _Plan, X: torch.Tensor, Y: torch.Tensor, key_bias: Optional[torch.Tensor]) -> None:
+        """The layer stack with one rcdm_layernorm launch per nn.LayerNorm (``fold_layernorm`` = False / debug_simple)."""
+        P, d = self._packed, self._dims
+        L = _lib.lib()
+        dtid = _lib.torch_dtype_id(self.dtype)
+        s = _lib.current_stream_ptr()
+        B, S, C = plan.B, d["seq"], d["inner"]
+        A, Hm, QKV, H = plan.A, plan.Hm, plan.QKV, plan.H
         heads, hd = d["heads"], d["head_dim"]
         mh = d["motion_heads"]
         for lay in P["layers"]:
@@ -404,11 +480,43 @@ class MyPriorTransformer(nn.Module):
             self._gemm(Y, mo["ff1"], H, flags=_lib.GEMM_GEGLU)
             self._gemm(H, mo["ff2"], Hm, res=Hm)
             self._gemm(Hm, mo["po"], X, res=X)
-        # norm_out on the last token of every sample only, then proj_to_clip_embeddings (myprior_transformer.py:397-402)
-        # (LayerNorm is row-wise, so normalising every row and projecting row S-1 of each sample through a strided A
-        # operand gives the same values without a gather)
-        self._ln(X, P["norm_out"], Y)
-        return self._gemm(Y, P["clip"], plan.out, M=B, lda=S * C, a_off=(S - 1) * C)
+
+    def _layers_folded(self, plan: _Plan, X: torch.Tensor, key_bias: Optional[torch.Tensor]) -> None:
+        """The layer stack without stand-alone LayerNorm passes: every GEMM that writes a residual stream (X: the token
+        matrix, Hm: the motion module's hidden state) also writes its row statistics, every Linear behind a LayerNorm runs
+        on the folded weights (``_fold_ln``).  Same reference lines as ``_layers_standalone_ln``."""
+        P, d = self._packed, self._dims
+        L = _lib.lib()
+        dtid = _lib.torch_dtype_id(self.dtype)
+        s = _lib.current_stream_ptr()
+        B, S, C = plan.B, d["seq"], d["inner"]
+        A, Hm, QKV, H, SX, SH = plan.A, plan.Hm, plan.QKV, plan.H, plan.SX, plan.SH
+        heads, hd = d["heads"], d["head_dim"]
+        mh = d["motion_heads"]
+        # statistics of the assembled token matrix (no GEMM of ours produced it): single-part layout
+        _lib.check(L.rcdm_rowstats(dtid, X.data_ptr(), SX.data_ptr(), plan.M, C, s))
+        sx = (SX, 1)
+        full = plan.parts
+        for lay in P["layers"]:
+            self._gemm(X, lay["qkv"], QKV, stats_in=sx)
+            _lib.check(L.rcdm_masked_attn(dtid, QKV.data_ptr(), 3 * C, key_bias.data_ptr() if key_bias is not None
+                                          else None, int(key_bias is not None), A.data_ptr(), C, B, heads, S, hd, s))
+            self._gemm(A, lay["o"], X, res=X, stats_out=SX)
+            sx = (SX, full)
+            self._gemm(X, lay["ff1"], H, flags=_lib.GEMM_GELU, stats_in=sx)
+            self._gemm(H, lay["ff2"], X, res=X, stats_out=SX)
+            mo = lay["motion"]
+            if mo is None:
+                continue
+            self._gemm(X, mo["pi"], Hm, stats_in=sx, stats_out=SH)
+            for att in mo["att"]:
+                self._gemm(Hm, att["qkv"], QKV, stats_in=(SH, full), rows_per_frame=S)
+                _lib.check(L.rcdm_temporal_attn(dtid, QKV.data_ptr(), A.data_ptr(), B // PRIOR_VIDEO_LENGTH,
+                                                PRIOR_VIDEO_LENGTH, S, mh, C // mh, s))
+                self._gemm(A, att["o"], Hm, res=Hm, stats_out=SH)
+            self._gemm(Hm, mo["ff1"], H, flags=_lib.GEMM_GEGLU, stats_in=(SH, full))
+            self._gemm(H, mo["ff2"], Hm, res=Hm)
+            self._gemm(Hm, mo["po"], X, res=X, stats_out=SX)
 
     # ---- reference-facing forward ------------------------------------------------------------------------------------
     @torch.no_grad()

@@ -216,6 +216,46 @@ def linear_ex(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = N
     return out
 
 
+def fold_ln(w: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, bias: Optional[torch.Tensor] = None,
+            pe: Optional[torch.Tensor] = None):
+    """rcdm_fold_ln (load-time half of the folded LayerNorm): -> (wf [N, K] 16 bit, c [frames, N] fp32)."""
+    N, K = w.shape
+    frames = pe.shape[0] if pe is not None else 1
+    wf = torch.empty_like(w)
+    c = torch.empty((frames, N), dtype=torch.float32, device=w.device)
+    _lib.check(_lib.lib().rcdm_fold_ln(_dt16(w), w.data_ptr(), gamma.data_ptr(), beta.data_ptr(), _ptr(pe), _ptr(bias),
+                                       wf.data_ptr(), c.data_ptr(), N, K, frames, _lib.current_stream_ptr()))
+    return wf, c
+
+
+def rowstats(x: torch.Tensor) -> torch.Tensor:
+    """rcdm_rowstats: single-part (sum, sum of squares) per row, [1, M, 2] fp32."""
+    M, K = x.shape
+    st = torch.empty((1, M, 2), dtype=torch.float32, device=x.device)
+    _lib.check(_lib.lib().rcdm_rowstats(_dt16(x), x.data_ptr(), st.data_ptr(), M, K, _lib.current_stream_ptr()))
+    return st
+
+
+def gemm_ln(a: torch.Tensor, w: torch.Tensor, vec: Optional[torch.Tensor], residual: Optional[torch.Tensor] = None,
+            act: Optional[str] = None, stats_in: Optional[torch.Tensor] = None, rows_per_frame: int = 1,
+            emit_stats: bool = False, eps: float = 1e-5):
+    """rcdm_gemm_ln.  stats_in [parts, M, 2]: ``w`` / ``vec`` are (wf, c) of ``fold_ln`` and the LayerNorm of ``a`` is
+    applied through them; else ``vec`` is the bias.  act in {None, "gelu", "silu", "geglu"}.  emit_stats: also returns
+    the row statistics [parts, M, 2] of the output.  -> out or (out, stats)."""
+    M, K = a.shape
+    N = w.shape[0]
+    flags = {None: 0, "gelu": _lib.GEMM_GELU, "silu": _lib.GEMM_SILU, "geglu": _lib.GEMM_GEGLU}[act]
+    out = torch.empty((M, N // 2 if act == "geglu" else N), dtype=a.dtype, device=a.device)
+    frames = vec.shape[0] if stats_in is not None else 1
+    so = None
+    if emit_stats:
+        so = torch.empty((int(_lib.lib().rcdm_gemm_stats_parts(M, N)), M, 2), dtype=torch.float32, device=a.device)
+    _lib.check(_lib.lib().rcdm_gemm_ln(_dt16(a), a.data_ptr(), K, w.data_ptr(), _ptr(vec), _ptr(residual), out.data_ptr(),
+                                       M, N, K, flags, _ptr(stats_in), stats_in.shape[0] if stats_in is not None else 0,
+                                       frames, rows_per_frame, eps, _ptr(so), _lib.current_stream_ptr()))
+    return (out, so) if emit_stats else out
+
+
 def masked_attention(qkv: torch.Tensor, heads: int, key_bias: Optional[torch.Tensor] = None,
                      causal: bool = False) -> torch.Tensor:
     """qkv [batch, S, 3C] (q | k | v) -> [batch, S, C]: softmax(q k^T / sqrt(d) + key_bias[b, j] + causal) v."""

@@ -1,6 +1,7 @@
 """TEST INFRASTRUCTURE ONLY — a CPU emulation of the handful of C-ABI entry points the stage-1 prior host code calls
 (``include/rcdm.h``: rcdm_gemm_ex, rcdm_layernorm, rcdm_masked_attn, rcdm_temporal_attn, rcdm_prior_assemble,
-rcdm_unclip_cfg_step, rcdm_pack_geglu), operating on raw pointers into CPU fp16 tensors.
+rcdm_unclip_cfg_step, rcdm_pack_geglu, and the folded-LayerNorm calls rcdm_fold_ln / rcdm_gemm_stats_parts /
+rcdm_rowstats / rcdm_gemm_ln), operating on raw pointers into CPU fp16 tensors.
 
 It exists so that the *host-side orchestration* (argument order, buffer reuse, row pitches, step counter, weight packing
 in ``MyPriorTransformer`` / ``Seq_Inpaint_Prior_Pipeline``) can be checked against the oracle in the CPU test tier,
@@ -64,6 +65,65 @@ class FakeLib:
         if res:
             y = _rn(y + _t(res, (M - 1) * ldr + N).as_strided((M, N), (ldr, 1)).float())
         _t(out, (M - 1) * ldo + n_out).as_strided((M, n_out), (ldo, 1)).copy_(y.half())
+        return 0
+
+    # ---- folded LayerNorm (rcdm_fold_ln / rcdm_gemm_stats_parts / rcdm_rowstats / rcdm_gemm_ln) ----
+    PARTS = 2  # the emulated producer splits its columns into two statistic parts
+
+    def rcdm_gemm_stats_parts(self, M, N):
+        return self.PARTS
+
+    def rcdm_fold_ln(self, dt, w, gamma, beta, pe, bias, wf, c, N, K, frames, stream):
+        W = _t(w, N * K).reshape(N, K).float()
+        g, b = _t(gamma, K, np.float32), _t(beta, K, np.float32)
+        wg = W * g
+        _t(wf, N * K).reshape(N, K).copy_((wg - wg.mean(dim=1, keepdim=True)).half())
+        cc = (W @ b)[None].repeat(frames, 1)
+        if pe:
+            cc = cc + _t(pe, frames * K, np.float32).reshape(frames, K) @ W.t()
+        if bias:
+            cc = cc + _t(bias, N, np.float32)
+        _t(c, frames * N, np.float32).reshape(frames, N).copy_(cc)
+        return 0
+
+    def rcdm_rowstats(self, dt, x, stats, M, K, stream):
+        self.calls.append(("rowstats", M, K))
+        X = _t(x, M * K).reshape(M, K).float()
+        _t(stats, M * 2, np.float32).reshape(M, 2).copy_(torch.stack([X.sum(1), (X * X).sum(1)], dim=1))
+        return 0
+
+    def rcdm_gemm_ln(self, dt, a, lda, w, vec, res, out, M, N, K, flags, stats_in, parts_in, frames, rows_per_frame, eps,
+                     stats_out, stream):
+        assert dt == 1 and lda == K
+        self.calls.append(("gemm_ln", M, N, K, flags, bool(stats_in), bool(stats_out)))
+        A = _t(a, M * K).reshape(M, K).float()
+        y = A @ _t(w, N * K).reshape(N, K).float().t()
+        if stats_in:
+            st = _t(stats_in, parts_in * M * 2, np.float32).reshape(parts_in, M, 2).double().sum(0)
+            mean = st[:, 0] / K
+            rstd = (st[:, 1] / K - mean * mean).clamp_min(0).add(eps).rsqrt().float()
+            cc = _t(vec, frames * N, np.float32).reshape(frames, N)
+            y = y * rstd[:, None] + cc[(torch.arange(M) // max(rows_per_frame, 1)) % frames]
+        elif vec:
+            y = y + _t(vec, N, np.float32)
+        n_out = N
+        if flags & 1:
+            h, g = y.chunk(2, dim=-1)
+            y = h * F.gelu(g)
+            n_out = N // 2
+        elif flags & 2:
+            y = F.gelu(y)
+        elif flags & 4:
+            y = F.silu(y)
+        y = _rn(y)
+        if res:
+            y = _rn(y + _t(res, M * N).reshape(M, N).float())
+        _t(out, M * n_out).reshape(M, n_out).copy_(y.half())
+        if stats_out:
+            S = _t(stats_out, self.PARTS * M * 2, np.float32).reshape(self.PARTS, M, 2)
+            for i, blk in enumerate(y.chunk(self.PARTS, dim=1)):
+                S[i, :, 0] = blk.sum(1)
+                S[i, :, 1] = (blk * blk).sum(1)
         return 0
 
     def rcdm_layernorm(self, dt, x, gamma, beta, out, rows, C, eps, pe, rows_per_frame, frames, stream):

@@ -274,6 +274,34 @@ def test_host_forward_orchestration_matches_oracle(fake_cabi, cfg, t, masked):
     kinds = [c[0] for c in fake_cabi.calls]
     assert kinds.count("mattn") == cfg["num_layers"]
     assert kinds.count("tattn") == (2 * cfg["num_layers"] if cfg["use_motion_module"] else 0)
+    # default = folded LayerNorm: stand-alone passes only for norm_out (+ norm_in / embedding_proj_norm), one statistics
+    # pass over the assembled tokens, every folded consumer fed by statistics
+    assert kinds.count("ln") == 1 + (cfg["norm_in_type"] == "layer") + (cfg["embedding_proj_norm_type"] == "layer")
+    assert kinds.count("rowstats") == 1
+    n_folded = sum(1 for c in fake_cabi.calls if c[0] == "gemm_ln" and c[5])
+    assert n_folded == cfg["num_layers"] * (2 + (4 if cfg["use_motion_module"] else 0))
+
+
+def test_host_forward_standalone_layernorm_path(fake_cabi, monkeypatch):
+    """``fold_layernorm`` = False: one rcdm_layernorm launch per nn.LayerNorm, plain rcdm_gemm_ex everywhere; same result
+    class against the oracle and close to the folded path."""
+    cfg = prior_tiny_config()
+    inp = synthetic_prior_inputs(cfg, clip_index=3)
+    a16 = [x.half() for x in [torch.cat([inp["latents"]] * 2), inp["prompt_embeds"], inp["text_hidden"],
+                              torch.cat([inp["imgs_proj_embeds1"]] * 2), torch.cat([inp["mask_label"]] * 2)]]
+    m, sdr = _half_module(cfg)
+    y_fold = m(a16[0], 500, a16[1], a16[2], a16[3], a16[4], inp["text_mask"]).predicted_image_embedding
+    fake_cabi.calls.clear()
+    monkeypatch.setattr(MyPriorTransformer, "fold_layernorm", False)
+    y = m(a16[0], 500, a16[1], a16[2], a16[3], a16[4], inp["text_mask"]).predicted_image_embedding  # re-packs (key changed)
+    kinds = [c[0] for c in fake_cabi.calls]
+    assert "gemm_ln" not in kinds and "rowstats" not in kinds
+    assert kinds.count("ln") == 1 + 6 * cfg["num_layers"]
+    with torch.no_grad():
+        ref = prior_forward(sdr, cfg, a16[0].float(), 500, a16[1].float(), a16[2].float(), a16[3].float(), a16[4].float(),
+                            inp["text_mask"])
+    assert (y.float() - ref).abs().max().item() < 2e-2 * max(1.0, ref.abs().max().item())
+    assert (y.float() - y_fold.float()).abs().max().item() < 2e-2 * max(1.0, ref.abs().max().item())
 
 
 @pytest.mark.parametrize("guidance", [4.0, 1.0])

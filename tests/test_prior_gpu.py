@@ -122,6 +122,73 @@ def test_layernorm_wide(rows, C, dtype, pe):
     _close(out, ref, dtype, "layernorm")
 
 
+@pytest.mark.parametrize("M,C,N,act,res,frames,S,dtype", [
+    # the prior's chains: to_out (stats) -> norm -> q|k|v / GELU ff / proj_in; temporal norm + PE (5 frames of 97 rows);
+    # GEGLU ff of the motion module; narrow shapes of the tiny config; 192-wide producer tiles (C = 1280, M = 2560: 14 parts)
+    (970, 2048, 6144, None, False, 1, 97, torch.float16), (970, 2048, 8192, "gelu", False, 1, 97, torch.float16),
+    (970, 2048, 2048, None, False, 1, 97, torch.bfloat16), (970, 2048, 6144, None, False, 5, 97, torch.float16),
+    (970, 2048, 16384, "geglu", False, 1, 97, torch.float16), (970, 2048, 16384, "geglu", False, 1, 97, torch.bfloat16),
+    (170, 128, 384, None, False, 5, 17, torch.float16), (170, 128, 512, "gelu", False, 1, 17, torch.float16),
+    (170, 128, 1024, "geglu", False, 1, 17, torch.float16), (2560, 1280, 1280, None, True, 1, 256, torch.float16),
+    (1940, 2048, 6144, None, False, 5, 97, torch.float16)])
+def test_layernorm_folded_gemm_chain(M, C, N, act, res, frames, S, dtype):
+    """rcdm_gemm_ln: a producer GEMM (+ bias + in-place residual) emits the row statistics of its output x; the consumer
+    computes act(LayerNorm(x) [+ pe[frame]]) W^T + b) (+ residual) from x, the statistics and the folded weights.
+    Reference: torch fp32 on the same rounded x (myprior_transformer.py / attention.py:487-522, motion_module.py:236-246)."""
+    g = _gen(11)
+    a0 = torch.randn((M, C), generator=g, device="cuda").to(dtype)
+    w0 = (torch.randn((C, C), generator=g, device="cuda") / C ** 0.5).to(dtype)
+    b0 = torch.randn((C,), generator=g, device="cuda") * 0.1
+    x = ((torch.randn((M, C), generator=g, device="cuda") * 2 + 0.3)).to(dtype)  # residual stream, updated in place
+    x_before = x.clone()
+    from rcdms_b200 import _lib
+    parts = int(_lib.lib().rcdm_gemm_stats_parts(M, C))
+    st = torch.empty((parts, M, 2), dtype=torch.float32, device="cuda")
+    _lib.check(_lib.lib().rcdm_gemm_ln(_lib.torch_dtype_id(dtype), a0.data_ptr(), C, w0.data_ptr(), b0.data_ptr(),
+                                       x.data_ptr(), x.data_ptr(), M, C, C, 0, None, 0, 1, 1, 1e-5, st.data_ptr(),
+                                       _lib.current_stream_ptr()))
+    xr = ((a0.float() @ w0.float().t() + b0).to(dtype).float() + x_before.float())
+    _close(x, xr, dtype, "producer")
+    xs = st.sum(0)
+    assert (xs[:, 0] - x.float().sum(1)).abs().max().item() <= 1e-3 * (1 + x.float().abs().sum(1).max().item())
+    assert (xs[:, 1] / (x.float() ** 2).sum(1) - 1).abs().max().item() <= 1e-4
+    # single-part statistics of the same matrix (rcdm_rowstats) agree
+    assert (ops.rowstats(x)[0] - xs).abs().max().item() <= 1e-3 * xs.abs().max().item()
+    # consumer
+    gamma = 1 + 0.2 * torch.randn((C,), generator=g, device="cuda")
+    beta = 0.2 * torch.randn((C,), generator=g, device="cuda")
+    w = (torch.randn((N, C), generator=g, device="cuda") / C ** 0.5).to(dtype)
+    bias = torch.randn((N,), generator=g, device="cuda") * 0.1
+    pe = torch.randn((frames, C), generator=g, device="cuda") if frames > 1 else None
+    r = torch.randn((M, N), generator=g, device="cuda").to(dtype) if res else None
+    ln = F.layer_norm(x.float(), (C,), gamma, beta, 1e-5)
+    if pe is not None:
+        ln = ln + pe[(torch.arange(M, device="cuda") // S) % frames]
+    y = ln @ w.float().t() + bias
+    if act == "geglu":
+        h, gate = y.chunk(2, dim=-1)
+        y = h * F.gelu(gate)
+        wp, bp = torch.empty_like(w), torch.empty_like(bias)
+        _lib.check(_lib.lib().rcdm_pack_geglu(_lib.torch_dtype_id(dtype), w.data_ptr(), bias.data_ptr(), wp.data_ptr(),
+                                              bp.data_ptr(), N, C, _lib.current_stream_ptr()))
+        w, bias = wp, bp
+    elif act == "gelu":
+        y = F.gelu(y)
+    if res:
+        y = y.to(dtype).float() + r.float()
+    wf, c = ops.fold_ln(w, gamma, beta, bias, pe)
+    out, so = ops.gemm_ln(x, wf, c, r, act, stats_in=st, rows_per_frame=S, emit_stats=True) if act != "geglu" else \
+        (ops.gemm_ln(x, wf, c, None, act, stats_in=st, rows_per_frame=S), None)
+    # the folded form multiplies un-normalised x by 16-bit weights: its rounding error scales with |x| / sigma (~1 here),
+    # same tolerance class as a plain Linear on LayerNorm's rounded output
+    _close(out, y, dtype, f"folded LN gemm {M}x{N}x{C} {act}")
+    if so is not None:
+        assert (so.sum(0)[:, 0] - out.float().sum(1)).abs().max().item() <= 1e-3 * (1 + out.float().abs().sum(1).max().item())
+    # fed by single-part statistics (first layer: the assembled token matrix)
+    out1 = ops.gemm_ln(x, wf, c, r, act, stats_in=ops.rowstats(x), rows_per_frame=S)
+    _close(out1, y, dtype, "single-part statistics")
+
+
 @pytest.mark.parametrize("b,hw,heads,d,dtype", [(2, 97, 8, 256, torch.float16), (2, 97, 8, 256, torch.bfloat16),
                                                 (1, 17, 8, 16, torch.float16), (2, 33, 8, 24, torch.float16),
                                                 (2, 33, 8, 64, torch.float16), (1, 50, 4, 128, torch.bfloat16),
@@ -281,6 +348,22 @@ def test_prior_simple_and_tensorcore_paths_agree():
     _assert_floor(a)
     _assert_floor(b)
     assert (a["y"].float() - b["y"].float()).abs().max().item() <= max(3 * a["fmax"], 5e-3)
+
+
+def test_prior_folded_and_standalone_layernorm_paths_agree():
+    """``fold_layernorm`` = False runs every nn.LayerNorm as its own launch (the round-1 path): both forms stay under the
+    half-precision noise floor against the fp32 oracle and agree with each other, tiny and full width."""
+    from rcdms_b200.models.myprior_transformer import MyPriorTransformer
+    for cfg in (prior_tiny_config(), prior_full_config(num_layers=2)):
+        a = _forward_case(cfg, torch.float16, 500)
+        MyPriorTransformer.fold_layernorm = False
+        try:
+            b = _forward_case(cfg, torch.float16, 500)
+        finally:
+            MyPriorTransformer.fold_layernorm = True
+        _assert_floor(a)
+        _assert_floor(b)
+        assert (a["y"].float() - b["y"].float()).abs().max().item() <= max(3 * a["fmax"], 5e-3)
 
 
 def test_prior_forward_contract():
