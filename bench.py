@@ -54,6 +54,8 @@ def parse():
     ap.add_argument("--workload", default="stage2", choices=["stage2", "prior"],
                     help="stage2 (default, the headline metric) | prior: BASELINE config 4, the stage-1 frame-prior loop "
                          "(SURVEY 8f rank 1), single GPU")
+    ap.add_argument("--unet-option", action="append", default=[], metavar="NAME=VALUE",
+                    help="A/B legs only: per-handle debug switch of the UNet (rcdm_unet_set_option), e.g. po_fold=0")
     ap.add_argument("--prior-steps", type=int, default=100)
     ap.add_argument("--prior-standalone-ln", action="store_true",
                     help="prior workload: every nn.LayerNorm as its own launch instead of folded around the GEMMs (A/B leg)")
@@ -258,6 +260,8 @@ def run_ours(a):
 
     def make_pipe(dtype):
         unet = UNet3DConditionModel.from_config(cfg)
+        for kv in a.unet_option:
+            unet.set_debug_option(kv.split("=")[0], int(kv.split("=")[1]))
         unet.load_state_dict(sd, strict=True)
         unet = unet.to(device=dev, dtype=dtype)
         pipe = RCDMsPipeline(vae=_Vae(), text_encoder=None, tokenizer=None, unet=unet, local_module=None,

@@ -134,7 +134,8 @@ size_t rcdm_unet_workspace_bytes(const rcdm_unet* h) { return h ? h->ws_bytes : 
 int rcdm_unet_set_option(rcdm_unet* h, const char* name, int value) {
   if (!h || !name) return set_err("null argument");
   int* field = !strcmp(name, "simple") ? &h->simple : !strcmp(name, "autotune") ? &h->autotune :
-               !strcmp(name, "ln_fold") ? &h->ln_fold : !strcmp(name, "gn_stats") ? &h->gn_stats : nullptr;
+               !strcmp(name, "ln_fold") ? &h->ln_fold : !strcmp(name, "gn_stats") ? &h->gn_stats :
+               !strcmp(name, "po_fold") ? &h->po_fold : nullptr;
   if (!field) return set_err(std::string("rcdm_unet_set_option: unknown option ") + name);
   if (*field != value) {
     *field = value;

@@ -63,6 +63,8 @@ struct TfW {
   Mat pi, ff1, ff2, po;
   AttW a1, a2;
   LnFold ff1_ln;
+  Mat pof;   // [C, 5C] = [po | po * ff2]: proj_out folded over ff.net.2 (no nonlinearity between them), see fold_proj_kernel
+  Vec pofb;  // [C] = po * ff2b + pob
 };
 struct MoW {
   int C = 0;
@@ -70,6 +72,8 @@ struct MoW {
   Mat pi, ff1, ff2, po;
   AttW att[4];
   LnFold ff1_ln;
+  Mat pof;   // as TfW
+  Vec pofb;
 };
 struct LayerW {
   ResW res;
@@ -135,6 +139,7 @@ struct rcdm_unet_impl {
   int gn_stats = 1;  // GroupNorm statistics from the producing GEMMs' epilogues (0: gn_fused_kernel everywhere)
   size_t gn_acc_bytes = 0;  // size of the accumulator region (from the dry planning pass)
   int ffn_pack64 = 0;  // C = 320 feed-forward weights GEGLU-packed with width 64 for the fused kernel (library option "ffn_fused" at creation)
+  int po_fold = 1;  // ff.net.2 + residual -> proj_out + residual as ONE two-segment GEMM on [po | po * ff2] (rcdm_unet_set_option("po_fold", 0): two GEMMs)
   int ln_fold = 1;  // LayerNorm folded into the consuming GEMM (rcdm_unet_set_option("ln_fold", 0): separate layernorm kernels)
   // per-call inputs (read by the recorded ops)
   const void* cur_sample = nullptr;

@@ -168,6 +168,8 @@ struct Builder {
     t.po = mat(C, C);
     slot(p + ".proj_out.weight", {C, C, 1, 1}, SLOT_MAT, t.po.off, C);
     t.pob = vslot(p + ".proj_out.bias", C);
+    t.pof = mat(C, 5 * C);
+    t.pofb = vec(C);
   }
   void motion(const std::string& p0, int C, MoW& m) {
     const std::string p = p0 + ".temporal_transformer";
@@ -197,6 +199,8 @@ struct Builder {
     m.ffnb = vslot(b + ".ff_norm.bias", C);
     m.po = lin(p + ".proj_out.weight", C, C);
     m.pob = vslot(p + ".proj_out.bias", C);
+    m.pof = mat(C, 5 * C);
+    m.pofb = vec(C);
   }
 };
 
@@ -370,12 +374,82 @@ static void fold_one(rcdm_unet_impl* h, const Mat& w, const LnFold& lf, const Ve
         reinterpret_cast<const __nv_bfloat16*>(h->arena + w.off), reinterpret_cast<__nv_bfloat16*>(h->arena + lf.wf.off),
         f(g), f(b), pe ? f(*pe) : nullptr, bias ? f(*bias) : nullptr, f(lf.c), N, K, lf.frames);
 }
+// proj_out folded over the feed-forward's second Linear.  Transformer3DModel / TemporalTransformer3DModel end with
+//   y2 = y + ff2(g) + b2;  x = x + po(y2) + bp        (attention.py:362-365,523-526; motion_module.py:176-181,244-246)
+// with nothing non-linear in between, so x = x + [y | g] [Wp | Wp W2]^T + (Wp b2 + bp): one GEMM over two K segments, the
+// intermediate y2 (one write + one read of the hidden state, one launch) never exists.
+//   wf [C, 5C]: columns 0..C-1 = Wp, columns C.. = Wp W2 (fp32 accumulation over the 16-bit weights, rounded once)
+//   cf [C]    : Wp b2 + bp (fp32)
+constexpr int FOLDP_NB = 8;  // output rows per block (each W2 element is read once per FOLDP_NB rows)
+template <typename T>
+__global__ void fold_proj_kernel(const T* __restrict__ Wp, const T* __restrict__ W2, const float* __restrict__ b2,
+                                 const float* __restrict__ bp, T* __restrict__ wf, float* __restrict__ cf, int C) {
+  const int J = 4 * C, n0 = blockIdx.y * FOLDP_NB;
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  __shared__ float wp_s[FOLDP_NB][64];
+  float acc[FOLDP_NB];
+#pragma unroll
+  for (int i = 0; i < FOLDP_NB; ++i) acc[i] = 0.f;
+  for (int c0 = 0; c0 < C; c0 += 64) {
+    __syncthreads();
+    for (int e = threadIdx.x; e < FOLDP_NB * 64; e += blockDim.x) {
+      const int i = e / 64, c = c0 + e % 64;
+      wp_s[i][e % 64] = (n0 + i < C && c < C) ? DT<T>::to_f(Wp[(size_t)(n0 + i) * C + c]) : 0.f;
+    }
+    __syncthreads();
+    if (j < J) {
+      const int cm = min(64, C - c0);
+      for (int c = 0; c < cm; ++c) {
+        const float w2 = DT<T>::to_f(W2[(size_t)(c0 + c) * J + j]);
+#pragma unroll
+        for (int i = 0; i < FOLDP_NB; ++i) acc[i] = fmaf(wp_s[i][c], w2, acc[i]);
+      }
+    }
+  }
+  if (j < J) {
+#pragma unroll
+    for (int i = 0; i < FOLDP_NB; ++i)
+      if (n0 + i < C) wf[(size_t)(n0 + i) * 5 * C + C + j] = DT<T>::from_f(acc[i]);
+  }
+  // the unchanged proj_out columns and the constant vector: by the blocks of the first column slab
+  if (blockIdx.x == 0) {
+    for (int e = threadIdx.x; e < FOLDP_NB * C; e += blockDim.x) {
+      const int i = e / C, c = e % C;
+      if (n0 + i < C) wf[(size_t)(n0 + i) * 5 * C + c] = Wp[(size_t)(n0 + i) * C + c];
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int i = warp; i < FOLDP_NB; i += blockDim.x >> 5) {
+      if (n0 + i >= C) continue;
+      float s = 0.f;
+      for (int c = lane; c < C; c += 32) s = fmaf(DT<T>::to_f(Wp[(size_t)(n0 + i) * C + c]), b2[c], s);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      if (lane == 0) cf[n0 + i] = s + bp[n0 + i];
+    }
+  }
+}
+static void fold_proj(rcdm_unet_impl* h, const Mat& po, const Mat& ff2, const Vec& ff2b, const Vec& pob, const Mat& pof,
+                      const Vec& pofb, cudaStream_t st) {
+  auto f = [&](const Vec& v) { return reinterpret_cast<float*>(h->arena + v.off); };
+  const int C = po.rows;
+  const dim3 grid((4 * C + 255) / 256, (C + FOLDP_NB - 1) / FOLDP_NB);
+  if (h->dt == DT_F16)
+    fold_proj_kernel<__half><<<grid, 256, 0, st>>>(reinterpret_cast<const __half*>(h->arena + po.off),
+                                                   reinterpret_cast<const __half*>(h->arena + ff2.off), f(ff2b), f(pob),
+                                                   reinterpret_cast<__half*>(h->arena + pof.off), f(pofb), C);
+  else
+    fold_proj_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(
+        reinterpret_cast<const __nv_bfloat16*>(h->arena + po.off), reinterpret_cast<const __nv_bfloat16*>(h->arena + ff2.off),
+        f(ff2b), f(pob), reinterpret_cast<__nv_bfloat16*>(h->arena + pof.off), f(pofb), C);
+}
 static void fold_tf(rcdm_unet_impl* h, const TfW& t, cudaStream_t st) {
+  fold_proj(h, t.po, t.ff2, t.ff2b, t.pob, t.pof, t.pofb, st);
   fold_one(h, t.a1.qkv, t.a1.qkv_ln, t.ln1g, t.ln1b, nullptr, nullptr, st);
   fold_one(h, t.a2.q, t.a2.q_ln, t.ln2g, t.ln2b, nullptr, nullptr, st);
   fold_one(h, t.ff1, t.ff1_ln, t.ln3g, t.ln3b, nullptr, &t.ff1b, st);
 }
 static void fold_mo(rcdm_unet_impl* h, const MoW& m, cudaStream_t st) {
+  fold_proj(h, m.po, m.ff2, m.ff2b, m.pob, m.pof, m.pofb, st);
   for (int i = 0; i < h->cfg.motion_attn_blocks; ++i)
     fold_one(h, m.att[i].qkv, m.att[i].qkv_ln, m.lng[i], m.lnb[i], &m.pe[i], nullptr, st);
   fold_one(h, m.ff1, m.ff1_ln, m.ffng, m.ffnb, nullptr, &m.ff1b, st);
@@ -644,6 +718,32 @@ struct Planner {
     if (K != w.cols) return fail("linear: K mismatch");
     gemm(d);
   }
+  // x <- x + [y | g] [po | po ff2]^T + (po ff2b + pob): ff.net.2 (+ residual) and proj_out (+ residual) as one launch
+  // over two K segments (fold_proj_kernel); the output's GroupNorm statistics come from this epilogue as before
+  bool po_fold_ok(int C) const { return h->po_fold && !h->simple && C % 64 == 0; }
+  void proj_out_folded(size_t y_off, size_t g_off, int M, int C, const Mat& pof, const Vec& pofb, size_t x_off,
+                       size_t gn_off, int gn_hw) {
+    GemmDesc d;
+    memset(&d, 0, sizeof d);
+    if (gn_off != NO_GN) {
+      d.gn_acc = gnp(gn_off);
+      d.gn_hw = gn_hw;
+    }
+    d.M = M;
+    d.N = C;
+    d.nseg = 2;
+    d.seg[0] = ASeg{SEG_PLAIN, p(y_off), C, C, 0, 0, 0};
+    d.seg[1] = ASeg{SEG_PLAIN, p(g_off), 4 * C, 4 * C, 0, 0, 0};
+    d.w = wm(pof);
+    d.Ktot = 5 * C;
+    d.w_rows = C;
+    d.out = p(x_off);
+    d.ldo = C;
+    d.bias = wv(pofb);
+    d.res = p(x_off);
+    d.ldr = C;
+    gemm(d);
+  }
   // fused GEGLU feed-forward of a 320-channel block (ffn_fused.cuh): y <- y + GEGLU(LN(y) W1^T + b1) W2^T + b2
   bool ffn_fused_ok(int C, bool fold) const { return fold && C == FFN_FUSED_C && h->ffn_pack64 && opt(OPT_FFN_FUSED); }
   void ffn_fused(size_t y_off, int M, const LnFold& ln, size_t stats_off, const Mat& w2, const Vec& b2) {
@@ -889,6 +989,15 @@ struct Planner {
         layernorm(y.off, tmp.off, M, C, t.ln3g, t.ln3b, nullptr, 1);
         linear(tmp.off, M, C, t.ff1, &t.ff1b, g.off, 4 * C, nullptr, 1);
       }
+      if (po_fold_ok(C)) {
+        free_act(tmp);
+        x.gn = new_gn(C, x.H, x.W);  // x is rewritten in place: its statistics are new
+        proj_out_folded(y.off, g.off, M, C, t.pof, t.pofb, x.off, x.gn, HW);
+        free_act(g);
+        free_act(y);
+        if (fold) release(st, st_bytes);
+        return;
+      }
       linear(g.off, M, 4 * C, t.ff2, &t.ff2b, y.off, C, &y.off);
       free_act(g);
     }
@@ -941,6 +1050,15 @@ struct Planner {
       } else {
         layernorm(y.off, tmp.off, M, C, m.ffng, m.ffnb, nullptr, 1);
         linear(tmp.off, M, C, m.ff1, &m.ff1b, g.off, 4 * C, nullptr, 1);
+      }
+      if (po_fold_ok(C)) {
+        free_act(tmp);
+        x.gn = new_gn(C, x.H, x.W);
+        proj_out_folded(y.off, g.off, M, C, m.pof, m.pofb, x.off, x.gn, HW);
+        free_act(g);
+        free_act(y);
+        if (fold) release(st, st_bytes);
+        return;
       }
       linear(g.off, M, 4 * C, m.ff2, &m.ff2b, y.off, C, &y.off);
       free_act(g);

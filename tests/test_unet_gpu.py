@@ -104,6 +104,26 @@ def test_fused_feed_forward_path_matches_oracle():
     torch.cuda.empty_cache()
 
 
+@pytest.mark.parametrize("cfg_fn,shape,dtype", [(tiny_config, (2, 5, 16, 16, 85), torch.float16),
+                                                (full_config, (2, 5, 16, 16, 85), torch.float16),
+                                                (full_config, (2, 5, 32, 32, 85), torch.bfloat16)])
+def test_proj_out_fold_and_two_gemm_paths_agree(cfg_fn, shape, dtype):
+    """Default: ``ff.net.2 (+ residual) -> proj_out (+ residual)`` of every transformer / motion module is ONE GEMM over
+    two K segments on [po | po ff2] (handle option "po_fold" = 1).  With the option off the two reference GEMMs run
+    (attention.py:362-365,523-526; motion_module.py:176-181,244-246): both forms must pass the whole-UNet bound and agree
+    with each other under it."""
+    sd = _full_sd() if cfg_fn is full_config else None
+    a = uc.run_case(cfg_fn(), shape, 501, dtype, sd=sd)
+    _assert_close(a)
+    ya, fl = a["y"].clone(), a["floor"]["max_abs"]
+    a.clear()
+    b = uc.run_case(cfg_fn(), shape, 501, dtype, sd=sd, options={"po_fold": 0})
+    _assert_close(b)
+    assert (ya.float() - b["y"].float()).abs().max().item() <= max(3 * fl, 5e-3)
+    b.clear()
+    torch.cuda.empty_cache()
+
+
 def test_forward_contract():
     """Boundary behaviour of unet.py:322-463: new tensor, inputs untouched, tuple when return_dict=False,
     python-number and 0-dim cuda int64 timesteps agree, state_dict round trip."""

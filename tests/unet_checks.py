@@ -19,12 +19,14 @@ def golden_inputs(cfg, b, f, h, w, L, seed):
     return x, ctx
 
 
-def build_model(cfg, dtype, sd=None, simple=False):
+def build_model(cfg, dtype, sd=None, simple=False, options=None):
     """Product module with the deterministic synthetic weights, on cuda:0 in `dtype`."""
     sd = sd if sd is not None else synthetic_state_dict(cfg, seed=0)
     m = UNet3DConditionModel.from_config(cfg)
     if simple:
         m.set_debug_option("simple", 1)  # explicit ABI switch (the library reads no environment variables)
+    for k, v in (options or {}).items():
+        m.set_debug_option(k, v)
     m.load_state_dict(sd, strict=True)
     m = m.to(device="cuda", dtype=dtype)
     return m
@@ -44,11 +46,11 @@ def noise_floor(cfg, sd32, x, t, ctx, dtype):
     return y16
 
 
-def run_case(cfg, shape, t, dtype, simple=False, taps=False, sd=None, seed=1234):
+def run_case(cfg, shape, t, dtype, simple=False, taps=False, sd=None, seed=1234, options=None):
     b, f, h, w, L = shape
     sd = sd if sd is not None else synthetic_state_dict(cfg, seed=0)
     x, ctx = golden_inputs(cfg, b, f, h, w, L, seed)
-    m = build_model(cfg, dtype, sd, simple=simple)
+    m = build_model(cfg, dtype, sd, simple=simple, options=options)
     if taps:
         m.enable_taps(True)
     xd, cd = x.to("cuda", dtype), ctx.to("cuda", dtype)
