@@ -57,6 +57,8 @@ def parse():
     ap.add_argument("--unet-option", action="append", default=[], metavar="NAME=VALUE",
                     help="A/B legs only: per-handle debug switch of the UNet (rcdm_unet_set_option), e.g. po_fold=0")
     ap.add_argument("--prior-steps", type=int, default=100)
+    ap.add_argument("--prior-two-gemm-proj-out", action="store_true",
+                    help="prior workload: ff.net.2 and proj_out of the motion modules as two GEMMs (A/B leg)")
     ap.add_argument("--prior-standalone-ln", action="store_true",
                     help="prior workload: every nn.LayerNorm as its own launch instead of folded around the GEMMs (A/B leg)")
     return ap.parse_args()
@@ -592,6 +594,7 @@ def run_prior(a):
     cfg = prior_full_config()
     model = device_random_weights(MyPriorTransformer.from_config(cfg), dtype)
     model.fold_layernorm = not a.prior_standalone_ln
+    model.fold_proj_out = not a.prior_two_gemm_proj_out
     pipe = Seq_Inpaint_Prior_Pipeline(prior=model, image_encoder=None, text_encoder=None, tokenizer=None,
                                       scheduler=UnCLIPScheduler(**PRIOR_SCHEDULER_KWARGS))
     pipe.use_cuda_graph = not a.no_graph
@@ -644,6 +647,7 @@ def run_prior(a):
         config=dict(workload="stage-1 prior: kandinsky-2-2 prior + 20 prior-state motion modules (2.88 B params), 97 tokens, "
                              f"CFG 4.0 (10 rows per clip), {steps_n} UnCLIP steps, {a.clips} clip(s) per run", clips_per_gpu=a.clips,
                     cuda_graph=not a.no_graph, layernorm="standalone launches" if a.prior_standalone_ln else "folded around the GEMMs",
+                    proj_out="two GEMMs" if (a.prior_two_gemm_proj_out or a.prior_standalone_ln) else "folded over ff.net.2",
                     launches_per_unclip_step=int(pipe.last_gpu_launches // steps_n),
                     ms_per_unclip_step=ms / steps_n,
                     l2="not flushed: 5.76 GB of fp16 weights stream through per step >> 126 MB L2"),

@@ -131,7 +131,8 @@ RCDM_API int64_t rcdm_unet_read_tap(rcdm_unet* h, const char* name, float* out_d
 RCDM_API int rcdm_unet_enable_taps(rcdm_unet* h, int enable); /* keep tapped activations alive (costs memory) */
 /* per-handle debug switches, effective from the next rcdm_unet_prepare: "simple" (1: every GEMM / attention through the
  * CUDA-core reference kernels, for bisecting a parity failure; never benchmarked), "ln_fold" (0: separate LayerNorm
- * kernels), "autotune" (1: plan-time tile selection). */
+ * kernels), "po_fold" (0: ff.net.2 and proj_out as two GEMMs instead of one on the folded weights), "autotune" (1:
+ * plan-time tile selection). */
 RCDM_API int rcdm_unet_set_option(rcdm_unet* h, const char* name, int value);
 
 /* ---- fused CFG + DDIM step (+ next 9-channel UNet input).  All tensors NCFHW.  eta = 0. ----
@@ -204,6 +205,16 @@ RCDM_API int rcdm_rowstats(int dtype, const void* x_dev, void* stats_dev, int M,
 RCDM_API int rcdm_gemm_ln(int dtype, const void* a_dev, int lda, const void* w_dev, const float* vec_dev,
                           const void* residual_dev, void* out_dev, int M, int N, int K, int flags, const void* stats_in_dev,
                           int parts_in, int frames, int rows_per_frame, float eps, void* stats_out_dev, void* stream);
+/* proj_out folded over ff.net.2: TemporalTransformer3DModel ends with y2 = y + ff2(g) + b2; x = x + po(y2) + bp
+ * (motion_module.py:176-181,244-246) with nothing non-linear in between, so x = x + [y | g] [wp | wp w2]^T + (wp b2 + bp).
+ *   rcdm_fold_proj: wp [C, C], w2 [C, 4C] -> wf [C, 5C] (16 bit, fp32 accumulation), cf [C] fp32 (load time).
+ *   rcdm_gemm_cat : out = [a0 | a1] w^T + bias (+ residual), a0 [M, K0], a1 [M, K1], w [N, K0 + K1] (K0, K1 multiples of
+ *                   64); stats_out_dev != NULL: row statistics of the output as rcdm_gemm_ln writes them. */
+RCDM_API int rcdm_fold_proj(int dtype, const void* wp_dev, const void* w2_dev, const float* b2_dev, const float* bp_dev,
+                            void* wf_out_dev, float* cf_out_dev, int C, void* stream);
+RCDM_API int rcdm_gemm_cat(int dtype, const void* a0_dev, int K0, const void* a1_dev, int K1, const void* w_dev,
+                           const float* bias_dev, const void* residual_dev, void* out_dev, int M, int N,
+                           void* stats_out_dev, void* stream);
 RCDM_API int rcdm_pack_geglu(int dtype, const void* w_dev, const float* bias_dev, void* w_out_dev, float* bias_out_dev, int N,
                     int K, void* stream);
 /* 3x3 conv, pad 1, stride 1|2, channels-last x [n,h,w,cin], w_packed [cout, 9*cin] (tap-major); stride = -2: stride 2

@@ -83,6 +83,8 @@ SIGNATURES = {
     "rcdm_gemm_stats_parts": (_I, [_I, _I]),
     "rcdm_rowstats": (_I, [_I, _P, _P, _I, _I, _P]),
     "rcdm_gemm_ln": (_I, [_I, _P, _I, _P, _P, _P, _P, _I, _I, _I, _I, _P, _I, _I, _I, _F, _P, _P]),
+    "rcdm_fold_proj": (_I, [_I, _P, _P, _P, _P, _P, _P, _I, _P]),
+    "rcdm_gemm_cat": (_I, [_I, _P, _I, _P, _I, _P, _P, _P, _P, _I, _I, _P, _P]),
     "rcdm_ffn_geglu_scratch_bytes": (C.c_size_t, [_I]),
     "rcdm_ffn_geglu_ln": (_I, [_I, _P, _P, _P, _P, _P, _P, _P, _P, _I, _F, _P, _P]),
     "rcdm_groupnorm_scratch_bytes": (C.c_size_t, [_I, _I, _I]),

@@ -892,6 +892,56 @@ int rcdm_gemm_ln(int dtype, const void* a_dev, int lda, const void* w_dev, const
   API_END
 }
 
+// proj_out folded over ff.net.2 (fold_proj_kernel, unet.cu) and the two-segment GEMM that runs on the folded weights, for a
+// host that chains GEMMs itself (stage-1 prior: motion_module.py:176-181,244-246).
+int rcdm_fold_proj(int dtype, const void* wp_dev, const void* w2_dev, const float* b2_dev, const float* bp_dev,
+                   void* wf_out_dev, float* cf_out_dev, int C, void* stream) {
+  API_BEGIN
+  if (!dt16(dtype)) return set_err("rcdm_fold_proj: dtype must be f16/bf16");
+  if (!wp_dev || !w2_dev || !b2_dev || !bp_dev || !wf_out_dev || !cf_out_dev || C <= 0) return set_err("rcdm_fold_proj: bad argument");
+  if (ensure_device_ready()) return 1;
+  fold_proj_launch(dtype, wp_dev, w2_dev, b2_dev, bp_dev, wf_out_dev, cf_out_dev, C, reinterpret_cast<cudaStream_t>(stream));
+  g_launches++;
+  return check_launch("rcdm_fold_proj");
+  API_END
+}
+
+int rcdm_gemm_cat(int dtype, const void* a0_dev, int K0, const void* a1_dev, int K1, const void* w_dev, const float* bias_dev,
+                  const void* residual_dev, void* out_dev, int M, int N, void* stats_out_dev, void* stream) {
+  API_BEGIN
+  if (!dt16(dtype)) return set_err("rcdm_gemm_cat: dtype must be f16/bf16");
+  if (!a0_dev || !a1_dev || !w_dev || !out_dev || M <= 0 || N <= 0 || K0 <= 0 || K1 <= 0) return set_err("rcdm_gemm_cat: bad argument");
+  if (K0 % 64 || K1 % 64) return set_err("rcdm_gemm_cat: K0 and K1 must be multiples of 64");
+  if (ensure_device_ready()) return 1;
+  GemmDesc d;
+  memset(&d, 0, sizeof d);
+  d.dt = dtype;
+  d.M = M;
+  d.N = N;
+  d.nseg = 2;
+  d.seg[0] = ASeg{SEG_PLAIN, a0_dev, K0, K0, 0, 0, 0};
+  d.seg[1] = ASeg{SEG_PLAIN, a1_dev, K1, K1, 0, 0, 0};
+  d.w = w_dev;
+  d.Ktot = K0 + K1;
+  d.w_rows = N;
+  d.out = out_dev;
+  d.ldo = N;
+  d.bias = bias_dev;
+  d.res = residual_dev;
+  d.ldr = N;
+  d.stats_out = reinterpret_cast<float2*>(stats_out_dev);
+  if (stats_out_dev) d.force_bn = gemm_plain_bn(M, N);  // the consumer sums gemm_stats_parts(N, M) parts: same tile width
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  GemmLaunch l;
+  std::string e;
+  d.sk = sk_workspace_for_stream(st, &e);
+  if (!gemm_prepare(d, &l, &e)) return set_err(e);
+  gemm_launch(l, st);
+  g_launches++;
+  return check_launch("rcdm_gemm_cat");
+  API_END
+}
+
 // Fused GEGLU feed-forward of the C = 320 transformer blocks (ffn_fused.cuh): out = y + GEGLU(LayerNorm(y) W1^T + b1) W2^T + b2.
 // w1 [2560, 320] / bias1 [2560] in the reference layout (h rows, then gate rows), w2 [320, 1280].  The weight folding /
 // packing and the row statistics of y (done once at load time / by the producing GEMM inside the UNet plan) run here per call.

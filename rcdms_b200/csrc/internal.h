@@ -20,6 +20,9 @@ int unet_load_weights(rcdm_unet* h, int count, const char* const* names, const v
                       const int64_t* dims, const int* ndims, void* stream);
 int unet_prepare(rcdm_unet* h, int batch, int frames, int height, int width, int ctx_len);
 int unet_run(rcdm_unet* h, bool run_ctx, bool run_step, cudaStream_t st);
+// wf [C, 5C] = [wp | wp w2] (16 bit, fp32 accumulation), cf [C] = wp b2 + bp: proj_out folded over ff.net.2 (unet.cu)
+void fold_proj_launch(int dt, const void* wp, const void* w2, const float* b2, const float* bp, void* wf, float* cf, int C,
+                      cudaStream_t st);
 
 struct GnLaunch {
   GnArgs a;

@@ -428,19 +428,21 @@ __global__ void fold_proj_kernel(const T* __restrict__ Wp, const T* __restrict__
     }
   }
 }
+void fold_proj_launch(int dt, const void* wp, const void* w2, const float* b2, const float* bp, void* wf, float* cf, int C,
+                      cudaStream_t st) {
+  const dim3 grid((4 * C + 255) / 256, (C + FOLDP_NB - 1) / FOLDP_NB);
+  if (dt == DT_F16)
+    fold_proj_kernel<__half><<<grid, 256, 0, st>>>(reinterpret_cast<const __half*>(wp), reinterpret_cast<const __half*>(w2),
+                                                   b2, bp, reinterpret_cast<__half*>(wf), cf, C);
+  else
+    fold_proj_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(wp),
+                                                          reinterpret_cast<const __nv_bfloat16*>(w2), b2, bp,
+                                                          reinterpret_cast<__nv_bfloat16*>(wf), cf, C);
+}
 static void fold_proj(rcdm_unet_impl* h, const Mat& po, const Mat& ff2, const Vec& ff2b, const Vec& pob, const Mat& pof,
                       const Vec& pofb, cudaStream_t st) {
   auto f = [&](const Vec& v) { return reinterpret_cast<float*>(h->arena + v.off); };
-  const int C = po.rows;
-  const dim3 grid((4 * C + 255) / 256, (C + FOLDP_NB - 1) / FOLDP_NB);
-  if (h->dt == DT_F16)
-    fold_proj_kernel<__half><<<grid, 256, 0, st>>>(reinterpret_cast<const __half*>(h->arena + po.off),
-                                                   reinterpret_cast<const __half*>(h->arena + ff2.off), f(ff2b), f(pob),
-                                                   reinterpret_cast<__half*>(h->arena + pof.off), f(pofb), C);
-  else
-    fold_proj_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(
-        reinterpret_cast<const __nv_bfloat16*>(h->arena + po.off), reinterpret_cast<const __nv_bfloat16*>(h->arena + ff2.off),
-        f(ff2b), f(pob), reinterpret_cast<__nv_bfloat16*>(h->arena + pof.off), f(pofb), C);
+  fold_proj_launch(h->dt, h->arena + po.off, h->arena + ff2.off, f(ff2b), f(pob), h->arena + pof.off, f(pofb), po.rows, st);
 }
 static void fold_tf(rcdm_unet_impl* h, const TfW& t, cudaStream_t st) {
   fold_proj(h, t.po, t.ff2, t.ff2b, t.pob, t.pof, t.pofb, st);

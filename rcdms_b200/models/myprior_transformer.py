@@ -206,7 +206,7 @@ class MyPriorTransformer(nn.Module):
         return out
 
     def _versions(self):
-        return (bool(self.debug_simple), bool(self.fold_layernorm)) + tuple(
+        return (bool(self.debug_simple), bool(self.fold_layernorm), bool(self.fold_proj_out)) + tuple(
             (t.data_ptr(), t._version) for t in self.state_dict(keep_vars=True).values())
 
     def _require_cuda(self) -> None:
@@ -247,6 +247,7 @@ class MyPriorTransformer(nn.Module):
                  emb_norm=norm("embedding_proj_norm") if "embedding_proj_norm.weight" in sd else None,
                  norm_in=norm("norm_in") if "norm_in.weight" in sd else None, layers=[])
         fold = P["fold"] = self._fold_active
+        C = d["inner"]
         for i in range(d["layers"]):
             p = f"transformer_blocks.{2 * i}"
             lay = dict(n1=norm(p + ".norm1"), qkv=qkv(p + ".attn1", True), o=lin(p + ".attn1.to_out.0"),
@@ -270,6 +271,9 @@ class MyPriorTransformer(nn.Module):
                     for a in att:
                         self._fold_ln(a["qkv"], a["n"], pe=a["pe"])
                     self._fold_ln(mo["ff1"], mo["fn"])  # after the GEGLU row interleave: folding is row-wise
+                    if self.fold_proj_out and C % 64 == 0:
+                        mo["pof"] = self._fold_proj(mo["po"], mo["ff2"])
+                        mo["po"] = mo["ff2"] = None  # (their device copies are not needed any more)
             P["layers"].append(lay)
         self._packed, self._packed_versions = P, v
         self._plans.clear()
@@ -297,6 +301,24 @@ class MyPriorTransformer(nn.Module):
                                            l.n, l.k, frames, _lib.current_stream_ptr()))
         l.w, l.c, l.b, l.frames = wf, c, None, frames
         return l
+
+    # motion_module.py:176-181,244-246: y2 = y + ff2(g); x = x + proj_out(y2) with nothing non-linear in between ->
+    # x = x + [y | g] [po | po ff2]^T + (po b2 + bp): one two-segment GEMM (rcdm_fold_proj at load time + rcdm_gemm_cat).
+    # Active with fold_layernorm (the folded layer stack); False: ff.net.2 and proj_out stay two GEMMs.
+    fold_proj_out = True
+
+    @staticmethod
+    def _fold_proj(po: _Lin, ff2: _Lin) -> _Lin:
+        C = po.n
+        assert po.k == C and ff2.n == C and ff2.k == 4 * C
+        out = _Lin.__new__(_Lin)
+        out.w = torch.empty((C, 5 * C), dtype=po.w.dtype, device=po.w.device)
+        out.b = torch.empty((C,), dtype=torch.float32, device=po.w.device)
+        out.n, out.k, out.c, out.frames = C, 5 * C, None, 1
+        _lib.check(_lib.lib().rcdm_fold_proj(_lib.torch_dtype_id(po.w.dtype), po.w.data_ptr(), ff2.w.data_ptr(),
+                                             ff2.b.data_ptr(), po.b.data_ptr(), out.w.data_ptr(), out.b.data_ptr(), C,
+                                             _lib.current_stream_ptr()))
+        return out
 
     @staticmethod
     def _pack_geglu(l: _Lin) -> _Lin:
@@ -515,6 +537,11 @@ class MyPriorTransformer(nn.Module):
                                                 PRIOR_VIDEO_LENGTH, S, mh, C // mh, s))
                 self._gemm(A, att["o"], Hm, res=Hm, stats_out=SH)
             self._gemm(Hm, mo["ff1"], H, flags=_lib.GEMM_GEGLU, stats_in=(SH, full))
+            pof = mo.get("pof")
+            if pof is not None:  # X += [Hm | H] [po | po ff2]^T + (po b2 + bp): ff.net.2 and proj_out in one launch
+                _lib.check(L.rcdm_gemm_cat(dtid, Hm.data_ptr(), C, H.data_ptr(), 4 * C, pof.w.data_ptr(), pof.b.data_ptr(),
+                                           X.data_ptr(), X.data_ptr(), plan.M, C, SX.data_ptr(), s))
+                continue
             self._gemm(H, mo["ff2"], Hm, res=Hm)
             self._gemm(Hm, mo["po"], X, res=X, stats_out=SX)
 

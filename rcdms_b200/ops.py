@@ -256,6 +256,31 @@ def gemm_ln(a: torch.Tensor, w: torch.Tensor, vec: Optional[torch.Tensor], resid
     return (out, so) if emit_stats else out
 
 
+def fold_proj(wp: torch.Tensor, w2: torch.Tensor, b2: torch.Tensor, bp: torch.Tensor):
+    """rcdm_fold_proj: wp [C, C], w2 [C, 4C] -> (wf [C, 5C] = [wp | wp w2], cf [C] = wp b2 + bp)."""
+    C = wp.shape[0]
+    wf = torch.empty((C, 5 * C), dtype=wp.dtype, device=wp.device)
+    cf = torch.empty((C,), dtype=torch.float32, device=wp.device)
+    _lib.check(_lib.lib().rcdm_fold_proj(_dt16(wp), wp.data_ptr(), w2.data_ptr(), b2.data_ptr(), bp.data_ptr(),
+                                         wf.data_ptr(), cf.data_ptr(), C, _lib.current_stream_ptr()))
+    return wf, cf
+
+
+def gemm_cat(a0: torch.Tensor, a1: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None,
+             residual: Optional[torch.Tensor] = None, emit_stats: bool = False):
+    """rcdm_gemm_cat: [a0 | a1] @ w^T + bias (+ residual) without materialising the concatenation."""
+    M, K0 = a0.shape
+    K1 = a1.shape[1]
+    N = w.shape[0]
+    out = torch.empty((M, N), dtype=a0.dtype, device=a0.device)
+    so = None
+    if emit_stats:
+        so = torch.empty((int(_lib.lib().rcdm_gemm_stats_parts(M, N)), M, 2), dtype=torch.float32, device=a0.device)
+    _lib.check(_lib.lib().rcdm_gemm_cat(_dt16(a0), a0.data_ptr(), K0, a1.data_ptr(), K1, w.data_ptr(), _ptr(bias),
+                                        _ptr(residual), out.data_ptr(), M, N, _ptr(so), _lib.current_stream_ptr()))
+    return (out, so) if emit_stats else out
+
+
 def masked_attention(qkv: torch.Tensor, heads: int, key_bias: Optional[torch.Tensor] = None,
                      causal: bool = False) -> torch.Tensor:
     """qkv [batch, S, 3C] (q | k | v) -> [batch, S, C]: softmax(q k^T / sqrt(d) + key_bias[b, j] + causal) v."""

@@ -1,7 +1,7 @@
 """TEST INFRASTRUCTURE ONLY — a CPU emulation of the handful of C-ABI entry points the stage-1 prior host code calls
 (``include/rcdm.h``: rcdm_gemm_ex, rcdm_layernorm, rcdm_masked_attn, rcdm_temporal_attn, rcdm_prior_assemble,
 rcdm_unclip_cfg_step, rcdm_pack_geglu, and the folded-LayerNorm calls rcdm_fold_ln / rcdm_gemm_stats_parts /
-rcdm_rowstats / rcdm_gemm_ln), operating on raw pointers into CPU fp16 tensors.
+rcdm_rowstats / rcdm_gemm_ln / rcdm_fold_proj / rcdm_gemm_cat), operating on raw pointers into CPU fp16 tensors.
 
 It exists so that the *host-side orchestration* (argument order, buffer reuse, row pitches, step counter, weight packing
 in ``MyPriorTransformer`` / ``Seq_Inpaint_Prior_Pipeline``) can be checked against the oracle in the CPU test tier,
@@ -67,7 +67,7 @@ class FakeLib:
         _t(out, (M - 1) * ldo + n_out).as_strided((M, n_out), (ldo, 1)).copy_(y.half())
         return 0
 
-    # ---- folded LayerNorm (rcdm_fold_ln / rcdm_gemm_stats_parts / rcdm_rowstats / rcdm_gemm_ln) ----
+    # ---- folded LayerNorm (rcdm_fold_ln / rcdm_gemm_stats_parts / rcdm_rowstats / rcdm_gemm_ln / rcdm_fold_proj / rcdm_gemm_cat) ----
     PARTS = 2  # the emulated producer splits its columns into two statistic parts
 
     def rcdm_gemm_stats_parts(self, M, N):
@@ -119,6 +119,29 @@ class FakeLib:
         if res:
             y = _rn(y + _t(res, M * N).reshape(M, N).float())
         _t(out, M * n_out).reshape(M, n_out).copy_(y.half())
+        if stats_out:
+            S = _t(stats_out, self.PARTS * M * 2, np.float32).reshape(self.PARTS, M, 2)
+            for i, blk in enumerate(y.chunk(self.PARTS, dim=1)):
+                S[i, :, 0] = blk.sum(1)
+                S[i, :, 1] = (blk * blk).sum(1)
+        return 0
+
+    def rcdm_fold_proj(self, dt, wp, w2, b2, bp, wf, cf, C, stream):
+        Wp, W2 = _t(wp, C * C).reshape(C, C).float(), _t(w2, C * 4 * C).reshape(C, 4 * C).float()
+        _t(wf, C * 5 * C).reshape(C, 5 * C).copy_(torch.cat([Wp, Wp @ W2], dim=1).half())
+        _t(cf, C, np.float32).copy_(Wp @ _t(b2, C, np.float32) + _t(bp, C, np.float32))
+        return 0
+
+    def rcdm_gemm_cat(self, dt, a0, K0, a1, K1, w, bias, res, out, M, N, stats_out, stream):
+        self.calls.append(("gemm_cat", M, N, K0, K1))
+        A = torch.cat([_t(a0, M * K0).reshape(M, K0), _t(a1, M * K1).reshape(M, K1)], dim=1).float()
+        y = A @ _t(w, N * (K0 + K1)).reshape(N, K0 + K1).float().t()
+        if bias:
+            y = y + _t(bias, N, np.float32)
+        y = _rn(y)
+        if res:
+            y = _rn(y + _t(res, M * N).reshape(M, N).float())
+        _t(out, M * N).reshape(M, N).copy_(y.half())
         if stats_out:
             S = _t(stats_out, self.PARTS * M * 2, np.float32).reshape(self.PARTS, M, 2)
             for i, blk in enumerate(y.chunk(self.PARTS, dim=1)):

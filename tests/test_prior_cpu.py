@@ -280,6 +280,8 @@ def test_host_forward_orchestration_matches_oracle(fake_cabi, cfg, t, masked):
     assert kinds.count("rowstats") == 1
     n_folded = sum(1 for c in fake_cabi.calls if c[0] == "gemm_ln" and c[5])
     assert n_folded == cfg["num_layers"] * (2 + (4 if cfg["use_motion_module"] else 0))
+    # ff.net.2 + proj_out of every motion module as one two-segment GEMM on the folded weights
+    assert kinds.count("gemm_cat") == (cfg["num_layers"] if cfg["use_motion_module"] else 0)
 
 
 def test_host_forward_standalone_layernorm_path(fake_cabi, monkeypatch):

@@ -189,6 +189,33 @@ def test_layernorm_folded_gemm_chain(M, C, N, act, res, frames, S, dtype):
     _close(out1, y, dtype, "single-part statistics")
 
 
+@pytest.mark.parametrize("M,C,dtype", [(970, 2048, torch.float16), (970, 2048, torch.bfloat16), (170, 128, torch.float16),
+                                       (2560, 1280, torch.float16), (640, 320, torch.bfloat16)])
+def test_proj_out_folded_over_ff2(M, C, dtype):
+    """rcdm_fold_proj + rcdm_gemm_cat against the two Linear layers they replace (motion_module.py:176-181,244-246):
+    x + po(y + ff2(g) + b2) + bp in torch fp32 on the same 16-bit weights / activations; the row statistics the fused
+    launch emits describe its rounded output."""
+    g_ = _gen(12)
+    y = torch.randn((M, C), generator=g_, device="cuda").to(dtype)
+    gg = torch.randn((M, 4 * C), generator=g_, device="cuda").to(dtype)
+    x = torch.randn((M, C), generator=g_, device="cuda").to(dtype)
+    wp = (torch.randn((C, C), generator=g_, device="cuda") / C ** 0.5).to(dtype)
+    w2 = (torch.randn((C, 4 * C), generator=g_, device="cuda") / (4 * C) ** 0.5).to(dtype)
+    b2 = torch.randn((C,), generator=g_, device="cuda") * 0.1
+    bp = torch.randn((C,), generator=g_, device="cuda") * 0.1
+    wf, cf = ops.fold_proj(wp, w2, b2, bp)
+    assert torch.equal(wf[:, :C], wp)
+    ref_w = wp.float() @ w2.float()
+    assert (wf[:, C:].float() - ref_w).abs().max().item() <= (2 ** -10 if dtype == torch.float16 else 2 ** -7) * ref_w.abs().max().item()
+    assert (cf - (wp.float() @ b2 + bp)).abs().max().item() <= 1e-4
+    out, st = ops.gemm_cat(y, gg, wf, cf, x, emit_stats=True)
+    ref = x.float() + (y.float() + gg.float() @ w2.float().t() + b2) @ wp.float().t() + bp
+    _close(out, ref, dtype, "proj_out over ff2")
+    ss = st.sum(0)
+    assert (ss[:, 0] - out.float().sum(1)).abs().max().item() <= 1e-3 * (1 + out.float().abs().sum(1).max().item())
+    assert (ss[:, 1] / (out.float() ** 2).sum(1) - 1).abs().max().item() <= 1e-4
+
+
 @pytest.mark.parametrize("b,hw,heads,d,dtype", [(2, 97, 8, 256, torch.float16), (2, 97, 8, 256, torch.bfloat16),
                                                 (1, 17, 8, 16, torch.float16), (2, 33, 8, 24, torch.float16),
                                                 (2, 33, 8, 64, torch.float16), (1, 50, 4, 128, torch.bfloat16),
@@ -361,6 +388,21 @@ def test_prior_folded_and_standalone_layernorm_paths_agree():
             b = _forward_case(cfg, torch.float16, 500)
         finally:
             MyPriorTransformer.fold_layernorm = True
+        _assert_floor(a)
+        _assert_floor(b)
+        assert (a["y"].float() - b["y"].float()).abs().max().item() <= max(3 * a["fmax"], 5e-3)
+
+
+def test_prior_proj_out_fold_and_two_gemm_paths_agree():
+    """``fold_proj_out`` = False keeps ff.net.2 and proj_out of the motion modules as two GEMMs: same bound, same result class."""
+    from rcdms_b200.models.myprior_transformer import MyPriorTransformer
+    for cfg in (prior_tiny_config(), prior_full_config(num_layers=2)):
+        a = _forward_case(cfg, torch.float16, 500)
+        MyPriorTransformer.fold_proj_out = False
+        try:
+            b = _forward_case(cfg, torch.float16, 500)
+        finally:
+            MyPriorTransformer.fold_proj_out = True
         _assert_floor(a)
         _assert_floor(b)
         assert (a["y"].float() - b["y"].float()).abs().max().item() <= max(3 * a["fmax"], 5e-3)
