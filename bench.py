@@ -54,6 +54,8 @@ def parse():
     ap.add_argument("--workload", default="stage2", choices=["stage2", "prior"],
                     help="stage2 (default, the headline metric) | prior: BASELINE config 4, the stage-1 frame-prior loop "
                          "(SURVEY 8f rank 1), single GPU")
+    ap.add_argument("--lib-option", action="append", default=[], metavar="NAME=VALUE",
+                    help="A/B legs only: library-wide debug switch (rcdm_debug_set_option), e.g. attn_short_kv=0")
     ap.add_argument("--unet-option", action="append", default=[], metavar="NAME=VALUE",
                     help="A/B legs only: per-handle debug switch of the UNet (rcdm_unet_set_option), e.g. po_fold=0")
     ap.add_argument("--prior-steps", type=int, default=100)
@@ -251,6 +253,9 @@ def run_ours(a):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     L = _lib.lib()  # fails loudly if the CUDA library is missing
+    for kv in a.lib_option:
+        if L.rcdm_debug_set_option(kv.split("=")[0].encode(), int(kv.split("=")[1])) < 0:
+            raise SystemExit(f"unknown library option {kv}")
     cfg = full_config()
     sd = synthetic_state_dict(cfg, seed=0)
 

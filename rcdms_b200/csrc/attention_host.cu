@@ -4,6 +4,10 @@
 #include "prior_kernels.cuh"
 
 namespace rcdm {
+int num_sms();  // gemm_host.cu
+}
+
+namespace rcdm {
 
 static int pick_dpad(int d) {
   if (d <= 16) return 16;
@@ -23,6 +27,8 @@ static bool head_map(CUtensorMap* m, const void* base, int ld, int S, int heads,
   return encode_tmap(m, base, 5, dims, str, box, false, err);
 }
 
+static bool short_kv_dim(int d) { return d == 8 || d == 16 || d == 32 || d == 40 || d == 64 || d == 80 || d == 160; }
+
 bool attn_prepare(const AttnDesc& d, AttnLaunch* l, std::string* err) {
   const int dpad = pick_dpad(d.d);
   if (dpad < 0 || d.d % 8 != 0) {
@@ -32,6 +38,23 @@ bool attn_prepare(const AttnDesc& d, AttnLaunch* l, std::string* err) {
   memset(&l->maps, 0, sizeof l->maps);
   l->dpad = dpad;
   l->dt = d.dt;
+  l->short_kv = 0;
+  l->desc = d;
+  auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  if (opt(OPT_ATTN_SHORT_KV) && d.S_kv <= XATTN_SK && short_kv_dim(d.d) && d.ldq % 8 == 0 && d.ldkv % 2 == 0 &&
+      d.ldo % 8 == 0 && al16(d.q) && al16(d.out)) {
+    // short key range: one warp per 16 query rows, whole key range in registers (cross_attn_mma_kernel)
+    const int row_tiles = (d.S_q + 15) / 16, pairs = d.batch * d.heads;
+    int chunks = (4 * num_sms() + pairs - 1) / pairs;            // ~4 CTAs per SM in flight
+    const int max_chunks = (row_tiles + 3) / 4;                  // at least one tile per warp
+    if (chunks > max_chunks) chunks = max_chunks;
+    if (chunks < 1) chunks = 1;
+    l->tiles_per_cta = (row_tiles + chunks - 1) / chunks;
+    l->grid = dim3(pairs, (row_tiles + l->tiles_per_cta - 1) / l->tiles_per_cta, 1);
+    l->p.scale_log2 = (float)(1.4426950408889634 / sqrt((double)d.d));
+    l->short_kv = 1;
+    return true;
+  }
   if (!head_map(&l->maps.q, d.q, d.ldq, d.S_q, d.heads, d.d, d.batch, dpad, 128, err)) return false;
   if (!head_map(&l->maps.k, d.k, d.ldkv, d.S_kv, d.heads, d.d, d.batch, dpad, 64, err)) return false;
   // V: only the real 16-byte chunks when the head dim leaves a padded chunk (the kernel presets that chunk, see MSUM)
@@ -63,7 +86,29 @@ template <typename T> static void launch_dt(const AttnLaunch& l, cudaStream_t s)
     default: launch_one<T, 160>(l, s); break;
   }
 }
+template <typename T, int D> static void launch_short(const AttnLaunch& l, cudaStream_t s) {
+  const AttnDesc& d = l.desc;
+  launch_k(cross_attn_mma_kernel<T, D>, l.grid, dim3(XATTN_THREADS), xattn_smem_bytes(D), s,
+           reinterpret_cast<const T*>(d.q), d.ldq, reinterpret_cast<const T*>(d.k), reinterpret_cast<const T*>(d.v), d.ldkv,
+           reinterpret_cast<T*>(d.out), d.ldo, d.S_q, d.S_kv, d.heads, l.tiles_per_cta, l.p.scale_log2);
+}
+template <typename T> static void launch_short_dt(const AttnLaunch& l, cudaStream_t s) {
+  switch (l.desc.d) {
+    case 8: launch_short<T, 8>(l, s); break;
+    case 16: launch_short<T, 16>(l, s); break;
+    case 32: launch_short<T, 32>(l, s); break;
+    case 40: launch_short<T, 40>(l, s); break;
+    case 64: launch_short<T, 64>(l, s); break;
+    case 80: launch_short<T, 80>(l, s); break;
+    default: launch_short<T, 160>(l, s); break;
+  }
+}
 void attn_launch(const AttnLaunch& l, cudaStream_t s) {
+  if (l.short_kv) {
+    if (l.dt == DT_F16) launch_short_dt<__half>(l, s);
+    else launch_short_dt<__nv_bfloat16>(l, s);
+    return;
+  }
   if (l.dt == DT_F16) launch_dt<__half>(l, s);
   else launch_dt<__nv_bfloat16>(l, s);
 }
@@ -82,6 +127,13 @@ template <typename T> static cudaError_t set_attr_dt() {
   if (e == cudaSuccess) e = set_attr<T, 48>();
   if (e == cudaSuccess) e = set_attr<T, 80>();
   if (e == cudaSuccess) e = set_attr<T, 160>();
+  // cross_attn_mma_kernel: D = 80 / 160 stage more than 48 KB (K rows + V^T + the warps' Q / O tiles)
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(cross_attn_mma_kernel<T, 80>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)xattn_smem_bytes(80));
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(cross_attn_mma_kernel<T, 160>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)xattn_smem_bytes(160));
   return e;
 }
 bool attn_setup_attributes(std::string* err) {

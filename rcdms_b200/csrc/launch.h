@@ -29,6 +29,8 @@ enum Opt : int {
   OPT_GN_FUSED,           // single-launch GroupNorm with a grid barrier (default 1; 0 = two-kernel path)
   OPT_LN_WIDE,            // CTA-per-row LayerNorm for rows wider than 1280 (default 1)
   OPT_GN_STATS,           // GroupNorm statistics from the producing GEMM's epilogue + streaming apply (default 1)
+  OPT_ATTN_SHORT_KV,      // attention over <= 112 keys (the UNet's cross-attention) on the register-resident mma.sync kernel
+                          // (default 0 = tcgen05 flash kernel for every key range: measured equal or faster, profiles/r02_ncu_cross_attn.txt)
   OPT_FFN_FUSED,          // fused GEGLU feed-forward kernel for the C = 320 transformer blocks (default 0: measured slower
                           // than the two GEMMs; set BEFORE rcdm_unet_create - it decides the weight packing)
   OPT_COUNT
@@ -200,6 +202,9 @@ struct AttnLaunch {
   AttnParams p;
   dim3 grid;
   int dpad, dt;
+  // short key range (cross_attn_mma_kernel, prior_kernels.cuh): plain pointers instead of tensor maps
+  int short_kv, tiles_per_cta;
+  AttnDesc desc;
 };
 bool attn_prepare(const AttnDesc& d, AttnLaunch* l, std::string* err);
 void attn_launch(const AttnLaunch& l, cudaStream_t s);

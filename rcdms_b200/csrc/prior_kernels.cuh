@@ -298,6 +298,235 @@ masked_attn_mma_kernel(const T* __restrict__ qkv, int ld, const float* __restric
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// Cross-attention to a SHORT key range (the UNet's attn2: 85 / 91 context tokens, attention.py:140-168,170-199): the same
+// register-resident scheme as masked_attn_mma_kernel - one warp owns 16 query rows and the whole key range, scores,
+// softmax and P V never leave registers - with queries and keys from different tensors, no mask, any head dim D that
+// is a multiple of 8 (k-steps padded to 16 with zeros), and a loop over the query tiles so that the K rows / V^T of one
+// (image, head) are staged in shared memory once per CTA.  The tcgen05 flash kernel spends a whole 128-row CTA
+// (TMEM allocation, barriers, 5-D TMA head gathers) on two key tiles: 45 us for 4096 x 85 keys against ~10 us of HBM time.
+//   q[(img * S_q + i) * ldq + h * D + c],  k / v[(img * S_kv + j) * ldkv + h * D + c],  out like q with ldo
+// grid (images * heads, query chunks); CTA = 4 warps; the chunk's 16-row tiles go round-robin over the warps.
+// OPT-IN (library option attn_short_kv = 1), parity-green, measured on B200 against the flash kernel on the same problems
+// (scripts/bench_xattn.py, profiles/r02_xattn_bench.txt): 80 images x 4096 queries x 91 keys d = 40: 315 vs 292 us; x 1024
+// d = 80: 132 vs 136 us; x 256 d = 160: 99 vs 88 us.  ncu (profiles/r02_ncu_cross_attn.txt): no pipe saturated (HMMA 35 %,
+// shared-memory wavefronts 43 %, XU 28 %), issue slots ~80 % used by 4 warps per scheduler - ~1 600 instructions per
+// 16-row tile, most of them the per-element softmax arithmetic over all 14 key tiles - so the default stays the flash kernel.
+// Global traffic is 16 bytes per lane both ways: a warp's Q tile and O tile pass through a private shared-memory tile
+// (pitch D + 8: fragment reads / writes conflict-free).  With 4-byte fragment loads / stores straight from / to global
+// memory the kernel was bound by L1 wavefronts (8-16 lines per instruction): 333 us for 80 x 4096 queries, flash 292.
+// q, out: 16-byte aligned rows (ldq, ldo multiples of 8).
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int XATTN_NT = 14;                        // 8-key tiles held in registers: S_kv <= 112
+constexpr int XATTN_SK = XATTN_NT * 8;
+constexpr int XATTN_VP = XATTN_SK + 8;              // V^T row pitch (elements)
+constexpr int XATTN_THREADS = 128;
+__host__ __device__ constexpr int xattn_dp(int D) { return (D + 15) / 16 * 16; }
+__host__ __device__ constexpr int xattn_kp(int D) { return xattn_dp(D) + 8; }  // K row pitch (elements): conflict-free B fragments
+__host__ __device__ constexpr size_t xattn_smem_bytes(int D) {  // K rows + V^T + one 16-row Q / O staging tile per warp
+  return (size_t)XATTN_SK * xattn_kp(D) * 2 + (size_t)xattn_dp(D) * XATTN_VP * 2 +
+         (size_t)(XATTN_THREADS / 32) * 16 * xattn_kp(D) * 2;
+}
+
+template <typename T, int D>
+__global__ void __launch_bounds__(XATTN_THREADS)
+cross_attn_mma_kernel(const T* __restrict__ q, int ldq, const T* __restrict__ k, const T* __restrict__ v, int ldkv,
+                      T* __restrict__ out, int ldo, int S_q, int S_kv, int heads, int tiles_per_cta, float scale_log2) {
+  using T2 = typename DT<T>::T2;
+  constexpr int DP = xattn_dp(D), KP = xattn_kp(D), NT = XATTN_NT, SK = XATTN_SK, VP = XATTN_VP;
+  constexpr int NCH = D / 8;                        // 8-wide output column tiles
+  constexpr int NCHUNK = NCH > 10 ? 10 : NCH;       // P V in chunks of <= 80 output dims (register budget at D = 160)
+  extern __shared__ __align__(16) uint8_t sm_raw[];
+  T* Ks = reinterpret_cast<T*>(sm_raw);   // [SK][KP]  rows >= S_kv and columns >= D zero
+  T* Vt = Ks + SK * KP;                   // [DP][VP]  columns >= S_kv zero
+  const int b = blockIdx.x / heads, h = blockIdx.x % heads;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  const T* kb = k + (size_t)b * S_kv * ldkv + h * D;
+  const T* vb = v + (size_t)b * S_kv * ldkv + h * D;
+  pdl_sync();
+  // ---- stage K rows and V^T of this (image, head).  Only what the fragments read beyond the data is zeroed (padding
+  // must be finite zeros): key rows S_kv .. 8 nt_used - 1, channel columns D .. DP - 1, V^T key columns up to the last
+  // 16-key step; these regions are disjoint from the data, so one barrier serves both.
+  const int nt_used = min(NT, (S_kv + 7) / 8);
+  const int sk_read = ((nt_used + 1) / 2) * 16;  // keys the P V k-steps read (<= SK)
+  for (int i = tid; i < (nt_used * 8 - S_kv) * (DP / 8); i += blockDim.x)
+    *reinterpret_cast<uint4*>(Ks + (S_kv + i / (DP / 8)) * KP + (i % (DP / 8)) * 8) = make_uint4(0, 0, 0, 0);
+  if constexpr (DP > D) {
+    for (int j = tid; j < S_kv; j += blockDim.x) *reinterpret_cast<uint4*>(Ks + j * KP + D) = make_uint4(0, 0, 0, 0);
+  }
+  for (int i = tid; i < D * (sk_read - S_kv); i += blockDim.x)
+    Vt[(i / (sk_read - S_kv)) * VP + S_kv + i % (sk_read - S_kv)] = DT<T>::from_f(0.f);
+  const bool vec16 = (ldkv % 8 == 0) && ((reinterpret_cast<uintptr_t>(kb) & 15) == 0) &&
+                     ((reinterpret_cast<uintptr_t>(vb) & 15) == 0);
+  // consecutive threads take consecutive keys of one 8-channel chunk: the transposed V^T stores of a warp then fall
+  // into consecutive half-words (with the chunk index fastest they would all hit one bank: pitch 240 B x 8 rows)
+  for (int i = tid; i < S_kv * NCH; i += blockDim.x) {
+    const int j = i % S_kv, c = (i / S_kv) * 8;
+    uint4 kv, vv;
+    const T* kp = kb + (size_t)j * ldkv + c;
+    const T* vp = vb + (size_t)j * ldkv + c;
+    if (vec16) {
+      kv = __ldg(reinterpret_cast<const uint4*>(kp));
+      vv = __ldg(reinterpret_cast<const uint4*>(vp));
+    } else {
+      uint32_t* k4 = reinterpret_cast<uint32_t*>(&kv);
+      uint32_t* v4 = reinterpret_cast<uint32_t*>(&vv);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        k4[e] = *reinterpret_cast<const uint32_t*>(kp + 2 * e);
+        v4[e] = *reinterpret_cast<const uint32_t*>(vp + 2 * e);
+      }
+    }
+    *reinterpret_cast<uint4*>(Ks + j * KP + c) = kv;  // KP * 2 bytes is a multiple of 16
+    const T* ve = reinterpret_cast<const T*>(&vv);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) Vt[(c + e) * VP + j] = ve[e];
+  }
+  // ---- per-warp Q / O staging tile [16][KP]; its padding columns D .. DP - 1 stay zero
+  T* Qs = Vt + DP * VP + warp * 16 * KP;
+  if constexpr (DP > D) {
+    if (lane < 16) *reinterpret_cast<uint4*>(Qs + lane * KP + D) = make_uint4(0, 0, 0, 0);
+  }
+  constexpr int KS = DP / 16;
+  constexpr int QV = (16 * NCH + 31) / 32;  // 16-byte vectors per lane of a 16 x D tile
+  uint4 qv[QV];
+  auto load_q = [&](int tile) {  // rows beyond S_q: clamped (computed, never stored)
+#pragma unroll
+    for (int i = 0; i < QV; ++i) {
+      const int idx = lane + i * 32, r = idx / NCH, ch = idx % NCH;
+      if (idx < 16 * NCH)
+        qv[i] = __ldg(reinterpret_cast<const uint4*>(q + ((size_t)b * S_q + min(tile * 16 + r, S_q - 1)) * ldq + h * D + ch * 8));
+    }
+  };
+  const int row_tiles = (S_q + 15) / 16;
+  const int tile0 = blockIdx.y * tiles_per_cta;
+  const int tile1 = min(row_tiles, tile0 + tiles_per_cta);
+  if (tile0 + warp < tile1) load_q(tile0 + warp);  // in flight across the staging barrier
+  __syncthreads();
+  // no CTA barrier below this point
+  for (int tile = tile0 + warp; tile < tile1; tile += XATTN_THREADS / 32) {
+    // ---- Q tile -> staging tile -> A fragments: a0 (g, c) a1 (g+8, c) a2 (g, c+8) a3 (g+8, c+8), c = 16 ks + 2t
+#pragma unroll
+    for (int i = 0; i < QV; ++i) {
+      const int idx = lane + i * 32, r = idx / NCH, ch = idx % NCH;
+      if (idx < 16 * NCH) *reinterpret_cast<uint4*>(Qs + r * KP + ch * 8) = qv[i];
+    }
+    __syncwarp();
+    uint32_t qf[KS][4];
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks) {
+      const int c = ks * 16 + 2 * t;
+      qf[ks][0] = *reinterpret_cast<const uint32_t*>(Qs + g * KP + c);
+      qf[ks][1] = *reinterpret_cast<const uint32_t*>(Qs + (g + 8) * KP + c);
+      qf[ks][2] = *reinterpret_cast<const uint32_t*>(Qs + g * KP + c + 8);
+      qf[ks][3] = *reinterpret_cast<const uint32_t*>(Qs + (g + 8) * KP + c + 8);
+    }
+    __syncwarp();  // the staging tile is free again (it takes this tile's output below)
+    // the next tile's Q vectors travel while this tile is computed
+    if (tile + XATTN_THREADS / 32 < tile1) load_q(tile + XATTN_THREADS / 32);
+    // ---- S = Q K^T: accumulator tile nt holds (row g | g+8, keys nt*8 + 2t, +1)
+    float sc[NT][4];
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) sc[nt][0] = sc[nt][1] = sc[nt][2] = sc[nt][3] = 0.f;
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks) {
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) {
+        if (nt < nt_used) {
+          const T* kr = Ks + (nt * 8 + g) * KP + ks * 16 + 2 * t;  // B fragment: b0 (k = 2t, 2t+1; n = g), b1 (k + 8)
+          MmaOp<T>::mma(sc[nt], qf[ks], *reinterpret_cast<const uint32_t*>(kr), *reinterpret_cast<const uint32_t*>(kr + 8));
+        }
+      }
+    }
+    // ---- softmax over the full key range (quad reduction: lanes 4g .. 4g+3 share rows g, g+8)
+    float mxa = -INFINITY, mxb = -INFINITY;
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const bool live = nt * 8 + 2 * t + e < S_kv;
+        const float va = live ? sc[nt][e] * scale_log2 : -INFINITY;
+        const float vb2 = live ? sc[nt][2 + e] * scale_log2 : -INFINITY;
+        sc[nt][e] = va;
+        sc[nt][2 + e] = vb2;
+        mxa = fmaxf(mxa, va);
+        mxb = fmaxf(mxb, vb2);
+      }
+    }
+    mxa = fmaxf(mxa, __shfl_xor_sync(0xffffffffu, mxa, 1));
+    mxa = fmaxf(mxa, __shfl_xor_sync(0xffffffffu, mxa, 2));
+    mxb = fmaxf(mxb, __shfl_xor_sync(0xffffffffu, mxb, 1));
+    mxb = fmaxf(mxb, __shfl_xor_sync(0xffffffffu, mxb, 2));
+    float la = 0.f, lb = 0.f;
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        sc[nt][e] = exp2f(sc[nt][e] - mxa);  // exp2(-inf) = 0 for the padding keys
+        sc[nt][2 + e] = exp2f(sc[nt][2 + e] - mxb);
+        la += sc[nt][e];
+        lb += sc[nt][2 + e];
+      }
+    }
+    la += __shfl_xor_sync(0xffffffffu, la, 1);
+    la += __shfl_xor_sync(0xffffffffu, la, 2);
+    lb += __shfl_xor_sync(0xffffffffu, lb, 1);
+    lb += __shfl_xor_sync(0xffffffffu, lb, 2);
+    const float ia = 1.0f / la, ib = 1.0f / lb;
+    // normalised, 16-bit-rounded probabilities (the reference's softmax output dtype) = A fragments of P V:
+    // key tiles (2 kj, 2 kj + 1) form k-step kj
+    uint32_t pa[NT / 2][4];
+#pragma unroll
+    for (int kj = 0; kj < NT / 2; ++kj) {
+      T2 p0 = DT<T>::from_f2(sc[2 * kj][0] * ia, sc[2 * kj][1] * ia);
+      T2 p1 = DT<T>::from_f2(sc[2 * kj][2] * ib, sc[2 * kj][3] * ib);
+      T2 p2 = DT<T>::from_f2(sc[2 * kj + 1][0] * ia, sc[2 * kj + 1][1] * ia);
+      T2 p3 = DT<T>::from_f2(sc[2 * kj + 1][2] * ib, sc[2 * kj + 1][3] * ib);
+      pa[kj][0] = *reinterpret_cast<uint32_t*>(&p0);
+      pa[kj][1] = *reinterpret_cast<uint32_t*>(&p1);
+      pa[kj][2] = *reinterpret_cast<uint32_t*>(&p2);
+      pa[kj][3] = *reinterpret_cast<uint32_t*>(&p3);
+    }
+    // ---- O = P V in chunks of NCHUNK column tiles, written into the staging tile
+#pragma unroll
+    for (int n0 = 0; n0 < NCH; n0 += NCHUNK) {
+      float oc[NCHUNK][4];
+#pragma unroll
+      for (int n = 0; n < NCHUNK; ++n) oc[n][0] = oc[n][1] = oc[n][2] = oc[n][3] = 0.f;
+#pragma unroll
+      for (int kj = 0; kj < NT / 2; ++kj) {
+        if (2 * kj < nt_used) {  // warp-uniform: the remaining probabilities are exactly zero
+#pragma unroll
+          for (int n = 0; n < NCHUNK; ++n) {
+            if (n0 + n < NCH) {
+              const T* vr = Vt + ((n0 + n) * 8 + g) * VP + kj * 16 + 2 * t;  // b0 (keys kj*16 + 2t, +1; dim), b1 (keys + 8)
+              MmaOp<T>::mma(oc[n], pa[kj], *reinterpret_cast<const uint32_t*>(vr), *reinterpret_cast<const uint32_t*>(vr + 8));
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int n = 0; n < NCHUNK; ++n) {
+        if (n0 + n < NCH) {
+          const int c = (n0 + n) * 8 + 2 * t;
+          *reinterpret_cast<T2*>(Qs + g * KP + c) = DT<T>::from_f2(oc[n][0], oc[n][1]);
+          *reinterpret_cast<T2*>(Qs + (g + 8) * KP + c) = DT<T>::from_f2(oc[n][2], oc[n][3]);
+        }
+      }
+    }
+    __syncwarp();
+    // ---- staging tile -> out, 16 bytes per lane
+#pragma unroll
+    for (int i = 0; i < QV; ++i) {
+      const int idx = lane + i * 32, r = idx / NCH, ch = idx % NCH;
+      if (idx < 16 * NCH && tile * 16 + r < S_q)
+        *reinterpret_cast<uint4*>(out + ((size_t)b * S_q + tile * 16 + r) * ldo + h * D + ch * 8) =
+            *reinterpret_cast<const uint4*>(Qs + r * KP + ch * 8);
+    }
+    __syncwarp();  // before the next tile's Q vectors overwrite the staging tile
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // Temporal attention for wide heads (the prior's motion modules: 8 heads x 256 channels; motion_module.py:294-354):
 // one warp slice of LPH = d / 8 lanes per (location, head); each lane keeps one 16-byte vector of q, k, v for all F
 // frames (coalesced 16-byte global loads, no shared memory), the F x F partial scores are reduced across the slice

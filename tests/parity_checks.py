@@ -237,19 +237,29 @@ def check_rowstats(M, N, K, dtype, residual=True, seed=9):
     return res
 
 
-def check_flash(batch, heads, sq, skv, d, dtype, simple=False, seed=5, qscale=1.0):
+def check_flash(batch, heads, sq, skv, d, dtype, simple=False, seed=5, qscale=1.0, short_kv=None):
+    """short_kv = 0 | 1: library option "attn_short_kv" for this call (1: key ranges <= 112 on the opt-in register-resident
+    mma.sync kernel; 0 = default: the tcgen05 flash kernel like every longer range)."""
     g = _gen(seed)
     q = _rand((batch, sq, heads * d), dtype, g, qscale)
     k = _rand((batch, skv, heads * d), dtype, g)
     v = _rand((batch, skv, heads * d), dtype, g)
-    out = ops.flash_attention(q, k, v, heads, simple=simple)
+    if short_kv is not None:
+        from rcdms_b200 import _lib
+        prev = _lib.lib().rcdm_debug_set_option(b"attn_short_kv", int(short_kv))
+        try:
+            out = ops.flash_attention(q, k, v, heads, simple=simple)
+        finally:
+            _lib.lib().rcdm_debug_set_option(b"attn_short_kv", prev)
+    else:
+        out = ops.flash_attention(q, k, v, heads, simple=simple)
 
     def split(t, s):
         return t.float().reshape(batch, s, heads, d).permute(0, 2, 1, 3)
     ref = F.scaled_dot_product_attention(split(q, sq), split(k, skv), split(v, skv))
     ref = ref.permute(0, 2, 1, 3).reshape(batch, sq, heads * d)
-    return _result(f"flash b{batch} h{heads} Sq{sq} Skv{skv} d{d} simple{int(simple)} qs{qscale}", out, ref, dtype,
-                   rtol_mul=3.0)
+    return _result(f"flash b{batch} h{heads} Sq{sq} Skv{skv} d{d} simple{int(simple)} qs{qscale} short{short_kv}", out, ref,
+                   dtype, rtol_mul=3.0)
 
 
 def check_temporal(batch, frames, hw, heads, d, dtype, seed=6):
@@ -396,7 +406,15 @@ def all_op_checks(dtypes=(torch.float16, torch.bfloat16), quick=False):
                                      # a head dim whose padded chunk is not the 6th (d = 24 -> 32)
                                      (2, 8, 256, 150, 40), (1, 4, 128, 320, 80), (2, 8, 130, 450, 160), (2, 2, 200, 129, 24)]:
             yield lambda a=(b, hds, sq, skv, d), dt=dt: check_flash(*a, dt)
+        # short key ranges (cross-attention to 85 / 91 context tokens at the UNet's four levels, the 8x8 level's self-attention,
+        # the 112-key limit, ragged query tiles): the opt-in register-resident mma.sync kernel AND the flash kernel on the same problems
+        for (b, hds, sq, skv, d) in [(10, 8, 4096, 85, 40), (10, 8, 1024, 85, 80), (10, 8, 256, 85, 160), (10, 8, 64, 85, 160),
+                                     (16, 8, 1024, 91, 80), (10, 8, 64, 64, 160), (2, 8, 100, 112, 40), (3, 4, 33, 5, 64),
+                                     (2, 8, 256, 113, 40)]:
+            for sk in (1, 0):
+                yield lambda a=(b, hds, sq, skv, d), dt=dt, sk=sk: check_flash(*a, dt, short_kv=sk)
         yield lambda dt=dt: check_flash(2, 4, 512, 512, 40, dt, qscale=8.0)
+        yield lambda dt=dt: check_flash(2, 8, 64, 85, 40, dt, qscale=8.0, short_kv=1)
         yield lambda dt=dt: check_flash(2, 8, 64, 85, 40, dt, simple=True)
         for (b, f, hw, hds, d) in [(2, 5, 64, 8, 40), (2, 5, 16, 8, 8), (2, 5, 4096, 8, 40), (2, 5, 1, 8, 32),
                                    (2, 5, 256, 8, 160), (1, 3, 10, 8, 80)]:
