@@ -206,7 +206,7 @@ RCDM_API int rcdm_gemm_ln(int dtype, const void* a_dev, int lda, const void* w_d
                           const void* residual_dev, void* out_dev, int M, int N, int K, int flags, const void* stats_in_dev,
                           int parts_in, int frames, int rows_per_frame, float eps, void* stats_out_dev, void* stream);
 /* proj_out folded over ff.net.2: TemporalTransformer3DModel ends with y2 = y + ff2(g) + b2; x = x + po(y2) + bp
- * (motion_module.py:176-181,244-246) with nothing non-linear in between, so x = x + [y | g] [wp | wp w2]^T + (wp b2 + bp).
+ * (motion_module.py:170-180,243) with nothing non-linear in between, so x = x + [y | g] [wp | wp w2]^T + (wp b2 + bp).
  *   rcdm_fold_proj: wp [C, C], w2 [C, 4C] -> wf [C, 5C] (16 bit, fp32 accumulation), cf [C] fp32 (load time).
  *   rcdm_gemm_cat : out = [a0 | a1] w^T + bias (+ residual), a0 [M, K0], a1 [M, K1], w [N, K0 + K1] (K0, K1 multiples of
  *                   64); stats_out_dev != NULL: row statistics of the output as rcdm_gemm_ln writes them. */

@@ -893,7 +893,7 @@ int rcdm_gemm_ln(int dtype, const void* a_dev, int lda, const void* w_dev, const
 }
 
 // proj_out folded over ff.net.2 (fold_proj_kernel, unet.cu) and the two-segment GEMM that runs on the folded weights, for a
-// host that chains GEMMs itself (stage-1 prior: motion_module.py:176-181,244-246).
+// host that chains GEMMs itself (stage-1 prior: motion_module.py:170-180,243).
 int rcdm_fold_proj(int dtype, const void* wp_dev, const void* w2_dev, const float* b2_dev, const float* bp_dev,
                    void* wf_out_dev, float* cf_out_dev, int C, void* stream) {
   API_BEGIN

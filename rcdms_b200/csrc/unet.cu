@@ -375,7 +375,7 @@ static void fold_one(rcdm_unet_impl* h, const Mat& w, const LnFold& lf, const Ve
         f(g), f(b), pe ? f(*pe) : nullptr, bias ? f(*bias) : nullptr, f(lf.c), N, K, lf.frames);
 }
 // proj_out folded over the feed-forward's second Linear.  Transformer3DModel / TemporalTransformer3DModel end with
-//   y2 = y + ff2(g) + b2;  x = x + po(y2) + bp        (attention.py:362-365,523-526; motion_module.py:176-181,244-246)
+//   y2 = y + ff2(g) + b2;  x = x + po(y2) + bp        (attention.py:347-359,514; motion_module.py:170-180,243)
 // with nothing non-linear in between, so x = x + [y | g] [Wp | Wp W2]^T + (Wp b2 + bp): one GEMM over two K segments, the
 // intermediate y2 (one write + one read of the hidden state, one launch) never exists.
 //   wf [C, 5C]: columns 0..C-1 = Wp, columns C.. = Wp W2 (fp32 accumulation over the 16-bit weights, rounded once)

@@ -302,7 +302,7 @@ class MyPriorTransformer(nn.Module):
         l.w, l.c, l.b, l.frames = wf, c, None, frames
         return l
 
-    # motion_module.py:176-181,244-246: y2 = y + ff2(g); x = x + proj_out(y2) with nothing non-linear in between ->
+    # motion_module.py:170-180,243: y2 = y + ff2(g); x = x + proj_out(y2) with nothing non-linear in between ->
     # x = x + [y | g] [po | po ff2]^T + (po b2 + bp): one two-segment GEMM (rcdm_fold_proj at load time + rcdm_gemm_cat).
     # Active with fold_layernorm (the folded layer stack); False: ff.net.2 and proj_out stay two GEMMs.
     fold_proj_out = True

@@ -192,7 +192,7 @@ def test_layernorm_folded_gemm_chain(M, C, N, act, res, frames, S, dtype):
 @pytest.mark.parametrize("M,C,dtype", [(970, 2048, torch.float16), (970, 2048, torch.bfloat16), (170, 128, torch.float16),
                                        (2560, 1280, torch.float16), (640, 320, torch.bfloat16)])
 def test_proj_out_folded_over_ff2(M, C, dtype):
-    """rcdm_fold_proj + rcdm_gemm_cat against the two Linear layers they replace (motion_module.py:176-181,244-246):
+    """rcdm_fold_proj + rcdm_gemm_cat against the two Linear layers they replace (motion_module.py:170-180,243):
     x + po(y + ff2(g) + b2) + bp in torch fp32 on the same 16-bit weights / activations; the row statistics the fused
     launch emits describe its rounded output."""
     g_ = _gen(12)

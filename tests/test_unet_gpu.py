@@ -110,7 +110,7 @@ def test_fused_feed_forward_path_matches_oracle():
 def test_proj_out_fold_and_two_gemm_paths_agree(cfg_fn, shape, dtype):
     """Default: ``ff.net.2 (+ residual) -> proj_out (+ residual)`` of every transformer / motion module is ONE GEMM over
     two K segments on [po | po ff2] (handle option "po_fold" = 1).  With the option off the two reference GEMMs run
-    (attention.py:362-365,523-526; motion_module.py:176-181,244-246): both forms must pass the whole-UNet bound and agree
+    (attention.py:347-359,514; motion_module.py:170-180,243): both forms must pass the whole-UNet bound and agree
     with each other under it."""
     sd = _full_sd() if cfg_fn is full_config else None
     a = uc.run_case(cfg_fn(), shape, 501, dtype, sd=sd)
