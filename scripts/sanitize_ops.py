@@ -33,6 +33,31 @@ if ONLY == "ffn":  # (re-run of a single family: python scripts/sanitize_ops.py 
     run("ffn fused 200 rows bf16", lambda: pc.check_ffn_fused(200, torch.bfloat16))
     print("ALL OK" if all(ok for _, ok in res) else "SOME FAILED", len(res), "checks")
     sys.exit(0)
+if ONLY == "folds":  # the last session's kernels / launch forms: python scripts/sanitize_ops.py folds
+    import test_prior_gpu as tp  # noqa: E402  (assert-based checks, called directly)
+
+    def asserts(fn, *a):
+        fn(*a)
+        return True
+    run("LN-folded chain 170x128 -> 384, 5 frames + pe", lambda: asserts(tp.test_layernorm_folded_gemm_chain, 170, 128, 384, None, False, 5, 17, f16))
+    run("LN-folded chain 170x128 -> 512 gelu", lambda: asserts(tp.test_layernorm_folded_gemm_chain, 170, 128, 512, "gelu", False, 1, 17, f16))
+    run("LN-folded chain 170x128 -> 1024 geglu", lambda: asserts(tp.test_layernorm_folded_gemm_chain, 170, 128, 1024, "geglu", False, 1, 17, f16))
+    run("LN-folded chain 640x1280 -> 1280 + res (192-wide producer parts)", lambda: asserts(tp.test_layernorm_folded_gemm_chain, 640, 1280, 1280, None, True, 1, 64, f16))
+    run("proj_out over ff2 170x128", lambda: asserts(tp.test_proj_out_folded_over_ff2, 170, 128, f16))
+    run("proj_out over ff2 640x320 bf16", lambda: asserts(tp.test_proj_out_folded_over_ff2, 640, 320, torch.bfloat16))
+    for (b, hds, sq, skv, d) in [(2, 8, 256, 85, 40), (2, 8, 100, 112, 40), (2, 8, 64, 91, 80), (2, 8, 64, 64, 160), (3, 4, 33, 5, 64),
+                                 (2, 8, 16, 7, 16)]:
+        run(f"short-kv mma.sync attention b{b} h{hds} Sq{sq} Skv{skv} d{d}", lambda: pc.check_flash(b, hds, sq, skv, d, f16, short_kv=1))
+    import unet_checks as uc  # noqa: E402
+    from rcdms_b200.unet_spec import tiny_config  # noqa: E402
+    r = uc.run_case(tiny_config(), (2, 5, 8, 8, 7), 981, f16)
+    run("tiny unet forward (two-segment proj_out launches)", lambda: bool(
+        r["stats"]["finite"] and r["stats"]["max_abs"] <= max(3 * r["floor"]["max_abs"], 5e-3)))
+    from rcdms_b200.prior_spec import prior_tiny_config  # noqa: E402
+    pr = tp._forward_case(prior_tiny_config(), f16, 500)
+    run("tiny prior forward (folded LayerNorms, rcdm_gemm_cat)", lambda: bool(pr["max"] <= max(3 * pr["fmax"], 5e-3)))
+    print("ALL OK" if all(ok for _, ok in res) else "SOME FAILED", len(res), "checks")
+    sys.exit(0)
 for pair, sk in ((0, 0), (2, 1)):
     L.rcdm_set_gemm_pair(pair)
     L.rcdm_set_stream_k_min(sk)
