@@ -86,21 +86,30 @@ template <typename T> static void launch_dt(const AttnLaunch& l, cudaStream_t s)
     default: launch_one<T, 160>(l, s); break;
   }
 }
-template <typename T, int D> static void launch_short(const AttnLaunch& l, cudaStream_t s) {
+template <typename T, int D, int NT, bool EXACT> static void launch_short(const AttnLaunch& l, cudaStream_t s) {
   const AttnDesc& d = l.desc;
-  launch_k(cross_attn_mma_kernel<T, D>, l.grid, dim3(XATTN_THREADS), xattn_smem_bytes(D), s,
+  launch_k(cross_attn_mma_kernel<T, D, NT, EXACT>, l.grid, dim3(XATTN_THREADS), xattn_smem_bytes(D, NT), s,
            reinterpret_cast<const T*>(d.q), d.ldq, reinterpret_cast<const T*>(d.k), reinterpret_cast<const T*>(d.v), d.ldkv,
            reinterpret_cast<T*>(d.out), d.ldo, d.S_q, d.S_kv, d.heads, l.tiles_per_cta, l.p.scale_log2);
 }
+// the UNet's head dims with the exact key-tile counts of its key ranges (64 keys: 8x8 self-attention; 85 / 91 context tokens)
+template <typename T, int D> static void launch_short_unet(const AttnLaunch& l, cudaStream_t s) {
+  switch ((l.desc.S_kv + 7) / 8) {
+    case 8: launch_short<T, D, 8, true>(l, s); break;
+    case 11: launch_short<T, D, 11, true>(l, s); break;
+    case 12: launch_short<T, D, 12, true>(l, s); break;
+    default: launch_short<T, D, XATTN_NT, false>(l, s); break;
+  }
+}
 template <typename T> static void launch_short_dt(const AttnLaunch& l, cudaStream_t s) {
   switch (l.desc.d) {
-    case 8: launch_short<T, 8>(l, s); break;
-    case 16: launch_short<T, 16>(l, s); break;
-    case 32: launch_short<T, 32>(l, s); break;
-    case 40: launch_short<T, 40>(l, s); break;
-    case 64: launch_short<T, 64>(l, s); break;
-    case 80: launch_short<T, 80>(l, s); break;
-    default: launch_short<T, 160>(l, s); break;
+    case 8: launch_short<T, 8, XATTN_NT, false>(l, s); break;
+    case 16: launch_short<T, 16, XATTN_NT, false>(l, s); break;
+    case 32: launch_short<T, 32, XATTN_NT, false>(l, s); break;
+    case 40: launch_short_unet<T, 40>(l, s); break;
+    case 64: launch_short<T, 64, XATTN_NT, false>(l, s); break;
+    case 80: launch_short_unet<T, 80>(l, s); break;
+    default: launch_short_unet<T, 160>(l, s); break;
   }
 }
 void attn_launch(const AttnLaunch& l, cudaStream_t s) {
@@ -127,13 +136,20 @@ template <typename T> static cudaError_t set_attr_dt() {
   if (e == cudaSuccess) e = set_attr<T, 48>();
   if (e == cudaSuccess) e = set_attr<T, 80>();
   if (e == cudaSuccess) e = set_attr<T, 160>();
-  // cross_attn_mma_kernel: D = 80 / 160 stage more than 48 KB (K rows + V^T + the warps' Q / O tiles)
-  if (e == cudaSuccess)
-    e = cudaFuncSetAttribute(cross_attn_mma_kernel<T, 80>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)xattn_smem_bytes(80));
-  if (e == cudaSuccess)
-    e = cudaFuncSetAttribute(cross_attn_mma_kernel<T, 160>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)xattn_smem_bytes(160));
+  // cross_attn_mma_kernel: the instantiations that stage more than 48 KB (K rows + V^T + the warps' Q / O tiles)
+  auto big = [&](auto kernel, size_t bytes) {
+    if (e == cudaSuccess && bytes > 48 * 1024)
+      e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  };
+  big(cross_attn_mma_kernel<T, 64, XATTN_NT, false>, xattn_smem_bytes(64, XATTN_NT));
+  big(cross_attn_mma_kernel<T, 80, 8, true>, xattn_smem_bytes(80, 8));
+  big(cross_attn_mma_kernel<T, 80, 11, true>, xattn_smem_bytes(80, 11));
+  big(cross_attn_mma_kernel<T, 80, 12, true>, xattn_smem_bytes(80, 12));
+  big(cross_attn_mma_kernel<T, 80, XATTN_NT, false>, xattn_smem_bytes(80, XATTN_NT));
+  big(cross_attn_mma_kernel<T, 160, 8, true>, xattn_smem_bytes(160, 8));
+  big(cross_attn_mma_kernel<T, 160, 11, true>, xattn_smem_bytes(160, 11));
+  big(cross_attn_mma_kernel<T, 160, 12, true>, xattn_smem_bytes(160, 12));
+  big(cross_attn_mma_kernel<T, 160, XATTN_NT, false>, xattn_smem_bytes(160, XATTN_NT));
   return e;
 }
 bool attn_setup_attributes(std::string* err) {

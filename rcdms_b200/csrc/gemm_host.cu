@@ -84,7 +84,7 @@ bool encode_tmap_sw(CUtensorMap* out, const void* base, int rank, const uint64_t
 // ------------------------------------------------------------------------------------------
 // GEMM prepare / launch
 // ------------------------------------------------------------------------------------------
-static std::atomic<int> g_opts[OPT_COUNT] = {{0}, {24}, {1}, {1}, {1}, {1}, {1}, {40}, {1}, {1}, {1}, {0}, {0}};
+static std::atomic<int> g_opts[OPT_COUNT] = {{0}, {24}, {1}, {1}, {1}, {1}, {1}, {40}, {1}, {1}, {1}, {1}, {0}};
 static const char* const g_opt_names[OPT_COUNT] = {"pdl", "sk_min", "gemm_pair", "masked_attn_mma",
                                                     "temporal_wide", "temporal_wide_all", "temporal_tiled",
                                                     "temporal_smem_kb", "gn_fused", "ln_wide", "gn_stats", "attn_short_kv",

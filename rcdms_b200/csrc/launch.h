@@ -30,7 +30,8 @@ enum Opt : int {
   OPT_LN_WIDE,            // CTA-per-row LayerNorm for rows wider than 1280 (default 1)
   OPT_GN_STATS,           // GroupNorm statistics from the producing GEMM's epilogue + streaming apply (default 1)
   OPT_ATTN_SHORT_KV,      // attention over <= 112 keys (the UNet's cross-attention) on the register-resident mma.sync kernel
-                          // (default 0 = tcgen05 flash kernel for every key range: measured equal or faster, profiles/r02_ncu_cross_attn.txt)
+                          // (default 1: 217 vs 292 us at 80 x 4096 queries x 91 keys, profiles/r02_xattn_bench_v3.txt; 0 = tcgen05 flash
+                          // kernel for every key range)
   OPT_FFN_FUSED,          // fused GEGLU feed-forward kernel for the C = 320 transformer blocks (default 0: measured slower
                           // than the two GEMMs; set BEFORE rcdm_unet_create - it decides the weight packing)
   OPT_COUNT

@@ -306,59 +306,69 @@ masked_attn_mma_kernel(const T* __restrict__ qkv, int ld, const float* __restric
 // (TMEM allocation, barriers, 5-D TMA head gathers) on two key tiles: 45 us for 4096 x 85 keys against ~10 us of HBM time.
 //   q[(img * S_q + i) * ldq + h * D + c],  k / v[(img * S_kv + j) * ldkv + h * D + c],  out like q with ldo
 // grid (images * heads, query chunks); CTA = 4 warps; the chunk's 16-row tiles go round-robin over the warps.
-// OPT-IN (library option attn_short_kv = 1), parity-green, measured on B200 against the flash kernel on the same problems
-// (scripts/bench_xattn.py, profiles/r02_xattn_bench.txt): 80 images x 4096 queries x 91 keys d = 40: 315 vs 292 us; x 1024
-// d = 80: 132 vs 136 us; x 256 d = 160: 99 vs 88 us.  ncu (profiles/r02_ncu_cross_attn.txt): no pipe saturated (HMMA 35 %,
-// shared-memory wavefronts 43 %, XU 28 %), issue slots ~80 % used by 4 warps per scheduler - ~1 600 instructions per
-// 16-row tile, most of them the per-element softmax arithmetic over all 14 key tiles - so the default stays the flash kernel.
-// Global traffic is 16 bytes per lane both ways: a warp's Q tile and O tile pass through a private shared-memory tile
-// (pitch D + 8: fragment reads / writes conflict-free).  With 4-byte fragment loads / stores straight from / to global
-// memory the kernel was bound by L1 wavefronts (8-16 lines per instruction): 333 us for 80 x 4096 queries, flash 292.
+// DEFAULT for key ranges <= 112 (library option attn_short_kv = 1; 0 = flash kernel).  History (scripts/bench_xattn.py,
+// profiles/r02_xattn_bench*.txt; 80 images x 4096 queries x 91 keys, d = 40; flash kernel 292 us):
+//   v1  4-byte fragment loads / stores straight from / to global memory: 333 us (L1 wavefronts: 8-16 lines per instruction)
+//   v2  Q / O tiles through a per-warp shared-memory tile, 16 bytes per lane to global memory: 315 us; ncu
+//       (profiles/r02_ncu_cross_attn.txt): no pipe saturated, ~1 035 warp instructions per 16-row tile of which 72 are MMAs:
+//       144 B-fragment LDS.32, 112 FMUL (scale, normalise), 130 ISETP / FSEL (key mask on every element), 48 WARPSYNC and
+//       predicated-off MMAs from the run-time tile count, 14 key tiles processed for 12 live ones
+//   v3  (this) tile count NT a template parameter (8 / 11 / 12 exact, 14 generic), key mask on the last tile only, scale
+//       folded into the exponent FFMA, normalisation deferred to the 16 x D output, K / V^T columns permuted inside each
+//       16-block so that a lane's (b0, b1) fragment pair is ONE 8-byte load: 217 us (x 1024 d = 80: 113 vs 137 us flash;
+//       x 256 d = 160: 84 vs 88 us; one clip, 10 images x 4096: 40 vs 48 us).
 // q, out: 16-byte aligned rows (ldq, ldo multiples of 8).
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int XATTN_NT = 14;                        // 8-key tiles held in registers: S_kv <= 112
+constexpr int XATTN_NT = 14;                        // generic instantiation: S_kv <= 112
 constexpr int XATTN_SK = XATTN_NT * 8;
-constexpr int XATTN_VP = XATTN_SK + 8;              // V^T row pitch (elements)
+constexpr int XATTN_VP = 112;                       // V^T row pitch (elements): >= 16 ceil(NT / 2), = 48 mod 64 (see xattn_kp)
 constexpr int XATTN_THREADS = 128;
 __host__ __device__ constexpr int xattn_dp(int D) { return (D + 15) / 16 * 16; }
-__host__ __device__ constexpr int xattn_kp(int D) { return xattn_dp(D) + 8; }  // K row pitch (elements): conflict-free B fragments
-__host__ __device__ constexpr size_t xattn_smem_bytes(int D) {  // K rows + V^T + one 16-row Q / O staging tile per warp
-  return (size_t)XATTN_SK * xattn_kp(D) * 2 + (size_t)xattn_dp(D) * XATTN_VP * 2 +
-         (size_t)(XATTN_THREADS / 32) * 16 * xattn_kp(D) * 2;
+// K row pitch (elements): the 8-byte B-fragment loads of a half-warp (rows g = 0..3 or 4..7, 8 t bytes into the row) are
+// conflict-free when the pitch is 16 or 48 mod 64 elements
+__host__ __device__ constexpr int xattn_kp(int D) { return (xattn_dp(D) % 64 == 16 || xattn_dp(D) % 64 == 48) ? xattn_dp(D) : xattn_dp(D) + 16; }
+__host__ __device__ constexpr int xattn_qp(int D) { return xattn_dp(D) + 8; }  // Q / O staging pitch: 4-byte fragment accesses
+__host__ __device__ constexpr size_t xattn_smem_bytes(int D, int NT) {  // K rows + V^T + one 16-row Q / O staging tile per warp
+  return (size_t)NT * 8 * xattn_kp(D) * 2 + (size_t)xattn_dp(D) * XATTN_VP * 2 +
+         (size_t)(XATTN_THREADS / 32) * 16 * xattn_qp(D) * 2;
 }
+// position of column c (0..15) inside its 16-block: (2t, 2t+1, 2t+8, 2t+9) -> 4t .. 4t+3
+__host__ __device__ constexpr int xattn_perm16(int c) { return 4 * ((c & 7) >> 1) + 2 * (c >> 3) + (c & 1); }
 
-template <typename T, int D>
+// EXACT: 8 (NT - 1) < S_kv <= 8 NT (only the last key tile can hold dead keys); else any S_kv <= 8 NT.
+template <typename T, int D, int NT, bool EXACT>
 __global__ void __launch_bounds__(XATTN_THREADS)
 cross_attn_mma_kernel(const T* __restrict__ q, int ldq, const T* __restrict__ k, const T* __restrict__ v, int ldkv,
                       T* __restrict__ out, int ldo, int S_q, int S_kv, int heads, int tiles_per_cta, float scale_log2) {
   using T2 = typename DT<T>::T2;
-  constexpr int DP = xattn_dp(D), KP = xattn_kp(D), NT = XATTN_NT, SK = XATTN_SK, VP = XATTN_VP;
+  constexpr int DP = xattn_dp(D), KP = xattn_kp(D), QP = xattn_qp(D), VP = XATTN_VP;
+  constexpr int NKJ = (NT + 1) / 2, NKP = NKJ * 16;  // 16-key steps of P V, keys they read
   constexpr int NCH = D / 8;                        // 8-wide output column tiles
   constexpr int NCHUNK = NCH > 10 ? 10 : NCH;       // P V in chunks of <= 80 output dims (register budget at D = 160)
+  static_assert(NKP <= VP, "V^T pitch");
   extern __shared__ __align__(16) uint8_t sm_raw[];
-  T* Ks = reinterpret_cast<T*>(sm_raw);   // [SK][KP]  rows >= S_kv and columns >= D zero
-  T* Vt = Ks + SK * KP;                   // [DP][VP]  columns >= S_kv zero
+  T* Ks = reinterpret_cast<T*>(sm_raw);   // [NT * 8][KP]  16-blocks permuted (xattn_perm16); rows >= S_kv, channels >= D zero
+  T* Vt = Ks + NT * 8 * KP;               // [DP][VP]      key 16-blocks permuted; keys >= S_kv zero
   const int b = blockIdx.x / heads, h = blockIdx.x % heads;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
   const T* kb = k + (size_t)b * S_kv * ldkv + h * D;
   const T* vb = v + (size_t)b * S_kv * ldkv + h * D;
   pdl_sync();
   // ---- stage K rows and V^T of this (image, head).  Only what the fragments read beyond the data is zeroed (padding
-  // must be finite zeros): key rows S_kv .. 8 nt_used - 1, channel columns D .. DP - 1, V^T key columns up to the last
-  // 16-key step; these regions are disjoint from the data, so one barrier serves both.
-  const int nt_used = min(NT, (S_kv + 7) / 8);
-  const int sk_read = ((nt_used + 1) / 2) * 16;  // keys the P V k-steps read (<= SK)
-  for (int i = tid; i < (nt_used * 8 - S_kv) * (DP / 8); i += blockDim.x)
+  // must be finite zeros); those regions are disjoint from the data, so one barrier serves both.
+  for (int i = tid; i < (NT * 8 - S_kv) * (DP / 8); i += blockDim.x)
     *reinterpret_cast<uint4*>(Ks + (S_kv + i / (DP / 8)) * KP + (i % (DP / 8)) * 8) = make_uint4(0, 0, 0, 0);
-  if constexpr (DP > D) {
-    for (int j = tid; j < S_kv; j += blockDim.x) *reinterpret_cast<uint4*>(Ks + j * KP + D) = make_uint4(0, 0, 0, 0);
+  if constexpr (DP > D) {  // channels D .. DP - 1 = the upper half of the last 16-block: positions 4 tt + 2, + 3
+    for (int i = tid; i < S_kv * 4; i += blockDim.x)
+      *reinterpret_cast<uint32_t*>(Ks + (i >> 2) * KP + (DP - 16) + 4 * (i & 3) + 2) = 0u;
   }
-  for (int i = tid; i < D * (sk_read - S_kv); i += blockDim.x)
-    Vt[(i / (sk_read - S_kv)) * VP + S_kv + i % (sk_read - S_kv)] = DT<T>::from_f(0.f);
+  for (int i = tid; i < D * (NKP - S_kv); i += blockDim.x) {
+    const int j = S_kv + i % (NKP - S_kv);
+    Vt[(i / (NKP - S_kv)) * VP + (j & ~15) + xattn_perm16(j & 15)] = DT<T>::from_f(0.f);
+  }
   const bool vec16 = (ldkv % 8 == 0) && ((reinterpret_cast<uintptr_t>(kb) & 15) == 0) &&
                      ((reinterpret_cast<uintptr_t>(vb) & 15) == 0);
-  // consecutive threads take consecutive keys of one 8-channel chunk: the transposed V^T stores of a warp then fall
-  // into consecutive half-words (with the chunk index fastest they would all hit one bank: pitch 240 B x 8 rows)
+  // consecutive threads take consecutive keys of one 8-channel chunk (V^T stores of a warp spread over the banks)
   for (int i = tid; i < S_kv * NCH; i += blockDim.x) {
     const int j = i % S_kv, c = (i / S_kv) * 8;
     uint4 kv, vv;
@@ -376,15 +386,20 @@ cross_attn_mma_kernel(const T* __restrict__ q, int ldq, const T* __restrict__ k,
         v4[e] = *reinterpret_cast<const uint32_t*>(vp + 2 * e);
       }
     }
-    *reinterpret_cast<uint4*>(Ks + j * KP + c) = kv;  // KP * 2 bytes is a multiple of 16
-    const T* ve = reinterpret_cast<const T*>(&vv);
+    // channels c .. c+7 = half hh of their 16-block: pair tt -> positions 4 tt + 2 hh, + 1
+    T* krow = Ks + j * KP + (c & ~15) + 2 * ((c >> 3) & 1);
+    const uint32_t* k4 = reinterpret_cast<const uint32_t*>(&kv);
 #pragma unroll
-    for (int e = 0; e < 8; ++e) Vt[(c + e) * VP + j] = ve[e];
+    for (int tt = 0; tt < 4; ++tt) *reinterpret_cast<uint32_t*>(krow + 4 * tt) = k4[tt];
+    const T* ve = reinterpret_cast<const T*>(&vv);
+    const int jp = (j & ~15) + xattn_perm16(j & 15);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) Vt[(c + e) * VP + jp] = ve[e];
   }
-  // ---- per-warp Q / O staging tile [16][KP]; its padding columns D .. DP - 1 stay zero
-  T* Qs = Vt + DP * VP + warp * 16 * KP;
+  // ---- per-warp Q / O staging tile [16][QP]; its padding columns D .. DP - 1 stay zero
+  T* Qs = Vt + DP * VP + warp * 16 * QP;
   if constexpr (DP > D) {
-    if (lane < 16) *reinterpret_cast<uint4*>(Qs + lane * KP + D) = make_uint4(0, 0, 0, 0);
+    if (lane < 16) *reinterpret_cast<uint4*>(Qs + lane * QP + D) = make_uint4(0, 0, 0, 0);
   }
   constexpr int KS = DP / 16;
   constexpr int QV = (16 * NCH + 31) / 32;  // 16-byte vectors per lane of a 16 x D tile
@@ -403,27 +418,28 @@ cross_attn_mma_kernel(const T* __restrict__ q, int ldq, const T* __restrict__ k,
   if (tile0 + warp < tile1) load_q(tile0 + warp);  // in flight across the staging barrier
   __syncthreads();
   // no CTA barrier below this point
+  const int nt_full = S_kv >> 3;  // key tiles without dead keys
   for (int tile = tile0 + warp; tile < tile1; tile += XATTN_THREADS / 32) {
     // ---- Q tile -> staging tile -> A fragments: a0 (g, c) a1 (g+8, c) a2 (g, c+8) a3 (g+8, c+8), c = 16 ks + 2t
 #pragma unroll
     for (int i = 0; i < QV; ++i) {
       const int idx = lane + i * 32, r = idx / NCH, ch = idx % NCH;
-      if (idx < 16 * NCH) *reinterpret_cast<uint4*>(Qs + r * KP + ch * 8) = qv[i];
+      if (idx < 16 * NCH) *reinterpret_cast<uint4*>(Qs + r * QP + ch * 8) = qv[i];
     }
     __syncwarp();
     uint32_t qf[KS][4];
 #pragma unroll
     for (int ks = 0; ks < KS; ++ks) {
       const int c = ks * 16 + 2 * t;
-      qf[ks][0] = *reinterpret_cast<const uint32_t*>(Qs + g * KP + c);
-      qf[ks][1] = *reinterpret_cast<const uint32_t*>(Qs + (g + 8) * KP + c);
-      qf[ks][2] = *reinterpret_cast<const uint32_t*>(Qs + g * KP + c + 8);
-      qf[ks][3] = *reinterpret_cast<const uint32_t*>(Qs + (g + 8) * KP + c + 8);
+      qf[ks][0] = *reinterpret_cast<const uint32_t*>(Qs + g * QP + c);
+      qf[ks][1] = *reinterpret_cast<const uint32_t*>(Qs + (g + 8) * QP + c);
+      qf[ks][2] = *reinterpret_cast<const uint32_t*>(Qs + g * QP + c + 8);
+      qf[ks][3] = *reinterpret_cast<const uint32_t*>(Qs + (g + 8) * QP + c + 8);
     }
     __syncwarp();  // the staging tile is free again (it takes this tile's output below)
     // the next tile's Q vectors travel while this tile is computed
     if (tile + XATTN_THREADS / 32 < tile1) load_q(tile + XATTN_THREADS / 32);
-    // ---- S = Q K^T: accumulator tile nt holds (row g | g+8, keys nt*8 + 2t, +1)
+    // ---- S = Q K^T: accumulator tile nt holds (row g | g+8, keys nt*8 + 2t, +1); B fragment (b0, b1) = one 8-byte load
     float sc[NT][4];
 #pragma unroll
     for (int nt = 0; nt < NT; ++nt) sc[nt][0] = sc[nt][1] = sc[nt][2] = sc[nt][3] = 0.f;
@@ -431,38 +447,39 @@ cross_attn_mma_kernel(const T* __restrict__ q, int ldq, const T* __restrict__ k,
     for (int ks = 0; ks < KS; ++ks) {
 #pragma unroll
       for (int nt = 0; nt < NT; ++nt) {
-        if (nt < nt_used) {
-          const T* kr = Ks + (nt * 8 + g) * KP + ks * 16 + 2 * t;  // B fragment: b0 (k = 2t, 2t+1; n = g), b1 (k + 8)
-          MmaOp<T>::mma(sc[nt], qf[ks], *reinterpret_cast<const uint32_t*>(kr), *reinterpret_cast<const uint32_t*>(kr + 8));
-        }
+        const uint2 bf = *reinterpret_cast<const uint2*>(Ks + (nt * 8 + g) * KP + ks * 16 + 4 * t);
+        MmaOp<T>::mma(sc[nt], qf[ks], bf.x, bf.y);
       }
     }
-    // ---- softmax over the full key range (quad reduction: lanes 4g .. 4g+3 share rows g, g+8)
+    // ---- softmax over the whole key range, on the raw scores: p = 2^(s scale - max scale), normalised after P V
+    // (quad reduction: lanes 4g .. 4g+3 share rows g, g+8).  Dead keys (>= S_kv) sit in the last tile only (EXACT) or from
+    // tile S_kv / 8 on (generic): their scores become -inf, their probabilities exactly 0.
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+      if (EXACT ? (nt == NT - 1) : (nt >= nt_full)) {
+#pragma unroll
+        for (int e = 0; e < 2; ++e)
+          if (nt * 8 + 2 * t + e >= S_kv) sc[nt][e] = sc[nt][2 + e] = -INFINITY;
+      }
+    }
     float mxa = -INFINITY, mxb = -INFINITY;
 #pragma unroll
     for (int nt = 0; nt < NT; ++nt) {
-#pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        const bool live = nt * 8 + 2 * t + e < S_kv;
-        const float va = live ? sc[nt][e] * scale_log2 : -INFINITY;
-        const float vb2 = live ? sc[nt][2 + e] * scale_log2 : -INFINITY;
-        sc[nt][e] = va;
-        sc[nt][2 + e] = vb2;
-        mxa = fmaxf(mxa, va);
-        mxb = fmaxf(mxb, vb2);
-      }
+      mxa = fmaxf(mxa, fmaxf(sc[nt][0], sc[nt][1]));
+      mxb = fmaxf(mxb, fmaxf(sc[nt][2], sc[nt][3]));
     }
     mxa = fmaxf(mxa, __shfl_xor_sync(0xffffffffu, mxa, 1));
     mxa = fmaxf(mxa, __shfl_xor_sync(0xffffffffu, mxa, 2));
     mxb = fmaxf(mxb, __shfl_xor_sync(0xffffffffu, mxb, 1));
     mxb = fmaxf(mxb, __shfl_xor_sync(0xffffffffu, mxb, 2));
+    const float nma = -mxa * scale_log2, nmb = -mxb * scale_log2;
     float la = 0.f, lb = 0.f;
 #pragma unroll
     for (int nt = 0; nt < NT; ++nt) {
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
-        sc[nt][e] = exp2f(sc[nt][e] - mxa);  // exp2(-inf) = 0 for the padding keys
-        sc[nt][2 + e] = exp2f(sc[nt][2 + e] - mxb);
+        sc[nt][e] = exp2f(fmaf(sc[nt][e], scale_log2, nma));  // exp2(-inf) = 0 for the dead keys
+        sc[nt][2 + e] = exp2f(fmaf(sc[nt][2 + e], scale_log2, nmb));
         la += sc[nt][e];
         lb += sc[nt][2 + e];
       }
@@ -472,35 +489,38 @@ cross_attn_mma_kernel(const T* __restrict__ q, int ldq, const T* __restrict__ k,
     lb += __shfl_xor_sync(0xffffffffu, lb, 1);
     lb += __shfl_xor_sync(0xffffffffu, lb, 2);
     const float ia = 1.0f / la, ib = 1.0f / lb;
-    // normalised, 16-bit-rounded probabilities (the reference's softmax output dtype) = A fragments of P V:
-    // key tiles (2 kj, 2 kj + 1) form k-step kj
-    uint32_t pa[NT / 2][4];
+    // 16-bit-rounded probabilities (values in [0, 1]: the same relative rounding as the reference's normalised 16-bit
+    // softmax output) = A fragments of P V: key tiles (2 kj, 2 kj + 1) form k-step kj; a missing odd tile is zero
+    uint32_t pa[NKJ][4];
 #pragma unroll
-    for (int kj = 0; kj < NT / 2; ++kj) {
-      T2 p0 = DT<T>::from_f2(sc[2 * kj][0] * ia, sc[2 * kj][1] * ia);
-      T2 p1 = DT<T>::from_f2(sc[2 * kj][2] * ib, sc[2 * kj][3] * ib);
-      T2 p2 = DT<T>::from_f2(sc[2 * kj + 1][0] * ia, sc[2 * kj + 1][1] * ia);
-      T2 p3 = DT<T>::from_f2(sc[2 * kj + 1][2] * ib, sc[2 * kj + 1][3] * ib);
+    for (int kj = 0; kj < NKJ; ++kj) {
+      T2 p0 = DT<T>::from_f2(sc[2 * kj][0], sc[2 * kj][1]);
+      T2 p1 = DT<T>::from_f2(sc[2 * kj][2], sc[2 * kj][3]);
       pa[kj][0] = *reinterpret_cast<uint32_t*>(&p0);
       pa[kj][1] = *reinterpret_cast<uint32_t*>(&p1);
-      pa[kj][2] = *reinterpret_cast<uint32_t*>(&p2);
-      pa[kj][3] = *reinterpret_cast<uint32_t*>(&p3);
+      if (2 * kj + 1 < NT) {  // (compile-time after unrolling; the index is wrapped only to stay in bounds)
+        T2 p2 = DT<T>::from_f2(sc[(2 * kj + 1) % NT][0], sc[(2 * kj + 1) % NT][1]);
+        T2 p3 = DT<T>::from_f2(sc[(2 * kj + 1) % NT][2], sc[(2 * kj + 1) % NT][3]);
+        pa[kj][2] = *reinterpret_cast<uint32_t*>(&p2);
+        pa[kj][3] = *reinterpret_cast<uint32_t*>(&p3);
+      } else {
+        pa[kj][2] = pa[kj][3] = 0u;
+      }
     }
-    // ---- O = P V in chunks of NCHUNK column tiles, written into the staging tile
+    // ---- O = (P V) / l in chunks of NCHUNK column tiles, written into the staging tile
 #pragma unroll
     for (int n0 = 0; n0 < NCH; n0 += NCHUNK) {
       float oc[NCHUNK][4];
 #pragma unroll
       for (int n = 0; n < NCHUNK; ++n) oc[n][0] = oc[n][1] = oc[n][2] = oc[n][3] = 0.f;
 #pragma unroll
-      for (int kj = 0; kj < NT / 2; ++kj) {
-        if (2 * kj < nt_used) {  // warp-uniform: the remaining probabilities are exactly zero
+      for (int kj = 0; kj < NKJ; ++kj) {
 #pragma unroll
-          for (int n = 0; n < NCHUNK; ++n) {
-            if (n0 + n < NCH) {
-              const T* vr = Vt + ((n0 + n) * 8 + g) * VP + kj * 16 + 2 * t;  // b0 (keys kj*16 + 2t, +1; dim), b1 (keys + 8)
-              MmaOp<T>::mma(oc[n], pa[kj], *reinterpret_cast<const uint32_t*>(vr), *reinterpret_cast<const uint32_t*>(vr + 8));
-            }
+        for (int n = 0; n < NCHUNK; ++n) {
+          if (n0 + n < NCH) {
+            // b0 (keys kj*16 + 2t, +1; dim (n0 + n)*8 + g), b1 (keys + 8): adjacent in the permuted 16-block
+            const uint2 bf = *reinterpret_cast<const uint2*>(Vt + ((n0 + n) * 8 + g) * VP + kj * 16 + 4 * t);
+            MmaOp<T>::mma(oc[n], pa[kj], bf.x, bf.y);
           }
         }
       }
@@ -508,8 +528,8 @@ cross_attn_mma_kernel(const T* __restrict__ q, int ldq, const T* __restrict__ k,
       for (int n = 0; n < NCHUNK; ++n) {
         if (n0 + n < NCH) {
           const int c = (n0 + n) * 8 + 2 * t;
-          *reinterpret_cast<T2*>(Qs + g * KP + c) = DT<T>::from_f2(oc[n][0], oc[n][1]);
-          *reinterpret_cast<T2*>(Qs + (g + 8) * KP + c) = DT<T>::from_f2(oc[n][2], oc[n][3]);
+          *reinterpret_cast<T2*>(Qs + g * QP + c) = DT<T>::from_f2(oc[n][0] * ia, oc[n][1] * ia);
+          *reinterpret_cast<T2*>(Qs + (g + 8) * QP + c) = DT<T>::from_f2(oc[n][2] * ib, oc[n][3] * ib);
         }
       }
     }
@@ -520,7 +540,7 @@ cross_attn_mma_kernel(const T* __restrict__ q, int ldq, const T* __restrict__ k,
       const int idx = lane + i * 32, r = idx / NCH, ch = idx % NCH;
       if (idx < 16 * NCH && tile * 16 + r < S_q)
         *reinterpret_cast<uint4*>(out + ((size_t)b * S_q + tile * 16 + r) * ldo + h * D + ch * 8) =
-            *reinterpret_cast<const uint4*>(Qs + r * KP + ch * 8);
+            *reinterpret_cast<const uint4*>(Qs + r * QP + ch * 8);
     }
     __syncwarp();  // before the next tile's Q vectors overwrite the staging tile
   }

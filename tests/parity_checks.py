@@ -238,8 +238,8 @@ def check_rowstats(M, N, K, dtype, residual=True, seed=9):
 
 
 def check_flash(batch, heads, sq, skv, d, dtype, simple=False, seed=5, qscale=1.0, short_kv=None):
-    """short_kv = 0 | 1: library option "attn_short_kv" for this call (1: key ranges <= 112 on the opt-in register-resident
-    mma.sync kernel; 0 = default: the tcgen05 flash kernel like every longer range)."""
+    """short_kv = 0 | 1: library option "attn_short_kv" for this call (1 = default: key ranges <= 112 on the register-resident
+    mma.sync kernel; 0: the tcgen05 flash kernel like every longer range)."""
     g = _gen(seed)
     q = _rand((batch, sq, heads * d), dtype, g, qscale)
     k = _rand((batch, skv, heads * d), dtype, g)
@@ -407,7 +407,7 @@ def all_op_checks(dtypes=(torch.float16, torch.bfloat16), quick=False):
                                      (2, 8, 256, 150, 40), (1, 4, 128, 320, 80), (2, 8, 130, 450, 160), (2, 2, 200, 129, 24)]:
             yield lambda a=(b, hds, sq, skv, d), dt=dt: check_flash(*a, dt)
         # short key ranges (cross-attention to 85 / 91 context tokens at the UNet's four levels, the 8x8 level's self-attention,
-        # the 112-key limit, ragged query tiles): the opt-in register-resident mma.sync kernel AND the flash kernel on the same problems
+        # the 112-key limit, ragged query tiles): the register-resident mma.sync kernel (default) AND the flash kernel on the same problems
         for (b, hds, sq, skv, d) in [(10, 8, 4096, 85, 40), (10, 8, 1024, 85, 80), (10, 8, 256, 85, 160), (10, 8, 64, 85, 160),
                                      (16, 8, 1024, 91, 80), (10, 8, 64, 64, 160), (2, 8, 100, 112, 40), (3, 4, 33, 5, 64),
                                      (2, 8, 256, 113, 40)]:
