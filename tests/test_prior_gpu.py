@@ -512,3 +512,35 @@ def test_prior_batched_clips_match_separate_runs():
     for i, a in enumerate(alone):
         d = (both[5 * i: 5 * i + 5].float() - a.float()).abs().max().item()
         assert d <= 2e-2 * max(1.0, a.float().abs().max().item()), (i, d)
+
+
+def test_prior_full_width_batched_clips_folded_vs_unfolded():
+    """Full width (inner 2048), 4 clips in one run (M = 3 880 rows: the 2 048-wide GEMMs now span 31 row tiles, so the
+    statistics-emitting and two-segment launches take the CTA-pair / multi-wave schedules that one clip never reaches):
+    the folded layer stack (default) against every LayerNorm as its own launch and two-GEMM proj_out, and against each
+    clip run alone."""
+    from rcdms_b200.synthetic import stack_prior_clips
+    cfg = prior_full_config(num_layers=2)
+    m, _ = _build(cfg, torch.float16)
+    pipe = Seq_Inpaint_Prior_Pipeline(prior=m, image_encoder=None, text_encoder=None, tokenizer=None,
+                                      scheduler=UnCLIPScheduler(**PRIOR_SCHEDULER_KWARGS))
+    steps = 3
+    clips = [{k: (v.cuda().half() if v.is_floating_point() else v.cuda())
+              for k, v in synthetic_prior_inputs(cfg, i, steps=steps).items()} for i in range(4)]
+
+    def run(inp):
+        return pipe.sample(inp["latents"], inp["prompt_embeds"], inp["text_hidden"], inp["text_mask"],
+                           inp["imgs_proj_embeds1"], inp["mask_label"], steps, 4.0, noise=inp["noise"])
+
+    stacked = stack_prior_clips(clips)
+    folded = run(stacked)
+    assert torch.isfinite(folded).all()
+    alone0 = run(clips[0])
+    MyPriorTransformer.fold_layernorm = False
+    try:
+        unfolded = run(stacked)
+    finally:
+        MyPriorTransformer.fold_layernorm = True
+    scale = max(1.0, unfolded.float().abs().max().item())
+    assert (folded.float() - unfolded.float()).abs().max().item() <= 2e-2 * scale
+    assert (folded[:5].float() - alone0.float()).abs().max().item() <= 2e-2 * scale
