@@ -5,7 +5,7 @@ mkdir -p gpurun_out
 timeout 900 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --csv \
   --log-file gpurun_out/r2z_launches_dram.csv python scripts/one_forward.py 2 > gpurun_out/r2z_ncu_launches.log 2>&1
 echo "ncu launches rc=$?"
-python scripts/traffic_summary.py gpurun_out/r2z_launches_dram.csv 0 gpurun_out/r2z_gemm_traffic.json > gpurun_out/r2z_launches_dram.txt 2>&1
+python scripts/traffic_summary.py gpurun_out/r2z_launches_dram.csv 0 gpurun_out/r2z_gemm_traffic.json > gpurun_out/r2z_launches_dram.txt 2>&1  # (whole process; the forward-only summary in profiles/ was cut from the csv afterwards: skip = first launch of the second forward)
 cp gpurun_out/r2z_gemm_traffic.json profiles/r02_gemm_traffic.json; tail -22 gpurun_out/r2z_launches_dram.txt | cut -c1-170
 timeout 900 python -m pytest tests -m gpu -q --timeout=300 > gpurun_out/r2z_pytest_gpu.log 2>&1
 echo "pytest rc=$?"; tail -3 gpurun_out/r2z_pytest_gpu.log | cut -c1-200
