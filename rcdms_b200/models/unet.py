@@ -238,7 +238,7 @@ class UNet3DConditionModel(nn.Module):
 
     def set_debug_option(self, name: str, value: int) -> None:
         """Explicit debug switch of the native handle ("simple": CUDA-core reference kernels for bisecting a parity
-        failure; "ln_fold"; "autotune").  Never set on a product path; the library reads no environment variables."""
+        failure; "ln_fold"; "po_fold"; "autotune").  Never set on a product path; the library reads no environment variables."""
         self._debug_options[name] = int(value)
         if self._handle is not None:
             _lib.check(_lib.lib().rcdm_unet_set_option(self._handle, name.encode(), int(value)))
