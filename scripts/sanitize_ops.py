@@ -33,6 +33,12 @@ if ONLY == "ffn":  # (re-run of a single family: python scripts/sanitize_ops.py 
     run("ffn fused 200 rows bf16", lambda: pc.check_ffn_fused(200, torch.bfloat16))
     print("ALL OK" if all(ok for _, ok in res) else "SOME FAILED", len(res), "checks")
     sys.exit(0)
+if ONLY == "xattn":  # the short-key-range attention kernel alone: python scripts/sanitize_ops.py xattn
+    for (b, hds, sq, skv, d) in [(2, 8, 256, 85, 40), (2, 8, 64, 91, 80), (2, 8, 64, 64, 160), (2, 8, 100, 112, 40),
+                                 (3, 4, 33, 5, 64), (2, 8, 16, 7, 16)]:
+        run(f"short-kv mma.sync attention b{b} h{hds} Sq{sq} Skv{skv} d{d}", lambda: pc.check_flash(b, hds, sq, skv, d, f16, short_kv=1))
+    print("ALL OK" if all(ok for _, ok in res) else "SOME FAILED", len(res), "checks")
+    sys.exit(0)
 if ONLY == "folds":  # the last session's kernels / launch forms: python scripts/sanitize_ops.py folds
     import test_prior_gpu as tp  # noqa: E402  (assert-based checks, called directly)
 
